@@ -1,0 +1,149 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes bindings for the two CPU checkers.
+
+* ``port``      -> oracle/liboracle.so, our plain-C restatement (oracle.c)
+* ``reference`` -> oracle/_ref/libloosref.so, the reference's own arithmetic
+  (src/alignment.cpp:12-281 compiled where it lies, OpenBLAS dgemm_/dgesvj_)
+
+Both expose the same functions under the prefixes ``oracle_`` / ``ref_``; the
+``Checker`` class hides the prefix.  Layouts follow the reference: coordinates are
+F rows of 3N doubles, xyz interleaved (src/ensembles.cpp:275-279); RMSD matrices
+are float32 column-major (src/MatrixOrder.hpp:101-103) -- returned here as numpy
+arrays indexed [i, j] (Fortran order), so ``M[i, j] == M(i, j)`` of the reference.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
+
+
+def build(quiet=True):
+    """(Re)build liboracle.so and, when /root/reference is present, _ref/."""
+    subprocess.run(["make", "-C", _HERE, "all"], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+class Checker:
+    def __init__(self, kind="port"):
+        self.kind = kind
+        if kind == "port":
+            path, self.pfx = os.path.join(_HERE, "liboracle.so"), "oracle_"
+        elif kind == "reference":
+            path, self.pfx = os.path.join(_HERE, "_ref", "libloosref.so"), "ref_"
+        else:
+            raise ValueError(kind)
+        if not os.path.exists(path):
+            if kind == "port":
+                build()
+            else:
+                raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        if kind == "reference":
+            self.lib.ref_set_blas_threads(1)  # Tools/rmsds.cpp:88-92 advice
+        f = self._f
+        f("centered_rmsd").restype = C.c_double
+        f("centered_rmsd").argtypes = [_dp, _dp, C.c_int]
+        f("center_at_origin").argtypes = [_dp, C.c_int, _dp]
+        f("kabsch").argtypes = [_dp, _dp, C.c_int, _dp]
+        f("kabsch_core_S").argtypes = [_dp, _dp, C.c_int, _dp]
+        f("rmsds_self").argtypes = [_dp, C.c_int, C.c_int, _fp, C.c_int]
+        f("rmsds_cross").argtypes = [_dp, C.c_int, _dp, C.c_int, C.c_int, _fp, C.c_int]
+        f("rmsd2ref_target").argtypes = [_dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp]
+        f("rmsd2ref_iterative").restype = C.c_int
+        f("rmsd2ref_iterative").argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double,
+                                            C.c_int, _dp, _dp, _dp, _dp]
+
+    def _f(self, name):
+        return getattr(self.lib, self.pfx + name)
+
+    # -- per-pair functions (src/alignment.cpp) --
+    def center_at_origin(self, v):
+        v = np.array(v, dtype=np.float64).ravel().copy()
+        c = np.zeros(3)
+        self._f("center_at_origin")(v.ctypes.data_as(_dp), v.size, c.ctypes.data_as(_dp))
+        return v, c
+
+    def centered_rmsd(self, u, v):
+        u, pu = _d(np.ravel(u)); v, pv = _d(np.ravel(v))
+        return self._f("centered_rmsd")(pu, pv, u.size)
+
+    def kabsch(self, u, v):
+        u, pu = _d(np.ravel(u)); v, pv = _d(np.ravel(v))
+        M = np.zeros(16)
+        self._f("kabsch")(pu, pv, u.size, M.ctypes.data_as(_dp))
+        return M.reshape(4, 4)
+
+    def kabsch_core_S(self, u, v):
+        u, pu = _d(np.ravel(u)); v, pv = _d(np.ravel(v))
+        S = np.zeros(3)
+        self._f("kabsch_core_S")(pu, pv, u.size, S.ctypes.data_as(_dp))
+        return S
+
+    # -- tool-level drivers --
+    def rmsds_self(self, T, nthreads=1):
+        """T: (F, N, 3) or (F, 3N) raw (uncentred) coords -> (F, F) float32."""
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(len(T), -1)
+        F, n3 = T.shape
+        M = np.zeros((F, F), dtype=np.float32, order="F")
+        self._f("rmsds_self")(T.ctypes.data_as(_dp), F, n3, M.ctypes.data_as(_fp), nthreads)
+        return M
+
+    def rmsds_cross(self, T1, T2, nthreads=1):
+        T1 = np.ascontiguousarray(T1, dtype=np.float64).reshape(len(T1), -1)
+        T2 = np.ascontiguousarray(T2, dtype=np.float64).reshape(len(T2), -1)
+        assert T1.shape[1] == T2.shape[1]
+        M = np.zeros((len(T1), len(T2)), dtype=np.float32, order="F")
+        self._f("rmsds_cross")(T1.ctypes.data_as(_dp), len(T1), T2.ctypes.data_as(_dp), len(T2),
+                               T1.shape[1], M.ctypes.data_as(_fp), nthreads)
+        return M
+
+    def rmsd2ref_target(self, fa, fr, ta, tr):
+        """fa: (F, Na, 3) align coords per frame, fr: (F, Nr, 3) rmsd coords per
+        frame, ta/tr the target's selections.  Returns (rmsd[F], xforms[F,4,4])."""
+        fa = np.ascontiguousarray(fa, dtype=np.float64).reshape(len(fa), -1)
+        fr = np.ascontiguousarray(fr, dtype=np.float64).reshape(len(fr), -1)
+        ta, pta = _d(np.ravel(ta)); tr, ptr = _d(np.ravel(tr))
+        F = len(fa)
+        out = np.zeros(F); xf = np.zeros((F, 16))
+        self._f("rmsd2ref_target")(fa.ctypes.data_as(_dp), fr.ctypes.data_as(_dp), pta, ptr, F,
+                                   fa.shape[1], fr.shape[1], out.ctypes.data_as(_dp),
+                                   xf.ctypes.data_as(_dp))
+        return out, xf.reshape(F, 4, 4)
+
+    def rmsd2ref_iterative(self, fa, fr, tol=1e-6, maxiter=1000):
+        fa = np.ascontiguousarray(fa, dtype=np.float64).reshape(len(fa), -1)
+        fr = np.ascontiguousarray(fr, dtype=np.float64).reshape(len(fr), -1)
+        F = len(fa)
+        out = np.zeros(F); xf = np.zeros((F, 16)); avg = np.zeros(fr.shape[1]); rms = C.c_double()
+        it = self._f("rmsd2ref_iterative")(fa.ctypes.data_as(_dp), fr.ctypes.data_as(_dp), F,
+                                           fa.shape[1], fr.shape[1], tol, maxiter,
+                                           out.ctypes.data_as(_dp), xf.ctypes.data_as(_dp),
+                                           avg.ctypes.data_as(_dp), C.byref(rms))
+        return out, xf.reshape(F, 4, 4), avg.reshape(-1, 3), it, rms.value
+
+
+def have_reference():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libloosref.so"))
+
+
+# ---------------------------------------------------------------------------
+# Text format of the result matrix: src/MatrixImpl.hpp:210-222 under
+# `cout << setprecision(p)` (Tools/rmsds.cpp:566-567).  C++ default floatfield
+# with precision p prints like printf("%.{p}g") (p == 0 behaves as 1).
+def matrix_text(M, precision=2):
+    M = np.asarray(M, dtype=np.float32)
+    m, n = M.shape
+    lines = ["# %d %d (0)" % (m, n)]
+    fmt = "%." + str(max(int(precision), 1) if precision == 0 else int(precision)) + "g"
+    for j in range(m):
+        lines.append("".join((fmt % float(M[j, i])) + " " for i in range(n)))
+    return "\n".join(lines) + "\n"
