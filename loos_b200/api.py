@@ -1,0 +1,199 @@
+"""Host-side mirror of the reference's function boundary for the RMSD path.
+
+Names and argument meaning follow the reference:
+  FrameSet(coords, sel)         ~ readCoords(subset, traj, indices)  (src/ensembles.cpp:291-296)
+  rmsds(fs)                     ~ Tools/rmsds.cpp single-trajectory mode -> RealMatrix (float32)
+  rmsds_cross(a, b)             ~ Tools/rmsds.cpp two-trajectory mode
+  rmsd2ref(fs_align, ...)       ~ Tools/rmsd2ref.cpp with --target
+  rmsd2ref_iterative(...)       ~ Tools/rmsd2ref.cpp default mode (iterativeAlignment)
+Errors the reference throws (LOOSError on size mismatch) surface as LoosB200Error.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import LoosB200Error, Stats, check, lib
+
+
+def _as_f32(x):
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+class FrameSet:
+    """A staged set of frames on one GPU (opaque loosb200_frames handle).
+
+    coords: (F, natoms, 3) float32 [layout 'xyz', the readCoords order] or
+            (F, 3, natoms) float32 [layout 'planes', the DCD record order]; a
+            torch CUDA tensor of the same shapes is staged without touching the host.
+    sel:    optional uint32 atom indices into the frame (Atom::index(), model order).
+    """
+
+    def __init__(self, coords, sel=None, layout="xyz", device=0):
+        L = lib()
+        self._h = C.c_void_p()
+        self.device = device
+        lay = {"xyz": capi.LAYOUT_XYZ, "planes": capi.LAYOUT_PLANES}[layout]
+        sel_arr = None if sel is None else np.ascontiguousarray(sel, dtype=np.uint32)
+        sel_p = None if sel_arr is None else sel_arr.ctypes.data_as(C.POINTER(C.c_uint32))
+        nsel = 0 if sel_arr is None else sel_arr.size
+        if hasattr(coords, "is_cuda") and coords.is_cuda:
+            import torch
+            t = coords.contiguous()
+            assert t.dtype == torch.float32 and t.dim() == 3
+            F = t.shape[0]
+            natoms = t.shape[1] if lay == capi.LAYOUT_XYZ else t.shape[2]
+            torch.cuda.current_stream(t.device).synchronize()
+            check(L.loosb200_stage_frames_device(C.byref(self._h), C.c_void_p(t.data_ptr()), F, natoms,
+                                                 sel_p, nsel, lay, t.device.index or 0))
+            self.device = t.device.index or 0
+        else:
+            a = _as_f32(coords.numpy() if hasattr(coords, "numpy") else coords)
+            assert a.ndim == 3
+            F = a.shape[0]
+            natoms = a.shape[1] if lay == capi.LAYOUT_XYZ else a.shape[2]
+            check(L.loosb200_stage_frames(C.byref(self._h), a.ctypes.data_as(C.c_void_p), F, natoms,
+                                          sel_p, nsel, lay, device))
+        self.F = F
+        self.N = nsel if sel_arr is not None else natoms
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().loosb200_free(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def centroids(self):
+        out = np.zeros((self.F, 3))
+        check(lib().loosb200_get_centroids(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def unit_log2(self):
+        e = C.c_int()
+        check(lib().loosb200_get_unit_log2(self._h, C.byref(e)))
+        return e.value
+
+    def last_timing(self):
+        """(ms of the main kernel(s), ms of the rest, kernel launches) of the last call."""
+        a, b = C.c_double(), C.c_double()
+        n = check(lib().loosb200_last_timing(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value, n
+
+
+def _stats_tuple(s):
+    return {"max": s.max, "sum": s.sum, "count": s.count, "avg": (s.sum / s.count) if s.count else 0.0}
+
+
+def _dev_ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def rmsds(fs, out=None, noout=False, engine="auto", want_stats=True):
+    """All-to-all RMSD of one frame set.  Returns (M, stats): M is (F, F) float32 in
+    Fortran order (== the reference's column-major RealMatrix), M[i, j] = M(i, j),
+    or None with noout=True (Tools/rmsds.cpp --noout).  `out` may be a
+    preallocated Fortran-ordered (F, F) float32 numpy array (pinned for speed) or a
+    torch CUDA tensor of shape (F, F) (result stays in HBM; symmetric, so the
+    memory order is immaterial)."""
+    L = lib()
+    st = Stats()
+    sp = C.byref(st) if want_stats else None
+    eng = capi.ENGINES[engine]
+    if noout:
+        check(L.loosb200_rmsds_self(fs._h, None, 0, sp, eng))
+        return None, _stats_tuple(st)
+    if out is not None and hasattr(out, "is_cuda") and out.is_cuda:
+        assert out.shape == (fs.F, fs.F) and out.is_contiguous()
+        check(L.loosb200_rmsds_self_device(fs._h, _dev_ptr(out), fs.F, sp, eng))
+        return out, _stats_tuple(st)
+    if out is None:
+        out = np.empty((fs.F, fs.F), dtype=np.float32, order="F")
+    assert out.dtype == np.float32 and out.shape == (fs.F, fs.F) and out.flags.f_contiguous
+    check(L.loosb200_rmsds_self(fs._h, out.ctypes.data_as(C.c_void_p), fs.F, sp, eng))
+    return out, _stats_tuple(st)
+
+
+def rmsds_cross(a, b, out=None, noout=False, engine="auto", want_stats=True):
+    """M[i, j] = rmsd(a_i, b_j): Tools/rmsds.cpp with model2/traj2 (DualWorker)."""
+    L = lib()
+    st = Stats()
+    sp = C.byref(st) if want_stats else None
+    eng = capi.ENGINES[engine]
+    if noout:
+        check(L.loosb200_rmsds_cross(a._h, b._h, None, 0, sp, eng))
+        return None, _stats_tuple(st)
+    if out is None:
+        out = np.empty((a.F, b.F), dtype=np.float32, order="F")
+    assert out.dtype == np.float32 and out.shape == (a.F, b.F) and out.flags.f_contiguous
+    check(L.loosb200_rmsds_cross(a._h, b._h, out.ctypes.data_as(C.c_void_p), a.F, sp, eng))
+    return out, _stats_tuple(st)
+
+
+def part_rows(F, part, nparts):
+    """Frame index of every packed row of `part` (0xffffffff marks padding rows)."""
+    n = C.c_size_t()
+    check(lib().loosb200_part_rows(F, part, nparts, None, C.byref(n)))
+    rows = np.empty(n.value, dtype=np.uint32)
+    check(lib().loosb200_part_rows(F, part, nparts, rows.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(n)))
+    return rows
+
+
+def rmsds_part(fs, part, nparts, out=None, noout=False, engine="auto"):
+    """The rows of the lower triangle owned by `part` of `nparts` (multi-GPU split).
+    Returns (rows, block, stats): block[r, j] = M(rows[r], j) for j < rows[r]."""
+    L = lib()
+    st = Stats()
+    eng = capi.ENGINES[engine]
+    rows = part_rows(fs.F, part, nparts)
+    if noout:
+        check(L.loosb200_rmsds_self_part(fs._h, part, nparts, None, 0, C.byref(st), eng))
+        return rows, None, _stats_tuple(st)
+    if out is not None and hasattr(out, "is_cuda") and out.is_cuda:
+        assert out.shape == (len(rows), fs.F) and out.is_contiguous()
+        check(L.loosb200_rmsds_self_part_device(fs._h, part, nparts, _dev_ptr(out), fs.F, C.byref(st), eng))
+        return rows, out, _stats_tuple(st)
+    if out is None:
+        out = np.zeros((len(rows), fs.F), dtype=np.float32)
+    check(L.loosb200_rmsds_self_part(fs._h, part, nparts, out.ctypes.data_as(C.c_void_p), fs.F, C.byref(st), eng))
+    return rows, out, _stats_tuple(st)
+
+
+def _dptr(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def rmsd2ref(fs_align, ref_align, fs_rmsd=None, ref_rmsd=None, want_xforms=False):
+    """Per-frame RMSD to a reference after superposition (Tools/rmsd2ref.cpp with
+    --target).  ref_align: (N_a, 3) target align-selection coords, or None for no
+    alignment; fs_rmsd / ref_rmsd: the rmsd selection (default: the align one)."""
+    F = fs_align.F
+    ra = None if ref_align is None else np.ascontiguousarray(ref_align, dtype=np.float64).reshape(-1)
+    rr = None if ref_rmsd is None else np.ascontiguousarray(ref_rmsd, dtype=np.float64).reshape(-1)
+    if ra is not None and ra.size != 3 * fs_align.N:
+        raise LoosB200Error(capi.ERR_SIZE_MISMATCH, "Cannot superimpose groups with differing numbers of atoms")
+    nr = (fs_rmsd or fs_align).N
+    if rr is not None and rr.size != 3 * nr:
+        raise LoosB200Error(capi.ERR_SIZE_MISMATCH, "Cannot compute RMSD between groups with different sizes")
+    out = np.zeros(F)
+    xf = np.zeros((F, 4, 4)) if want_xforms else None
+    check(lib().loosb200_rmsd2ref(fs_align._h, None if fs_rmsd is None else fs_rmsd._h, _dptr(ra), _dptr(rr),
+                                  _dptr(out), _dptr(xf)))
+    return (out, xf) if want_xforms else out
+
+
+def rmsd2ref_iterative(fs_align, fs_rmsd=None, tol=1e-6, maxiter=1000):
+    """rmsd2ref's default mode.  Returns dict(rmsd, xforms, avg, iters, rms)."""
+    F = fs_align.F
+    nr = (fs_rmsd or fs_align).N
+    out, xf, avg = np.zeros(F), np.zeros((F, 4, 4)), np.zeros((nr, 3))
+    it, rms = C.c_int(), C.c_double()
+    check(lib().loosb200_rmsd2ref_iterative(fs_align._h, None if fs_rmsd is None else fs_rmsd._h, tol, maxiter,
+                                            _dptr(out), _dptr(xf), _dptr(avg), C.byref(it), C.byref(rms)))
+    return {"rmsd": out, "xforms": xf, "avg": avg, "iters": it.value, "rms": rms.value}

@@ -1,0 +1,339 @@
+// C-ABI glue: argument checking, tile-space partitioning, band pipelining of the
+// result copy, error reporting.  See include/loosb200.h for the contract.
+#include <limits.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace loosb200 {
+
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string& s) { g_last_error = s; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  g_last_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " in " + what +
+                 " (" + file + ":" + std::to_string(line) + ")";
+  cudaGetLastError();
+  return e == cudaErrorMemoryAllocation ? LOOSB200_ERR_NOMEM : LOOSB200_ERR_CUDA;
+}
+
+// Static split of the row tiles of the lower triangle over `nparts` parts.  Row
+// tile t costs t+1 tiles, so tiles are dealt from the heaviest down in
+// boustrophedon order (0..P-1, P-1..0, ...): every part gets the same number of
+// row tiles (+-1) and the same number of tiles to within one row tile.
+static std::vector<uint32_t> part_row_tiles(size_t F, int part, int nparts) {
+  const uint32_t T = (uint32_t)((F + TILE_FRAMES - 1) / TILE_FRAMES);
+  std::vector<uint32_t> rows;
+  for (uint32_t k = 0; k < T; ++k) {
+    const uint32_t t = T - 1 - k;
+    const uint32_t round = k / nparts, pos = k % nparts;
+    const uint32_t owner = (round & 1) ? (nparts - 1 - pos) : pos;
+    if ((int)owner == part) rows.push_back(t);
+  }
+  std::sort(rows.begin(), rows.end());
+  return rows;
+}
+
+struct Bands {
+  std::vector<uint32_t> rows;    // all row tiles of the job, ascending
+  std::vector<uint32_t> prefix;  // per band: local prefix arrays, concatenated
+  struct Band { uint32_t r0, r1, p0; uint64_t ntiles; };  // rows[r0..r1), prefix offset
+  std::vector<Band> bands;       // in launch order (heaviest rows first)
+};
+
+// Cut `rows` (ascending) into <= maxbands contiguous bands of about equal tile
+// count, ordered from the last rows to the first so that, in symmetric mode, the
+// columns of a band are complete as soon as the band has been computed.
+static Bands make_bands(const std::vector<uint32_t>& rows, bool self, uint32_t col_tiles, int maxbands) {
+  Bands B;
+  B.rows = rows;
+  uint64_t total = 0;
+  for (uint32_t t : rows) total += self ? (uint64_t)t + 1 : col_tiles;
+  int nb = (int)std::min<uint64_t>((uint64_t)std::max(1, maxbands), std::max<uint64_t>(1, rows.size()));
+  const uint64_t per = (total + nb - 1) / nb;
+  uint32_t r1 = (uint32_t)rows.size();
+  while (r1 > 0) {
+    uint64_t acc = 0;
+    uint32_t r0 = r1;
+    while (r0 > 0 && (acc < per || B.bands.size() + 1 == (size_t)nb)) {
+      --r0;
+      acc += self ? (uint64_t)rows[r0] + 1 : col_tiles;
+    }
+    Bands::Band b;
+    b.r0 = r0; b.r1 = r1; b.p0 = (uint32_t)B.prefix.size(); b.ntiles = acc;
+    uint32_t run = 0;
+    for (uint32_t r = r0; r < r1; ++r) {
+      B.prefix.push_back(run);
+      run += self ? rows[r] + 1 : col_tiles;
+    }
+    B.prefix.push_back(run);
+    B.bands.push_back(b);
+    r1 = r0;
+  }
+  return B;
+}
+
+static int pick_engine(int engine, const loosb200_frames* a) {
+  if (engine == LOOSB200_ENGINE_FP64) return LOOSB200_ENGINE_FP64;
+  const bool can = tensor_path_available() && a->N <= TENSOR_MAX_ATOMS;
+  if (engine == LOOSB200_ENGINE_TENSOR) return can ? LOOSB200_ENGINE_TENSOR : LOOSB200_ERR_UNSUPPORTED;
+  if (engine == LOOSB200_ENGINE_AUTO) return can ? LOOSB200_ENGINE_TENSOR : LOOSB200_ENGINE_FP64;
+  return LOOSB200_ERR_INVALID;
+}
+
+enum class OutKind { None, Host, Device };
+
+// The one driver behind every all-to-all entry point.
+static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric, bool packed,
+                     const std::vector<uint32_t>& rows, float* out, OutKind okind, size_t ld,
+                     loosb200_stats* stats, int engine) {
+  LB_CUDA(cudaSetDevice(a->device));
+  engine = pick_engine(engine, a);
+  if (engine < 0) return engine;
+  if (engine == LOOSB200_ENGINE_TENSOR) {
+    int rc;
+    if (self) {
+      if ((rc = ensure_quantised(a, INT_MIN))) return rc;
+    } else {
+      // both sets must share one fixed-point unit: quantise each, then re-quantise
+      // the finer one on the coarser grid
+      if ((rc = ensure_quantised(a, INT_MIN))) return rc;
+      if ((rc = ensure_quantised(b, INT_MIN))) return rc;
+      const int e = std::max(a->unit_log2, b->unit_log2);
+      if ((rc = ensure_quantised(a, e))) return rc;
+      if ((rc = ensure_quantised(b, e))) return rc;
+    }
+  }
+  cudaStream_t st = a->stream;
+  const size_t FA = a->F, FB = b->F;
+  const uint32_t col_tiles = (uint32_t)((FB + TILE_FRAMES - 1) / TILE_FRAMES);
+  const size_t out_rows = packed ? rows.size() * TILE_FRAMES : 0;  // packed: rows x ld (row-major)
+  const size_t out_cols = packed ? 0 : FB;                          // else: FB columns of ld
+  const size_t dev_ld = (okind == OutKind::Host) ? (packed ? FB : FA) : ld;
+
+  const int maxbands = (okind == OutKind::Host) ? 12 : 1;
+  Bands B = make_bands(rows, self, col_tiles, maxbands);
+
+  uint32_t *d_rows = nullptr, *d_prefix = nullptr;
+  float* d_out = nullptr;
+  double* d_stats = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> evs(B.bands.size(), nullptr);
+  auto cleanup = [&]() {
+    cudaFree(d_rows); cudaFree(d_prefix); cudaFree(d_stats);
+    if (okind == OutKind::Host) cudaFree(d_out);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (auto e : evs) if (e) cudaEventDestroy(e);
+  };
+  bool ok = cudaMalloc(&d_rows, sizeof(uint32_t) * std::max<size_t>(1, B.rows.size())) == cudaSuccess &&
+            cudaMalloc(&d_prefix, sizeof(uint32_t) * std::max<size_t>(1, B.prefix.size())) == cudaSuccess &&
+            cudaMalloc(&d_stats, 2 * sizeof(double)) == cudaSuccess;
+  if (ok && okind == OutKind::Host) {
+    const size_t n = packed ? out_rows * dev_ld : out_cols * dev_ld;
+    ok = cudaMalloc(&d_out, sizeof(float) * std::max<size_t>(1, n)) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& e : evs) if (ok) ok = cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+  } else if (okind == OutKind::Device) {
+    d_out = out;
+  }
+  if (!ok) { cudaGetLastError(); cleanup(); return LOOSB200_ERR_NOMEM; }
+
+  cudaEventRecord(a->timing.ev[0], st);
+  cudaMemcpyAsync(d_rows, B.rows.data(), sizeof(uint32_t) * B.rows.size(), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_prefix, B.prefix.data(), sizeof(uint32_t) * B.prefix.size(), cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(d_stats, 0, 2 * sizeof(double), st);
+  cudaEventRecord(a->timing.ev[1], st);
+  int launches = 0, rc = LOOSB200_OK;
+  for (size_t k = 0; k < B.bands.size() && rc == LOOSB200_OK; ++k) {
+    const Bands::Band& bd = B.bands[k];
+    PairJob job;
+    job.a = a; job.b = b; job.self = self; job.symmetric = symmetric;
+    job.ld = dev_ld;
+    job.row_tiles_dev = d_rows + bd.r0;
+    job.tile_prefix_dev = d_prefix + bd.p0;
+    job.n_row_tiles = bd.r1 - bd.r0;
+    job.n_tiles = bd.ntiles;
+    job.packed_rows = packed;
+    job.out = d_out ? (packed ? d_out + (size_t)bd.r0 * TILE_FRAMES * dev_ld : d_out) : nullptr;
+    job.stats_dev = stats ? d_stats : nullptr;
+    if (engine == LOOSB200_ENGINE_TENSOR) {
+      int l = 0;
+      rc = launch_pairs_tensor(job, st, &l);
+      launches += l;
+    } else {
+      rc = launch_pairs_fp64(job, st);
+      launches += 1;
+    }
+    if (rc == LOOSB200_OK && okind == OutKind::Host) {
+      cudaEventRecord(evs[k], st);
+      cudaStreamWaitEvent(copy_stream, evs[k], 0);
+      if (packed) {
+        // rows of the band are contiguous in the packed buffer
+        const size_t r_lo = (size_t)bd.r0 * TILE_FRAMES, nr = (size_t)(bd.r1 - bd.r0) * TILE_FRAMES;
+        cudaMemcpy2DAsync(out + r_lo * ld, ld * sizeof(float), d_out + r_lo * dev_ld, dev_ld * sizeof(float),
+                          FB * sizeof(float), nr, cudaMemcpyDeviceToHost, copy_stream);
+      } else if (self) {
+        // columns [c0, c1) are final once all rows >= c0 are done (bands run last-to-first)
+        const size_t c0 = (size_t)B.rows[bd.r0] * TILE_FRAMES;
+        const size_t c1 = std::min(FA, ((size_t)B.rows[bd.r1 - 1] + 1) * TILE_FRAMES);
+        cudaMemcpy2DAsync(out + c0 * ld, ld * sizeof(float), d_out + c0 * dev_ld, dev_ld * sizeof(float),
+                          FA * sizeof(float), c1 - c0, cudaMemcpyDeviceToHost, copy_stream);
+      }
+    }
+  }
+  cudaEventRecord(a->timing.ev[2], st);
+  if (rc == LOOSB200_OK && okind == OutKind::Host && !packed && !self) {
+    cudaMemcpy2DAsync(out, ld * sizeof(float), d_out, dev_ld * sizeof(float), FA * sizeof(float), FB,
+                      cudaMemcpyDeviceToHost, st);
+  }
+  double hs[2] = {0.0, 0.0};
+  if (stats) cudaMemcpyAsync(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st);
+  cudaEventRecord(a->timing.ev[3], st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess && copy_stream) e = cudaStreamSynchronize(copy_stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cleanup();
+  if (rc != LOOSB200_OK) return rc;
+  if (e != cudaSuccess) return cuda_fail(e, "all-to-all kernel", __FILE__, __LINE__);
+  if (stats) {
+    stats->sum = hs[0];
+    stats->max = hs[1];
+    uint64_t cnt = 0;
+    if (self) {
+      for (uint32_t t : rows) {
+        const uint64_t i0 = (uint64_t)t * TILE_FRAMES, i1 = std::min<uint64_t>(FA, i0 + TILE_FRAMES);
+        cnt += (i1 * (i1 - 1) - i0 * (i0 ? i0 - 1 : 0)) / 2;
+      }
+    } else {
+      cnt = (uint64_t)FA * FB;
+    }
+    stats->count = cnt;
+  }
+  a->timing.launches = launches; a->timing.valid = true;
+  return LOOSB200_OK;
+}
+
+}  // namespace loosb200
+
+using namespace loosb200;
+
+extern "C" const char* loosb200_version(void) { return "loosb200 0.1 (sm_100a)"; }
+
+extern "C" const char* loosb200_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" const char* loosb200_strerror(int code) {
+  switch (code) {
+    case LOOSB200_OK: return "success";
+    case LOOSB200_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (there is no CPU fallback)";
+    case LOOSB200_ERR_CUDA: return "CUDA call failed";
+    case LOOSB200_ERR_INVALID: return "invalid argument";
+    case LOOSB200_ERR_SIZE_MISMATCH: return "groups/frames of differing sizes";
+    case LOOSB200_ERR_RANGE: return "index or coordinate out of range";
+    case LOOSB200_ERR_NOMEM: return "out of memory";
+    case LOOSB200_ERR_NUMERICAL: return "numerical failure in the superposition solver";
+    case LOOSB200_ERR_UNSUPPORTED: return "request not supported by this build";
+    default: return "unknown error";
+  }
+}
+
+extern "C" int loosb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int usable = 0;
+  for (int d = 0; d < n; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10)
+      usable = d + 1;  // devices are addressed by CUDA ordinal
+  }
+  cudaGetLastError();
+  return usable;
+}
+
+static int check_self(loosb200_frames* h, float* out, size_t ld) {
+  if (!h) return LOOSB200_ERR_INVALID;
+  if (out && ld < h->F) return LOOSB200_ERR_INVALID;
+  return LOOSB200_OK;
+}
+
+static std::vector<uint32_t> all_rows(size_t F) { return part_row_tiles(F, 0, 1); }
+
+extern "C" int loosb200_rmsds_self(loosb200_frames* h, float* out, size_t ld, loosb200_stats* stats, int engine) {
+  int rc = check_self(h, out, ld);
+  if (rc) return rc;
+  return run_pairs(h, h, true, true, false, all_rows(h->F), out, out ? OutKind::Host : OutKind::None, ld, stats, engine);
+}
+
+extern "C" int loosb200_rmsds_self_device(loosb200_frames* h, float* out_dev, size_t ld, loosb200_stats* stats, int engine) {
+  int rc = check_self(h, out_dev, ld);
+  if (rc) return rc;
+  return run_pairs(h, h, true, true, false, all_rows(h->F), out_dev, out_dev ? OutKind::Device : OutKind::None, ld, stats, engine);
+}
+
+static int check_cross(loosb200_frames* a, loosb200_frames* b, float* out, size_t ld) {
+  if (!a || !b) return LOOSB200_ERR_INVALID;
+  if (a->N != b->N) return LOOSB200_ERR_SIZE_MISMATCH;
+  if (a->device != b->device) return LOOSB200_ERR_INVALID;
+  if (out && ld < a->F) return LOOSB200_ERR_INVALID;
+  return LOOSB200_OK;
+}
+
+extern "C" int loosb200_rmsds_cross(loosb200_frames* a, loosb200_frames* b, float* out, size_t ld, loosb200_stats* stats, int engine) {
+  int rc = check_cross(a, b, out, ld);
+  if (rc) return rc;
+  return run_pairs(a, b, false, false, false, all_rows(a->F), out, out ? OutKind::Host : OutKind::None, ld, stats, engine);
+}
+
+extern "C" int loosb200_rmsds_cross_device(loosb200_frames* a, loosb200_frames* b, float* out_dev, size_t ld, loosb200_stats* stats, int engine) {
+  int rc = check_cross(a, b, out_dev, ld);
+  if (rc) return rc;
+  return run_pairs(a, b, false, false, false, all_rows(a->F), out_dev, out_dev ? OutKind::Device : OutKind::None, ld, stats, engine);
+}
+
+extern "C" int loosb200_part_rows(size_t F, int part, int nparts, uint32_t* rows_or_null, size_t* nrows) {
+  if (F == 0 || nparts < 1 || part < 0 || part >= nparts) return LOOSB200_ERR_INVALID;
+  std::vector<uint32_t> rt = part_row_tiles(F, part, nparts);
+  size_t n = 0;
+  for (uint32_t t : rt)
+    for (uint32_t k = 0; k < (uint32_t)TILE_FRAMES; ++k) {
+      const size_t f = (size_t)t * TILE_FRAMES + k;
+      // the packed buffer always has TILE_FRAMES rows per row tile; rows beyond F are padding
+      if (rows_or_null) rows_or_null[n] = (uint32_t)(f < F ? f : 0xffffffffu);
+      ++n;
+    }
+  if (nrows) *nrows = n;
+  return LOOSB200_OK;
+}
+
+static int check_part(loosb200_frames* h, int part, int nparts, float* out, size_t ld) {
+  if (!h || nparts < 1 || part < 0 || part >= nparts) return LOOSB200_ERR_INVALID;
+  if (out && ld < h->F) return LOOSB200_ERR_INVALID;
+  return LOOSB200_OK;
+}
+
+extern "C" int loosb200_rmsds_self_part(loosb200_frames* h, int part, int nparts, float* out, size_t ld, loosb200_stats* stats, int engine) {
+  int rc = check_part(h, part, nparts, out, ld);
+  if (rc) return rc;
+  return run_pairs(h, h, true, false, true, part_row_tiles(h->F, part, nparts), out, out ? OutKind::Host : OutKind::None, ld, stats, engine);
+}
+
+extern "C" int loosb200_rmsds_self_part_device(loosb200_frames* h, int part, int nparts, float* out_dev, size_t ld, loosb200_stats* stats, int engine) {
+  int rc = check_part(h, part, nparts, out_dev, ld);
+  if (rc) return rc;
+  return run_pairs(h, h, true, false, true, part_row_tiles(h->F, part, nparts), out_dev, out_dev ? OutKind::Device : OutKind::None, ld, stats, engine);
+}
+
+extern "C" int loosb200_last_timing(const loosb200_frames* h, double* ms_main, double* ms_other) {
+  if (!h) return LOOSB200_ERR_INVALID;
+  if (!h->timing.valid) return LOOSB200_ERR_INVALID;
+  float t_all = 0.f, t_main = 0.f;
+  LB_CUDA(cudaEventElapsedTime(&t_all, h->timing.ev[0], h->timing.ev[3]));
+  LB_CUDA(cudaEventElapsedTime(&t_main, h->timing.ev[1], h->timing.ev[2]));
+  if (ms_main) *ms_main = t_main;
+  if (ms_other) *ms_other = t_all - t_main;
+  return h->timing.launches;
+}

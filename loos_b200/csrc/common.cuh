@@ -1,0 +1,96 @@
+// Shared declarations of the loosb200 CUDA implementation (not part of the ABI).
+#pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/loosb200.h"
+
+namespace loosb200 {
+
+// Frames are grouped in blocks of FRAMES_PER_BLOCK; one block of frames occupies
+// ROWS_PER_BLOCK rows of the tensor-core operand planes (row = 3*j + axis for
+// frame j of the block, rows 30 and 31 are zero) so that the three axes of one
+// frame always live in the same warp's 32 TMEM lanes.  A tile is 4 blocks =
+// 40 frames = 128 operand rows.
+constexpr int FRAMES_PER_BLOCK = 10;
+constexpr int ROWS_PER_BLOCK = 32;
+constexpr int BLOCKS_PER_TILE = 4;
+constexpr int TILE_FRAMES = FRAMES_PER_BLOCK * BLOCKS_PER_TILE;  // 40
+constexpr int TILE_ROWS = ROWS_PER_BLOCK * BLOCKS_PER_TILE;      // 128
+constexpr int K_CHUNK = 64;    // atoms (bytes of int8) per pipeline stage / swizzle row
+constexpr int NUM_SLICES = 3;  // signed 8-bit digits of the 24-bit fixed-point coordinate
+// int32 accumulators hold up to 3 slice products of magnitude <= 2^14 per atom.
+constexpr size_t TENSOR_MAX_ATOMS = 43000;
+
+void set_last_error(const std::string& s);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define LB_CUDA(call)                                                       \
+  do {                                                                      \
+    cudaError_t e__ = (call);                                               \
+    if (e__ != cudaSuccess) return ::loosb200::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+struct Timing {
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, main0, main1, end
+  int launches = 0;
+  bool valid = false;
+};
+
+}  // namespace loosb200
+
+// The opaque handle of include/loosb200.h.
+struct loosb200_frames {
+  int device = 0;
+  size_t F = 0, N = 0;
+  size_t Npad = 0;  // N rounded up to 4 floats (16 B) -- row pitch of `raw`
+  // fp32 SoA planes of the selected atoms, uncentred: raw[(f*3 + axis)*Npad + i]
+  float* raw = nullptr;
+  double* centroid = nullptr;  // [F][3]
+  double* gd = nullptr;        // [F] sum |x - c|^2 in A^2
+  float* maxabs = nullptr;     // [F] max |x - c| over atoms and axes
+
+  // tensor-core operands (lazy): q8[(slice*rows_total + row)*Kpad + atom]
+  int8_t* q8 = nullptr;
+  long long* gq = nullptr;  // [F] sum q^2, exact
+  int* unit_log2_dev = nullptr;
+  int unit_log2 = 0;
+  bool quantised = false;
+  size_t rows_total = 0, Kpad = 0;
+  CUtensorMap tmap;  // 3-D map over q8: (atom, row, slice)
+  bool tmap_valid = false;
+
+  cudaStream_t stream = nullptr;
+  loosb200::Timing timing;
+};
+
+namespace loosb200 {
+
+// What one all-to-all launch needs to know about its share of the tile space.
+struct PairJob {
+  const loosb200_frames* a;
+  const loosb200_frames* b;   // == a for self mode
+  bool self;                  // lower triangle only (j < i), else full rectangle
+  bool symmetric;             // self mode: also store M(j,i); rows unpacked
+  float* out;                 // device, may be null (stats only)
+  size_t ld;
+  // row blocks (of TILE_FRAMES frames of `a`) this launch covers, ascending
+  const uint32_t* row_tiles_dev;   // [n_row_tiles]
+  const uint32_t* tile_prefix_dev; // [n_row_tiles+1] prefix sum of column tiles per row tile
+  uint32_t n_row_tiles;
+  uint64_t n_tiles;
+  bool packed_rows;           // out row index = position in the launch's row list
+  double* stats_dev;          // [2]: sum, max-as-bits ; may be null
+};
+
+int ensure_quantised(loosb200_frames* h, int force_unit_log2 /* INT_MIN: auto */);
+int launch_pairs_fp64(const PairJob& job, cudaStream_t st);
+int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches);
+bool tensor_path_available();
+
+}  // namespace loosb200

@@ -1,0 +1,168 @@
+// All-to-all RMSD, CUDA-core fp64 variant.
+//
+// Same tile space, same epilogue (fused QCP solve, float32 store, symmetric fill,
+// stats) as the tensor-core kernel in pairs_tensor.cu, but the 3x3 covariance of
+// every frame pair is accumulated with DFMA from the fp32 planes centred in fp64
+// -- i.e. the arithmetic of dgemm_('N','T',3,3,n,...) at src/alignment.cpp:34
+// done for a 40 x 40 tile of pairs at once.  It serves selections larger than
+// the int32 accumulation bound of the tensor path, and is the on-device
+// cross-check for it.  Roofline: fp64 pipe (18 N flop per pair).
+#include "common.cuh"
+#include "qcp.cuh"
+
+namespace loosb200 {
+
+namespace {
+
+constexpr int TF = TILE_FRAMES;  // 40
+constexpr int KC = 16;           // atoms per smem chunk
+constexpr int NT = 416;          // 13 warps; threads 0..399 own a 2x2 block of pairs
+
+__device__ __forceinline__ uint32_t find_row_tile(const uint32_t* __restrict__ prefix, uint32_t n,
+                                                  uint64_t tile) {
+  uint32_t lo = 0, hi = n;  // prefix[lo] <= tile < prefix[hi]
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if ((uint64_t)prefix[mid] <= tile) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(NT)
+k_pairs_fp64(const float* __restrict__ rawA, const double* __restrict__ cenA,
+             const double* __restrict__ gdA, uint32_t FA, size_t NpadA,
+             const float* __restrict__ rawB, const double* __restrict__ cenB,
+             const double* __restrict__ gdB, uint32_t FB, size_t NpadB, uint32_t N,
+             const uint32_t* __restrict__ row_tiles, const uint32_t* __restrict__ prefix,
+             uint32_t n_row_tiles, int self, int symmetric, int packed, float* __restrict__ out,
+             size_t ld, double* __restrict__ stats) {
+  __shared__ double As[3][KC][TF];
+  __shared__ double Bs[3][KC][TF];
+  __shared__ double cA[TF][3], cB[TF][3];
+  __shared__ double red_sum[13], red_max[13];
+
+  const uint64_t tile = blockIdx.x;
+  const uint32_t rt = find_row_tile(prefix, n_row_tiles, tile);
+  const uint32_t I = row_tiles[rt];
+  const uint32_t J = (uint32_t)(tile - prefix[rt]);
+  const int tid = threadIdx.x;
+  const bool worker = tid < TF * TF / 4;
+  const int ty = tid / 20, tx = tid % 20;
+
+  for (int t = tid; t < TF * 3; t += NT) {
+    const uint32_t fa = I * TF + t / 3, fb = J * TF + t / 3;
+    cA[t / 3][t % 3] = fa < FA ? cenA[(size_t)fa * 3 + t % 3] : 0.0;
+    cB[t / 3][t % 3] = fb < FB ? cenB[(size_t)fb * 3 + t % 3] : 0.0;
+  }
+  __syncthreads();
+
+  double acc[2][2][9];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[a][b][k] = 0.0;
+
+  for (uint32_t k0 = 0; k0 < N; k0 += KC) {
+    for (int idx = tid; idx < TF * 3 * KC; idx += NT) {
+      const int f = idx / (3 * KC), rem = idx % (3 * KC), ax = rem / KC, k = rem % KC;
+      const uint32_t fa = I * TF + f, fb = J * TF + f, at = k0 + k;
+      double va = 0.0, vb = 0.0;
+      if (at < N) {
+        if (fa < FA) va = (double)rawA[((size_t)fa * 3 + ax) * NpadA + at] - cA[f][ax];
+        if (fb < FB) vb = (double)rawB[((size_t)fb * 3 + ax) * NpadB + at] - cB[f][ax];
+      }
+      As[ax][k][f] = va;
+      Bs[ax][k][f] = vb;
+    }
+    __syncthreads();
+    if (worker) {
+#pragma unroll 4
+      for (int k = 0; k < KC; ++k) {
+        double a0[3], a1[3], b0[3], b1[3];
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+          a0[ax] = As[ax][k][ty]; a1[ax] = As[ax][k][ty + 20];
+          b0[ax] = Bs[ax][k][tx]; b1[ax] = Bs[ax][k][tx + 20];
+        }
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            acc[0][0][3 * p + q] = fma(a0[p], b0[q], acc[0][0][3 * p + q]);
+            acc[0][1][3 * p + q] = fma(a0[p], b1[q], acc[0][1][3 * p + q]);
+            acc[1][0][3 * p + q] = fma(a1[p], b0[q], acc[1][0][3 * p + q]);
+            acc[1][1][3 * p + q] = fma(a1[p], b1[q], acc[1][1][3 * p + q]);
+          }
+      }
+    }
+    __syncthreads();
+  }
+
+  double ssum = 0.0, smax = 0.0;
+  if (worker) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const uint32_t la = ty + 20 * a, lb = tx + 20 * b;
+        const uint32_t i = I * TF + la, j = J * TF + lb;
+        if (i >= FA || j >= FB) continue;
+        if (self && j >= i) {
+          // the diagonal is never computed and stays 0 (Tools/rmsds.cpp:359-365)
+          if (j == i && out) {
+            if (packed) out[((size_t)rt * TF + la) * ld + j] = 0.f;
+            else out[(size_t)j * ld + i] = 0.f;
+          }
+          continue;
+        }
+        const double d = qcp_rmsd(acc[a][b], gdA[i], gdB[j], (double)N, 1.0);
+        const float v = (float)d;  // Tools/rmsds.cpp:363: double -> float on store
+        ssum += (double)v;
+        smax = fmax(smax, (double)v);
+        if (out) {
+          if (packed) {
+            out[((size_t)rt * TF + la) * ld + j] = v;
+          } else {
+            out[(size_t)j * ld + i] = v;
+            if (symmetric) out[(size_t)i * ld + j] = v;
+          }
+        }
+      }
+  }
+  if (stats) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+      smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    }
+    if ((tid & 31) == 0) { red_sum[tid >> 5] = ssum; red_max[tid >> 5] = smax; }
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0, m = 0.0;
+      for (int w = 0; w < NT / 32; ++w) { s += red_sum[w]; m = fmax(m, red_max[w]); }
+      atomicAdd(&stats[0], s);
+      // non-negative doubles order like their bit patterns
+      atomicMax(reinterpret_cast<unsigned long long*>(&stats[1]), (unsigned long long)__double_as_longlong(m));
+    }
+  }
+}
+
+}  // namespace
+
+int launch_pairs_fp64(const PairJob& job, cudaStream_t st) {
+  if (job.n_tiles == 0) return LOOSB200_OK;
+  if (job.n_tiles > 0x7fffffffull) return LOOSB200_ERR_UNSUPPORTED;
+  const loosb200_frames* a = job.a;
+  const loosb200_frames* b = job.b;
+  k_pairs_fp64<<<(unsigned)job.n_tiles, NT, 0, st>>>(
+      a->raw, a->centroid, a->gd, (uint32_t)a->F, a->Npad, b->raw, b->centroid, b->gd,
+      (uint32_t)b->F, b->Npad, (uint32_t)a->N, job.row_tiles_dev, job.tile_prefix_dev,
+      job.n_row_tiles, job.self ? 1 : 0, job.symmetric ? 1 : 0, job.packed_rows ? 1 : 0, job.out,
+      job.ld, job.stats_dev);
+  LB_CUDA(cudaGetLastError());
+  return LOOSB200_OK;
+}
+
+}  // namespace loosb200

@@ -1,0 +1,68 @@
+"""Generate tests/golden/*.npz from the REFERENCE's own arithmetic
+(oracle/_ref/libloosref.so = /root/reference/src/alignment.cpp:12-281 compiled in
+place against OpenBLAS 0.3.15).  Run in the build container, where /root/reference
+exists; the fixtures travel to the GPU box, the reference does not.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from loos_b200.synth import SEED0, synth_frames  # noqa: E402
+from oracle.oracle import Checker, matrix_text  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    R = Checker("reference")
+    # (1) a small all-to-all case with ragged sizes (F, N not multiples of any tile)
+    X = synth_frames(53, 137, seed=SEED0 + 101)
+    M = R.rmsds_self(X.astype(np.float64), nthreads=4)
+    Y = synth_frames(31, 137, seed=SEED0 + 102)
+    Mx = R.rmsds_cross(X.astype(np.float64), Y.astype(np.float64), nthreads=4)
+    np.savez_compressed(os.path.join(HERE, "rmsds_small.npz"), X=X, Y=Y, M=M, Mx=Mx,
+                        text_p2=np.array(matrix_text(M, 2)), text_p8=np.array(matrix_text(M, 8)))
+    # (2) analytic / degenerate known-answer cases evaluated by the reference
+    rng = np.random.default_rng(SEED0 + 103)
+    a = synth_frames(1, 64, seed=SEED0 + 104)[0].astype(np.float64)
+    th = 0.7
+    Rz = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    cases = {
+        "identical": (a, a.copy()),
+        "rigid": (a, (a @ Rz.T + [3.0, -2.0, 9.0]).astype(np.float32).astype(np.float64)),
+        "mirror": (a, a * [1, 1, -1]),
+        "planar": (a * [1, 1, 0], (a * [1, 1, 0]) @ Rz.T + rng.normal(size=a.shape) * [0.2, 0.2, 0]),
+        "collinear": (a * [1, 0, 0], a * [1.1, 0, 0] + 0.5),
+        "n1": (a[:1], a[1:2]),
+        "n2": (a[:2], a[5:7]),
+        "n3": (a[:3], a[7:10]),
+        "noisy": (a, a + rng.normal(size=a.shape) * 0.4),
+    }
+    out = {}
+    for k, (u, v) in cases.items():
+        u = u.astype(np.float32); v = v.astype(np.float32)
+        pair = np.stack([u, v])
+        out[k + "_xyz"] = pair
+        out[k + "_rmsd"] = np.array(R.rmsds_self(pair.astype(np.float64))[1, 0], dtype=np.float32)
+    np.savez_compressed(os.path.join(HERE, "kat_pairs.npz"), **out)
+    # (3) rmsd2ref with a target, align selection != rmsd selection
+    F, N = 40, 90
+    Z = synth_frames(F + 1, N, seed=SEED0 + 105).astype(np.float64)
+    sel_a = np.arange(0, N, 3)
+    sel_r = np.array([i for i in range(N) if i % 5 != 0])
+    tgt = Z[-1]
+    d, xf = R.rmsd2ref_target(Z[:F, sel_a], Z[:F, sel_r], tgt[sel_a], tgt[sel_r])
+    it = R.rmsd2ref_iterative(Z[:F, sel_a], Z[:F, sel_r], 1e-6, 1000)
+    np.savez_compressed(os.path.join(HERE, "rmsd2ref_small.npz"), Z=Z.astype(np.float32), sel_a=sel_a,
+                        sel_r=sel_r, rmsd=d, xforms=xf, it_rmsd=it[0], it_xforms=it[1], it_avg=it[2],
+                        it_iters=np.array(it[3]), it_rms=np.array(it[4]))
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,86 @@
+"""GPU parity tests for the single-reference streaming path (rmsd2ref)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import loos_b200
+    from loos_b200 import capi
+    assert capi.device_count() >= 1
+    return loos_b200
+
+
+def test_golden_target_mode(lb):
+    g = np.load(os.path.join(G, "rmsd2ref_small.npz"))
+    Z = g["Z"]
+    F = len(Z) - 1
+    sa, sr = g["sel_a"].astype(np.uint32), g["sel_r"].astype(np.uint32)
+    tgt = Z[-1].astype(np.float64)
+    with lb.FrameSet(Z[:F], sel=sa) as fa, lb.FrameSet(Z[:F], sel=sr) as fr:
+        d, xf = lb.rmsd2ref(fa, tgt[sa], fr, tgt[sr], want_xforms=True)
+    assert np.abs(d - g["rmsd"]).max() < 1e-9
+    assert np.abs(xf - g["xforms"]).max() < 1e-9     # same rotation, same 4x4 convention
+
+
+def test_golden_iterative_mode(lb):
+    g = np.load(os.path.join(G, "rmsd2ref_small.npz"))
+    Z = g["Z"]
+    F = len(Z) - 1
+    sa, sr = g["sel_a"].astype(np.uint32), g["sel_r"].astype(np.uint32)
+    with lb.FrameSet(Z[:F], sel=sa) as fa, lb.FrameSet(Z[:F], sel=sr) as fr:
+        r = lb.rmsd2ref_iterative(fa, fr, tol=1e-6, maxiter=1000)
+    assert r["iters"] == int(g["it_iters"])
+    assert np.abs(r["rmsd"] - g["it_rmsd"]).max() < 1e-7
+    assert np.abs(r["avg"] - g["it_avg"]).max() < 1e-7
+    assert np.abs(r["xforms"] - g["it_xforms"]).max() < 1e-7
+
+
+@pytest.mark.parametrize("F,N", [(1, 3), (7, 4), (300, 2000), (1000, 501)])
+def test_vs_oracle(lb, checker, F, N):
+    from loos_b200.synth import synth_frames
+    Z = synth_frames(F + 1, N, seed=1000 + F + N)
+    tgt = Z[-1].astype(np.float64)
+    ref, rxf = checker.rmsd2ref_target(Z[:F].astype(np.float64), Z[:F].astype(np.float64), tgt, tgt)
+    with lb.FrameSet(Z[:F]) as fs:
+        d, xf = lb.rmsd2ref(fs, tgt, want_xforms=True)
+    assert np.abs(d - ref).max() <= TOL
+    assert np.abs(d - ref).max() < 1e-8
+    if N >= 4:
+        assert np.abs(xf - rxf).max() < 1e-7
+
+
+def test_no_alignment_and_errors(lb):
+    from loos_b200 import capi
+    from loos_b200.synth import synth_frames
+    Z = synth_frames(20, 50, seed=4)
+    tgt = Z[0].astype(np.float64)
+    with lb.FrameSet(Z) as fs:
+        d = lb.rmsd2ref(fs, None, None, tgt)            # --align '' : plain rmsd, identity transform
+        want = np.sqrt(((Z.astype(np.float64) - tgt[None]) ** 2).sum(-1).mean(-1))
+        assert np.abs(d - want).max() < 1e-12
+        with pytest.raises(lb.LoosB200Error) as e:
+            lb.rmsd2ref(fs, tgt[:-1])
+        assert e.value.code == capi.ERR_SIZE_MISMATCH
+
+
+def test_streaming_identities(lb):
+    """Property at scale: a frame set that is a rigidly moved copy of the reference
+    has RMSD ~0, and its transforms undo the motion."""
+    from loos_b200.synth import _rot_from_rotvec, synth_frames
+    base = synth_frames(1, 2000, seed=6)[0].astype(np.float64)
+    rng = np.random.default_rng(2)
+    R = _rot_from_rotvec(rng.normal(size=(4096, 3)))
+    t = rng.normal(size=(4096, 1, 3)) * 30
+    X = (np.einsum("fij,nj->fni", R, base) + t).astype(np.float32)
+    with lb.FrameSet(X) as fs:
+        d, xf = lb.rmsd2ref(fs, base, want_xforms=True)
+    assert d.max() < 2e-5                    # float32 rounding of the moved coordinates
+    back = np.einsum("fij,fnj->fni", xf[:, :3, :3], X.astype(np.float64)) + xf[:, None, :3, 3]
+    assert np.abs(back - base[None]).max() < 1e-4
