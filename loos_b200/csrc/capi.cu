@@ -154,6 +154,7 @@ static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool sym
     PairJob job;
     job.a = a; job.b = b; job.self = self; job.symmetric = symmetric;
     job.ld = dev_ld;
+    job.rows_host = B.rows.data() + bd.r0;
     job.row_tiles_dev = d_rows + bd.r0;
     job.tile_prefix_dev = d_prefix + bd.p0;
     job.n_row_tiles = bd.r1 - bd.r0;

@@ -22,6 +22,11 @@ constexpr int ROWS_PER_BLOCK = 32;
 constexpr int BLOCKS_PER_TILE = 4;
 constexpr int TILE_FRAMES = FRAMES_PER_BLOCK * BLOCKS_PER_TILE;  // 40
 constexpr int TILE_ROWS = ROWS_PER_BLOCK * BLOCKS_PER_TILE;      // 128
+// Tensor path: an accumulator tile is 40 "a" frames (128 TMEM lanes) x 30 "b"
+// frames (96 TMEM columns per weight class, 5 classes = 480 of 512 columns).
+constexpr int COL_BLOCKS_PER_TILE = 3;
+constexpr int COL_TILE_FRAMES = FRAMES_PER_BLOCK * COL_BLOCKS_PER_TILE;  // 30
+constexpr int COL_TILE_ROWS = ROWS_PER_BLOCK * COL_BLOCKS_PER_TILE;      // 96
 constexpr int K_CHUNK = 64;    // atoms (bytes of int8) per pipeline stage / swizzle row
 constexpr int NUM_SLICES = 3;  // signed 8-bit digits of the 24-bit fixed-point coordinate
 // int32 accumulators hold up to 3 slice products of magnitude <= 2^14 per atom.
@@ -62,7 +67,8 @@ struct loosb200_frames {
   int unit_log2 = 0;
   bool quantised = false;
   size_t rows_total = 0, Kpad = 0;
-  CUtensorMap tmap;  // 3-D map over q8: (atom, row, slice)
+  CUtensorMap tmapA;  // 3-D map over q8 (atom, row, slice), box 64 x 128 x 3
+  CUtensorMap tmapB;  // same tensor, box 64 x 96 x 3
   bool tmap_valid = false;
 
   cudaStream_t stream = nullptr;
@@ -80,6 +86,7 @@ struct PairJob {
   float* out;                 // device, may be null (stats only)
   size_t ld;
   // row blocks (of TILE_FRAMES frames of `a`) this launch covers, ascending
+  const uint32_t* rows_host;       // [n_row_tiles] same list on the host
   const uint32_t* row_tiles_dev;   // [n_row_tiles]
   const uint32_t* tile_prefix_dev; // [n_row_tiles+1] prefix sum of column tiles per row tile
   uint32_t n_row_tiles;

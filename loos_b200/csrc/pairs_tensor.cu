@@ -1,6 +1,436 @@
-// placeholder until the tcgen05 kernel lands
+// All-to-all RMSD on the 5th-generation tensor cores (tcgen05 / TMEM / TMA).
+//
+// The F x F frame-pair covariance (nine N-long inner products per pair, the
+// dgemm_ of src/alignment.cpp:34 for every pair at once) is one dense
+// contraction  C = A A^T  with A = (3F) x N.  fp32 accumulation cannot hold the
+// cancellation in Ga + Gb - 2 lambda, so the operands are
+// 24-bit fixed point split into three signed 8-bit digits and multiplied with
+// tcgen05.mma kind::i8: int32 accumulation is EXACT.  The nine digit products
+// fall into five weight classes s = p + q (weight 2^(8s)); products of one class
+// share an accumulator, so a tile needs 5 accumulators.
+//
+// Tile = 128 TMEM lanes x 96 columns per class:
+//   lane   = 32*blk + 3*jf + axis   -> "a" frame 10*blk + jf of the row tile (40 frames)
+//   column = 96*s + 32*g + 3*jb + axis' -> "b" frame 10*g + jb of the column tile (30 frames)
+// 5 x 96 = 480 of the 512 TMEM columns.  The three axes of one "a" frame sit in
+// three adjacent lanes of one warp, so the epilogue assembles each 3x3 with a few
+// warp shuffles and solves one pair per lane (QCP, qcp.cuh) straight out of TMEM:
+// covariance tiles never touch HBM.
+//
+// Warp roles (192 threads, 1 CTA per SM, persistent over a tile list):
+//   warp 0   TMA producer: per 64-atom K chunk one 3-D box for A (64 x 128 rows x
+//            3 digits = 24 KB) and one for B (64 x 96 x 3 = 18 KB), SWIZZLE_64B
+//   warp 1   TMEM allocator + MMA issuer: per 32-atom K step six tcgen05.mma
+//            (three with N = 192 spanning two adjacent classes, three with N = 96)
+//   warps 2-5 epilogue: tcgen05.ld -> exact integer combine in fp64 -> shuffle
+//            -> QCP -> float32 tile in smem -> coalesced (and mirrored) stores
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
+#include "qcp.cuh"
+
 namespace loosb200 {
-bool tensor_path_available() { return false; }
-int launch_pairs_tensor(const PairJob&, cudaStream_t, int*) { return LOOSB200_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int NUM_STAGES = 5;
+constexpr int A_STAGE_BYTES = NUM_SLICES * TILE_ROWS * K_CHUNK;      // 24576
+constexpr int B_STAGE_BYTES = NUM_SLICES * COL_TILE_ROWS * K_CHUNK;  // 18432
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;           // 43008
+constexpr int A_SLICE_BYTES = TILE_ROWS * K_CHUNK;                   // 8192
+constexpr int B_SLICE_BYTES = COL_TILE_ROWS * K_CHUNK;               // 6144
+constexpr int NUM_CLASSES = 5;
+constexpr int CLASS_COLS = COL_TILE_ROWS;  // 96
+constexpr int TMEM_COLS = 512;
+constexpr int NTHREADS = 192;
+constexpr int TPAD = TILE_FRAMES + 1;  // out tile row pitch (floats)
+
+struct __align__(8) SmemCtl {
+  unsigned long long full[NUM_STAGES];
+  unsigned long long empty[NUM_STAGES];
+  unsigned long long tmem_full;
+  unsigned long long tmem_empty;
+  uint32_t tmem_base;
+  uint32_t pad;
+  double gB[COL_TILE_FRAMES];
+  float T[COL_TILE_FRAMES][TPAD];  // T[b][a]
+  double red_sum[4], red_max[4];
+};
+
+constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + (int)sizeof(SmemCtl) + 1024;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+// Bounded wait: a protocol bug must trap, not hang the GPU box.
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
+  const uint32_t addr = smem_u32(b);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 2000;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    if (spin > (1u << 21)) __trap();  // ~4 s
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor,
+// cutlass mma_sm100_desc.hpp:98-121): start>>4 | LBO=1<<16 | SBO=(8 rows*64 B)>>4<<32
+// | version 1<<46 | layout SWIZZLE_64B(4)<<61.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed
+// int8, both K-major, M = 128, N = n.
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+struct TensorArgs {
+  const uint2* tiles;          // (row tile index within the launch, column tile J)
+  uint32_t n_tiles;
+  const uint32_t* row_tiles;   // row tile index -> I
+  const long long* gA; const long long* gB;
+  uint32_t FA, FB, N, n_kchunks;
+  int self, symmetric, packed;
+  double unit;                 // Angstrom per fixed-point unit
+  float* out; size_t ld;
+  double* stats;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const TensorArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  SmemCtl* ctl = (SmemCtl*)(smem + NUM_STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+    mbar_init(&ctl->tmem_full, 1);
+    mbar_init(&ctl->tmem_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+        const uint2 tl = a.tiles[t];
+        const int rowA = (int)a.row_tiles[tl.x] * TILE_ROWS;
+        const int rowB = (int)tl.y * COL_TILE_ROWS;
+        for (uint32_t kc = 0; kc < a.n_kchunks; ++kc) {
+          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          unsigned char* sA = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&ctl->full[stage], STAGE_BYTES);
+          tma_load_3d(sA, &mapA, &ctl->full[stage], (int)(kc * K_CHUNK), rowA, 0);
+          tma_load_3d(sA + A_STAGE_BYTES, &mapB, &ctl->full[stage], (int)(kc * K_CHUNK), rowB, 0);
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t ID192 = make_idesc(2 * CLASS_COLS), ID96 = make_idesc(CLASS_COLS);
+      uint32_t stage = 0, phase = 0, tphase = 0;
+      for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+        mbar_wait(&ctl->tmem_empty, tphase ^ 1);  // epilogue has drained the previous tile
+        tc_fence_after();
+        for (uint32_t kc = 0; kc < a.n_kchunks; ++kc) {
+          mbar_wait(&ctl->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sB = sA + A_STAGE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < K_CHUNK / 32; ++ks) {
+            const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
+            const uint64_t A0 = make_desc(sA + 0 * A_SLICE_BYTES + ks * 32);
+            const uint64_t A1 = make_desc(sA + 1 * A_SLICE_BYTES + ks * 32);
+            const uint64_t A2 = make_desc(sA + 2 * A_SLICE_BYTES + ks * 32);
+            const uint64_t B0 = make_desc(sB + 0 * B_SLICE_BYTES + ks * 32);
+            const uint64_t B1 = make_desc(sB + 1 * B_SLICE_BYTES + ks * 32);  // spans digits 1,2 when N = 192
+            // class s lives at columns [96 s, 96 s + 96); first touch of a class overwrites
+            tc_mma_i8(tmem_base + 3 * CLASS_COLS, A2, B1, ID192, first);  // a2.b1 -> s3, a2.b2 -> s4
+            tc_mma_i8(tmem_base + 1 * CLASS_COLS, A0, B1, ID192, first);  // a0.b1 -> s1, a0.b2 -> s2
+            tc_mma_i8(tmem_base + 0 * CLASS_COLS, A0, B0, ID96, first);   // a0.b0 -> s0
+            tc_mma_i8(tmem_base + 2 * CLASS_COLS, A1, B1, ID192, 1u);     // a1.b1 -> s2, a1.b2 -> s3
+            tc_mma_i8(tmem_base + 2 * CLASS_COLS, A2, B0, ID96, 1u);      // a2.b0 -> s2
+            tc_mma_i8(tmem_base + 1 * CLASS_COLS, A1, B0, ID96, 1u);      // a1.b0 -> s1
+          }
+          tc_commit(&ctl->empty[stage]);  // smem slot reusable once these MMAs have read it
+          if (kc + 1 == a.n_kchunks) tc_commit(&ctl->tmem_full);
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tphase ^= 1;
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp & 3;               // TMEM lane quarter == frame block of the row tile
+    const int et = (warp - 2) * 32 + lane;  // 0..127
+    const int jf = lane / 3, al = lane - 3 * jf;
+    const bool active = lane < 30;
+    const int a_local = q * FRAMES_PER_BLOCK + jf;
+    const int tri = lane - al;            // first lane of this frame's lane triple
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t tphase = 0;
+    double ssum = 0.0, smax = 0.0;
+    const double inv_n = 1.0 / (double)a.N;
+
+    for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+      const uint2 tl = a.tiles[t];
+      const uint32_t I = a.row_tiles[tl.x], J = tl.y;
+      const uint32_t i = I * TILE_FRAMES + a_local;
+      const bool i_ok = active && i < a.FA;
+      const double ga = i_ok ? (double)a.gA[i] : 0.0;
+      // previous tile's stores are done (barrier at the end of the loop body)
+      if (et < COL_TILE_FRAMES) {
+        const uint32_t j = J * COL_TILE_FRAMES + et;
+        ctl->gB[et] = j < a.FB ? (double)a.gB[j] : 0.0;
+      }
+      mbar_wait(&ctl->tmem_full, tphase);
+      tphase ^= 1;
+      tc_fence_after();
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // gB visible
+
+#pragma unroll 1
+      for (int g = 0; g < COL_BLOCKS_PER_TILE; ++g) {
+        double v[30];
+#pragma unroll
+        for (int c = 0; c < 30; ++c) v[c] = 0.0;
+#pragma unroll
+        for (int s = 0; s < NUM_CLASSES; ++s) {
+          uint32_t r[32];
+          tc_ld32(tlane + (uint32_t)(s * CLASS_COLS + g * 32), r);
+          tc_wait_ld();
+          const double w = (double)(1ull << (8 * s));
+#pragma unroll
+          for (int c = 0; c < 30; ++c) v[c] = fma((double)(int)r[c], w, v[c]);
+        }
+        if (g == COL_BLOCKS_PER_TILE - 1) {
+          // all of this warp's TMEM reads are complete: hand the accumulators back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->tmem_empty);
+        }
+#pragma unroll
+        for (int round = 0; round < 4; ++round) {
+          // lanes of a triple own pairs jb = 3*round + al (round 3: jb = 9, lane al == 0)
+          double own[3], s1[3], s2[3], R[9];
+          if (round < 3) {
+            const int d1 = (al + 2) % 3, d2 = (al + 1) % 3;  // destination axis served at shift 1, 2
+#pragma unroll
+            for (int be = 0; be < 3; ++be) {
+              const double x0 = v[9 * round + be], x1 = v[9 * round + 3 + be], x2 = v[9 * round + 6 + be];
+              own[be] = al == 0 ? x0 : (al == 1 ? x1 : x2);
+              s1[be] = d1 == 0 ? x0 : (d1 == 1 ? x1 : x2);
+              s2[be] = d2 == 0 ? x0 : (d2 == 1 ? x1 : x2);
+            }
+          } else {
+#pragma unroll
+            for (int be = 0; be < 3; ++be) own[be] = s1[be] = s2[be] = v[27 + be];
+          }
+          const int src1 = tri + (al + 1) % 3, src2 = tri + (al + 2) % 3;
+#pragma unroll
+          for (int be = 0; be < 3; ++be) {
+            R[be] = own[be];
+            R[3 + be] = __shfl_sync(0xffffffffu, s1[be], src1);
+            R[6 + be] = __shfl_sync(0xffffffffu, s2[be], src2);
+          }
+          const int jb = round < 3 ? 3 * round + al : 9;
+          const bool owner = active && (round < 3 || al == 0);
+          if (owner) {
+            const int b_local = g * FRAMES_PER_BLOCK + jb;
+            const uint32_t j = J * COL_TILE_FRAMES + b_local;
+            float val = -1.0f;  // "no entry"
+            if (i_ok && j < a.FB) {
+              if (a.self && j >= i) {
+                if (j == i) val = 0.0f;  // diagonal stays 0 (Tools/rmsds.cpp:359-365)
+              } else {
+                // rows of R are (al, al+1, al+2) mod 3: a cyclic relabelling of the axes
+                // of frame a is a proper rotation and leaves lambda_max unchanged
+                const double gb = ctl->gB[b_local];
+                const QcpResult qr = qcp_lambda(R, ga, gb);
+                const double msd = qr.msd_x2_over_e0 * 0.5 * (ga + gb) * inv_n;
+                val = (float)(a.unit * sqrt(msd));
+                ssum += (double)val;
+                smax = fmax(smax, (double)val);
+              }
+            }
+            ctl->T[b_local][a_local] = val;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // tile T complete
+      if (a.out) {
+        const size_t i0 = (size_t)I * TILE_FRAMES, j0 = (size_t)J * COL_TILE_FRAMES;
+        if (a.packed) {
+          // out[(rt*40 + a) * ld + j]: rows of the lower triangle, row-major
+          for (int idx = et; idx < TILE_FRAMES * COL_TILE_FRAMES; idx += 128) {
+            const int al_ = idx / COL_TILE_FRAMES, bl = idx - al_ * COL_TILE_FRAMES;
+            const float val = ctl->T[bl][al_];
+            if (val >= 0.0f) a.out[((size_t)tl.x * TILE_FRAMES + al_) * a.ld + j0 + bl] = val;
+          }
+        } else {
+          for (int idx = et; idx < TILE_FRAMES * COL_TILE_FRAMES; idx += 128) {
+            const int bl = idx / TILE_FRAMES, al_ = idx - bl * TILE_FRAMES;
+            const float val = ctl->T[bl][al_];
+            if (val >= 0.0f) a.out[(j0 + bl) * a.ld + i0 + al_] = val;  // M(i,j), column-major
+          }
+          if (a.symmetric) {
+            for (int idx = et; idx < TILE_FRAMES * COL_TILE_FRAMES; idx += 128) {
+              const int al_ = idx / COL_TILE_FRAMES, bl = idx - al_ * COL_TILE_FRAMES;
+              const float val = ctl->T[bl][al_];
+              if (val >= 0.0f) a.out[(i0 + al_) * a.ld + j0 + bl] = val;  // M(j,i)
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // T and gB free for the next tile
+    }
+    if (a.stats) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+        smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+      }
+      if (lane == 0) { ctl->red_sum[warp - 2] = ssum; ctl->red_max[warp - 2] = smax; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        double s = 0.0, m = 0.0;
+        for (int w = 0; w < 4; ++w) { s += ctl->red_sum[w]; m = fmax(m, ctl->red_max[w]); }
+        atomicAdd(&a.stats[0], s);
+        atomicMax(reinterpret_cast<unsigned long long*>(&a.stats[1]), (unsigned long long)__double_as_longlong(m));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+}  // namespace
+
+bool tensor_path_available() { return true; }
+
+// Tile order: super-blocks of SB_R row tiles x SB_C column tiles so that the ~150
+// tiles in flight share a few MB of operands in L2 (operand sets are larger than L2).
+int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
+  constexpr uint32_t SB_R = 12, SB_C = 16;
+  const loosb200_frames* A = job.a;
+  const loosb200_frames* B = job.b;
+  if (!A->quantised || !B->quantised || A->unit_log2 != B->unit_log2 || A->Kpad != B->Kpad)
+    return LOOSB200_ERR_INVALID;
+  const uint32_t FB = (uint32_t)B->F;
+  const uint32_t ncol = (FB + COL_TILE_FRAMES - 1) / COL_TILE_FRAMES;
+  std::vector<uint2> tiles;
+  for (uint32_t r0 = 0; r0 < job.n_row_tiles; r0 += SB_R) {
+    const uint32_t r1 = std::min(job.n_row_tiles, r0 + SB_R);
+    // columns needed by the last (largest) row tile of the group
+    uint32_t cmax = ncol;
+    if (job.self) {
+      const uint64_t last_i = (uint64_t)job.rows_host[r1 - 1] * TILE_FRAMES + TILE_FRAMES - 1;
+      cmax = std::min<uint32_t>(ncol, (uint32_t)(last_i / COL_TILE_FRAMES) + 1);
+    }
+    for (uint32_t c0 = 0; c0 < cmax; c0 += SB_C)
+      for (uint32_t r = r0; r < r1; ++r) {
+        uint32_t cend = std::min(cmax, c0 + SB_C);
+        if (job.self) {
+          const uint64_t last_i = (uint64_t)job.rows_host[r] * TILE_FRAMES + TILE_FRAMES - 1;
+          cend = std::min<uint32_t>(cend, (uint32_t)(last_i / COL_TILE_FRAMES) + 1);
+        }
+        for (uint32_t c = c0; c < cend; ++c) tiles.push_back(make_uint2(r, c));
+      }
+  }
+  if (tiles.empty()) return LOOSB200_OK;
+  if (tiles.size() > 0xfffffff0ull) return LOOSB200_ERR_UNSUPPORTED;
+
+  uint2* d_tiles = nullptr;
+  LB_CUDA(cudaMallocAsync(&d_tiles, sizeof(uint2) * tiles.size(), st));
+  LB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(uint2) * tiles.size(), cudaMemcpyHostToDevice, st));
+  // pageable source: the copy has been staged by the time the call returns
+
+  TensorArgs ta;
+  ta.tiles = d_tiles; ta.n_tiles = (uint32_t)tiles.size();
+  ta.row_tiles = job.row_tiles_dev;
+  ta.gA = A->gq; ta.gB = B->gq;
+  ta.FA = (uint32_t)A->F; ta.FB = FB; ta.N = (uint32_t)A->N;
+  ta.n_kchunks = (uint32_t)(A->Kpad / K_CHUNK);
+  ta.self = job.self; ta.symmetric = job.symmetric; ta.packed = job.packed_rows;
+  ta.unit = exp2((double)A->unit_log2);
+  ta.out = job.out; ta.ld = job.ld; ta.stats = job.stats_dev;
+
+  LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)std::min<size_t>((size_t)sms, tiles.size());
+  k_pairs_tensor<<<grid, NTHREADS, SMEM_BYTES, st>>>(A->tmapA, B->tmapB, ta);
+  LB_CUDA(cudaGetLastError());
+  LB_CUDA(cudaFreeAsync(d_tiles, st));
+  if (launches) *launches = 1;
+  return LOOSB200_OK;
+}
+
+}  // namespace loosb200

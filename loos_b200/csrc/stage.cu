@@ -177,7 +177,8 @@ int ensure_quantised(loosb200_frames* h, int force_unit_log2) {
   LB_CUDA(cudaSetDevice(h->device));
   const size_t nblocks = (h->F + FRAMES_PER_BLOCK - 1) / FRAMES_PER_BLOCK;
   const size_t ntiles = (nblocks + BLOCKS_PER_TILE - 1) / BLOCKS_PER_TILE;
-  h->rows_total = ntiles * TILE_ROWS;
+  // a 96-row B box may start at the last frame block: pad so that no box runs out of bounds
+  h->rows_total = ntiles * TILE_ROWS + TILE_ROWS;
   h->Kpad = ((h->N + K_CHUNK - 1) / K_CHUNK) * K_CHUNK;
   const size_t bytes = (size_t)NUM_SLICES * h->rows_total * h->Kpad;
   if (!h->q8) {
@@ -203,14 +204,16 @@ int ensure_quantised(loosb200_frames* h, int force_unit_log2) {
   if (!enc) { set_last_error("cuTensorMapEncodeTiled not available"); return LOOSB200_ERR_CUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)h->Kpad, (cuuint64_t)h->rows_total, (cuuint64_t)NUM_SLICES};
   cuuint64_t strides[2] = {(cuuint64_t)h->Kpad, (cuuint64_t)(h->rows_total * h->Kpad)};
-  cuuint32_t box[3] = {(cuuint32_t)K_CHUNK, (cuuint32_t)TILE_ROWS, (cuuint32_t)NUM_SLICES};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->q8, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
-    return LOOSB200_ERR_CUDA;
+  for (int which = 0; which < 2; ++which) {
+    cuuint32_t box[3] = {(cuuint32_t)K_CHUNK, (cuuint32_t)(which ? COL_TILE_ROWS : TILE_ROWS), (cuuint32_t)NUM_SLICES};
+    CUresult r = enc(which ? &h->tmapB : &h->tmapA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->q8, dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+      return LOOSB200_ERR_CUDA;
+    }
   }
   h->tmap_valid = true;
   return LOOSB200_OK;
