@@ -17,13 +17,19 @@
 // warp shuffles and solves one pair per lane (QCP, qcp.cuh) straight out of TMEM:
 // covariance tiles never touch HBM.
 //
-// Warp roles (192 threads, 1 CTA per SM, persistent over a tile list):
+// Warp roles (448 threads, 1 CTA per SM, persistent over a tile list):
 //   warp 0   TMA producer: per 64-atom K chunk one 3-D box for A (64 x 128 rows x
 //            3 digits = 24 KB) and one for B (64 x 96 x 3 = 18 KB), SWIZZLE_64B
 //   warp 1   TMEM allocator + MMA issuer: per 32-atom K step six tcgen05.mma
 //            (three with N = 192 spanning two adjacent classes, three with N = 96)
-//   warps 2-5 epilogue: tcgen05.ld -> exact integer combine in fp64 -> shuffle
-//            -> QCP -> float32 tile in smem -> coalesced (and mirrored) stores
+//   warps 2-13 epilogue, one (lane quarter, 10-frame column group) each:
+//            tcgen05.ld -> exact integer combine in fp64 -> TMEM handed back to the
+//            MMA warp -> shuffle -> QCP -> float32 tile in smem -> coalesced (and
+//            mirrored) stores.  Only the TMEM drain is serial with the MMAs of the
+//            next tile; the solves overlap them.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -43,7 +49,9 @@ constexpr int B_SLICE_BYTES = COL_TILE_ROWS * K_CHUNK;               // 6144
 constexpr int NUM_CLASSES = 5;
 constexpr int CLASS_COLS = COL_TILE_ROWS;  // 96
 constexpr int TMEM_COLS = 512;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 448;  // 2 control warps + 12 epilogue warps; 65536/448 -> 144 regs
+constexpr int NUM_EPI_WARPS = 12;
+constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;  // 384
 constexpr int TPAD = TILE_FRAMES + 1;  // out tile row pitch (floats)
 
 struct __align__(8) SmemCtl {
@@ -53,9 +61,8 @@ struct __align__(8) SmemCtl {
   unsigned long long tmem_empty;
   uint32_t tmem_base;
   uint32_t pad;
-  double gB[COL_TILE_FRAMES];
-  float T[COL_TILE_FRAMES][TPAD];  // T[b][a]
-  double red_sum[4], red_max[4];
+  float T[2][COL_TILE_FRAMES][TPAD];  // double-buffered out tile, T[.][b][a]
+  double red_sum[NUM_EPI_WARPS], red_max[NUM_EPI_WARPS];
 };
 
 constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + (int)sizeof(SmemCtl) + 1024;
@@ -130,6 +137,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+#define LB_TICK(slot)                                               \
+  do {                                                              \
+    if (a.prof) {                                                   \
+      const long long now__ = clock64();                           \
+      pacc[slot] += now__ - tprev;                                  \
+      tprev = now__;                                                \
+    }                                                               \
+  } while (0)
+
 struct TensorArgs {
   const uint2* tiles;          // (row tile index within the launch, column tile J)
   uint32_t n_tiles;
@@ -140,6 +156,7 @@ struct TensorArgs {
   double unit;                 // Angstrom per fixed-point unit
   float* out; size_t ld;
   double* stats;
+  long long* prof;  // optional [grid][14 warps][8] cycle counters (LOOSB200_PROF=1)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -153,7 +170,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
     mbar_init(&ctl->tmem_full, 1);
-    mbar_init(&ctl->tmem_empty, 4);
+    mbar_init(&ctl->tmem_empty, NUM_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -190,12 +207,16 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t ID192 = make_idesc(2 * CLASS_COLS), ID96 = make_idesc(CLASS_COLS);
       uint32_t stage = 0, phase = 0, tphase = 0;
+      long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      long long tprev = a.prof ? clock64() : 0;
       for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
         mbar_wait(&ctl->tmem_empty, tphase ^ 1);  // epilogue has drained the previous tile
         tc_fence_after();
+        LB_TICK(0);  // waiting for TMEM
         for (uint32_t kc = 0; kc < a.n_kchunks; ++kc) {
           mbar_wait(&ctl->full[stage], phase);
           tc_fence_after();
+          LB_TICK(1);  // waiting for operands
           const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sB = sA + A_STAGE_BYTES;
 #pragma unroll
@@ -217,134 +238,200 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tc_commit(&ctl->empty[stage]);  // smem slot reusable once these MMAs have read it
           if (kc + 1 == a.n_kchunks) tc_commit(&ctl->tmem_full);
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+          LB_TICK(2);  // issuing
         }
         tphase ^= 1;
       }
+      if (a.prof)
+        for (int k = 0; k < 8; ++k) a.prof[((size_t)blockIdx.x * 14 + warp) * 8 + k] = pacc[k];
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
-    const int q = warp & 3;               // TMEM lane quarter == frame block of the row tile
-    const int et = (warp - 2) * 32 + lane;  // 0..127
+    // ================= epilogue (warps 2..13) =================
+    const int q = warp & 3;                 // TMEM lane quarter == frame block of the row tile
+    const int g = (warp - 2) >> 2;          // 10-frame column group of the column tile
+    const int et = (warp - 2) * 32 + lane;  // 0..383
     const int jf = lane / 3, al = lane - 3 * jf;
     const bool active = lane < 30;
     const int a_local = q * FRAMES_PER_BLOCK + jf;
-    const int tri = lane - al;            // first lane of this frame's lane triple
-    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t tphase = 0;
+    const int tri = lane - al;              // first lane of this frame's lane triple
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 32);
+    uint32_t tphase = 0, buf = 0;
     double ssum = 0.0, smax = 0.0;
     const double inv_n = 1.0 / (double)a.N;
+    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = a.prof ? clock64() : 0;
 
-    for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x, buf ^= 1) {
       const uint2 tl = a.tiles[t];
       const uint32_t I = a.row_tiles[tl.x], J = tl.y;
       const uint32_t i = I * TILE_FRAMES + a_local;
       const bool i_ok = active && i < a.FA;
       const double ga = i_ok ? (double)a.gA[i] : 0.0;
-      // previous tile's stores are done (barrier at the end of the loop body)
-      if (et < COL_TILE_FRAMES) {
-        const uint32_t j = J * COL_TILE_FRAMES + et;
-        ctl->gB[et] = j < a.FB ? (double)a.gB[j] : 0.0;
-      }
       mbar_wait(&ctl->tmem_full, tphase);
       tphase ^= 1;
       tc_fence_after();
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // gB visible
+      LB_TICK(0);  // waiting for the accumulators
 
-#pragma unroll 1
-      for (int g = 0; g < COL_BLOCKS_PER_TILE; ++g) {
-        double v[30];
+      // ---- drain: v[3 jb + axis'] = sum_s 2^(8s) D_s, exact (|v| < 2^58 rounds at 2^-53) ----
+      double v[30];
 #pragma unroll
-        for (int c = 0; c < 30; ++c) v[c] = 0.0;
+      for (int c = 0; c < 30; ++c) v[c] = 0.0;
 #pragma unroll
-        for (int s = 0; s < NUM_CLASSES; ++s) {
-          uint32_t r[32];
-          tc_ld32(tlane + (uint32_t)(s * CLASS_COLS + g * 32), r);
-          tc_wait_ld();
-          const double w = (double)(1ull << (8 * s));
+      for (int s = 0; s < NUM_CLASSES; ++s) {
+        uint32_t r[32];
+        tc_ld32(tlane + (uint32_t)(s * CLASS_COLS), r);
+        tc_wait_ld();
+        // int32 -> double without the conversion unit: the bits (0x433+8s)<<52 | (D ^ 2^31)
+        // are the double 2^(52+8s) + (D + 2^31) 2^(8s); subtracting the bias leaves D 2^(8s).
+        const uint32_t hi = (uint32_t)(0x433 + 8 * s) << 20;
+        const double bias = __hiloint2double((int)hi, (int)0x80000000u);
 #pragma unroll
-          for (int c = 0; c < 30; ++c) v[c] = fma((double)(int)r[c], w, v[c]);
-        }
-        if (g == COL_BLOCKS_PER_TILE - 1) {
-          // all of this warp's TMEM reads are complete: hand the accumulators back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&ctl->tmem_empty);
-        }
+        for (int c = 0; c < 30; ++c)
+          v[c] += __hiloint2double((int)hi, (int)(r[c] ^ 0x80000000u)) - bias;
+      }
+      // this warp's TMEM reads are complete: hand the accumulators back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->tmem_empty);
+      LB_TICK(1);  // drain
+
+      // ---- exchange rows inside each lane triple, build the four quartics ----
+      // (everything from here on overlaps the next tile's MMAs)
+      QcpPoly poly[4];
+      double e0s[4];
+      int state[4];  // 0: no entry, 1: diagonal zero, 2: solve
 #pragma unroll
-        for (int round = 0; round < 4; ++round) {
-          // lanes of a triple own pairs jb = 3*round + al (round 3: jb = 9, lane al == 0)
-          double own[3], s1[3], s2[3], R[9];
-          if (round < 3) {
-            const int d1 = (al + 2) % 3, d2 = (al + 1) % 3;  // destination axis served at shift 1, 2
-#pragma unroll
-            for (int be = 0; be < 3; ++be) {
-              const double x0 = v[9 * round + be], x1 = v[9 * round + 3 + be], x2 = v[9 * round + 6 + be];
-              own[be] = al == 0 ? x0 : (al == 1 ? x1 : x2);
-              s1[be] = d1 == 0 ? x0 : (d1 == 1 ? x1 : x2);
-              s2[be] = d2 == 0 ? x0 : (d2 == 1 ? x1 : x2);
-            }
-          } else {
-#pragma unroll
-            for (int be = 0; be < 3; ++be) own[be] = s1[be] = s2[be] = v[27 + be];
-          }
-          const int src1 = tri + (al + 1) % 3, src2 = tri + (al + 2) % 3;
+      for (int round = 0; round < 4; ++round) {
+        // lanes of a triple own pairs jb = 3*round + al (round 3: jb = 9, lane al == 0)
+        double own[3], s1[3], s2[3], R[9];
+        if (round < 3) {
+          const int d1 = (al + 2) % 3, d2 = (al + 1) % 3;  // destination axis served at shift 1, 2
 #pragma unroll
           for (int be = 0; be < 3; ++be) {
-            R[be] = own[be];
-            R[3 + be] = __shfl_sync(0xffffffffu, s1[be], src1);
-            R[6 + be] = __shfl_sync(0xffffffffu, s2[be], src2);
+            const double x0 = v[9 * round + be], x1 = v[9 * round + 3 + be], x2 = v[9 * round + 6 + be];
+            own[be] = al == 0 ? x0 : (al == 1 ? x1 : x2);
+            s1[be] = d1 == 0 ? x0 : (d1 == 1 ? x1 : x2);
+            s2[be] = d2 == 0 ? x0 : (d2 == 1 ? x1 : x2);
           }
-          const int jb = round < 3 ? 3 * round + al : 9;
-          const bool owner = active && (round < 3 || al == 0);
-          if (owner) {
-            const int b_local = g * FRAMES_PER_BLOCK + jb;
-            const uint32_t j = J * COL_TILE_FRAMES + b_local;
-            float val = -1.0f;  // "no entry"
-            if (i_ok && j < a.FB) {
-              if (a.self && j >= i) {
-                if (j == i) val = 0.0f;  // diagonal stays 0 (Tools/rmsds.cpp:359-365)
-              } else {
-                // rows of R are (al, al+1, al+2) mod 3: a cyclic relabelling of the axes
-                // of frame a is a proper rotation and leaves lambda_max unchanged
-                const double gb = ctl->gB[b_local];
-                const QcpResult qr = qcp_lambda(R, ga, gb);
-                const double msd = qr.msd_x2_over_e0 * 0.5 * (ga + gb) * inv_n;
-                val = (float)(a.unit * sqrt(msd));
-                ssum += (double)val;
-                smax = fmax(smax, (double)val);
-              }
-            }
-            ctl->T[b_local][a_local] = val;
+        } else {
+#pragma unroll
+          for (int be = 0; be < 3; ++be) own[be] = s1[be] = s2[be] = v[27 + be];
+        }
+        const int src1 = tri + (al + 1) % 3, src2 = tri + (al + 2) % 3;
+#pragma unroll
+        for (int be = 0; be < 3; ++be) {
+          // rows of R end up as (al, al+1, al+2) mod 3: a cyclic relabelling of the axes of
+          // frame a is a proper rotation and leaves lambda_max unchanged
+          R[be] = own[be];
+          R[3 + be] = __shfl_sync(0xffffffffu, s1[be], src1);
+          R[6 + be] = __shfl_sync(0xffffffffu, s2[be], src2);
+        }
+        const int jb = round < 3 ? 3 * round + al : 9;
+        const uint32_t j = J * COL_TILE_FRAMES + g * FRAMES_PER_BLOCK + jb;
+        const bool owner = active && (round < 3 || al == 0);
+        int stt = 0;
+        double e0 = 1.0;
+        if (owner && i_ok && j < a.FB) {
+          if (a.self && j >= i) {
+            stt = (j == i) ? 1 : 0;  // diagonal stays 0 (Tools/rmsds.cpp:359-365)
+          } else {
+            e0 = 0.5 * (ga + (double)__ldg(a.gB + j));
+            stt = e0 > 0.0 ? 2 : 1;  // all atoms at the centroid in both frames: rmsd 0
           }
         }
+        if (stt != 2) {  // benign quartic for idle slots: keeps the lock-step loop finite
+          e0 = 1.0;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? (1.0 / 3.0) : 0.0;
+        }
+        state[round] = stt;
+        e0s[round] = e0;
+        poly[round] = qcp_poly(R, e0);
+        if (stt == 2 && !(fabs(poly[round].c0) < 1e30)) state[round] = 3;  // non-finite: safeguard
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // tile T complete
+      LB_TICK(2);  // exchange + quartic coefficients
+      // ---- four fp32 Newton recurrences in lock-step, warp-uniform exit ----
+      float tt[4];
+#pragma unroll
+      for (int r4 = 0; r4 < 4; ++r4) tt[r4] = poly[r4].t0;
+      for (int it = 0; it < 12; ++it) {
+        bool conv = true;
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+          const float st = qcp_newton_step((float)poly[r4].c0, (float)poly[r4].c1, (float)poly[r4].c2,
+                                           (float)poly[r4].c3, tt[r4]);
+          conv = conv && (fabsf(st) <= 4e-7f * fabsf(tt[r4]) + 1e-12f);
+        }
+        if (it >= 1 && __all_sync(0xffffffffu, conv)) break;
+      }
+      LB_TICK(3);  // Newton
+      // ---- fp64 polish, float32 result ----
+#pragma unroll
+      for (int round = 0; round < 4; ++round) {
+        const int jb = round < 3 ? 3 * round + al : 9;
+        const int b_local = g * FRAMES_PER_BLOCK + jb;
+        const bool owner = active && (round < 3 || al == 0);
+        float val = -1.0f;  // "no entry"
+        if (state[round] == 1) val = 0.0f;
+        if (state[round] >= 2) {
+          bool ok;
+          double y = qcp_polish(poly[round], tt[round], &ok);
+          if (!ok || state[round] == 3) {
+            // rare: multiple / far-off root.  Re-derive R is not possible here (registers were
+            // recycled), so the safeguard re-reads nothing: it solves the SAME quartic in fp64
+            // by bisection-safeguarded Newton from the upper bound.
+            const QcpPoly& pp = poly[round];
+            double td = pp.xform ? (double)pp.t0 : 0.0;
+            for (int it = 0; it < 200; ++it) {
+              const double fd = fma(td, fma(td, fma(td, td + pp.c3, pp.c2), pp.c1), pp.c0);
+              const double dd = fma(td, fma(td, fma(td, 4.0, 3.0 * pp.c3), 2.0 * pp.c2), pp.c1);
+              if (dd == 0.0) break;
+              const double stp = fd / dd;
+              td -= stp;
+              if (fabs(stp) <= 1e-15 * fabs(td) + 1e-300) break;
+            }
+            y = pp.xform ? 1.0 - td : td;
+            y = y < 0.0 ? -y : y;
+          }
+          val = (float)a.unit * sqrtf((float)(2.0 * y * e0s[round] * inv_n));
+          ssum += (double)val;
+          smax = fmax(smax, (double)val);
+        }
+        if (owner) ctl->T[buf][b_local][a_local] = val;
+      }
+      LB_TICK(4);  // polish
+      asm volatile("bar.sync 1, 384;" ::: "memory");  // tile T[buf] complete
+      LB_TICK(5);  // barrier
       if (a.out) {
         const size_t i0 = (size_t)I * TILE_FRAMES, j0 = (size_t)J * COL_TILE_FRAMES;
         if (a.packed) {
           // out[(rt*40 + a) * ld + j]: rows of the lower triangle, row-major
-          for (int idx = et; idx < TILE_FRAMES * COL_TILE_FRAMES; idx += 128) {
+          for (int idx = et; idx < TILE_FRAMES * COL_TILE_FRAMES; idx += NUM_EPI_THREADS) {
             const int al_ = idx / COL_TILE_FRAMES, bl = idx - al_ * COL_TILE_FRAMES;
-            const float val = ctl->T[bl][al_];
+            const float val = ctl->T[buf][bl][al_];
             if (val >= 0.0f) a.out[((size_t)tl.x * TILE_FRAMES + al_) * a.ld + j0 + bl] = val;
           }
         } else {
-          for (int idx = et; idx < TILE_FRAMES * COL_TILE_FRAMES; idx += 128) {
+          for (int idx = et; idx < TILE_FRAMES * COL_TILE_FRAMES; idx += NUM_EPI_THREADS) {
             const int bl = idx / TILE_FRAMES, al_ = idx - bl * TILE_FRAMES;
-            const float val = ctl->T[bl][al_];
+            const float val = ctl->T[buf][bl][al_];
             if (val >= 0.0f) a.out[(j0 + bl) * a.ld + i0 + al_] = val;  // M(i,j), column-major
           }
           if (a.symmetric) {
-            for (int idx = et; idx < TILE_FRAMES * COL_TILE_FRAMES; idx += 128) {
+            for (int idx = et; idx < TILE_FRAMES * COL_TILE_FRAMES; idx += NUM_EPI_THREADS) {
               const int al_ = idx / COL_TILE_FRAMES, bl = idx - al_ * COL_TILE_FRAMES;
-              const float val = ctl->T[bl][al_];
+              const float val = ctl->T[buf][bl][al_];
               if (val >= 0.0f) a.out[(i0 + al_) * a.ld + j0 + bl] = val;  // M(j,i)
             }
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // T and gB free for the next tile
+      LB_TICK(6);  // stores
+      // no second barrier: the next tile writes T[buf ^ 1]; T[buf] is rewritten two tiles
+      // later, after every thread has passed the next tile's barrier
     }
+    if (a.prof && lane == 0)
+      for (int k = 0; k < 8; ++k) a.prof[((size_t)blockIdx.x * 14 + warp) * 8 + k] = pacc[k];
     if (a.stats) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -352,11 +439,11 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, o));
       }
       if (lane == 0) { ctl->red_sum[warp - 2] = ssum; ctl->red_max[warp - 2] = smax; }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 384;" ::: "memory");
       if (et == 0) {
-        double s = 0.0, m = 0.0;
-        for (int w = 0; w < 4; ++w) { s += ctl->red_sum[w]; m = fmax(m, ctl->red_max[w]); }
-        atomicAdd(&a.stats[0], s);
+        double sm = 0.0, m = 0.0;
+        for (int w = 0; w < NUM_EPI_WARPS; ++w) { sm += ctl->red_sum[w]; m = fmax(m, ctl->red_max[w]); }
+        atomicAdd(&a.stats[0], sm);
         atomicMax(reinterpret_cast<unsigned long long*>(&a.stats[1]), (unsigned long long)__double_as_longlong(m));
       }
     }
@@ -420,14 +507,34 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   ta.self = job.self; ta.symmetric = job.symmetric; ta.packed = job.packed_rows;
   ta.unit = exp2((double)A->unit_log2);
   ta.out = job.out; ta.ld = job.ld; ta.stats = job.stats_dev;
+  ta.prof = nullptr;
+  const bool want_prof = getenv("LOOSB200_PROF") != nullptr;
 
   LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)std::min<size_t>((size_t)sms, tiles.size());
+  if (want_prof) {
+    LB_CUDA(cudaMalloc(&ta.prof, sizeof(long long) * grid * 14 * 8));
+    LB_CUDA(cudaMemsetAsync(ta.prof, 0, sizeof(long long) * grid * 14 * 8, st));
+  }
   k_pairs_tensor<<<grid, NTHREADS, SMEM_BYTES, st>>>(A->tmapA, B->tmapB, ta);
   LB_CUDA(cudaGetLastError());
+  if (want_prof) {
+    std::vector<long long> hp((size_t)grid * 14 * 8);
+    LB_CUDA(cudaMemcpyAsync(hp.data(), ta.prof, sizeof(long long) * hp.size(), cudaMemcpyDeviceToHost, st));
+    LB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(ta.prof);
+    const char* names_e[7] = {"wait_acc", "drain", "exch+poly", "newton", "polish", "barrier", "stores"};
+    const char* names_m[3] = {"wait_tmem", "wait_operands", "issue"};
+    const double ntl = (double)tiles.size() / grid;
+    fprintf(stderr, "[loosb200 prof] tiles/CTA %.1f  cycles per tile (mean over CTAs):\n  MMA warp:", ntl);
+    for (int k = 0; k < 3; ++k) { double s = 0; for (unsigned c = 0; c < grid; ++c) s += hp[((size_t)c * 14 + 1) * 8 + k]; fprintf(stderr, " %s=%.0f", names_m[k], s / grid / ntl); }
+    fprintf(stderr, "\n  epilogue warps:");
+    for (int k = 0; k < 7; ++k) { double s = 0; for (unsigned c = 0; c < grid; ++c) for (int w = 2; w < 14; ++w) s += hp[((size_t)c * 14 + w) * 8 + k]; fprintf(stderr, " %s=%.0f", names_e[k], s / grid / 12 / ntl); }
+    fprintf(stderr, "\n");
+  }
   LB_CUDA(cudaFreeAsync(d_tiles, st));
   if (launches) *launches = 1;
   return LOOSB200_OK;

@@ -21,6 +21,13 @@
 #else
 #define LB_HD static inline
 #endif
+#if defined(__CUDA_ARCH__)
+#define LB_FDIV(a, b) __fdividef((a), (b))
+#define LB_FRCP(a) __frcp_rn(a)
+#else
+#define LB_FDIV(a, b) ((a) / (b))
+#define LB_FRCP(a) (1.0f / (a))
+#endif
 
 namespace loosb200 {
 
@@ -130,7 +137,7 @@ LB_HD QcpResult qcp_lambda(const double* R, double ga, double gb) {
           (-(SxymSyx) * (SyzpSzy) + (SxzmSzx) * (SxxpSyy - Szz));
 
   // Newton from x0 = 1 >= x_max: monotone from above for a quartic with real roots.
-  double x = 1.0;
+  double x = fmin(1.0, sqrt(fmax(0.0, -1.5 * C2)) * (1.0 + 1e-12));
   int it = 0;
   bool ok = false;
   for (; it < 64; ++it) {
@@ -157,6 +164,104 @@ LB_HD QcpResult qcp_lambda(const double* R, double ga, double gb) {
   out.iters = it;
   out.msd_x2_over_e0 = fabs(2.0 * (1.0 - x));  // |E0 - 2 ss| / E0  (alignment.cpp:137 abs())
   return out;
+}
+
+// Fast path of the same solve for the per-pair epilogue of the tensor kernel.
+// With x = 1 - y the quartic becomes Q(y) = P(1 - y) = y^4 + q3 y^3 + q2 y^2 + q1 y + q0
+// whose smallest root y* = 1 - lambda_max/E0 = (Ga + Gb - 2 lambda)/(Ga + Gb) is the
+// quantity wanted, so the cancellation is confined to q0, q1 (computed in fp64);
+// Newton from y = 0 then only needs RELATIVE accuracy in y and runs in fp32, and
+// one fp64 correction step (with an fp32 reciprocal) restores full precision.
+// Returns y* (>= 0); sets *ok = false when the iteration has not settled
+// (multiple root / far-off root), in which case the caller takes qcp_lambda().
+// The same fast path split into phases so that a thread can run several solves
+// in lock-step (the tensor-core epilogue interleaves four: the Newton recurrences
+// are strictly serial, and only independent solves can fill their latency).
+struct QcpPoly {
+  double c0, c1, c2, c3;  // monic quartic t^4 + c3 t^3 + c2 t^2 + c1 t + c0 in t = x or y = 1 - x
+  float t0;               // Newton start (an upper bound of the root in x, 0 in y)
+  bool xform;
+};
+
+LB_HD QcpPoly qcp_poly(const double* R, double e0) {
+  double inv = (double)LB_FRCP((float)e0);
+  inv = inv * (2.0 - e0 * inv);
+  inv = inv * (2.0 - e0 * inv);
+  const double Sxx = R[0] * inv, Sxy = R[1] * inv, Sxz = R[2] * inv;
+  const double Syx = R[3] * inv, Syy = R[4] * inv, Syz = R[5] * inv;
+  const double Szx = R[6] * inv, Szy = R[7] * inv, Szz = R[8] * inv;
+  const double Sxx2 = Sxx * Sxx, Syy2 = Syy * Syy, Szz2 = Szz * Szz;
+  const double Sxy2 = Sxy * Sxy, Syz2 = Syz * Syz, Sxz2 = Sxz * Sxz;
+  const double Syx2 = Syx * Syx, Szy2 = Szy * Szy, Szx2 = Szx * Szx;
+  const double SyzSzymSyySzz2 = 2.0 * (Syz * Szy - Syy * Szz);
+  const double Sxx2Syy2Szz2Syz2Szy2 = Syy2 + Szz2 - Sxx2 + Syz2 + Szy2;
+  const double C2 = -2.0 * (Sxx2 + Syy2 + Szz2 + Sxy2 + Syx2 + Sxz2 + Szx2 + Syz2 + Szy2);
+  const double C1 = 8.0 * (Sxx * Syz * Szy + Syy * Szx * Sxz + Szz * Sxy * Syx -
+                           Sxx * Syy * Szz - Syz * Szx * Sxy - Szy * Syx * Sxz);
+  const double SxzpSzx = Sxz + Szx, SyzpSzy = Syz + Szy, SxypSyx = Sxy + Syx;
+  const double SyzmSzy = Syz - Szy, SxzmSzx = Sxz - Szx, SxymSyx = Sxy - Syx;
+  const double SxxpSyy = Sxx + Syy, SxxmSyy = Sxx - Syy;
+  const double Sxy2Sxz2Syx2Szx2 = Sxy2 + Sxz2 - Syx2 - Szx2;
+  const double C0 =
+      Sxy2Sxz2Syx2Szx2 * Sxy2Sxz2Syx2Szx2 +
+      (Sxx2Syy2Szz2Syz2Szy2 + SyzSzymSyySzz2) * (Sxx2Syy2Szz2Syz2Szy2 - SyzSzymSyySzz2) +
+      (-(SxzpSzx) * (SyzmSzy) + (SxymSyx) * (SxxmSyy - Szz)) *
+          (-(SxzmSzx) * (SyzpSzy) + (SxymSyx) * (SxxmSyy + Szz)) +
+      (-(SxzpSzx) * (SyzpSzy) - (SxypSyx) * (SxxpSyy - Szz)) *
+          (-(SxzmSzx) * (SyzmSzy) - (SxypSyx) * (SxxpSyy + Szz)) +
+      (+(SxypSyx) * (SyzpSzy) + (SxzpSzx) * (SxxmSyy + Szz)) *
+          (-(SxymSyx) * (SyzmSzy) + (SxzpSzx) * (SxxpSyy + Szz)) +
+      (+(SxypSyx) * (SyzmSzy) + (SxzmSzx) * (SxxmSyy - Szz)) *
+          (-(SxymSyx) * (SyzpSzy) + (SxzmSzx) * (SxxpSyy - Szz));
+  QcpPoly p;
+  const float xb = sqrtf(fmaxf(0.0f, -1.5f * (float)C2)) * 1.000001f;
+  p.xform = xb < 0.5f;
+  p.c0 = p.xform ? C0 : ((1.0 + C2) + C1) + C0;
+  p.c1 = p.xform ? C1 : (-4.0 - 2.0 * C2) - C1;
+  p.c2 = p.xform ? C2 : 6.0 + C2;
+  p.c3 = p.xform ? 0.0 : -4.0;
+  p.t0 = p.xform ? xb : 0.0f;
+  return p;
+}
+
+// One fp32 Newton step on t; returns the step taken.
+LB_HD float qcp_newton_step(float f0, float f1, float f2, float f3, float& t) {
+  const float f = fmaf(t, fmaf(t, fmaf(t, t + f3, f2), f1), f0);
+  const float df = fmaf(t, fmaf(t, fmaf(t, 4.0f, 3.0f * f3), 2.0f * f2), f1);
+  const float st = LB_FDIV(f, df);
+  t -= st;
+  return st;
+}
+
+// Two fp64 residual corrections; returns y = 1 - lambda_max / E0 (>= 0) and whether it settled.
+LB_HD double qcp_polish(const QcpPoly& p, float t, bool* ok) {
+  const float f1 = (float)p.c1, f2 = (float)p.c2, f3 = (float)p.c3;
+  double td = (double)t, corr = 0.0;
+  float df = 0.0f;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const float tf = (float)td;
+    const double fd = fma(td, fma(td, fma(td, td + p.c3, p.c2), p.c1), p.c0);
+    df = fmaf(tf, fmaf(tf, fmaf(tf, 4.0f, 3.0f * f3), 2.0f * f2), f1);
+    corr = fd * (double)LB_FRCP(df);
+    td -= corr;
+  }
+  const double yn = p.xform ? 1.0 - td : td;
+  *ok = (fabs(corr) <= 1e-6 * fabs(td) + 1e-14) && (p.xform ? df > 0.0f : df < 0.0f) && (yn == yn) &&
+        (yn <= 1.0 + 1e-9);
+  return yn < 0.0 ? -yn : yn;
+}
+
+#ifndef QCP_FAST_ITERS
+#define QCP_FAST_ITERS 10
+#endif
+// Scalar composition of the phases above (used by host-side unit tests).
+LB_HD double qcp_y_fast(const double* R, double e0, bool* ok) {
+  const QcpPoly p = qcp_poly(R, e0);
+  const float f0 = (float)p.c0, f1 = (float)p.c1, f2 = (float)p.c2, f3 = (float)p.c3;
+  float t = p.t0;
+  for (int it = 0; it < QCP_FAST_ITERS; ++it) qcp_newton_step(f0, f1, f2, f3, t);
+  return qcp_polish(p, t, ok);
 }
 
 // rmsd = sqrt(|Ga + Gb - 2 lambda| / n) scaled by `unit` (length of one operand unit).

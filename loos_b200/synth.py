@@ -207,3 +207,60 @@ def write_dcd(path, coords, with_crystal=False, big_endian=False, header_nframes
                 fh.write(xtal)
             for k in range(3):
                 fh.write(rec); fh.write(coords[f, :, k].astype(fdt).tobytes()); fh.write(rec)
+
+
+def synth_frames_torch(F, N, seed=SEED0, device="cuda", chunk=8192):
+    """Same model as synth_frames(), generated with torch on `device` (different
+    random stream; used for the large benchmark workloads).  (F, N, 3) float32."""
+    import math
+
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    dd = dict(device=device, dtype=torch.float64)
+    rg = 2.2 * N ** 0.38
+    base = torch.randn((N, 3), generator=g, **dd) * (rg / math.sqrt(3.0))
+    modes = torch.randn((N_MODES, N, 3), generator=g, **dd)
+    modes = modes / torch.sqrt((modes ** 2).sum(dim=(1, 2), keepdim=True) / N)
+    rho = 0.999
+    sig = 3.0 / torch.sqrt(torch.arange(N_MODES, **dd) + 1.0)
+    # AR(1) via blocked scan: a_f = rho^(f-f0) a_f0 + sum rho^(f-k) e_k, done in blocks of B
+    B = 1024
+    nb = (F + B - 1) // B
+    e = torch.randn((nb * B, N_MODES), generator=g, **dd) * math.sqrt(1 - rho * rho)
+    e[0] = torch.randn((N_MODES,), generator=g, **dd)
+    pw = rho ** torch.arange(B, **dd)
+    # lower-triangular Toeplitz of powers
+    idx = torch.arange(B, device=device)
+    Tm = torch.where(idx[:, None] >= idx[None, :], rho ** (idx[:, None] - idx[None, :]).to(torch.float64),
+                     torch.zeros((), **dd))
+    loc = torch.einsum("ij,bjm->bim", Tm, e.view(nb, B, N_MODES))
+    amp = torch.empty((nb, B, N_MODES), **dd)
+    carry = torch.zeros((N_MODES,), **dd)
+    for b in range(nb):
+        amp[b] = loc[b] + (pw * rho)[:, None] * carry[None, :]
+        carry = amp[b, -1]
+    amp = amp.view(nb * B, N_MODES)[:F] * sig[None, :]
+    # rotation random walk: cumulative product by recursive doubling
+    v = torch.randn((F, 3), generator=g, **dd) * (math.radians(2.0) / math.sqrt(3.0))
+    v[0] = torch.randn((3,), generator=g, **dd) * 2.0
+    th = v.norm(dim=1)
+    k = v / torch.where(th > 0, th, torch.ones_like(th))[:, None]
+    K = torch.zeros((F, 3, 3), **dd)
+    K[:, 0, 1], K[:, 0, 2] = -k[:, 2], k[:, 1]
+    K[:, 1, 0], K[:, 1, 2] = k[:, 2], -k[:, 0]
+    K[:, 2, 0], K[:, 2, 1] = -k[:, 1], k[:, 0]
+    R = torch.eye(3, **dd)[None] + torch.sin(th)[:, None, None] * K + (1 - torch.cos(th))[:, None, None] * (K @ K)
+    shift = 1
+    while shift < F:
+        R = torch.cat([R[:shift], R[shift:] @ R[:-shift]], dim=0)
+        shift *= 2
+    trans = torch.randn((F, 3), generator=g, **dd) * 5.0
+    out = torch.empty((F, N, 3), device=device, dtype=torch.float32)
+    for lo in range(0, F, chunk):
+        hi = min(F, lo + chunk)
+        x = base[None] + torch.einsum("fm,mnj->fnj", amp[lo:hi], modes)
+        x = x + torch.randn(x.shape, generator=g, **dd) * 0.3
+        x = torch.einsum("fij,fnj->fni", R[lo:hi], x) + trans[lo:hi, None, :]
+        out[lo:hi] = x.to(torch.float32)
+    return out
