@@ -1,0 +1,66 @@
+"""Multi-GPU work splitting for the all-to-all path: one process per GPU, static
+split of the 40-frame row tiles of the lower triangle, no collective while computing.
+
+    rows, block, stats = local_part(fs, rank, world)      # this rank's packed rows
+    M = gather_matrix(rows, block, F, rank, world)        # optional: whole matrix on rank 0
+
+Works with any torch.distributed backend (NCCL on the GPU box, gloo in the CPU tests;
+the compute call itself needs a GPU)."""
+import numpy as np
+
+from . import api
+
+PAD = 0xFFFFFFFF
+
+
+def local_part(fs, rank, world, out=None, noout=False, engine="auto"):
+    return api.rmsds_part(fs, rank, world, out=out, noout=noout, engine=engine)
+
+
+def assemble(parts, F):
+    """parts: iterable of (rows, block) from every rank -> full symmetric (F, F) float32
+    matrix (Fortran order, like the reference's RealMatrix), diagonal 0."""
+    M = np.zeros((F, F), dtype=np.float32, order="F")
+    for rows, block in parts:
+        rows = np.asarray(rows)
+        block = np.asarray(block)
+        for r, i in enumerate(rows):
+            if i == PAD or i == 0:
+                continue
+            M[i, :i] = block[r, :i]
+    M += M.T
+    return M
+
+
+def merge_stats(stats_list):
+    tot = sum(s["sum"] for s in stats_list)
+    cnt = sum(s["count"] for s in stats_list)
+    return {"max": max(s["max"] for s in stats_list), "sum": tot, "count": cnt, "avg": tot / cnt if cnt else 0.0}
+
+
+def gather_matrix(rows, block, F, rank, world, group=None):
+    """Gather every rank's row blocks on rank 0 and assemble the matrix there
+    (the only communication of the path: 'final gather of row blocks')."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return assemble([(rows, block)], F)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t_rows = torch.as_tensor(np.asarray(rows).astype(np.int64), device=dev)
+    t_blk = torch.as_tensor(np.asarray(block), device=dev) if not hasattr(block, "is_cuda") else block.to(dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([t_rows.numel()], dtype=torch.int64, device=dev), group=group)
+    sizes = [int(s.item()) for s in sizes]
+    if rank == 0:
+        parts = [(t_rows.cpu().numpy(), t_blk.cpu().numpy())]
+        for src in range(1, world):
+            r = torch.empty(sizes[src], dtype=torch.int64, device=dev)
+            b = torch.empty((sizes[src], F), dtype=torch.float32, device=dev)
+            dist.recv(r, src=src, group=group)
+            dist.recv(b, src=src, group=group)
+            parts.append((r.cpu().numpy(), b.cpu().numpy()))
+        return assemble([(np.where(r < 0, PAD, r).astype(np.uint32), b) for r, b in parts], F)
+    dist.send(t_rows, dst=0, group=group)
+    dist.send(t_blk.contiguous(), dst=0, group=group)
+    return None
