@@ -79,18 +79,23 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t b
 __device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
-// Bounded wait: a protocol bug must trap, not hang the GPU box.
+// Bounded wait: a protocol bug must trap, not hang the GPU box.  A waiting warp backs
+// off with nanosleep so that its polling does not eat the issue slots of the epilogue
+// warps sharing its scheduler (the two control warps executed 39 % of all
+// instructions of the kernel before this was added).
+template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
   const uint32_t addr = smem_u32(b);
   for (uint32_t spin = 0;; ++spin) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 2000;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     if (done) return;
-    if (spin > (1u << 21)) __trap();  // ~4 s
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    if (spin > (1u << 24)) __trap();  // seconds
   }
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar,
@@ -156,6 +161,7 @@ struct TensorArgs {
   double unit;                 // Angstrom per fixed-point unit
   float* out; size_t ld;
   double* stats;
+  int release_at;  // when the epilogue hands TMEM back (see kernel)
   long long* prof;  // optional [grid][14 warps][8] cycle counters (LOOSB200_PROF=1)
 };
 
@@ -193,7 +199,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int rowA = (int)a.row_tiles[tl.x] * TILE_ROWS;
         const int rowB = (int)tl.y * COL_TILE_ROWS;
         for (uint32_t kc = 0; kc < a.n_kchunks; ++kc) {
-          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          mbar_wait<200>(&ctl->empty[stage], phase ^ 1);
           unsigned char* sA = smem + stage * STAGE_BYTES;
           mbar_expect_tx(&ctl->full[stage], STAGE_BYTES);
           tma_load_3d(sA, &mapA, &ctl->full[stage], (int)(kc * K_CHUNK), rowA, 0);
@@ -210,11 +216,11 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       long long tprev = a.prof ? clock64() : 0;
       for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
-        mbar_wait(&ctl->tmem_empty, tphase ^ 1);  // epilogue has drained the previous tile
+        mbar_wait<100>(&ctl->tmem_empty, tphase ^ 1);  // epilogue has drained the previous tile
         tc_fence_after();
         LB_TICK(0);  // waiting for TMEM
         for (uint32_t kc = 0; kc < a.n_kchunks; ++kc) {
-          mbar_wait(&ctl->full[stage], phase);
+          mbar_wait<20>(&ctl->full[stage], phase);
           tc_fence_after();
           LB_TICK(1);  // waiting for operands
           const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
@@ -258,6 +264,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint32_t tphase = 0, buf = 0;
     double ssum = 0.0, smax = 0.0;
     const double inv_n = 1.0 / (double)a.N;
+    const int release_at = a.release_at;  // 0 after drain, 1 after fp64 coefficients, 2 after Newton, 3 after polish
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = a.prof ? clock64() : 0;
 
@@ -267,7 +274,13 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t i = I * TILE_FRAMES + a_local;
       const bool i_ok = active && i < a.FA;
       const double ga = i_ok ? (double)a.gA[i] : 0.0;
-      mbar_wait(&ctl->tmem_full, tphase);
+      long long gbq[4];  // G of the four "b" frames this lane solves against (prefetched)
+#pragma unroll
+      for (int round = 0; round < 4; ++round) {
+        const uint32_t j = J * COL_TILE_FRAMES + g * FRAMES_PER_BLOCK + (round < 3 ? 3 * round + al : 9);
+        gbq[round] = j < a.FB ? __ldg(a.gB + j) : 0;
+      }
+      mbar_wait<50>(&ctl->tmem_full, tphase);
       tphase ^= 1;
       tc_fence_after();
       LB_TICK(0);  // waiting for the accumulators
@@ -289,17 +302,18 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int c = 0; c < 30; ++c)
           v[c] += __hiloint2double((int)hi, (int)(r[c] ^ 0x80000000u)) - bias;
       }
-      // this warp's TMEM reads are complete: hand the accumulators back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl->tmem_empty);
+      tc_fence_before();  // this warp's TMEM reads are complete
+      if (release_at == 0) { __syncwarp(); if (lane == 0) mbar_arrive(&ctl->tmem_empty); }
       LB_TICK(1);  // drain
 
-      // ---- exchange rows inside each lane triple, build the four quartics ----
-      // (everything from here on overlaps the next tile's MMAs)
+      // ---- fp64 phase: exchange rows inside each lane triple, build the four quartics ----
+      // On sm_100 CUDA-core fp64 shares the tensor pipe with tcgen05.mma and gets ~10 % of
+      // its throughput while MMAs run (tools/ubench_contend.cu), so the accumulators are
+      // handed back only AFTER the fp64-heavy part; the fp32 Newton recurrences, the
+      // final correction and the stores then overlap the next tile's MMAs.
       QcpPoly poly[4];
       double e0s[4];
-      int state[4];  // 0: no entry, 1: diagonal zero, 2: solve
+      int state[4];  // 0: no entry, 1: zero, 2: solve
 #pragma unroll
       for (int round = 0; round < 4; ++round) {
         // lanes of a triple own pairs jb = 3*round + al (round 3: jb = 9, lane al == 0)
@@ -335,51 +349,55 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (a.self && j >= i) {
             stt = (j == i) ? 1 : 0;  // diagonal stays 0 (Tools/rmsds.cpp:359-365)
           } else {
-            e0 = 0.5 * (ga + (double)__ldg(a.gB + j));
-            stt = e0 > 0.0 ? 2 : 1;  // all atoms at the centroid in both frames: rmsd 0
+            e0 = 0.5 * (ga + (double)gbq[round]);
+            stt = e0 > 0.0 ? 2 : 1;  // every atom at the centroid in both frames: rmsd 0
           }
         }
-        if (stt != 2) {  // benign quartic for idle slots: keeps the lock-step loop finite
+        if (stt != 2) {  // benign quartic for idle slots: keeps the lock-step loop short
           e0 = 1.0;
 #pragma unroll
           for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? (1.0 / 3.0) : 0.0;
         }
         state[round] = stt;
-        e0s[round] = e0;
+        e0s[round] = 2.0 * e0 * inv_n;  // msd = y * this
         poly[round] = qcp_poly(R, e0);
-        if (stt == 2 && !(fabs(poly[round].c0) < 1e30)) state[round] = 3;  // non-finite: safeguard
       }
-      LB_TICK(2);  // exchange + quartic coefficients
+      if (release_at == 1) { __syncwarp(); if (lane == 0) mbar_arrive(&ctl->tmem_empty); }
+      LB_TICK(2);  // exchange + quartic coefficients (fp64)
+
       // ---- four fp32 Newton recurrences in lock-step, warp-uniform exit ----
-      float tt[4];
+      float tt[4], ls[4], fc[4][4];
 #pragma unroll
-      for (int r4 = 0; r4 < 4; ++r4) tt[r4] = poly[r4].t0;
+      for (int r4 = 0; r4 < 4; ++r4) {
+        tt[r4] = poly[r4].t0; ls[r4] = 0.0f;
+        fc[r4][0] = (float)poly[r4].c0; fc[r4][1] = (float)poly[r4].c1;
+        fc[r4][2] = (float)poly[r4].c2; fc[r4][3] = (float)poly[r4].c3;
+      }
       for (int it = 0; it < 12; ++it) {
         bool conv = true;
 #pragma unroll
         for (int r4 = 0; r4 < 4; ++r4) {
-          const float st = qcp_newton_step((float)poly[r4].c0, (float)poly[r4].c1, (float)poly[r4].c2,
-                                           (float)poly[r4].c3, tt[r4]);
-          conv = conv && (fabsf(st) <= 4e-7f * fabsf(tt[r4]) + 1e-12f);
+          ls[r4] = qcp_newton_step(fc[r4][0], fc[r4][1], fc[r4][2], fc[r4][3], tt[r4]);
+          conv = conv && (fabsf(ls[r4]) <= 4e-7f * fabsf(tt[r4]) + 1e-12f);
         }
         if (it >= 1 && __all_sync(0xffffffffu, conv)) break;
       }
-      LB_TICK(3);  // Newton
-      // ---- fp64 polish, float32 result ----
+      if (release_at == 2) { __syncwarp(); if (lane == 0) mbar_arrive(&ctl->tmem_empty); }
+      LB_TICK(3);  // Newton (fp32)
+
+      // ---- one fp64 residual correction per pair, float32 result ----
 #pragma unroll
       for (int round = 0; round < 4; ++round) {
         const int jb = round < 3 ? 3 * round + al : 9;
         const int b_local = g * FRAMES_PER_BLOCK + jb;
         const bool owner = active && (round < 3 || al == 0);
-        float val = -1.0f;  // "no entry"
-        if (state[round] == 1) val = 0.0f;
-        if (state[round] >= 2) {
+        float val = state[round] == 1 ? 0.0f : -1.0f;  // -1: "no entry"
+        if (state[round] == 2) {
           bool ok;
-          double y = qcp_polish(poly[round], tt[round], &ok);
-          if (!ok || state[round] == 3) {
-            // rare: multiple / far-off root.  Re-derive R is not possible here (registers were
-            // recycled), so the safeguard re-reads nothing: it solves the SAME quartic in fp64
-            // by bisection-safeguarded Newton from the upper bound.
+          double y = qcp_polish(poly[round], tt[round], ls[round], &ok);
+          if (!ok || !(fabs(poly[round].c0) < 1e30)) {
+            // rare (multiple / far-off root, non-finite input): the same quartic in fp64,
+            // Newton from the upper bound
             const QcpPoly& pp = poly[round];
             double td = pp.xform ? (double)pp.t0 : 0.0;
             for (int it = 0; it < 200; ++it) {
@@ -393,12 +411,13 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             y = pp.xform ? 1.0 - td : td;
             y = y < 0.0 ? -y : y;
           }
-          val = (float)a.unit * sqrtf((float)(2.0 * y * e0s[round] * inv_n));
+          val = (float)a.unit * sqrtf((float)(y * e0s[round]));
           ssum += (double)val;
           smax = fmax(smax, (double)val);
         }
         if (owner) ctl->T[buf][b_local][a_local] = val;
       }
+      if (release_at == 3) { __syncwarp(); if (lane == 0) mbar_arrive(&ctl->tmem_empty); }
       LB_TICK(4);  // polish
       asm volatile("bar.sync 1, 384;" ::: "memory");  // tile T[buf] complete
       LB_TICK(5);  // barrier
@@ -508,6 +527,7 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   ta.unit = exp2((double)A->unit_log2);
   ta.out = job.out; ta.ld = job.ld; ta.stats = job.stats_dev;
   ta.prof = nullptr;
+  ta.release_at = getenv("LOOSB200_RELEASE_AT") ? atoi(getenv("LOOSB200_RELEASE_AT")) : 0;
   const bool want_prof = getenv("LOOSB200_PROF") != nullptr;
 
   LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

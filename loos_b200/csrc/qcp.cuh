@@ -183,42 +183,36 @@ struct QcpPoly {
   bool xform;
 };
 
+// Quartic coefficients from the invariants of S = R / E0.  The eigenvalues of K are
+// {s1+s2+s3, s1-s2-s3, -s1+s2-s3, -s1-s2+s3} for the (signed) singular values s_i of S, hence
+//   C2 = -2 F,  C1 = -8 det S,  C0 = F^2 - 4 G   with  F = ||S||_F^2,  G = ||cof S||_F^2
+// (sum of the squared 2x2 minors): 45 fp64 operations instead of the ~100 of the
+// textbook expansion of det K, and det S reuses the first row of cofactors.
 LB_HD QcpPoly qcp_poly(const double* R, double e0) {
+  // 1/e0: fp32 seed + one Newton step in fp64 (relative error 2^-46: a uniform scaling
+  // of S by (1 + eps) moves y by eps, far below the 1e-13 the coefficients carry)
   double inv = (double)LB_FRCP((float)e0);
   inv = inv * (2.0 - e0 * inv);
-  inv = inv * (2.0 - e0 * inv);
-  const double Sxx = R[0] * inv, Sxy = R[1] * inv, Sxz = R[2] * inv;
-  const double Syx = R[3] * inv, Syy = R[4] * inv, Syz = R[5] * inv;
-  const double Szx = R[6] * inv, Szy = R[7] * inv, Szz = R[8] * inv;
-  const double Sxx2 = Sxx * Sxx, Syy2 = Syy * Syy, Szz2 = Szz * Szz;
-  const double Sxy2 = Sxy * Sxy, Syz2 = Syz * Syz, Sxz2 = Sxz * Sxz;
-  const double Syx2 = Syx * Syx, Szy2 = Szy * Szy, Szx2 = Szx * Szx;
-  const double SyzSzymSyySzz2 = 2.0 * (Syz * Szy - Syy * Szz);
-  const double Sxx2Syy2Szz2Syz2Szy2 = Syy2 + Szz2 - Sxx2 + Syz2 + Szy2;
-  const double C2 = -2.0 * (Sxx2 + Syy2 + Szz2 + Sxy2 + Syx2 + Sxz2 + Szx2 + Syz2 + Szy2);
-  const double C1 = 8.0 * (Sxx * Syz * Szy + Syy * Szx * Sxz + Szz * Sxy * Syx -
-                           Sxx * Syy * Szz - Syz * Szx * Sxy - Szy * Syx * Sxz);
-  const double SxzpSzx = Sxz + Szx, SyzpSzy = Syz + Szy, SxypSyx = Sxy + Syx;
-  const double SyzmSzy = Syz - Szy, SxzmSzx = Sxz - Szx, SxymSyx = Sxy - Syx;
-  const double SxxpSyy = Sxx + Syy, SxxmSyy = Sxx - Syy;
-  const double Sxy2Sxz2Syx2Szx2 = Sxy2 + Sxz2 - Syx2 - Szx2;
-  const double C0 =
-      Sxy2Sxz2Syx2Szx2 * Sxy2Sxz2Syx2Szx2 +
-      (Sxx2Syy2Szz2Syz2Szy2 + SyzSzymSyySzz2) * (Sxx2Syy2Szz2Syz2Szy2 - SyzSzymSyySzz2) +
-      (-(SxzpSzx) * (SyzmSzy) + (SxymSyx) * (SxxmSyy - Szz)) *
-          (-(SxzmSzx) * (SyzpSzy) + (SxymSyx) * (SxxmSyy + Szz)) +
-      (-(SxzpSzx) * (SyzpSzy) - (SxypSyx) * (SxxpSyy - Szz)) *
-          (-(SxzmSzx) * (SyzmSzy) - (SxypSyx) * (SxxpSyy + Szz)) +
-      (+(SxypSyx) * (SyzpSzy) + (SxzpSzx) * (SxxmSyy + Szz)) *
-          (-(SxymSyx) * (SyzmSzy) + (SxzpSzx) * (SxxpSyy + Szz)) +
-      (+(SxypSyx) * (SyzmSzy) + (SxzmSzx) * (SxxmSyy - Szz)) *
-          (-(SxymSyx) * (SyzpSzy) + (SxzmSzx) * (SxxpSyy - Szz));
+  // invariants of the unnormalised R, scaled once at the end
+  const double c00 = R[4] * R[8] - R[5] * R[7], c01 = R[5] * R[6] - R[3] * R[8], c02 = R[3] * R[7] - R[4] * R[6];
+  const double c10 = R[2] * R[7] - R[1] * R[8], c11 = R[0] * R[8] - R[2] * R[6], c12 = R[1] * R[6] - R[0] * R[7];
+  const double c20 = R[1] * R[5] - R[2] * R[4], c21 = R[2] * R[3] - R[0] * R[5], c22 = R[0] * R[4] - R[1] * R[3];
+  const double FR = (R[0] * R[0] + R[1] * R[1] + R[2] * R[2]) + (R[3] * R[3] + R[4] * R[4] + R[5] * R[5]) +
+                    (R[6] * R[6] + R[7] * R[7] + R[8] * R[8]);
+  const double GR = (c00 * c00 + c01 * c01 + c02 * c02) + (c10 * c10 + c11 * c11 + c12 * c12) +
+                    (c20 * c20 + c21 * c21 + c22 * c22);
+  const double DR = R[0] * c00 + R[1] * c01 + R[2] * c02;
+  const double inv2 = inv * inv;
+  const double F = FR * inv2, G = GR * (inv2 * inv2), D8 = 8.0 * (DR * (inv2 * inv));
+  const double C2 = -2.0 * F, C1 = -D8, C0 = F * F - 4.0 * G;
   QcpPoly p;
-  const float xb = sqrtf(fmaxf(0.0f, -1.5f * (float)C2)) * 1.000001f;
+  const float xb = sqrtf(fmaxf(0.0f, 3.0f * (float)F)) * 1.000001f;  // sqrt(-1.5 C2)
   p.xform = xb < 0.5f;
-  p.c0 = p.xform ? C0 : ((1.0 + C2) + C1) + C0;
-  p.c1 = p.xform ? C1 : (-4.0 - 2.0 * C2) - C1;
-  p.c2 = p.xform ? C2 : 6.0 + C2;
+  // y-form: Q(y) = P(1 - y);  q0 = 1 + C2 + C1 + C0 = (1 - F)^2 - 8 det S - 4 G
+  const double omf = 1.0 - F;
+  p.c0 = p.xform ? C0 : (omf * omf - D8) - 4.0 * G;
+  p.c1 = p.xform ? C1 : (4.0 * F - 4.0) + D8;
+  p.c2 = p.xform ? C2 : 6.0 - 2.0 * F;
   p.c3 = p.xform ? 0.0 : -4.0;
   p.t0 = p.xform ? xb : 0.0f;
   return p;
@@ -233,22 +227,20 @@ LB_HD float qcp_newton_step(float f0, float f1, float f2, float f3, float& t) {
   return st;
 }
 
-// Two fp64 residual corrections; returns y = 1 - lambda_max / E0 (>= 0) and whether it settled.
-LB_HD double qcp_polish(const QcpPoly& p, float t, bool* ok) {
+// One fp64 residual correction of the fp32 root (fp32 slope).  `last_step` is the
+// final fp32 Newton step: if the recurrence had settled to ~1e-5 relative, the
+// corrected root is good to ~1e-10 relative.  Returns y = 1 - lambda_max / E0 (>= 0).
+LB_HD double qcp_polish(const QcpPoly& p, float t, float last_step, bool* ok) {
   const float f1 = (float)p.c1, f2 = (float)p.c2, f3 = (float)p.c3;
-  double td = (double)t, corr = 0.0;
-  float df = 0.0f;
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const float tf = (float)td;
-    const double fd = fma(td, fma(td, fma(td, td + p.c3, p.c2), p.c1), p.c0);
-    df = fmaf(tf, fmaf(tf, fmaf(tf, 4.0f, 3.0f * f3), 2.0f * f2), f1);
-    corr = fd * (double)LB_FRCP(df);
-    td -= corr;
-  }
+  const double td0 = (double)t;
+  const double fd = fma(td0, fma(td0, fma(td0, td0 + p.c3, p.c2), p.c1), p.c0);
+  const float df = fmaf(t, fmaf(t, fmaf(t, 4.0f, 3.0f * f3), 2.0f * f2), f1);
+  const double corr = fd * (double)LB_FRCP(df);
+  const double td = td0 - corr;
   const double yn = p.xform ? 1.0 - td : td;
-  *ok = (fabs(corr) <= 1e-6 * fabs(td) + 1e-14) && (p.xform ? df > 0.0f : df < 0.0f) && (yn == yn) &&
-        (yn <= 1.0 + 1e-9);
+  // slope sign: P' > 0 right of the largest root, Q' < 0 left of the smallest
+  *ok = (fabsf(last_step) <= 1e-5f * fabsf(t) + 1e-12f) && (fabs(corr) <= 1e-4 * fabs(td) + 1e-12) &&
+        (p.xform ? df > 0.0f : df < 0.0f) && (yn == yn) && (yn <= 1.0 + 1e-9);
   return yn < 0.0 ? -yn : yn;
 }
 
@@ -259,9 +251,9 @@ LB_HD double qcp_polish(const QcpPoly& p, float t, bool* ok) {
 LB_HD double qcp_y_fast(const double* R, double e0, bool* ok) {
   const QcpPoly p = qcp_poly(R, e0);
   const float f0 = (float)p.c0, f1 = (float)p.c1, f2 = (float)p.c2, f3 = (float)p.c3;
-  float t = p.t0;
-  for (int it = 0; it < QCP_FAST_ITERS; ++it) qcp_newton_step(f0, f1, f2, f3, t);
-  return qcp_polish(p, t, ok);
+  float t = p.t0, st = 0.0f;
+  for (int it = 0; it < QCP_FAST_ITERS; ++it) st = qcp_newton_step(f0, f1, f2, f3, t);
+  return qcp_polish(p, t, st, ok);
 }
 
 // rmsd = sqrt(|Ga + Gb - 2 lambda| / n) scaled by `unit` (length of one operand unit).

@@ -18,7 +18,7 @@ __global__ void k(const double* in, double* out, int iters) {
       bool ok; QcpPoly p = qcp_poly(R, e0);
       float t = p.t0; const float f0 = (float)p.c0, f1 = (float)p.c1, f2 = (float)p.c2, f3 = (float)p.c3;
       for (int k2 = 0; k2 < 6; ++k2) qcp_newton_step(f0, f1, f2, f3, t);
-      acc += qcp_polish(p, t, &ok) + (ok ? 0.0 : 1.0);
+      float st=0; acc += qcp_polish(p, t, st, &ok) + (ok ? 0.0 : 1.0);
     } else if (MODE == 2) {  // 4 interleaved
       QcpPoly p[4]; float t[4]; bool ok;
 #pragma unroll
@@ -27,7 +27,7 @@ __global__ void k(const double* in, double* out, int iters) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) qcp_newton_step((float)p[r].c0, (float)p[r].c1, (float)p[r].c2, (float)p[r].c3, t[r]);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) acc += qcp_polish(p[r], t[r], &ok);
+      for (int r = 0; r < 4; ++r) acc += qcp_polish(p[r], t[r], 0.f, &ok);
     }
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
