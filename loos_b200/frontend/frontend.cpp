@@ -1,0 +1,701 @@
+// See frontend.hpp.  Integer/text semantics follow the reference line by line;
+// the code is ours (no Boost, no bison/flex output).
+#include "frontend.hpp"
+
+#include <pwd.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <regex>
+#include <set>
+#include <sstream>
+
+namespace lbfe {
+
+// ======================================================================= PDB
+
+// parseStringAs<std::string> (src/utils.cpp:228-242): blanks removed; empty when the
+// field is not entirely inside the line.
+static std::string fieldStr(const std::string& s, unsigned pos, unsigned n) {
+  std::string v;
+  if ((size_t)pos + n > s.size()) return v;
+  for (unsigned i = pos; i < pos + n; ++i)
+    if (s[i] != ' ') v += s[i];
+  return v;
+}
+
+// parseStringAs<T> (src/utils.hpp:324-360): stream extraction from the (clipped) field.
+template <typename T>
+static T fieldNum(const std::string& s, unsigned pos, unsigned nelem) {
+  if (pos >= s.size()) throw Error("Missing Field at position " + std::to_string(pos) + "\n> " + s);
+  unsigned n = nelem;
+  if ((size_t)pos + n > s.size()) n = (unsigned)(s.size() - pos + 1);
+  std::istringstream iss(s.substr(pos, n));
+  T val(0);
+  if (!(iss >> val)) throw Error("PARSE ERROR\n" + s);
+  return val;
+}
+
+int parseHybrid36(const std::string& source, unsigned pos, unsigned nelem) {
+  static const int pow10[6] = {1, 10, 100, 1000, 10000, 100000};
+  static const int pow36[6] = {1, 36, 1296, 46656, 1679616, 60466176};
+  unsigned n = !nelem ? (unsigned)(source.size() - pos) : nelem;
+  if ((size_t)pos + n > source.size()) return 0;
+  if (n > 6) throw std::logic_error("Requested size exceeds max");
+  std::string s(source.substr(pos, n));
+  bool negative = false;
+  std::string::iterator si = s.begin();
+  n = (unsigned)s.size();
+  if (si != s.end() && *si == '-') { negative = true; ++si; --n; }
+  for (; si != s.end() && *si == ' '; ++si, --n) {}
+  int offset = 0, ibase = 10;
+  char cbase = 'a';
+  if (si != s.end() && n >= 1 && n <= 5) {
+    if (*si >= 'a') { offset = pow10[n] + 16 * pow36[n - 1]; cbase = 'a'; ibase = 36; }
+    else if (*si >= 'A') { offset = pow10[n] - 10 * pow36[n - 1]; cbase = 'A'; ibase = 36; }
+  }
+  int result = 0;
+  while (si != s.end()) {
+    const int c = (*si >= cbase) ? *si - cbase + 10 : *si - '0';
+    result = result * ibase + c;
+    ++si;
+  }
+  result += offset;
+  return negative ? -result : result;
+}
+
+static void parseAtomRecord(const std::string& s, Model& m) {  // src/pdb.cpp:66-141
+  Atom a;
+  a.index = (uint32_t)m.size();
+  a.record = fieldStr(s, 0, 6);
+  a.id = parseHybrid36(s, 6, 5);
+  a.name = fieldStr(s, 12, 4);
+  a.altloc = fieldStr(s, 16, 1);
+  a.resname = fieldStr(s, 17, 4);
+  a.chain = fieldStr(s, 21, 1);
+  a.resid = parseHybrid36(s, 22, 4);
+  std::string t = s.size() > 26 ? s.substr(26, 1) : std::string(" ");
+  if (t[0] != ' ' && isdigit((unsigned char)t[0])) {  // frame-shifted resid (non-strict policy)
+    a.resid = fieldNum<int>(s, 22, 5);
+    t = " ";
+  }
+  a.icode = t == " " ? "" : t;
+  a.x = fieldNum<float>(s, 30, 8);
+  a.y = fieldNum<float>(s, 38, 8);
+  a.z = fieldNum<float>(s, 46, 8);
+  if (s.size() > 54) {
+    a.occupancy = fieldNum<float>(s, 54, 6);
+    if (s.size() > 60) {
+      a.bfactor = fieldNum<float>(s, 60, 6);
+      if (s.size() > 72) {
+        a.segid = fieldStr(s, 72, 4);
+        if (s.size() > 76) a.element = fieldStr(s, 76, 2);
+      }
+    }
+  }
+  m.push_back(a);
+}
+
+Model readPDB(std::istream& is) {
+  Model m;
+  std::string line;
+  while (std::getline(is, line)) {
+    if (line.compare(0, 4, "ATOM") == 0 || line.compare(0, 6, "HETATM") == 0) parseAtomRecord(line, m);
+    else if (line.compare(0, 3, "END") == 0) break;
+    // REMARK / CONECT / CRYST1 / TER and unknown records do not affect the RMSD path
+  }
+  return m;
+}
+
+Model readPDB(const std::string& path) {
+  std::ifstream ifs(path.c_str());
+  if (!ifs) throw Error("Cannot open " + path);
+  return readPDB(ifs);
+}
+
+// ================================================================= selection
+
+namespace {
+
+enum Tok { T_END, T_NUM, T_STR, T_SKEY, T_NKEY, T_ALL, T_HYD, T_BB, T_LT, T_LE, T_GE, T_GT, T_EQ, T_NE,
+           T_REGEX, T_ARROW, T_NOT, T_AND, T_OR, T_LP, T_RP, T_CHAR };
+struct Token { Tok t; std::string s; long n; };
+
+// src/scanner.ll:29-81 -- flex semantics: longest match, first rule on ties, no word
+// boundaries.
+std::vector<Token> lex(const std::string& in) {
+  static const struct { const char* lit; Tok t; } fixed[] = {
+      {"<", T_LT}, {"<=", T_LE}, {">=", T_GE}, {">", T_GT}, {"==", T_EQ}, {"!=", T_NE}, {"ne", T_NE},
+      {"=~", T_REGEX}, {"&&", T_AND}, {"||", T_OR}, {"!", T_NOT}, {"not", T_NOT}, {"->", T_ARROW},
+      {"all", T_ALL}, {"hydrogen", T_HYD}, {"backbone", T_BB},
+      {"name", T_SKEY}, {"resname", T_SKEY}, {"segid", T_SKEY}, {"segname", T_SKEY}, {"chainid", T_SKEY},
+      {"id", T_NKEY}, {"resid", T_NKEY}, {"index", T_NKEY}};
+  std::vector<Token> out;
+  size_t p = 0;
+  while (p < in.size()) {
+    const char c = in[p];
+    if (c == '\n' || c == '+') { ++p; continue; }
+    if (c == ' ' || c == '\t') { ++p; continue; }
+    if (c == '#' && p + 1 < in.size() && in[p + 1] != '\n') {  // "#.+"
+      while (p < in.size() && in[p] != '\n') ++p;
+      continue;
+    }
+    if (isdigit((unsigned char)c)) {
+      size_t q = p;
+      while (q < in.size() && isdigit((unsigned char)in[q])) ++q;
+      Token t; t.t = T_NUM; t.s = in.substr(p, q - p); t.n = atoi(t.s.c_str());
+      out.push_back(t); p = q; continue;
+    }
+    size_t best = 0; Tok bt = T_CHAR;
+    for (const auto& f : fixed) {
+      const size_t l = strlen(f.lit);
+      if (l > best && in.compare(p, l, f.lit) == 0) { best = l; bt = f.t; }
+    }
+    if (best) {
+      Token t; t.t = bt; t.s = in.substr(p, best); t.n = 0;
+      out.push_back(t); p += best; continue;
+    }
+    if (c == '"' || c == '\'') {
+      std::string text; size_t q = p + 1; bool closed = false;
+      while (q < in.size()) {
+        if (in[q] == '\n' || in[q] == c) { closed = true; ++q; break; }
+        text += in[q++];
+      }
+      if (!closed) { Token t; t.t = T_END; t.n = 0; out.push_back(t); return out; }  // EOF inside a string
+      Token t; t.t = T_STR; t.s = text; t.n = 0; out.push_back(t); p = q; continue;
+    }
+    Token t; t.t = c == '(' ? T_LP : (c == ')' ? T_RP : T_CHAR); t.s = std::string(1, c); t.n = 0;
+    out.push_back(t); ++p;
+  }
+  Token e; e.t = T_END; e.n = 0; out.push_back(e);
+  return out;
+}
+
+enum Op { O_PUSH_INT, O_PUSH_STR, O_NAME, O_RESNAME, O_SEGID, O_CHAIN, O_ID, O_RESID, O_INDEX, O_LT, O_LE, O_GE,
+          O_GT, O_EQ, O_NOT, O_AND, O_OR, O_REGEX, O_EXTRACT, O_TRUE, O_HYD, O_BB };
+struct Ins { Op op; long n; std::string s; std::shared_ptr<std::regex> re; };
+typedef std::vector<Ins> Program;
+
+struct Parser {  // src/grammar.yy:80-148; actions are emitted in bison's reduction order
+  const std::vector<Token>& tk;
+  size_t p = 0;
+  explicit Parser(const std::vector<Token>& t) : tk(t) {}
+  const Token& cur() const { return tk[p]; }
+  [[noreturn]] void fail(const std::string& why) const { throw Error("Bad selection syntax - " + why); }
+
+  static std::shared_ptr<std::regex> mkre(const std::string& s) {
+    try {  // boost::regex::perl | icase (src/KernelActions.hpp:190,222)
+      return std::make_shared<std::regex>(s, std::regex::ECMAScript | std::regex::icase);
+    } catch (const std::regex_error& e) { throw Error(std::string("Bad regular expression '") + s + "': " + e.what()); }
+  }
+
+  void pushKey(const Token& t, Program& out) {
+    Ins i; i.n = 0;
+    if (t.t == T_SKEY) {
+      if (t.s == "name") i.op = O_NAME; else if (t.s == "resname") i.op = O_RESNAME;
+      else if (t.s == "segid" || t.s == "segname") i.op = O_SEGID; else i.op = O_CHAIN;
+    } else {
+      if (t.s == "id") i.op = O_ID; else if (t.s == "resid") i.op = O_RESID; else i.op = O_INDEX;
+    }
+    out.push_back(i);
+  }
+
+  // value : '(' value ')' | NUMBER | NKEY | STRING | SKEY | SKEY "->" STRING
+  bool value(Program& out) {
+    const Token& t = cur();
+    if (t.t == T_LP) {
+      const size_t save = p; const size_t osz = out.size();
+      ++p;
+      if (value(out) && cur().t == T_RP) { ++p; return true; }
+      p = save; out.resize(osz);
+      return false;
+    }
+    if (t.t == T_NUM) { Ins i; i.op = O_PUSH_INT; i.n = t.n; out.push_back(i); ++p; return true; }
+    if (t.t == T_NKEY) { pushKey(t, out); ++p; return true; }
+    if (t.t == T_STR) { Ins i; i.op = O_PUSH_STR; i.n = 0; i.s = t.s; out.push_back(i); ++p; return true; }
+    if (t.t == T_SKEY) {
+      pushKey(t, out); ++p;
+      if (cur().t == T_ARROW) {
+        ++p;
+        if (cur().t != T_STR) fail("expected a pattern after ->");
+        Ins i; i.op = O_EXTRACT; i.n = 0; i.s = cur().s; i.re = mkre(cur().s); out.push_back(i); ++p;
+      }
+      return true;
+    }
+    return false;
+  }
+
+  void rexpr(Program& out) {
+    const Token& t = cur();
+    if (t.t == T_NOT) { ++p; rexpr(out); Ins i; i.op = O_NOT; i.n = 0; out.push_back(i); return; }
+    if (t.t == T_ALL) { ++p; Ins i; i.op = O_TRUE; i.n = 0; out.push_back(i); return; }
+    if (t.t == T_HYD) { ++p; Ins i; i.op = O_HYD; i.n = 0; out.push_back(i); return; }
+    if (t.t == T_BB) { ++p; Ins i; i.op = O_BB; i.n = 0; out.push_back(i); return; }
+    // value OP value  |  alphid =~ strval   (tried before '(' expr ')': a parenthesis may open either)
+    const size_t save = p; const size_t osz = out.size();
+    const bool bare_skey = t.t == T_SKEY;
+    if (value(out)) {
+      const Tok op = cur().t;
+      if (op == T_REGEX) {
+        if (!bare_skey || tk[save + 1].t != T_REGEX) fail("=~ needs name|resname|segid|chainid on its left");
+        ++p;
+        if (cur().t != T_STR) fail("expected a pattern after =~");
+        Ins i; i.op = O_REGEX; i.n = 0; i.s = cur().s; i.re = mkre(cur().s); out.push_back(i); ++p;
+        return;
+      }
+      if (op == T_LT || op == T_LE || op == T_GE || op == T_GT || op == T_EQ || op == T_NE) {
+        ++p;
+        if (!value(out)) fail("expected a value after the comparison operator");
+        Ins i; i.n = 0;
+        i.op = op == T_LT ? O_LT : op == T_LE ? O_LE : op == T_GE ? O_GE : op == T_GT ? O_GT : O_EQ;
+        out.push_back(i);
+        if (op == T_NE) { Ins j; j.op = O_NOT; j.n = 0; out.push_back(j); }
+        return;
+      }
+      p = save; out.resize(osz);
+    }
+    if (cur().t == T_LP) {
+      ++p; expr(out);
+      if (cur().t != T_RP) fail("missing )");
+      ++p; return;
+    }
+    fail("unexpected '" + cur().s + "'");
+  }
+
+  void expr(Program& out) {  // left-associative, && and || at the SAME precedence (grammar.yy:70)
+    rexpr(out);
+    while (cur().t == T_AND || cur().t == T_OR) {
+      const Tok op = cur().t; ++p;
+      rexpr(out);
+      Ins i; i.op = op == T_AND ? O_AND : O_OR; i.n = 0; out.push_back(i);
+    }
+  }
+};
+
+struct Value { bool is_int; long i; std::string s; };
+
+// src/KernelValue.cpp:31-67
+int compareValues(const Value& x, const Value& y) {
+  if (x.is_int != y.is_int) throw Error("Comparing values with different types.");
+  if (!x.is_int) return x.s == y.s ? 0 : (x.s < y.s ? -1 : 1);
+  return (int)(x.i - y.i);
+}
+
+const char* kBackboneRes[48] = {"A", "A3", "A5", "ALA", "ARG", "ASN", "ASP", "C", "C3", "C5", "CYS", "CYX", "DA", "DC",
+                                "DG", "DT", "G", "G3", "G5", "GLN", "GLU", "GLY", "HID", "HIE", "HIP", "HIS", "HSD",
+                                "HSE", "HSP", "ILE", "LEU", "LYS", "MET", "MSE", "PHE", "PRO", "PTR", "SER", "T", "T3",
+                                "T5", "THR", "TRP", "TYR", "U", "U3", "U5", "VAL"};  // src/Selectors.cpp:37-86
+const char* kBackboneAtoms[33] = {"C", "C1'", "C2'", "C3'", "C4'", "C5'", "CA", "H", "H1'", "H12'", "H15'", "H2'",
+                                  "H2''", "H22'", "H25'", "H3'", "H4'", "H5'", "H5''", "HO2'", "HO3'", "HO5'", "N",
+                                  "O", "O2'", "O3'", "O4'", "O5'", "OP1", "OP2", "OP3", "OXT", "P"};  // :88-122
+
+bool isBackbone(const Atom& a) {  // src/Selectors.cpp:126-132 (binary_search over the tables as listed)
+  static const std::vector<std::string> res(kBackboneRes, kBackboneRes + 48), atm(kBackboneAtoms, kBackboneAtoms + 33);
+  return std::binary_search(res.begin(), res.end(), a.resname) && std::binary_search(atm.begin(), atm.end(), a.name);
+}
+
+bool extractInt(const std::string& s, long* out) {  // std::stringstream(s) >> int
+  std::istringstream iss(s);
+  int v;
+  if (iss >> v) { *out = v; return true; }
+  return false;
+}
+
+bool run(const Program& prog, const Atom& a) {  // src/KernelActions.cpp:33-297, Selectors.cpp:189-200
+  std::vector<Value> st;
+  auto pop = [&]() { if (st.empty()) throw Error("Execution error - stack underflow"); Value v = st.back(); st.pop_back(); return v; };
+  auto pushi = [&](long v) { Value x; x.is_int = true; x.i = v; st.push_back(x); };
+  auto pushs = [&](const std::string& v) { Value x; x.is_int = false; x.i = 0; x.s = v; st.push_back(x); };
+  for (const Ins& in : prog) {
+    switch (in.op) {
+      case O_PUSH_INT: pushi(in.n); break;
+      case O_PUSH_STR: pushs(in.s); break;
+      case O_NAME: pushs(a.name); break;
+      case O_RESNAME: pushs(a.resname); break;
+      case O_SEGID: pushs(a.segid); break;
+      case O_CHAIN: pushs(a.chain); break;
+      case O_ID: pushi(a.id); break;
+      case O_RESID: pushi(a.resid); break;
+      case O_INDEX: pushi((long)a.index); break;
+      case O_LT: case O_LE: {
+        if (st.size() < 2) throw Error("Execution error - stack underflow");
+        const Value& v1 = st[st.size() - 1]; const Value& v2 = st[st.size() - 2];
+        if ((v1.is_int && v1.i < 0) || (v2.is_int && v2.i < 0)) { st.pop_back(); st.pop_back(); pushi(0); break; }
+        Value b = pop(), c = pop(); const int e = compareValues(c, b);
+        pushi(in.op == O_LT ? e < 0 : e <= 0); break;
+      }
+      case O_GE: case O_GT: case O_EQ: {
+        Value b = pop(), c = pop(); const int e = compareValues(c, b);
+        pushi(in.op == O_GE ? e >= 0 : in.op == O_GT ? e > 0 : e == 0); break;
+      }
+      case O_NOT: { Value v = pop(); if (!v.is_int) throw Error("Invalid operand to logicalNot"); pushi(!v.i); break; }
+      case O_AND: case O_OR: {
+        Value b = pop(), c = pop();
+        if (!b.is_int || !c.is_int) throw Error(in.op == O_AND ? "Invalid operands to logicalAnd" : "Invalid operands to logicalOr");
+        pushi(in.op == O_AND ? (c.i && b.i) : (c.i || b.i)); break;
+      }
+      case O_REGEX: {
+        Value v = pop();
+        if (v.is_int) throw Error("Expected a string value but got something else...");
+        pushi(std::regex_search(v.s, *in.re) ? 1 : 0); break;
+      }
+      case O_EXTRACT: {
+        Value v = pop();
+        if (v.is_int) throw Error("Expected a string value but got something else...");
+        long r = -1; std::smatch what;
+        if (std::regex_search(v.s, what, *in.re))
+          for (size_t k = 0; k < what.size(); ++k)
+            if (extractInt(what[k].str(), &r)) break;
+        pushi(r); break;
+      }
+      case O_TRUE: pushi(1); break;
+      case O_HYD: pushi(!a.name.empty() && a.name[0] == 'H'); break;  // PDB models carry no mass (KernelActions.cpp:270-284)
+      case O_BB: pushi(isBackbone(a)); break;
+    }
+  }
+  if (st.size() != 1) throw Error("Execution error - unexpected values on stack");
+  if (!st.back().is_int) throw Error("Execution error - unexpected value on top of stack");
+  return st.back().i != 0;
+}
+
+}  // namespace
+
+std::vector<uint32_t> selectAtoms(const Model& model, const std::string& selection) {
+  const std::vector<Token> toks = lex(selection);
+  Parser ps(toks);
+  Program prog;
+  ps.expr(prog);
+  if (ps.cur().t != T_END) throw Error("Bad selection syntax - unexpected '" + ps.cur().s + "'");
+  std::vector<uint32_t> out;
+  for (size_t i = 0; i < model.size(); ++i)
+    if (run(prog, model[i])) out.push_back((uint32_t)i);
+  return out;
+}
+
+std::vector<uint32_t> selectionToFrameIndices(const Model& model, const std::vector<uint32_t>& picked) {
+  std::vector<uint32_t> out(picked.size());
+  for (size_t i = 0; i < picked.size(); ++i) out[i] = model[picked[i]].index;
+  return out;
+}
+
+// ============================================================== frame ranges
+
+namespace {
+struct RangeLex {  // Boost.Spirit qi with an ascii::space skipper: blanks are skipped before every terminal
+  const std::string& s; size_t p;
+  void skip() { while (p < s.size() && isspace((unsigned char)s[p])) ++p; }
+  bool uint_(uint32_t* v) {
+    skip(); size_t q = p; unsigned long long x = 0;
+    while (q < s.size() && isdigit((unsigned char)s[q])) { x = x * 10 + (s[q] - '0'); if (x > 0xffffffffULL) return false; ++q; }
+    if (q == p) return false;
+    *v = (uint32_t)x; p = q; return true;
+  }
+  bool int_(int* v) {
+    skip(); size_t q = p; bool neg = false;
+    if (q < s.size() && (s[q] == '+' || s[q] == '-')) { neg = s[q] == '-'; ++q; }
+    size_t d = q; long long x = 0;
+    while (q < s.size() && isdigit((unsigned char)s[q])) { x = x * 10 + (s[q] - '0'); if (x > 0x80000000LL) return false; ++q; }
+    if (q == d) return false;
+    *v = (int)(neg ? -x : x); p = q; return true;
+  }
+  bool lit(char c) { skip(); if (p < s.size() && s[p] == c) { ++p; return true; } return false; }
+};
+struct RangeItem { uint32_t start, stop; int step; };
+}  // namespace
+
+std::vector<uint32_t> parseIndexRange(const std::string& spec, uint32_t maxsize) {
+  RangeLex L{spec, 0};
+  std::vector<RangeItem> items;
+  auto endpoint = [&](uint32_t* v) { if (!L.uint_(v)) *v = maxsize; return true; };  // uint_ | eps[maxsize]
+  auto ranger = [&](RangeItem* it) {  // ordered alternatives, src/index_range_parser.cpp:126-130
+    const size_t save = L.p; uint32_t a, b; int st;
+    if (L.uint_(&a) && L.lit(':') && L.int_(&st) && L.lit(':') && endpoint(&b)) { *it = {a, b, st}; return true; }
+    L.p = save;
+    if (endpoint(&a) && L.lit(':') && L.int_(&st) && L.lit(':') && L.uint_(&b)) { *it = {a, b, st}; return true; }
+    L.p = save;
+    if (L.uint_(&a) && L.lit(':') && endpoint(&b)) { *it = {a, b, 1}; return true; }
+    L.p = save;
+    if (endpoint(&a) && L.lit(':') && L.uint_(&b)) { *it = {a, b, -1}; return true; }
+    L.p = save;
+    if (L.uint_(&a)) { *it = {a, a, 0}; return true; }
+    L.p = save;
+    return false;
+  };
+  RangeItem it;
+  bool ok = ranger(&it);
+  if (ok) {
+    items.push_back(it);
+    for (;;) {  // ranger % ','
+      const size_t save = L.p;
+      if (!L.lit(',')) break;
+      if (!ranger(&it)) { L.p = save; break; }
+      items.push_back(it);
+    }
+  }
+  L.skip();
+  if (!ok || L.p != spec.size()) throw Error("Could not parse range: " + spec);
+  std::vector<uint32_t> out;
+  for (const RangeItem& r : items) {  // RangeItem::generate, :79-96
+    if ((r.start < r.stop && r.step < 0) || (r.start > r.stop && r.step > 0)) throw Error("Invalid range");
+    if (r.step == 0) out.push_back(r.start);
+    else if (r.step > 0) { for (uint32_t i = r.start; i <= r.stop; i += (uint32_t)r.step) { out.push_back(i); if (i + (uint32_t)r.step < i) break; } }
+    else { for (uint32_t i = r.start; i >= r.stop && i <= r.start; i += (uint32_t)r.step) out.push_back(i); }
+  }
+  return out;
+}
+
+std::vector<uint32_t> assignTrajectoryFrames(uint32_t nframes, const std::string& spec, uint32_t skip, uint32_t stride) {
+  std::vector<uint32_t> frames;
+  if (spec.empty()) { for (uint32_t i = skip; i < nframes; i += stride) frames.push_back(i); }
+  else frames = parseIndexRange(spec, nframes - 1);
+  return frames;
+}
+
+std::vector<uint32_t> uniquify(const std::vector<uint32_t>& v) {
+  std::set<uint32_t> s(v.begin(), v.end());
+  return std::vector<uint32_t>(s.begin(), s.end());
+}
+
+// ======================================================================= DCD
+
+static uint32_t swab32(uint32_t x) { return __builtin_bswap32(x); }
+
+uint32_t DCD::recordLen() {
+  uint32_t n = 0;
+  ifs_.read((char*)&n, 4);
+  if (ifs_.eof()) return 0;
+  if (ifs_.fail()) throw Error("Error while reading F77 record from DCD " + path_);
+  return swab_ ? swab32(n) : n;
+}
+
+DCD::DCD(const std::string& path) : path_(path), ifs_(path.c_str(), std::ios::binary) {
+  if (!ifs_) throw Error("Cannot open " + path);
+  uint32_t datum = 0;
+  ifs_.read((char*)&datum, 4);
+  if (ifs_.eof() || ifs_.fail()) throw Error("Unable to read first datum from DCD file " + path);
+  ifs_.seekg(0);
+  if (datum != 0x54) {  // src/dcd.cpp:109-125
+    if (swab32(datum) != 0x54) throw Error("Unable to determine endian-ness of DCD file " + path);
+    swab_ = true;
+  }
+  uint32_t len = recordLen();
+  if (len != 84) throw Error("Error while reading DCD header of " + path);
+  unsigned char hdr[84];
+  ifs_.read((char*)hdr, 84);
+  if (recordLen() != 84) throw Error("Mismatch in record length while reading from DCD " + path);
+  if (memcmp(hdr, "CORD", 4) != 0) throw Error("DCD is missing CORD magic marker: " + path);
+  for (int i = 0; i < 20; ++i) {
+    uint32_t w; memcpy(&w, hdr + 4 * (i + 1), 4);
+    icntrl_[i] = (int)(swab_ ? swab32(w) : w);
+  }
+  { uint32_t w; memcpy(&w, hdr + 40, 4); if (swab_) w = swab32(w); memcpy(&delta_, &w, 4); }
+  nframes_ = (uint32_t)icntrl_[0];
+  if (icntrl_[8] != 0) throw Error("Fixed atoms not yet supported by LOOS DCD reader");
+  len = recordLen();  // TITLE
+  if (len == 0) throw Error("Unexpected EOF reading DCD TITLE of " + path);
+  ifs_.seekg(len, std::ios::cur);
+  if (recordLen() != len) throw Error("Mismatch in record length while reading from DCD " + path);
+  len = recordLen();  // NATOMS
+  if (len != 4) throw Error("Error reading number of atoms from DCD " + path);
+  uint32_t na = 0; ifs_.read((char*)&na, 4);
+  natoms_ = swab_ ? swab32(na) : na;
+  if (recordLen() != 4) throw Error("Mismatch in record length while reading from DCD " + path);
+  first_frame_pos_ = (uint64_t)ifs_.tellg();
+  frame_size_ = 12ull * (2 + natoms_) + (hasCrystal() ? 56 : 0);  // src/dcd.cpp:246-248
+  if (nframes_ == 0) {  // header without a frame count: derive it from the file size (:254-260,156-164)
+    ifs_.seekg(0, std::ios::end);
+    const uint64_t datasize = (uint64_t)ifs_.tellg() - first_frame_pos_;
+    nframes_ = (datasize % frame_size_) ? 0 : (uint32_t)(datasize / frame_size_);
+    if (nframes_ == 0) std::cerr << "Warning- DCD '" << path << "' appears empty and could not determine size\n";
+  }
+}
+
+void DCD::readFramePlanes(uint32_t i, float* out) {  // src/dcd.cpp:329-371
+  if (i >= nframes_) throw Error("Requested DCD frame is out of range");
+  ifs_.clear();
+  ifs_.seekg((std::streamoff)(first_frame_pos_ + (uint64_t)i * frame_size_));
+  if (hasCrystal()) {
+    if (recordLen() != 48) throw Error("Cannot read crystal parameters");
+    ifs_.seekg(48, std::ios::cur);
+    if (recordLen() != 48) throw Error("Mismatch in record length while reading from DCD");
+  }
+  for (int k = 0; k < 3; ++k) {
+    const uint32_t len = recordLen();
+    if (len != 4 * natoms_) throw Error("Size of coords stored in frame does not match model size");
+    ifs_.read((char*)(out + (size_t)k * natoms_), len);
+    if (ifs_.fail()) throw Error("Error reading data record from DCD");
+    if (recordLen() != len) throw Error("Mismatch in record length while reading from DCD");
+    if (swab_) {
+      uint32_t* w = (uint32_t*)(out + (size_t)k * natoms_);
+      for (uint32_t a = 0; a < natoms_; ++a) w[a] = swab32(w[a]);
+    }
+  }
+}
+
+// ================================================================= MultiTraj
+
+uint32_t MultiTraj::nframes(size_t i) const {
+  const uint32_t n = trajs.at(i)->nframes();
+  if (n <= skip) return 0;
+  return (n - skip + stride - 1) / stride;
+}
+uint32_t MultiTraj::nframes() const {
+  uint32_t t = 0;
+  for (size_t i = 0; i < trajs.size(); ++i) t += nframes(i);
+  return t;
+}
+std::pair<uint32_t, uint32_t> MultiTraj::location(uint32_t i) const {
+  uint32_t k, j;
+  for (j = k = 0; k < trajs.size(); ++k) {
+    const uint32_t n = nframes(k);
+    if (j + n > i) break;
+    j += n;
+  }
+  return std::make_pair(k, skip + (i - j) * stride);
+}
+
+// ==================================================================== output
+
+std::string formatG(double v, unsigned precision) {
+  char buf[64];
+  snprintf(buf, sizeof(buf), "%.*g", (int)precision, v);
+  return buf;
+}
+
+void writeMatrix(std::ostream& os, const float* M, size_t m, size_t n, size_t ld, unsigned precision) {
+  os << "# " << m << " " << n << " (0)\n";
+  std::string line;
+  char buf[64];
+  for (size_t j = 0; j < m; ++j) {
+    line.clear();
+    for (size_t i = 0; i < n; ++i) {
+      const int l = snprintf(buf, sizeof(buf), "%.*g ", (int)precision, (double)M[i * ld + j]);
+      line.append(buf, (size_t)l);
+    }
+    line += '\n';
+    os.write(line.data(), (std::streamsize)line.size());
+  }
+  os.flush();
+}
+
+std::string invocationHeader(int argc, char* argv[]) {  // src/utils.cpp:119-164
+  time_t t = time(0);
+  std::string timestamp(asctime(localtime(&t)));
+  timestamp.erase(timestamp.length() - 1, 1);
+  struct passwd* pwd = getpwuid(getuid());
+  const std::string user = pwd ? pwd->pw_name : "UNKNOWN USER";
+  char cwd[4096];
+  const char* cd = getcwd(cwd, sizeof(cwd));
+  std::string invoke = std::string(argv[0]) + " ";
+  for (int i = 1; i < argc; ++i) invoke += "'" + std::string(argv[i]) + "'" + (i == argc - 1 ? "" : " ");
+  invoke += " - " + user + " (" + timestamp + ")";
+  if (cd) invoke += " {" + std::string(cd) + "}";
+  invoke += " [loos-b200 0.1 BUILT ON " __DATE__ " " __TIME__ "]";
+  std::string out;
+  for (char c : invoke) { if (c == '\n') out += "\\n"; else out += c; }
+  return out;
+}
+
+// =================================================================== options
+
+void Options::add(const std::string& longname, char shortname, const std::string& defval, const std::string& help, bool is_bool) {
+  Opt o; o.name = longname; o.shortname = shortname; o.defval = defval; o.help = help; o.is_bool = is_bool; o.set = false;
+  opts_.push_back(o);
+}
+void Options::addPositional(const std::string& name, int max_count) { positional_.push_back(std::make_pair(name, max_count)); }
+Options::Opt* Options::find(const std::string& name) { for (auto& o : opts_) if (o.name == name) return &o; return nullptr; }
+const Options::Opt* Options::find(const std::string& name) const { for (auto& o : opts_) if (o.name == name) return &o; return nullptr; }
+
+static bool parseBool(const std::string& v, bool* out) {  // boost::program_options bool syntax
+  std::string s; for (char c : v) s += (char)tolower((unsigned char)c);
+  if (s == "1" || s == "true" || s == "yes" || s == "on") { *out = true; return true; }
+  if (s == "0" || s == "false" || s == "no" || s == "off") { *out = false; return true; }
+  return false;
+}
+
+bool Options::parse(int argc, char* argv[]) {
+  size_t pos_i = 0; size_t pos_count = 0;
+  auto store = [&](Opt* o, const std::string& v) -> bool {
+    bool b;
+    if (o->is_bool && !parseBool(v, &b)) { std::cerr << "Error- the argument ('" << v << "') for option '--" << o->name << "' is invalid\n"; return false; }
+    o->values.push_back(v); o->set = true; return true;
+  };
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    Opt* o = nullptr; std::string val; bool have_val = false;
+    if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
+      const size_t eq = a.find('=');
+      const std::string name = a.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
+      o = find(name);  // exact names only: prefix guessing is off (OptionsFramework.cpp:754-755)
+      if (!o) { std::cerr << "Error- unrecognised option '--" << name << "'\n"; return false; }
+      if (eq != std::string::npos) { val = a.substr(eq + 1); have_val = true; }
+    } else if (a.size() >= 2 && a[0] == '-' && !isdigit((unsigned char)a[1]) && a[1] != '.') {
+      for (auto& c : opts_) if (c.shortname && c.shortname == a[1]) o = &c;
+      if (!o) { std::cerr << "Error- unrecognised option '" << a << "'\n"; return false; }
+      if (a.size() > 2) { val = a.substr(2); have_val = true; }
+    }
+    if (o) {
+      if (!have_val) {
+        if (i + 1 >= argc) { std::cerr << "Error- the required argument for option '--" << o->name << "' is missing\n"; return false; }
+        val = argv[++i];
+      }
+      if (!store(o, val)) return false;
+      continue;
+    }
+    if (pos_i >= positional_.size()) { std::cerr << "Error- too many positional options have been specified on the command line\n"; return false; }
+    Opt* po = find(positional_[pos_i].first);
+    if (!po) { add(positional_[pos_i].first, 0, "", "", false); po = find(positional_[pos_i].first); }
+    po->values.push_back(a); po->set = true;
+    ++pos_count;
+    if (positional_[pos_i].second >= 0 && (int)pos_count >= positional_[pos_i].second) { ++pos_i; pos_count = 0; }
+  }
+  return true;
+}
+
+bool Options::has(const std::string& name) const { const Opt* o = find(name); return o && o->set; }
+std::string Options::str(const std::string& name) const {
+  const Opt* o = find(name);
+  if (!o) return "";
+  return o->set ? o->values.back() : o->defval;
+}
+unsigned long Options::uns(const std::string& name) const {
+  const std::string v = str(name);
+  char* end = nullptr;
+  if (v.empty() || v[0] == '-') throw Error("the argument ('" + v + "') for option '--" + name + "' is invalid");
+  const unsigned long x = strtoul(v.c_str(), &end, 10);
+  if (!end || *end) throw Error("the argument ('" + v + "') for option '--" + name + "' is invalid");
+  return x;
+}
+double Options::dbl(const std::string& name) const {
+  const std::string v = str(name);
+  char* end = nullptr;
+  const double x = strtod(v.c_str(), &end);
+  if (v.empty() || !end || *end) throw Error("the argument ('" + v + "') for option '--" + name + "' is invalid");
+  return x;
+}
+bool Options::flag(const std::string& name) const { bool b = false; parseBool(str(name), &b); return b; }
+const std::vector<std::string>& Options::multi(const std::string& name) const {
+  static const std::vector<std::string> empty;
+  const Opt* o = find(name);
+  return o ? o->values : empty;
+}
+std::string Options::usage(const std::string& prog, const std::string& positional_help) const {
+  std::ostringstream os;
+  os << "Usage- " << prog << " [options] " << positional_help << "\nAllowed Options:\n";
+  for (const auto& o : opts_) {
+    if (o.help.empty()) continue;
+    std::string lhs = "  ";
+    if (o.shortname) lhs += std::string("-") + o.shortname + " [ --" + o.name + " ]"; else lhs += "--" + o.name;
+    lhs += " arg";
+    if (!o.defval.empty()) lhs += " (=" + o.defval + ")";
+    os << lhs << (lhs.size() < 40 ? std::string(40 - lhs.size(), ' ') : " ") << o.help << "\n";
+  }
+  return os.str();
+}
+
+}  // namespace lbfe

@@ -1,0 +1,120 @@
+// Native front-end for the three RMSD tools: just enough of LOOS's L1/L2/L4 layers
+// (PDB model, DCD trajectory, selection language, frame ranges, MultiTrajectory
+// indexing, Matrix text output, option parsing) to drive the C ABI in
+// include/loosb200.h from the same command lines, with bit-exact integer/text
+// semantics.  LOOS itself cannot be linked here (Boost/NetCDF/HDF5 are absent), see
+// DESIGN.md; in a LOOS build these pieces are LOOS's own.
+// Every function cites the reference code whose behaviour it reproduces.
+#pragma once
+#include <stdint.h>
+
+#include <fstream>
+#include <iosfwd>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace lbfe {
+
+struct Error : std::runtime_error {
+  explicit Error(const std::string& s) : std::runtime_error(s) {}
+};
+
+// ---- model (src/Atom.hpp, src/pdb.cpp:66-141) ----
+struct Atom {
+  uint32_t index = 0;  // position among the atom records of the file (pdb.cpp:73)
+  long id = 0, resid = 0;
+  std::string record, name, altloc, resname, chain, icode, segid, element;
+  double x = 0, y = 0, z = 0;
+  double occupancy = 1.0, bfactor = 0.0;
+};
+typedef std::vector<Atom> Model;
+
+int parseHybrid36(const std::string& src, unsigned pos, unsigned n);  // src/utils.cpp:259-316
+Model readPDB(const std::string& path);                               // src/pdb.cpp:342-380
+Model readPDB(std::istream& is);
+
+// ---- selection language (src/grammar.yy, src/scanner.ll, src/KernelActions.cpp) ----
+// Returns the indices INTO `model` (ascending: AtomicGroup::select keeps model
+// order, src/AtomicGroup.cpp:341-351) of the atoms the expression accepts.
+std::vector<uint32_t> selectAtoms(const Model& model, const std::string& selection);  // src/utils.cpp:183-201
+// Atom::index() of the selected atoms (what updateGroupCoords uses as the frame offset).
+std::vector<uint32_t> selectionToFrameIndices(const Model& model, const std::vector<uint32_t>& picked);
+
+// ---- frame lists (src/index_range_parser.cpp:60-173, src/utils_structural.cpp:113-123) ----
+std::vector<uint32_t> parseIndexRange(const std::string& spec, uint32_t maxsize);
+std::vector<uint32_t> assignTrajectoryFrames(uint32_t nframes, const std::string& spec, uint32_t skip,
+                                             uint32_t stride = 1);
+std::vector<uint32_t> uniquify(const std::vector<uint32_t>& v);  // src/utils.hpp:427-436
+
+// ---- DCD (src/dcd.cpp:109-261,329-371) ----
+class DCD {
+ public:
+  explicit DCD(const std::string& path);
+  uint32_t natoms() const { return natoms_; }
+  uint32_t nframes() const { return nframes_; }
+  bool hasCrystal() const { return icntrl_[10] == 1; }
+  float timestep() const { return delta_; }
+  const std::string& filename() const { return path_; }
+  // Frame `i` as three planes X[natoms] Y[natoms] Z[natoms] (the record order of the
+  // file): out must hold 3*natoms floats.
+  void readFramePlanes(uint32_t i, float* out);
+
+ private:
+  uint32_t recordLen();
+  std::string path_;
+  std::ifstream ifs_;
+  bool swab_ = false;
+  int icntrl_[20];
+  float delta_ = 0;
+  uint32_t natoms_ = 0, nframes_ = 0;
+  uint64_t first_frame_pos_ = 0, frame_size_ = 0;
+};
+
+// ---- MultiTrajectory indexing (src/MultiTraj.hpp:98-105, src/MultiTraj.cpp:48-58) ----
+struct MultiTraj {
+  std::vector<std::shared_ptr<DCD>> trajs;
+  uint32_t skip = 0, stride = 1;
+  uint32_t nframes(size_t i) const;
+  uint32_t nframes() const;
+  // composite frame -> (trajectory, raw frame)
+  std::pair<uint32_t, uint32_t> location(uint32_t k) const;
+};
+
+// ---- output (src/MatrixImpl.hpp:210-222, src/utils.cpp:119-164) ----
+// M: float32 column-major, ld >= m.  Same bytes as `os << setprecision(p) << M`.
+void writeMatrix(std::ostream& os, const float* M, size_t m, size_t n, size_t ld, unsigned precision);
+std::string invocationHeader(int argc, char* argv[]);
+// default-floatfield formatting of a double with `precision` significant digits
+// (std::ostream default: 6), as rmsd2ref prints its values.
+std::string formatG(double v, unsigned precision);
+
+// ---- options (src/OptionsFramework.cpp:742-795: boost::program_options semantics used by
+// the tools: long names without prefix guessing, short aliases, every option takes a
+// value -- booleans too --, positionals in declaration order) ----
+class Options {
+ public:
+  void add(const std::string& longname, char shortname, const std::string& defval, const std::string& help,
+           bool is_bool = false);
+  void addPositional(const std::string& name, int max_count);  // -1: unlimited
+  // returns false (after printing to stderr) on a syntax error
+  bool parse(int argc, char* argv[]);
+  bool has(const std::string& name) const;
+  std::string str(const std::string& name) const;
+  unsigned long uns(const std::string& name) const;
+  double dbl(const std::string& name) const;
+  bool flag(const std::string& name) const;
+  const std::vector<std::string>& multi(const std::string& name) const;
+  std::string usage(const std::string& prog, const std::string& positional_help) const;
+
+ private:
+  struct Opt { std::string name, defval, help; char shortname; bool is_bool, set; std::vector<std::string> values; };
+  std::vector<Opt> opts_;
+  std::vector<std::pair<std::string, int>> positional_;
+  Opt* find(const std::string& name);
+  const Opt* find(const std::string& name) const;
+};
+
+}  // namespace lbfe

@@ -1,0 +1,94 @@
+// Test hooks: a C view of the front-end pieces so that tests/ can check them
+// bit-exactly against independent restatements (not part of include/loosb200.h).
+#include <string.h>
+
+#include <sstream>
+
+#include "frontend.hpp"
+
+using namespace lbfe;
+
+static thread_local std::string g_err;
+static int fail(const std::exception& e) { g_err = e.what(); return -1; }
+
+extern "C" {
+const char* lbfe_last_error(void) { return g_err.c_str(); }
+
+// indices into the model (and Atom::index, identical for PDB) of the selected atoms
+long lbfe_select(const char* pdb_path, const char* selection, uint32_t* out, long cap) {
+  try {
+    Model m = readPDB(pdb_path);
+    std::vector<uint32_t> s = selectionToFrameIndices(m, selectAtoms(m, selection));
+    for (long i = 0; i < (long)s.size() && i < cap; ++i) out[i] = s[i];
+    return (long)s.size();
+  } catch (const std::exception& e) { return fail(e); }
+}
+
+long lbfe_pdb_atoms(const char* pdb_path, long* ids, long* resids, double* xyz, char* names /* 8 bytes each: name|resname */, long cap) {
+  try {
+    Model m = readPDB(pdb_path);
+    for (long i = 0; i < (long)m.size() && i < cap; ++i) {
+      ids[i] = m[i].id; resids[i] = m[i].resid;
+      xyz[3 * i] = m[i].x; xyz[3 * i + 1] = m[i].y; xyz[3 * i + 2] = m[i].z;
+      memset(names + 16 * i, 0, 16);
+      strncpy(names + 16 * i, m[i].name.c_str(), 7);
+      strncpy(names + 16 * i + 8, m[i].segid.c_str(), 7);
+    }
+    return (long)m.size();
+  } catch (const std::exception& e) { return fail(e); }
+}
+
+int lbfe_hybrid36(const char* field, int n) { try { return parseHybrid36(std::string(field), 0, (unsigned)n); } catch (const std::exception& e) { fail(e); return -999999; } }
+
+long lbfe_parse_range(const char* spec, uint32_t maxsize, uint32_t* out, long cap) {
+  try {
+    std::vector<uint32_t> r = parseIndexRange(spec, maxsize);
+    for (long i = 0; i < (long)r.size() && i < cap; ++i) out[i] = r[i];
+    return (long)r.size();
+  } catch (const std::exception& e) { return fail(e); }
+}
+
+long lbfe_assign_frames(uint32_t nframes, const char* spec, uint32_t skip, uint32_t stride, int uniq, uint32_t* out, long cap) {
+  try {
+    std::vector<uint32_t> r = assignTrajectoryFrames(nframes, spec, skip, stride);
+    if (uniq) r = uniquify(r);
+    for (long i = 0; i < (long)r.size() && i < cap; ++i) out[i] = r[i];
+    return (long)r.size();
+  } catch (const std::exception& e) { return fail(e); }
+}
+
+int lbfe_dcd_info(const char* path, uint32_t* natoms, uint32_t* nframes, int* crystal) {
+  try { DCD d(path); *natoms = d.natoms(); *nframes = d.nframes(); *crystal = d.hasCrystal(); return 0; }
+  catch (const std::exception& e) { return fail(e); }
+}
+
+int lbfe_dcd_read(const char* path, uint32_t frame, float* planes) {
+  try { DCD d(path); d.readFramePlanes(frame, planes); return 0; }
+  catch (const std::exception& e) { return fail(e); }
+}
+
+// MultiTraj: sizes[] = frames in each sub-trajectory; returns composite count and the
+// (traj, frame) location of composite frame k for every k < cap
+long lbfe_multitraj(const uint32_t* sizes, int ntraj, uint32_t skip, uint32_t stride, uint32_t* loc_traj, uint32_t* loc_frame, long cap) {
+  long total = 0;
+  for (int i = 0; i < ntraj; ++i) total += sizes[i] <= skip ? 0 : (sizes[i] - skip + stride - 1) / stride;
+  for (long k = 0; k < total && k < cap; ++k) {
+    uint32_t t, j = 0;
+    for (t = 0; t < (uint32_t)ntraj; ++t) {
+      const uint32_t n = sizes[t] <= skip ? 0 : (sizes[t] - skip + stride - 1) / stride;
+      if (j + n > k) break;
+      j += n;
+    }
+    loc_traj[k] = t; loc_frame[k] = skip + ((uint32_t)k - j) * stride;
+  }
+  return total;
+}
+
+long lbfe_matrix_text(const float* M, size_t m, size_t n, size_t ld, unsigned precision, char* out, long cap) {
+  std::ostringstream os;
+  writeMatrix(os, M, m, n, ld, precision);
+  const std::string s = os.str();
+  if ((long)s.size() < cap) memcpy(out, s.data(), s.size());
+  return (long)s.size();
+}
+}

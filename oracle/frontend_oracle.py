@@ -1,0 +1,325 @@
+"""TEST INFRASTRUCTURE ONLY: Python restatement of the reference's integer/text
+front-end semantics (selection language, PDB fields, hybrid-36, frame ranges,
+MultiTrajectory indexing, DCD layout), used to check loos_b200/frontend bit-exactly.
+Each function cites the reference code it follows (paths under /root/reference)."""
+import re
+import struct
+
+import numpy as np
+
+# ---------------------------------------------------------------- PDB (src/pdb.cpp:66-141)
+
+
+def hybrid36(field):
+    """src/utils.cpp:259-316 (parseStringAsHybrid36) on an already-cut field."""
+    s = field
+    n = len(s)
+    neg = False
+    i = 0
+    if n and s[0] == "-":
+        neg, i, n = True, 1, n - 1
+    while i < len(s) and s[i] == " ":
+        i += 1
+        n -= 1
+    pow10 = [1, 10, 100, 1000, 10000, 100000]
+    pow36 = [1, 36, 1296, 46656, 1679616, 60466176]
+    offset, cbase, ibase = 0, "a", 10
+    if i < len(s):
+        if s[i] >= "a":
+            offset, cbase, ibase = pow10[n] + 16 * pow36[n - 1], "a", 36
+        elif s[i] >= "A":
+            offset, cbase, ibase = pow10[n] - 10 * pow36[n - 1], "A", 36
+    r = 0
+    for ch in s[i:]:
+        c = ord(ch) - ord(cbase) + 10 if ch >= cbase else ord(ch) - ord("0")
+        r = r * ibase + c
+    r += offset
+    return -r if neg else r
+
+
+def _fs(s, pos, n):
+    return "" if pos + n > len(s) else s[pos:pos + n].replace(" ", "")
+
+
+def read_pdb(path):
+    atoms = []
+    for line in open(path):
+        line = line.rstrip("\n")
+        if line.startswith("ATOM") or line.startswith("HETATM"):
+            a = dict(index=len(atoms), id=hybrid36(line[6:11]) if len(line) >= 11 else 0, name=_fs(line, 12, 4),
+                     resname=_fs(line, 17, 4), chain=_fs(line, 21, 1),
+                     resid=hybrid36(line[22:26]) if len(line) >= 26 else 0, segid=_fs(line, 72, 4) if len(line) > 72 else "")
+            if len(line) > 26 and line[26].isdigit():
+                a["resid"] = int(line[22:27])
+            a["xyz"] = tuple(float(np.float32(float(line[p:p + 8]))) for p in (30, 38, 46))
+            atoms.append(a)
+        elif line.startswith("END"):
+            break
+    return atoms
+
+
+# ---------------------------------------------------------------- selection language
+_BB_RES = set("A A3 A5 ALA ARG ASN ASP C C3 C5 CYS CYX DA DC DG DT G G3 G5 GLN GLU GLY HID HIE HIP HIS HSD HSE HSP ILE "
+              "LEU LYS MET MSE PHE PRO PTR SER T T3 T5 THR TRP TYR U U3 U5 VAL".split())   # src/Selectors.cpp:37-86
+_BB_ATOM = set("C C1' C2' C3' C4' C5' CA H H1' H12' H15' H2' H2'' H22' H25' H3' H4' H5' H5'' HO2' HO3' HO5' N O O2' "
+               "O3' O4' O5' OP1 OP2 OP3 OXT P".split())                                       # :88-122
+
+_LITS = ["<=", ">=", "==", "!=", "=~", "&&", "||", "->", "<", ">", "!", "hydrogen", "backbone", "resname", "segname",
+         "chainid", "segid", "resid", "index", "name", "not", "all", "ne", "id"]
+
+
+def _lex(text):  # src/scanner.ll:29-81 (longest match, no word boundaries)
+    toks, p = [], 0
+    while p < len(text):
+        c = text[p]
+        if c in " \t\n+":
+            p += 1
+            continue
+        if c == "#" and p + 1 < len(text) and text[p + 1] != "\n":
+            while p < len(text) and text[p] != "\n":
+                p += 1
+            continue
+        if c.isdigit():
+            q = p
+            while q < len(text) and text[q].isdigit():
+                q += 1
+            toks.append(("num", int(text[p:q])))
+            p = q
+            continue
+        best = max((l for l in _LITS if text.startswith(l, p)), key=len, default=None)
+        if best:
+            toks.append(("lit", best))
+            p += len(best)
+            continue
+        if c in "\"'":
+            q = p + 1
+            s = ""
+            while q < len(text) and text[q] not in (c, "\n"):
+                s += text[q]
+                q += 1
+            if q >= len(text):
+                raise ValueError("unterminated string")
+            toks.append(("str", s))
+            p = q + 1
+            continue
+        toks.append(("chr", c))
+        p += 1
+    toks.append(("end", None))
+    return toks
+
+
+class _P:  # src/grammar.yy:80-148, evaluated directly per atom (src/KernelActions.cpp:33-297)
+    def __init__(self, toks):
+        self.t, self.p = toks, 0
+
+    def cur(self):
+        return self.t[self.p]
+
+    def value(self):
+        k, v = self.cur()
+        if (k, v) == ("chr", "("):
+            save = self.p
+            self.p += 1
+            r = self.value()
+            if r is not None and self.cur() == ("chr", ")"):
+                self.p += 1
+                return r
+            self.p = save
+            return None
+        if k == "num":
+            self.p += 1
+            return ("int", v)
+        if k == "str":
+            self.p += 1
+            return ("strlit", v)
+        if k == "lit" and v in ("id", "resid", "index"):
+            self.p += 1
+            return ("nkey", v)
+        if k == "lit" and v in ("name", "resname", "segid", "segname", "chainid"):
+            self.p += 1
+            if self.cur() == ("lit", "->"):
+                self.p += 1
+                kk, pat = self.cur()
+                if kk != "str":
+                    raise ValueError("pattern expected")
+                self.p += 1
+                return ("extract", v, re.compile(pat, re.I))
+            return ("skey", v)
+        return None
+
+    def rexpr(self):
+        k, v = self.cur()
+        if k == "lit" and v in ("!", "not"):
+            self.p += 1
+            return ("not", self.rexpr())
+        if k == "lit" and v in ("all", "hydrogen", "backbone"):
+            self.p += 1
+            return (v,)
+        save = self.p
+        lhs = self.value()
+        if lhs is not None:
+            k2, op = self.cur()
+            if k2 == "lit" and op == "=~":
+                if lhs[0] != "skey" or self.p != save + 1:
+                    raise ValueError("bad =~")
+                self.p += 1
+                kk, pat = self.cur()
+                if kk != "str":
+                    raise ValueError("pattern expected")
+                self.p += 1
+                return ("regex", lhs, re.compile(pat, re.I))
+            if k2 == "lit" and op in ("<", "<=", ">=", ">", "==", "!=", "ne"):
+                self.p += 1
+                rhs = self.value()
+                if rhs is None:
+                    raise ValueError("value expected")
+                return ("cmp", op, lhs, rhs)
+            self.p = save
+        if self.cur() == ("chr", "("):
+            self.p += 1
+            e = self.expr()
+            if self.cur() != ("chr", ")"):
+                raise ValueError("missing )")
+            self.p += 1
+            return e
+        raise ValueError("unexpected %r" % (self.cur(),))
+
+    def expr(self):
+        e = self.rexpr()
+        while self.cur() in (("lit", "&&"), ("lit", "||")):
+            op = self.cur()[1]
+            self.p += 1
+            e = (op, e, self.rexpr())     # same precedence, left associative (grammar.yy:70)
+        return e
+
+
+def _val(v, a):
+    if v[0] == "int":
+        return v[1]
+    if v[0] == "strlit":
+        return v[1]
+    if v[0] == "nkey":
+        return a[v[1]]
+    key = {"segname": "segid", "chainid": "chain"}.get(v[1], v[1])
+    s = a[key]
+    if v[0] == "skey":
+        return s
+    m = v[2].search(s)                       # extractNumber, KernelActions.cpp:156-172
+    if m:
+        for g in (m.group(0),) + m.groups():
+            mm = re.match(r"\s*[+-]?\d+", g or "")
+            if mm:
+                return int(mm.group(0))
+    return -1
+
+
+def _ev(e, a):
+    t = e[0]
+    if t == "all":
+        return True
+    if t == "hydrogen":
+        return a["name"][:1] == "H"
+    if t == "backbone":
+        return a["resname"] in _BB_RES and a["name"] in _BB_ATOM
+    if t == "not":
+        return not _ev(e[1], a)
+    if t in ("&&", "||"):
+        l, r = _ev(e[1], a), _ev(e[2], a)   # no short circuit in the stack machine
+        return (l and r) if t == "&&" else (l or r)
+    if t == "regex":
+        return e[2].search(_val(e[1], a)) is not None
+    op, x, y = e[1], _val(e[2], a), _val(e[3], a)
+    if isinstance(x, int) != isinstance(y, int):
+        raise ValueError("Comparing values with different types.")
+    if op in ("<", "<=") and ((isinstance(x, int) and x < 0) or (isinstance(y, int) and y < 0)):
+        return False                          # KernelActions.cpp:39-48,105-121
+    return {"<": x < y, "<=": x <= y, ">=": x >= y, ">": x > y, "==": x == y, "!=": x != y, "ne": x != y}[op]
+
+
+def select(atoms, selection):
+    p = _P(_lex(selection))
+    e = p.expr()
+    if p.cur()[0] != "end":
+        raise ValueError("trailing input")
+    return np.array([a["index"] for a in atoms if _ev(e, a)], dtype=np.uint32)
+
+
+# ---------------------------------------------------------------- frame ranges
+def parse_index_range(spec, maxsize):
+    """src/index_range_parser.cpp:60-173 (PEG alternatives in order, inclusive ends)."""
+    out = []
+    items = [x.strip() for x in spec.split(",")]
+    for it in items:
+        parts = [x.strip() for x in it.split(":")]
+        if not all(re.fullmatch(r"[+-]?\d*", x) for x in parts) or not 1 <= len(parts) <= 3:
+            raise ValueError("Could not parse range: " + spec)
+        if len(parts) == 1:
+            if not re.fullmatch(r"\d+", parts[0]):
+                raise ValueError("Could not parse range: " + spec)
+            a = int(parts[0]); b = a; st = 0
+        elif len(parts) == 2:
+            if re.fullmatch(r"\d+", parts[0]):            # uint ':' endpoint
+                if not re.fullmatch(r"\d*", parts[1]):
+                    raise ValueError("Could not parse range: " + spec)
+                a, b, st = int(parts[0]), (int(parts[1]) if parts[1] else maxsize), 1
+            elif parts[0] == "" and re.fullmatch(r"\d+", parts[1]):   # endpoint ':' uint
+                a, b, st = maxsize, int(parts[1]), -1
+            else:
+                raise ValueError("Could not parse range: " + spec)
+        else:
+            if not re.fullmatch(r"[+-]?\d+", parts[1]):
+                raise ValueError("Could not parse range: " + spec)
+            st = int(parts[1])
+            if re.fullmatch(r"\d+", parts[0]) and re.fullmatch(r"\d*", parts[2]):      # uint:int:endpoint
+                a, b = int(parts[0]), (int(parts[2]) if parts[2] else maxsize)
+            elif parts[0] == "" and re.fullmatch(r"\d+", parts[2]):                     # endpoint:int:uint
+                a, b = maxsize, int(parts[2])
+            else:
+                raise ValueError("Could not parse range: " + spec)
+        if (a < b and st < 0) or (a > b and st > 0):
+            raise ValueError("Invalid range")
+        if st == 0:
+            out.append(a)
+        elif st > 0:
+            out.extend(range(a, b + 1, st))
+        else:
+            out.extend(range(a, b - 1, st))
+    return np.array(out, dtype=np.uint32)
+
+
+def assign_frames(nframes, spec, skip, stride=1):   # src/utils_structural.cpp:113-123
+    if not spec:
+        return np.arange(skip, nframes, stride, dtype=np.uint32)
+    return parse_index_range(spec, nframes - 1)
+
+
+def multitraj_locations(sizes, skip, stride):       # src/MultiTraj.hpp:98-105, MultiTraj.cpp:48-58
+    locs = []
+    for t, n in enumerate(sizes):
+        cnt = 0 if n <= skip else (n - skip + stride - 1) // stride
+        locs += [(t, skip + k * stride) for k in range(cnt)]
+    return locs
+
+
+# ---------------------------------------------------------------- DCD (src/dcd.cpp:175-261,329-371)
+def read_dcd(path):
+    b = open(path, "rb").read()
+    e = "<" if struct.unpack("<i", b[:4])[0] == 84 else ">"
+    assert struct.unpack(e + "i", b[:4])[0] == 84 and b[4:8] == b"CORD"
+    icntrl = struct.unpack(e + "20i", b[8:88])
+    p = 92
+    n = struct.unpack(e + "i", b[p:p + 4])[0]
+    p += 8 + n
+    assert struct.unpack(e + "i", b[p:p + 4])[0] == 4
+    natoms = struct.unpack(e + "i", b[p + 4:p + 8])[0]
+    p += 12
+    xtal = icntrl[10] == 1
+    fsize = 12 * (2 + natoms) + (56 if xtal else 0)
+    nframes = icntrl[0] or ((len(b) - p) // fsize if (len(b) - p) % fsize == 0 else 0)
+    out = np.empty((nframes, 3, natoms), dtype=np.float32)
+    for f in range(nframes):
+        q = p + f * fsize + (56 if xtal else 0)
+        for k in range(3):
+            out[f, k] = np.frombuffer(b, dtype=np.dtype(np.float32).newbyteorder(e), count=natoms, offset=q + 4)
+            q += 8 + 4 * natoms
+    return out

@@ -1,0 +1,194 @@
+"""CPU tests of the native front-end (loos_b200/frontend, C++) against the Python
+restatement of the reference semantics in oracle/frontend_oracle.py: selection
+language, PDB/hybrid-36, frame ranges, MultiTrajectory indexing, DCD decoding and
+the Matrix text format -- all integer/byte/text work, so the bar is bit-exact."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from loos_b200.synth import synth_system, write_dcd, write_pdb
+from oracle import frontend_oracle as fo
+from oracle.oracle import matrix_text
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FE = os.path.join(ROOT, "loos_b200", "lib", "libloosb200fe.so")
+_u32p = C.POINTER(C.c_uint32)
+
+
+@pytest.fixture(scope="module")
+def fe():
+    if not os.path.exists(FE):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "loos_b200", "frontend")], check=True, stdout=subprocess.DEVNULL)
+    L = C.CDLL(FE)
+    L.lbfe_last_error.restype = C.c_char_p
+    L.lbfe_select.restype = C.c_long
+    L.lbfe_parse_range.restype = C.c_long
+    L.lbfe_assign_frames.restype = C.c_long
+    L.lbfe_multitraj.restype = C.c_long
+    L.lbfe_matrix_text.restype = C.c_long
+    L.lbfe_pdb_atoms.restype = C.c_long
+    return L
+
+
+@pytest.fixture(scope="module")
+def system(tmp_path_factory):
+    d = tmp_path_factory.mktemp("sys")
+    atoms, xyz = synth_system(40, 12, seed=77, flavour="rich")
+    # make the model harder: big ids/resids (hybrid-36), a negative resid, odd names
+    for k, a in enumerate(atoms):
+        a["resid"] = a["resid"] + 9990 if a["segid"] == "PROT" else a["resid"]
+    atoms[3]["name"] = "H12'"
+    atoms[7]["resname"] = "DA"
+    atoms[7]["name"] = "C1'"
+    pdb = str(d / "model.pdb")
+    write_pdb(pdb, atoms, xyz[0])
+    dcd = str(d / "traj.dcd")
+    write_dcd(dcd, xyz)
+    return dict(dir=d, pdb=pdb, dcd=dcd, atoms=atoms, xyz=xyz)
+
+
+SELECTIONS = [
+    "name == 'CA'", "all", "backbone", "hydrogen", "!hydrogen", "!(hydrogen || segid =~ 'SOLV|BULK')",
+    "name =~ '^C'", "name =~ 'c'", "resid >= 10000 && resid < 10010", "resid > 10020 || name == 'N'",
+    "name == 'CA' && resid < 10005 || name == 'O'", "name == 'O' || name == 'CA' && resid < 10005",
+    "not (name == 'CA')", "segname == 'SOLV'", "segid != 'PROT'", "resname ne 'ALA'", "index < 17", "index >= 200 && index <= 210",
+    "id > 100 && id <= 120", "(resid) == 10001", "(name == 'CA')", "((name == 'CA') && (index > 5))",
+    "name -> '(\\d+)' == 12", "name -> '(\\d+)' < 13", "name -> 'H(\\d)' >= 1", "chainid == 'W' && name == 'OH2'",
+    "resname =~ 'tip'", "name == \"CB\"", "backbone && !hydrogen", "name == 'CA' # trailing comment", "resid+ == 10003",
+]
+
+
+@pytest.mark.parametrize("sel", SELECTIONS)
+def test_selection_bit_exact(fe, system, sel):
+    want = fo.select(fo.read_pdb(system["pdb"]), sel)
+    out = np.zeros(len(system["atoms"]) + 8, dtype=np.uint32)
+    n = fe.lbfe_select(system["pdb"].encode(), sel.encode(), out.ctypes.data_as(_u32p), len(out))
+    assert n >= 0, fe.lbfe_last_error()
+    assert n == len(want) and np.array_equal(out[:n], want), (sel, n, len(want))
+    if sel in ("name == 'CA'", "backbone", "hydrogen"):
+        assert n > 0
+
+
+@pytest.mark.parametrize("sel", ["name == 5", "name ==", "name === 'CA'", "resid == 'A'", "foo == 1", "(name == 'CA'", "name =~ 3",
+                                 "'CA' =~ 'C'", "index"])
+def test_selection_errors(fe, system, sel):
+    out = np.zeros(8, dtype=np.uint32)
+    n = fe.lbfe_select(system["pdb"].encode(), sel.encode(), out.ctypes.data_as(_u32p), 8)
+    assert n == -1
+    with pytest.raises(Exception):
+        fo.select(fo.read_pdb(system["pdb"]), sel)
+
+
+def test_pdb_fields_and_hybrid36(fe, system):
+    atoms = fo.read_pdb(system["pdb"])
+    n = len(atoms)
+    ids = np.zeros(n, np.int64); resids = np.zeros(n, np.int64); xyz = np.zeros((n, 3)); names = C.create_string_buffer(16 * n)
+    got = fe.lbfe_pdb_atoms(system["pdb"].encode(), ids.ctypes.data_as(C.POINTER(C.c_long)),
+                            resids.ctypes.data_as(C.POINTER(C.c_long)), xyz.ctypes.data_as(C.POINTER(C.c_double)), names, n)
+    assert got == n == len(system["atoms"])
+    assert [a["id"] for a in atoms] == list(ids) and [a["resid"] for a in atoms] == list(resids)
+    assert max(resids) > 9999                      # the hybrid-36 branch was exercised
+    assert np.array_equal(xyz, np.array([a["xyz"] for a in atoms]))
+    raw = names.raw
+    for i, a in enumerate(atoms):
+        assert raw[16 * i:16 * i + 8].rstrip(b"\0").decode() == a["name"]
+        assert raw[16 * i + 8:16 * i + 16].rstrip(b"\0").decode() == a["segid"]
+    for field, val in [("    1", 1), ("99999", 99999), ("A0000", 100000), ("A0001", 100001), ("ZZZZZ", 43770015),
+                       ("a0000", 43770016), ("  -12", None), ("A000", 10000), ("9999", 9999), ("-123", -123)]:
+        got = fe.lbfe_hybrid36(field.encode(), len(field))
+        assert got == fo.hybrid36(field)
+        if val is not None:
+            assert got == val
+
+
+RANGES = ["5", "0:9", "3:", "0:2:20", "0:3:", "10:-1:0", "10:-3:2", ":5", ":-2:10", "1,5,9", "0:4,10:12,7", " 2 : 2 : 8 ", "7:7",
+          "0:1:0", "20:-5:", "4,4,4", "15:-1:15"]
+
+
+@pytest.mark.parametrize("spec", RANGES)
+def test_frame_ranges(fe, spec):
+    maxsize = 49
+    try:
+        want = fo.parse_index_range(spec, maxsize)
+    except ValueError:
+        want = None
+    out = np.zeros(4096, dtype=np.uint32)
+    n = fe.lbfe_parse_range(spec.encode(), maxsize, out.ctypes.data_as(_u32p), len(out))
+    if want is None:
+        assert n == -1
+    else:
+        assert n == len(want) and np.array_equal(out[:n], want), (spec, out[:n], want)
+
+
+@pytest.mark.parametrize("spec", ["10:0", "0:-1:10", "a:b", "1:2:3:4", "1,,2", "", "5:x", ":2:10", "-3"])
+def test_frame_range_errors(fe, spec):
+    out = np.zeros(64, dtype=np.uint32)
+    assert fe.lbfe_parse_range(spec.encode(), 49, out.ctypes.data_as(_u32p), 64) == -1
+    with pytest.raises(ValueError):
+        fo.parse_index_range(spec, 49)
+
+
+def test_assign_frames_sorted_vs_raw(fe):
+    out = np.zeros(256, dtype=np.uint32)
+    # rmsds keeps order and duplicates (Tools/rmsds.cpp:506); multi-rmsds / rmsd2ref sort + dedup
+    n = fe.lbfe_assign_frames(30, b"9,3:5,4,20:-10:0", 0, 1, 0, out.ctypes.data_as(_u32p), 256)
+    assert list(out[:n]) == [9, 3, 4, 5, 4, 20, 10, 0]
+    n = fe.lbfe_assign_frames(30, b"9,3:5,4,20:-10:0", 0, 1, 1, out.ctypes.data_as(_u32p), 256)
+    assert list(out[:n]) == [0, 3, 4, 5, 9, 10, 20]
+    n = fe.lbfe_assign_frames(30, b"", 7, 4, 0, out.ctypes.data_as(_u32p), 256)
+    assert list(out[:n]) == list(fo.assign_frames(30, "", 7, 4)) == [7, 11, 15, 19, 23, 27]
+
+
+@pytest.mark.parametrize("sizes,skip,stride", [([10, 7, 12], 0, 1), ([10, 7, 12], 3, 2), ([5, 2, 9], 4, 3), ([3], 3, 1), ([100, 1, 50], 10, 7)])
+def test_multitraj_indexing(fe, sizes, skip, stride):
+    want = fo.multitraj_locations(sizes, skip, stride)
+    s = np.array(sizes, dtype=np.uint32)
+    lt = np.zeros(512, np.uint32); lf = np.zeros(512, np.uint32)
+    n = fe.lbfe_multitraj(s.ctypes.data_as(_u32p), len(sizes), skip, stride, lt.ctypes.data_as(_u32p), lf.ctypes.data_as(_u32p), 512)
+    assert n == len(want)
+    assert [(int(a), int(b)) for a, b in zip(lt[:n], lf[:n])] == want
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(with_crystal=True), dict(big_endian=True), dict(header_nframes=0),
+                                dict(with_crystal=True, big_endian=True, header_nframes=0)])
+def test_dcd_decoding(fe, system, tmp_path, kw):
+    path = str(tmp_path / "t.dcd")
+    write_dcd(path, system["xyz"], **kw)
+    na, nf, xt = C.c_uint32(), C.c_uint32(), C.c_int()
+    assert fe.lbfe_dcd_info(path.encode(), C.byref(na), C.byref(nf), C.byref(xt)) == 0, fe.lbfe_last_error()
+    F, N, _ = system["xyz"].shape
+    assert (na.value, nf.value, bool(xt.value)) == (N, F, bool(kw.get("with_crystal")))
+    ref = fo.read_dcd(path)
+    assert np.array_equal(ref, system["xyz"].transpose(0, 2, 1))     # byte-exact float planes
+    buf = np.zeros((3, N), dtype=np.float32)
+    for f in (0, F - 1, F // 2):
+        assert fe.lbfe_dcd_read(path.encode(), f, buf.ctypes.data_as(C.POINTER(C.c_float))) == 0
+        assert np.array_equal(buf, ref[f])
+    assert fe.lbfe_dcd_read(path.encode(), F, buf.ctypes.data_as(C.POINTER(C.c_float))) == -1
+
+
+@pytest.mark.parametrize("prec", [0, 1, 2, 6, 8])
+def test_matrix_text_bytes(fe, prec):
+    rng = np.random.default_rng(3)
+    M = np.asfortranarray((rng.random((7, 5)) * 10.0 ** rng.integers(-6, 4, (7, 5))).astype(np.float32))
+    M[0, 0] = 0.0; M[1, 1] = 123456.0; M[2, 2] = 1e-5; M[3, 3] = 99.5
+    cap = 1 << 16
+    out = C.create_string_buffer(cap)
+    n = fe.lbfe_matrix_text(M.ctypes.data_as(C.POINTER(C.c_float)), 7, 5, 7, prec, out, cap)
+    assert out.raw[:n].decode() == matrix_text(M, prec)
+
+
+def test_tools_fail_loudly_without_gpu(system):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    exe = os.path.join(ROOT, "loos_b200", "bin", "rmsds")
+    r = subprocess.run([exe, system["pdb"], system["dcd"]], capture_output=True, text=True)
+    assert r.returncode == 255 and "no usable sm_100" in r.stderr and r.stdout == ""
+    r = subprocess.run([exe, system["pdb"]], capture_output=True, text=True)      # traj missing -> usage, exit(-1)
+    assert r.returncode == 255 and "Usage-" in r.stderr
+    r = subprocess.run([exe, "--sel", "all", system["pdb"], system["dcd"]], capture_output=True, text=True)
+    assert r.returncode == 255 and "unrecognised option '--sel'" in r.stderr   # no prefix guessing

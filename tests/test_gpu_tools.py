@@ -1,0 +1,143 @@
+"""GPU end-to-end tests of the drop-in tools (loos_b200/bin/rmsds, multi-rmsds,
+rmsd2ref): real PDB + DCD files in, the reference's stdout/stderr formats out,
+checked against the CPU oracle fed through the Python restatement of the
+reference's readers/selection (oracle/frontend_oracle.py)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from loos_b200.synth import synth_system, write_dcd, write_pdb
+from oracle import frontend_oracle as fo
+from oracle.oracle import matrix_text
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "loos_b200", "bin")
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("tools")
+    atoms, xyz = synth_system(60, 150, seed=4242, flavour="rich")
+    write_pdb(str(d / "model.pdb"), atoms, xyz[0])
+    write_dcd(str(d / "a.dcd"), xyz[:70])
+    write_dcd(str(d / "b.dcd"), xyz[70:115], with_crystal=True)
+    write_dcd(str(d / "c.dcd"), xyz[115:], big_endian=True)
+    write_dcd(str(d / "all.dcd"), xyz)
+    write_pdb(str(d / "target.pdb"), atoms, xyz[149])
+    return dict(d=d, atoms=fo.read_pdb(str(d / "model.pdb")), xyz=xyz)
+
+
+def run(tool, *args):
+    r = subprocess.run([os.path.join(BIN, tool)] + [str(a) for a in args], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return r.stdout, r.stderr
+
+
+def parse_matrix(out):
+    lines = out.splitlines()
+    hdr = [k for k, l in enumerate(lines) if re.fullmatch(r"# \d+ \d+ \(0\)", l)][0]
+    m, n = map(int, lines[hdr].split()[1:3])
+    M = np.array([[float(x) for x in l.split()] for l in lines[hdr + 1:hdr + 1 + m]])
+    assert M.shape == (m, n)
+    assert all(l.endswith(" ") for l in lines[hdr + 1:hdr + 1 + m])       # "value " per element
+    return lines[:hdr], M, "\n".join(lines[hdr:]) + "\n"
+
+
+def test_rmsds_default_and_precision(files, checker):
+    d = files["d"]
+    sel = fo.select(files["atoms"], "name == 'CA'")
+    ref = checker.rmsds_self(files["xyz"][:, sel].astype(np.float64), 8)
+    out, err = run("rmsds", d / "model.pdb", d / "all.dcd")
+    head, M, text = parse_matrix(out)
+    assert len(head) == 1 and head[0].startswith("# ") and "rmsds" in head[0] and "[loos-b200" in head[0]
+    want = matrix_text(ref, 2)
+    ta, tb = text.split(), want.split()
+    assert len(ta) == len(tb) and sum(x != y for x, y in zip(ta, tb)) <= 2   # 2-digit rounding boundaries only
+    assert err == ""
+    out8, _ = run("rmsds", "-p", "8", "--sel1", "name == 'CA'", d / "model.pdb", d / "all.dcd")
+    _, M8, _ = parse_matrix(out8)
+    assert np.abs(M8 - ref).max() <= 1e-4 and np.abs(M8 - ref).max() < 2e-5
+    assert np.all(np.diag(M8) == 0)
+
+
+def test_rmsds_unsorted_range_and_stats(files, checker):
+    d = files["d"]
+    sel = fo.select(files["atoms"], "backbone")
+    frames = fo.assign_frames(150, "40:-7:0,5,5,100:3:120", 0)       # rmsds keeps order and duplicates
+    ref = checker.rmsds_self(files["xyz"][frames][:, sel].astype(np.float64), 4)
+    out, err = run("rmsds", "--sel1", "backbone", "--range1", "40:-7:0,5,5,100:3:120", "--stats", "1", "-p", "7",
+                   d / "model.pdb", d / "all.dcd")
+    _, M, _ = parse_matrix(out)
+    assert M.shape == (len(frames),) * 2 and np.abs(M - ref).max() < 2e-5
+    low = ref[np.tril_indices(len(frames), -1)].astype(np.float64)
+    assert err.strip() == "Max rmsd = %.4f, avg rmsd = %.4f" % (low.max(), low.mean())
+    out, err = run("rmsds", "-N", "1", "--skip1", "100", d / "model.pdb", d / "all.dcd")
+    assert out == "" and err.startswith("Max rmsd = ")
+
+
+def test_rmsds_two_trajectories(files, checker):
+    d = files["d"]
+    s1 = fo.select(files["atoms"], "name == 'CA' && resid <= 30")
+    s2 = fo.select(files["atoms"], "name == 'CB' && resid > 30")
+    ref = checker.rmsds_cross(files["xyz"][:70][:, s1].astype(np.float64), files["xyz"][115:][:, s2].astype(np.float64), 4)
+    out, err = run("rmsds", "--sel1", "name == 'CA' && resid <= 30", "--sel2", "name == 'CB' && resid > 30", "-p", "7",
+                   "--stats", "1", d / "model.pdb", d / "a.dcd", d / "model.pdb", d / "c.dcd")
+    _, M, _ = parse_matrix(out)
+    assert M.shape == (70, 35) and np.abs(M - ref).max() < 2e-5
+    assert err.strip() == "Max rmsd = %.4f, avg rmsd = %.4f" % (ref.astype(np.float64).max(), ref.astype(np.float64).mean())
+
+
+def test_multi_rmsds_table_and_matrix(files, checker):
+    d = files["d"]
+    sizes = [70, 45, 35]
+    locs = fo.multitraj_locations(sizes, 4, 3)
+    starts = np.cumsum([0] + sizes)
+    glob = [starts[t] + f for t, f in locs]
+    sel = fo.select(files["atoms"], "name == 'CA'")
+    ref = checker.rmsds_self(files["xyz"][glob][:, sel].astype(np.float64), 4)
+    out, _ = run("multi-rmsds", "-k", "4", "-i", "3", "-p", "7", d / "model.pdb", d / "a.dcd", d / "b.dcd", d / "c.dcd")
+    head, M, _ = parse_matrix(out)
+    assert head[1] == "# traj\tstart\tend\tfilename"
+    counts = [0 if n <= 4 else (n - 4 + 2) // 3 for n in sizes]
+    s = 0
+    for k, (n, name) in enumerate(zip(counts, "abc")):
+        assert head[2 + k] == "# %d\t%d\t%d\t%s" % (k, s, s + n - 1, d / (name + ".dcd"))
+        s += n
+    assert M.shape == (sum(counts),) * 2 and np.abs(M - ref).max() < 2e-5
+    out, _ = run("multi-rmsds", "-r", "30:-10:0,5,5", "-p", "7", d / "model.pdb", d / "a.dcd", d / "b.dcd")
+    head, M, _ = parse_matrix(out)
+    assert head[1] == "# Note- composite frame range used was '30:-10:0,5,5'"
+    ref = checker.rmsds_self(files["xyz"][[0, 5, 10, 20, 30]][:, sel].astype(np.float64), 2)   # sorted + unique
+    assert np.abs(M - ref).max() < 2e-5
+
+
+def test_rmsd2ref_target_and_iterative(files, checker):
+    d = files["d"]
+    atoms, xyz = files["atoms"], files["xyz"].astype(np.float64)
+    sa = fo.select(atoms, "name == 'CA'")
+    sr = fo.select(atoms, "!(hydrogen || segid =~ 'SOLV|BULK')")
+    tgt = np.array([a["xyz"] for a in fo.read_pdb(str(d / "target.pdb"))])
+    ref, _ = checker.rmsd2ref_target(xyz[:, sa], xyz[:, sr], tgt[sa], tgt[sr])
+    out, err = run("rmsd2ref", "--target", d / "target.pdb", d / "model.pdb", d / "all.dcd")
+    lines = out.splitlines()
+    assert lines[0].startswith("# ") and len(lines) == 151
+    got = np.array([float(l.split("\t")[1]) for l in lines[1:]])
+    assert [int(l.split("\t")[0]) for l in lines[1:]] == list(range(150))
+    assert np.abs(got - ref).max() < 1e-5 * np.maximum(1, ref).max()           # 6 significant digits printed
+    assert "Warning: Using --align selection for target" in err and "Computing RMSD vs target" in err
+    assert ("Average RMSD was %.3f, std RMSD was %.3f" % (ref.mean(), ref.std(ddof=1))) in err
+    # default mode: iterative alignment to the running average, frames 10..59 by --range
+    sub = np.arange(10, 60)
+    it = checker.rmsd2ref_iterative(xyz[sub][:, sa], xyz[sub][:, sr], 1e-6, 1000)
+    out, err = run("rmsd2ref", "-r", "10:59", d / "model.pdb", d / "all.dcd")
+    got = np.array([float(l.split("\t")[1]) for l in out.splitlines()[1:]])
+    assert np.abs(got - it[0]).max() < 1e-5 * np.maximum(1, it[0]).max()
+    assert "Computing using average structure..." in err and "Aligning using 60 atoms" in err
+    # skip + range together is an error (src/OptionsFramework.cpp:375-379)
+    r = subprocess.run([os.path.join(BIN, "rmsd2ref"), "-k", "3", "-r", "0:5", str(d / "model.pdb"), str(d / "all.dcd")],
+                       capture_output=True, text=True)
+    assert r.returncode == 255 and "cannot specify both a skip and a frame range" in r.stderr
