@@ -116,7 +116,7 @@ static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool sym
   const size_t out_cols = packed ? 0 : FB;                          // else: FB columns of ld
   const size_t dev_ld = (okind == OutKind::Host) ? (packed ? FB : FA) : ld;
 
-  const int maxbands = (okind == OutKind::Host) ? 12 : 1;
+  const int maxbands = (okind == OutKind::Host) ? 16 : 1;
   Bands B = make_bands(rows, self, col_tiles, maxbands);
 
   uint32_t *d_rows = nullptr, *d_prefix = nullptr;
@@ -174,16 +174,23 @@ static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool sym
       cudaEventRecord(evs[k], st);
       cudaStreamWaitEvent(copy_stream, evs[k], 0);
       if (packed) {
-        // rows of the band are contiguous in the packed buffer
+        // rows of the band are contiguous in the packed buffer; only columns j < i exist
         const size_t r_lo = (size_t)bd.r0 * TILE_FRAMES, nr = (size_t)(bd.r1 - bd.r0) * TILE_FRAMES;
+        const size_t width = std::min(FB, ((size_t)B.rows[bd.r1 - 1] + 1) * TILE_FRAMES);
         cudaMemcpy2DAsync(out + r_lo * ld, ld * sizeof(float), d_out + r_lo * dev_ld, dev_ld * sizeof(float),
-                          FB * sizeof(float), nr, cudaMemcpyDeviceToHost, copy_stream);
+                          width * sizeof(float), nr, cudaMemcpyDeviceToHost, copy_stream);
       } else if (self) {
-        // columns [c0, c1) are final once all rows >= c0 are done (bands run last-to-first)
-        const size_t c0 = (size_t)B.rows[bd.r0] * TILE_FRAMES;
-        const size_t c1 = std::min(FA, ((size_t)B.rows[bd.r1 - 1] + 1) * TILE_FRAMES);
-        cudaMemcpy2DAsync(out + c0 * ld, ld * sizeof(float), d_out + c0 * dev_ld, dev_ld * sizeof(float),
-                          FA * sizeof(float), c1 - c0, cudaMemcpyDeviceToHost, copy_stream);
+        // Everything that involves the band's rows [R0, R1) is final once the band is done:
+        // the row strip rows [R0,R1) x cols [0,R1) and its mirror cols [R0,R1) x rows [0,R0).
+        // Both are copied now, so the D2H volume of a band is proportional to its work
+        // and only the last band's copy is exposed.
+        const size_t R0 = (size_t)B.rows[bd.r0] * TILE_FRAMES;
+        const size_t R1 = std::min(FA, ((size_t)B.rows[bd.r1 - 1] + 1) * TILE_FRAMES);
+        cudaMemcpy2DAsync(out + R0, ld * sizeof(float), d_out + R0, dev_ld * sizeof(float),
+                          (R1 - R0) * sizeof(float), R1, cudaMemcpyDeviceToHost, copy_stream);
+        if (R0 > 0)
+          cudaMemcpy2DAsync(out + R0 * ld, ld * sizeof(float), d_out + R0 * dev_ld, dev_ld * sizeof(float),
+                            R0 * sizeof(float), R1 - R0, cudaMemcpyDeviceToHost, copy_stream);
       }
     }
   }

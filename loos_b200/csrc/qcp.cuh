@@ -279,4 +279,73 @@ LB_HD void qcp_rotation(const double* R, double* Z, double* lambda_out) {
   Z[6] = 2 * (x * z - w * y);           Z[7] = 2 * (y * z + w * x);           Z[8] = w * w - x * x - y * y + z * z;
 }
 
+// Rotation for the streaming path without the Jacobi sweeps: lambda_max from the
+// quartic (fp64 coefficients, fp32 Newton, fp64 correction), then the eigenvector as the
+// best-conditioned column of adj(K - lambda I) = prod(lambda - lambda_i) q q^T.
+// Returns false (caller falls back to qcp_rotation) when the top eigenvalue is not
+// well separated -- collinear / planar / N < 3 inputs -- or the solve did not settle.
+LB_HD bool qcp_rotation_fast(const double* R, double ga, double gb, double* Z) {
+  const double e0 = 0.5 * (ga + gb);
+  if (!(e0 > 0.0)) return false;
+  const QcpPoly p = qcp_poly(R, e0);
+  const float f0 = (float)p.c0, f1 = (float)p.c1, f2 = (float)p.c2, f3 = (float)p.c3;
+  float t = p.t0, st = 0.0f;
+  for (int it = 0; it < 12; ++it) st = qcp_newton_step(f0, f1, f2, f3, t);
+  bool ok;
+  double y = qcp_polish(p, t, st, &ok);
+  if (!ok) return false;
+  // a second fp64 Newton step on the same quartic: the eigenvector needs lambda to ~1e-15
+  {
+    double td = p.xform ? 1.0 - y : y;
+    const double fd = fma(td, fma(td, fma(td, td + p.c3, p.c2), p.c1), p.c0);
+    const double dd = fma(td, fma(td, fma(td, 4.0, 3.0 * p.c3), 2.0 * p.c2), p.c1);
+    if (dd != 0.0) td -= fd / dd;
+    y = p.xform ? 1.0 - td : td;
+  }
+  const double lam = (1.0 - y);  // in units of e0
+  const double inv = 1.0 / e0;
+  double S[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) S[k] = R[k] * inv;
+  double Kd[10];
+  qcp_build_K(S, Kd);
+  // A = K - lam I (symmetric), row-major upper triangle -> full
+  const double a00 = Kd[0] - lam, a01 = Kd[1], a02 = Kd[2], a03 = Kd[3];
+  const double a11 = Kd[4] - lam, a12 = Kd[5], a13 = Kd[6];
+  const double a22 = Kd[7] - lam, a23 = Kd[8];
+  const double a33 = Kd[9] - lam;
+  // 2x2 minors of rows (2,3) and of rows (0,1)
+  const double m23_01 = a02 * a13 - a03 * a12, m23_02 = a02 * a23 - a03 * a22, m23_03 = a02 * a33 - a03 * a23;
+  const double m23_12 = a12 * a23 - a13 * a22, m23_13 = a12 * a33 - a13 * a23, m23_23 = a22 * a33 - a23 * a23;
+  const double m01_01 = a00 * a11 - a01 * a01, m01_02 = a00 * a12 - a01 * a02, m01_03 = a00 * a13 - a01 * a03;
+  const double m01_12 = a01 * a12 - a11 * a02, m01_13 = a01 * a13 - a11 * a03, m01_23 = a02 * a13 - a12 * a03;
+  // adjugate (symmetric) by Laplace expansion over row pairs; here m23_xy is the minor of
+  // rows 2,3 and columns x,y, m01_xy that of rows 0,1
+  const double d00 = a11 * m23_23 - a12 * m23_13 + a13 * m23_12;
+  const double d01 = -(a01 * m23_23 - a12 * m23_03 + a13 * m23_02);
+  const double d02 = a01 * m23_13 - a11 * m23_03 + a13 * m23_01;
+  const double d03 = -(a01 * m23_12 - a11 * m23_02 + a12 * m23_01);
+  const double d11 = a00 * m23_23 - a02 * m23_03 + a03 * m23_02;
+  const double d12 = -(a00 * m23_13 - a01 * m23_03 + a03 * m23_01);
+  const double d13 = a00 * m23_12 - a01 * m23_02 + a02 * m23_01;
+  const double d22 = a33 * m01_01 - a13 * m01_03 + a03 * m01_13;
+  const double d23 = -(a23 * m01_01 - a13 * m01_02 + a03 * m01_12);
+  const double d33 = a22 * m01_01 - a12 * m01_02 + a02 * m01_12;
+  (void)m01_23;
+  // best-conditioned column: the largest diagonal entry ~ q_k^2
+  double q0 = d00, q1 = d01, q2 = d02, q3 = d03, dm = fabs(d00);
+  if (fabs(d11) > dm) { dm = fabs(d11); q0 = d01; q1 = d11; q2 = d12; q3 = d13; }
+  if (fabs(d22) > dm) { dm = fabs(d22); q0 = d02; q1 = d12; q2 = d22; q3 = d23; }
+  if (fabs(d33) > dm) { dm = fabs(d33); q0 = d03; q1 = d13; q2 = d23; q3 = d33; }
+  // |adj| = |P'(lambda)| = prod of gaps: tiny => (near-)multiple eigenvalue
+  if (!(dm > 1e-7)) return false;
+  const double n2 = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
+  const double sN = 1.0 / sqrt(n2);
+  const double w = q0 * sN, x = q1 * sN, yv = q2 * sN, z = q3 * sN;
+  Z[0] = w * w + x * x - yv * yv - z * z; Z[1] = 2 * (x * yv - w * z);           Z[2] = 2 * (x * z + w * yv);
+  Z[3] = 2 * (x * yv + w * z);           Z[4] = w * w - x * x + yv * yv - z * z; Z[5] = 2 * (yv * z - w * x);
+  Z[6] = 2 * (x * z - w * yv);           Z[7] = 2 * (yv * z + w * x);           Z[8] = w * w - x * x - yv * yv + z * z;
+  return true;
+}
+
 }  // namespace loosb200

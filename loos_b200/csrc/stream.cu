@@ -52,6 +52,7 @@ struct StreamArgs {
   const double* refA;   // [3][NpadA] centred reference (align selection)
   double refA_c[3];     // its centroid before centring
   double refA_sum[3];   // sum of the centred reference (~0; kept for exactness)
+  double refA_g;        // sum of squares of the centred reference
   const double* refR;   // [3][NpadR] uncentred reference (rmsd selection)
   double* xf;           // [F][16] in/out
   double* out_rmsd;     // [F]
@@ -163,6 +164,103 @@ __global__ void __launch_bounds__(ST) k_stream(const StreamArgs a) {
       if (acc_s[i] != 0.0) atomicAdd(&a.avg[i], acc_s[i]);
 }
 
+// Warp-per-frame variant for the modes without accumulation (rmsd2ref with a target,
+// final per-frame RMSD of the iterative mode): one warp owns a frame, so the warps of
+// an SM keep hundreds of KB of loads in flight, nothing is block-synchronised, and the
+// 3x3 solve (quartic + adjugate eigenvector, redundantly in every lane) is ~300 fp64
+// instructions instead of a Jacobi sweep in local memory.  This is the HBM-bound
+// kernel of the path: 12 N_align (+ 12 N_rmsd) bytes per frame.
+constexpr int SW_THREADS = 256;
+
+__device__ __forceinline__ double wsum_all(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(SW_THREADS) k_stream_warp(const StreamArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp_global = (blockIdx.x * SW_THREADS + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * SW_THREADS) >> 5;
+  for (uint32_t f = warp_global; f < a.F; f += nwarps) {
+    double W[12];
+    if (a.mode & M_COMPUTE_W) {
+      const float4* px = reinterpret_cast<const float4*>(a.rawA + ((size_t)f * 3 + 0) * a.NpadA);
+      const float4* py = reinterpret_cast<const float4*>(a.rawA + ((size_t)f * 3 + 1) * a.NpadA);
+      const float4* pz = reinterpret_cast<const float4*>(a.rawA + ((size_t)f * 3 + 2) * a.NpadA);
+      const double2* rx = reinterpret_cast<const double2*>(a.refA);
+      const double2* ry = reinterpret_cast<const double2*>(a.refA + a.NpadA);
+      const double2* rz = reinterpret_cast<const double2*>(a.refA + 2 * a.NpadA);
+      double s[13];
+#pragma unroll
+      for (int k = 0; k < 13; ++k) s[k] = 0.0;
+      for (uint32_t i4 = lane; i4 < a.NpadA / 4; i4 += 32) {
+        const float4 X = __ldcs(px + i4), Y = __ldcs(py + i4), Z = __ldcs(pz + i4);  // streamed once
+        const double2 vx0 = __ldg(rx + 2 * i4), vx1 = __ldg(rx + 2 * i4 + 1);
+        const double2 vy0 = __ldg(ry + 2 * i4), vy1 = __ldg(ry + 2 * i4 + 1);
+        const double2 vz0 = __ldg(rz + 2 * i4), vz1 = __ldg(rz + 2 * i4 + 1);
+        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+        const double vxs[4] = {vx0.x, vx0.y, vx1.x, vx1.y}, vys[4] = {vy0.x, vy0.y, vy1.x, vy1.y},
+                     vzs[4] = {vz0.x, vz0.y, vz1.x, vz1.y};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double x = xs[k], y = ys[k], z = zs[k];
+          s[0] += x; s[1] += y; s[2] += z;
+          s[3] = fma(x, vxs[k], s[3]); s[4] = fma(x, vys[k], s[4]); s[5] = fma(x, vzs[k], s[5]);
+          s[6] = fma(y, vxs[k], s[6]); s[7] = fma(y, vys[k], s[7]); s[8] = fma(y, vzs[k], s[8]);
+          s[9] = fma(z, vxs[k], s[9]); s[10] = fma(z, vys[k], s[10]); s[11] = fma(z, vzs[k], s[11]);
+          s[12] = fma(x, x, fma(y, y, fma(z, z, s[12])));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 13; ++k) s[k] = wsum_all(s[k]);
+      const double uc[3] = {s[0] / a.Na, s[1] / a.Na, s[2] / a.Na};
+      double R[9];
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) R[3 * p + q] = s[3 + 3 * p + q] - uc[p] * a.refA_sum[q];
+      // the frame's own centred sum of squares: with E0 = (ga + gb)/2 the quartic's root is <= 1
+      const double ga = s[12] - (double)a.Na * (uc[0] * uc[0] + uc[1] * uc[1] + uc[2] * uc[2]);
+      double Z[9];
+      if (!qcp_rotation_fast(R, ga, a.refA_g, Z)) qcp_rotation(R, Z, 0);  // degenerate: Jacobi
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        W[4 * i] = Z[3 * i]; W[4 * i + 1] = Z[3 * i + 1]; W[4 * i + 2] = Z[3 * i + 2];
+        W[4 * i + 3] = a.refA_c[i] - (Z[3 * i] * uc[0] + Z[3 * i + 1] * uc[1] + Z[3 * i + 2] * uc[2]);
+      }
+      if (a.xf && lane == 0) {
+        double* o = a.xf + (size_t)f * 16;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) o[k] = W[k];
+        o[12] = o[13] = o[14] = 0.0; o[15] = 1.0;
+      }
+    } else if (a.mode & M_IDENTITY) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) W[k] = (k % 5 == 0) ? 1.0 : 0.0;
+      if (a.xf && lane < 16) a.xf[(size_t)f * 16 + lane] = (lane % 5 == 0) ? 1.0 : 0.0;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) W[k] = a.xf[(size_t)f * 16 + k];
+    }
+    if (a.mode & M_RMSD) {
+      const float* px = a.rawR + ((size_t)f * 3 + 0) * a.NpadR;
+      const float* py = px + a.NpadR, *pz = py + a.NpadR;
+      const double* rx = a.refR, *ry = rx + a.NpadR, *rz = ry + a.NpadR;
+      double d = 0.0;
+      for (uint32_t i = lane; i < a.Nr; i += 32) {  // second pass: L1/L2 hits when the selections coincide
+        const double x = px[i], y = py[i], z = pz[i];
+        const double ex = rx[i] - (W[0] * x + W[1] * y + W[2] * z + W[3]);
+        const double ey = ry[i] - (W[4] * x + W[5] * y + W[6] * z + W[7]);
+        const double ez = rz[i] - (W[8] * x + W[9] * y + W[10] * z + W[11]);
+        d += ex * ex + ey * ey + ez * ez;
+      }
+      d = wsum_all(d);
+      if (lane == 0) a.out_rmsd[f] = sqrt(d / a.Nr);
+    }
+  }
+}
+
 // avg /= F; rms = sqrt(sum |avg - target|^2 / n) (AtomicGroup::rmsd); then the new
 // target := avg, stored centred with its centroid (kabsch centres it anyway).
 // target_c holds the uncentred target as [3][Npad] = tgt_centred + centroid.
@@ -249,6 +347,17 @@ int grid_for(uint32_t F, bool accum) {
   return (int)((F < (uint32_t)g) ? F : (uint32_t)g);
 }
 
+int grid_warp(uint32_t F) {  // persistent: as many CTAs as fit, each warp walks frames
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stream_warp, SW_THREADS, 0);
+  if (per_sm < 1) per_sm = 1;
+  const uint32_t need = (F + SW_THREADS / 32 - 1) / (SW_THREADS / 32);
+  const uint32_t cap = (uint32_t)(sms * per_sm);
+  return (int)(need < cap ? need : cap);
+}
+
 int smem_for_accum(size_t Npad) { return (int)(3 * Npad * sizeof(double)); }
 
 }  // namespace
@@ -297,10 +406,12 @@ extern "C" int loosb200_rmsd2ref(loosb200_frames* align, loosb200_frames* rmsd_s
   a.rawR = rs->raw; a.NpadR = rs->Npad; a.Nr = (uint32_t)rs->N;
   a.refA = dA; a.refR = dR;
   for (int k = 0; k < 3; ++k) { a.refA_c[k] = c[k]; a.refA_sum[k] = cs[k]; }
+  a.refA_g = 0.0;
+  for (double v : soaA) a.refA_g += v * v;
   a.xf = dXf; a.out_rmsd = dOut; a.F = (uint32_t)F;
   a.mode = (ref_align ? M_COMPUTE_W : M_IDENTITY) | M_RMSD;
   cudaEventRecord(align->timing.ev[1], st);
-  k_stream<<<grid_for((uint32_t)F, false), ST, 0, st>>>(a);
+  k_stream_warp<<<grid_warp((uint32_t)F), SW_THREADS, 0, st>>>(a);
   cudaEventRecord(align->timing.ev[2], st);
   cudaMemcpyAsync(out_rmsd, dOut, sizeof(double) * F, cudaMemcpyDeviceToHost, st);
   if (out_xforms) cudaMemcpyAsync(out_xforms, dXf, sizeof(double) * 16 * F, cudaMemcpyDeviceToHost, st);
@@ -386,7 +497,7 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
     k_scale<<<(unsigned)((3 * NpR + 255) / 256), 256, 0, st>>>(dAvgR, 3 * NpR, 1.0 / (double)F);
     // per-frame rmsd to the average: rmsd2ref.cpp:238-245
     a.mode = M_RMSD; a.refR = dAvgR; a.avg = nullptr;
-    k_stream<<<grid_for((uint32_t)F, false), ST, 0, st>>>(a);
+    k_stream_warp<<<grid_warp((uint32_t)F), SW_THREADS, 0, st>>>(a);
     launches += 3;
     cudaEventRecord(align->timing.ev[2], st);
     cudaMemcpyAsync(out_rmsd, dOut, sizeof(double) * F, cudaMemcpyDeviceToHost, st);
