@@ -162,6 +162,9 @@ static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool sym
     job.packed_rows = packed;
     job.out = d_out ? (packed ? d_out + (size_t)bd.r0 * TILE_FRAMES * dev_ld : d_out) : nullptr;
     job.stats_dev = stats ? d_stats : nullptr;
+    while (a->timing.kev.size() < 2 * (k + 1)) { cudaEvent_t e = nullptr; cudaEventCreate(&e); a->timing.kev.push_back(e); }
+    job.ev_k0 = a->timing.kev[2 * k]; job.ev_k1 = a->timing.kev[2 * k + 1];
+    a->timing.kev_used = (int)(2 * (k + 1));
     if (engine == LOOSB200_ENGINE_TENSOR) {
       int l = 0;
       rc = launch_pairs_tensor(job, st, &l);
@@ -341,6 +344,14 @@ extern "C" int loosb200_last_timing(const loosb200_frames* h, double* ms_main, d
   float t_all = 0.f, t_main = 0.f;
   LB_CUDA(cudaEventElapsedTime(&t_all, h->timing.ev[0], h->timing.ev[3]));
   LB_CUDA(cudaEventElapsedTime(&t_main, h->timing.ev[1], h->timing.ev[2]));
+  if (h->timing.kev_used > 0) {  // precise: events right around every contraction launch
+    t_main = 0.f;
+    for (int k = 0; k + 1 < h->timing.kev_used; k += 2) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, h->timing.kev[k], h->timing.kev[k + 1]) == cudaSuccess) t_main += t;
+    }
+    cudaGetLastError();
+  }
   if (ms_main) *ms_main = t_main;
   if (ms_other) *ms_other = t_all - t_main;
   return h->timing.launches;

@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/loosb200.h"
 
@@ -45,6 +46,9 @@ struct Timing {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, main0, main1, end
   int launches = 0;
   bool valid = false;
+  // per-band events recorded right around the contraction kernel (ms_main = their sum)
+  std::vector<cudaEvent_t> kev;
+  int kev_used = 0;
 };
 
 }  // namespace loosb200
@@ -93,6 +97,7 @@ struct PairJob {
   uint64_t n_tiles;
   bool packed_rows;           // out row index = position in the launch's row list
   double* stats_dev;          // [2]: sum, max-as-bits ; may be null
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // optional: recorded right around the contraction kernel
 };
 
 int ensure_quantised(loosb200_frames* h, int force_unit_log2 /* INT_MIN: auto */);

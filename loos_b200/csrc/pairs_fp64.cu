@@ -156,11 +156,13 @@ int launch_pairs_fp64(const PairJob& job, cudaStream_t st) {
   if (job.n_tiles > 0x7fffffffull) return LOOSB200_ERR_UNSUPPORTED;
   const loosb200_frames* a = job.a;
   const loosb200_frames* b = job.b;
+  if (job.ev_k0) cudaEventRecord(job.ev_k0, st);
   k_pairs_fp64<<<(unsigned)job.n_tiles, NT, 0, st>>>(
       a->raw, a->centroid, a->gd, (uint32_t)a->F, a->Npad, b->raw, b->centroid, b->gd,
       (uint32_t)b->F, b->Npad, (uint32_t)a->N, job.row_tiles_dev, job.tile_prefix_dev,
       job.n_row_tiles, job.self ? 1 : 0, job.symmetric ? 1 : 0, job.packed_rows ? 1 : 0, job.out,
       job.ld, job.stats_dev);
+  if (job.ev_k1) cudaEventRecord(job.ev_k1, st);
   LB_CUDA(cudaGetLastError());
   return LOOSB200_OK;
 }

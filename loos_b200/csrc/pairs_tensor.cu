@@ -152,8 +152,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
   } while (0)
 
 struct TensorArgs {
-  const uint2* tiles;          // (row tile index within the launch, column tile J)
-  uint32_t n_tiles;
+  const uint4* sblocks;        // super-blocks: {first row index, #rows, first column tile, #columns}
+  const uint32_t* sb_prefix;   // [n_sb + 1] prefix sum of #rows * #columns (tile slots)
+  uint32_t n_slots;            // total slots; slots above the diagonal are skipped by every role alike
   const uint32_t* row_tiles;   // row tile index -> I
   const long long* gA; const long long* gB;
   uint32_t FA, FB, N, n_kchunks;
@@ -163,6 +164,31 @@ struct TensorArgs {
   double* stats;
   int release_at;  // when the epilogue hands TMEM back (see kernel)
   long long* prof;  // optional [grid][14 warps][8] cycle counters (LOOSB200_PROF=1)
+};
+
+
+// Tile slots are numbered super-block by super-block (row-major inside); CTA c takes
+// slots c, c + grid, ...  All three warp roles walk the same sequence and apply the same
+// "is this a tile of the lower triangle" test, so they stay in step without talking.
+struct TileWalk {
+  uint32_t slot, sb;
+  __device__ __forceinline__ TileWalk() : slot(blockIdx.x), sb(0) {}
+  // Next valid tile: returns false when the CTA is done.  rt = row index within the launch.
+  __device__ __forceinline__ bool next(const TensorArgs& a, uint32_t& rt, uint32_t& I, uint32_t& J) {
+    for (; slot < a.n_slots; slot += gridDim.x) {
+      while (slot >= a.sb_prefix[sb + 1]) ++sb;
+      const uint4 b = a.sblocks[sb];
+      const uint32_t local = slot - a.sb_prefix[sb];
+      const uint32_t lr = local / b.w, lc = local - lr * b.w;
+      rt = b.x + lr;
+      I = a.row_tiles[rt];
+      J = b.z + lc;
+      if (a.self && (uint64_t)J * COL_TILE_FRAMES >= (uint64_t)I * TILE_FRAMES + TILE_FRAMES) continue;
+      slot += gridDim.x;
+      return true;
+    }
+    return false;
+  }
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -194,10 +220,11 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
       uint32_t stage = 0, phase = 0;
-      for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
-        const uint2 tl = a.tiles[t];
-        const int rowA = (int)a.row_tiles[tl.x] * TILE_ROWS;
-        const int rowB = (int)tl.y * COL_TILE_ROWS;
+      TileWalk walk;
+      uint32_t rt, I, J;
+      while (walk.next(a, rt, I, J)) {
+        const int rowA = (int)I * TILE_ROWS;
+        const int rowB = (int)J * COL_TILE_ROWS;
         for (uint32_t kc = 0; kc < a.n_kchunks; ++kc) {
           mbar_wait<200>(&ctl->empty[stage], phase ^ 1);
           unsigned char* sA = smem + stage * STAGE_BYTES;
@@ -215,7 +242,9 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       uint32_t stage = 0, phase = 0, tphase = 0;
       long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       long long tprev = a.prof ? clock64() : 0;
-      for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+      TileWalk walk;
+      uint32_t rt, I, J;
+      while (walk.next(a, rt, I, J)) {
         mbar_wait<100>(&ctl->tmem_empty, tphase ^ 1);  // epilogue has drained the previous tile
         tc_fence_after();
         LB_TICK(0);  // waiting for TMEM
@@ -268,9 +297,9 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = a.prof ? clock64() : 0;
 
-    for (uint32_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x, buf ^= 1) {
-      const uint2 tl = a.tiles[t];
-      const uint32_t I = a.row_tiles[tl.x], J = tl.y;
+    TileWalk walk;
+    uint32_t rt, I, J;
+    for (; walk.next(a, rt, I, J); buf ^= 1) {
       const uint32_t i = I * TILE_FRAMES + a_local;
       const bool i_ok = active && i < a.FA;
       const double ga = i_ok ? (double)a.gA[i] : 0.0;
@@ -428,7 +457,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int idx = et; idx < TILE_FRAMES * COL_TILE_FRAMES; idx += NUM_EPI_THREADS) {
             const int al_ = idx / COL_TILE_FRAMES, bl = idx - al_ * COL_TILE_FRAMES;
             const float val = ctl->T[buf][bl][al_];
-            if (val >= 0.0f) a.out[((size_t)tl.x * TILE_FRAMES + al_) * a.ld + j0 + bl] = val;
+            if (val >= 0.0f) a.out[((size_t)rt * TILE_FRAMES + al_) * a.ld + j0 + bl] = val;
           }
         } else {
           for (int idx = et; idx < TILE_FRAMES * COL_TILE_FRAMES; idx += NUM_EPI_THREADS) {
@@ -490,7 +519,9 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
     return LOOSB200_ERR_INVALID;
   const uint32_t FB = (uint32_t)B->F;
   const uint32_t ncol = (FB + COL_TILE_FRAMES - 1) / COL_TILE_FRAMES;
-  std::vector<uint2> tiles;
+  std::vector<uint4> sbl;
+  std::vector<uint32_t> prefix(1, 0u);
+  uint64_t slots = 0;
   for (uint32_t r0 = 0; r0 < job.n_row_tiles; r0 += SB_R) {
     const uint32_t r1 = std::min(job.n_row_tiles, r0 + SB_R);
     // columns needed by the last (largest) row tile of the group
@@ -499,26 +530,26 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
       const uint64_t last_i = (uint64_t)job.rows_host[r1 - 1] * TILE_FRAMES + TILE_FRAMES - 1;
       cmax = std::min<uint32_t>(ncol, (uint32_t)(last_i / COL_TILE_FRAMES) + 1);
     }
-    for (uint32_t c0 = 0; c0 < cmax; c0 += SB_C)
-      for (uint32_t r = r0; r < r1; ++r) {
-        uint32_t cend = std::min(cmax, c0 + SB_C);
-        if (job.self) {
-          const uint64_t last_i = (uint64_t)job.rows_host[r] * TILE_FRAMES + TILE_FRAMES - 1;
-          cend = std::min<uint32_t>(cend, (uint32_t)(last_i / COL_TILE_FRAMES) + 1);
-        }
-        for (uint32_t c = c0; c < cend; ++c) tiles.push_back(make_uint2(r, c));
-      }
+    for (uint32_t c0 = 0; c0 < cmax; c0 += SB_C) {
+      const uint32_t nc = std::min(cmax, c0 + SB_C) - c0;
+      sbl.push_back(make_uint4(r0, r1 - r0, c0, nc));
+      slots += (uint64_t)(r1 - r0) * nc;
+      prefix.push_back((uint32_t)slots);
+    }
   }
-  if (tiles.empty()) return LOOSB200_OK;
-  if (tiles.size() > 0xfffffff0ull) return LOOSB200_ERR_UNSUPPORTED;
+  if (slots == 0) return LOOSB200_OK;
+  if (slots > 0xfffffff0ull) return LOOSB200_ERR_UNSUPPORTED;
 
-  uint2* d_tiles = nullptr;
-  LB_CUDA(cudaMallocAsync(&d_tiles, sizeof(uint2) * tiles.size(), st));
-  LB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(uint2) * tiles.size(), cudaMemcpyHostToDevice, st));
-  // pageable source: the copy has been staged by the time the call returns
+  uint4* d_sbl = nullptr;
+  uint32_t* d_prefix = nullptr;
+  LB_CUDA(cudaMallocAsync(&d_sbl, sizeof(uint4) * sbl.size(), st));
+  LB_CUDA(cudaMallocAsync(&d_prefix, sizeof(uint32_t) * prefix.size(), st));
+  LB_CUDA(cudaMemcpyAsync(d_sbl, sbl.data(), sizeof(uint4) * sbl.size(), cudaMemcpyHostToDevice, st));
+  LB_CUDA(cudaMemcpyAsync(d_prefix, prefix.data(), sizeof(uint32_t) * prefix.size(), cudaMemcpyHostToDevice, st));
+  // pageable sources: the copies have been staged by the time the calls return
 
   TensorArgs ta;
-  ta.tiles = d_tiles; ta.n_tiles = (uint32_t)tiles.size();
+  ta.sblocks = d_sbl; ta.sb_prefix = d_prefix; ta.n_slots = (uint32_t)slots;
   ta.row_tiles = job.row_tiles_dev;
   ta.gA = A->gq; ta.gB = B->gq;
   ta.FA = (uint32_t)A->F; ta.FB = FB; ta.N = (uint32_t)A->N;
@@ -534,12 +565,14 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const unsigned grid = (unsigned)std::min<size_t>((size_t)sms, tiles.size());
+  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sms, slots);
   if (want_prof) {
     LB_CUDA(cudaMalloc(&ta.prof, sizeof(long long) * grid * 14 * 8));
     LB_CUDA(cudaMemsetAsync(ta.prof, 0, sizeof(long long) * grid * 14 * 8, st));
   }
+  if (job.ev_k0) cudaEventRecord(job.ev_k0, st);
   k_pairs_tensor<<<grid, NTHREADS, SMEM_BYTES, st>>>(A->tmapA, B->tmapB, ta);
+  if (job.ev_k1) cudaEventRecord(job.ev_k1, st);
   LB_CUDA(cudaGetLastError());
   if (want_prof) {
     std::vector<long long> hp((size_t)grid * 14 * 8);
@@ -548,14 +581,15 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
     cudaFree(ta.prof);
     const char* names_e[7] = {"wait_acc", "drain", "exch+poly", "newton", "polish", "barrier", "stores"};
     const char* names_m[3] = {"wait_tmem", "wait_operands", "issue"};
-    const double ntl = (double)tiles.size() / grid;
+    const double ntl = (double)job.n_tiles * TILE_FRAMES / COL_TILE_FRAMES / grid;  // approximate
     fprintf(stderr, "[loosb200 prof] tiles/CTA %.1f  cycles per tile (mean over CTAs):\n  MMA warp:", ntl);
     for (int k = 0; k < 3; ++k) { double s = 0; for (unsigned c = 0; c < grid; ++c) s += hp[((size_t)c * 14 + 1) * 8 + k]; fprintf(stderr, " %s=%.0f", names_m[k], s / grid / ntl); }
     fprintf(stderr, "\n  epilogue warps:");
     for (int k = 0; k < 7; ++k) { double s = 0; for (unsigned c = 0; c < grid; ++c) for (int w = 2; w < 14; ++w) s += hp[((size_t)c * 14 + w) * 8 + k]; fprintf(stderr, " %s=%.0f", names_e[k], s / grid / 12 / ntl); }
     fprintf(stderr, "\n");
   }
-  LB_CUDA(cudaFreeAsync(d_tiles, st));
+  LB_CUDA(cudaFreeAsync(d_sbl, st));
+  LB_CUDA(cudaFreeAsync(d_prefix, st));
   if (launches) *launches = 1;
   return LOOSB200_OK;
 }

@@ -380,6 +380,7 @@ extern "C" void loosb200_free(loosb200_frames* h) {
   cudaFree(h->raw); cudaFree(h->centroid); cudaFree(h->gd); cudaFree(h->maxabs);
   cudaFree(h->q8); cudaFree(h->gq); cudaFree(h->unit_log2_dev);
   for (int i = 0; i < 4; ++i) if (h->timing.ev[i]) cudaEventDestroy(h->timing.ev[i]);
+  for (cudaEvent_t e : h->timing.kev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   cudaGetLastError();
   delete h;

@@ -420,7 +420,7 @@ extern "C" int loosb200_rmsd2ref(loosb200_frames* align, loosb200_frames* rmsd_s
   if (e == cudaSuccess) e = cudaGetLastError();
   cudaFree(dA); cudaFree(dR); cudaFree(dOut); cudaFree(dXf);
   if (e != cudaSuccess) return cuda_fail(e, "k_stream", __FILE__, __LINE__);
-  align->timing.launches = 1; align->timing.valid = true;
+  align->timing.launches = 1; align->timing.valid = true; align->timing.kev_used = 0;
   return LOOSB200_OK;
 }
 
@@ -518,6 +518,6 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
   if (e != cudaSuccess) return cuda_fail(e, "rmsd2ref_iterative", __FILE__, __LINE__);
   if (iters) *iters = iter;
   if (final_rms) *final_rms = rms;
-  align->timing.launches = launches; align->timing.valid = true;
+  align->timing.launches = launches; align->timing.valid = true; align->timing.kev_used = 0;
   return LOOSB200_OK;
 }
