@@ -46,43 +46,50 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, read through NVML in a
+    background thread (same counters as `nvidia-smi --query-gpu=clocks.sm,
+    clocks_event_reasons.*`, without forking nvidia-smi, which stalls the driver for
+    tens of ms per query)."""
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period=0.1):
         super().__init__(daemon=True)
-        self.idx, self.rows, self._stop_ev = gpu_index, [], threading.Event()
+        self.idx, self.period, self.rows, self._stop_ev = gpu_index, period, [], threading.Event()
+        self.max_mhz = None
 
     def run(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.p = None
-            return
-        for line in self.p.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-            if self._stop_ev.is_set():
-                break
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.idx]) if vis and vis.split(",")[0].isdigit() else self.idx
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self._stop_ev.is_set():
+                clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((clk, rs))
+                time.sleep(self.period)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
     def stop(self):
         self._stop_ev.set()
-        if getattr(self, "p", None):
-            self.p.terminate()
-        sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
-        mx = [int(float(r[2])) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) > 8:
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.join(timeout=2.0)
+        try:
+            import pynvml as nv
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        except Exception:
+            names = {}
+        sm = sorted(c for c, _ in self.rows)
+        reasons = sorted(n for n, bit in names.items() if any(r & bit for _, r in self.rows))
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "how": "NVML, %.0f ms period, during the timed region" % (self.period * 1e3)}
 
 
 def dist_setup(ngpus):

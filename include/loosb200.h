@@ -86,7 +86,16 @@ int loosb200_device_count(void);
  * host_xyz: F * natoms * 3 floats in `layout`. */
 int loosb200_stage_frames(loosb200_frames** out, const float* host_xyz, size_t F, size_t natoms,
                           const uint32_t* sel, size_t nsel, int layout, int device);
-/* Same, but `dev_xyz` already lives in the HBM of `device` (used to time the
+/* Incremental form, for overlapping trajectory decode with the upload: announce F
+ * frames, append them in any number of pieces (each call copies its frames to a
+ * pinned bounce buffer and returns; H2D and the gather kernel run behind the
+ * caller's next decode), then finish.  The handle may only be used for compute
+ * after loosb200_stage_end() returned LOOSB200_OK. */
+int loosb200_stage_begin(loosb200_frames** out, size_t F, size_t natoms, const uint32_t* sel,
+                         size_t nsel, int layout, int device);
+int loosb200_stage_append(loosb200_frames* h, const float* host_xyz, size_t nframes);
+int loosb200_stage_end(loosb200_frames* h);
+/* Same as loosb200_stage_frames, but `dev_xyz` already lives in the HBM of `device` (used to time the
  * device-resident path; also lets a decoder running on the GPU hand frames over). */
 int loosb200_stage_frames_device(loosb200_frames** out, const float* dev_xyz, size_t F,
                                  size_t natoms, const uint32_t* sel, size_t nsel, int layout,

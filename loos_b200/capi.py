@@ -39,6 +39,9 @@ SIGNATURES = {
     "loosb200_device_count": (_i, []),
     "loosb200_stage_frames": (_i, [C.POINTER(_vp), _vp, _sz, _sz, _up, _sz, _i, _i]),
     "loosb200_stage_frames_device": (_i, [C.POINTER(_vp), _vp, _sz, _sz, _up, _sz, _i, _i]),
+    "loosb200_stage_begin": (_i, [C.POINTER(_vp), _sz, _sz, _up, _sz, _i, _i]),
+    "loosb200_stage_append": (_i, [_vp, _vp, _sz]),
+    "loosb200_stage_end": (_i, [_vp]),
     "loosb200_free": (None, [_vp]),
     "loosb200_frames_info": (_i, [_vp, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i)]),
     "loosb200_get_centroids": (_i, [_vp, _dp]),

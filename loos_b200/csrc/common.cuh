@@ -53,8 +53,11 @@ struct Timing {
 
 }  // namespace loosb200
 
+namespace loosb200 { struct Stager; }
+
 // The opaque handle of include/loosb200.h.
 struct loosb200_frames {
+  loosb200::Stager* stager = nullptr;  // non-null between stage_begin and stage_end
   int device = 0;
   size_t F = 0, N = 0;
   size_t Npad = 0;  // N rounded up to 4 floats (16 B) -- row pitch of `raw`

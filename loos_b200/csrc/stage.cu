@@ -299,76 +299,127 @@ extern "C" int loosb200_stage_frames_device(loosb200_frames** out, const float* 
 }
 
 // Host frames -> device: two pinned bounce buffers and two device chunk buffers;
-// the CPU fills bounce[k] while the copy engine drains bounce[k^1] and the SMs
-// gather the chunk before that.  (If the caller's buffer is already pinned the
-// bounce copy is skipped.)
-extern "C" int loosb200_stage_frames(loosb200_frames** out, const float* host_xyz, size_t F,
-                                     size_t natoms, const uint32_t* sel, size_t nsel, int layout,
-                                     int device) {
-  int rc = check_stage_args(out, host_xyz, F, natoms, sel, nsel, layout, device);
-  if (rc) return rc;
-  loosb200_frames* h = nullptr;
-  if ((rc = alloc_handle(&h, F, sel ? nsel : natoms, device))) return rc;
+// the CPU (trajectory decode + memcpy) fills bounce[k] while the copy engine drains
+// bounce[k^1] on a side stream and the SMs gather the chunk before that.
+namespace loosb200 {
+struct Stager {
+  size_t natoms = 0, F_total = 0, done = 0, chunk_frames = 0, frame_bytes = 0;
+  int layout = 0;
   uint32_t* sel_dev = nullptr;
-  if ((rc = upload_sel(sel, nsel, &sel_dev, h->stream))) { loosb200_free(h); return rc; }
-
-  const size_t frame_bytes = natoms * 3 * sizeof(float);
-  size_t chunk_frames = (size_t)(64u << 20) / frame_bytes;  // ~64 MiB per chunk
-  if (chunk_frames < 1) chunk_frames = 1;
-  if (chunk_frames > F) chunk_frames = F;
-  const size_t chunk_bytes = chunk_frames * frame_bytes;
-
-  cudaPointerAttributes attr;
-  bool pinned = cudaPointerGetAttributes(&attr, host_xyz) == cudaSuccess &&
-                (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
-  cudaGetLastError();
-
   float* bounce[2] = {nullptr, nullptr};
   float* dchunk[2] = {nullptr, nullptr};
   cudaEvent_t copied[2] = {nullptr, nullptr}, staged[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;
-  bool ok = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) == cudaSuccess;
-  for (int k = 0; k < 2 && ok; ++k) {
-    ok = cudaMalloc(&dchunk[k], chunk_bytes) == cudaSuccess &&
-         cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&staged[k], cudaEventDisableTiming) == cudaSuccess;
-    if (ok && !pinned) ok = cudaMallocHost(&bounce[k], chunk_bytes) == cudaSuccess;
-  }
-  cudaError_t e = cudaSuccess;
-  if (ok) {
-    cudaEventRecord(h->timing.ev[0], h->stream);
-    int k = 0;
-    for (size_t f0 = 0; f0 < F; f0 += chunk_frames, k ^= 1) {
-      const size_t nf = (F - f0 < chunk_frames) ? F - f0 : chunk_frames;
-      const float* srcp = host_xyz + f0 * natoms * 3;
-      // the device chunk buffer and the bounce buffer are free once the gather
-      // kernel that read dchunk[k] (two iterations ago) has finished
-      cudaEventSynchronize(staged[k]);
-      if (!pinned) { memcpy(bounce[k], srcp, nf * frame_bytes); srcp = bounce[k]; }
-      cudaMemcpyAsync(dchunk[k], srcp, nf * frame_bytes, cudaMemcpyHostToDevice, copy_stream);
-      cudaEventRecord(copied[k], copy_stream);
-      cudaStreamWaitEvent(h->stream, copied[k], 0);
-      launch_stage(h, dchunk[k], f0, nf, natoms, sel_dev, layout, h->stream);
-      cudaEventRecord(staged[k], h->stream);
-      h->timing.launches++;
+  int k = 0;
+  bool started = false;
+  ~Stager() {
+    for (int i = 0; i < 2; ++i) {
+      if (bounce[i]) cudaFreeHost(bounce[i]);
+      if (dchunk[i]) cudaFree(dchunk[i]);
+      if (copied[i]) cudaEventDestroy(copied[i]);
+      if (staged[i]) cudaEventDestroy(staged[i]);
     }
-    cudaEventRecord(h->timing.ev[1], h->stream);
-    cudaEventRecord(h->timing.ev[2], h->stream);
-    cudaEventRecord(h->timing.ev[3], h->stream);
-    e = cudaStreamSynchronize(h->stream);
-    if (e == cudaSuccess) e = cudaGetLastError();
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (sel_dev) cudaFree(sel_dev);
+    cudaGetLastError();
   }
-  for (int k = 0; k < 2; ++k) {
-    if (bounce[k]) cudaFreeHost(bounce[k]);
-    if (dchunk[k]) cudaFree(dchunk[k]);
-    if (copied[k]) cudaEventDestroy(copied[k]);
-    if (staged[k]) cudaEventDestroy(staged[k]);
-  }
-  if (copy_stream) cudaStreamDestroy(copy_stream);
-  if (sel_dev) cudaFree(sel_dev);
+};
+}  // namespace loosb200
+
+static int stager_push(loosb200_frames* h, Stager* s, const float* src, size_t nf, bool src_pinned) {
+  // slot k is free once the gather kernel that read dchunk[k] (two pushes ago) has finished
+  cudaEventSynchronize(s->staged[s->k]);
+  const float* from = src;
+  if (!src_pinned) { memcpy(s->bounce[s->k], src, nf * s->frame_bytes); from = s->bounce[s->k]; }
+  if (!s->started) { cudaEventRecord(h->timing.ev[0], h->stream); s->started = true; }
+  cudaMemcpyAsync(s->dchunk[s->k], from, nf * s->frame_bytes, cudaMemcpyHostToDevice, s->copy_stream);
+  cudaEventRecord(s->copied[s->k], s->copy_stream);
+  cudaStreamWaitEvent(h->stream, s->copied[s->k], 0);
+  launch_stage(h, s->dchunk[s->k], s->done, nf, s->natoms, s->sel_dev, s->layout, h->stream);
+  cudaEventRecord(s->staged[s->k], h->stream);
+  h->timing.launches++;
+  s->done += nf;
+  s->k ^= 1;
+  return cudaGetLastError() == cudaSuccess ? LOOSB200_OK : LOOSB200_ERR_CUDA;
+}
+
+extern "C" int loosb200_stage_begin(loosb200_frames** out, size_t F, size_t natoms, const uint32_t* sel,
+                                    size_t nsel, int layout, int device) {
+  static const float dummy = 0.f;
+  int rc = check_stage_args(out, &dummy, F, natoms, sel, nsel, layout, device);
+  if (rc) return rc;
+  loosb200_frames* h = nullptr;
+  if ((rc = alloc_handle(&h, F, sel ? nsel : natoms, device))) return rc;
+  Stager* s = new (std::nothrow) Stager();
+  if (!s) { loosb200_free(h); return LOOSB200_ERR_NOMEM; }
+  h->stager = s;
+  s->natoms = natoms; s->F_total = F; s->layout = layout;
+  s->frame_bytes = natoms * 3 * sizeof(float);
+  s->chunk_frames = (size_t)(64u << 20) / s->frame_bytes;  // ~64 MiB per chunk
+  if (s->chunk_frames < 1) s->chunk_frames = 1;
+  if (s->chunk_frames > F) s->chunk_frames = F;
+  if ((rc = upload_sel(sel, nsel, &s->sel_dev, h->stream))) { loosb200_free(h); return rc; }
+  bool ok = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int k = 0; k < 2 && ok; ++k)
+    ok = cudaMalloc(&s->dchunk[k], s->chunk_frames * s->frame_bytes) == cudaSuccess &&
+         cudaMallocHost(&s->bounce[k], s->chunk_frames * s->frame_bytes) == cudaSuccess &&
+         cudaEventCreateWithFlags(&s->copied[k], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&s->staged[k], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { cudaGetLastError(); loosb200_free(h); return LOOSB200_ERR_NOMEM; }
-  if (e != cudaSuccess) { loosb200_free(h); return cuda_fail(e, "stage_frames", __FILE__, __LINE__); }
+  *out = h;
+  return LOOSB200_OK;
+}
+
+static int stage_append_impl(loosb200_frames* h, const float* host_xyz, size_t nframes, bool allow_direct) {
+  if (!h || !h->stager || !host_xyz) return LOOSB200_ERR_INVALID;
+  Stager* s = h->stager;
+  if (s->done + nframes > s->F_total) return LOOSB200_ERR_RANGE;
+  LB_CUDA(cudaSetDevice(h->device));
+  bool pinned = false;
+  if (allow_direct) {  // one-shot staging from a pinned caller buffer: no bounce copy
+    cudaPointerAttributes attr;
+    pinned = cudaPointerGetAttributes(&attr, host_xyz) == cudaSuccess &&
+             (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+  }
+  for (size_t f0 = 0; f0 < nframes; f0 += s->chunk_frames) {
+    const size_t nf = nframes - f0 < s->chunk_frames ? nframes - f0 : s->chunk_frames;
+    int rc = stager_push(h, s, host_xyz + f0 * s->natoms * 3, nf, pinned);
+    if (rc) return rc;
+  }
+  return LOOSB200_OK;
+}
+
+extern "C" int loosb200_stage_append(loosb200_frames* h, const float* host_xyz, size_t nframes) {
+  return stage_append_impl(h, host_xyz, nframes, false);
+}
+
+extern "C" int loosb200_stage_end(loosb200_frames* h) {
+  if (!h || !h->stager) return LOOSB200_ERR_INVALID;
+  Stager* s = h->stager;
+  LB_CUDA(cudaSetDevice(h->device));
+  const bool complete = s->done == s->F_total;
+  cudaEventRecord(h->timing.ev[1], h->stream);
+  cudaEventRecord(h->timing.ev[2], h->stream);
+  cudaEventRecord(h->timing.ev[3], h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  delete s;
+  h->stager = nullptr;
+  if (e != cudaSuccess) return cuda_fail(e, "stage_end", __FILE__, __LINE__);
+  if (!complete) return LOOSB200_ERR_INVALID;  // fewer frames appended than announced
   h->timing.valid = true;
+  return LOOSB200_OK;
+}
+
+extern "C" int loosb200_stage_frames(loosb200_frames** out, const float* host_xyz, size_t F,
+                                     size_t natoms, const uint32_t* sel, size_t nsel, int layout,
+                                     int device) {
+  if (!host_xyz) return LOOSB200_ERR_INVALID;
+  loosb200_frames* h = nullptr;
+  int rc = loosb200_stage_begin(&h, F, natoms, sel, nsel, layout, device);
+  if (rc) return rc;
+  if ((rc = stage_append_impl(h, host_xyz, F, true)) || (rc = loosb200_stage_end(h))) { loosb200_free(h); return rc; }
   *out = h;
   return LOOSB200_OK;
 }
@@ -377,6 +428,7 @@ extern "C" void loosb200_free(loosb200_frames* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stager) { delete h->stager; h->stager = nullptr; }
   cudaFree(h->raw); cudaFree(h->centroid); cudaFree(h->gd); cudaFree(h->maxabs);
   cudaFree(h->q8); cudaFree(h->gq); cudaFree(h->unit_log2_dev);
   for (int i = 0; i < 4; ++i) if (h->timing.ev[i]) cudaEventDestroy(h->timing.ev[i]);

@@ -45,15 +45,13 @@ int main(int argc, char* argv[]) {
     // frameList(): sorted + unique (src/OptionsFramework.cpp:460-464)
     const std::vector<uint32_t> indices = uniquify(assignTrajectoryFrames(mt.nframes(), range, 0, 1));
     const size_t F = indices.size(), na = model.size();
-    std::vector<float> buf(F * 3 * na);
-    for (size_t j = 0; j < F; ++j) {
-      if (indices[j] >= mt.nframes()) throw Error("Cannot seek past end of MultiTraj");
-      const std::pair<uint32_t, uint32_t> loc = mt.location(indices[j]);
-      mt.trajs[loc.first]->readFramePlanes(loc.second, buf.data() + j * 3 * na);
-    }
+    for (uint32_t k : indices)
+      if (k >= mt.nframes()) throw Error("Cannot seek past end of MultiTraj");
     Frames A;
-    stage(A, buf, F, na, sel, device);
-    buf.clear(); buf.shrink_to_fit();
+    stageStreaming({&A}, {&sel}, F, na, device, [&](size_t j, float* dst) {
+      const std::pair<uint32_t, uint32_t> loc = mt.location(indices[j]);
+      mt.trajs[loc.first]->readFramePlanes(loc.second, dst);
+    });
     if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
     std::vector<float> M;
     if (!noop) M.assign(F * F, 0.0f);

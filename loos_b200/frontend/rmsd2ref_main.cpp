@@ -77,16 +77,21 @@ int main(int argc, char* argv[]) {
       std::cerr << line;
     }
 
-    const std::vector<float> buf = readFrames(traj, indices);
     Frames fr, fa;
-    stage(fr, buf, F, molecule.size(), selectionToFrameIndices(molecule, subset), device);
     std::vector<double> rmsds(F, 0.0);
     const bool do_align = !alignment.empty();
     std::vector<uint32_t> align_subset;
+    const std::vector<uint32_t> sel_r = selectionToFrameIndices(molecule, subset);
+    std::vector<uint32_t> sel_a;
+    std::vector<float> buf;  // only the --align '' / no-target corner needs the frames on the host
+    auto reader = [&](size_t j, float* dst) { traj.readFramePlanes(indices[j], dst); };
     if (do_align) {
       align_subset = selectAtoms(molecule, alignment);
       if (align_subset.empty()) throw Error("Error- --align selection matched no atoms");
-      stage(fa, buf, F, molecule.size(), selectionToFrameIndices(molecule, align_subset), device);
+      sel_a = selectionToFrameIndices(molecule, align_subset);
+      stageStreaming({&fr, &fa}, {&sel_r, &sel_a}, F, molecule.size(), device, reader);
+    } else {
+      stageStreaming({&fr}, {&sel_r}, F, molecule.size(), device, reader, target_name.empty() ? &buf : nullptr);
     }
     if (target_name.empty()) {
       if (do_align) {

@@ -41,7 +41,7 @@ int main(int argc, char* argv[]) {
     const std::vector<uint32_t> indices = assignTrajectoryFrames(traj.nframes(), o.str("range1"), (uint32_t)o.uns("skip1"));
     if (verbosity > 1) std::cerr << "Reading trajectory - " << o.str("traj1") << std::endl;
     Frames A;
-    { const std::vector<float> buf = readFrames(traj, indices); stage(A, buf, indices.size(), model.size(), sel, device); }
+    stageTrajectory(A, traj, indices, model.size(), sel, device);
 
     std::vector<float> M;
     size_t rows = indices.size(), cols = indices.size();
@@ -59,7 +59,7 @@ int main(int argc, char* argv[]) {
       const std::vector<uint32_t> indices2 = assignTrajectoryFrames(traj2.nframes(), o.str("range2"), (uint32_t)o.uns("skip2"));
       if (verbosity > 1) std::cerr << "Reading trajectory - " << o.str("traj2") << std::endl;
       Frames B;
-      { const std::vector<float> buf = readFrames(traj2, indices2); stage(B, buf, indices2.size(), model2.size(), sel2, device); }
+      stageTrajectory(B, traj2, indices2, model2.size(), sel2, device);
       cols = indices2.size();
       if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
       if (!noop) M.assign(rows * cols, 0.0f);

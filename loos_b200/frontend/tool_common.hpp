@@ -1,5 +1,6 @@
 // Shared pieces of the three tool mains.
 #pragma once
+#include <algorithm>
 #include <cstdio>
 #include <iostream>
 #include <memory>
@@ -36,24 +37,38 @@ inline int engineOf(const Options& o) {
   throw Error("the argument ('" + e + "') for option '--engine' is invalid");
 }
 
-// readCoords (src/ensembles.cpp:253-296): the listed frames of one trajectory as
-// planes [F][3][natoms]; the device gathers the selection.
-inline std::vector<float> readFrames(DCD& traj, const std::vector<uint32_t>& indices) {
-  const size_t na = traj.natoms();
-  std::vector<float> buf(indices.size() * 3 * na);
-  for (size_t j = 0; j < indices.size(); ++j) traj.readFramePlanes(indices[j], buf.data() + j * 3 * na);
-  return buf;
-}
-
 struct Frames {  // RAII around loosb200_frames
   loosb200_frames* h = nullptr;
   ~Frames() { if (h) loosb200_free(h); }
 };
 
-inline void stage(Frames& f, const std::vector<float>& planes, size_t F, size_t natoms,
-                  const std::vector<uint32_t>& sel, int device) {
-  check(loosb200_stage_frames(&f.h, planes.data(), F, natoms, sel.data(), sel.size(), LOOSB200_LAYOUT_PLANES, device),
-        "staging frames");
+// readCoords (src/ensembles.cpp:253-296) without the host-side coordinate cache: frames
+// are decoded in batches (planes X|Y|Z per frame, the DCD record order) and appended to
+// one or more staged sets; while batch k+1 is being decoded, batch k is on its way to
+// the GPU (pinned bounce buffer -> async H2D on a side stream -> gather kernel).
+// `read(j, dst)` must put frame j of the list (3 * natoms floats) at dst.
+template <class ReadFrame>
+inline void stageStreaming(std::vector<Frames*> sets, const std::vector<const std::vector<uint32_t>*>& sels,
+                           size_t F, size_t natoms, int device, ReadFrame read, std::vector<float>* keep = nullptr) {
+  for (size_t k = 0; k < sets.size(); ++k)
+    check(loosb200_stage_begin(&sets[k]->h, F, natoms, sels[k]->data(), sels[k]->size(), LOOSB200_LAYOUT_PLANES, device),
+          "staging frames");
+  const size_t batch = std::max<size_t>(1, std::min<size_t>(F, (16u << 20) / (natoms * 12)));
+  std::vector<float> buf(batch * 3 * natoms);
+  if (keep) keep->resize(F * 3 * natoms);
+  for (size_t j0 = 0; j0 < F; j0 += batch) {
+    const size_t nb = std::min(batch, F - j0);
+    for (size_t j = 0; j < nb; ++j) read(j0 + j, buf.data() + j * 3 * natoms);
+    if (keep) std::copy(buf.begin(), buf.begin() + nb * 3 * natoms, keep->begin() + j0 * 3 * natoms);
+    for (size_t k = 0; k < sets.size(); ++k) check(loosb200_stage_append(sets[k]->h, buf.data(), nb), "staging frames");
+  }
+  for (size_t k = 0; k < sets.size(); ++k) check(loosb200_stage_end(sets[k]->h), "staging frames");
+}
+
+inline void stageTrajectory(Frames& f, DCD& traj, const std::vector<uint32_t>& indices, size_t natoms,
+                            const std::vector<uint32_t>& sel, int device) {
+  stageStreaming({&f}, {&sel}, indices.size(), natoms, device,
+                 [&](size_t j, float* dst) { traj.readFramePlanes(indices[j], dst); });
 }
 
 }  // namespace lbfe

@@ -188,3 +188,39 @@ def test_errors(lb):
     # all-zero frames (every atom at the centroid): RMSD 0, no NaN
     M, _ = lb.rmsds(b)
     assert np.all(M == 0)
+
+
+def test_incremental_staging_equals_one_shot(lb):
+    """loosb200_stage_begin/append/end (decode overlapped with upload) must stage exactly
+    what loosb200_stage_frames stages: ragged pieces, selection gather, both layouts."""
+    import ctypes as C
+
+    from loos_b200 import capi
+    from loos_b200.synth import synth_frames
+    L = capi.lib()
+    X = synth_frames(157, 90, seed=31)
+    sel = np.arange(0, 90, 2, dtype=np.uint32)
+    with lb.FrameSet(X, sel=sel) as fs:
+        M0, _ = lb.rmsds(fs)
+        c0 = fs.centroids()
+    h = C.c_void_p()
+    selp = sel.ctypes.data_as(C.POINTER(C.c_uint32))
+    capi.check(L.loosb200_stage_begin(C.byref(h), 157, 90, selp, sel.size, capi.LAYOUT_XYZ, 0))
+    pos = 0
+    for n in (1, 40, 3, 100, 13):
+        piece = np.ascontiguousarray(X[pos:pos + n])
+        capi.check(L.loosb200_stage_append(h, piece.ctypes.data_as(C.c_void_p), n))
+        piece[:] = 7.0          # the caller may reuse its buffer immediately
+        pos += n
+    assert L.loosb200_stage_append(h, X.ctypes.data_as(C.c_void_p), 1) == capi.ERR_RANGE   # more than announced
+    capi.check(L.loosb200_stage_end(h))
+    fs2 = lb.FrameSet.__new__(lb.FrameSet)
+    fs2._h, fs2.F, fs2.N, fs2.device = h, 157, sel.size, 0
+    M1, _ = lb.rmsds(fs2)
+    assert np.array_equal(M0, M1) and np.array_equal(c0, fs2.centroids())
+    fs2.close()
+    # ending early is an error, not a silently short set
+    capi.check(L.loosb200_stage_begin(C.byref(h), 10, 90, None, 0, capi.LAYOUT_XYZ, 0))
+    capi.check(L.loosb200_stage_append(h, X.ctypes.data_as(C.c_void_p), 4))
+    assert L.loosb200_stage_end(h) == capi.ERR_INVALID
+    L.loosb200_free(h)
