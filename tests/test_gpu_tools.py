@@ -141,3 +141,39 @@ def test_rmsd2ref_target_and_iterative(files, checker):
     r = subprocess.run([os.path.join(BIN, "rmsd2ref"), "-k", "3", "-r", "0:5", str(d / "model.pdb"), str(d / "all.dcd")],
                        capture_output=True, text=True)
     assert r.returncode == 255 and "cannot specify both a skip and a frame range" in r.stderr
+
+
+def test_rms_overlap(files, checker):
+    """set A x set B rectangular matrix, two trajectory tables, stats with and
+    without --cutoff (including the reference's brace-less `if` in showFractionalStats)."""
+    d = files["d"]
+    sel = fo.select(files["atoms"], "backbone && !hydrogen")
+    A = files["xyz"][:115:2][:, sel].astype(np.float64)          # a.dcd + b.dcd, stride 2 per sub-trajectory
+    ia = [f for t, f in fo.multitraj_locations([70, 45], 0, 2)]
+    A = np.concatenate([files["xyz"][:70][0::2], files["xyz"][70:115][0::2]])[:, sel].astype(np.float64)
+    B = files["xyz"][115:][0::2][:, sel].astype(np.float64)
+    ref = checker.rmsds_cross(A, B, 4)
+    out, err = run("rms-overlap", "-s", "backbone && !hydrogen", "-i", "2", "-p", "7", "--stats", "1",
+                   "-A", "%s %s" % (d / "a.dcd", d / "b.dcd"), "-B", str(d / "c.dcd"), d / "model.pdb")
+    head, M, _ = parse_matrix(out)
+    assert head[1] == "# traj\tstart\tend\tfilename" and head[2].endswith("a.dcd") and head[3].endswith("b.dcd")
+    assert head[4] == "# traj\tstart\tend\tfilename" and head[5] == "# 0\t0\t17\t%s" % (d / "c.dcd")
+    assert M.shape == ref.shape == (58, 18) and np.abs(M - ref).max() < 2e-5
+    assert err.strip() == "Max rmsd = %.4f, avg rmsd = %.4f" % (ref.astype(np.float64).max(), ref.astype(np.float64).mean())
+    out, err = run("rms-overlap", "-s", "backbone && !hydrogen", "-i", "2", "-c", "6.5", "-N", "1",
+                   "-A", "%s %s" % (d / "a.dcd", d / "b.dcd"), "-B", str(d / "c.dcd"), d / "model.pdb")
+    r64 = ref.astype(np.float64)
+    off = ~np.eye(58, 18, dtype=bool)
+    avg = r64[off].sum() / r64.size
+    var = (r64[off] ** 2).sum() / r64.size - avg * avg
+    # bug-compatible "max": the last off-diagonal element visited, row index of the last increase
+    mval, mi = 0.0, 0
+    for i in range(58):
+        for j in range(18):
+            if i != j:
+                if r64[i, j] > mval:
+                    mi = i
+                mval = r64[i, j]
+    want = "Max rmsd = %.4f between frames %d, %d, avg rmsd = %.4f, variance = %.4f, frames below %.4f = %d, total = %d" % (
+        mval, mi, 17, avg, var, 6.5, int((ref[off] < np.float32(6.5)).sum()), ref.size)
+    assert out.strip() == want and err == ""
