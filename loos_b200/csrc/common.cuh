@@ -75,6 +75,7 @@ struct loosb200_frames {
   bool quantised = false;
   size_t rows_total = 0, Kpad = 0;
   CUtensorMap tmapA;  // 3-D map over q8 (atom, row, slice), box 64 x 128 x 3
+  CUtensorMap tmapAh; // same tensor, box 64 x 64 x 1 (half an "a" tile of one digit, for cluster multicast)
   CUtensorMap tmapB;  // same tensor, box 64 x 96 x 3
   bool tmap_valid = false;
 

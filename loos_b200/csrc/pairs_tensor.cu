@@ -29,6 +29,7 @@
 //            next tile; the solves overlap them.
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -104,6 +105,25 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, unsigned long long* bar,
+                                               int c0, int c1, int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(unsigned long long* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(unsigned long long* bar) {
@@ -167,40 +187,60 @@ struct TensorArgs {
 };
 
 
-// Tile slots are numbered super-block by super-block (row-major inside); CTA c takes
-// slots c, c + grid, ...  All three warp roles walk the same sequence and apply the same
-// "is this a tile of the lower triangle" test, so they stay in step without talking.
+// Tile slots are numbered super-block by super-block (row-major inside); cluster c takes
+// slots c, c + #clusters, ...  A slot is CL adjacent column tiles of one row tile: the CTAs of
+// a cluster (CL = 2) share the "a" operand, each loading half of it with TMA multicast.
+// All warp roles of all CTAs of a cluster walk the same sequence and apply the same tests,
+// so they stay in step without talking.  A CTA whose own column tile does not exist while
+// its partner's does shadows the partner's tile (same operands, results masked), which
+// keeps the multicast/barrier protocol identical for both.
+template <int CL>
 struct TileWalk {
-  uint32_t slot, sb;
-  __device__ __forceinline__ TileWalk() : slot(blockIdx.x), sb(0) {}
-  // Next valid tile: returns false when the CTA is done.  rt = row index within the launch.
-  __device__ __forceinline__ bool next(const TensorArgs& a, uint32_t& rt, uint32_t& I, uint32_t& J) {
-    for (; slot < a.n_slots; slot += gridDim.x) {
+  uint32_t slot, sb, stride, crank;
+  __device__ __forceinline__ TileWalk(uint32_t rank) : slot(blockIdx.x / CL), sb(0), stride(gridDim.x / CL), crank(rank) {}
+  __device__ __forceinline__ bool exists(const TensorArgs& a, const uint4& b, uint32_t I, uint32_t J) const {
+    if (J >= b.z + b.w) return false;
+    return !(a.self && (uint64_t)J * COL_TILE_FRAMES >= (uint64_t)I * TILE_FRAMES + TILE_FRAMES);
+  }
+  // Next tile: returns false when the CTA is done.  rt = row index within the launch.
+  __device__ __forceinline__ bool next(const TensorArgs& a, uint32_t& rt, uint32_t& I, uint32_t& J, bool& masked) {
+    for (; slot < a.n_slots; slot += stride) {
       while (slot >= a.sb_prefix[sb + 1]) ++sb;
       const uint4 b = a.sblocks[sb];
+      const uint32_t ncg = (b.w + CL - 1) / CL;  // column groups per row
       const uint32_t local = slot - a.sb_prefix[sb];
-      const uint32_t lr = local / b.w, lc = local - lr * b.w;
+      const uint32_t lr = local / ncg, lc = local - lr * ncg;
       rt = b.x + lr;
       I = a.row_tiles[rt];
-      J = b.z + lc;
-      if (a.self && (uint64_t)J * COL_TILE_FRAMES >= (uint64_t)I * TILE_FRAMES + TILE_FRAMES) continue;
-      slot += gridDim.x;
+      J = b.z + lc * CL + crank;
+      masked = false;
+      if (!exists(a, b, I, J)) {
+        if (CL == 1) continue;
+        const uint32_t Jp = b.z + lc * CL + (crank ^ 1);
+        if (!exists(a, b, I, Jp)) continue;
+        J = Jp;
+        masked = true;
+      }
+      slot += stride;
       return true;
     }
     return false;
   }
 };
 
+template <int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const TensorArgs a) {
+k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAh,
+               const __grid_constant__ CUtensorMap mapB, const TensorArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   SmemCtl* ctl = (SmemCtl*)(smem + NUM_STAGES * STAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+    // empty[s] collects the MMA completions of every CTA that multicasts into this CTA's slot
+    for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], CL); }
     mbar_init(&ctl->tmem_full, 1);
     mbar_init(&ctl->tmem_empty, NUM_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -210,7 +250,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();  // barriers of both CTAs exist before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
@@ -220,16 +260,26 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
       uint32_t stage = 0, phase = 0;
-      TileWalk walk;
+      TileWalk<CL> walk(crank);
       uint32_t rt, I, J;
-      while (walk.next(a, rt, I, J)) {
+      bool masked;
+      while (walk.next(a, rt, I, J, masked)) {
         const int rowA = (int)I * TILE_ROWS;
         const int rowB = (int)J * COL_TILE_ROWS;
         for (uint32_t kc = 0; kc < a.n_kchunks; ++kc) {
-          mbar_wait<200>(&ctl->empty[stage], phase ^ 1);
+          mbar_wait<32>(&ctl->empty[stage], phase ^ 1);
           unsigned char* sA = smem + stage * STAGE_BYTES;
           mbar_expect_tx(&ctl->full[stage], STAGE_BYTES);
-          tma_load_3d(sA, &mapA, &ctl->full[stage], (int)(kc * K_CHUNK), rowA, 0);
+          if (CL == 1) {
+            tma_load_3d(sA, &mapA, &ctl->full[stage], (int)(kc * K_CHUNK), rowA, 0);
+          } else {
+            // this CTA's half of the shared "a" tile (64 rows of each digit) goes to both CTAs
+            const int half_rows = TILE_ROWS / 2;
+#pragma unroll
+            for (int d = 0; d < NUM_SLICES; ++d)
+              tma_load_3d_mc(sA + d * A_SLICE_BYTES + crank * (half_rows * K_CHUNK), &mapAh, &ctl->full[stage],
+                             (int)(kc * K_CHUNK), rowA + (int)crank * half_rows, d, (uint16_t)0x3);
+          }
           tma_load_3d(sA + A_STAGE_BYTES, &mapB, &ctl->full[stage], (int)(kc * K_CHUNK), rowB, 0);
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -242,14 +292,15 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       uint32_t stage = 0, phase = 0, tphase = 0;
       long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       long long tprev = a.prof ? clock64() : 0;
-      TileWalk walk;
+      TileWalk<CL> walk(crank);
       uint32_t rt, I, J;
-      while (walk.next(a, rt, I, J)) {
-        mbar_wait<100>(&ctl->tmem_empty, tphase ^ 1);  // epilogue has drained the previous tile
+      bool masked;
+      while (walk.next(a, rt, I, J, masked)) {
+        mbar_wait<32>(&ctl->tmem_empty, tphase ^ 1);  // epilogue has drained the previous tile
         tc_fence_after();
         LB_TICK(0);  // waiting for TMEM
         for (uint32_t kc = 0; kc < a.n_kchunks; ++kc) {
-          mbar_wait<20>(&ctl->full[stage], phase);
+          mbar_wait<0>(&ctl->full[stage], phase);
           tc_fence_after();
           LB_TICK(1);  // waiting for operands
           const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
@@ -270,7 +321,8 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tc_mma_i8(tmem_base + 2 * CLASS_COLS, A2, B0, ID96, 1u);      // a2.b0 -> s2
             tc_mma_i8(tmem_base + 1 * CLASS_COLS, A1, B0, ID96, 1u);      // a1.b0 -> s1
           }
-          tc_commit(&ctl->empty[stage]);  // smem slot reusable once these MMAs have read it
+          // smem slot reusable once these MMAs have read it (tell every CTA that writes into it)
+          if (CL == 1) tc_commit(&ctl->empty[stage]); else tc_commit_mc(&ctl->empty[stage], (uint16_t)0x3);
           if (kc + 1 == a.n_kchunks) tc_commit(&ctl->tmem_full);
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
           LB_TICK(2);  // issuing
@@ -297,11 +349,12 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = a.prof ? clock64() : 0;
 
-    TileWalk walk;
+    TileWalk<CL> walk(crank);
     uint32_t rt, I, J;
-    for (; walk.next(a, rt, I, J); buf ^= 1) {
+    bool masked;
+    for (; walk.next(a, rt, I, J, masked); buf ^= 1) {
       const uint32_t i = I * TILE_FRAMES + a_local;
-      const bool i_ok = active && i < a.FA;
+      const bool i_ok = active && i < a.FA && !masked;  // a shadow tile contributes nothing
       const double ga = i_ok ? (double)a.gA[i] : 0.0;
       long long gbq[4];  // G of the four "b" frames this lane solves against (prefetched)
 #pragma unroll
@@ -309,7 +362,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t j = J * COL_TILE_FRAMES + g * FRAMES_PER_BLOCK + (round < 3 ? 3 * round + al : 9);
         gbq[round] = j < a.FB ? __ldg(a.gB + j) : 0;
       }
-      mbar_wait<50>(&ctl->tmem_full, tphase);
+      mbar_wait<32>(&ctl->tmem_full, tphase);
       tphase ^= 1;
       tc_fence_after();
       LB_TICK(0);  // waiting for the accumulators
@@ -498,7 +551,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA leaves while its partner may still signal it
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
@@ -513,6 +566,8 @@ bool tensor_path_available() { return true; }
 // tiles in flight share a few MB of operands in L2 (operand sets are larger than L2).
 int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   constexpr uint32_t SB_R = 12, SB_C = 16;
+  const char* cl_env = getenv("LOOSB200_CLUSTER");
+  const uint32_t CLs = (cl_env && atoi(cl_env) == 1) ? 1u : 2u;  // CTAs per cluster sharing the "a" tile
   const loosb200_frames* A = job.a;
   const loosb200_frames* B = job.b;
   if (!A->quantised || !B->quantised || A->unit_log2 != B->unit_log2 || A->Kpad != B->Kpad)
@@ -533,7 +588,7 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
     for (uint32_t c0 = 0; c0 < cmax; c0 += SB_C) {
       const uint32_t nc = std::min(cmax, c0 + SB_C) - c0;
       sbl.push_back(make_uint4(r0, r1 - r0, c0, nc));
-      slots += (uint64_t)(r1 - r0) * nc;
+      slots += (uint64_t)(r1 - r0) * ((nc + CLs - 1) / CLs);
       prefix.push_back((uint32_t)slots);
     }
   }
@@ -561,17 +616,29 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   ta.release_at = getenv("LOOSB200_RELEASE_AT") ? atoi(getenv("LOOSB200_RELEASE_AT")) : 0;
   const bool want_prof = getenv("LOOSB200_PROF") != nullptr;
 
-  LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sms, slots);
+  unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sms / CLs, slots) * CLs;
   if (want_prof) {
     LB_CUDA(cudaMalloc(&ta.prof, sizeof(long long) * grid * 14 * 8));
     LB_CUDA(cudaMemsetAsync(ta.prof, 0, sizeof(long long) * grid * 14 * 8, st));
   }
   if (job.ev_k0) cudaEventRecord(job.ev_k0, st);
-  k_pairs_tensor<<<grid, NTHREADS, SMEM_BYTES, st>>>(A->tmapA, B->tmapB, ta);
+  if (CLs == 1) {
+    k_pairs_tensor<1><<<grid, NTHREADS, SMEM_BYTES, st>>>(A->tmapA, A->tmapAh, B->tmapB, ta);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    LB_CUDA(cudaLaunchKernelEx(&cfg, k_pairs_tensor<2>, A->tmapA, A->tmapAh, B->tmapB, ta));
+  }
   if (job.ev_k1) cudaEventRecord(job.ev_k1, st);
   LB_CUDA(cudaGetLastError());
   if (want_prof) {
