@@ -41,7 +41,7 @@ namespace loosb200 {
 
 namespace {
 
-constexpr int NUM_STAGES = 5;
+constexpr int NUM_STAGES = 4;
 constexpr int A_STAGE_BYTES = NUM_SLICES * TILE_ROWS * K_CHUNK;      // 24576
 constexpr int B_STAGE_BYTES = NUM_SLICES * COL_TILE_ROWS * K_CHUNK;  // 18432
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;           // 43008
@@ -343,7 +343,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int tri = lane - al;              // first lane of this frame's lane triple
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 32);
     uint32_t tphase = 0, buf = 0;
-    double ssum = 0.0, smax = 0.0;
+    float sum_h = 0.0f, sum_l = 0.0f, tmax = 0.0f;
     const double inv_n = 1.0 / (double)a.N;
     const int release_at = a.release_at;  // 0 after drain, 1 after fp64 coefficients, 2 after Newton, 3 after polish
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -394,7 +394,8 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       // handed back only AFTER the fp64-heavy part; the fp32 Newton recurrences, the
       // final correction and the stores then overlap the next tile's MMAs.
       QcpPoly poly[4];
-      double e0s[4];
+      QcpPolyF polf[4];
+      float e0s[4];
       int state[4];  // 0: no entry, 1: zero, 2: solve
 #pragma unroll
       for (int round = 0; round < 4; ++round) {
@@ -441,9 +442,16 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? (1.0 / 3.0) : 0.0;
         }
         state[round] = stt;
-        e0s[round] = 2.0 * e0 * inv_n;  // msd = y * this
+        e0s[round] = (float)(2.0 * e0 * inv_n);  // msd = y * this
         poly[round] = qcp_poly(R, e0);
+        polf[round] = qcp_poly_split(poly[round]);
       }
+      // pin every fp64-derived value on this side of the hand-over: without this the compiler
+      // is free to sink the fp64 -> float conversions below it, into the contended region
+#pragma unroll
+      for (int r4 = 0; r4 < 4; ++r4)
+        asm volatile("" : "+f"(polf[r4].c0h), "+f"(polf[r4].c0l), "+f"(polf[r4].c1h), "+f"(polf[r4].c1l),
+                          "+f"(polf[r4].c2), "+f"(polf[r4].c3), "+f"(e0s[r4]), "+f"(poly[r4].t0));
       if (release_at == 1) { __syncwarp(); if (lane == 0) mbar_arrive(&ctl->tmem_empty); }
       LB_TICK(2);  // exchange + quartic coefficients (fp64)
 
@@ -452,8 +460,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
       for (int r4 = 0; r4 < 4; ++r4) {
         tt[r4] = poly[r4].t0; ls[r4] = 0.0f;
-        fc[r4][0] = (float)poly[r4].c0; fc[r4][1] = (float)poly[r4].c1;
-        fc[r4][2] = (float)poly[r4].c2; fc[r4][3] = (float)poly[r4].c3;
+        fc[r4][0] = polf[r4].c0h; fc[r4][1] = polf[r4].c1h; fc[r4][2] = polf[r4].c2; fc[r4][3] = polf[r4].c3;
       }
       for (int it = 0; it < 12; ++it) {
         bool conv = true;
@@ -467,7 +474,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (release_at == 2) { __syncwarp(); if (lane == 0) mbar_arrive(&ctl->tmem_empty); }
       LB_TICK(3);  // Newton (fp32)
 
-      // ---- one fp64 residual correction per pair, float32 result ----
+      // ---- one float-float residual correction per pair, float32 result ----
 #pragma unroll
       for (int round = 0; round < 4; ++round) {
         const int jb = round < 3 ? 3 * round + al : 9;
@@ -476,12 +483,13 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         float val = state[round] == 1 ? 0.0f : -1.0f;  // -1: "no entry"
         if (state[round] == 2) {
           bool ok;
-          double y = qcp_polish(poly[round], tt[round], ls[round], &ok);
-          if (!ok || !(fabs(poly[round].c0) < 1e30)) {
-            // rare (multiple / far-off root, non-finite input): the same quartic in fp64,
-            // Newton from the upper bound
+          // no fp64 here in the common case: this code overlaps the next tile's MMAs
+          float y = qcp_polish_f32(polf[round], poly[round].xform, tt[round], ls[round], &ok);
+          if (!ok || poly[round].xform || !(fabs(poly[round].c0) < 1e30)) {
+            // rare (dissimilar structures, multiple / far-off root, non-finite input): the same
+            // quartic in fp64, Newton from the fp32 root or from the upper bound
             const QcpPoly& pp = poly[round];
-            double td = pp.xform ? (double)pp.t0 : 0.0;
+            double td = ok ? (double)tt[round] : (pp.xform ? (double)pp.t0 : 0.0);
             for (int it = 0; it < 200; ++it) {
               const double fd = fma(td, fma(td, fma(td, td + pp.c3, pp.c2), pp.c1), pp.c0);
               const double dd = fma(td, fma(td, fma(td, 4.0, 3.0 * pp.c3), 2.0 * pp.c2), pp.c1);
@@ -490,12 +498,16 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               td -= stp;
               if (fabs(stp) <= 1e-15 * fabs(td) + 1e-300) break;
             }
-            y = pp.xform ? 1.0 - td : td;
-            y = y < 0.0 ? -y : y;
+            const double yd = pp.xform ? 1.0 - td : td;
+            y = (float)(yd < 0.0 ? -yd : yd);
           }
-          val = (float)a.unit * sqrtf((float)(y * e0s[round]));
-          ssum += (double)val;
-          smax = fmax(smax, (double)val);
+          val = (float)a.unit * sqrtf(y * e0s[round]);
+          // running sum of the float32 results as a float-float pair (error-free two-sum): the
+          // reference accumulates in double (Tools/rmsds.cpp:425-439); no fp64 in this loop
+          const float s2 = sum_h + val, bb2 = s2 - sum_h;
+          sum_l += (sum_h - (s2 - bb2)) + (val - bb2);
+          sum_h = s2;
+          tmax = fmaxf(tmax, val);
         }
         if (owner) ctl->T[buf][b_local][a_local] = val;
       }
@@ -534,6 +546,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (a.prof && lane == 0)
       for (int k = 0; k < 8; ++k) a.prof[((size_t)blockIdx.x * 14 + warp) * 8 + k] = pacc[k];
     if (a.stats) {
+      double ssum = (double)sum_h + (double)sum_l, smax = (double)tmax;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
@@ -613,7 +626,9 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   ta.unit = exp2((double)A->unit_log2);
   ta.out = job.out; ta.ld = job.ld; ta.stats = job.stats_dev;
   ta.prof = nullptr;
-  ta.release_at = getenv("LOOSB200_RELEASE_AT") ? atoi(getenv("LOOSB200_RELEASE_AT")) : 0;
+  // Short contractions are bound by the epilogue: hold the accumulators until its fp64 part is
+  // done (fp64 crawls while MMAs run); long ones are MMA-bound: hand them back right after the drain.
+  ta.release_at = getenv("LOOSB200_RELEASE_AT") ? atoi(getenv("LOOSB200_RELEASE_AT")) : (A->Kpad <= 2048 ? 1 : 0);
   const bool want_prof = getenv("LOOSB200_PROF") != nullptr;
 
   LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -244,6 +244,42 @@ LB_HD double qcp_polish(const QcpPoly& p, float t, float last_step, bool* ok) {
   return yn < 0.0 ? -yn : yn;
 }
 
+// fp64-free version of the residual correction, for code that runs while the tensor
+// pipe is busy (on sm_100 fp64 CUDA-core math shares that pipe and crawls under MMA load).
+// c0 and c1 -- the two coefficients whose sum cancels at the root -- are carried as
+// float-float pairs prepared in fp64 beforehand; the rest of the quartic only needs
+// fp32.  Returns the corrected root t' = t - Q(t)/Q'(t) in fp32 (relative accuracy ~1e-7,
+// i.e. 5e-8 in the RMSD) and whether the iteration had settled.
+struct QcpPolyF {
+  float c0h, c0l, c1h, c1l, c2, c3;
+};
+
+LB_HD QcpPolyF qcp_poly_split(const QcpPoly& p) {
+  QcpPolyF f;
+  f.c0h = (float)p.c0; f.c0l = (float)(p.c0 - (double)f.c0h);
+  f.c1h = (float)p.c1; f.c1l = (float)(p.c1 - (double)f.c1h);
+  f.c2 = (float)p.c2; f.c3 = (float)p.c3;
+  return f;
+}
+
+LB_HD float qcp_polish_f32(const QcpPolyF& c, bool xform, float t, float last_step, bool* ok) {
+  // Q(t) = c0 + t c1 + t^2 (c2 + t (c3 + t)); the first two terms in float-float
+  const float p = t * c.c1h;
+  const float pe = fmaf(t, c.c1h, -p) + t * c.c1l;          // exact product error + low word
+  const float s = c.c0h + p;                                 // two-sum
+  const float bb = s - c.c0h;
+  const float se = (c.c0h - (s - bb)) + (p - bb);
+  const float tail = t * t * fmaf(t, c.c3 + t, c.c2);
+  const float f = s + (((se + pe) + c.c0l) + tail);
+  const float df = fmaf(t, fmaf(t, fmaf(t, 4.0f, 3.0f * c.c3), 2.0f * c.c2), c.c1h);
+  const float corr = LB_FDIV(f, df);
+  const float tn = t - corr;
+  const float yn = xform ? 1.0f - tn : tn;
+  *ok = (fabsf(last_step) <= 1e-5f * fabsf(t) + 1e-12f) && (fabsf(corr) <= 1e-4f * fabsf(tn) + 1e-12f) &&
+        (xform ? df > 0.0f : df < 0.0f) && (yn == yn) && (yn <= 1.0f + 1e-6f);
+  return yn < 0.0f ? -yn : yn;
+}
+
 #ifndef QCP_FAST_ITERS
 #define QCP_FAST_ITERS 10
 #endif
