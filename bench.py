@@ -51,7 +51,7 @@ class ClockSampler(threading.Thread):
     clocks_event_reasons.*`, without forking nvidia-smi, which stalls the driver for
     tens of ms per query)."""
 
-    def __init__(self, gpu_index, period=0.1):
+    def __init__(self, gpu_index, period=float(os.environ.get("LOOSB200_CLOCK_PERIOD", "0.25"))):
         super().__init__(daemon=True)
         self.idx, self.period, self.rows, self._stop_ev = gpu_index, period, [], threading.Event()
         self.max_mhz = None

@@ -101,6 +101,10 @@ int loosb200_stage_frames_device(loosb200_frames** out, const float* dev_xyz, si
                                  size_t natoms, const uint32_t* sel, size_t nsel, int layout,
                                  int device);
 void loosb200_free(loosb200_frames* h);
+/* Freed handles leave their large device buffers in a size-keyed cache so that the next
+ * call of the same shape skips cudaMalloc/cudaFree (hundreds of ms at 40 GB).  This
+ * returns the cache to the driver. */
+void loosb200_trim(void);
 int loosb200_frames_info(const loosb200_frames* h, size_t* F, size_t* N, int* device);
 /* Centroids as centerAtOrigin returns them: F x 3 doubles (host). */
 int loosb200_get_centroids(const loosb200_frames* h, double* out_F3);

@@ -43,6 +43,7 @@ SIGNATURES = {
     "loosb200_stage_append": (_i, [_vp, _vp, _sz]),
     "loosb200_stage_end": (_i, [_vp]),
     "loosb200_free": (None, [_vp]),
+    "loosb200_trim": (None, []),
     "loosb200_frames_info": (_i, [_vp, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i)]),
     "loosb200_get_centroids": (_i, [_vp, _dp]),
     "loosb200_get_unit_log2": (_i, [_vp, C.POINTER(_i)]),

@@ -4,6 +4,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -12,6 +14,65 @@
 namespace loosb200 {
 
 static thread_local std::string g_last_error;
+
+namespace {
+struct DevCache {
+  std::mutex mu;
+  std::map<std::pair<int, size_t>, std::vector<void*>> free_blocks;  // (device, bytes) -> blocks
+  std::map<void*, std::pair<int, size_t>> live;                     // block -> (device, bytes)
+  size_t cached_bytes = 0;
+};
+DevCache& cache() { static DevCache c; return c; }
+constexpr size_t CACHE_MIN_BLOCK = 1u << 20;          // small blocks are not worth keeping
+constexpr size_t CACHE_MAX_TOTAL = (size_t)96 << 30;  // never sit on more than this
+}  // namespace
+
+cudaError_t dev_alloc(void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DevCache& c = cache();
+  {
+    std::lock_guard<std::mutex> g(c.mu);
+    auto it = c.free_blocks.find(std::make_pair(dev, bytes));
+    if (it != c.free_blocks.end() && !it->second.empty()) {
+      *p = it->second.back();
+      it->second.pop_back();
+      c.cached_bytes -= bytes;
+      c.live[*p] = std::make_pair(dev, bytes);
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {  // give the cached blocks back and retry once
+    cudaGetLastError();
+    loosb200_trim();
+    e = cudaMalloc(p, bytes);
+  }
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> g(c.mu);
+    c.live[*p] = std::make_pair(dev, bytes);
+  }
+  return e;
+}
+
+void dev_release(void* p) {
+  if (!p) return;
+  DevCache& c = cache();
+  std::pair<int, size_t> info(-1, 0);
+  {
+    std::lock_guard<std::mutex> g(c.mu);
+    auto it = c.live.find(p);
+    if (it != c.live.end()) { info = it->second; c.live.erase(it); }
+    if (info.first >= 0 && info.second >= CACHE_MIN_BLOCK && c.cached_bytes + info.second <= CACHE_MAX_TOTAL) {
+      c.free_blocks[info].push_back(p);
+      c.cached_bytes += info.second;
+      return;
+    }
+  }
+  cudaFree(p);
+}
 
 void set_last_error(const std::string& s) { g_last_error = s; }
 
@@ -126,7 +187,7 @@ static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool sym
   std::vector<cudaEvent_t> evs(B.bands.size(), nullptr);
   auto cleanup = [&]() {
     cudaFree(d_rows); cudaFree(d_prefix); cudaFree(d_stats);
-    if (okind == OutKind::Host) cudaFree(d_out);
+    if (okind == OutKind::Host) dev_release(d_out);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     for (auto e : evs) if (e) cudaEventDestroy(e);
   };
@@ -135,7 +196,7 @@ static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool sym
             cudaMalloc(&d_stats, 2 * sizeof(double)) == cudaSuccess;
   if (ok && okind == OutKind::Host) {
     const size_t n = packed ? out_rows * dev_ld : out_cols * dev_ld;
-    ok = cudaMalloc(&d_out, sizeof(float) * std::max<size_t>(1, n)) == cudaSuccess &&
+    ok = dev_alloc_t(&d_out, sizeof(float) * std::max<size_t>(1, n)) == cudaSuccess &&
          cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (auto& e : evs) if (ok) ok = cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
   } else if (okind == OutKind::Device) {
@@ -232,6 +293,21 @@ static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool sym
 }  // namespace loosb200
 
 using namespace loosb200;
+
+extern "C" void loosb200_trim(void) {
+  DevCache& c = cache();
+  std::lock_guard<std::mutex> g(c.mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& kv : c.free_blocks) {
+    cudaSetDevice(kv.first.first);
+    for (void* p : kv.second) cudaFree(p);
+    kv.second.clear();
+  }
+  c.cached_bytes = 0;
+  cudaSetDevice(cur);
+  cudaGetLastError();
+}
 
 extern "C" const char* loosb200_version(void) { return "loosb200 0.1 (sm_100a)"; }
 

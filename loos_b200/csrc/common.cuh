@@ -34,6 +34,14 @@ constexpr int NUM_SLICES = 3;  // signed 8-bit digits of the 24-bit fixed-point 
 constexpr size_t TENSOR_MAX_ATOMS = 43000;
 
 void set_last_error(const std::string& s);
+
+// Size-keyed cache of device buffers (per device).  A staged frame set of C4 size owns
+// ~2.2 GB and the host-output path a 40 GB bounce matrix; cudaMalloc/cudaFree of such
+// blocks costs tens to hundreds of ms and synchronises the device, so freed blocks are
+// kept for the next call of the same shape (loosb200_trim() returns them to the driver).
+cudaError_t dev_alloc(void** p, size_t bytes);
+void dev_release(void* p);
+template <class T> inline cudaError_t dev_alloc_t(T** p, size_t bytes) { return dev_alloc(reinterpret_cast<void**>(p), bytes); }
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define LB_CUDA(call)                                                       \

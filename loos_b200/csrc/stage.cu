@@ -182,7 +182,7 @@ int ensure_quantised(loosb200_frames* h, int force_unit_log2) {
   h->Kpad = ((h->N + K_CHUNK - 1) / K_CHUNK) * K_CHUNK;
   const size_t bytes = (size_t)NUM_SLICES * h->rows_total * h->Kpad;
   if (!h->q8) {
-    if (cudaMalloc(&h->q8, bytes) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
+    if (dev_alloc_t(&h->q8, bytes) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
     if (cudaMalloc(&h->gq, sizeof(long long) * h->F) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
     if (cudaMalloc(&h->unit_log2_dev, 2 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
   }
@@ -231,7 +231,7 @@ static int alloc_handle(loosb200_frames** out, size_t F, size_t N, int device) {
   cudaError_t e;
   if ((e = cudaSetDevice(device)) != cudaSuccess) { delete h; return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__); }
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
-  bool ok = cudaMalloc(&h->raw, sizeof(float) * F * 3 * h->Npad) == cudaSuccess &&
+  bool ok = dev_alloc_t(&h->raw, sizeof(float) * F * 3 * h->Npad) == cudaSuccess &&
             cudaMalloc(&h->centroid, sizeof(double) * F * 3) == cudaSuccess &&
             cudaMalloc(&h->gd, sizeof(double) * F) == cudaSuccess &&
             cudaMalloc(&h->maxabs, sizeof(float) * F) == cudaSuccess;
@@ -317,7 +317,7 @@ struct Stager {
   ~Stager() {
     for (int i = 0; i < 2; ++i) {
       if (bounce[i]) cudaFreeHost(bounce[i]);
-      if (dchunk[i]) cudaFree(dchunk[i]);
+      if (dchunk[i]) dev_release(dchunk[i]);
       if (copied[i]) cudaEventDestroy(copied[i]);
       if (staged[i]) cudaEventDestroy(staged[i]);
     }
@@ -363,7 +363,7 @@ extern "C" int loosb200_stage_begin(loosb200_frames** out, size_t F, size_t nato
   if ((rc = upload_sel(sel, nsel, &s->sel_dev, h->stream))) { loosb200_free(h); return rc; }
   bool ok = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int k = 0; k < 2 && ok; ++k)
-    ok = cudaMalloc(&s->dchunk[k], s->chunk_frames * s->frame_bytes) == cudaSuccess &&
+    ok = dev_alloc_t(&s->dchunk[k], s->chunk_frames * s->frame_bytes) == cudaSuccess &&
          cudaMallocHost(&s->bounce[k], s->chunk_frames * s->frame_bytes) == cudaSuccess &&
          cudaEventCreateWithFlags(&s->copied[k], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&s->staged[k], cudaEventDisableTiming) == cudaSuccess;
@@ -431,8 +431,8 @@ extern "C" void loosb200_free(loosb200_frames* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->stager) { delete h->stager; h->stager = nullptr; }
-  cudaFree(h->raw); cudaFree(h->centroid); cudaFree(h->gd); cudaFree(h->maxabs);
-  cudaFree(h->q8); cudaFree(h->gq); cudaFree(h->unit_log2_dev);
+  dev_release(h->raw); cudaFree(h->centroid); cudaFree(h->gd); cudaFree(h->maxabs);
+  dev_release(h->q8); cudaFree(h->gq); cudaFree(h->unit_log2_dev);
   for (int i = 0; i < 4; ++i) if (h->timing.ev[i]) cudaEventDestroy(h->timing.ev[i]);
   for (cudaEvent_t e : h->timing.kev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
