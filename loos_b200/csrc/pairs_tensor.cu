@@ -54,12 +54,17 @@ constexpr int NTHREADS = 448;  // 2 control warps + 12 epilogue warps; 65536/448
 constexpr int NUM_EPI_WARPS = 12;
 constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;  // 384
 constexpr int TPAD = TILE_FRAMES + 1;  // out tile row pitch (floats)
+constexpr int NUM_SCHED = 4;           // depth of the tile-slot ring
+constexpr uint32_t SLOT_END = 0xffffffffu;
 
 struct __align__(8) SmemCtl {
   unsigned long long full[NUM_STAGES];
   unsigned long long empty[NUM_STAGES];
   unsigned long long tmem_full;
   unsigned long long tmem_empty;
+  unsigned long long sched_full[NUM_SCHED];   // ring of tile slots handed out by the cluster leader
+  unsigned long long sched_empty[NUM_SCHED];  // (only the leader CTA's copy is used)
+  uint32_t sched_slot[NUM_SCHED];
   uint32_t tmem_base;
   uint32_t pad;
   float T[2][COL_TILE_FRAMES][TPAD];  // double-buffered out tile, T[.][b][a]
@@ -98,6 +103,34 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity
     if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
     if (spin > (1u << 24)) __trap();  // seconds
   }
+}
+// Same, acquiring at cluster scope: the data guarded by the barrier was written by another CTA.
+template <int SLEEP_NS>
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* b, uint32_t parity) {
+  const uint32_t addr = smem_u32(b);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    if (spin > (1u << 24)) __trap();
+  }
+}
+// address of the same shared-memory object in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_remote_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar,
                                             int c0, int c1, int c2) {
@@ -174,7 +207,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 struct TensorArgs {
   const uint4* sblocks;        // super-blocks: {first row index, #rows, first column tile, #columns}
   const uint32_t* sb_prefix;   // [n_sb + 1] prefix sum of #rows * #columns (tile slots)
-  uint32_t n_slots;            // total slots; slots above the diagonal are skipped by every role alike
+  uint32_t n_slots;            // total slots; slots above the diagonal are skipped by the leader
+  uint32_t* counter;           // next slot to hand out (zeroed per launch)
   const uint32_t* row_tiles;   // row tile index -> I
   const long long* gA; const long long* gB;
   uint32_t FA, FB, N, n_kchunks;
@@ -187,44 +221,76 @@ struct TensorArgs {
 };
 
 
-// Tile slots are numbered super-block by super-block (row-major inside); cluster c takes
-// slots c, c + #clusters, ...  A slot is CL adjacent column tiles of one row tile: the CTAs of
-// a cluster (CL = 2) share the "a" operand, each loading half of it with TMA multicast.
-// All warp roles of all CTAs of a cluster walk the same sequence and apply the same tests,
-// so they stay in step without talking.  A CTA whose own column tile does not exist while
-// its partner's does shadows the partner's tile (same operands, results masked), which
-// keeps the multicast/barrier protocol identical for both.
+// Tile slots are numbered super-block by super-block (row-major inside).  A slot is CL
+// adjacent column tiles of one row tile: the CTAs of a cluster (CL = 2) share the "a" operand,
+// each loading half of it with TMA multicast.  Slots are handed out DYNAMICALLY: the producer
+// thread of the cluster's leader CTA takes the next slot from a global counter and publishes it
+// through a small shared-memory ring (one copy per CTA, written remotely for the partner); every
+// other role of every CTA of the cluster consumes the ring in order, so the roles stay in step
+// without further talk, and all slots in flight on the GPU are consecutive -- they share one
+// super-block's few MB of operands in L2.  (With a static slot = cluster + k * #clusters walk the
+// clusters drift apart over the ~50000 tiles each computes, and 55 % of the operand reads missed
+// L2: profiles/r1_summary.md.)  A CTA whose own column tile does not exist while its partner's
+// does shadows the partner's tile (same operands, results masked), which keeps the
+// multicast/barrier protocol identical for both.
 template <int CL>
 struct TileWalk {
-  uint32_t slot, sb, stride, crank;
-  __device__ __forceinline__ TileWalk(uint32_t rank) : slot(blockIdx.x / CL), sb(0), stride(gridDim.x / CL), crank(rank) {}
+  uint32_t sb, crank, ridx, rphase;
+  __device__ __forceinline__ TileWalk(uint32_t rank) : sb(0), crank(rank), ridx(0), rphase(0) {}
   __device__ __forceinline__ bool exists(const TensorArgs& a, const uint4& b, uint32_t I, uint32_t J) const {
     if (J >= b.z + b.w) return false;
     return !(a.self && (uint64_t)J * COL_TILE_FRAMES >= (uint64_t)I * TILE_FRAMES + TILE_FRAMES);
   }
-  // Next tile: returns false when the CTA is done.  rt = row index within the launch.
-  __device__ __forceinline__ bool next(const TensorArgs& a, uint32_t& rt, uint32_t& I, uint32_t& J, bool& masked) {
-    for (; slot < a.n_slots; slot += stride) {
-      while (slot >= a.sb_prefix[sb + 1]) ++sb;
-      const uint4 b = a.sblocks[sb];
-      const uint32_t ncg = (b.w + CL - 1) / CL;  // column groups per row
-      const uint32_t local = slot - a.sb_prefix[sb];
-      const uint32_t lr = local / ncg, lc = local - lr * ncg;
-      rt = b.x + lr;
-      I = a.row_tiles[rt];
-      J = b.z + lc * CL + crank;
-      masked = false;
-      if (!exists(a, b, I, J)) {
-        if (CL == 1) continue;
-        const uint32_t Jp = b.z + lc * CL + (crank ^ 1);
-        if (!exists(a, b, I, Jp)) continue;
-        J = Jp;
-        masked = true;
-      }
-      slot += stride;
-      return true;
+  // slot -> tile of this CTA; false when neither CTA of the cluster has a tile there.
+  // Slots arrive in increasing order, so the super-block search only moves forward.
+  __device__ __forceinline__ bool decode(const TensorArgs& a, uint32_t slot, uint32_t& rt, uint32_t& I, uint32_t& J,
+                                         bool& masked) {
+    while (slot >= a.sb_prefix[sb + 1]) ++sb;
+    const uint4 b = a.sblocks[sb];
+    const uint32_t ncg = (b.w + CL - 1) / CL;  // column groups per row
+    const uint32_t local = slot - a.sb_prefix[sb];
+    const uint32_t lr = local / ncg, lc = local - lr * ncg;
+    rt = b.x + lr;
+    I = a.row_tiles[rt];
+    J = b.z + lc * CL + crank;
+    masked = false;
+    if (!exists(a, b, I, J)) {
+      if (CL == 1) return false;
+      const uint32_t Jp = b.z + lc * CL + (crank ^ 1);
+      if (!exists(a, b, I, Jp)) return false;
+      J = Jp;
+      masked = true;
     }
-    return false;
+    return true;
+  }
+  // Leader producer thread: hand `slot` (or SLOT_END) to every consumer of the cluster.
+  __device__ __forceinline__ void publish(SmemCtl* ctl, uint32_t slot) {
+    mbar_wait_cluster<32>(&ctl->sched_empty[ridx], rphase ^ 1);
+    ctl->sched_slot[ridx] = slot;
+    mbar_arrive(&ctl->sched_full[ridx]);
+#pragma unroll
+    for (uint32_t r = 1; r < (uint32_t)CL; ++r) {
+      st_remote_u32(map_to_cta(&ctl->sched_slot[ridx], r), slot);
+      mbar_arrive_remote(map_to_cta(&ctl->sched_full[ridx], r));
+    }
+    if (++ridx == NUM_SCHED) { ridx = 0; rphase ^= 1; }
+  }
+  // Consumers: next tile, false when the cluster is done.  WARP: called by all lanes of a warp
+  // (one release per warp), otherwise by a single thread.
+  template <bool WARP>
+  __device__ __forceinline__ bool next(const TensorArgs& a, SmemCtl* ctl, uint32_t& rt, uint32_t& I, uint32_t& J,
+                                       bool& masked) {
+    mbar_wait_cluster<32>(&ctl->sched_full[ridx], rphase);
+    const uint32_t slot = *(volatile uint32_t*)&ctl->sched_slot[ridx];
+    if (WARP) __syncwarp();
+    if (!WARP || (threadIdx.x & 31) == 0) {
+      if (CL == 1 || crank == 0) mbar_arrive(&ctl->sched_empty[ridx]);
+      else mbar_arrive_remote(map_to_cta(&ctl->sched_empty[ridx], 0));
+    }
+    if (++ridx == NUM_SCHED) { ridx = 0; rphase ^= 1; }
+    if (slot == SLOT_END) return false;
+    decode(a, slot, rt, I, J, masked);  // published slots always decode
+    return true;
   }
 };
 
@@ -243,6 +309,11 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], CL); }
     mbar_init(&ctl->tmem_full, 1);
     mbar_init(&ctl->tmem_empty, NUM_EPI_WARPS);
+    // ring consumers: MMA thread + epilogue warps of every CTA, producer threads of the non-leaders
+    for (int s = 0; s < NUM_SCHED; ++s) {
+      mbar_init(&ctl->sched_full[s], 1);
+      mbar_init(&ctl->sched_empty[s], CL * (1 + NUM_EPI_WARPS) + (CL - 1));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -263,7 +334,18 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       TileWalk<CL> walk(crank);
       uint32_t rt, I, J;
       bool masked;
-      while (walk.next(a, rt, I, J, masked)) {
+      const bool leader = (CL == 1 || crank == 0);
+      uint32_t ahead = leader ? atomicAdd(a.counter, 1u) : 0u;  // the slot after the current one, fetched early
+      while (true) {
+        if (leader) {
+          const uint32_t slot = ahead;
+          if (slot >= a.n_slots) { walk.publish(ctl, SLOT_END); break; }
+          ahead = atomicAdd(a.counter, 1u);
+          if (!walk.decode(a, slot, rt, I, J, masked)) continue;  // above the diagonal
+          walk.publish(ctl, slot);
+        } else if (!walk.template next<false>(a, ctl, rt, I, J, masked)) {
+          break;
+        }
         const int rowA = (int)I * TILE_ROWS;
         const int rowB = (int)J * COL_TILE_ROWS;
         for (uint32_t kc = 0; kc < a.n_kchunks; ++kc) {
@@ -295,7 +377,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       TileWalk<CL> walk(crank);
       uint32_t rt, I, J;
       bool masked;
-      while (walk.next(a, rt, I, J, masked)) {
+      while (walk.template next<false>(a, ctl, rt, I, J, masked)) {
         mbar_wait<32>(&ctl->tmem_empty, tphase ^ 1);  // epilogue has drained the previous tile
         tc_fence_after();
         LB_TICK(0);  // waiting for TMEM
@@ -352,7 +434,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     TileWalk<CL> walk(crank);
     uint32_t rt, I, J;
     bool masked;
-    for (; walk.next(a, rt, I, J, masked); buf ^= 1) {
+    for (; walk.template next<true>(a, ctl, rt, I, J, masked); buf ^= 1) {
       const uint32_t i = I * TILE_FRAMES + a_local;
       const bool i_ok = active && i < a.FA && !masked;  // a shadow tile contributes nothing
       const double ga = i_ok ? (double)a.gA[i] : 0.0;
@@ -612,12 +694,15 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   uint32_t* d_prefix = nullptr;
   LB_CUDA(cudaMallocAsync(&d_sbl, sizeof(uint4) * sbl.size(), st));
   LB_CUDA(cudaMallocAsync(&d_prefix, sizeof(uint32_t) * prefix.size(), st));
+  uint32_t* d_counter = nullptr;
+  LB_CUDA(cudaMallocAsync(&d_counter, sizeof(uint32_t), st));
+  LB_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), st));
   LB_CUDA(cudaMemcpyAsync(d_sbl, sbl.data(), sizeof(uint4) * sbl.size(), cudaMemcpyHostToDevice, st));
   LB_CUDA(cudaMemcpyAsync(d_prefix, prefix.data(), sizeof(uint32_t) * prefix.size(), cudaMemcpyHostToDevice, st));
   // pageable sources: the copies have been staged by the time the calls return
 
   TensorArgs ta;
-  ta.sblocks = d_sbl; ta.sb_prefix = d_prefix; ta.n_slots = (uint32_t)slots;
+  ta.sblocks = d_sbl; ta.sb_prefix = d_prefix; ta.n_slots = (uint32_t)slots; ta.counter = d_counter;
   ta.row_tiles = job.row_tiles_dev;
   ta.gA = A->gq; ta.gB = B->gq;
   ta.FA = (uint32_t)A->F; ta.FB = FB; ta.N = (uint32_t)A->N;
@@ -672,6 +757,7 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   }
   LB_CUDA(cudaFreeAsync(d_sbl, st));
   LB_CUDA(cudaFreeAsync(d_prefix, st));
+  LB_CUDA(cudaFreeAsync(d_counter, st));
   if (launches) *launches = 1;
   return LOOSB200_OK;
 }
