@@ -215,6 +215,10 @@ def parity_sample(X_dev, M_get, F, N, owned=None, nrand=3000, nnear=1000):
             "tolerance": 1e-4, "checker": kind}
 
 
+NCU_TRAFFIC = {("c4", 1, "tensor"): 104.957248e9 + 40.027554e9}
+NCU_TRAFFIC_SOURCE = "profiles/r1_k_pairs_tensor_F100000_N1000_dynamic_metrics.csv (result matrix 40.0 GB written once, operands 0.92 GB read 114x)"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -366,6 +370,9 @@ def main():
         cpu = {"value": pps, "unit": UNIT, "cores": threads, "kind": kind,
                "sample": "first %d frames of the workload (%d pairs), %.1f s" % (S, S * (S - 1) // 2, dt)}
 
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_pairs_tensor launch from the committed
+    # ncu --set full capture (only that workload / engine / 1 GPU has a capture)
+    traffic = NCU_TRAFFIC.get((args.workload, world, args.engine)) if not (args.frames or args.atoms) else None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -383,7 +390,8 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
+                         "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
                          "kernel": "k_pairs_tensor" if args.engine != "fp64" else "k_pairs_fp64",
                          "kernel_ms_per_launch": kern_ms_step, "peak_basis": basis,
                          "algorithmic": "18*N flop per frame pair x pairs per launch"},

@@ -41,6 +41,8 @@ void set_last_error(const std::string& s);
 // kept for the next call of the same shape (loosb200_trim() returns them to the driver).
 cudaError_t dev_alloc(void** p, size_t bytes);
 void dev_release(void* p);
+cudaError_t host_alloc(void** p, size_t bytes);  // pinned host blocks, same cache
+void host_release(void* p);
 template <class T> inline cudaError_t dev_alloc_t(T** p, size_t bytes) { return dev_alloc(reinterpret_cast<void**>(p), bytes); }
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 

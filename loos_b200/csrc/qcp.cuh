@@ -24,9 +24,11 @@
 #if defined(__CUDA_ARCH__)
 #define LB_FDIV(a, b) __fdividef((a), (b))
 #define LB_FRCP(a) __frcp_rn(a)
+#define LB_FMUL(a, b) __fmul_rn((a), (b))  // a rounded product the compiler may not fuse into an FMA
 #else
 #define LB_FDIV(a, b) ((a) / (b))
 #define LB_FRCP(a) (1.0f / (a))
+#define LB_FMUL(a, b) ((a) * (b))
 #endif
 
 namespace loosb200 {
@@ -244,21 +246,159 @@ LB_HD double qcp_polish(const QcpPoly& p, float t, float last_step, bool* ok) {
   return yn < 0.0 ? -yn : yn;
 }
 
+// ---------------------------------------------------------------------------------------
+// The same quartic built WITHOUT fp64, in float-float ("two-float") arithmetic: a value is
+// an unevaluated sum h + l of two floats (~48 significant bits).  On sm_100 fp64 CUDA-core
+// math shares a pipe with the tensor cores and runs at a tenth of its rate while MMAs are in
+// flight (tools/ubench_contend.cu); fp32 is unaffected.  With this builder the tensor-core
+// epilogue needs fp64 only to drain the exact integer accumulators.
+//
+// Inputs: R = Rh + Rl (nine entries) and e0 = e0h + e0l, all scaled by one power of two such
+// that e0 lies in [0.5, 1) (|R_ij| <= e0 then keeps every intermediate in [-4, 4]).
+// Error budget: every product keeps its exact fp32 error term and first-order cross terms,
+// every sum is an error-free two-sum with the errors collected in an fp32 bucket, so each of
+// F, det S, G carries ~2^-46 and q0 (the coefficient that cancels) ~1e-13 absolute -- the
+// accuracy qcp_poly() documents for its fp64 coefficients (tests/test_qcp_host.py).
+struct FFAcc { float h, e; };  // running sum: two-sum chain in h, all error terms in e
+
+// s += (ah + al) (bh + bl)   (al bl is below 2^-48 of the product and dropped)
+LB_HD void ff_acc_prod(FFAcc& s, float ah, float al, float bh, float bl) {
+  const float p = LB_FMUL(ah, bh);
+  float pe = fmaf(ah, bh, -p);
+  pe = fmaf(ah, bl, pe);
+  pe = fmaf(al, bh, pe);
+  const float t = s.h + p, bb = t - s.h;
+  const float err = (s.h - (t - bb)) + (p - bb);
+  s.h = t;
+  s.e += err + pe;
+}
+// s += (ah + al)^2
+LB_HD void ff_acc_sq(FFAcc& s, float ah, float al) {
+  const float p = LB_FMUL(ah, ah);
+  float pe = fmaf(ah, ah, -p);
+  pe = fmaf(ah + ah, al, pe);
+  const float t = s.h + p, bb = t - s.h;
+  const float err = (s.h - (t - bb)) + (p - bb);
+  s.h = t;
+  s.e += err + pe;
+}
+// s += (ah + al), error-free in the high word
+LB_HD void ff_acc_add(FFAcc& s, float ah, float al) {
+  const float t = s.h + ah, bb = t - s.h;
+  const float err = (s.h - (t - bb)) + (ah - bb);
+  s.h = t;
+  s.e += err + al;
+}
+// normalise h + e into a float-float pair (full two-sum: after cancellation e may exceed h)
+LB_HD void ff_norm(const FFAcc& s, float& h, float& l) {
+  const float t = s.h + s.e, bb = t - s.h;
+  l = (s.h - (t - bb)) + (s.e - bb);
+  h = t;
+}
+// (ah + al)(bh + bl) -> (h, l)
+LB_HD void ff_mul(float ah, float al, float bh, float bl, float& h, float& l) {
+  const float p = LB_FMUL(ah, bh);
+  float pe = fmaf(ah, bh, -p);
+  pe = fmaf(ah, bl, pe);
+  pe = fmaf(al, bh, pe);
+  h = p + pe;
+  l = pe - (h - p);
+}
+// a b - c d -> (h, l), all operands float-float
+LB_HD void ff_minor(float ah, float al, float bh, float bl, float ch, float cl, float dh, float dl, float& h, float& l) {
+  FFAcc s;
+  s.h = LB_FMUL(ah, bh);
+  s.e = fmaf(ah, bh, -s.h);
+  s.e = fmaf(ah, bl, s.e);
+  s.e = fmaf(al, bh, s.e);
+  ff_acc_prod(s, -ch, -cl, dh, dl);
+  ff_norm(s, h, l);
+}
+
+struct QcpPolyF {
+  float c0h, c0l, c1h, c1l, c2h, c2l, c3;  // monic quartic in t (y-form, or x-form when xform)
+  float t0;                                 // Newton start
+  bool xform;
+};
+
+LB_HD QcpPolyF qcp_poly_ff(const float* Rh, const float* Rl, float e0h, float e0l) {
+  // 1/e0 to second order around the fp32 reciprocal
+  const float ih = LB_FRCP(e0h);
+  float r = fmaf(-e0h, ih, 1.0f);
+  r = fmaf(-e0l, ih, r);
+  const float il = ih * fmaf(r, r, r);
+  // cofactors of R
+  float ch[9], cl[9];
+#define LB_MINOR(k, a, b, c, d) ff_minor(Rh[a], Rl[a], Rh[b], Rl[b], Rh[c], Rl[c], Rh[d], Rl[d], ch[k], cl[k])
+  LB_MINOR(0, 4, 8, 5, 7); LB_MINOR(1, 5, 6, 3, 8); LB_MINOR(2, 3, 7, 4, 6);
+  LB_MINOR(3, 2, 7, 1, 8); LB_MINOR(4, 0, 8, 2, 6); LB_MINOR(5, 1, 6, 0, 7);
+  LB_MINOR(6, 1, 5, 2, 4); LB_MINOR(7, 2, 3, 0, 5); LB_MINOR(8, 0, 4, 1, 3);
+#undef LB_MINOR
+  FFAcc sF = {0.0f, 0.0f}, sG = {0.0f, 0.0f}, sD = {0.0f, 0.0f};
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { ff_acc_sq(sF, Rh[k], Rl[k]); ff_acc_sq(sG, ch[k], cl[k]); }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) ff_acc_prod(sD, Rh[k], Rl[k], ch[k], cl[k]);
+  float FRh, FRl, GRh, GRl, DRh, DRl;
+  ff_norm(sF, FRh, FRl); ff_norm(sG, GRh, GRl); ff_norm(sD, DRh, DRl);
+  // scale by powers of 1/e0
+  float i2h, i2l, i3h, i3l, i4h, i4l, Fh, Fl, Gh, Gl, Dh, Dl;
+  ff_mul(ih, il, ih, il, i2h, i2l);
+  ff_mul(i2h, i2l, ih, il, i3h, i3l);
+  ff_mul(i2h, i2l, i2h, i2l, i4h, i4l);
+  ff_mul(FRh, FRl, i2h, i2l, Fh, Fl);
+  ff_mul(GRh, GRl, i4h, i4l, Gh, Gl);
+  ff_mul(DRh, DRl, i3h, i3l, Dh, Dl);
+  Dh *= 8.0f; Dl *= 8.0f;  // D8 = 8 det S
+  QcpPolyF p;
+  const float xb = sqrtf(fmaxf(0.0f, 3.0f * Fh)) * 1.000001f;  // sqrt(-1.5 C2) >= lambda_max / e0
+  p.xform = xb < 0.5f;
+  if (!p.xform) {
+    // y-form: q0 = (1 - F)^2 - D8 - 4 G,  q1 = -4 (1 - F) + D8,  q2 = 6 - 2 F,  q3 = -4
+    FFAcc o = {1.0f, 0.0f};
+    ff_acc_add(o, -Fh, -Fl);
+    float oh, ol;
+    ff_norm(o, oh, ol);
+    FFAcc q = {0.0f, 0.0f};
+    ff_acc_sq(q, oh, ol);
+    ff_acc_add(q, -Dh, -Dl);
+    ff_acc_add(q, -4.0f * Gh, -4.0f * Gl);
+    ff_norm(q, p.c0h, p.c0l);
+    FFAcc q1 = {-4.0f * oh, -4.0f * ol};
+    ff_acc_add(q1, Dh, Dl);
+    ff_norm(q1, p.c1h, p.c1l);
+    FFAcc q2 = {6.0f, 0.0f};
+    ff_acc_add(q2, -2.0f * Fh, -2.0f * Fl);
+    ff_norm(q2, p.c2h, p.c2l);
+    p.c3 = -4.0f;
+    p.t0 = 0.0f;
+  } else {
+    // x-form: C0 = F^2 - 4 G,  C1 = -D8,  C2 = -2 F,  C3 = 0
+    FFAcc q = {0.0f, 0.0f};
+    ff_acc_sq(q, Fh, Fl);
+    ff_acc_add(q, -4.0f * Gh, -4.0f * Gl);
+    ff_norm(q, p.c0h, p.c0l);
+    p.c1h = -Dh; p.c1l = -Dl;
+    p.c2h = -2.0f * Fh; p.c2l = -2.0f * Fl;
+    p.c3 = 0.0f;
+    p.t0 = xb;
+  }
+  return p;
+}
+
 // fp64-free version of the residual correction, for code that runs while the tensor
 // pipe is busy (on sm_100 fp64 CUDA-core math shares that pipe and crawls under MMA load).
 // c0 and c1 -- the two coefficients whose sum cancels at the root -- are carried as
 // float-float pairs prepared in fp64 beforehand; the rest of the quartic only needs
 // fp32.  Returns the corrected root t' = t - Q(t)/Q'(t) in fp32 (relative accuracy ~1e-7,
 // i.e. 5e-8 in the RMSD) and whether the iteration had settled.
-struct QcpPolyF {
-  float c0h, c0l, c1h, c1l, c2, c3;
-};
-
 LB_HD QcpPolyF qcp_poly_split(const QcpPoly& p) {
   QcpPolyF f;
   f.c0h = (float)p.c0; f.c0l = (float)(p.c0 - (double)f.c0h);
   f.c1h = (float)p.c1; f.c1l = (float)(p.c1 - (double)f.c1h);
-  f.c2 = (float)p.c2; f.c3 = (float)p.c3;
+  f.c2h = (float)p.c2; f.c2l = (float)(p.c2 - (double)f.c2h);
+  f.c3 = (float)p.c3;
+  f.t0 = p.t0; f.xform = p.xform;
   return f;
 }
 
@@ -269,9 +409,9 @@ LB_HD float qcp_polish_f32(const QcpPolyF& c, bool xform, float t, float last_st
   const float s = c.c0h + p;                                 // two-sum
   const float bb = s - c.c0h;
   const float se = (c.c0h - (s - bb)) + (p - bb);
-  const float tail = t * t * fmaf(t, c.c3 + t, c.c2);
+  const float tail = t * t * fmaf(t, c.c3 + t, c.c2h);
   const float f = s + (((se + pe) + c.c0l) + tail);
-  const float df = fmaf(t, fmaf(t, fmaf(t, 4.0f, 3.0f * c.c3), 2.0f * c.c2), c.c1h);
+  const float df = fmaf(t, fmaf(t, fmaf(t, 4.0f, 3.0f * c.c3), 2.0f * c.c2h), c.c1h);
   const float corr = LB_FDIV(f, df);
   const float tn = t - corr;
   const float yn = xform ? 1.0f - tn : tn;

@@ -300,7 +300,8 @@ extern "C" int loosb200_stage_frames_device(loosb200_frames** out, const float* 
   return LOOSB200_OK;
 }
 
-// Host frames -> device: two pinned bounce buffers and two device chunk buffers;
+// Host frames -> device: two pinned bounce buffers (allocated on first use: a pinned caller
+// buffer is copied from directly) and two device chunk buffers;
 // the CPU (trajectory decode + memcpy) fills bounce[k] while the copy engine drains
 // bounce[k^1] on a side stream and the SMs gather the chunk before that.
 namespace loosb200 {
@@ -316,7 +317,7 @@ struct Stager {
   bool started = false;
   ~Stager() {
     for (int i = 0; i < 2; ++i) {
-      if (bounce[i]) cudaFreeHost(bounce[i]);
+      if (bounce[i]) host_release(bounce[i]);
       if (dchunk[i]) dev_release(dchunk[i]);
       if (copied[i]) cudaEventDestroy(copied[i]);
       if (staged[i]) cudaEventDestroy(staged[i]);
@@ -332,7 +333,15 @@ static int stager_push(loosb200_frames* h, Stager* s, const float* src, size_t n
   // slot k is free once the gather kernel that read dchunk[k] (two pushes ago) has finished
   cudaEventSynchronize(s->staged[s->k]);
   const float* from = src;
-  if (!src_pinned) { memcpy(s->bounce[s->k], src, nf * s->frame_bytes); from = s->bounce[s->k]; }
+  if (!src_pinned) {
+    if (!s->bounce[s->k] &&
+        host_alloc(reinterpret_cast<void**>(&s->bounce[s->k]), s->chunk_frames * s->frame_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return LOOSB200_ERR_NOMEM;
+    }
+    memcpy(s->bounce[s->k], src, nf * s->frame_bytes);
+    from = s->bounce[s->k];
+  }
   if (!s->started) { cudaEventRecord(h->timing.ev[0], h->stream); s->started = true; }
   cudaMemcpyAsync(s->dchunk[s->k], from, nf * s->frame_bytes, cudaMemcpyHostToDevice, s->copy_stream);
   cudaEventRecord(s->copied[s->k], s->copy_stream);
@@ -364,7 +373,6 @@ extern "C" int loosb200_stage_begin(loosb200_frames** out, size_t F, size_t nato
   bool ok = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int k = 0; k < 2 && ok; ++k)
     ok = dev_alloc_t(&s->dchunk[k], s->chunk_frames * s->frame_bytes) == cudaSuccess &&
-         cudaMallocHost(&s->bounce[k], s->chunk_frames * s->frame_bytes) == cudaSuccess &&
          cudaEventCreateWithFlags(&s->copied[k], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&s->staged[k], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { cudaGetLastError(); loosb200_free(h); return LOOSB200_ERR_NOMEM; }
