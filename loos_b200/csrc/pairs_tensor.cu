@@ -475,7 +475,6 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       // its throughput while MMAs run (tools/ubench_contend.cu), so the accumulators are
       // handed back only AFTER the fp64-heavy part; the fp32 Newton recurrences, the
       // final correction and the stores then overlap the next tile's MMAs.
-      QcpPoly poly[4];
       QcpPolyF polf[4];
       float e0s[4];
       int state[4];  // 0: no entry, 1: zero, 2: solve
@@ -525,30 +524,26 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         state[round] = stt;
         e0s[round] = (float)(2.0 * e0 * inv_n);  // msd = y * this
-        poly[round] = qcp_poly(R, e0);
-        polf[round] = qcp_poly_split(poly[round]);
+        polf[round] = qcp_poly_split(qcp_poly(R, e0));
       }
       // pin every fp64-derived value on this side of the hand-over: without this the compiler
       // is free to sink the fp64 -> float conversions below it, into the contended region
 #pragma unroll
       for (int r4 = 0; r4 < 4; ++r4)
         asm volatile("" : "+f"(polf[r4].c0h), "+f"(polf[r4].c0l), "+f"(polf[r4].c1h), "+f"(polf[r4].c1l),
-                          "+f"(polf[r4].c2), "+f"(polf[r4].c3), "+f"(e0s[r4]), "+f"(poly[r4].t0));
+                          "+f"(polf[r4].c2h), "+f"(polf[r4].c2l), "+f"(e0s[r4]), "+f"(polf[r4].t0));
       if (release_at == 1) { __syncwarp(); if (lane == 0) mbar_arrive(&ctl->tmem_empty); }
       LB_TICK(2);  // exchange + quartic coefficients (fp64)
 
       // ---- four fp32 Newton recurrences in lock-step, warp-uniform exit ----
-      float tt[4], ls[4], fc[4][4];
+      float tt[4], ls[4];
 #pragma unroll
-      for (int r4 = 0; r4 < 4; ++r4) {
-        tt[r4] = poly[r4].t0; ls[r4] = 0.0f;
-        fc[r4][0] = polf[r4].c0h; fc[r4][1] = polf[r4].c1h; fc[r4][2] = polf[r4].c2; fc[r4][3] = polf[r4].c3;
-      }
+      for (int r4 = 0; r4 < 4; ++r4) { tt[r4] = polf[r4].t0; ls[r4] = 0.0f; }
       for (int it = 0; it < 12; ++it) {
         bool conv = true;
 #pragma unroll
         for (int r4 = 0; r4 < 4; ++r4) {
-          ls[r4] = qcp_newton_step(fc[r4][0], fc[r4][1], fc[r4][2], fc[r4][3], tt[r4]);
+          ls[r4] = qcp_newton_step(polf[r4].c0h, polf[r4].c1h, polf[r4].c2h, polf[r4].c3, tt[r4]);
           conv = conv && (fabsf(ls[r4]) <= 4e-7f * fabsf(tt[r4]) + 1e-12f);
         }
         if (it >= 1 && __all_sync(0xffffffffu, conv)) break;
@@ -566,22 +561,11 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (state[round] == 2) {
           bool ok;
           // no fp64 here in the common case: this code overlaps the next tile's MMAs
-          float y = qcp_polish_f32(polf[round], poly[round].xform, tt[round], ls[round], &ok);
-          if (!ok || poly[round].xform || !(fabs(poly[round].c0) < 1e30)) {
-            // rare (dissimilar structures, multiple / far-off root, non-finite input): the same
-            // quartic in fp64, Newton from the fp32 root or from the upper bound
-            const QcpPoly& pp = poly[round];
-            double td = ok ? (double)tt[round] : (pp.xform ? (double)pp.t0 : 0.0);
-            for (int it = 0; it < 200; ++it) {
-              const double fd = fma(td, fma(td, fma(td, td + pp.c3, pp.c2), pp.c1), pp.c0);
-              const double dd = fma(td, fma(td, fma(td, 4.0, 3.0 * pp.c3), 2.0 * pp.c2), pp.c1);
-              if (dd == 0.0) break;
-              const double stp = fd / dd;
-              td -= stp;
-              if (fabs(stp) <= 1e-15 * fabs(td) + 1e-300) break;
-            }
-            const double yd = pp.xform ? 1.0 - td : td;
-            y = (float)(yd < 0.0 ? -yd : yd);
+          float y = qcp_polish_f32(polf[round], polf[round].xform, tt[round], ls[round], &ok);
+          if (!ok || polf[round].xform || !(fabsf(polf[round].c0h) < 1e30f)) {
+            // rare (dissimilar or mirror-image structures, multiple / far-off root, non-finite
+            // input): the same quartic in fp64, see qcp_root_fp64
+            y = (float)qcp_root_fp64(polf[round], ok ? tt[round] : polf[round].t0);
           }
           val = (float)a.unit * sqrtf(y * e0s[round]);
           // running sum of the float32 results as a float-float pair (error-free two-sum): the

@@ -415,9 +415,61 @@ LB_HD float qcp_polish_f32(const QcpPolyF& c, bool xform, float t, float last_st
   const float corr = LB_FDIV(f, df);
   const float tn = t - corr;
   const float yn = xform ? 1.0f - tn : tn;
+  // |Q'/Q''| below the noise floor of the coefficients: a (numerically) double root, which only
+  // qcp_root_fp64() resolves
+  const float ddf = fmaf(t, fmaf(t, 12.0f, 6.0f * c.c3), 2.0f * c.c2h);
   *ok = (fabsf(last_step) <= 1e-5f * fabsf(t) + 1e-12f) && (fabsf(corr) <= 1e-4f * fabsf(tn) + 1e-12f) &&
-        (xform ? df > 0.0f : df < 0.0f) && (yn == yn) && (yn <= 1.0f + 1e-6f);
+        (xform ? df > 0.0f : df < 0.0f) && (fabsf(df) >= 5e-7f * fabsf(ddf)) &&
+        (corr * corr * fabsf(ddf) <= 2e-7f * fabsf(tn) * fabsf(df) + 1e-30f) &&  // what one more step would still move
+        (fabsf(tail) <= 3.0f * fabsf(tn * df)) &&  // the fp32 part of Q(t) is accurate enough for this slope
+        (yn == yn) && (yn <= 1.0f + 1e-6f);
   return yn < 0.0f ? -yn : yn;
+}
+
+// Rare path (dissimilar structures, multiple or far-off root, Newton not settled): the same
+// quartic in fp64 from the float-float coefficients.  Returns y = 1 - lambda_max / E0 (>= 0).
+// Started outside the outermost root Newton is monotone and its steps -f/f' = 1 / sum_i 1/(r_i - t)
+// can only shrink; a step that grows means the outermost roots are a (numerically) double or
+// complex pair r +- sqrt(eps) -- collinear atoms, N = 2 -- where Q' has a simple root: finishing on
+// Q' recovers the root to O(eps) instead of O(sqrt(eps)).
+LB_HD double qcp_root_fp64(const QcpPolyF& p, float start) {
+  const double c0 = (double)p.c0h + (double)p.c0l, c1 = (double)p.c1h + (double)p.c1l;
+  const double c2 = (double)p.c2h + (double)p.c2l, c3 = (double)p.c3;
+  double td = (double)start, prev = 1e300;
+  bool multiple = false;
+  for (int it = 0; it < 200; ++it) {
+    const double fd = fma(td, fma(td, fma(td, td + c3, c2), c1), c0);
+    const double dd = fma(td, fma(td, fma(td, 4.0, 3.0 * c3), 2.0 * c2), c1);
+    if (dd == 0.0) { multiple = true; break; }
+    const double stp = fd / dd;
+    // rounding noise of the Horner evaluation, as a step
+    const double at = fabs(td);
+    const double noise = 4e-16 * (fabs(c0) + at * (fabs(c1) + at * (fabs(c2) + at * (fabs(c3) + at)))) / fabs(dd);
+    if (fabs(stp) <= 4.0 * noise) break;  // at the floor
+    if (fabs(stp) > prev) { multiple = true; break; }
+    prev = fabs(stp);
+    td -= stp;
+    if (fabs(stp) <= 1e-15 * fabs(td) + 1e-300) break;
+  }
+  if (!multiple) {
+    // a converged root closer than the coefficients' noise floor (sqrt(5e-14)) to a critical
+    // point cannot be told from a double root: treat it as one
+    const double d1 = fma(td, fma(td, fma(td, 4.0, 3.0 * c3), 2.0 * c2), c1);
+    const double d2 = fma(td, fma(td, 12.0, 6.0 * c3), 2.0 * c2);
+    multiple = fabs(d1) < 5e-7 * fabs(d2);
+  }
+  if (multiple) {
+    for (int it = 0; it < 60; ++it) {
+      const double d1 = fma(td, fma(td, fma(td, 4.0, 3.0 * c3), 2.0 * c2), c1);
+      const double d2 = fma(td, fma(td, 12.0, 6.0 * c3), 2.0 * c2);
+      if (d2 == 0.0) break;
+      const double stp = d1 / d2;
+      td -= stp;
+      if (fabs(stp) <= 1e-15 * fabs(td) + 1e-300) break;
+    }
+  }
+  const double yd = p.xform ? 1.0 - td : td;
+  return yd < 0.0 ? -yd : yd;
 }
 
 #ifndef QCP_FAST_ITERS

@@ -48,7 +48,10 @@ __global__ void __launch_bounds__(416, 1) k(double* out, long long* cyc, int ite
     const double c = 1.0000001, d = 1e-9;
     for (int i = 0; i < iters; ++i) {
       if (OP == 0) { a0 = fma(a0, c, d); a1 = fma(a1, c, d); a2 = fma(a2, c, d); a3 = fma(a3, c, d); }
-      else { f0 = fmaf(f0, 1.0000001f, 1e-9f); f1 = fmaf(f1, 1.0000001f, 1e-9f); f2 = fmaf(f2, 1.0000001f, 1e-9f); f3 = fmaf(f3, 1.0000001f, 1e-9f); }
+      else if (OP == 1) { f0 = fmaf(f0, 1.0000001f, 1e-9f); f1 = fmaf(f1, 1.0000001f, 1e-9f); f2 = fmaf(f2, 1.0000001f, 1e-9f); f3 = fmaf(f3, 1.0000001f, 1e-9f); }
+      else if (OP == 2) { f0 = __shfl_sync(0xffffffffu, f0, (lane + 1) & 31); f1 = __shfl_sync(0xffffffffu, f1, (lane + 2) & 31); f2 = __shfl_sync(0xffffffffu, f2, (lane + 3) & 31); f3 = __shfl_sync(0xffffffffu, f3, (lane + 4) & 31); }
+      else if (OP == 3) { f0 = __double2float_rn(a0 + f0); f1 = __double2float_rn(a1 + f1); f2 = __double2float_rn(a2 + f2); f3 = __double2float_rn(a3 + f3); }
+      else if (OP == 4) { f0 = f0 + f1; f1 = f1 - f2; f2 = f2 + f3; f3 = f3 - f0; }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + f0 + f1 + f2 + f3;
     if (threadIdx.x == 32) cyc[blockIdx.x * 2 + 1] = clock64() - t0;
@@ -77,5 +80,12 @@ int main() {
   run<0>("DFMA", 10, 20000);     // MMA alone
   run<1>("FFMA", 40000, 0);
   run<1>("FFMA", 40000, 20000);
+  run<1>("FFMA", 80000, 20000);
+  run<2>("SHFL", 10000, 0);
+  run<2>("SHFL", 10000, 20000);
+  run<3>("F2F+DADD", 10000, 0);
+  run<3>("F2F+DADD", 10000, 20000);
+  run<4>("FADD", 40000, 0);
+  run<4>("FADD", 80000, 20000);
   return 0;
 }
