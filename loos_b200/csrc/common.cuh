@@ -28,7 +28,7 @@ constexpr int TILE_ROWS = ROWS_PER_BLOCK * BLOCKS_PER_TILE;      // 128
 constexpr int COL_BLOCKS_PER_TILE = 3;
 constexpr int COL_TILE_FRAMES = FRAMES_PER_BLOCK * COL_BLOCKS_PER_TILE;  // 30
 constexpr int COL_TILE_ROWS = ROWS_PER_BLOCK * COL_BLOCKS_PER_TILE;      // 96
-constexpr int K_CHUNK = 64;    // atoms (bytes of int8) per pipeline stage / swizzle row
+constexpr int K_CHUNK = 128;   // atoms (bytes of int8) per pipeline stage = one 128-byte swizzle row
 constexpr int NUM_SLICES = 3;  // signed 8-bit digits of the 24-bit fixed-point coordinate
 // int32 accumulators hold up to 3 slice products of magnitude <= 2^14 per atom.
 constexpr size_t TENSOR_MAX_ATOMS = 43000;

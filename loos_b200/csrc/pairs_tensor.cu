@@ -18,8 +18,8 @@
 // covariance tiles never touch HBM.
 //
 // Warp roles (448 threads, 1 CTA per SM, persistent over a tile list):
-//   warp 0   TMA producer: per 64-atom K chunk one 3-D box for A (64 x 128 rows x
-//            3 digits = 24 KB) and one for B (64 x 96 x 3 = 18 KB), SWIZZLE_64B
+//   warp 0   TMA producer: per 128-atom K chunk one 3-D box for A (128 B x 128 rows x
+//            3 digits = 48 KB) and one for B (128 B x 96 x 3 = 36 KB), SWIZZLE_128B
 //   warp 1   TMEM allocator + MMA issuer: per 32-atom K step six tcgen05.mma
 //            (three with N = 192 spanning two adjacent classes, three with N = 96)
 //   warps 2-13 epilogue, one (lane quarter, 10-frame column group) each:
@@ -41,12 +41,12 @@ namespace loosb200 {
 
 namespace {
 
-constexpr int NUM_STAGES = 4;
-constexpr int A_STAGE_BYTES = NUM_SLICES * TILE_ROWS * K_CHUNK;      // 24576
-constexpr int B_STAGE_BYTES = NUM_SLICES * COL_TILE_ROWS * K_CHUNK;  // 18432
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;           // 43008
-constexpr int A_SLICE_BYTES = TILE_ROWS * K_CHUNK;                   // 8192
-constexpr int B_SLICE_BYTES = COL_TILE_ROWS * K_CHUNK;               // 6144
+constexpr int NUM_STAGES = 2;
+constexpr int A_STAGE_BYTES = NUM_SLICES * TILE_ROWS * K_CHUNK;      // 49152
+constexpr int B_STAGE_BYTES = NUM_SLICES * COL_TILE_ROWS * K_CHUNK;  // 36864
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;           // 86016
+constexpr int A_SLICE_BYTES = TILE_ROWS * K_CHUNK;                   // 16384
+constexpr int B_SLICE_BYTES = COL_TILE_ROWS * K_CHUNK;               // 12288
 constexpr int NUM_CLASSES = 5;
 constexpr int CLASS_COLS = COL_TILE_ROWS;  // 96
 constexpr int TMEM_COLS = 512;
@@ -182,12 +182,13 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor,
-// cutlass mma_sm100_desc.hpp:98-121): start>>4 | LBO=1<<16 | SBO=(8 rows*64 B)>>4<<32
-// | version 1<<46 | layout SWIZZLE_64B(4)<<61.
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor,
+// cutlass mma_sm100_desc.hpp:98-121): start>>4 | LBO=1<<16 | SBO=(8 rows*128 B)>>4<<32
+// | version 1<<46 | layout SWIZZLE_128B(2)<<61.  A K step of 32 int8 inside the 128-byte
+// swizzle row is addressed by advancing the start address by 32 bytes.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed
 // int8, both K-major, M = 128, N = n.
@@ -646,7 +647,9 @@ bool tensor_path_available() { return true; }
 int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   constexpr uint32_t SB_R = 12, SB_C = 16;
   const char* cl_env = getenv("LOOSB200_CLUSTER");
-  const uint32_t CLs = (cl_env && atoi(cl_env) == 1) ? 1u : 2u;  // CTAs per cluster sharing the "a" tile
+  // CTAs per cluster sharing the "a" tile.  Default 1: multicast saves 12 % of the L2 reads but
+  // not the bytes an SM has to ingest, and measures 2-5 % slower (profiles/r1_summary.md).
+  const uint32_t CLs = (cl_env && atoi(cl_env) == 2) ? 2u : 1u;
   const loosb200_frames* A = job.a;
   const loosb200_frames* B = job.b;
   if (!A->quantised || !B->quantised || A->unit_log2 != B->unit_log2 || A->Kpad != B->Kpad)
@@ -695,8 +698,10 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   ta.unit = exp2((double)A->unit_log2);
   ta.out = job.out; ta.ld = job.ld; ta.stats = job.stats_dev;
   ta.prof = nullptr;
-  // Short contractions are bound by the epilogue: hold the accumulators until its fp64 part is
-  // done (fp64 crawls while MMAs run); long ones are MMA-bound: hand them back right after the drain.
+  // Short contractions: hold the accumulators until the epilogue's fp64 part is done (fp64
+  // crawls while MMAs run, and with two 128-atom stages the MMA warp would otherwise start a tile
+  // it cannot feed); long ones: hand them back right after the drain.  Measured both ways at
+  // N = 1000 and N = 3000 (profiles/r1_summary.md).
   ta.release_at = getenv("LOOSB200_RELEASE_AT") ? atoi(getenv("LOOSB200_RELEASE_AT")) : (A->Kpad <= 2048 ? 1 : 0);
   const bool want_prof = getenv("LOOSB200_PROF") != nullptr;
 

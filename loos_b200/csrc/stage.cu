@@ -199,7 +199,7 @@ int ensure_quantised(loosb200_frames* h, int force_unit_log2) {
   h->quantised = true;
   h->timing.launches += 2;
 
-  // 3-D tensor map (atom, row, slice); one TMA box = 64 atoms x 128 rows x 3 slices.
+  // 3-D tensor map (atom, row, slice); one TMA box = 128 atoms x 128 rows x 3 slices.
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   if (!enc) { set_last_error("cuTensorMapEncodeTiled not available"); return LOOSB200_ERR_CUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)h->Kpad, (cuuint64_t)h->rows_total, (cuuint64_t)NUM_SLICES};
@@ -210,7 +210,7 @@ int ensure_quantised(loosb200_frames* h, int force_unit_log2) {
                          (cuuint32_t)(which == 2 ? 1 : NUM_SLICES)};
     CUtensorMap* dst = which == 0 ? &h->tmapA : which == 1 ? &h->tmapB : &h->tmapAh;
     CUresult r = enc(dst, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->q8, dims, strides, box,
-                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
