@@ -84,9 +84,9 @@ struct loosb200_frames {
   int unit_log2 = 0;
   bool quantised = false;
   size_t rows_total = 0, Kpad = 0;
-  CUtensorMap tmapA;  // 3-D map over q8 (atom, row, slice), box 64 x 128 x 3
-  CUtensorMap tmapAh; // same tensor, box 64 x 64 x 1 (half an "a" tile of one digit, for cluster multicast)
-  CUtensorMap tmapB;  // same tensor, box 64 x 96 x 3
+  CUtensorMap tmapA;  // 3-D map over q8 (atom, row, slice), box 128 x 128 x 3
+  CUtensorMap tmapB96, tmapB48;  // same tensor, boxes 128 x 96 x 1 and 128 x 48 x 1: the halves of a "b" stage a CTA of a pair loads
+  CUtensorMap tmapB;  // same tensor, box 128 x 96 x 3
   bool tmap_valid = false;
 
   cudaStream_t stream = nullptr;

@@ -41,12 +41,26 @@ namespace loosb200 {
 
 namespace {
 
-constexpr int NUM_STAGES = 2;
+// Two launch shapes (template parameter CL):
+//   CL = 1  one CTA per tile, tcgen05 cta_group::1: stage = A 48 KB + B 36 KB, 2 stages
+//   CL = 2  a CTA PAIR per two row tiles x one column tile, tcgen05 cta_group::2 (UMMA M = 256):
+//           each CTA loads its own "a" tile and HALF of the shared "b" operand (digit 1 or 2 in
+//           full and half the rows of digit 0); the tensor cores of both SMs read both halves.
+//           Stage = A 48 KB + B 18 KB, 3 stages, and 21 % fewer operand bytes leave L2 per pair.
+constexpr int MAX_STAGES = 3;
 constexpr int A_STAGE_BYTES = NUM_SLICES * TILE_ROWS * K_CHUNK;      // 49152
-constexpr int B_STAGE_BYTES = NUM_SLICES * COL_TILE_ROWS * K_CHUNK;  // 36864
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;           // 86016
 constexpr int A_SLICE_BYTES = TILE_ROWS * K_CHUNK;                   // 16384
 constexpr int B_SLICE_BYTES = COL_TILE_ROWS * K_CHUNK;               // 12288
+template <int CL> struct Shape;
+template <> struct Shape<1> {
+  static constexpr int STAGES = 2;
+  static constexpr int B_STAGE_BYTES = NUM_SLICES * B_SLICE_BYTES;   // 36864
+};
+template <> struct Shape<2> {
+  static constexpr int STAGES = 3;
+  static constexpr int B_STAGE_BYTES = B_SLICE_BYTES + B_SLICE_BYTES / 2;  // 18432: one digit + half of digit 0
+};
+template <int CL> __host__ __device__ constexpr int stage_bytes() { return A_STAGE_BYTES + Shape<CL>::B_STAGE_BYTES; }
 constexpr int NUM_CLASSES = 5;
 constexpr int CLASS_COLS = COL_TILE_ROWS;  // 96
 constexpr int TMEM_COLS = 512;
@@ -58,8 +72,8 @@ constexpr int NUM_SCHED = 4;           // depth of the tile-slot ring
 constexpr uint32_t SLOT_END = 0xffffffffu;
 
 struct __align__(8) SmemCtl {
-  unsigned long long full[NUM_STAGES];
-  unsigned long long empty[NUM_STAGES];
+  unsigned long long full[MAX_STAGES];
+  unsigned long long empty[MAX_STAGES];
   unsigned long long tmem_full;
   unsigned long long tmem_empty;
   unsigned long long sched_full[NUM_SCHED];   // ring of tile slots handed out by the cluster leader
@@ -71,7 +85,7 @@ struct __align__(8) SmemCtl {
   double red_sum[NUM_EPI_WARPS], red_max[NUM_EPI_WARPS];
 };
 
-constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + (int)sizeof(SmemCtl) + 1024;
+template <int CL> __host__ __device__ constexpr int smem_bytes() { return Shape<CL>::STAGES * stage_bytes<CL>() + (int)sizeof(SmemCtl) + 1024; }
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -138,16 +152,18 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, unsigned long long* bar,
-                                               int c0, int c1, int c2, uint16_t cta_mask) {
+// CTA-pair forms (cute SM100_TMA_2SM_LOAD_3D, umma_arrive_multicast_2x1SM): both CTAs issue their
+// loads against the LEADER's barrier (its shared::cluster address, from mapa); the leader's
+// commit arrives on the same barrier in both CTAs.
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, unsigned long long* bar,
+                                                 int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-      "[%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask) : "memory");
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(map_to_cta(bar, 0)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void tc_commit_mc(unsigned long long* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+__device__ __forceinline__ void tc_commit_pair(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)0x3) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -162,12 +178,20 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+template <int CL>
 __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+  if (CL == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -191,9 +215,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed
-// int8, both K-major, M = 128, N = n.
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// int8, both K-major, M = m (128, or 256 across a CTA pair), N = n.
+__host__ __device__ constexpr uint32_t make_idesc(int n, int m) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 #define LB_TICK(slot)                                               \
@@ -222,46 +246,47 @@ struct TensorArgs {
 };
 
 
-// Tile slots are numbered super-block by super-block (row-major inside).  A slot is CL
-// adjacent column tiles of one row tile: the CTAs of a cluster (CL = 2) share the "a" operand,
-// each loading half of it with TMA multicast.  Slots are handed out DYNAMICALLY: the producer
-// thread of the cluster's leader CTA takes the next slot from a global counter and publishes it
-// through a small shared-memory ring (one copy per CTA, written remotely for the partner); every
-// other role of every CTA of the cluster consumes the ring in order, so the roles stay in step
+// Tile slots are numbered super-block by super-block (row-major inside).  A slot is one tile
+// (CL = 1) or, for a CTA pair (CL = 2), two consecutive row tiles of the job against one column
+// tile: the pair shares the "b" operand, CTA r takes row r of the two.  Slots are handed out
+// DYNAMICALLY: the producer thread of the leader CTA takes the next slot from a global counter
+// and publishes it through a small shared-memory ring (one copy per CTA, written remotely for the
+// partner); every other role of every CTA consumes the ring in order, so the roles stay in step
 // without further talk, and all slots in flight on the GPU are consecutive -- they share one
 // super-block's few MB of operands in L2.  (With a static slot = cluster + k * #clusters walk the
-// clusters drift apart over the ~50000 tiles each computes, and 55 % of the operand reads missed
-// L2: profiles/r1_summary.md.)  A CTA whose own column tile does not exist while its partner's
-// does shadows the partner's tile (same operands, results masked), which keeps the
-// multicast/barrier protocol identical for both.
+// CTAs drift apart over the ~28000 tiles each computes, and 55 % of the operand reads missed
+// L2: profiles/r1_summary.md.)  A CTA of a pair whose own tile does not exist (above the
+// diagonal, or an odd row count) while its partner's does still loads its half of "b" and some
+// valid "a" rows and takes part in every barrier; its results are masked.
 template <int CL>
 struct TileWalk {
   uint32_t sb, crank, ridx, rphase;
   __device__ __forceinline__ TileWalk(uint32_t rank) : sb(0), crank(rank), ridx(0), rphase(0) {}
-  __device__ __forceinline__ bool exists(const TensorArgs& a, const uint4& b, uint32_t I, uint32_t J) const {
-    if (J >= b.z + b.w) return false;
-    return !(a.self && (uint64_t)J * COL_TILE_FRAMES >= (uint64_t)I * TILE_FRAMES + TILE_FRAMES);
+  __device__ __forceinline__ bool above_diagonal(const TensorArgs& a, uint32_t I, uint32_t J) const {
+    return a.self && (uint64_t)J * COL_TILE_FRAMES >= (uint64_t)I * TILE_FRAMES + TILE_FRAMES;
   }
-  // slot -> tile of this CTA; false when neither CTA of the cluster has a tile there.
+  // slot -> tile of this CTA; false when no CTA of the cluster has a tile there.
   // Slots arrive in increasing order, so the super-block search only moves forward.
   __device__ __forceinline__ bool decode(const TensorArgs& a, uint32_t slot, uint32_t& rt, uint32_t& I, uint32_t& J,
                                          bool& masked) {
     while (slot >= a.sb_prefix[sb + 1]) ++sb;
-    const uint4 b = a.sblocks[sb];
-    const uint32_t ncg = (b.w + CL - 1) / CL;  // column groups per row
+    const uint4 b = a.sblocks[sb];  // {first row index, #rows, first column tile, #columns}
     const uint32_t local = slot - a.sb_prefix[sb];
-    const uint32_t lr = local / ncg, lc = local - lr * ncg;
-    rt = b.x + lr;
-    I = a.row_tiles[rt];
-    J = b.z + lc * CL + crank;
+    const uint32_t lr = local / b.w, lc = local - lr * b.w;
+    J = b.z + lc;
     masked = false;
-    if (!exists(a, b, I, J)) {
-      if (CL == 1) return false;
-      const uint32_t Jp = b.z + lc * CL + (crank ^ 1);
-      if (!exists(a, b, I, Jp)) return false;
-      J = Jp;
-      masked = true;
+    if (CL == 1) {
+      rt = b.x + lr;
+      I = a.row_tiles[rt];
+      return !above_diagonal(a, I, J);
     }
+    // rows of the job are ascending, so the second row of a pair reaches further right
+    const uint32_t r0 = b.x + 2 * lr, r1 = r0 + 1 < b.x + b.y ? r0 + 1 : r0;
+    const uint32_t I1 = a.row_tiles[r1];
+    if (above_diagonal(a, I1, J)) return false;
+    rt = crank == 0 ? r0 : r1;
+    I = a.row_tiles[rt];
+    masked = (crank == 1 && r1 == r0) || above_diagonal(a, I, J);
     return true;
   }
   // Leader producer thread: hand `slot` (or SLOT_END) to every consumer of the cluster.
@@ -295,10 +320,20 @@ struct TileWalk {
   }
 };
 
+// An epilogue warp hands the accumulators back: to the MMA thread of its own CTA, or of the leader.
+template <int CL>
+__device__ __forceinline__ void release_tmem(SmemCtl* ctl, uint32_t crank) {
+  if (CL == 1 || crank == 0) mbar_arrive(&ctl->tmem_empty);
+  else mbar_arrive_remote(map_to_cta(&ctl->tmem_empty, 0));
+}
+
 template <int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAh,
-               const __grid_constant__ CUtensorMap mapB, const TensorArgs a) {
+k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapB96, const __grid_constant__ CUtensorMap mapB48,
+               const TensorArgs a) {
+  constexpr int NUM_STAGES = Shape<CL>::STAGES;
+  constexpr int STAGE_BYTES = stage_bytes<CL>();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   SmemCtl* ctl = (SmemCtl*)(smem + NUM_STAGES * STAGE_BYTES);
@@ -306,10 +341,11 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
-    // empty[s] collects the MMA completions of every CTA that multicasts into this CTA's slot
-    for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], CL); }
+    // pair: the leader's full[s] collects the bytes of both CTAs, its commits arrive on empty[s]
+    // and tmem_full of both, and its tmem_empty collects the epilogue warps of both
+    for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
     mbar_init(&ctl->tmem_full, 1);
-    mbar_init(&ctl->tmem_empty, NUM_EPI_WARPS);
+    mbar_init(&ctl->tmem_empty, CL * NUM_EPI_WARPS);
     // ring consumers: MMA thread + epilogue warps of every CTA, producer threads of the non-leaders
     for (int s = 0; s < NUM_SCHED; ++s) {
       mbar_init(&ctl->sched_full[s], 1);
@@ -318,8 +354,13 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "n"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (CL == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "n"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    } else {  // the same warp of both CTAs, same destination address
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "n"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
   }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();  // barriers of both CTAs exist before any remote signal
@@ -330,7 +371,12 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ================= TMA producer =================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+      if (CL == 1) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+      } else {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB96) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB48) : "memory");
+      }
       uint32_t stage = 0, phase = 0;
       TileWalk<CL> walk(crank);
       uint32_t rt, I, J;
@@ -352,18 +398,20 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (uint32_t kc = 0; kc < a.n_kchunks; ++kc) {
           mbar_wait<32>(&ctl->empty[stage], phase ^ 1);
           unsigned char* sA = smem + stage * STAGE_BYTES;
-          mbar_expect_tx(&ctl->full[stage], STAGE_BYTES);
+          const int k0 = (int)(kc * K_CHUNK);
           if (CL == 1) {
-            tma_load_3d(sA, &mapA, &ctl->full[stage], (int)(kc * K_CHUNK), rowA, 0);
+            mbar_expect_tx(&ctl->full[stage], STAGE_BYTES);
+            tma_load_3d(sA, &mapA, &ctl->full[stage], k0, rowA, 0);
+            tma_load_3d(sA + A_STAGE_BYTES, &mapB, &ctl->full[stage], k0, rowB, 0);
           } else {
-            // this CTA's half of the shared "a" tile (64 rows of each digit) goes to both CTAs
-            const int half_rows = TILE_ROWS / 2;
-#pragma unroll
-            for (int d = 0; d < NUM_SLICES; ++d)
-              tma_load_3d_mc(sA + d * A_SLICE_BYTES + crank * (half_rows * K_CHUNK), &mapAh, &ctl->full[stage],
-                             (int)(kc * K_CHUNK), rowA + (int)crank * half_rows, d, (uint16_t)0x3);
+            if (crank == 0) mbar_expect_tx(&ctl->full[stage], 2 * STAGE_BYTES);
+            tma_load_3d_pair(sA, &mapA, &ctl->full[stage], k0, rowA, 0);
+            // this CTA's half of "b": digit 1 + crank in full (the N = 192 operand is [digit 1 | digit 2],
+            // one digit per CTA) and rows [48 crank, +48) of digit 0 (the N = 96 operand)
+            tma_load_3d_pair(sA + A_STAGE_BYTES, &mapB96, &ctl->full[stage], k0, rowB, 1 + (int)crank);
+            tma_load_3d_pair(sA + A_STAGE_BYTES + B_SLICE_BYTES, &mapB48, &ctl->full[stage], k0,
+                             rowB + (int)crank * (COL_TILE_ROWS / 2), 0);
           }
-          tma_load_3d(sA + A_STAGE_BYTES, &mapB, &ctl->full[stage], (int)(kc * K_CHUNK), rowB, 0);
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -371,7 +419,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t ID192 = make_idesc(2 * CLASS_COLS), ID96 = make_idesc(CLASS_COLS);
+      constexpr uint32_t ID192 = make_idesc(2 * CLASS_COLS, 128 * CL), ID96 = make_idesc(CLASS_COLS, 128 * CL);
       uint32_t stage = 0, phase = 0, tphase = 0;
       long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       long long tprev = a.prof ? clock64() : 0;
@@ -379,7 +427,9 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       uint32_t rt, I, J;
       bool masked;
       while (walk.template next<false>(a, ctl, rt, I, J, masked)) {
-        mbar_wait<32>(&ctl->tmem_empty, tphase ^ 1);  // epilogue has drained the previous tile
+        if (CL > 1 && crank != 0) continue;  // only the leader of a pair issues; the other keeps the ring moving
+        // the epilogue (of both CTAs) has drained the previous tile
+        if (CL == 1) mbar_wait<32>(&ctl->tmem_empty, tphase ^ 1); else mbar_wait_cluster<32>(&ctl->tmem_empty, tphase ^ 1);
         tc_fence_after();
         LB_TICK(0);  // waiting for TMEM
         for (uint32_t kc = 0; kc < a.n_kchunks; ++kc) {
@@ -394,19 +444,22 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint64_t A0 = make_desc(sA + 0 * A_SLICE_BYTES + ks * 32);
             const uint64_t A1 = make_desc(sA + 1 * A_SLICE_BYTES + ks * 32);
             const uint64_t A2 = make_desc(sA + 2 * A_SLICE_BYTES + ks * 32);
-            const uint64_t B0 = make_desc(sB + 0 * B_SLICE_BYTES + ks * 32);
-            const uint64_t B1 = make_desc(sB + 1 * B_SLICE_BYTES + ks * 32);  // spans digits 1,2 when N = 192
+            // single CTA: digits 0 | 1 | 2 of "b" back to back, the N = 192 operand spans digits 1, 2.
+            // pair: [this CTA's digit (96 rows) | its 48 rows of digit 0]; the hardware reads the
+            // other half of N at the same offsets of the partner's shared memory.
+            const uint64_t B0 = make_desc(sB + (CL == 1 ? 0 : B_SLICE_BYTES) + ks * 32);
+            const uint64_t B1 = make_desc(sB + (CL == 1 ? B_SLICE_BYTES : 0) + ks * 32);
             // class s lives at columns [96 s, 96 s + 96); first touch of a class overwrites
-            tc_mma_i8(tmem_base + 3 * CLASS_COLS, A2, B1, ID192, first);  // a2.b1 -> s3, a2.b2 -> s4
-            tc_mma_i8(tmem_base + 1 * CLASS_COLS, A0, B1, ID192, first);  // a0.b1 -> s1, a0.b2 -> s2
-            tc_mma_i8(tmem_base + 0 * CLASS_COLS, A0, B0, ID96, first);   // a0.b0 -> s0
-            tc_mma_i8(tmem_base + 2 * CLASS_COLS, A1, B1, ID192, 1u);     // a1.b1 -> s2, a1.b2 -> s3
-            tc_mma_i8(tmem_base + 2 * CLASS_COLS, A2, B0, ID96, 1u);      // a2.b0 -> s2
-            tc_mma_i8(tmem_base + 1 * CLASS_COLS, A1, B0, ID96, 1u);      // a1.b0 -> s1
+            tc_mma_i8<CL>(tmem_base + 3 * CLASS_COLS, A2, B1, ID192, first);  // a2.b1 -> s3, a2.b2 -> s4
+            tc_mma_i8<CL>(tmem_base + 1 * CLASS_COLS, A0, B1, ID192, first);  // a0.b1 -> s1, a0.b2 -> s2
+            tc_mma_i8<CL>(tmem_base + 0 * CLASS_COLS, A0, B0, ID96, first);   // a0.b0 -> s0
+            tc_mma_i8<CL>(tmem_base + 2 * CLASS_COLS, A1, B1, ID192, 1u);     // a1.b1 -> s2, a1.b2 -> s3
+            tc_mma_i8<CL>(tmem_base + 2 * CLASS_COLS, A2, B0, ID96, 1u);      // a2.b0 -> s2
+            tc_mma_i8<CL>(tmem_base + 1 * CLASS_COLS, A1, B0, ID96, 1u);      // a1.b0 -> s1
           }
-          // smem slot reusable once these MMAs have read it (tell every CTA that writes into it)
-          if (CL == 1) tc_commit(&ctl->empty[stage]); else tc_commit_mc(&ctl->empty[stage], (uint16_t)0x3);
-          if (kc + 1 == a.n_kchunks) tc_commit(&ctl->tmem_full);
+          // smem slot reusable once these MMAs have read it (in both CTAs of a pair)
+          if (CL == 1) tc_commit(&ctl->empty[stage]); else tc_commit_pair(&ctl->empty[stage]);
+          if (kc + 1 == a.n_kchunks) { if (CL == 1) tc_commit(&ctl->tmem_full); else tc_commit_pair(&ctl->tmem_full); }
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
           LB_TICK(2);  // issuing
         }
@@ -468,7 +521,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           v[c] += __hiloint2double((int)hi, (int)(r[c] ^ 0x80000000u)) - bias;
       }
       tc_fence_before();  // this warp's TMEM reads are complete
-      if (release_at == 0) { __syncwarp(); if (lane == 0) mbar_arrive(&ctl->tmem_empty); }
+      if (release_at == 0) { __syncwarp(); if (lane == 0) release_tmem<CL>(ctl, crank); }
       LB_TICK(1);  // drain
 
       // ---- fp64 phase: exchange rows inside each lane triple, build the four quartics ----
@@ -533,7 +586,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int r4 = 0; r4 < 4; ++r4)
         asm volatile("" : "+f"(polf[r4].c0h), "+f"(polf[r4].c0l), "+f"(polf[r4].c1h), "+f"(polf[r4].c1l),
                           "+f"(polf[r4].c2h), "+f"(polf[r4].c2l), "+f"(e0s[r4]), "+f"(polf[r4].t0));
-      if (release_at == 1) { __syncwarp(); if (lane == 0) mbar_arrive(&ctl->tmem_empty); }
+      if (release_at == 1) { __syncwarp(); if (lane == 0) release_tmem<CL>(ctl, crank); }
       LB_TICK(2);  // exchange + quartic coefficients (fp64)
 
       // ---- four fp32 Newton recurrences in lock-step, warp-uniform exit ----
@@ -549,7 +602,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         if (it >= 1 && __all_sync(0xffffffffu, conv)) break;
       }
-      if (release_at == 2) { __syncwarp(); if (lane == 0) mbar_arrive(&ctl->tmem_empty); }
+      if (release_at == 2) { __syncwarp(); if (lane == 0) release_tmem<CL>(ctl, crank); }
       LB_TICK(3);  // Newton (fp32)
 
       // ---- one float-float residual correction per pair, float32 result ----
@@ -578,7 +631,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         if (owner) ctl->T[buf][b_local][a_local] = val;
       }
-      if (release_at == 3) { __syncwarp(); if (lane == 0) mbar_arrive(&ctl->tmem_empty); }
+      if (release_at == 3) { __syncwarp(); if (lane == 0) release_tmem<CL>(ctl, crank); }
       LB_TICK(4);  // polish
       asm volatile("bar.sync 1, 384;" ::: "memory");  // tile T[buf] complete
       LB_TICK(5);  // barrier
@@ -634,7 +687,8 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (CL > 1) cluster_sync_all(); else __syncthreads();  // no CTA leaves while its partner may still signal it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    if (CL == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
@@ -647,8 +701,9 @@ bool tensor_path_available() { return true; }
 int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   constexpr uint32_t SB_R = 12, SB_C = 16;
   const char* cl_env = getenv("LOOSB200_CLUSTER");
-  // CTAs per cluster sharing the "a" tile.  Default 1: multicast saves 12 % of the L2 reads but
-  // not the bytes an SM has to ingest, and measures 2-5 % slower (profiles/r1_summary.md).
+  // 1 (default): independent CTAs.  2: CTA pairs (tcgen05 cta_group::2) sharing the "b" operand --
+  // 21 % fewer operand bytes out of L2, but the leader then waits for the slower of two epilogues
+  // before every tile; measured equal or 1-3 % slower at N = 1000 and N = 3000 (profiles/r1_summary.md).
   const uint32_t CLs = (cl_env && atoi(cl_env) == 2) ? 2u : 1u;
   const loosb200_frames* A = job.a;
   const loosb200_frames* B = job.b;
@@ -670,7 +725,7 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
     for (uint32_t c0 = 0; c0 < cmax; c0 += SB_C) {
       const uint32_t nc = std::min(cmax, c0 + SB_C) - c0;
       sbl.push_back(make_uint4(r0, r1 - r0, c0, nc));
-      slots += (uint64_t)(r1 - r0) * ((nc + CLs - 1) / CLs);
+      slots += (uint64_t)((r1 - r0 + CLs - 1) / CLs) * nc;  // pair: two rows per slot
       prefix.push_back((uint32_t)slots);
     }
   }
@@ -705,8 +760,8 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   ta.release_at = getenv("LOOSB200_RELEASE_AT") ? atoi(getenv("LOOSB200_RELEASE_AT")) : (A->Kpad <= 2048 ? 1 : 0);
   const bool want_prof = getenv("LOOSB200_PROF") != nullptr;
 
-  LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<1>()));
+  LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<2>()));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -717,16 +772,16 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   }
   if (job.ev_k0) cudaEventRecord(job.ev_k0, st);
   if (CLs == 1) {
-    k_pairs_tensor<1><<<grid, NTHREADS, SMEM_BYTES, st>>>(A->tmapA, A->tmapAh, B->tmapB, ta);
+    k_pairs_tensor<1><<<grid, NTHREADS, smem_bytes<1>(), st>>>(A->tmapA, B->tmapB, B->tmapB96, B->tmapB48, ta);
   } else {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem_bytes<2>(); cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    LB_CUDA(cudaLaunchKernelEx(&cfg, k_pairs_tensor<2>, A->tmapA, A->tmapAh, B->tmapB, ta));
+    LB_CUDA(cudaLaunchKernelEx(&cfg, k_pairs_tensor<2>, A->tmapA, B->tmapB, B->tmapB96, B->tmapB48, ta));
   }
   if (job.ev_k1) cudaEventRecord(job.ev_k1, st);
   LB_CUDA(cudaGetLastError());

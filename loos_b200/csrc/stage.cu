@@ -205,10 +205,10 @@ int ensure_quantised(loosb200_frames* h, int force_unit_log2) {
   cuuint64_t dims[3] = {(cuuint64_t)h->Kpad, (cuuint64_t)h->rows_total, (cuuint64_t)NUM_SLICES};
   cuuint64_t strides[2] = {(cuuint64_t)h->Kpad, (cuuint64_t)(h->rows_total * h->Kpad)};
   cuuint32_t estr[3] = {1, 1, 1};
-  for (int which = 0; which < 3; ++which) {
-    cuuint32_t box[3] = {(cuuint32_t)K_CHUNK, (cuuint32_t)(which == 0 ? TILE_ROWS : which == 1 ? COL_TILE_ROWS : TILE_ROWS / 2),
-                         (cuuint32_t)(which == 2 ? 1 : NUM_SLICES)};
-    CUtensorMap* dst = which == 0 ? &h->tmapA : which == 1 ? &h->tmapB : &h->tmapAh;
+  for (int which = 0; which < 4; ++which) {
+    const cuuint32_t rows[4] = {TILE_ROWS, COL_TILE_ROWS, COL_TILE_ROWS, COL_TILE_ROWS / 2};
+    cuuint32_t box[3] = {(cuuint32_t)K_CHUNK, rows[which], (cuuint32_t)(which < 2 ? NUM_SLICES : 1)};
+    CUtensorMap* dst = which == 0 ? &h->tmapA : which == 1 ? &h->tmapB : which == 2 ? &h->tmapB96 : &h->tmapB48;
     CUresult r = enc(dst, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->q8, dims, strides, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
