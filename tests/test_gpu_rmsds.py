@@ -224,3 +224,28 @@ def test_incremental_staging_equals_one_shot(lb):
     capi.check(L.loosb200_stage_append(h, X.ctypes.data_as(C.c_void_p), 4))
     assert L.loosb200_stage_end(h) == capi.ERR_INVALID
     L.loosb200_free(h)
+
+
+@pytest.mark.parametrize("F,N", [(83, 70), (407, 300), (1201, 129)])
+def test_cta_pair_launch_shape_is_bit_identical(lb, F, N, monkeypatch):
+    """k_pairs_tensor has two launch shapes: independent CTAs (default) and CTA pairs that share
+    the "b" operand through tcgen05 cta_group::2.  Exact integer accumulation and the same
+    per-pair solve: the matrices, packed parts and the cross matrix must agree bit for bit
+    (odd row-tile counts, masked partner tiles and the diagonal included)."""
+    from loos_b200.api import rmsds_part
+    from loos_b200.synth import synth_frames
+    X = synth_frames(F, N, seed=11 + F)
+    Y = synth_frames(F // 2 + 3, N, seed=5 + F)
+    got = {}
+    for shape in ("1", "2"):
+        monkeypatch.setenv("LOOSB200_CLUSTER", shape)
+        with lb.FrameSet(X) as fs, lb.FrameSet(Y) as fy:
+            M, st = lb.rmsds(fs, engine="tensor")
+            rows, blk, _ = rmsds_part(fs, 1, 3, engine="tensor")
+            C, _ = lb.rmsds_cross(fs, fy, engine="tensor")
+        got[shape] = (M, st["max"], blk, C)
+    assert np.array_equal(got["1"][0], got["2"][0])
+    assert got["1"][1] == got["2"][1]
+    assert np.array_equal(got["1"][2], got["2"][2])
+    assert np.array_equal(got["1"][3], got["2"][3])
+    assert (np.diag(got["2"][0]) == 0).all() and np.array_equal(got["2"][0], got["2"][0].T)
