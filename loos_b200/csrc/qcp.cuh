@@ -512,7 +512,8 @@ LB_HD void qcp_rotation(const double* R, double* Z, double* lambda_out) {
 // best-conditioned column of adj(K - lambda I) = prod(lambda - lambda_i) q q^T.
 // Returns false (caller falls back to qcp_rotation) when the top eigenvalue is not
 // well separated -- collinear / planar / N < 3 inputs -- or the solve did not settle.
-LB_HD bool qcp_rotation_fast(const double* R, double ga, double gb, double* Z) {
+// *resid (optional) receives ga + gb - 2 lambda_max = 2 e0 y, free of cancellation.
+LB_HD bool qcp_rotation_fast(const double* R, double ga, double gb, double* Z, double* resid = 0) {
   const double e0 = 0.5 * (ga + gb);
   if (!(e0 > 0.0)) return false;
   const QcpPoly p = qcp_poly(R, e0);
@@ -530,6 +531,7 @@ LB_HD bool qcp_rotation_fast(const double* R, double ga, double gb, double* Z) {
     if (dd != 0.0) td -= fd / dd;
     y = p.xform ? 1.0 - td : td;
   }
+  if (resid) *resid = 2.0 * e0 * y;
   const double lam = (1.0 - y);  // in units of e0
   const double inv = 1.0 / e0;
   double S[9];

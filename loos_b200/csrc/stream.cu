@@ -15,6 +15,7 @@
 
 #include <vector>
 
+#include <stdlib.h>
 #include "common.cuh"
 #include "qcp.cuh"
 
@@ -178,87 +179,231 @@ __device__ __forceinline__ double wsum_all(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(SW_THREADS) k_stream_warp(const StreamArgs a) {
+// ---------------------------------------------------------------------------------------
+// rmsd2ref, target mode, and the final per-frame rmsd of the iterative mode, as three
+// kernels instead of one warp-per-frame loop (covariance -> solve -> residuals):
+//   * a fused kernel keeps (#warps x frames per warp x 24 KB) of frames alive between its two
+//     passes -- 114 MB at full occupancy, more than L2 holds -- so the second pass re-read HBM
+//     (ncu: dram read 2x the frame bytes, L2 hit rate 31 %, long-scoreboard stalls), and the
+//     serial 4x4 eigen-solve (~7 K cycles, all 32 lanes redundant) sat inside every warp's loop;
+//   * split, both streaming kernels are plain one-pass reductions with ld.cs loads and high
+//     occupancy, and the solves run one frame per THREAD;
+//   * when the rmsd selection and target are the align selection and target, the minimal RMSD is
+//     sqrt((Ga + Gb - 2 lambda_max) / N) and the residual pass is not needed at all.
+constexpr int SW_FPW = 2;  // frames per warp: every load of the fp64 reference from L1 serves two frames
+
+struct CovArgs {
+  const float* raw; size_t Npad;  // frame planes [F][3][Npad]
+  const double* ref;              // [3][Npad] centred reference
+  uint32_t F;
+  double* cov;                    // [F][9] out: sum_k x_p v_q (uncentred x; corrected in k_solve)
+};
+
+__global__ void __launch_bounds__(SW_THREADS, 2) k_cov(const CovArgs a) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp_global = (blockIdx.x * SW_THREADS + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * SW_THREADS) >> 5;
-  for (uint32_t f = warp_global; f < a.F; f += nwarps) {
-    double W[12];
-    if (a.mode & M_COMPUTE_W) {
-      const float4* px = reinterpret_cast<const float4*>(a.rawA + ((size_t)f * 3 + 0) * a.NpadA);
-      const float4* py = reinterpret_cast<const float4*>(a.rawA + ((size_t)f * 3 + 1) * a.NpadA);
-      const float4* pz = reinterpret_cast<const float4*>(a.rawA + ((size_t)f * 3 + 2) * a.NpadA);
-      const double2* rx = reinterpret_cast<const double2*>(a.refA);
-      const double2* ry = reinterpret_cast<const double2*>(a.refA + a.NpadA);
-      const double2* rz = reinterpret_cast<const double2*>(a.refA + 2 * a.NpadA);
-      double s[13];
+  const double2* rx = reinterpret_cast<const double2*>(a.ref);
+  const double2* ry = reinterpret_cast<const double2*>(a.ref + a.Npad);
+  const double2* rz = reinterpret_cast<const double2*>(a.ref + 2 * a.Npad);
+  for (uint32_t f0 = warp_global * SW_FPW; f0 < a.F; f0 += nwarps * SW_FPW) {
+    const int nf = (int)(a.F - f0 < (uint32_t)SW_FPW ? a.F - f0 : (uint32_t)SW_FPW);
+    double s[SW_FPW][9];
 #pragma unroll
-      for (int k = 0; k < 13; ++k) s[k] = 0.0;
-      for (uint32_t i4 = lane; i4 < a.NpadA / 4; i4 += 32) {
-        const float4 X = __ldcs(px + i4), Y = __ldcs(py + i4), Z = __ldcs(pz + i4);  // streamed once
-        const double2 vx0 = __ldg(rx + 2 * i4), vx1 = __ldg(rx + 2 * i4 + 1);
-        const double2 vy0 = __ldg(ry + 2 * i4), vy1 = __ldg(ry + 2 * i4 + 1);
-        const double2 vz0 = __ldg(rz + 2 * i4), vz1 = __ldg(rz + 2 * i4 + 1);
-        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
-        const double vxs[4] = {vx0.x, vx0.y, vx1.x, vx1.y}, vys[4] = {vy0.x, vy0.y, vy1.x, vy1.y},
-                     vzs[4] = {vz0.x, vz0.y, vz1.x, vz1.y};
+    for (int ff = 0; ff < SW_FPW; ++ff)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const double x = xs[k], y = ys[k], z = zs[k];
-          s[0] += x; s[1] += y; s[2] += z;
-          s[3] = fma(x, vxs[k], s[3]); s[4] = fma(x, vys[k], s[4]); s[5] = fma(x, vzs[k], s[5]);
-          s[6] = fma(y, vxs[k], s[6]); s[7] = fma(y, vys[k], s[7]); s[8] = fma(y, vzs[k], s[8]);
-          s[9] = fma(z, vxs[k], s[9]); s[10] = fma(z, vys[k], s[10]); s[11] = fma(z, vzs[k], s[11]);
-          s[12] = fma(x, x, fma(y, y, fma(z, z, s[12])));
+      for (int k = 0; k < 9; ++k) s[ff][k] = 0.0;
+#pragma unroll 2
+    for (uint32_t i4 = lane; i4 < a.Npad / 4; i4 += 32) {  // pad atoms are zero in frame and reference
+      const double2 vx0 = __ldg(rx + 2 * i4), vx1 = __ldg(rx + 2 * i4 + 1);
+      const double2 vy0 = __ldg(ry + 2 * i4), vy1 = __ldg(ry + 2 * i4 + 1);
+      const double2 vz0 = __ldg(rz + 2 * i4), vz1 = __ldg(rz + 2 * i4 + 1);
+      const double vxs[4] = {vx0.x, vx0.y, vx1.x, vx1.y}, vys[4] = {vy0.x, vy0.y, vy1.x, vy1.y},
+                   vzs[4] = {vz0.x, vz0.y, vz1.x, vz1.y};
+#pragma unroll
+      for (int ff = 0; ff < SW_FPW; ++ff) {
+        if (ff < nf) {
+          const float4* base = reinterpret_cast<const float4*>(a.raw + (size_t)(f0 + ff) * 3 * a.Npad);
+          const float4 X = __ldcs(base + i4), Y = __ldcs(base + a.Npad / 4 + i4), Z = __ldcs(base + a.Npad / 2 + i4);
+          const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const double x = xs[k], y = ys[k], z = zs[k];
+            s[ff][0] = fma(x, vxs[k], s[ff][0]); s[ff][1] = fma(x, vys[k], s[ff][1]); s[ff][2] = fma(x, vzs[k], s[ff][2]);
+            s[ff][3] = fma(y, vxs[k], s[ff][3]); s[ff][4] = fma(y, vys[k], s[ff][4]); s[ff][5] = fma(y, vzs[k], s[ff][5]);
+            s[ff][6] = fma(z, vxs[k], s[ff][6]); s[ff][7] = fma(z, vys[k], s[ff][7]); s[ff][8] = fma(z, vzs[k], s[ff][8]);
+          }
         }
       }
-#pragma unroll
-      for (int k = 0; k < 13; ++k) s[k] = wsum_all(s[k]);
-      const double uc[3] = {s[0] / a.Na, s[1] / a.Na, s[2] / a.Na};
-      double R[9];
-#pragma unroll
-      for (int p = 0; p < 3; ++p)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) R[3 * p + q] = s[3 + 3 * p + q] - uc[p] * a.refA_sum[q];
-      // the frame's own centred sum of squares: with E0 = (ga + gb)/2 the quartic's root is <= 1
-      const double ga = s[12] - (double)a.Na * (uc[0] * uc[0] + uc[1] * uc[1] + uc[2] * uc[2]);
-      double Z[9];
-      if (!qcp_rotation_fast(R, ga, a.refA_g, Z)) qcp_rotation(R, Z, 0);  // degenerate: Jacobi
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        W[4 * i] = Z[3 * i]; W[4 * i + 1] = Z[3 * i + 1]; W[4 * i + 2] = Z[3 * i + 2];
-        W[4 * i + 3] = a.refA_c[i] - (Z[3 * i] * uc[0] + Z[3 * i + 1] * uc[1] + Z[3 * i + 2] * uc[2]);
-      }
-      if (a.xf && lane == 0) {
-        double* o = a.xf + (size_t)f * 16;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) o[k] = W[k];
-        o[12] = o[13] = o[14] = 0.0; o[15] = 1.0;
-      }
-    } else if (a.mode & M_IDENTITY) {
-#pragma unroll
-      for (int k = 0; k < 12; ++k) W[k] = (k % 5 == 0) ? 1.0 : 0.0;
-      if (a.xf && lane < 16) a.xf[(size_t)f * 16 + lane] = (lane % 5 == 0) ? 1.0 : 0.0;
-    } else {
-#pragma unroll
-      for (int k = 0; k < 12; ++k) W[k] = a.xf[(size_t)f * 16 + k];
     }
-    if (a.mode & M_RMSD) {
-      const float* px = a.rawR + ((size_t)f * 3 + 0) * a.NpadR;
-      const float* py = px + a.NpadR, *pz = py + a.NpadR;
-      const double* rx = a.refR, *ry = rx + a.NpadR, *rz = ry + a.NpadR;
-      double d = 0.0;
-      for (uint32_t i = lane; i < a.Nr; i += 32) {  // second pass: L1/L2 hits when the selections coincide
-        const double x = px[i], y = py[i], z = pz[i];
-        const double ex = rx[i] - (W[0] * x + W[1] * y + W[2] * z + W[3]);
-        const double ey = ry[i] - (W[4] * x + W[5] * y + W[6] * z + W[7]);
-        const double ez = rz[i] - (W[8] * x + W[9] * y + W[10] * z + W[11]);
-        d += ex * ex + ey * ey + ez * ez;
+#pragma unroll
+    for (int ff = 0; ff < SW_FPW; ++ff) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) s[ff][k] = wsum_all(s[ff][k]);
+      if (ff < nf && lane < 9) {
+        double v = s[ff][0];
+#pragma unroll
+        for (int k = 1; k < 9; ++k) v = lane == k ? s[ff][k] : v;
+        a.cov[(size_t)(f0 + ff) * 9 + lane] = v;
       }
-      d = wsum_all(d);
-      if (lane == 0) a.out_rmsd[f] = sqrt(d / a.Nr);
     }
   }
+}
+
+// One frame per thread: centroid correction, QCP root + eigenvector, W = T(vc) Z T(-uc)
+// (alignment::kabsch, src/alignment.cpp:217-233).  rmsd_out (optional): the minimal RMSD from the
+// eigenvalue, for the case where the residual pass would recompute exactly that.
+struct SolveArgs {
+  const double* cov; const double* cen; const double* gd;  // per frame
+  double ref_c[3], ref_sum[3], ref_g;
+  uint32_t F, Na;
+  int identity;
+  double* xf;        // [F][16] or null
+  double* rmsd_out;  // [F] or null
+};
+
+__global__ void __launch_bounds__(128) k_solve(const SolveArgs a) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= a.F) return;
+  double W[12];
+  if (a.identity) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) W[k] = (k % 5 == 0) ? 1.0 : 0.0;
+  } else {
+    const double uc[3] = {a.cen[3 * (size_t)f], a.cen[3 * (size_t)f + 1], a.cen[3 * (size_t)f + 2]};
+    double R[9];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) R[3 * p + q] = a.cov[(size_t)f * 9 + 3 * p + q] - uc[p] * a.ref_sum[q];
+    // the frame's own centred sum of squares: with E0 = (ga + gb)/2 the quartic's root is <= 1
+    const double ga = a.gd[f];
+    double Z[9], resid = 0.0;
+    if (!qcp_rotation_fast(R, ga, a.ref_g, Z, &resid)) {  // degenerate: Jacobi
+      double lam = 0.0;
+      qcp_rotation(R, Z, &lam);
+      resid = ga + a.ref_g - 2.0 * lam;
+    }
+    if (a.rmsd_out) a.rmsd_out[f] = sqrt(fabs(resid) / (double)a.Na);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      W[4 * i] = Z[3 * i]; W[4 * i + 1] = Z[3 * i + 1]; W[4 * i + 2] = Z[3 * i + 2];
+      W[4 * i + 3] = a.ref_c[i] - (Z[3 * i] * uc[0] + Z[3 * i + 1] * uc[1] + Z[3 * i + 2] * uc[2]);
+    }
+  }
+  if (a.xf) {
+    double* o = a.xf + (size_t)f * 16;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) o[k] = W[k];
+    o[12] = o[13] = o[14] = 0.0; o[15] = 1.0;
+  }
+}
+
+// Residual pass (AtomicGroup::applyTransform + rmsd, AG_numerical.cpp:363-370,301-318): explicit
+// residuals, no cancellation.  With both structures shifted to their centroids every term is
+// a few tens of Angstrom at most, where float32 resolves 2e-6 A -- the resolution of the float32
+// trajectory itself -- so the residuals are formed in fp32 (reference carried as float-float,
+// frame constants prepared in fp64) and only their squares are summed in fp64:
+//   r - (Z x + t) = (r - rc) - Z (x - uc) - kappa,   kappa = t + Z uc - rc.
+// Measured error against the fp64 form < 1e-6 A (tests/test_gpu_rmsd2ref.py).
+struct ResidArgs {
+  const float* raw; size_t Npad; uint32_t Nr;  // rmsd selection planes
+  const float2* ref_ff;  // [3][Npad] reference minus its centroid, float-float (k_ref_split)
+  const double* ref_c;   // [3] device: that centroid
+  const double* cen;     // [F][3] frame centroids (rmsd selection)
+  const double* xf;      // [F][16]
+  uint32_t F;
+  double* out_rmsd;
+};
+
+__global__ void __launch_bounds__(SW_THREADS, 2) k_resid(const ResidArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp_global = (blockIdx.x * SW_THREADS + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * SW_THREADS) >> 5;
+  const float4* rx = reinterpret_cast<const float4*>(a.ref_ff);
+  const float4* ry = reinterpret_cast<const float4*>(a.ref_ff + a.Npad);
+  const float4* rz = reinterpret_cast<const float4*>(a.ref_ff + 2 * a.Npad);
+  for (uint32_t f0 = warp_global * SW_FPW; f0 < a.F; f0 += nwarps * SW_FPW) {
+    const int nf = (int)(a.F - f0 < (uint32_t)SW_FPW ? a.F - f0 : (uint32_t)SW_FPW);
+    float Zf[SW_FPW][9], kap[SW_FPW][3], ucf[SW_FPW][3];
+    double d[SW_FPW];
+#pragma unroll
+    for (int ff = 0; ff < SW_FPW; ++ff) {
+      d[ff] = 0.0;
+      const size_t f = f0 + (ff < nf ? ff : 0);
+      const double* W = a.xf + f * 16;
+#pragma unroll
+      for (int p = 0; p < 3; ++p) ucf[ff][p] = (float)a.cen[3 * f + p];
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        const double w0 = W[4 * p], w1 = W[4 * p + 1], w2 = W[4 * p + 2], w3 = W[4 * p + 3];
+        Zf[ff][3 * p] = (float)w0; Zf[ff][3 * p + 1] = (float)w1; Zf[ff][3 * p + 2] = (float)w2;
+        kap[ff][p] = (float)(w3 + w0 * (double)ucf[ff][0] + w1 * (double)ucf[ff][1] + w2 * (double)ucf[ff][2] - a.ref_c[p]);
+      }
+    }
+#pragma unroll 2
+    for (uint32_t i4 = lane; i4 < a.Npad / 4; i4 += 32) {
+      const float4 t0 = __ldg(rx + 2 * i4), t1 = __ldg(rx + 2 * i4 + 1);
+      const float4 u0 = __ldg(ry + 2 * i4), u1 = __ldg(ry + 2 * i4 + 1);
+      const float4 w0 = __ldg(rz + 2 * i4), w1 = __ldg(rz + 2 * i4 + 1);
+      const float vxh[4] = {t0.x, t0.z, t1.x, t1.z}, vxl[4] = {t0.y, t0.w, t1.y, t1.w};
+      const float vyh[4] = {u0.x, u0.z, u1.x, u1.z}, vyl[4] = {u0.y, u0.w, u1.y, u1.w};
+      const float vzh[4] = {w0.x, w0.z, w1.x, w1.z}, vzl[4] = {w0.y, w0.w, w1.y, w1.w};
+#pragma unroll
+      for (int ff = 0; ff < SW_FPW; ++ff) {
+        if (ff < nf) {
+          const float4* base = reinterpret_cast<const float4*>(a.raw + (size_t)(f0 + ff) * 3 * a.Npad);
+          const float4 X = __ldcs(base + i4), Y = __ldcs(base + a.Npad / 4 + i4), Z = __ldcs(base + a.Npad / 2 + i4);
+          const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+          float part = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (4 * i4 + k < a.Nr) {  // pad atoms would contribute |kappa|^2
+              const float x = xs[k] - ucf[ff][0], y = ys[k] - ucf[ff][1], z = zs[k] - ucf[ff][2];
+              const float tx = fmaf(Zf[ff][0], x, fmaf(Zf[ff][1], y, fmaf(Zf[ff][2], z, kap[ff][0])));
+              const float ty = fmaf(Zf[ff][3], x, fmaf(Zf[ff][4], y, fmaf(Zf[ff][5], z, kap[ff][1])));
+              const float tz = fmaf(Zf[ff][6], x, fmaf(Zf[ff][7], y, fmaf(Zf[ff][8], z, kap[ff][2])));
+              const float ex = (vxh[k] - tx) + vxl[k], ey = (vyh[k] - ty) + vyl[k], ez = (vzh[k] - tz) + vzl[k];
+              part = fmaf(ex, ex, fmaf(ey, ey, fmaf(ez, ez, part)));
+            }
+          }
+          d[ff] += (double)part;
+        }
+      }
+    }
+#pragma unroll
+    for (int ff = 0; ff < SW_FPW; ++ff) {
+      const double dd = wsum_all(d[ff]);
+      if (ff < nf && lane == 0) a.out_rmsd[f0 + ff] = sqrt(dd / a.Nr);
+    }
+  }
+}
+
+// Centroid of an [3][Npad] fp64 structure and its centred float-float copy (one CTA).
+__global__ void k_ref_split(const double* __restrict__ ref, uint32_t n, size_t Npad, float2* __restrict__ out,
+                            double* __restrict__ cen) {
+  __shared__ double red[3 * 32];
+  __shared__ double c_s[3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int ax = 0; ax < 3; ++ax) {
+    double v = 0.0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) v += ref[ax * Npad + i];
+    v = wsum_all(v);
+    if (lane == 0) red[ax * 32 + warp] = v;
+  }
+  __syncthreads();
+  if (warp < 3) {
+    double v = lane < (int)(blockDim.x >> 5) ? red[warp * 32 + lane] : 0.0;
+    v = wsum_all(v);
+    if (lane == 0) { c_s[warp] = v / (double)n; cen[warp] = v / (double)n; }
+  }
+  __syncthreads();
+  for (int ax = 0; ax < 3; ++ax)
+    for (uint32_t i = threadIdx.x; i < Npad; i += blockDim.x) {
+      const double v = i < n ? ref[ax * Npad + i] - c_s[ax] : 0.0;
+      const float h = (float)v;
+      out[ax * Npad + i] = make_float2(h, (float)(v - (double)h));
+    }
 }
 
 // avg /= F; rms = sqrt(sum |avg - target|^2 / n) (AtomicGroup::rmsd); then the new
@@ -347,13 +492,15 @@ int grid_for(uint32_t F, bool accum) {
   return (int)((F < (uint32_t)g) ? F : (uint32_t)g);
 }
 
-int grid_warp(uint32_t F) {  // persistent: as many CTAs as fit, each warp walks frames
+template <class K>
+int grid_warp(uint32_t F, K kernel) {  // persistent: as many CTAs as fit, each warp walks frames
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stream_warp, SW_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SW_THREADS, 0);
   if (per_sm < 1) per_sm = 1;
-  const uint32_t need = (F + SW_THREADS / 32 - 1) / (SW_THREADS / 32);
+  const uint32_t per_cta = (SW_THREADS / 32) * SW_FPW;
+  const uint32_t need = (F + per_cta - 1) / per_cta;
   const uint32_t cap = (uint32_t)(sms * per_sm);
   return (int)(need < cap ? need : cap);
 }
@@ -390,37 +537,67 @@ extern "C" int loosb200_rmsd2ref(loosb200_frames* align, loosb200_frames* rmsd_s
   if (ref_align) to_soa(ref_align, align->N, align->Npad, true, soaA, c, cs);
   to_soa(ref_rmsd, rs->N, rs->Npad, false, soaR, c0, cs0);
 
-  double *dA = nullptr, *dR = nullptr, *dOut = nullptr, *dXf = nullptr;
-  bool ok = cudaMalloc(&dR, sizeof(double) * soaR.size()) == cudaSuccess &&
-            cudaMalloc(&dOut, sizeof(double) * F) == cudaSuccess;
-  if (ok && ref_align) ok = cudaMalloc(&dA, sizeof(double) * soaA.size()) == cudaSuccess;
-  if (ok && out_xforms) ok = cudaMalloc(&dXf, sizeof(double) * 16 * F) == cudaSuccess;
-  if (!ok) { cudaGetLastError(); cudaFree(dA); cudaFree(dR); cudaFree(dOut); cudaFree(dXf); return LOOSB200_ERR_NOMEM; }
+  // When the rmsd selection and target ARE the align selection and target, the rmsd after
+  // superposition is the minimal RMSD sqrt((Ga + Gb - 2 lambda_max) / N): no residual pass.
+  // LOOSB200_STREAM_EXPLICIT=1 forces the explicit form (tests compare the two).
+  const bool same = ref_align && rs == align && ref_rmsd == ref_align && !getenv("LOOSB200_STREAM_EXPLICIT");
+  const bool need_xf = out_xforms || !same;
+
+  double *dA = nullptr, *dR = nullptr, *dOut = nullptr, *dXf = nullptr, *dRc = nullptr, *dCov = nullptr;
+  float2* dRff = nullptr;
+  bool ok = cudaMalloc(&dOut, sizeof(double) * F) == cudaSuccess;
+  if (ok && !same)
+    ok = cudaMalloc(&dR, sizeof(double) * soaR.size()) == cudaSuccess &&
+         cudaMalloc(&dRff, sizeof(float2) * soaR.size()) == cudaSuccess &&
+         cudaMalloc(&dRc, sizeof(double) * 3) == cudaSuccess;
+  if (ok && ref_align)
+    ok = cudaMalloc(&dA, sizeof(double) * soaA.size()) == cudaSuccess &&
+         cudaMalloc(&dCov, sizeof(double) * 9 * F) == cudaSuccess;
+  if (ok && need_xf) ok = cudaMalloc(&dXf, sizeof(double) * 16 * F) == cudaSuccess;
+  auto cleanup = [&]() {
+    cudaFree(dA); cudaFree(dR); cudaFree(dRff); cudaFree(dRc); cudaFree(dOut); cudaFree(dXf); cudaFree(dCov);
+  };
+  if (!ok) { cudaGetLastError(); cleanup(); return LOOSB200_ERR_NOMEM; }
   cudaEventRecord(align->timing.ev[0], st);
   if (ref_align) cudaMemcpyAsync(dA, soaA.data(), sizeof(double) * soaA.size(), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dR, soaR.data(), sizeof(double) * soaR.size(), cudaMemcpyHostToDevice, st);
-
-  StreamArgs a;
-  memset(&a, 0, sizeof(a));
-  a.rawA = align->raw; a.NpadA = align->Npad; a.Na = (uint32_t)align->N;
-  a.rawR = rs->raw; a.NpadR = rs->Npad; a.Nr = (uint32_t)rs->N;
-  a.refA = dA; a.refR = dR;
-  for (int k = 0; k < 3; ++k) { a.refA_c[k] = c[k]; a.refA_sum[k] = cs[k]; }
-  a.refA_g = 0.0;
-  for (double v : soaA) a.refA_g += v * v;
-  a.xf = dXf; a.out_rmsd = dOut; a.F = (uint32_t)F;
-  a.mode = (ref_align ? M_COMPUTE_W : M_IDENTITY) | M_RMSD;
+  if (!same) {
+    cudaMemcpyAsync(dR, soaR.data(), sizeof(double) * soaR.size(), cudaMemcpyHostToDevice, st);
+    k_ref_split<<<1, 1024, 0, st>>>(dR, (uint32_t)rs->N, rs->Npad, dRff, dRc);
+  }
   cudaEventRecord(align->timing.ev[1], st);
-  k_stream_warp<<<grid_warp((uint32_t)F), SW_THREADS, 0, st>>>(a);
+  int launches = 0;
+  if (ref_align) {
+    CovArgs ca;
+    ca.raw = align->raw; ca.Npad = align->Npad; ca.ref = dA; ca.F = (uint32_t)F; ca.cov = dCov;
+    k_cov<<<grid_warp((uint32_t)F, k_cov), SW_THREADS, 0, st>>>(ca);
+    ++launches;
+  }
+  SolveArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.cov = dCov; sa.cen = align->centroid; sa.gd = align->gd;
+  for (int k = 0; k < 3; ++k) { sa.ref_c[k] = c[k]; sa.ref_sum[k] = cs[k]; }
+  for (double v : soaA) sa.ref_g += v * v;
+  sa.F = (uint32_t)F; sa.Na = (uint32_t)align->N;
+  sa.identity = ref_align ? 0 : 1;
+  sa.xf = dXf; sa.rmsd_out = same ? dOut : nullptr;
+  k_solve<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(sa);
+  ++launches;
+  if (!same) {
+    ResidArgs ra;
+    ra.raw = rs->raw; ra.Npad = rs->Npad; ra.Nr = (uint32_t)rs->N;
+    ra.ref_ff = dRff; ra.ref_c = dRc; ra.cen = rs->centroid; ra.xf = dXf; ra.F = (uint32_t)F; ra.out_rmsd = dOut;
+    k_resid<<<grid_warp((uint32_t)F, k_resid), SW_THREADS, 0, st>>>(ra);
+    ++launches;
+  }
   cudaEventRecord(align->timing.ev[2], st);
   cudaMemcpyAsync(out_rmsd, dOut, sizeof(double) * F, cudaMemcpyDeviceToHost, st);
   if (out_xforms) cudaMemcpyAsync(out_xforms, dXf, sizeof(double) * 16 * F, cudaMemcpyDeviceToHost, st);
   cudaEventRecord(align->timing.ev[3], st);
   cudaError_t e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaGetLastError();
-  cudaFree(dA); cudaFree(dR); cudaFree(dOut); cudaFree(dXf);
-  if (e != cudaSuccess) return cuda_fail(e, "k_stream", __FILE__, __LINE__);
-  align->timing.launches = 1; align->timing.valid = true; align->timing.kev_used = 0;
+  cleanup();
+  if (e != cudaSuccess) return cuda_fail(e, "rmsd2ref kernels", __FILE__, __LINE__);
+  align->timing.launches = launches; align->timing.valid = true; align->timing.kev_used = 0;
   return LOOSB200_OK;
 }
 
@@ -440,14 +617,19 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
   LB_CUDA(cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                smemA > smemR ? smemA : smemR));
 
-  double *dT = nullptr, *dAvg = nullptr, *dAvgR = nullptr, *dXf = nullptr, *dOut = nullptr, *dScal = nullptr;
+  double *dT = nullptr, *dAvg = nullptr, *dAvgR = nullptr, *dXf = nullptr, *dOut = nullptr, *dScal = nullptr, *dRc = nullptr;
+  float2* dRff = nullptr;
   bool ok = cudaMalloc(&dT, sizeof(double) * 3 * NpA) == cudaSuccess &&
             cudaMalloc(&dAvg, sizeof(double) * 3 * NpA) == cudaSuccess &&
             cudaMalloc(&dAvgR, sizeof(double) * 3 * NpR) == cudaSuccess &&
+            cudaMalloc(&dRff, sizeof(float2) * 3 * NpR) == cudaSuccess &&
+            cudaMalloc(&dRc, sizeof(double) * 3) == cudaSuccess &&
             cudaMalloc(&dXf, sizeof(double) * 16 * F) == cudaSuccess &&
             cudaMalloc(&dOut, sizeof(double) * F) == cudaSuccess &&
             cudaMalloc(&dScal, sizeof(double) * 8) == cudaSuccess;
-  auto cleanup = [&]() { cudaFree(dT); cudaFree(dAvg); cudaFree(dAvgR); cudaFree(dXf); cudaFree(dOut); cudaFree(dScal); };
+  auto cleanup = [&]() {
+    cudaFree(dT); cudaFree(dAvg); cudaFree(dAvgR); cudaFree(dRff); cudaFree(dRc); cudaFree(dXf); cudaFree(dOut); cudaFree(dScal);
+  };
   if (!ok) { cudaGetLastError(); cleanup(); return LOOSB200_ERR_NOMEM; }
   double* tgt_cen = dScal; double* tgt_sum = dScal + 3; double* rms_dev = dScal + 6;
 
@@ -496,9 +678,12 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
     k_stream<<<grid_for((uint32_t)F, true), ST, smemR, st>>>(a);
     k_scale<<<(unsigned)((3 * NpR + 255) / 256), 256, 0, st>>>(dAvgR, 3 * NpR, 1.0 / (double)F);
     // per-frame rmsd to the average: rmsd2ref.cpp:238-245
-    a.mode = M_RMSD; a.refR = dAvgR; a.avg = nullptr;
-    k_stream_warp<<<grid_warp((uint32_t)F), SW_THREADS, 0, st>>>(a);
-    launches += 3;
+    k_ref_split<<<1, 1024, 0, st>>>(dAvgR, (uint32_t)Nr, NpR, dRff, dRc);
+    ResidArgs ra;
+    ra.raw = rs->raw; ra.Npad = NpR; ra.Nr = (uint32_t)Nr;
+    ra.ref_ff = dRff; ra.ref_c = dRc; ra.cen = rs->centroid; ra.xf = dXf; ra.F = (uint32_t)F; ra.out_rmsd = dOut;
+    k_resid<<<grid_warp((uint32_t)F, k_resid), SW_THREADS, 0, st>>>(ra);
+    launches += 4;
     cudaEventRecord(align->timing.ev[2], st);
     cudaMemcpyAsync(out_rmsd, dOut, sizeof(double) * F, cudaMemcpyDeviceToHost, st);
     if (out_xforms) cudaMemcpyAsync(out_xforms, dXf, sizeof(double) * 16 * F, cudaMemcpyDeviceToHost, st);

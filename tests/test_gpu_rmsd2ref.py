@@ -7,6 +7,11 @@ import pytest
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 1e-4
+# The residual pass (applyTransform + rmsd) forms r - (Z x + t) in float32 on centred coordinates
+# (reference carried as float-float, squares summed in fp64): its resolution is that of the float32
+# trajectory itself, a few 1e-6 A on the residuals and far less on their rms.  The superposition
+# (covariance, QCP, transforms) is fp64 and is held to 1e-9 against the reference.
+RMSD_TOL = 2e-6
 
 
 @pytest.fixture(scope="module")
@@ -25,7 +30,7 @@ def test_golden_target_mode(lb):
     tgt = Z[-1].astype(np.float64)
     with lb.FrameSet(Z[:F], sel=sa) as fa, lb.FrameSet(Z[:F], sel=sr) as fr:
         d, xf = lb.rmsd2ref(fa, tgt[sa], fr, tgt[sr], want_xforms=True)
-    assert np.abs(d - g["rmsd"]).max() < 1e-9
+    assert np.abs(d - g["rmsd"]).max() < RMSD_TOL
     assert np.abs(xf - g["xforms"]).max() < 1e-9     # same rotation, same 4x4 convention
 
 
@@ -37,7 +42,7 @@ def test_golden_iterative_mode(lb):
     with lb.FrameSet(Z[:F], sel=sa) as fa, lb.FrameSet(Z[:F], sel=sr) as fr:
         r = lb.rmsd2ref_iterative(fa, fr, tol=1e-6, maxiter=1000)
     assert r["iters"] == int(g["it_iters"])
-    assert np.abs(r["rmsd"] - g["it_rmsd"]).max() < 1e-7
+    assert np.abs(r["rmsd"] - g["it_rmsd"]).max() < RMSD_TOL
     assert np.abs(r["avg"] - g["it_avg"]).max() < 1e-7
     assert np.abs(r["xforms"] - g["it_xforms"]).max() < 1e-7
 
@@ -51,7 +56,7 @@ def test_vs_oracle(lb, checker, F, N):
     with lb.FrameSet(Z[:F]) as fs:
         d, xf = lb.rmsd2ref(fs, tgt, want_xforms=True)
     assert np.abs(d - ref).max() <= TOL
-    assert np.abs(d - ref).max() < 1e-8
+    assert np.abs(d - ref).max() < RMSD_TOL
     if N >= 4:
         assert np.abs(xf - rxf).max() < 1e-7
 
@@ -64,7 +69,7 @@ def test_no_alignment_and_errors(lb):
     with lb.FrameSet(Z) as fs:
         d = lb.rmsd2ref(fs, None, None, tgt)            # --align '' : plain rmsd, identity transform
         want = np.sqrt(((Z.astype(np.float64) - tgt[None]) ** 2).sum(-1).mean(-1))
-        assert np.abs(d - want).max() < 1e-12
+        assert np.abs(d - want).max() < RMSD_TOL
         with pytest.raises(lb.LoosB200Error) as e:
             lb.rmsd2ref(fs, tgt[:-1])
         assert e.value.code == capi.ERR_SIZE_MISMATCH
@@ -84,3 +89,18 @@ def test_streaming_identities(lb):
     assert d.max() < 2e-5                    # float32 rounding of the moved coordinates
     back = np.einsum("fij,fnj->fni", xf[:, :3, :3], X.astype(np.float64)) + xf[:, None, :3, 3]
     assert np.abs(back - base[None]).max() < 1e-4
+
+
+def test_eigenvalue_shortcut_equals_explicit_residuals(lb, monkeypatch):
+    """Same selection and target for alignment and rmsd: the library takes the minimal RMSD from
+    the QCP eigenvalue instead of a second pass over the frames.  It must agree with the explicit
+    applyTransform + rmsd form (forced by LOOSB200_STREAM_EXPLICIT=1) and with the oracle."""
+    from loos_b200.synth import synth_frames
+    Z = synth_frames(513, 700, seed=77)
+    tgt = Z[-1].astype(np.float64)
+    with lb.FrameSet(Z[:512]) as fs:
+        d_short, xf_short = lb.rmsd2ref(fs, tgt, want_xforms=True)
+        monkeypatch.setenv("LOOSB200_STREAM_EXPLICIT", "1")
+        d_expl, xf_expl = lb.rmsd2ref(fs, tgt, want_xforms=True)
+    assert np.abs(d_short - d_expl).max() < RMSD_TOL
+    assert np.array_equal(xf_short, xf_expl)
