@@ -409,7 +409,7 @@ __global__ void k_ref_split(const double* __restrict__ ref, uint32_t n, size_t N
 // avg /= F; rms = sqrt(sum |avg - target|^2 / n) (AtomicGroup::rmsd); then the new
 // target := avg, stored centred with its centroid (kabsch centres it anyway).
 // target_c holds the uncentred target as [3][Npad] = tgt_centred + centroid.
-__global__ void k_finish_iter(double* avg, double* tgt_centred, double* tgt_cen, double* tgt_sum,
+__global__ void k_finish_iter(double* avg, double* tgt_centred, double* tgt_cen, double* tgt_sum, double* tgt_g,
                               uint32_t n, size_t Npad, double invF, double* rms_out) {
   __shared__ double red[4 * 32];
   double s[4] = {0, 0, 0, 0};
@@ -436,14 +436,15 @@ __global__ void k_finish_iter(double* avg, double* tgt_centred, double* tgt_cen,
   }
   __syncthreads();
   const double c[3] = {s[0] / n, s[1] / n, s[2] / n};
-  double cs[3] = {0, 0, 0};
+  double cs[4] = {0, 0, 0, 0};
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
     for (int ax = 0; ax < 3; ++ax) {
       const double v = avg[ax * Npad + i] - c[ax];
       tgt_centred[ax * Npad + i] = v;
       cs[ax] += v;
+      cs[3] = fma(v, v, cs[3]);
     }
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < 4; ++k) {
     double v = cs[k];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) red[k * 32 + warp] = v;
@@ -455,6 +456,11 @@ __global__ void k_finish_iter(double* avg, double* tgt_centred, double* tgt_cen,
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[k * 32 + w];
       tgt_sum[k] = v;
       tgt_cen[k] = c[k];
+    }
+    {
+      double v = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[3 * 32 + w];
+      tgt_g[0] = v;
     }
     rms_out[0] = sqrt(s[3] / n);
   }
@@ -617,7 +623,7 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
   LB_CUDA(cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                smemA > smemR ? smemA : smemR));
 
-  double *dT = nullptr, *dAvg = nullptr, *dAvgR = nullptr, *dXf = nullptr, *dOut = nullptr, *dScal = nullptr, *dRc = nullptr;
+  double *dT = nullptr, *dAvg = nullptr, *dAvgR = nullptr, *dXf = nullptr, *dOut = nullptr, *dScal = nullptr, *dRc = nullptr, *dCov = nullptr;
   float2* dRff = nullptr;
   bool ok = cudaMalloc(&dT, sizeof(double) * 3 * NpA) == cudaSuccess &&
             cudaMalloc(&dAvg, sizeof(double) * 3 * NpA) == cudaSuccess &&
@@ -626,9 +632,10 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
             cudaMalloc(&dRc, sizeof(double) * 3) == cudaSuccess &&
             cudaMalloc(&dXf, sizeof(double) * 16 * F) == cudaSuccess &&
             cudaMalloc(&dOut, sizeof(double) * F) == cudaSuccess &&
+            cudaMalloc(&dCov, sizeof(double) * 9 * F) == cudaSuccess &&
             cudaMalloc(&dScal, sizeof(double) * 8) == cudaSuccess;
   auto cleanup = [&]() {
-    cudaFree(dT); cudaFree(dAvg); cudaFree(dAvgR); cudaFree(dRff); cudaFree(dRc); cudaFree(dXf); cudaFree(dOut); cudaFree(dScal);
+    cudaFree(dT); cudaFree(dAvg); cudaFree(dAvgR); cudaFree(dRff); cudaFree(dRc); cudaFree(dXf); cudaFree(dOut); cudaFree(dScal); cudaFree(dCov);
   };
   if (!ok) { cudaGetLastError(); cleanup(); return LOOSB200_ERR_NOMEM; }
   double* tgt_cen = dScal; double* tgt_sum = dScal + 3; double* rms_dev = dScal + 6;
@@ -644,7 +651,9 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
     for (size_t i = 0; i < Na; ++i) { t0[ax * NpA + i] = (double)f0[ax * NpA + i] - c[ax]; cs[ax] += t0[ax * NpA + i]; }
   }
   // the centred first frame IS the target (centroid 0)
-  double scal[8] = {0, 0, 0, cs[0], cs[1], cs[2], 0, 0};
+  double g0 = 0.0;
+  for (double v : t0) g0 += v * v;
+  double scal[8] = {0, 0, 0, cs[0], cs[1], cs[2], 0, g0};
   cudaEventRecord(align->timing.ev[0], st);
   cudaMemcpyAsync(dT, t0.data(), sizeof(double) * 3 * NpA, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(dScal, scal, sizeof(scal), cudaMemcpyHostToDevice, st);
@@ -659,14 +668,25 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
   double rms = 0.0;
   cudaError_t e = cudaSuccess;
   do {
+    // one iteration = covariance of every frame with the current target (k_cov), one solve per
+    // thread (k_solve -> transforms), transformed frames summed into the new average (k_stream)
     cudaMemsetAsync(dAvg, 0, sizeof(double) * 3 * NpA, st);
     cudaMemcpyAsync(scal, dScal, sizeof(scal), cudaMemcpyDeviceToHost, st);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
-    for (int k = 0; k < 3; ++k) { a.refA_c[k] = scal[k]; a.refA_sum[k] = scal[3 + k]; }
-    a.mode = M_COMPUTE_W | M_ACCUM; a.accum_align_set = 1; a.avg = dAvg;
+    CovArgs ca;
+    ca.raw = align->raw; ca.Npad = NpA; ca.ref = dT; ca.F = (uint32_t)F; ca.cov = dCov;
+    k_cov<<<grid_warp((uint32_t)F, k_cov), SW_THREADS, 0, st>>>(ca);
+    SolveArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.cov = dCov; sa.cen = align->centroid; sa.gd = align->gd;
+    for (int k = 0; k < 3; ++k) { sa.ref_c[k] = scal[k]; sa.ref_sum[k] = scal[3 + k]; }
+    sa.ref_g = scal[7];
+    sa.F = (uint32_t)F; sa.Na = (uint32_t)Na; sa.xf = dXf;
+    k_solve<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(sa);
+    a.mode = M_ACCUM; a.accum_align_set = 1; a.avg = dAvg;
     k_stream<<<grid_for((uint32_t)F, true), ST, smemA, st>>>(a);
-    k_finish_iter<<<1, 1024, 0, st>>>(dAvg, dT, tgt_cen, tgt_sum, (uint32_t)Na, NpA, 1.0 / (double)F, rms_dev);
-    launches += 2;
+    k_finish_iter<<<1, 1024, 0, st>>>(dAvg, dT, tgt_cen, tgt_sum, dScal + 7, (uint32_t)Na, NpA, 1.0 / (double)F, rms_dev);
+    launches += 4;
     cudaMemcpyAsync(&rms, rms_dev, sizeof(double), cudaMemcpyDeviceToHost, st);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
     ++iter;
