@@ -79,7 +79,7 @@ struct loosb200_frames {
 
   // tensor-core operands (lazy): q8[(slice*rows_total + row)*Kpad + atom]
   int8_t* q8 = nullptr;
-  long long* gq = nullptr;  // [F] sum q^2, exact
+  double* gq = nullptr;     // [F] sum q^2 of the quantised frame (exact integer, rounded once to double)
   int* unit_log2_dev = nullptr;
   int unit_log2 = 0;
   bool quantised = false;

@@ -205,6 +205,22 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+// wait for the outstanding TMEM loads; the registers are listed so that no use of them is
+// scheduled above the wait
+__device__ __forceinline__ void tc_wait_ld16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor,
 // cutlass mma_sm100_desc.hpp:98-121): start>>4 | LBO=1<<16 | SBO=(8 rows*128 B)>>4<<32
@@ -235,7 +251,7 @@ struct TensorArgs {
   uint32_t n_slots;            // total slots; slots above the diagonal are skipped by the leader
   uint32_t* counter;           // next slot to hand out (zeroed per launch)
   const uint32_t* row_tiles;   // row tile index -> I
-  const long long* gA; const long long* gB;
+  const double* gA; const double* gB;  // exact sum of squares of every quantised frame, as double
   uint32_t FA, FB, N, n_kchunks;
   int self, symmetric, packed;
   double unit;                 // Angstrom per fixed-point unit
@@ -491,12 +507,12 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (; walk.template next<true>(a, ctl, rt, I, J, masked); buf ^= 1) {
       const uint32_t i = I * TILE_FRAMES + a_local;
       const bool i_ok = active && i < a.FA && !masked;  // a shadow tile contributes nothing
-      const double ga = i_ok ? (double)a.gA[i] : 0.0;
-      long long gbq[4];  // G of the four "b" frames this lane solves against (prefetched)
+      const double ga = i_ok ? __ldg(a.gA + i) : 0.0;
+      double gbq[4];  // G of the four "b" frames this lane solves against (prefetched)
 #pragma unroll
       for (int round = 0; round < 4; ++round) {
         const uint32_t j = J * COL_TILE_FRAMES + g * FRAMES_PER_BLOCK + (round < 3 ? 3 * round + al : 9);
-        gbq[round] = j < a.FB ? __ldg(a.gB + j) : 0;
+        gbq[round] = j < a.FB ? __ldg(a.gB + j) : 0.0;
       }
       mbar_wait<32>(&ctl->tmem_full, tphase);
       tphase ^= 1;
@@ -507,18 +523,23 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       double v[30];
 #pragma unroll
       for (int c = 0; c < 30; ++c) v[c] = 0.0;
+      // ten 16-column loads, software-pipelined: load t+1 is in flight while load t is combined
+      uint32_t rb[2][16];
+      tc_ld16(tlane, rb[0]);
 #pragma unroll
-      for (int s = 0; s < NUM_CLASSES; ++s) {
-        uint32_t r[32];
-        tc_ld32(tlane + (uint32_t)(s * CLASS_COLS), r);
-        tc_wait_ld();
+      for (int t = 0; t < 2 * NUM_CLASSES; ++t) {
+        const int s = t >> 1, h = t & 1;
+        tc_wait_ld16(rb[t & 1]);
+        if (t + 1 < 2 * NUM_CLASSES)
+          tc_ld16(tlane + (uint32_t)(((t + 1) >> 1) * CLASS_COLS + ((t + 1) & 1) * 16), rb[(t + 1) & 1]);
         // int32 -> double without the conversion unit: the bits (0x433+8s)<<52 | (D ^ 2^31)
         // are the double 2^(52+8s) + (D + 2^31) 2^(8s); subtracting the bias leaves D 2^(8s).
         const uint32_t hi = (uint32_t)(0x433 + 8 * s) << 20;
         const double bias = __hiloint2double((int)hi, (int)0x80000000u);
 #pragma unroll
-        for (int c = 0; c < 30; ++c)
-          v[c] += __hiloint2double((int)hi, (int)(r[c] ^ 0x80000000u)) - bias;
+        for (int c = 0; c < 16; ++c)
+          if (16 * h + c < 30)
+            v[16 * h + c] += __hiloint2double((int)hi, (int)(rb[t & 1][c] ^ 0x80000000u)) - bias;
       }
       tc_fence_before();  // this warp's TMEM reads are complete
       if (release_at == 0) { __syncwarp(); if (lane == 0) release_tmem<CL>(ctl, crank); }
@@ -561,22 +582,16 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int jb = round < 3 ? 3 * round + al : 9;
         const uint32_t j = J * COL_TILE_FRAMES + g * FRAMES_PER_BLOCK + jb;
         const bool owner = active && (round < 3 || al == 0);
-        int stt = 0;
-        double e0 = 1.0;
-        if (owner && i_ok && j < a.FB) {
-          if (a.self && j >= i) {
-            stt = (j == i) ? 1 : 0;  // diagonal stays 0 (Tools/rmsds.cpp:359-365)
-          } else {
-            e0 = 0.5 * (ga + (double)gbq[round]);
-            stt = e0 > 0.0 ? 2 : 1;  // every atom at the centroid in both frames: rmsd 0
-          }
-        }
-        if (stt != 2) {  // benign quartic for idle slots: keeps the lock-step loop short
-          e0 = 1.0;
-#pragma unroll
-          for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? (1.0 / 3.0) : 0.0;
-        }
-        state[round] = stt;
+        // 0: no entry (idle lane, out of range, or j > i of the self matrix), 1: exact zero (the
+        // diagonal, Tools/rmsds.cpp:359-365, or every atom at the centroid in both frames), 2: solve.
+        // Idle lanes run the same arithmetic on whatever their registers hold; their results are
+        // never stored and they are excluded from the convergence vote below.
+        const bool in_range = owner && i_ok && j < a.FB;
+        const bool upper = a.self && j >= i;
+        double e0 = 0.5 * (ga + gbq[round]);
+        const bool pos = e0 > 0.0;
+        e0 = pos ? e0 : 1.0;
+        state[round] = !in_range ? 0 : (upper ? (j == i ? 1 : 0) : (pos ? 2 : 1));
         e0s[round] = (float)(2.0 * e0 * inv_n);  // msd = y * this
         polf[round] = qcp_poly_split(qcp_poly(R, e0));
       }
@@ -598,7 +613,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
         for (int r4 = 0; r4 < 4; ++r4) {
           ls[r4] = qcp_newton_step(polf[r4].c0h, polf[r4].c1h, polf[r4].c2h, polf[r4].c3, tt[r4]);
-          conv = conv && (fabsf(ls[r4]) <= 4e-7f * fabsf(tt[r4]) + 1e-12f);
+          conv = conv && (state[r4] != 2 || fabsf(ls[r4]) <= 4e-7f * fabsf(tt[r4]) + 1e-12f);
         }
         if (it >= 1 && __all_sync(0xffffffffu, conv)) break;
       }

@@ -15,6 +15,7 @@
 // the fp64 path go through the same code.
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define LB_HD __host__ __device__ __forceinline__
@@ -392,12 +393,29 @@ LB_HD QcpPolyF qcp_poly_ff(const float* Rh, const float* Rl, float e0h, float e0
 // float-float pairs prepared in fp64 beforehand; the rest of the quartic only needs
 // fp32.  Returns the corrected root t' = t - Q(t)/Q'(t) in fp32 (relative accuracy ~1e-7,
 // i.e. 5e-8 in the RMSD) and whether the iteration had settled.
+// double -> (high float, low float) with the high part TRUNCATED to 24 bits by masking the
+// mantissa: the high part is then exactly a float and its double image is known without
+// converting it back (conversions run on a 16-lane unit).  |low| < ulp(high).
+LB_HD void qcp_split_trunc(double v, float& h, float& l) {
+#if defined(__CUDA_ARCH__)
+  const double hd = __hiloint2double(__double2hiint(v), __double2loint(v) & (int)0xE0000000u);
+#else
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+  b &= ~((1ull << 29) - 1);
+  double hd;
+  memcpy(&hd, &b, 8);
+#endif
+  h = (float)hd;
+  l = (float)(v - hd);
+}
+
 LB_HD QcpPolyF qcp_poly_split(const QcpPoly& p) {
   QcpPolyF f;
-  f.c0h = (float)p.c0; f.c0l = (float)(p.c0 - (double)f.c0h);
-  f.c1h = (float)p.c1; f.c1l = (float)(p.c1 - (double)f.c1h);
-  f.c2h = (float)p.c2; f.c2l = (float)(p.c2 - (double)f.c2h);
-  f.c3 = (float)p.c3;
+  qcp_split_trunc(p.c0, f.c0h, f.c0l);
+  qcp_split_trunc(p.c1, f.c1h, f.c1l);
+  qcp_split_trunc(p.c2, f.c2h, f.c2l);
+  f.c3 = p.xform ? 0.0f : -4.0f;
   f.t0 = p.t0; f.xform = p.xform;
   return f;
 }

@@ -123,7 +123,7 @@ __global__ void k_unit(const float* __restrict__ maxabs, size_t F, int force, in
 __global__ void __launch_bounds__(256)
 k_quantise(const float* __restrict__ raw, const double* __restrict__ centroid, size_t N,
            size_t Npad, size_t rows_total, size_t Kpad, const int* __restrict__ unit_log2,
-           int8_t* __restrict__ q8, long long* __restrict__ gq) {
+           int8_t* __restrict__ q8, double* __restrict__ gq) {
   __shared__ long long red[32];
   const size_t f = blockIdx.x;
   const double inv_unit = exp2(-(double)unit_log2[0]);
@@ -154,7 +154,7 @@ k_quantise(const float* __restrict__ raw, const double* __restrict__ centroid, s
   if (threadIdx.x == 0) {
     long long t = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    gq[f] = t;
+    gq[f] = (double)t;
   }
 }
 
@@ -183,7 +183,7 @@ int ensure_quantised(loosb200_frames* h, int force_unit_log2) {
   const size_t bytes = (size_t)NUM_SLICES * h->rows_total * h->Kpad;
   if (!h->q8) {
     if (dev_alloc_t(&h->q8, bytes) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
-    if (cudaMalloc(&h->gq, sizeof(long long) * h->F) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
+    if (cudaMalloc(&h->gq, sizeof(double) * h->F) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
     if (cudaMalloc(&h->unit_log2_dev, 2 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
   }
   LB_CUDA(cudaMemsetAsync(h->q8, 0, bytes, h->stream));
