@@ -49,12 +49,23 @@ class ClockSampler(threading.Thread):
     """SM clock and throttle reasons DURING the timed region, read through NVML in a
     background thread (same counters as `nvidia-smi --query-gpu=clocks.sm,
     clocks_event_reasons.*`, without forking nvidia-smi, which stalls the driver for
-    tens of ms per query)."""
+    tens of ms per query).  An NVML query that overlaps host-side CUDA calls delays them by
+    ~30 ms (measured: free-running 250 ms sampling cost 79 ms per 430 ms step), so samples are
+    taken on demand: `kick()` at the start of a step schedules one sample `delay` seconds later,
+    i.e. while the step's one long kernel runs and the host is blocked on it anyway."""
 
-    def __init__(self, gpu_index, period=float(os.environ.get("LOOSB200_CLOCK_PERIOD", "0.25"))):
+    def __init__(self, gpu_index, delay=float(os.environ.get("LOOSB200_CLOCK_DELAY", "0.12"))):
         super().__init__(daemon=True)
-        self.idx, self.period, self.rows, self._stop_ev = gpu_index, period, [], threading.Event()
+        self.idx, self.delay, self.rows, self._stop_ev = gpu_index, delay, [], threading.Event()
+        self._go = threading.Event()
+        self._ready = threading.Event()
         self.max_mhz = None
+
+    def kick(self):
+        self._go.set()
+
+    def wait_ready(self, timeout=5.0):
+        self._ready.wait(timeout)
 
     def run(self):
         try:
@@ -64,16 +75,21 @@ class ClockSampler(threading.Thread):
             idx = int(vis.split(",")[self.idx]) if vis and vis.split(",")[0].isdigit() else self.idx
             h = nv.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self._ready.set()
             while not self._stop_ev.is_set():
+                if not self._go.wait(0.05):
+                    continue
+                self._go.clear()
+                time.sleep(self.delay)
                 clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
                     rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.rows.append((clk, rs))
-                time.sleep(self.period)
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
+            self._ready.set()
 
     def stop(self):
         self._stop_ev.set()
@@ -89,7 +105,8 @@ class ClockSampler(threading.Thread):
         sm = sorted(c for c, _ in self.rows)
         reasons = sorted(n for n, bit in names.items() if any(r & bit for _, r in self.rows))
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                "samples": len(sm), "how": "NVML, %.0f ms period, during the timed region" % (self.period * 1e3)}
+                "samples": len(sm),
+                "how": "NVML, one sample %.0f ms into every timed step (while its kernel runs)" % (self.delay * 1e3)}
 
 
 def dist_setup(ngpus):
@@ -274,17 +291,24 @@ def main():
         fs.close()
         return st, t
 
+    t_est = 0.4
     for _ in range(args.warmup):
+        torch.cuda.synchronize()
+        t_w = time.perf_counter()
         step_device()
-    sampler = ClockSampler(local) if rank == 0 else None
+        t_est = time.perf_counter() - t_w
+    # one clock sample a third of the way into every timed step
+    sampler = ClockSampler(local, delay=min(0.12, t_est / 3)) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.25)
+        sampler.wait_ready()
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     kern_ms, launches, st = 0.0, 0, None
     for _ in range(args.steps):
+        if sampler:
+            sampler.kick()
         st, (ms_main, ms_other, nl) = step_device()
         kern_ms += ms_main
         launches += nl + 3          # + stage, unit, quantise kernels of the FrameSet
