@@ -1,6 +1,8 @@
 // See frontend.hpp.  Integer/text semantics follow the reference line by line;
 // the code is ours (no Boost, no bison/flex output).
 #include "frontend.hpp"
+#include <thread>
+#include <cmath>
 
 #include <pwd.h>
 #include <string.h>
@@ -567,21 +569,144 @@ std::string formatG(double v, unsigned precision) {
   return buf;
 }
 
+// ---- matrix text (src/MatrixImpl.hpp:210-222) ----
+// `os << setprecision(p) << M` prints every float with the stream's default notation, i.e. printf's
+// "%.{p}g", followed by one space.  At BASELINE's C4 size that is 10^10 values (45 GB of text):
+// glibc's snprintf (~130 ns per value) would take 20 minutes on one core, the GPU kernel takes
+// 0.45 s.  formatG_fast produces the same bytes for float inputs from exact integer arithmetic
+// (a float times a power of ten fits 128 bits), ~10x faster, and writeMatrix formats 16-row blocks
+// on all host threads.  Anything outside the fast path's range goes through snprintf.
+namespace {
+
+const double kPow10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11,
+                           1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+const uint64_t kPow10u[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull,
+                              100000000ull, 1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull,
+                              10000000000000ull, 100000000000000ull, 1000000000000000ull, 10000000000000000ull,
+                              100000000000000000ull, 1000000000000000000ull, 10000000000000000000ull};
+
+// Appends "%.{p}g" of v to out (no terminator); returns the number of characters.
+// Exact for every finite float with 1 <= p <= 9 and 1e-5 <= |v| < 1e9 (and for 0); others: snprintf.
+inline int formatG_fast(float v, unsigned p, char* out) {
+  uint32_t bits;
+  memcpy(&bits, &v, 4);
+  const uint32_t mag = bits & 0x7fffffffu;
+  if (mag == 0) {
+    int n = 0;
+    if (bits >> 31) out[n++] = '-';
+    out[n++] = '0';
+    return n;
+  }
+  const double av = std::fabs((double)v);
+  if (p < 1 || p > 9 || !(av >= 1e-5) || !(av < 1e9)) return snprintf(out, 40, "%.*g", (int)(p ? p : 1), (double)v);
+  // decimal exponent of the leading digit: 10^X <= av < 10^(X+1).  Exact: powers of ten up to
+  // 10^22 are doubles, and a float times 10^k (k <= 5) still fits the 53-bit significand.
+  int X;
+  if (av >= 1.0) {
+    X = 0;
+    while (X < 8 && av >= kPow10[X + 1]) ++X;
+  } else {
+    X = -1;
+    while (X > -5 && av * kPow10[-X] < 1.0) --X;
+  }
+  // n = round_half_even(av * 10^k), k = p - 1 - X, from the float's exact value m * 2^e
+  const int e_raw = (int)(mag >> 23);
+  uint64_t m = mag & 0x7fffffu;
+  int e;
+  if (e_raw == 0) e = -149; else { m |= 0x800000u; e = e_raw - 150; }
+  const int k = (int)p - 1 - X;  // -8 .. 13
+  uint64_t n;
+  if (k >= 0 && k <= 11 && e < 0 && e > -64) {
+    // the common case: the denominator is a power of two and everything fits 64 bits
+    const uint64_t num = m * kPow10u[k];  // < 2^24 * 10^11 < 2^61
+    const int sh = -e;
+    const uint64_t q = num >> sh, r = num & ((1ull << sh) - 1), half = 1ull << (sh - 1);
+    n = q + ((r > half || (r == half && (q & 1))) ? 1 : 0);
+  } else {
+    unsigned __int128 num = m, den = 1;
+    if (k >= 0) num *= kPow10u[k]; else den *= kPow10u[-k];
+    if (e >= 0) num <<= e; else den <<= -e;   // av >= 1e-5 bounds -e <= 40: den < 2^41 * 10^8
+    unsigned __int128 q = num / den, r = num - q * den;
+    const unsigned __int128 twice = r * 2;
+    if (twice > den || (twice == den && (q & 1))) ++q;
+    n = (uint64_t)q;
+  }
+  if (n >= kPow10u[p]) { n /= 10; ++X; }  // rounding carried into a new decade (n == 10^p exactly)
+  // digits of n: exactly p of them
+  char dig[20];
+  for (int i = (int)p - 1; i >= 0; --i) { dig[i] = (char)('0' + n % 10); n /= 10; }
+  int nd = (int)p;
+  while (nd > 1 && dig[nd - 1] == '0') --nd;  // %g strips trailing zeros
+  int len = 0;
+  if (bits >> 31) out[len++] = '-';
+  if (X < -4 || X >= (int)p) {  // scientific: d[.ddd]e+XX
+    out[len++] = dig[0];
+    if (nd > 1) { out[len++] = '.'; for (int i = 1; i < nd; ++i) out[len++] = dig[i]; }
+    out[len++] = 'e';
+    int ax = X;
+    if (ax < 0) { out[len++] = '-'; ax = -ax; } else out[len++] = '+';
+    out[len++] = (char)('0' + ax / 10);
+    out[len++] = (char)('0' + ax % 10);
+  } else if (X >= 0) {  // X + 1 integer digits, the rest after the point
+    for (int i = 0; i <= X; ++i) out[len++] = i < nd ? dig[i] : '0';
+    if (nd > X + 1) { out[len++] = '.'; for (int i = X + 1; i < nd; ++i) out[len++] = dig[i]; }
+  } else {  // 0.000ddd
+    out[len++] = '0'; out[len++] = '.';
+    for (int i = 0; i < -X - 1; ++i) out[len++] = '0';
+    for (int i = 0; i < nd; ++i) out[len++] = dig[i];
+  }
+  return len;
+}
+
+}  // namespace
+
 void writeMatrix(std::ostream& os, const float* M, size_t m, size_t n, size_t ld, unsigned precision) {
   os << "# " << m << " " << n << " (0)\n";
-  std::string line;
-  char buf[64];
-  for (size_t j = 0; j < m; ++j) {
-    line.clear();
-    for (size_t i = 0; i < n; ++i) {
-      const int l = snprintf(buf, sizeof(buf), "%.*g ", (int)precision, (double)M[i * ld + j]);
-      line.append(buf, (size_t)l);
+  // Blocks of RB rows: a column-major matrix is read one cache line (16 consecutive rows of one
+  // column) at a time; a batch of blocks is formatted by all threads, then written in order.
+  constexpr size_t RB = 16;
+  const size_t nblocks = (m + RB - 1) / RB;
+  unsigned nthreads = std::thread::hardware_concurrency();
+  if (nthreads == 0) nthreads = 1;
+  if (const char* env = getenv("LOOSB200_WRITER_THREADS")) nthreads = (unsigned)std::max(1, atoi(env));
+  if ((size_t)nthreads > nblocks) nthreads = (unsigned)std::max<size_t>(1, nblocks);
+  const size_t batch = (size_t)nthreads * 4;  // blocks formatted per round
+  std::vector<std::string> text(batch);
+  for (size_t b0 = 0; b0 < nblocks; b0 += batch) {
+    const size_t nb = std::min(batch, nblocks - b0);
+    auto work = [&](unsigned t) {
+      std::string line[RB];
+      char buf[48];
+      for (size_t b = t; b < nb; b += nthreads) {
+        const size_t j0 = (b0 + b) * RB, rows = std::min(RB, m - j0);
+        for (size_t r = 0; r < rows; ++r) { line[r].clear(); line[r].reserve(n * (precision + 7)); }
+        for (size_t i = 0; i < n; ++i) {
+          const float* col = M + i * ld + j0;
+          for (size_t r = 0; r < rows; ++r) {
+            int l = formatG_fast(col[r], precision, buf);
+            buf[l++] = ' ';
+            line[r].append(buf, (size_t)l);
+          }
+        }
+        std::string& out = text[b];
+        out.clear();
+        for (size_t r = 0; r < rows; ++r) { out += line[r]; out += '\n'; }
+      }
+    };
+    if (nthreads == 1) {
+      work(0);
+    } else {
+      std::vector<std::thread> pool;
+      for (unsigned t = 0; t < nthreads; ++t) pool.emplace_back(work, t);
+      for (auto& th : pool) th.join();
     }
-    line += '\n';
-    os.write(line.data(), (std::streamsize)line.size());
+    for (size_t b = 0; b < nb; ++b) os.write(text[b].data(), (std::streamsize)text[b].size());
   }
   os.flush();
 }
+
+// test hook: the fast formatter on one value (frontend_capi.cpp)
+int formatFloatG(float v, unsigned precision, char* out) { return formatG_fast(v, precision, out); }
 
 std::string invocationHeader(int argc, char* argv[]) {  // src/utils.cpp:119-164
   time_t t = time(0);

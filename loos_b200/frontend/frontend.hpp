@@ -90,6 +90,8 @@ std::string invocationHeader(int argc, char* argv[]);
 // default-floatfield formatting of a double with `precision` significant digits
 // (std::ostream default: 6), as rmsd2ref prints its values.
 std::string formatG(double v, unsigned precision);
+// "%.{precision}g" of a float from exact integer arithmetic (same bytes as printf; test hook)
+int formatFloatG(float v, unsigned precision, char* out);
 
 // ---- options (src/OptionsFramework.cpp:742-795: boost::program_options semantics used by
 // the tools: long names without prefix guessing, short aliases, every option takes a

@@ -84,6 +84,20 @@ long lbfe_multitraj(const uint32_t* sizes, int ntraj, uint32_t skip, uint32_t st
   return total;
 }
 
+// n floats -> their "%.{p}g" texts, '\n'-separated, into out (cap bytes); returns the length
+long lbfe_format_floats(const float* v, size_t n, unsigned precision, char* out, long cap) {
+  long len = 0;
+  char buf[48];
+  for (size_t i = 0; i < n; ++i) {
+    const int l = formatFloatG(v[i], precision, buf);
+    if (len + l + 1 > cap) return -1;
+    memcpy(out + len, buf, (size_t)l);
+    len += l;
+    out[len++] = '\n';
+  }
+  return len;
+}
+
 long lbfe_matrix_text(const float* M, size_t m, size_t n, size_t ld, unsigned precision, char* out, long cap) {
   std::ostringstream os;
   writeMatrix(os, M, m, n, ld, precision);
