@@ -541,6 +541,198 @@ void DCD::readFramePlanes(uint32_t i, float* out) {  // src/dcd.cpp:329-371
 
 // ================================================================= MultiTraj
 
+// =================================================================== Amber NetCDF
+
+namespace {
+
+struct NcCursor {  // big-endian NetCDF-3 header reader
+  std::ifstream& f;
+  const std::string& name;
+  uint32_t u32() {
+    unsigned char b[4];
+    f.read((char*)b, 4);
+    if (!f) throw Error("Error- " + name + ": truncated NetCDF header");
+    return ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+  }
+  uint64_t u64() { const uint64_t h = u32(); return (h << 32) | u32(); }
+  std::string str() {
+    const uint32_t n = u32();
+    if (n > (1u << 20)) throw Error("Error- " + name + ": implausible name length in NetCDF header");
+    std::string s(n, '\0');
+    f.read(&s[0], n);
+    f.ignore((4 - n % 4) % 4);
+    if (!f) throw Error("Error- " + name + ": truncated NetCDF header");
+    return s;
+  }
+};
+
+size_t ncTypeSize(uint32_t t, const std::string& name) {
+  switch (t) {
+    case 1: case 2: return 1;  // NC_BYTE, NC_CHAR
+    case 3: return 2;          // NC_SHORT
+    case 4: case 5: return 4;  // NC_INT, NC_FLOAT
+    case 6: return 8;          // NC_DOUBLE
+  }
+  throw Error("Error- " + name + ": unknown NetCDF type " + std::to_string(t));
+}
+
+// att_list = ABSENT | NC_ATTRIBUTE nelems [name type nelems values...]; text attributes are collected
+void ncAttributes(NcCursor& c, std::map<std::string, std::string>* text) {
+  const uint32_t tag = c.u32(), n = c.u32();
+  if (tag == 0 && n == 0) return;
+  if (tag != 0x0C) throw Error("Error- " + c.name + ": malformed NetCDF attribute list");
+  for (uint32_t i = 0; i < n; ++i) {
+    const std::string an = c.str();
+    const uint32_t type = c.u32(), ne = c.u32();
+    const size_t bytes = (size_t)ne * ncTypeSize(type, c.name);
+    std::string v(bytes, '\0');
+    c.f.read(&v[0], (std::streamsize)bytes);
+    c.f.ignore((4 - bytes % 4) % 4);
+    if (!c.f) throw Error("Error- " + c.name + ": truncated NetCDF header");
+    if (text && type == 2) {
+      while (!v.empty() && v.back() == '\0') v.pop_back();
+      (*text)[an] = v;
+    }
+  }
+}
+
+}  // namespace
+
+bool AmberNetcdf::isNetcdf(const std::string& path) {
+  std::ifstream f(path.c_str(), std::ios::binary);
+  char m[4] = {0, 0, 0, 0};
+  f.read(m, 4);
+  return f && m[0] == 'C' && m[1] == 'D' && m[2] == 'F';
+}
+
+AmberNetcdf::AmberNetcdf(const std::string& path, uint32_t natoms_expected)
+    : path_(path), ifs_(path.c_str(), std::ios::binary) {
+  if (!ifs_) throw Error("Error- cannot open " + path);
+  char magic[4];
+  ifs_.read(magic, 4);
+  if (!ifs_) throw Error("Error- " + path + ": not a NetCDF file");
+  if (magic[0] == '\x89' && magic[1] == 'H' && magic[2] == 'D' && magic[3] == 'F')
+    throw Error("Error- " + path + ": NetCDF-4 (HDF5) container is not supported, only NetCDF-3 classic / 64-bit offset");
+  if (!(magic[0] == 'C' && magic[1] == 'D' && magic[2] == 'F' && (magic[3] == 1 || magic[3] == 2)))
+    throw Error("Error- " + path + ": not a NetCDF-3 file");
+  const bool off64 = magic[3] == 2;
+  NcCursor c{ifs_, path_};
+  uint32_t numrecs = c.u32();
+
+  // dim_list
+  std::vector<std::pair<std::string, uint32_t>> dims;
+  {
+    const uint32_t tag = c.u32(), n = c.u32();
+    if (!(tag == 0 && n == 0)) {
+      if (tag != 0x0A) throw Error("Error- " + path + ": malformed NetCDF dimension list");
+      for (uint32_t i = 0; i < n; ++i) { std::string dn = c.str(); const uint32_t len = c.u32(); dims.push_back(std::make_pair(dn, len)); }
+    }
+  }
+  std::map<std::string, std::string> gatt;
+  ncAttributes(c, &gatt);
+  // AmberNetcdf::init, src/amber_netcdf.cpp:28-38
+  if (gatt["Conventions"].empty() || gatt["ConventionVersion"].empty())
+    throw Error("Error- " + path + ": Unable to find convention global attributes.  Is this really an Amber NetCDF trajectory?");
+  if (gatt["Conventions"].find("AMBER") == std::string::npos)
+    throw Error("Error- " + path + ": Cannot find AMBER tag in global attribues.  Is this really an Amber NetCDF trajectory?");
+  if (gatt["ConventionVersion"] != "1.0")
+    throw Error("Error- " + path + ": Convention version is '" + gatt["ConventionVersion"] + "', but only 1.0 is supported for Amber NetCDF trajectories.");
+
+  int atom_dim = -1, frame_dim = -1, spatial_dim = -1;
+  for (size_t i = 0; i < dims.size(); ++i) {
+    if (dims[i].first == "atom") atom_dim = (int)i;
+    if (dims[i].first == "frame") frame_dim = (int)i;
+    if (dims[i].first == "spatial") spatial_dim = (int)i;
+  }
+  if (atom_dim < 0) throw Error("Error- " + path + ": Cannot read atom id");
+  natoms_ = dims[atom_dim].second;
+  if (natoms_ != natoms_expected) throw Error("Error- " + path + ": AmberNetcdf has different number of atoms than expected");
+  if (frame_dim < 0) throw Error("Error- " + path + ": Cannot read frame information");
+
+  // var_list: every record variable adds its (padded) size to the record
+  bool have_coords = false;
+  uint64_t rec_size = 0, coord_vsize = 0;
+  int nrecvars = 0;
+  {
+    const uint32_t tag = c.u32(), n = c.u32();
+    if (!(tag == 0 && n == 0)) {
+      if (tag != 0x0B) throw Error("Error- " + path + ": malformed NetCDF variable list");
+      for (uint32_t i = 0; i < n; ++i) {
+        const std::string vn = c.str();
+        const uint32_t nd = c.u32();
+        std::vector<uint32_t> vd(nd);
+        for (uint32_t k = 0; k < nd; ++k) { vd[k] = c.u32(); if (vd[k] >= dims.size()) throw Error("Error- " + path + ": bad dimension id"); }
+        ncAttributes(c, nullptr);
+        const uint32_t type = c.u32();
+        const uint32_t vsize = c.u32();
+        const uint64_t begin = off64 ? c.u64() : c.u32();
+        const bool is_rec = nd > 0 && dims[vd[0]].second == 0;
+        if (is_rec) { rec_size += vsize; ++nrecvars; }
+        if (vn == "cell_lengths") periodic_ = true;
+        if (vn == "coordinates") {
+          if (!(nd == 3 && (int)vd[0] == frame_dim && (int)vd[1] == atom_dim && (spatial_dim < 0 || (int)vd[2] == spatial_dim) &&
+                dims[vd[2]].second == 3))
+            throw Error("Error- " + path + ": coordinates variable is not (frame, atom, spatial)");
+          if (type != 5 && type != 6) throw Error("Error- " + path + ": coordinates are neither float nor double");
+          coords_double_ = type == 6;
+          coord_begin_ = begin;
+          coord_vsize = (uint64_t)natoms_ * 3 * (coords_double_ ? 8 : 4);
+          have_coords = true;
+          if (!is_rec) throw Error("Error- " + path + ": coordinates do not vary along the record dimension");
+        }
+      }
+    }
+  }
+  if (!have_coords) throw Error("Error- " + path + ": Cannot get id for coordinates");
+  // a single record variable is stored without padding between records
+  rec_size_ = nrecvars == 1 ? coord_vsize : rec_size;
+  if (numrecs == 0xFFFFFFFFu) {  // "streaming": the count was never finalised, take it from the file size
+    ifs_.seekg(0, std::ios::end);
+    const uint64_t sz = (uint64_t)ifs_.tellg();
+    numrecs = rec_size_ && sz > coord_begin_ ? (uint32_t)((sz - coord_begin_ + rec_size_ - coord_vsize) / rec_size_) : 0;
+  }
+  nframes_ = numrecs;  // length of the unlimited dimension "frame"
+  if (dims[frame_dim].second != 0) nframes_ = dims[frame_dim].second;  // fixed-size frame dimension
+  raw_.resize(coord_vsize);
+}
+
+void AmberNetcdf::readFramePlanes(uint32_t i, float* out) {  // readRawFrame + updateGroupCoords, :108-150
+  if (i >= nframes_) throw Error("Error- " + path_ + ": Cannot read Amber netcdf frame (coords)");
+  ifs_.clear();
+  ifs_.seekg((std::streamoff)(coord_begin_ + (uint64_t)i * rec_size_));
+  ifs_.read((char*)raw_.data(), (std::streamsize)raw_.size());
+  if (!ifs_) throw Error("Error- " + path_ + ": Cannot read Amber netcdf frame (coords)");
+  const unsigned char* p = raw_.data();
+  const size_t n = natoms_;
+  if (!coords_double_) {
+    for (size_t k = 0; k < n; ++k)
+      for (int ax = 0; ax < 3; ++ax, p += 4) {
+        const uint32_t b = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+        memcpy(out + ax * n + k, &b, 4);
+      }
+  } else {  // nc_get_vara_float converts doubles to float (GCoord is double in the reference; the
+            // staged planes are float32 like every other trajectory format)
+    for (size_t k = 0; k < n; ++k)
+      for (int ax = 0; ax < 3; ++ax, p += 8) {
+        uint64_t b = 0;
+        for (int q = 0; q < 8; ++q) b = (b << 8) | p[q];
+        double d;
+        memcpy(&d, &b, 8);
+        out[ax * n + k] = (float)d;
+      }
+  }
+}
+
+std::shared_ptr<Trajectory> openTrajectory(const std::string& path, uint32_t natoms) {
+  const size_t dot = path.rfind('.');
+  std::string suffix = dot == std::string::npos ? "" : path.substr(dot + 1);
+  std::transform(suffix.begin(), suffix.end(), suffix.begin(), ::tolower);
+  if (suffix == "dcd") return std::make_shared<DCD>(path);
+  if (suffix == "nc" || suffix == "netcdf") return std::make_shared<AmberNetcdf>(path, natoms);
+  if ((suffix == "crd" || suffix == "mdcrd") && AmberNetcdf::isNetcdf(path)) return std::make_shared<AmberNetcdf>(path, natoms);
+  throw Error("Error- unknown or unsupported trajectory format for '" + path + "' (supported here: dcd, nc/netcdf)");
+}
+
 uint32_t MultiTraj::nframes(size_t i) const {
   const uint32_t n = trajs.at(i)->nframes();
   if (n <= skip) return 0;

@@ -49,18 +49,34 @@ std::vector<uint32_t> assignTrajectoryFrames(uint32_t nframes, const std::string
                                              uint32_t stride = 1);
 std::vector<uint32_t> uniquify(const std::vector<uint32_t>& v);  // src/utils.hpp:427-436
 
+// ---- trajectories ----
+// What the tools need from a trajectory (src/Trajectory.hpp: natoms, nframes, readFrame +
+// updateGroupCoords): frame `i` as three planes X[natoms] Y[natoms] Z[natoms].
+class Trajectory {
+ public:
+  virtual ~Trajectory() {}
+  virtual uint32_t natoms() const = 0;
+  virtual uint32_t nframes() const = 0;
+  virtual const std::string& filename() const = 0;
+  virtual void readFramePlanes(uint32_t i, float* out) = 0;  // out holds 3*natoms floats
+};
+// createTrajectory (src/sfactories.cpp:133-148): by suffix -- dcd; nc / netcdf (Amber NetCDF);
+// crd / mdcrd when the file is NetCDF (the reference's text Amber format is not read here).
+// `natoms` is the model's size; Amber NetCDF insists on a match (src/amber_netcdf.cpp:44-45).
+std::shared_ptr<Trajectory> openTrajectory(const std::string& path, uint32_t natoms);
+
 // ---- DCD (src/dcd.cpp:109-261,329-371) ----
-class DCD {
+class DCD : public Trajectory {
  public:
   explicit DCD(const std::string& path);
-  uint32_t natoms() const { return natoms_; }
-  uint32_t nframes() const { return nframes_; }
+  uint32_t natoms() const override { return natoms_; }
+  uint32_t nframes() const override { return nframes_; }
   bool hasCrystal() const { return icntrl_[10] == 1; }
   float timestep() const { return delta_; }
-  const std::string& filename() const { return path_; }
+  const std::string& filename() const override { return path_; }
   // Frame `i` as three planes X[natoms] Y[natoms] Z[natoms] (the record order of the
   // file): out must hold 3*natoms floats.
-  void readFramePlanes(uint32_t i, float* out);
+  void readFramePlanes(uint32_t i, float* out) override;
 
  private:
   uint32_t recordLen();
@@ -73,9 +89,35 @@ class DCD {
   uint64_t first_frame_pos_ = 0, frame_size_ = 0;
 };
 
+// ---- Amber NetCDF trajectories (src/amber_netcdf.cpp:20-130) ----
+// The reference links libnetcdf; here the NetCDF-3 container (classic and 64-bit-offset: magic
+// "CDF\1" / "CDF\2", big-endian header of dimensions, attributes and variables, fixed-size records)
+// is parsed directly.  Same checks as AmberNetcdf::init: global attributes Conventions (must contain
+// "AMBER") and ConventionVersion ("1.0"), dimension "atom" equal to the model size, dimension
+// "frame", variable "coordinates" (frame, atom, spatial) as float or double.  NetCDF-4 (HDF5) files
+// are refused.
+class AmberNetcdf : public Trajectory {
+ public:
+  AmberNetcdf(const std::string& path, uint32_t natoms_expected);
+  uint32_t natoms() const override { return natoms_; }
+  uint32_t nframes() const override { return nframes_; }
+  const std::string& filename() const override { return path_; }
+  bool hasPeriodicBox() const { return periodic_; }
+  void readFramePlanes(uint32_t i, float* out) override;
+  static bool isNetcdf(const std::string& path);  // isFileNetCDF, src/amber_netcdf.hpp:22
+
+ private:
+  std::string path_;
+  std::ifstream ifs_;
+  uint32_t natoms_ = 0, nframes_ = 0;
+  bool periodic_ = false, coords_double_ = false;
+  uint64_t coord_begin_ = 0, rec_size_ = 0;
+  std::vector<unsigned char> raw_;
+};
+
 // ---- MultiTrajectory indexing (src/MultiTraj.hpp:98-105, src/MultiTraj.cpp:48-58) ----
 struct MultiTraj {
-  std::vector<std::shared_ptr<DCD>> trajs;
+  std::vector<std::shared_ptr<Trajectory>> trajs;
   uint32_t skip = 0, stride = 1;
   uint32_t nframes(size_t i) const;
   uint32_t nframes() const;

@@ -67,6 +67,17 @@ int lbfe_dcd_read(const char* path, uint32_t frame, float* planes) {
   catch (const std::exception& e) { return fail(e); }
 }
 
+// any supported trajectory through openTrajectory (suffix dispatch)
+int lbfe_traj_info(const char* path, uint32_t natoms_expected, uint32_t* natoms, uint32_t* nframes) {
+  try { auto t = openTrajectory(path, natoms_expected); *natoms = t->natoms(); *nframes = t->nframes(); return 0; }
+  catch (const std::exception& e) { return fail(e); }
+}
+
+int lbfe_traj_read(const char* path, uint32_t natoms_expected, uint32_t frame, float* planes) {
+  try { auto t = openTrajectory(path, natoms_expected); t->readFramePlanes(frame, planes); return 0; }
+  catch (const std::exception& e) { return fail(e); }
+}
+
 // MultiTraj: sizes[] = frames in each sub-trajectory; returns composite count and the
 // (traj, frame) location of composite frame k for every k < cap
 long lbfe_multitraj(const uint32_t* sizes, int ntraj, uint32_t skip, uint32_t stride, uint32_t* loc_traj, uint32_t* loc_frame, long cap) {

@@ -36,7 +36,7 @@ int main(int argc, char* argv[]) {
     mt.skip = (uint32_t)o.uns("skip"); mt.stride = (uint32_t)o.uns("stride");
     if (mt.stride == 0) throw Error("Error- stride must be at least 1");
     for (const std::string& name : o.multi("traj")) {
-      mt.trajs.push_back(std::make_shared<DCD>(name));
+      mt.trajs.push_back(openTrajectory(name, (uint32_t)model.size()));
       if (mt.trajs.back()->natoms() != model.size()) throw Error("Error- '" + name + "' does not match the model size");
     }
     const std::vector<uint32_t> picked = selectAtoms(model, o.str("selection"));

@@ -70,7 +70,7 @@ int main(int argc, char* argv[]) {
       mt[s].skip = (uint32_t)o.uns("skip"); mt[s].stride = (uint32_t)o.uns("stride");
       if (mt[s].stride == 0) throw Error("Error- stride must be at least 1");
       for (const std::string& name : splitSpaces(sets[s])) {
-        mt[s].trajs.push_back(std::make_shared<DCD>(name));
+        mt[s].trajs.push_back(openTrajectory(name, (uint32_t)model.size()));
         if (mt[s].trajs.back()->natoms() != model.size()) throw Error("Error- '" + name + "' does not match the model size");
       }
     }

@@ -52,7 +52,8 @@ int main(int argc, char* argv[]) {
     std::cout << "# " << hdr << std::endl;
 
     Model molecule = readPDB(o.str("model"));
-    DCD traj(o.str("traj"));
+    const std::shared_ptr<Trajectory> trajp = openTrajectory(o.str("traj"), (uint32_t)molecule.size());
+    Trajectory& traj = *trajp;
     if (traj.natoms() != molecule.size()) throw Error("Error- trajectory and model differ in size");
     const std::vector<uint32_t> subset = selectAtoms(molecule, selection);
     if (subset.empty()) throw Error("Error- --rmsd selection matched no atoms");

@@ -33,7 +33,8 @@ int main(int argc, char* argv[]) {
     const int device = (int)o.uns("gpu"), engine = engineOf(o);
 
     Model model = readPDB(o.str("model1"));
-    DCD traj(o.str("traj1"));
+    const std::shared_ptr<Trajectory> trajp = openTrajectory(o.str("traj1"), (uint32_t)model.size());
+    Trajectory& traj = *trajp;
     if (traj.natoms() != model.size()) throw Error("Error- trajectory has " + std::to_string(traj.natoms()) + " atoms but the model has " + std::to_string(model.size()));
     const std::vector<uint32_t> picked = selectAtoms(model, o.str("sel1"));
     if (picked.empty()) throw Error("Error- selection '" + o.str("sel1") + "' matched no atoms");
@@ -52,7 +53,8 @@ int main(int argc, char* argv[]) {
       check(loosb200_rmsds_self(A.h, noop ? nullptr : M.data(), rows, &st, engine), "rmsds");
     } else {
       Model model2 = readPDB(o.str("model2"));
-      DCD traj2(o.str("traj2"));
+      const std::shared_ptr<Trajectory> traj2p = openTrajectory(o.str("traj2"), (uint32_t)model2.size());
+      Trajectory& traj2 = *traj2p;
       if (traj2.natoms() != model2.size()) throw Error("Error- second trajectory and model differ in size");
       const std::vector<uint32_t> picked2 = selectAtoms(model2, o.str("sel2"));
       const std::vector<uint32_t> sel2 = selectionToFrameIndices(model2, picked2);

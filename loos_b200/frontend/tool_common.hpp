@@ -65,7 +65,7 @@ inline void stageStreaming(std::vector<Frames*> sets, const std::vector<const st
   for (size_t k = 0; k < sets.size(); ++k) check(loosb200_stage_end(sets[k]->h), "staging frames");
 }
 
-inline void stageTrajectory(Frames& f, DCD& traj, const std::vector<uint32_t>& indices, size_t natoms,
+inline void stageTrajectory(Frames& f, Trajectory& traj, const std::vector<uint32_t>& indices, size_t natoms,
                             const std::vector<uint32_t>& sel, int device) {
   stageStreaming({&f}, {&sel}, indices.size(), natoms, device,
                  [&](size_t j, float* dst) { traj.readFramePlanes(indices[j], dst); });

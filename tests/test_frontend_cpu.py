@@ -232,3 +232,84 @@ def test_tools_fail_loudly_without_gpu(system):
     assert r.returncode == 255 and "Usage-" in r.stderr
     r = subprocess.run([exe, "--sel", "all", system["pdb"], system["dcd"]], capture_output=True, text=True)
     assert r.returncode == 255 and "unrecognised option '--sel'" in r.stderr   # no prefix guessing
+
+
+# ---------------------------------------------------------------- Amber NetCDF (src/amber_netcdf.cpp)
+
+def _write_amber_nc(path, xyz, version=1, dtype="f", box=True, conventions="AMBER", conv_version="1.0",
+                    extra_record_var=True):
+    """Amber NetCDF trajectory written with scipy's NetCDF-3 writer (independent of the reader under test)."""
+    from scipy.io import netcdf_file
+    F, N, _ = xyz.shape
+    f = netcdf_file(path, "w", version=version)
+    if conventions is not None:
+        f.Conventions = conventions
+    if conv_version is not None:
+        f.ConventionVersion = conv_version
+    f.program = "test"
+    f.createDimension("frame", None)
+    f.createDimension("spatial", 3)
+    f.createDimension("atom", N)
+    if box:
+        f.createDimension("cell_spatial", 3)
+    if extra_record_var:
+        t = f.createVariable("time", "f", ("frame",))
+        t.units = "picosecond"
+    c = f.createVariable("coordinates", dtype, ("frame", "atom", "spatial"))
+    c.units = "angstrom"
+    if box:
+        b = f.createVariable("cell_lengths", "d", ("frame", "cell_spatial"))
+    for k in range(F):
+        c[k] = xyz[k]
+        if extra_record_var:
+            t[k] = 0.5 * k
+        if box:
+            b[k] = [50.0, 60.0, 70.0]
+    f.close()
+
+
+@pytest.mark.parametrize("version,dtype,box,extra", [(1, "f", True, True), (2, "f", False, True), (1, "d", True, True),
+                                                    (1, "f", False, False)])
+def test_amber_netcdf_reader(fe, tmp_path, version, dtype, box, extra):
+    """NetCDF-3 classic and 64-bit-offset containers, float and double coordinates, with and without
+    other record variables (a lone record variable is stored unpadded): every frame comes back as
+    X|Y|Z planes with the exact float32 values."""
+    rng = np.random.default_rng(5)
+    F, N = 9, 37                                   # N*3*4 not a multiple of 8: exercises record padding rules
+    xyz = (rng.normal(size=(F, N, 3)) * 30).astype(np.float32)
+    path = str(tmp_path / ("t%d%s.nc" % (version, dtype)))
+    _write_amber_nc(path, xyz.astype(np.float64 if dtype == "d" else np.float32), version, dtype, box, extra_record_var=extra)
+    na, nf = C.c_uint32(), C.c_uint32()
+    assert fe.lbfe_traj_info(path.encode(), N, C.byref(na), C.byref(nf)) == 0, fe.lbfe_last_error()
+    assert (na.value, nf.value) == (N, F)
+    buf = np.zeros(3 * N, np.float32)
+    for k in (0, 4, F - 1):
+        assert fe.lbfe_traj_read(path.encode(), N, k, buf.ctypes.data_as(C.POINTER(C.c_float))) == 0
+        assert np.array_equal(buf.reshape(3, N), xyz[k].T)
+    assert fe.lbfe_traj_read(path.encode(), N, F, buf.ctypes.data_as(C.POINTER(C.c_float))) == -1
+
+
+def test_amber_netcdf_validation(fe, tmp_path):
+    """The checks of AmberNetcdf::init (src/amber_netcdf.cpp:28-45) and the container checks."""
+    xyz = np.zeros((2, 5, 3), np.float32)
+    na, nf = C.c_uint32(), C.c_uint32()
+
+    def err(path, natoms=5):
+        assert fe.lbfe_traj_info(path.encode(), natoms, C.byref(na), C.byref(nf)) == -1
+        return fe.lbfe_last_error().decode()
+
+    p = str(tmp_path / "a.nc"); _write_amber_nc(p, xyz, conventions=None)
+    assert "Unable to find convention global attributes" in err(p)
+    p = str(tmp_path / "b.nc"); _write_amber_nc(p, xyz, conventions="CF-1.0")
+    assert "Cannot find AMBER tag" in err(p)
+    p = str(tmp_path / "c.nc"); _write_amber_nc(p, xyz, conv_version="2.0")
+    assert "only 1.0 is supported" in err(p)
+    p = str(tmp_path / "d.nc"); _write_amber_nc(p, xyz)
+    assert "different number of atoms than expected" in err(p, natoms=6)
+    p = str(tmp_path / "e.nc"); open(p, "wb").write(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    assert "NetCDF-4" in err(p)
+    p = str(tmp_path / "f.xtc"); open(p, "wb").write(b"\0" * 64)
+    assert "unsupported trajectory format" in err(p)
+    # the suffix rules of createTrajectory: .crd is NetCDF when it carries the magic
+    p = str(tmp_path / "g.crd"); _write_amber_nc(p, xyz)
+    assert fe.lbfe_traj_info(p.encode(), 5, C.byref(na), C.byref(nf)) == 0 and nf.value == 2

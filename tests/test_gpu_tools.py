@@ -177,3 +177,34 @@ def test_rms_overlap(files, checker):
     want = "Max rmsd = %.4f between frames %d, %d, avg rmsd = %.4f, variance = %.4f, frames below %.4f = %d, total = %d" % (
         mval, mi, 17, avg, var, 6.5, int((ref[off] < np.float32(6.5)).sum()), ref.size)
     assert out.strip() == want and err == ""
+
+
+def test_amber_netcdf_trajectories_give_the_same_matrices(files, tmp_path):
+    """The same frames as Amber NetCDF (.nc, written with scipy's NetCDF-3 writer) and as DCD: rmsds,
+    multi-rmsds (mixed formats in one MultiTrajectory) and rmsd2ref print identical numbers."""
+    from scipy.io import netcdf_file
+    d, xyz = files["d"], files["xyz"]
+
+    def write_nc(path, X, version):
+        f = netcdf_file(str(path), "w", version=version)
+        f.Conventions = "AMBER"; f.ConventionVersion = "1.0"
+        f.createDimension("frame", None); f.createDimension("spatial", 3); f.createDimension("atom", X.shape[1])
+        t = f.createVariable("time", "f", ("frame",))
+        c = f.createVariable("coordinates", "f", ("frame", "atom", "spatial"))
+        for k in range(len(X)):
+            c[k] = X[k]; t[k] = k
+        f.close()
+
+    write_nc(tmp_path / "all.nc", xyz, 1)
+    write_nc(tmp_path / "b.nc", xyz[70:115], 2)
+    body = lambda out: "\n".join(l for l in out.splitlines() if not (l.startswith("# ") and "[loos-b200" in l))
+    a, _ = run("rmsds", "-p", "6", d / "model.pdb", d / "all.dcd")
+    b, _ = run("rmsds", "-p", "6", d / "model.pdb", tmp_path / "all.nc")
+    assert body(a) == body(b)
+    a, _ = run("multi-rmsds", "-p", "5", d / "model.pdb", d / "a.dcd", d / "b.dcd", d / "c.dcd")
+    b, _ = run("multi-rmsds", "-p", "5", d / "model.pdb", d / "a.dcd", tmp_path / "b.nc", d / "c.dcd")
+    strip = lambda out: "\n".join(l for l in body(out).splitlines() if not l.startswith("# "))   # trajectory table names differ
+    assert strip(a) == strip(b)
+    a, _ = run("rmsd2ref", "--target", d / "target.pdb", d / "model.pdb", d / "all.dcd")
+    b, _ = run("rmsd2ref", "--target", d / "target.pdb", d / "model.pdb", tmp_path / "all.nc")
+    assert body(a) == body(b)
