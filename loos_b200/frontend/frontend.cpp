@@ -2,6 +2,7 @@
 // the code is ours (no Boost, no bison/flex output).
 #include "frontend.hpp"
 #include <thread>
+#include <iterator>
 #include <cmath>
 
 #include <pwd.h>
@@ -895,6 +896,35 @@ void writeMatrix(std::ostream& os, const float* M, size_t m, size_t n, size_t ld
     for (size_t b = 0; b < nb; ++b) os.write(text[b].data(), (std::streamsize)text[b].size());
   }
   os.flush();
+}
+
+std::vector<float> readMatrix(std::istream& is, size_t* m_out, size_t* n_out) {
+  std::string line;
+  int m = 0, n = 0;
+  while (std::getline(is, line).good())
+    if (sscanf(line.c_str(), "# %d %d", &m, &n) == 2) break;
+  if (m == 0 && n == 0) throw Error("Could not find magic marker in matrix file");
+  if (m <= 0 || n <= 0) throw Error("Error while reading magic marker");
+  std::vector<float> M((size_t)m * (size_t)n);
+  // the rest of the stream in one piece: strtof per token (operator>> per value is ~10x slower)
+  std::string body((std::istreambuf_iterator<char>(is)), std::istreambuf_iterator<char>());
+  const char* p = body.c_str();
+  for (int j = 0; j < m; ++j)
+    for (int i = 0; i < n; ++i) {
+      while (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r') ++p;
+      if (!*p) throw Error("Read error at (" + std::to_string(j) + "," + std::to_string(i) + ") with input ''");
+      char* end = nullptr;
+      const float v = strtof(p, &end);
+      if (end == p) {
+        const char* q = p;
+        while (*q && *q != ' ' && *q != '\n') ++q;
+        throw Error("Invalid conversion on matrix read at (" + std::to_string(j) + "," + std::to_string(i) + ") of '" + std::string(p, q) + "'");
+      }
+      M[(size_t)i * (size_t)m + (size_t)j] = v;
+      p = end;
+    }
+  *m_out = (size_t)m; *n_out = (size_t)n;
+  return M;
 }
 
 // test hook: the fast formatter on one value (frontend_capi.cpp)

@@ -128,6 +128,10 @@ struct MultiTraj {
 // ---- output (src/MatrixImpl.hpp:210-222, src/utils.cpp:119-164) ----
 // M: float32 column-major, ld >= m.  Same bytes as `os << setprecision(p) << M`.
 void writeMatrix(std::ostream& os, const float* M, size_t m, size_t n, size_t ld, unsigned precision);
+// readAsciiMatrix (src/MatrixRead.hpp:102-143): skip lines until one scans as "# m n", then m*n
+// whitespace-separated values, row by row.  Returns column-major float32 (ld = m), i.e. exactly
+// what writeMatrix was given.  Errors carry the reference's messages.
+std::vector<float> readMatrix(std::istream& is, size_t* m, size_t* n);
 std::string invocationHeader(int argc, char* argv[]);
 // default-floatfield formatting of a double with `precision` significant digits
 // (std::ostream default: 6), as rmsd2ref prints its values.

@@ -95,6 +95,19 @@ long lbfe_multitraj(const uint32_t* sizes, int ntraj, uint32_t skip, uint32_t st
   return total;
 }
 
+// text -> column-major floats (ld = m); returns 0 and the shape, or -1 (lbfe_last_error)
+int lbfe_read_matrix(const char* text, long len, float* out, long cap, long* m, long* n) {
+  try {
+    std::istringstream is(std::string(text, (size_t)len));
+    size_t mm = 0, nn = 0;
+    const std::vector<float> M = readMatrix(is, &mm, &nn);
+    *m = (long)mm; *n = (long)nn;
+    if ((long)M.size() > cap) return -2;
+    memcpy(out, M.data(), M.size() * sizeof(float));
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+
 // n floats -> their "%.{p}g" texts, '\n'-separated, into out (cap bytes); returns the length
 long lbfe_format_floats(const float* v, size_t n, unsigned precision, char* out, long cap) {
   long len = 0;

@@ -313,3 +313,32 @@ def test_amber_netcdf_validation(fe, tmp_path):
     # the suffix rules of createTrajectory: .crd is NetCDF when it carries the magic
     p = str(tmp_path / "g.crd"); _write_amber_nc(p, xyz)
     assert fe.lbfe_traj_info(p.encode(), 5, C.byref(na), C.byref(nf)) == 0 and nf.value == 2
+
+
+def test_matrix_write_read_round_trip(fe):
+    """writeMatrix -> readMatrix (readAsciiMatrix, src/MatrixRead.hpp:102-143) reproduces every float32
+    bit at -p 9 and the rounded values at the default -p 2; header lines before the marker are skipped."""
+    rng = np.random.default_rng(12)
+    m, n = 41, 29
+    M = np.asfortranarray(rng.gamma(2.0, 2.5, (m, n)).astype(np.float32))
+    M[3, 4] = 0.0
+    fe.lbfe_read_matrix.restype = C.c_int
+    for prec in (9, 2):
+        cap = 1 << 20
+        out = C.create_string_buffer(cap)
+        k = fe.lbfe_matrix_text(M.ctypes.data_as(C.POINTER(C.c_float)), m, n, m, prec, out, cap)
+        text = b"# rmsds 'model.pdb' 'traj.dcd' - user (date) {cwd} [loos-b200]\n" + out.raw[:k]
+        back = np.zeros((n, m), np.float32)
+        mm, nn = C.c_long(), C.c_long()
+        assert fe.lbfe_read_matrix(text, len(text), back.ctypes.data_as(C.POINTER(C.c_float)), back.size,
+                                   C.byref(mm), C.byref(nn)) == 0, fe.lbfe_last_error()
+        assert (mm.value, nn.value) == (m, n)
+        if prec == 9:
+            assert np.array_equal(back.T, M)
+        else:
+            assert np.array_equal(back.T, np.array([[float("%.2g" % v) for v in row] for row in M], np.float32))
+    bad = b"# 2 2 (0)\n1 2 \n3 x \n"
+    assert fe.lbfe_read_matrix(bad, len(bad), back.ctypes.data_as(C.POINTER(C.c_float)), back.size, C.byref(mm), C.byref(nn)) == -1
+    assert b"Invalid conversion on matrix read at (1,1) of 'x'" in fe.lbfe_last_error()
+    assert fe.lbfe_read_matrix(b"1 2 3\n", 6, back.ctypes.data_as(C.POINTER(C.c_float)), back.size, C.byref(mm), C.byref(nn)) == -1
+    assert b"Could not find magic marker" in fe.lbfe_last_error()
