@@ -23,10 +23,11 @@
 //   warp 1   TMEM allocator + MMA issuer: per 32-atom K step six tcgen05.mma
 //            (three with N = 192 spanning two adjacent classes, three with N = 96)
 //   warps 2-13 epilogue, one (lane quarter, 10-frame column group) each:
-//            tcgen05.ld -> exact integer combine in fp64 -> TMEM handed back to the
-//            MMA warp -> shuffle -> QCP -> float32 tile in smem -> coalesced (and
-//            mirrored) stores.  Only the TMEM drain is serial with the MMAs of the
-//            next tile; the solves overlap them.
+//            tcgen05.ld -> exact integer combine in fp64 -> shuffle -> quartic coefficients
+//            (fp64) -> TMEM handed back to the MMA warp -> fp32 Newton + float-float
+//            correction -> float32 tile in smem -> coalesced (and mirrored) stores.
+//            The fp64 part is serial with the next tile's MMAs on purpose: fp64 CUDA-core
+//            math and the tensor pipe contend on sm_100 (see the epilogue).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -193,18 +194,6 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -497,7 +486,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint32_t tphase = 0, buf = 0;
     float sum_h = 0.0f, sum_l = 0.0f, tmax = 0.0f;
     const double inv_n = 1.0 / (double)a.N;
-    const int release_at = a.release_at;  // 0 after drain, 1 after fp64 coefficients, 2 after Newton, 3 after polish
+    const int release_at = a.release_at;  // hand TMEM back: 0 right after the drain, 1 after the fp64 coefficient phase
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = a.prof ? clock64() : 0;
 
@@ -617,7 +606,6 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         if (it >= 1 && __all_sync(0xffffffffu, conv)) break;
       }
-      if (release_at == 2) { __syncwarp(); if (lane == 0) release_tmem<CL>(ctl, crank); }
       LB_TICK(3);  // Newton (fp32)
 
       // ---- one float-float residual correction per pair, float32 result ----
@@ -646,7 +634,6 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         if (owner) ctl->T[buf][b_local][a_local] = val;
       }
-      if (release_at == 3) { __syncwarp(); if (lane == 0) release_tmem<CL>(ctl, crank); }
       LB_TICK(4);  // polish
       asm volatile("bar.sync 1, 384;" ::: "memory");  // tile T[buf] complete
       LB_TICK(5);  // barrier
@@ -772,7 +759,7 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   // crawls while MMAs run, and with two 128-atom stages the MMA warp would otherwise start a tile
   // it cannot feed); long ones: hand them back right after the drain.  Measured both ways at
   // N = 1000 and N = 3000 (profiles/r1_summary.md).
-  ta.release_at = getenv("LOOSB200_RELEASE_AT") ? atoi(getenv("LOOSB200_RELEASE_AT")) : (A->Kpad <= 2048 ? 1 : 0);
+  ta.release_at = getenv("LOOSB200_RELEASE_AT") ? (atoi(getenv("LOOSB200_RELEASE_AT")) ? 1 : 0) : (A->Kpad <= 2048 ? 1 : 0);
   const bool want_prof = getenv("LOOSB200_PROF") != nullptr;
 
   LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<1>()));

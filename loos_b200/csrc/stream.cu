@@ -1,16 +1,14 @@
 // Single-reference streaming path (rmsd2ref and iterative alignment).
 //
-// One CTA walks frames; per frame it makes at most two passes over the frame's
-// fp32 planes (the second one hits L1/L2):
-//   pass 1  centroid + 3x3 covariance against the centred reference
-//           (alignment::kabsch, src/alignment.cpp:217-233: centre both, dgemm)
-//           -> Jacobi eigen-solve of Horn's K -> rotation Z, 4x4 W = T(vc) Z T(-uc)
-//   pass 2  x' = W x over the rmsd selection (AtomicGroup::applyTransform,
-//           src/AG_numerical.cpp:363-370) and either sum |x' - y|^2
-//           (AtomicGroup::rmsd, :301-318) or accumulation of x' into the running
-//           average (iterativeAlignment / averageStructure,
-//           src/alignment.cpp:379-393, src/ensembles.cpp:108-118).
-// HBM-bound: 12 N_align (+ 12 N_rmsd if a different selection) bytes per frame.
+//   k_cov     3x3 covariance of every frame with the centred reference (alignment::kabsch,
+//             src/alignment.cpp:217-233: centre both, dgemm); frame centroids come from staging
+//   k_solve   one frame per thread: QCP root of Horn's K, eigenvector -> rotation Z,
+//             4x4 W = T(vc) Z T(-uc); optionally the minimal RMSD from the eigenvalue
+//   k_resid   x' = W x over the rmsd selection (AtomicGroup::applyTransform,
+//             src/AG_numerical.cpp:363-370) and sum |x' - y|^2 (AtomicGroup::rmsd, :301-318)
+//   k_accum   sum of x' into the running average (iterativeAlignment / averageStructure,
+//             src/alignment.cpp:379-393, src/ensembles.cpp:108-118), k_finish_iter closes an iteration
+// HBM-bound: 12 N_align (+ 12 N_rmsd if a different selection) bytes per frame and pass.
 #include <string.h>
 
 #include <vector>
@@ -25,158 +23,40 @@ namespace {
 
 constexpr int ST = 128;  // threads per CTA
 
-enum : int { M_COMPUTE_W = 1, M_ACCUM = 2, M_RMSD = 4, M_IDENTITY = 8 };
-
-__device__ __forceinline__ double wsum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-template <int NV>
-__device__ __forceinline__ void bsum(double (&v)[NV], double* red /* NV*4 */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = wsum(v[i]);
-  __syncthreads();
-  if (lane == 0)
-#pragma unroll
-    for (int i = 0; i < NV; ++i) red[i * 4 + warp] = v[i];
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = red[i * 4] + red[i * 4 + 1] + red[i * 4 + 2] + red[i * 4 + 3];
-}
-
-struct StreamArgs {
-  const float* rawA; size_t NpadA; uint32_t Na;   // align selection planes
-  const float* rawR; size_t NpadR; uint32_t Nr;   // rmsd selection planes
-  const double* refA;   // [3][NpadA] centred reference (align selection)
-  double refA_c[3];     // its centroid before centring
-  double refA_sum[3];   // sum of the centred reference (~0; kept for exactness)
-  double refA_g;        // sum of squares of the centred reference
-  const double* refR;   // [3][NpadR] uncentred reference (rmsd selection)
-  double* xf;           // [F][16] in/out
-  double* out_rmsd;     // [F]
-  double* avg;          // [3][Npad of the accumulated set] global accumulators
+// Sum of the transformed frames, sum_f (W_f x_f), for iterativeAlignment's running average
+// (src/alignment.cpp:385-397) and averageStructure (src/ensembles.cpp:91-121).  Each CTA walks
+// frames f = blockIdx.x, blockIdx.x + gridDim.x, ... and keeps its partial sum in shared memory;
+// a thread owns atoms tid, tid + ST, ..., so there is no synchronisation inside the frame loop and
+// no atomic until the final flush.  W_f ([F][16], from k_solve) is read straight from global memory
+// (one broadcast line per frame).
+struct AccumArgs {
+  const float* raw; size_t Npad; uint32_t N;  // frame planes [F][3][Npad]
+  const double* xf;                           // [F][16]
   uint32_t F;
-  int mode;
-  int accum_align_set;  // M_ACCUM over the align planes (iterative) or the rmsd planes
+  double* avg;                                // [3][Npad] global accumulators (zeroed by the caller)
 };
 
-__global__ void __launch_bounds__(ST) k_stream(const StreamArgs a) {
-  extern __shared__ double acc_s[];  // [3][Npad] when M_ACCUM
-  __shared__ double red[12 * 4];
-  __shared__ double Ws[12];
+__global__ void __launch_bounds__(ST) k_accum(const AccumArgs a) {
+  extern __shared__ double acc_s[];  // [3][Npad]
   const int tid = threadIdx.x;
-  const bool accum = a.mode & M_ACCUM;
-  const float* rawS = a.accum_align_set ? a.rawA : a.rawR;
-  const size_t NpadS = a.accum_align_set ? a.NpadA : a.NpadR;
-  const uint32_t Ns = a.accum_align_set ? a.Na : a.Nr;
-  if (accum)
-    for (size_t i = tid; i < 3 * NpadS; i += ST) acc_s[i] = 0.0;
-
+  for (size_t i = tid; i < 3 * a.Npad; i += ST) acc_s[i] = 0.0;
+  __syncthreads();  // the zeroing and the flush stride over all three planes, the frame loop does not
   for (uint32_t f = blockIdx.x; f < a.F; f += gridDim.x) {
-    if (a.mode & M_COMPUTE_W) {
-      const float4* px = reinterpret_cast<const float4*>(a.rawA + ((size_t)f * 3 + 0) * a.NpadA);
-      const float4* py = reinterpret_cast<const float4*>(a.rawA + ((size_t)f * 3 + 1) * a.NpadA);
-      const float4* pz = reinterpret_cast<const float4*>(a.rawA + ((size_t)f * 3 + 2) * a.NpadA);
-      const double* rx = a.refA, *ry = a.refA + a.NpadA, *rz = a.refA + 2 * a.NpadA;
-      double s[12];
-#pragma unroll
-      for (int k = 0; k < 12; ++k) s[k] = 0.0;
-      for (uint32_t i4 = tid; i4 < a.NpadA / 4; i4 += ST) {
-        const float4 X = __ldg(px + i4), Y = __ldg(py + i4), Z = __ldg(pz + i4);
-        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const double x = xs[k], y = ys[k], z = zs[k];
-          const double vx = rx[4 * i4 + k], vy = ry[4 * i4 + k], vz = rz[4 * i4 + k];
-          s[0] += x; s[1] += y; s[2] += z;
-          s[3] = fma(x, vx, s[3]); s[4] = fma(x, vy, s[4]); s[5] = fma(x, vz, s[5]);
-          s[6] = fma(y, vx, s[6]); s[7] = fma(y, vy, s[7]); s[8] = fma(y, vz, s[8]);
-          s[9] = fma(z, vx, s[9]); s[10] = fma(z, vy, s[10]); s[11] = fma(z, vz, s[11]);
-        }
-      }
-      bsum<12>(s, red);
-      if (tid == 0) {
-        const double uc[3] = {s[0] / a.Na, s[1] / a.Na, s[2] / a.Na};
-        double R[9];
-        // sum (x - uc) v^T = sum x v^T - uc (sum v)^T
-#pragma unroll
-        for (int p = 0; p < 3; ++p)
-#pragma unroll
-          for (int q = 0; q < 3; ++q) R[3 * p + q] = s[3 + 3 * p + q] - uc[p] * a.refA_sum[q];
-        double Z[9];
-        qcp_rotation(R, Z, 0);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          Ws[4 * i] = Z[3 * i]; Ws[4 * i + 1] = Z[3 * i + 1]; Ws[4 * i + 2] = Z[3 * i + 2];
-          Ws[4 * i + 3] = a.refA_c[i] - (Z[3 * i] * uc[0] + Z[3 * i + 1] * uc[1] + Z[3 * i + 2] * uc[2]);
-        }
-        if (a.xf) {
-          double* o = a.xf + (size_t)f * 16;
-#pragma unroll
-          for (int k = 0; k < 12; ++k) o[k] = Ws[k];
-          o[12] = o[13] = o[14] = 0.0; o[15] = 1.0;
-        }
-      }
-      __syncthreads();
-    } else {
-      if (tid < 12) {
-        if (a.mode & M_IDENTITY) Ws[tid] = (tid % 5 == 0) ? 1.0 : 0.0;
-        else Ws[tid] = a.xf[(size_t)f * 16 + tid];
-      }
-      if ((a.mode & M_IDENTITY) && a.xf && tid < 16) a.xf[(size_t)f * 16 + tid] = (tid % 5 == 0) ? 1.0 : 0.0;
-      __syncthreads();
-    }
     double W[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) W[k] = Ws[k];
-
-    if (accum) {
-      const float* px = rawS + ((size_t)f * 3 + 0) * NpadS;
-      const float* py = px + NpadS, *pz = py + NpadS;
-      for (uint32_t i = tid; i < Ns; i += ST) {  // each thread owns its atoms: no atomics
-        const double x = px[i], y = py[i], z = pz[i];
-        acc_s[i] += W[0] * x + W[1] * y + W[2] * z + W[3];
-        acc_s[NpadS + i] += W[4] * x + W[5] * y + W[6] * z + W[7];
-        acc_s[2 * NpadS + i] += W[8] * x + W[9] * y + W[10] * z + W[11];
-      }
+    for (int k = 0; k < 12; ++k) W[k] = __ldg(a.xf + (size_t)f * 16 + k);
+    const float* px = a.raw + (size_t)f * 3 * a.Npad;
+    const float* py = px + a.Npad, *pz = py + a.Npad;
+    for (uint32_t i = tid; i < a.N; i += ST) {
+      const double x = __ldcs(px + i), y = __ldcs(py + i), z = __ldcs(pz + i);
+      acc_s[i] += W[0] * x + W[1] * y + W[2] * z + W[3];
+      acc_s[a.Npad + i] += W[4] * x + W[5] * y + W[6] * z + W[7];
+      acc_s[2 * a.Npad + i] += W[8] * x + W[9] * y + W[10] * z + W[11];
     }
-    if (a.mode & M_RMSD) {
-      const float* px = a.rawR + ((size_t)f * 3 + 0) * a.NpadR;
-      const float* py = px + a.NpadR, *pz = py + a.NpadR;
-      const double* rx = a.refR, *ry = rx + a.NpadR, *rz = ry + a.NpadR;
-      double d[1] = {0.0};
-      for (uint32_t i = tid; i < a.Nr; i += ST) {
-        const double x = px[i], y = py[i], z = pz[i];
-        const double ex = rx[i] - (W[0] * x + W[1] * y + W[2] * z + W[3]);
-        const double ey = ry[i] - (W[4] * x + W[5] * y + W[6] * z + W[7]);
-        const double ez = rz[i] - (W[8] * x + W[9] * y + W[10] * z + W[11]);
-        d[0] += ex * ex + ey * ey + ez * ez;
-      }
-      bsum<1>(d, red);
-      if (tid == 0) a.out_rmsd[f] = sqrt(d[0] / a.Nr);
-    }
-    __syncthreads();
   }
-  if (accum)
-    for (size_t i = tid; i < 3 * NpadS; i += ST)
-      if (acc_s[i] != 0.0) atomicAdd(&a.avg[i], acc_s[i]);
-}
-
-// Warp-per-frame variant for the modes without accumulation (rmsd2ref with a target,
-// final per-frame RMSD of the iterative mode): one warp owns a frame, so the warps of
-// an SM keep hundreds of KB of loads in flight, nothing is block-synchronised, and the
-// 3x3 solve (quartic + adjugate eigenvector, redundantly in every lane) is ~300 fp64
-// instructions instead of a Jacobi sweep in local memory.  This is the HBM-bound
-// kernel of the path: 12 N_align (+ 12 N_rmsd) bytes per frame.
-constexpr int SW_THREADS = 256;
-
-__device__ __forceinline__ double wsum_all(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+  __syncthreads();
+  for (size_t i = tid; i < 3 * a.Npad; i += ST)
+    if (acc_s[i] != 0.0) atomicAdd(&a.avg[i], acc_s[i]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -190,6 +70,14 @@ __device__ __forceinline__ double wsum_all(double v) {
 //     occupancy, and the solves run one frame per THREAD;
 //   * when the rmsd selection and target are the align selection and target, the minimal RMSD is
 //     sqrt((Ga + Gb - 2 lambda_max) / N) and the residual pass is not needed at all.
+constexpr int SW_THREADS = 256;
+
+__device__ __forceinline__ double wsum_all(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 constexpr int SW_FPW = 2;  // frames per warp: every load of the fp64 reference from L1 serves two frames
 
 struct CovArgs {
@@ -490,12 +378,14 @@ void to_soa(const double* xyz, size_t n, size_t Npad, bool centre, std::vector<d
     }
 }
 
-int grid_for(uint32_t F, bool accum) {
-  int dev = 0, sms = 148;
+int grid_accum(uint32_t F, int smem) {  // as many CTAs as the shared-memory accumulators allow
+  int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int g = accum ? sms * 2 : sms * 16;
-  return (int)((F < (uint32_t)g) ? F : (uint32_t)g);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accum, ST, (size_t)smem);
+  if (per_sm < 1) per_sm = 1;
+  const uint32_t g = (uint32_t)(sms * per_sm);
+  return (int)(F < g ? F : g);
 }
 
 template <class K>
@@ -620,7 +510,7 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
   const size_t F = align->F, Na = align->N, NpA = align->Npad, Nr = rs->N, NpR = rs->Npad;
   const int smemA = smem_for_accum(NpA), smemR = smem_for_accum(NpR);
   if (smemA > 200 * 1024 || smemR > 200 * 1024) return LOOSB200_ERR_UNSUPPORTED;
-  LB_CUDA(cudaFuncSetAttribute(k_stream, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  LB_CUDA(cudaFuncSetAttribute(k_accum, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                smemA > smemR ? smemA : smemR));
 
   double *dT = nullptr, *dAvg = nullptr, *dAvgR = nullptr, *dXf = nullptr, *dOut = nullptr, *dScal = nullptr, *dRc = nullptr, *dCov = nullptr;
@@ -659,17 +549,12 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
   cudaMemcpyAsync(dScal, scal, sizeof(scal), cudaMemcpyHostToDevice, st);
   cudaEventRecord(align->timing.ev[1], st);
 
-  StreamArgs a;
-  memset(&a, 0, sizeof(a));
-  a.rawA = align->raw; a.NpadA = NpA; a.Na = (uint32_t)Na;
-  a.rawR = rs->raw; a.NpadR = NpR; a.Nr = (uint32_t)Nr;
-  a.refA = dT; a.xf = dXf; a.out_rmsd = dOut; a.F = (uint32_t)F;
   int iter = 0, launches = 0;
   double rms = 0.0;
   cudaError_t e = cudaSuccess;
   do {
     // one iteration = covariance of every frame with the current target (k_cov), one solve per
-    // thread (k_solve -> transforms), transformed frames summed into the new average (k_stream)
+    // thread (k_solve -> transforms), transformed frames summed into the new average (k_accum)
     cudaMemsetAsync(dAvg, 0, sizeof(double) * 3 * NpA, st);
     cudaMemcpyAsync(scal, dScal, sizeof(scal), cudaMemcpyDeviceToHost, st);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
@@ -683,8 +568,9 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
     sa.ref_g = scal[7];
     sa.F = (uint32_t)F; sa.Na = (uint32_t)Na; sa.xf = dXf;
     k_solve<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(sa);
-    a.mode = M_ACCUM; a.accum_align_set = 1; a.avg = dAvg;
-    k_stream<<<grid_for((uint32_t)F, true), ST, smemA, st>>>(a);
+    AccumArgs aa;
+    aa.raw = align->raw; aa.Npad = NpA; aa.N = (uint32_t)Na; aa.xf = dXf; aa.F = (uint32_t)F; aa.avg = dAvg;
+    k_accum<<<grid_accum((uint32_t)F, smemA), ST, smemA, st>>>(aa);
     k_finish_iter<<<1, 1024, 0, st>>>(dAvg, dT, tgt_cen, tgt_sum, dScal + 7, (uint32_t)Na, NpA, 1.0 / (double)F, rms_dev);
     launches += 4;
     cudaMemcpyAsync(&rms, rms_dev, sizeof(double), cudaMemcpyDeviceToHost, st);
@@ -694,8 +580,9 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
   if (e == cudaSuccess) {
     // averageStructure(subset, xforms, traj, indices): ensembles.cpp:91-121
     cudaMemsetAsync(dAvgR, 0, sizeof(double) * 3 * NpR, st);
-    a.mode = M_ACCUM; a.accum_align_set = 0; a.avg = dAvgR;
-    k_stream<<<grid_for((uint32_t)F, true), ST, smemR, st>>>(a);
+    AccumArgs ar;
+    ar.raw = rs->raw; ar.Npad = NpR; ar.N = (uint32_t)Nr; ar.xf = dXf; ar.F = (uint32_t)F; ar.avg = dAvgR;
+    k_accum<<<grid_accum((uint32_t)F, smemR), ST, smemR, st>>>(ar);
     k_scale<<<(unsigned)((3 * NpR + 255) / 256), 256, 0, st>>>(dAvgR, 3 * NpR, 1.0 / (double)F);
     // per-frame rmsd to the average: rmsd2ref.cpp:238-245
     k_ref_split<<<1, 1024, 0, st>>>(dAvgR, (uint32_t)Nr, NpR, dRff, dRc);
