@@ -497,10 +497,15 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t i = I * TILE_FRAMES + a_local;
       const bool i_ok = active && i < a.FA && !masked;  // a shadow tile contributes nothing
       const double ga = i_ok ? __ldg(a.gA + i) : 0.0;
+      // The ten "b" frames of this warp's column group are solved in four rounds: the lanes of a
+      // triple (al = 0, 1, 2) own frames base + al for base = 0, 3, 5, 8 (3, 2, 3, 2 frames).  Rounds
+      // 0 and 1 only need TMEM columns 0..14, so they run while the loads of columns 16..31 are in
+      // flight: the latency-bound coefficient chains and the issue-bound combine fill each other's gaps.
+      constexpr int RBASE[4] = {0, 3, 5, 8}, RCNT[4] = {3, 2, 3, 2};
       double gbq[4];  // G of the four "b" frames this lane solves against (prefetched)
 #pragma unroll
       for (int round = 0; round < 4; ++round) {
-        const uint32_t j = J * COL_TILE_FRAMES + g * FRAMES_PER_BLOCK + (round < 3 ? 3 * round + al : 9);
+        const uint32_t j = J * COL_TILE_FRAMES + g * FRAMES_PER_BLOCK + RBASE[round] + (al < RCNT[round] ? al : 0);
         gbq[round] = j < a.FB ? __ldg(a.gB + j) : 0.0;
       }
       mbar_wait<32>(&ctl->tmem_full, tphase);
@@ -508,56 +513,34 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_after();
       LB_TICK(0);  // waiting for the accumulators
 
-      // ---- drain: v[3 jb + axis'] = sum_s 2^(8s) D_s, exact (|v| < 2^58 rounds at 2^-53) ----
-      double v[30];
+      double v[32];  // v[3 jb + axis'] = sum_s 2^(8s) D_s, exact (|v| < 2^58 rounds at 2^-53)
 #pragma unroll
-      for (int c = 0; c < 30; ++c) v[c] = 0.0;
-      // ten 16-column loads, software-pipelined: load t+1 is in flight while load t is combined
-      uint32_t rb[2][16];
-      tc_ld16(tlane, rb[0]);
-#pragma unroll
-      for (int t = 0; t < 2 * NUM_CLASSES; ++t) {
-        const int s = t >> 1, h = t & 1;
-        tc_wait_ld16(rb[t & 1]);
-        if (t + 1 < 2 * NUM_CLASSES)
-          tc_ld16(tlane + (uint32_t)(((t + 1) >> 1) * CLASS_COLS + ((t + 1) & 1) * 16), rb[(t + 1) & 1]);
-        // int32 -> double without the conversion unit: the bits (0x433+8s)<<52 | (D ^ 2^31)
-        // are the double 2^(52+8s) + (D + 2^31) 2^(8s); subtracting the bias leaves D 2^(8s).
+      for (int c = 0; c < 32; ++c) v[c] = 0.0;
+      QcpPolyF polf[4];
+      float e0s[4];
+      int state[4];  // 0: no entry, 1: zero, 2: solve
+
+      // int32 -> double without the conversion unit: the bits (0x433+8s)<<52 | (D ^ 2^31)
+      // are the double 2^(52+8s) + (D + 2^31) 2^(8s); subtracting the bias leaves D 2^(8s).
+      auto combine = [&](const uint32_t (&r)[16], int s, int c0) {
         const uint32_t hi = (uint32_t)(0x433 + 8 * s) << 20;
         const double bias = __hiloint2double((int)hi, (int)0x80000000u);
 #pragma unroll
         for (int c = 0; c < 16; ++c)
-          if (16 * h + c < 30)
-            v[16 * h + c] += __hiloint2double((int)hi, (int)(rb[t & 1][c] ^ 0x80000000u)) - bias;
-      }
-      tc_fence_before();  // this warp's TMEM reads are complete
-      if (release_at == 0) { __syncwarp(); if (lane == 0) release_tmem<CL>(ctl, crank); }
-      LB_TICK(1);  // drain
-
-      // ---- fp64 phase: exchange rows inside each lane triple, build the four quartics ----
-      // On sm_100 CUDA-core fp64 shares the tensor pipe with tcgen05.mma and gets ~10 % of
-      // its throughput while MMAs run (tools/ubench_contend.cu), so the accumulators are
-      // handed back only AFTER the fp64-heavy part; the fp32 Newton recurrences, the
-      // final correction and the stores then overlap the next tile's MMAs.
-      QcpPolyF polf[4];
-      float e0s[4];
-      int state[4];  // 0: no entry, 1: zero, 2: solve
-#pragma unroll
-      for (int round = 0; round < 4; ++round) {
-        // lanes of a triple own pairs jb = 3*round + al (round 3: jb = 9, lane al == 0)
+          if (c0 + c < 30) v[c0 + c] += __hiloint2double((int)hi, (int)(r[c] ^ 0x80000000u)) - bias;
+      };
+      // exchange rows inside each lane triple and build the quartic of this lane's pair (fp64)
+      auto do_round = [&](const int round) {
+        const int cb = 3 * RBASE[round];  // first column of the round's frames
         double own[3], s1[3], s2[3], R[9];
-        if (round < 3) {
-          const int d1 = (al + 2) % 3, d2 = (al + 1) % 3;  // destination axis served at shift 1, 2
+        const int d1 = (al + 2) % 3, d2 = (al + 1) % 3;  // destination axis served at shift 1, 2
 #pragma unroll
-          for (int be = 0; be < 3; ++be) {
-            const double x0 = v[9 * round + be], x1 = v[9 * round + 3 + be], x2 = v[9 * round + 6 + be];
-            own[be] = al == 0 ? x0 : (al == 1 ? x1 : x2);
-            s1[be] = d1 == 0 ? x0 : (d1 == 1 ? x1 : x2);
-            s2[be] = d2 == 0 ? x0 : (d2 == 1 ? x1 : x2);
-          }
-        } else {
-#pragma unroll
-          for (int be = 0; be < 3; ++be) own[be] = s1[be] = s2[be] = v[27 + be];
+        for (int be = 0; be < 3; ++be) {
+          const double x0 = v[cb + be], x1 = v[cb + 3 + be];
+          const double x2 = RCNT[round] == 3 ? v[cb + 6 + be] : x0;  // two-frame rounds: lane al = 2 idles
+          own[be] = al == 0 ? x0 : (al == 1 ? x1 : x2);
+          s1[be] = d1 == 0 ? x0 : (d1 == 1 ? x1 : x2);
+          s2[be] = d2 == 0 ? x0 : (d2 == 1 ? x1 : x2);
         }
         const int src1 = tri + (al + 1) % 3, src2 = tri + (al + 2) % 3;
 #pragma unroll
@@ -568,9 +551,9 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           R[3 + be] = __shfl_sync(0xffffffffu, s1[be], src1);
           R[6 + be] = __shfl_sync(0xffffffffu, s2[be], src2);
         }
-        const int jb = round < 3 ? 3 * round + al : 9;
+        const int jb = RBASE[round] + al;
         const uint32_t j = J * COL_TILE_FRAMES + g * FRAMES_PER_BLOCK + jb;
-        const bool owner = active && (round < 3 || al == 0);
+        const bool owner = active && al < RCNT[round];
         // 0: no entry (idle lane, out of range, or j > i of the self matrix), 1: exact zero (the
         // diagonal, Tools/rmsds.cpp:359-365, or every atom at the centroid in both frames), 2: solve.
         // Idle lanes run the same arithmetic on whatever their registers hold; their results are
@@ -583,7 +566,35 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         state[round] = !in_range ? 0 : (upper ? (j == i ? 1 : 0) : (pos ? 2 : 1));
         e0s[round] = (float)(2.0 * e0 * inv_n);  // msd = y * this
         polf[round] = qcp_poly_split(qcp_poly(R, e0));
+      };
+
+      // ---- drain, software-pipelined 16-column loads: columns 0..15 of the five classes first ----
+      // On sm_100 CUDA-core fp64 shares the tensor pipe with tcgen05.mma and gets ~10 % of its
+      // throughput while MMAs run (tools/ubench_contend.cu), so the accumulators are handed back
+      // only AFTER the fp64-heavy part; the fp32 Newton recurrences, the final correction and the
+      // stores then overlap the next tile's MMAs.
+      uint32_t rb[2][16];
+      tc_ld16(tlane, rb[0]);
+#pragma unroll
+      for (int s5 = 0; s5 < NUM_CLASSES; ++s5) {
+        tc_wait_ld16(rb[s5 & 1]);
+        tc_ld16(tlane + (uint32_t)(s5 + 1 < NUM_CLASSES ? (s5 + 1) * CLASS_COLS : 16), rb[(s5 + 1) & 1]);
+        combine(rb[s5 & 1], s5, 0);
       }
+      // columns 16..31: class 0 is in flight in rb[1]
+      do_round(0);
+#pragma unroll
+      for (int s5 = 0; s5 < NUM_CLASSES; ++s5) {
+        tc_wait_ld16(rb[(s5 + 1) & 1]);
+        if (s5 + 1 < NUM_CLASSES) tc_ld16(tlane + (uint32_t)((s5 + 1) * CLASS_COLS + 16), rb[s5 & 1]);
+        combine(rb[(s5 + 1) & 1], s5, 16);
+        if (s5 == 1) do_round(1);
+      }
+      tc_fence_before();  // this warp's TMEM reads are complete
+      if (release_at == 0) { __syncwarp(); if (lane == 0) release_tmem<CL>(ctl, crank); }
+      LB_TICK(1);  // drain (+ rounds 0, 1)
+      do_round(2);
+      do_round(3);
       // pin every fp64-derived value on this side of the hand-over: without this the compiler
       // is free to sink the fp64 -> float conversions below it, into the contended region
 #pragma unroll
@@ -611,9 +622,9 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       // ---- one float-float residual correction per pair, float32 result ----
 #pragma unroll
       for (int round = 0; round < 4; ++round) {
-        const int jb = round < 3 ? 3 * round + al : 9;
+        const int jb = RBASE[round] + al;
         const int b_local = g * FRAMES_PER_BLOCK + jb;
-        const bool owner = active && (round < 3 || al == 0);
+        const bool owner = active && al < RCNT[round];
         float val = state[round] == 1 ? 0.0f : -1.0f;  // -1: "no entry"
         if (state[round] == 2) {
           bool ok;
