@@ -766,11 +766,11 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   ta.unit = exp2((double)A->unit_log2);
   ta.out = job.out; ta.ld = job.ld; ta.stats = job.stats_dev;
   ta.prof = nullptr;
-  // Short contractions: hold the accumulators until the epilogue's fp64 part is done (fp64
-  // crawls while MMAs run, and with two 128-atom stages the MMA warp would otherwise start a tile
-  // it cannot feed); long ones: hand them back right after the drain.  Measured both ways at
-  // N = 1000 and N = 3000 (profiles/r1_summary.md).
-  ta.release_at = getenv("LOOSB200_RELEASE_AT") ? (atoi(getenv("LOOSB200_RELEASE_AT")) ? 1 : 0) : (A->Kpad <= 2048 ? 1 : 0);
+  // The accumulators are handed back right after the drain (0): rounds 2 and 3 of the coefficient
+  // phase then run next to the MMAs (fp64 crawls there, but the tensor pipe is not left idle).
+  // LOOSB200_RELEASE_AT=1 holds them until the whole fp64 phase is done -- the better choice for
+  // N <= 2048 until rounds 0 and 1 were moved under the drain; now 3 % slower at N = 1000 and 3000.
+  ta.release_at = getenv("LOOSB200_RELEASE_AT") ? (atoi(getenv("LOOSB200_RELEASE_AT")) ? 1 : 0) : 0;
   const bool want_prof = getenv("LOOSB200_PROF") != nullptr;
 
   LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<1>()));
