@@ -101,8 +101,25 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_cov(const CovArgs a) {
     for (int ff = 0; ff < SW_FPW; ++ff)
 #pragma unroll
       for (int k = 0; k < 9; ++k) s[ff][k] = 0.0;
-#pragma unroll 2
-    for (uint32_t i4 = lane; i4 < a.Npad / 4; i4 += 32) {  // pad atoms are zero in frame and reference
+    // explicit two-deep pipeline: the frame loads of group i4 + 32 are issued before group i4 is
+    // consumed (the kernel is latency-bound on HBM: ncu long-scoreboard 14 per issue without it)
+    const uint32_t n4 = (uint32_t)(a.Npad / 4);
+    const float4* fb[SW_FPW];
+#pragma unroll
+    for (int ff = 0; ff < SW_FPW; ++ff)
+      fb[ff] = reinterpret_cast<const float4*>(a.raw + (size_t)(f0 + (ff < nf ? ff : 0)) * 3 * a.Npad);
+    float4 cur[SW_FPW][3], nxt[SW_FPW][3];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ff = 0; ff < SW_FPW; ++ff)
+#pragma unroll
+      for (int p = 0; p < 3; ++p) cur[ff][p] = lane < n4 ? __ldcs(fb[ff] + p * (a.Npad / 4) + lane) : zero4;
+    for (uint32_t i4 = lane; i4 < n4; i4 += 32) {  // pad atoms are zero in frame and reference
+      const uint32_t i4n = i4 + 32;
+#pragma unroll
+      for (int ff = 0; ff < SW_FPW; ++ff)
+#pragma unroll
+        for (int p = 0; p < 3; ++p) nxt[ff][p] = i4n < n4 ? __ldcs(fb[ff] + p * (a.Npad / 4) + i4n) : zero4;
       const double2 vx0 = __ldg(rx + 2 * i4), vx1 = __ldg(rx + 2 * i4 + 1);
       const double2 vy0 = __ldg(ry + 2 * i4), vy1 = __ldg(ry + 2 * i4 + 1);
       const double2 vz0 = __ldg(rz + 2 * i4), vz1 = __ldg(rz + 2 * i4 + 1);
@@ -111,8 +128,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_cov(const CovArgs a) {
 #pragma unroll
       for (int ff = 0; ff < SW_FPW; ++ff) {
         if (ff < nf) {
-          const float4* base = reinterpret_cast<const float4*>(a.raw + (size_t)(f0 + ff) * 3 * a.Npad);
-          const float4 X = __ldcs(base + i4), Y = __ldcs(base + a.Npad / 4 + i4), Z = __ldcs(base + a.Npad / 2 + i4);
+          const float4 X = cur[ff][0], Y = cur[ff][1], Z = cur[ff][2];
           const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -123,6 +139,10 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_cov(const CovArgs a) {
           }
         }
       }
+#pragma unroll
+      for (int ff = 0; ff < SW_FPW; ++ff)
+#pragma unroll
+        for (int p = 0; p < 3; ++p) cur[ff][p] = nxt[ff][p];
     }
 #pragma unroll
     for (int ff = 0; ff < SW_FPW; ++ff) {
