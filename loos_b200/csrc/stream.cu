@@ -249,8 +249,24 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_resid(const ResidArgs a) {
         kap[ff][p] = (float)(w3 + w0 * (double)ucf[ff][0] + w1 * (double)ucf[ff][1] + w2 * (double)ucf[ff][2] - a.ref_c[p]);
       }
     }
-#pragma unroll 2
-    for (uint32_t i4 = lane; i4 < a.Npad / 4; i4 += 32) {
+    // same two-deep pipeline of the frame loads as k_cov
+    const uint32_t n4 = (uint32_t)(a.Npad / 4);
+    const float4* fb[SW_FPW];
+#pragma unroll
+    for (int ff = 0; ff < SW_FPW; ++ff)
+      fb[ff] = reinterpret_cast<const float4*>(a.raw + (size_t)(f0 + (ff < nf ? ff : 0)) * 3 * a.Npad);
+    float4 cur[SW_FPW][3], nxt[SW_FPW][3];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ff = 0; ff < SW_FPW; ++ff)
+#pragma unroll
+      for (int p = 0; p < 3; ++p) cur[ff][p] = lane < n4 ? __ldcs(fb[ff] + p * (a.Npad / 4) + lane) : zero4;
+    for (uint32_t i4 = lane; i4 < n4; i4 += 32) {
+      const uint32_t i4n = i4 + 32;
+#pragma unroll
+      for (int ff = 0; ff < SW_FPW; ++ff)
+#pragma unroll
+        for (int p = 0; p < 3; ++p) nxt[ff][p] = i4n < n4 ? __ldcs(fb[ff] + p * (a.Npad / 4) + i4n) : zero4;
       const float4 t0 = __ldg(rx + 2 * i4), t1 = __ldg(rx + 2 * i4 + 1);
       const float4 u0 = __ldg(ry + 2 * i4), u1 = __ldg(ry + 2 * i4 + 1);
       const float4 w0 = __ldg(rz + 2 * i4), w1 = __ldg(rz + 2 * i4 + 1);
@@ -260,8 +276,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_resid(const ResidArgs a) {
 #pragma unroll
       for (int ff = 0; ff < SW_FPW; ++ff) {
         if (ff < nf) {
-          const float4* base = reinterpret_cast<const float4*>(a.raw + (size_t)(f0 + ff) * 3 * a.Npad);
-          const float4 X = __ldcs(base + i4), Y = __ldcs(base + a.Npad / 4 + i4), Z = __ldcs(base + a.Npad / 2 + i4);
+          const float4 X = cur[ff][0], Y = cur[ff][1], Z = cur[ff][2];
           const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
           float part = 0.0f;
 #pragma unroll
@@ -278,6 +293,10 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_resid(const ResidArgs a) {
           d[ff] += (double)part;
         }
       }
+#pragma unroll
+      for (int ff = 0; ff < SW_FPW; ++ff)
+#pragma unroll
+        for (int p = 0; p < 3; ++p) cur[ff][p] = nxt[ff][p];
     }
 #pragma unroll
     for (int ff = 0; ff < SW_FPW; ++ff) {
