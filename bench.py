@@ -60,6 +60,7 @@ class ClockSampler(threading.Thread):
         self._go = threading.Event()
         self._ready = threading.Event()
         self.max_mhz = None
+        self.query_ms = []
 
     def kick(self):
         self._go.set()
@@ -76,23 +77,27 @@ class ClockSampler(threading.Thread):
             h = nv.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             self._ready.set()
-            while not self._stop_ev.is_set():
-                if not self._go.wait(0.05):
-                    continue
+            while True:
+                self._go.wait()          # blocking: a polling wait costs the main thread GIL hand-offs
                 self._go.clear()
+                if self._stop_ev.is_set():
+                    break
                 time.sleep(self.delay)
+                t_q = time.perf_counter()
                 clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
                     rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.rows.append((clk, rs))
+                self.query_ms.append(1e3 * (time.perf_counter() - t_q))
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
             self._ready.set()
 
     def stop(self):
         self._stop_ev.set()
+        self._go.set()
         self.join(timeout=2.0)
         try:
             import pynvml as nv
@@ -105,7 +110,7 @@ class ClockSampler(threading.Thread):
         sm = sorted(c for c, _ in self.rows)
         reasons = sorted(n for n, bit in names.items() if any(r & bit for _, r in self.rows))
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                "samples": len(sm),
+                "samples": len(sm), "nvml_query_ms": [round(q, 1) for q in self.query_ms],
                 "how": "NVML, one sample %.0f ms into every timed step (while its kernel runs)" % (self.delay * 1e3)}
 
 
@@ -282,13 +287,18 @@ def main():
         out_dev = torch.empty((len(rows), F), dtype=torch.float32, device=dev)
 
     def step_device():
+        t_a = time.perf_counter()
         fs = lb.FrameSet(X)
+        t_b = time.perf_counter()
         if world == 1:
             _, st = lb.rmsds(fs, out=out_dev, engine=args.engine)
         else:
             _, _, st = rmsds_part(fs, rank, world, out=out_dev, engine=args.engine)
         t = fs.last_timing()
+        t_c = time.perf_counter()
         fs.close()
+        if os.environ.get("LOOSB200_BENCH_TRACE"):
+            sys.stderr.write("  stage %.1f ms, rmsds %.1f ms, close %.1f ms\n" % (1e3 * (t_b - t_a), 1e3 * (t_c - t_b), 1e3 * (time.perf_counter() - t_c)))
         return st, t
 
     t_est = 0.4
@@ -298,7 +308,7 @@ def main():
         step_device()
         t_est = time.perf_counter() - t_w
     # one clock sample a third of the way into every timed step
-    sampler = ClockSampler(local, delay=min(0.12, t_est / 3)) if rank == 0 else None
+    sampler = ClockSampler(local, delay=min(0.12, t_est / 3)) if rank == 0 and not os.environ.get("LOOSB200_NO_SAMPLER") else None
     if sampler:
         sampler.start()
         sampler.wait_ready()
@@ -309,7 +319,10 @@ def main():
     for _ in range(args.steps):
         if sampler:
             sampler.kick()
+        t_s = time.perf_counter()
         st, (ms_main, ms_other, nl) = step_device()
+        if os.environ.get("LOOSB200_BENCH_TRACE"):
+            sys.stderr.write("step wall %.1f ms, kernel %.1f ms, other kernels %.1f ms\n" % (1e3 * (time.perf_counter() - t_s), ms_main, ms_other))
         kern_ms += ms_main
         launches += nl + 3          # + stage, unit, quantise kernels of the FrameSet
     e1.record()

@@ -23,7 +23,7 @@ struct DevCache {
   size_t cached_bytes = 0;
 };
 DevCache& cache() { static DevCache c; return c; }
-constexpr size_t CACHE_MIN_BLOCK = 1u << 20;          // small blocks are not worth keeping
+constexpr size_t CACHE_MAX_PER_KEY = 64;               // blocks kept per (device, size)
 constexpr size_t CACHE_MAX_TOTAL = (size_t)96 << 30;  // never sit on more than this
 }  // namespace
 
@@ -65,7 +65,8 @@ void dev_release(void* p) {
     std::lock_guard<std::mutex> g(c.mu);
     auto it = c.live.find(p);
     if (it != c.live.end()) { info = it->second; c.live.erase(it); }
-    if (info.first >= 0 && info.second >= CACHE_MIN_BLOCK && c.cached_bytes + info.second <= CACHE_MAX_TOTAL) {
+    if (info.first >= 0 && c.cached_bytes + info.second <= CACHE_MAX_TOTAL &&
+        c.free_blocks[info].size() < CACHE_MAX_PER_KEY) {
       c.free_blocks[info].push_back(p);
       c.cached_bytes += info.second;
       return;
@@ -223,16 +224,18 @@ static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool sym
   float* d_out = nullptr;
   double* d_stats = nullptr;
   cudaStream_t copy_stream = nullptr;
+  std::vector<void*> scratch;  // per-launch device scratch of the engines, released after the final sync
   std::vector<cudaEvent_t> evs(B.bands.size(), nullptr);
   auto cleanup = [&]() {
-    cudaFree(d_rows); cudaFree(d_prefix); cudaFree(d_stats);
+    dev_release(d_rows); dev_release(d_prefix); dev_release(d_stats);
+    for (void* p : scratch) dev_release(p);
     if (okind == OutKind::Host) dev_release(d_out);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     for (auto e : evs) if (e) cudaEventDestroy(e);
   };
-  bool ok = cudaMalloc(&d_rows, sizeof(uint32_t) * std::max<size_t>(1, B.rows.size())) == cudaSuccess &&
-            cudaMalloc(&d_prefix, sizeof(uint32_t) * std::max<size_t>(1, B.prefix.size())) == cudaSuccess &&
-            cudaMalloc(&d_stats, 2 * sizeof(double)) == cudaSuccess;
+  bool ok = dev_alloc_t(&d_rows, sizeof(uint32_t) * std::max<size_t>(1, B.rows.size())) == cudaSuccess &&
+            dev_alloc_t(&d_prefix, sizeof(uint32_t) * std::max<size_t>(1, B.prefix.size())) == cudaSuccess &&
+            dev_alloc_t(&d_stats, 2 * sizeof(double)) == cudaSuccess;
   if (ok && okind == OutKind::Host) {
     const size_t n = packed ? out_rows * dev_ld : out_cols * dev_ld;
     ok = dev_alloc_t(&d_out, sizeof(float) * std::max<size_t>(1, n)) == cudaSuccess &&
@@ -262,6 +265,7 @@ static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool sym
     job.packed_rows = packed;
     job.out = d_out ? (packed ? d_out + (size_t)bd.r0 * TILE_FRAMES * dev_ld : d_out) : nullptr;
     job.stats_dev = stats ? d_stats : nullptr;
+    job.scratch = &scratch;
     while (a->timing.kev.size() < 2 * (k + 1)) { cudaEvent_t e = nullptr; cudaEventCreate(&e); a->timing.kev.push_back(e); }
     job.ev_k0 = a->timing.kev[2 * k]; job.ev_k1 = a->timing.kev[2 * k + 1];
     a->timing.kev_used = (int)(2 * (k + 1));

@@ -112,6 +112,8 @@ struct PairJob {
   bool packed_rows;           // out row index = position in the launch's row list
   double* stats_dev;          // [2]: sum, max-as-bits ; may be null
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // optional: recorded right around the contraction kernel
+  std::vector<void*>* scratch = nullptr;  // device scratch (dev_alloc) the engine leaves for the caller to
+                                          // dev_release once the stream has been synchronised
 };
 
 int ensure_quantised(loosb200_frames* h, int force_unit_log2 /* INT_MIN: auto */);

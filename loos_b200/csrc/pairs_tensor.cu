@@ -747,10 +747,15 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
 
   uint4* d_sbl = nullptr;
   uint32_t* d_prefix = nullptr;
-  LB_CUDA(cudaMallocAsync(&d_sbl, sizeof(uint4) * sbl.size(), st));
-  LB_CUDA(cudaMallocAsync(&d_prefix, sizeof(uint32_t) * prefix.size(), st));
+  // scratch from the buffer cache; the caller releases it after synchronising the stream
+  if (!job.scratch) return LOOSB200_ERR_INVALID;
+  LB_CUDA(dev_alloc_t(&d_sbl, sizeof(uint4) * sbl.size()));
+  job.scratch->push_back(d_sbl);
+  LB_CUDA(dev_alloc_t(&d_prefix, sizeof(uint32_t) * prefix.size()));
+  job.scratch->push_back(d_prefix);
   uint32_t* d_counter = nullptr;
-  LB_CUDA(cudaMallocAsync(&d_counter, sizeof(uint32_t), st));
+  LB_CUDA(dev_alloc_t(&d_counter, sizeof(uint32_t)));
+  job.scratch->push_back(d_counter);
   LB_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), st));
   LB_CUDA(cudaMemcpyAsync(d_sbl, sbl.data(), sizeof(uint4) * sbl.size(), cudaMemcpyHostToDevice, st));
   LB_CUDA(cudaMemcpyAsync(d_prefix, prefix.data(), sizeof(uint32_t) * prefix.size(), cudaMemcpyHostToDevice, st));
@@ -780,7 +785,7 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sms / CLs, slots) * CLs;
   if (want_prof) {
-    LB_CUDA(cudaMalloc(&ta.prof, sizeof(long long) * grid * 14 * 8));
+    LB_CUDA(dev_alloc_t(&ta.prof, sizeof(long long) * grid * 14 * 8));
     LB_CUDA(cudaMemsetAsync(ta.prof, 0, sizeof(long long) * grid * 14 * 8, st));
   }
   if (job.ev_k0) cudaEventRecord(job.ev_k0, st);
@@ -802,7 +807,7 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
     std::vector<long long> hp((size_t)grid * 14 * 8);
     LB_CUDA(cudaMemcpyAsync(hp.data(), ta.prof, sizeof(long long) * hp.size(), cudaMemcpyDeviceToHost, st));
     LB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(ta.prof);
+    dev_release(ta.prof);
     const char* names_e[7] = {"wait_acc", "drain", "exch+poly", "newton", "polish", "barrier", "stores"};
     const char* names_m[3] = {"wait_tmem", "wait_operands", "issue"};
     const double ntl = (double)job.n_tiles * TILE_FRAMES / COL_TILE_FRAMES / grid;  // approximate
@@ -812,9 +817,6 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
     for (int k = 0; k < 7; ++k) { double s = 0; for (unsigned c = 0; c < grid; ++c) for (int w = 2; w < 14; ++w) s += hp[((size_t)c * 14 + w) * 8 + k]; fprintf(stderr, " %s=%.0f", names_e[k], s / grid / 12 / ntl); }
     fprintf(stderr, "\n");
   }
-  LB_CUDA(cudaFreeAsync(d_sbl, st));
-  LB_CUDA(cudaFreeAsync(d_prefix, st));
-  LB_CUDA(cudaFreeAsync(d_counter, st));
   if (launches) *launches = 1;
   return LOOSB200_OK;
 }

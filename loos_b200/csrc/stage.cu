@@ -183,8 +183,8 @@ int ensure_quantised(loosb200_frames* h, int force_unit_log2) {
   const size_t bytes = (size_t)NUM_SLICES * h->rows_total * h->Kpad;
   if (!h->q8) {
     if (dev_alloc_t(&h->q8, bytes) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
-    if (cudaMalloc(&h->gq, sizeof(double) * h->F) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
-    if (cudaMalloc(&h->unit_log2_dev, 2 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
+    if (dev_alloc_t(&h->gq, sizeof(double) * h->F) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
+    if (dev_alloc_t(&h->unit_log2_dev, 2 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
   }
   LB_CUDA(cudaMemsetAsync(h->q8, 0, bytes, h->stream));
   k_unit<<<1, 1024, 0, h->stream>>>(h->maxabs, h->F, force_unit_log2, h->unit_log2_dev);
@@ -232,9 +232,9 @@ static int alloc_handle(loosb200_frames** out, size_t F, size_t N, int device) {
   if ((e = cudaSetDevice(device)) != cudaSuccess) { delete h; return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__); }
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
   bool ok = dev_alloc_t(&h->raw, sizeof(float) * F * 3 * h->Npad) == cudaSuccess &&
-            cudaMalloc(&h->centroid, sizeof(double) * F * 3) == cudaSuccess &&
-            cudaMalloc(&h->gd, sizeof(double) * F) == cudaSuccess &&
-            cudaMalloc(&h->maxabs, sizeof(float) * F) == cudaSuccess;
+            dev_alloc_t(&h->centroid, sizeof(double) * F * 3) == cudaSuccess &&
+            dev_alloc_t(&h->gd, sizeof(double) * F) == cudaSuccess &&
+            dev_alloc_t(&h->maxabs, sizeof(float) * F) == cudaSuccess;
   for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreate(&h->timing.ev[i]) == cudaSuccess;
   if (!ok) { cudaGetLastError(); loosb200_free(h); return LOOSB200_ERR_NOMEM; }
   *out = h;
@@ -268,7 +268,7 @@ static int check_stage_args(loosb200_frames** out, const void* xyz, size_t F, si
 static int upload_sel(const uint32_t* sel, size_t nsel, uint32_t** dev, cudaStream_t st) {
   *dev = nullptr;
   if (!sel) return LOOSB200_OK;
-  if (cudaMalloc(dev, sizeof(uint32_t) * nsel) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
+  if (dev_alloc_t(dev, sizeof(uint32_t) * nsel) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
   LB_CUDA(cudaMemcpyAsync(*dev, sel, sizeof(uint32_t) * nsel, cudaMemcpyHostToDevice, st));
   return LOOSB200_OK;
 }
@@ -293,7 +293,7 @@ extern "C" int loosb200_stage_frames_device(loosb200_frames** out, const float* 
   cudaEventRecord(h->timing.ev[3], h->stream);
   cudaError_t e = cudaStreamSynchronize(h->stream);
   if (e == cudaSuccess) e = cudaGetLastError();
-  if (sel_dev) cudaFree(sel_dev);
+  if (sel_dev) dev_release(sel_dev);
   if (e != cudaSuccess) { loosb200_free(h); return cuda_fail(e, "k_stage", __FILE__, __LINE__); }
   h->timing.launches = 1; h->timing.valid = true;
   *out = h;
@@ -323,7 +323,7 @@ struct Stager {
       if (staged[i]) cudaEventDestroy(staged[i]);
     }
     if (copy_stream) cudaStreamDestroy(copy_stream);
-    if (sel_dev) cudaFree(sel_dev);
+    if (sel_dev) dev_release(sel_dev);
     cudaGetLastError();
   }
 };
@@ -439,8 +439,8 @@ extern "C" void loosb200_free(loosb200_frames* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->stager) { delete h->stager; h->stager = nullptr; }
-  dev_release(h->raw); cudaFree(h->centroid); cudaFree(h->gd); cudaFree(h->maxabs);
-  dev_release(h->q8); cudaFree(h->gq); cudaFree(h->unit_log2_dev);
+  dev_release(h->raw); dev_release(h->centroid); dev_release(h->gd); dev_release(h->maxabs);
+  dev_release(h->q8); dev_release(h->gq); dev_release(h->unit_log2_dev);
   for (int i = 0; i < 4; ++i) if (h->timing.ev[i]) cudaEventDestroy(h->timing.ev[i]);
   for (cudaEvent_t e : h->timing.kev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);

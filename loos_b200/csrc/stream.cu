@@ -480,17 +480,17 @@ extern "C" int loosb200_rmsd2ref(loosb200_frames* align, loosb200_frames* rmsd_s
 
   double *dA = nullptr, *dR = nullptr, *dOut = nullptr, *dXf = nullptr, *dRc = nullptr, *dCov = nullptr;
   float2* dRff = nullptr;
-  bool ok = cudaMalloc(&dOut, sizeof(double) * F) == cudaSuccess;
+  bool ok = dev_alloc_t(&dOut, sizeof(double) * F) == cudaSuccess;
   if (ok && !same)
-    ok = cudaMalloc(&dR, sizeof(double) * soaR.size()) == cudaSuccess &&
-         cudaMalloc(&dRff, sizeof(float2) * soaR.size()) == cudaSuccess &&
-         cudaMalloc(&dRc, sizeof(double) * 3) == cudaSuccess;
+    ok = dev_alloc_t(&dR, sizeof(double) * soaR.size()) == cudaSuccess &&
+         dev_alloc_t(&dRff, sizeof(float2) * soaR.size()) == cudaSuccess &&
+         dev_alloc_t(&dRc, sizeof(double) * 3) == cudaSuccess;
   if (ok && ref_align)
-    ok = cudaMalloc(&dA, sizeof(double) * soaA.size()) == cudaSuccess &&
-         cudaMalloc(&dCov, sizeof(double) * 9 * F) == cudaSuccess;
-  if (ok && need_xf) ok = cudaMalloc(&dXf, sizeof(double) * 16 * F) == cudaSuccess;
+    ok = dev_alloc_t(&dA, sizeof(double) * soaA.size()) == cudaSuccess &&
+         dev_alloc_t(&dCov, sizeof(double) * 9 * F) == cudaSuccess;
+  if (ok && need_xf) ok = dev_alloc_t(&dXf, sizeof(double) * 16 * F) == cudaSuccess;
   auto cleanup = [&]() {
-    cudaFree(dA); cudaFree(dR); cudaFree(dRff); cudaFree(dRc); cudaFree(dOut); cudaFree(dXf); cudaFree(dCov);
+    dev_release(dA); dev_release(dR); dev_release(dRff); dev_release(dRc); dev_release(dOut); dev_release(dXf); dev_release(dCov);
   };
   if (!ok) { cudaGetLastError(); cleanup(); return LOOSB200_ERR_NOMEM; }
   cudaEventRecord(align->timing.ev[0], st);
@@ -554,17 +554,17 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
 
   double *dT = nullptr, *dAvg = nullptr, *dAvgR = nullptr, *dXf = nullptr, *dOut = nullptr, *dScal = nullptr, *dRc = nullptr, *dCov = nullptr;
   float2* dRff = nullptr;
-  bool ok = cudaMalloc(&dT, sizeof(double) * 3 * NpA) == cudaSuccess &&
-            cudaMalloc(&dAvg, sizeof(double) * 3 * NpA) == cudaSuccess &&
-            cudaMalloc(&dAvgR, sizeof(double) * 3 * NpR) == cudaSuccess &&
-            cudaMalloc(&dRff, sizeof(float2) * 3 * NpR) == cudaSuccess &&
-            cudaMalloc(&dRc, sizeof(double) * 3) == cudaSuccess &&
-            cudaMalloc(&dXf, sizeof(double) * 16 * F) == cudaSuccess &&
-            cudaMalloc(&dOut, sizeof(double) * F) == cudaSuccess &&
-            cudaMalloc(&dCov, sizeof(double) * 9 * F) == cudaSuccess &&
-            cudaMalloc(&dScal, sizeof(double) * 8) == cudaSuccess;
+  bool ok = dev_alloc_t(&dT, sizeof(double) * 3 * NpA) == cudaSuccess &&
+            dev_alloc_t(&dAvg, sizeof(double) * 3 * NpA) == cudaSuccess &&
+            dev_alloc_t(&dAvgR, sizeof(double) * 3 * NpR) == cudaSuccess &&
+            dev_alloc_t(&dRff, sizeof(float2) * 3 * NpR) == cudaSuccess &&
+            dev_alloc_t(&dRc, sizeof(double) * 3) == cudaSuccess &&
+            dev_alloc_t(&dXf, sizeof(double) * 16 * F) == cudaSuccess &&
+            dev_alloc_t(&dOut, sizeof(double) * F) == cudaSuccess &&
+            dev_alloc_t(&dCov, sizeof(double) * 9 * F) == cudaSuccess &&
+            dev_alloc_t(&dScal, sizeof(double) * 8) == cudaSuccess;
   auto cleanup = [&]() {
-    cudaFree(dT); cudaFree(dAvg); cudaFree(dAvgR); cudaFree(dRff); cudaFree(dRc); cudaFree(dXf); cudaFree(dOut); cudaFree(dScal); cudaFree(dCov);
+    dev_release(dT); dev_release(dAvg); dev_release(dAvgR); dev_release(dRff); dev_release(dRc); dev_release(dXf); dev_release(dOut); dev_release(dScal); dev_release(dCov);
   };
   if (!ok) { cudaGetLastError(); cleanup(); return LOOSB200_ERR_NOMEM; }
   double* tgt_cen = dScal; double* tgt_sum = dScal + 3; double* rms_dev = dScal + 6;

@@ -5,7 +5,7 @@ from loos_b200.synth import synth_frames_torch
 F, N = 100000, 1000
 X = synth_frames_torch(F, N, device="cuda")
 out = torch.empty((F, F), dtype=torch.float32, device="cuda")
-for it in range(3):
+for it in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     fs = lb.FrameSet(X); torch.cuda.synchronize(); t1 = time.perf_counter()
     e = fs.unit_log2(); torch.cuda.synchronize(); t2 = time.perf_counter()
