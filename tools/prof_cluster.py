@@ -1,4 +1,4 @@
-"""One launch of k_pairs_tensor with the 2-CTA cluster (multicast "a" tile) and one without,
+"""One launch of k_pairs_tensor per launch shape (LOOSB200_CLUSTER=2: CTA pairs, 1: independent CTAs),
 for an ncu metrics pass: ncu --metrics ... python tools/prof_cluster.py [F]"""
 import os, sys, torch
 sys.path.insert(0, "/root/repo")
