@@ -898,6 +898,25 @@ void writeMatrix(std::ostream& os, const float* M, size_t m, size_t n, size_t ld
   os.flush();
 }
 
+void writeNpy(const std::string& path, const float* M, size_t m, size_t n, size_t ld) {
+  std::ofstream f(path.c_str(), std::ios::binary);
+  if (!f) throw Error("Error- cannot open " + path + " for writing");
+  std::string dict = "{'descr': '<f4', 'fortran_order': True, 'shape': (" + std::to_string(m) + ", " + std::to_string(n) + "), }";
+  size_t total = 10 + dict.size() + 1;          // magic(6) + version(2) + header length(2) + dict + newline
+  dict.append((64 - total % 64) % 64, ' ');     // data starts on a 64-byte boundary
+  dict += '\n';
+  if (dict.size() > 65535) throw Error("Error- npy header too long");
+  const unsigned char head[10] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0, (unsigned char)(dict.size() & 0xff), (unsigned char)(dict.size() >> 8)};
+  f.write((const char*)head, 10);
+  f.write(dict.data(), (std::streamsize)dict.size());
+  if (ld == m) {
+    f.write((const char*)M, (std::streamsize)(m * n * sizeof(float)));
+  } else {
+    for (size_t j = 0; j < n; ++j) f.write((const char*)(M + j * ld), (std::streamsize)(m * sizeof(float)));
+  }
+  if (!f) throw Error("Error- write to " + path + " failed");
+}
+
 std::vector<float> readMatrix(std::istream& is, size_t* m_out, size_t* n_out) {
   std::string line;
   int m = 0, n = 0;

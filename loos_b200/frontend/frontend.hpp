@@ -132,6 +132,10 @@ void writeMatrix(std::ostream& os, const float* M, size_t m, size_t n, size_t ld
 // whitespace-separated values, row by row.  Returns column-major float32 (ld = m), i.e. exactly
 // what writeMatrix was given.  Errors carry the reference's messages.
 std::vector<float> readMatrix(std::istream& is, size_t* m, size_t* n);
+// Binary side channel (extension): the same column-major float32 matrix as a NumPy
+// .npy file (format 1.0, fortran_order True) -- 4 bytes per value instead of ~5 of text and no
+// formatting cost; numpy.load gives M[i, j].
+void writeNpy(const std::string& path, const float* M, size_t m, size_t n, size_t ld);
 std::string invocationHeader(int argc, char* argv[]);
 // default-floatfield formatting of a double with `precision` significant digits
 // (std::ostream default: 6), as rmsd2ref prints its values.

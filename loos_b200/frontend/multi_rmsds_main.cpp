@@ -18,6 +18,7 @@ int main(int argc, char* argv[]) {
   o.add("noout", 'N', "0", "Do not output the matrix (i.e. only calc pair-wise RMSD stats)", true);
   o.add("threads", 0, "1", "Number of threads to use (0=all available); accepted, unused on the GPU path");
   o.add("stats", 0, "0", "Show some statistics for matrix", true);
+  o.add("binary", 0, "", "Also write the matrix as float32 NumPy .npy to this file (extension; written even with --noout 1)");
   o.add("precision", 'p', "2", "Write out matrix coefficients with this many digits.");
   o.addPositional("model", 1); o.addPositional("traj", -1);
   try {
@@ -54,9 +55,12 @@ int main(int argc, char* argv[]) {
     });
     if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
     std::vector<float> M;
-    if (!noop) M.assign(F * F, 0.0f);
+    const std::string binary = o.str("binary");
+    const bool want_m = !noop || !binary.empty();
+    if (want_m) M.assign(F * F, 0.0f);
     loosb200_stats st;
-    check(loosb200_rmsds_self(A.h, noop ? nullptr : M.data(), F, &st, engine), "multi-rmsds");
+    check(loosb200_rmsds_self(A.h, want_m ? M.data() : nullptr, F, &st, engine), "multi-rmsds");
+    if (!binary.empty()) writeNpy(binary, M.data(), F, F, F);
     if (verbosity || noop || stats) {
       char line[128];
       snprintf(line, sizeof(line), "Max rmsd = %.4f, avg rmsd = %.4f\n", st.max, st.count ? st.sum / (double)st.count : 0.0);

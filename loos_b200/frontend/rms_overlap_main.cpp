@@ -50,6 +50,7 @@ int main(int argc, char* argv[]) {
   o.add("threads", 0, "1", "Number of threads to use (0=all available); accepted, unused on the GPU path");
   o.add("cutoff", 'c', "-1", "Outputs fraction of frame-pairs below cutoff.");
   o.add("stats", 0, "0", "Show some statistics for matrix", true);
+  o.add("binary", 0, "", "Also write the matrix as float32 NumPy .npy to this file (extension; written even with --noout 1)");
   o.add("precision", 'p', "2", "Write out matrix coefficients with this many digits.");
   o.addPositional("model", 1);
   try {
@@ -90,11 +91,13 @@ int main(int argc, char* argv[]) {
     }
     if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
     const bool want_fraction = cutoff > 0;
-    const bool need_matrix = !noop || want_fraction;
+    const std::string binary = o.str("binary");
+    const bool need_matrix = !noop || want_fraction || !binary.empty();
     std::vector<float> M;
     if (need_matrix) M.assign(F[0] * F[1], 0.0f);
     loosb200_stats st;
     check(loosb200_rmsds_cross(fs[0].h, fs[1].h, need_matrix ? M.data() : nullptr, F[0], &st, engine), "rms-overlap");
+    if (!binary.empty()) writeNpy(binary, M.data(), F[0], F[1], F[0]);
     if (verbosity || noop || stats || want_fraction) {
       char line[512];
       if (want_fraction) {  // showFractionalStats, bug-for-bug (see the header comment)

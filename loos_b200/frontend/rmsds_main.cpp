@@ -19,6 +19,7 @@ int main(int argc, char* argv[]) {
   o.add("skip2", 0, "0", "Skip n-frames of second trajectory");
   o.add("range2", 0, "", "Matlab-style range of frames to use from second trajectory");
   o.add("stats", 0, "0", "Show some statistics for matrix", true);
+  o.add("binary", 0, "", "Also write the matrix as float32 NumPy .npy to this file (extension; written even with --noout 1)");
   o.add("precision", 'p', "2", "Write out matrix coefficients with this many digits.");
   o.addPositional("model1", 1); o.addPositional("traj1", 1); o.addPositional("model2", 1); o.addPositional("traj2", 1);
   try {
@@ -30,6 +31,8 @@ int main(int argc, char* argv[]) {
     }
     const long verbosity = std::stol(o.str("verbosity"));
     const bool noop = o.flag("noout"), stats = o.flag("stats");
+    const std::string binary = o.str("binary");
+    const bool want_m = !noop || !binary.empty();
     const int device = (int)o.uns("gpu"), engine = engineOf(o);
 
     Model model = readPDB(o.str("model1"));
@@ -49,8 +52,8 @@ int main(int argc, char* argv[]) {
     loosb200_stats st;
     if (!o.has("model2")) {
       if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
-      if (!noop) M.assign(rows * cols, 0.0f);
-      check(loosb200_rmsds_self(A.h, noop ? nullptr : M.data(), rows, &st, engine), "rmsds");
+      if (want_m) M.assign(rows * cols, 0.0f);
+      check(loosb200_rmsds_self(A.h, want_m ? M.data() : nullptr, rows, &st, engine), "rmsds");
     } else {
       Model model2 = readPDB(o.str("model2"));
       const std::shared_ptr<Trajectory> traj2p = openTrajectory(o.str("traj2"), (uint32_t)model2.size());
@@ -64,14 +67,15 @@ int main(int argc, char* argv[]) {
       stageTrajectory(B, traj2, indices2, model2.size(), sel2, device);
       cols = indices2.size();
       if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
-      if (!noop) M.assign(rows * cols, 0.0f);
-      check(loosb200_rmsds_cross(A.h, B.h, noop ? nullptr : M.data(), rows, &st, engine), "rmsds");
+      if (want_m) M.assign(rows * cols, 0.0f);
+      check(loosb200_rmsds_cross(A.h, B.h, want_m ? M.data() : nullptr, rows, &st, engine), "rmsds");
     }
     if (verbosity || noop || stats) {  // showStatsHalf / showStatsWhole, :425-456
       char line[128];
       snprintf(line, sizeof(line), "Max rmsd = %.4f, avg rmsd = %.4f\n", st.max, st.count ? st.sum / (double)st.count : 0.0);
       std::cerr << line;
     }
+    if (!binary.empty()) writeNpy(binary, M.data(), rows, cols, rows);
     if (!noop) {
       std::cout << "# " << header << std::endl;
       writeMatrix(std::cout, M.data(), rows, cols, rows, (unsigned)o.uns("precision"));

@@ -208,3 +208,23 @@ def test_amber_netcdf_trajectories_give_the_same_matrices(files, tmp_path):
     a, _ = run("rmsd2ref", "--target", d / "target.pdb", d / "model.pdb", d / "all.dcd")
     b, _ = run("rmsd2ref", "--target", d / "target.pdb", d / "model.pdb", tmp_path / "all.nc")
     assert body(a) == body(b)
+
+
+def test_binary_side_channel(files, tmp_path):
+    """--binary writes the float32 matrix as .npy (fortran order): identical to the values behind the
+    text at -p 9, also with --noout 1, for the self and the cross matrix."""
+    d = files["d"]
+    npy = tmp_path / "m.npy"
+    out, _ = run("rmsds", "-p", "9", "--binary", npy, d / "model.pdb", d / "all.dcd")
+    _, M, _ = parse_matrix(out)
+    B = np.load(npy)
+    assert B.dtype == np.float32 and B.flags["F_CONTIGUOUS"] and B.shape == M.shape
+    assert np.array_equal(B, M.astype(np.float32))
+    out, err = run("rmsds", "-N", "1", "--binary", npy, "--skip2", "100", d / "model.pdb", d / "a.dcd", d / "model.pdb", d / "all.dcd")
+    assert out == "" and err.startswith("Max rmsd")
+    C2 = np.load(npy)
+    assert C2.shape == (70, 50)
+    out, _ = run("rmsds", "-p", "9", "--skip2", "100", d / "model.pdb", d / "a.dcd", d / "model.pdb", d / "all.dcd")
+    assert np.array_equal(C2, parse_matrix(out)[1].astype(np.float32))
+    run("multi-rmsds", "-N", "1", "--binary", npy, d / "model.pdb", d / "a.dcd", d / "b.dcd")
+    assert np.load(npy).shape == (115, 115)
