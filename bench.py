@@ -31,6 +31,9 @@ WORKLOADS = {
     "c1": (1000, 500, "C1 rmsds all-to-all 1,000 frames x 500 atoms"),
     "c3": (20000, 3000, "C3 rmsds all-to-all 20,000 frames x 3,000 atoms"),
     "c4": (100000, 1000, "C4 rmsds all-to-all 100,000 frames x 1,000 atoms"),
+    # multi-rmsds of 8 trajectories x 25,000 frames = 200,000 composite frames; the 160 GB result only
+    # fits as packed row blocks over >= 2 GPUs (run with --gpus 8 --no-e2e)
+    "c5": (200000, 5000, "C5 multi-rmsds all-to-all 8 x 25,000 frames x 5,000 atoms"),
 }
 METRIC = "frame-pairs/sec all-to-all RMSD"
 UNIT = "frame-pairs/s"

@@ -41,17 +41,46 @@ __global__ void __launch_bounds__(ST) k_accum(const AccumArgs a) {
   const int tid = threadIdx.x;
   for (size_t i = tid; i < 3 * a.Npad; i += ST) acc_s[i] = 0.0;
   __syncthreads();  // the zeroing and the flush stride over all three planes, the frame loop does not
+  const uint32_t n4 = (uint32_t)(a.Npad / 4);  // a thread owns the float4 groups tid, tid + ST, ...
+  double2* ax = reinterpret_cast<double2*>(acc_s);
+  double2* ay = reinterpret_cast<double2*>(acc_s + a.Npad);
+  double2* az = reinterpret_cast<double2*>(acc_s + 2 * a.Npad);
   for (uint32_t f = blockIdx.x; f < a.F; f += gridDim.x) {
     double W[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) W[k] = __ldg(a.xf + (size_t)f * 16 + k);
-    const float* px = a.raw + (size_t)f * 3 * a.Npad;
-    const float* py = px + a.Npad, *pz = py + a.Npad;
-    for (uint32_t i = tid; i < a.N; i += ST) {
-      const double x = __ldcs(px + i), y = __ldcs(py + i), z = __ldcs(pz + i);
-      acc_s[i] += W[0] * x + W[1] * y + W[2] * z + W[3];
-      acc_s[a.Npad + i] += W[4] * x + W[5] * y + W[6] * z + W[7];
-      acc_s[2 * a.Npad + i] += W[8] * x + W[9] * y + W[10] * z + W[11];
+    const float4* px = reinterpret_cast<const float4*>(a.raw + (size_t)f * 3 * a.Npad);
+    const float4* py = px + n4, *pz = py + n4;
+    // two groups per trip, all six loads issued before the first use
+    for (uint32_t g0 = tid; g0 < n4; g0 += 2 * ST) {
+      const uint32_t g1 = g0 + ST;
+      const bool two = g1 < n4;
+      const float4 X0 = __ldcs(px + g0), Y0 = __ldcs(py + g0), Z0 = __ldcs(pz + g0);
+      float4 X1 = X0, Y1 = Y0, Z1 = Z0;
+      if (two) { X1 = __ldcs(px + g1); Y1 = __ldcs(py + g1); Z1 = __ldcs(pz + g1); }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        const uint32_t g = h ? g1 : g0;
+        const float4 X = h ? X1 : X0, Y = h ? Y1 : Y0, Z = h ? Z1 : Z0;
+        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+        double tx[4], ty[4], tz[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool real = 4 * g + k < a.N;  // pad atoms stay zero
+          const double x = xs[k], y = ys[k], z = zs[k];
+          tx[k] = real ? W[0] * x + W[1] * y + W[2] * z + W[3] : 0.0;
+          ty[k] = real ? W[4] * x + W[5] * y + W[6] * z + W[7] : 0.0;
+          tz[k] = real ? W[8] * x + W[9] * y + W[10] * z + W[11] : 0.0;
+        }
+        double2 u;
+        u = ax[2 * g]; u.x += tx[0]; u.y += tx[1]; ax[2 * g] = u;
+        u = ax[2 * g + 1]; u.x += tx[2]; u.y += tx[3]; ax[2 * g + 1] = u;
+        u = ay[2 * g]; u.x += ty[0]; u.y += ty[1]; ay[2 * g] = u;
+        u = ay[2 * g + 1]; u.x += ty[2]; u.y += ty[3]; ay[2 * g + 1] = u;
+        u = az[2 * g]; u.x += tz[0]; u.y += tz[1]; az[2 * g] = u;
+        u = az[2 * g + 1]; u.x += tz[2]; u.y += tz[3]; az[2 * g + 1] = u;
+      }
     }
   }
   __syncthreads();
