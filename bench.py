@@ -240,7 +240,7 @@ def parity_sample(X_dev, M_get, F, N, owned=None, nrand=3000, nnear=1000):
             "tolerance": 1e-4, "checker": kind}
 
 
-NCU_TRAFFIC = {("c4", 1, "tensor"): 104.732945e9 + 40.134005e9}
+NCU_TRAFFIC = {("c4", 1, "tensor"): 107.047827e9 + 40.017349e9}
 NCU_TRAFFIC_SOURCE = "profiles/r1_k_pairs_tensor_F100000_N1000_final_metrics.csv (result matrix 40.0 GB written once, operands 0.92 GB read 114x)"
 
 

@@ -1,0 +1,29 @@
+"""Small run of every kernel for `compute-sanitizer --tool memcheck python tools/sanitize_smoke.py`."""
+import os, sys
+import numpy as np
+sys.path.insert(0, "/root/repo")
+import loos_b200 as lb
+from loos_b200.api import rmsds_part
+from loos_b200.synth import synth_frames
+X = synth_frames(203, 333, seed=3)          # odd sizes: partial tiles, Npad > N, Kpad > N
+Y = synth_frames(77, 333, seed=4)
+for shape in ("1", "2"):
+    os.environ["LOOSB200_CLUSTER"] = shape
+    with lb.FrameSet(X) as fs, lb.FrameSet(Y) as fy:
+        M, st = lb.rmsds(fs, engine="tensor")
+        C, _ = lb.rmsds_cross(fs, fy, engine="tensor")
+        rows, blk, _ = rmsds_part(fs, 1, 3, engine="tensor")
+        print("tensor shape", shape, M.shape, C.shape, blk.shape, st["max"])
+with lb.FrameSet(X) as fs:
+    M64, _ = lb.rmsds(fs, engine="fp64")
+    print("fp64 max |d|", np.abs(M64 - M).max())
+    tgt = X[5].astype(np.float64)
+    d, xf = lb.rmsd2ref(fs, tgt, want_xforms=True)
+    os.environ["LOOSB200_STREAM_EXPLICIT"] = "1"
+    d2 = lb.rmsd2ref(fs, tgt)
+    print("rmsd2ref", d[:3], np.abs(d - d2).max())
+    sel = np.arange(0, 333, 3, dtype=np.uint32)
+with lb.FrameSet(X, sel=sel) as fa, lb.FrameSet(X) as fr:
+    r = lb.rmsd2ref_iterative(fa, fr, tol=1e-6, maxiter=50)
+    print("iterative", r["iters"], r["rmsd"][:3])
+print("sanitize smoke done")
