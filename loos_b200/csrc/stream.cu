@@ -600,7 +600,10 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
 
   // target_0 = first frame, centred (alignment.cpp:372-373): fetch its planes
   std::vector<float> f0(3 * NpA);
-  LB_CUDA(cudaMemcpy(f0.data(), align->raw, sizeof(float) * 3 * NpA, cudaMemcpyDeviceToHost));
+  {
+    const cudaError_t ce = cudaMemcpy(f0.data(), align->raw, sizeof(float) * 3 * NpA, cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) { cleanup(); return cuda_fail(ce, "fetching the first frame", __FILE__, __LINE__); }
+  }
   std::vector<double> t0(3 * NpA, 0.0);
   double c[3] = {0, 0, 0}, cs[3] = {0, 0, 0};
   for (int ax = 0; ax < 3; ++ax) {
