@@ -868,22 +868,29 @@ void writeMatrix(std::ostream& os, const float* M, size_t m, size_t n, size_t ld
   for (size_t b0 = 0; b0 < nblocks; b0 += batch) {
     const size_t nb = std::min(batch, nblocks - b0);
     auto work = [&](unsigned t) {
-      std::string line[RB];
-      char buf[48];
+      // one flat buffer per block: row r writes at rowbuf + r * cap (cap = worst-case line length),
+      // values are formatted in place -- no per-value string append
+      const size_t cap = n * (size_t)(precision + 9) + 2;  // sign, digits, '.', "e+XX", ' ' per value
+      std::vector<char> rowbuf(RB * cap);
+      char* pos[RB];
       for (size_t b = t; b < nb; b += nthreads) {
         const size_t j0 = (b0 + b) * RB, rows = std::min(RB, m - j0);
-        for (size_t r = 0; r < rows; ++r) { line[r].clear(); line[r].reserve(n * (precision + 7)); }
+        for (size_t r = 0; r < rows; ++r) pos[r] = rowbuf.data() + r * cap;
         for (size_t i = 0; i < n; ++i) {
           const float* col = M + i * ld + j0;
           for (size_t r = 0; r < rows; ++r) {
-            int l = formatG_fast(col[r], precision, buf);
-            buf[l++] = ' ';
-            line[r].append(buf, (size_t)l);
+            char* q = pos[r];
+            q += formatG_fast(col[r], precision, q);
+            *q++ = ' ';
+            pos[r] = q;
           }
         }
         std::string& out = text[b];
         out.clear();
-        for (size_t r = 0; r < rows; ++r) { out += line[r]; out += '\n'; }
+        size_t total = 0;
+        for (size_t r = 0; r < rows; ++r) total += (size_t)(pos[r] - (rowbuf.data() + r * cap)) + 1;
+        out.reserve(total);
+        for (size_t r = 0; r < rows; ++r) { out.append(rowbuf.data() + r * cap, (size_t)(pos[r] - (rowbuf.data() + r * cap))); out += '\n'; }
       }
     };
     if (nthreads == 1) {
