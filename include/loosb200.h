@@ -175,6 +175,19 @@ int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_frames* rmsd_se
                                 int maxiter, double* out_rmsd, double* out_xforms,
                                 double* out_avg, int* iters, double* final_rms);
 
+/* One pass of iterativeAlignment's loop body over THIS handle's frames (src/alignment.cpp:379-390:
+ * alignOnto(target) for every frame, transformed coordinates summed), for callers that shard a
+ * trajectory over several GPUs / processes: sum the per-shard results (the one collective of the
+ * whole RMSD path), divide by the total frame count, compare with the target and
+ * iterate -- loos_b200/multigpu.py::rmsd2ref_iterative_sharded is that loop.
+ *   target     3*N_align doubles (need not be centred: kabsch centres it, src/alignment.cpp:217-233)
+ *   accum_set  frames whose transformed coordinates are summed (NULL: the align set itself);
+ *              with the rmsd selection this is averageStructure's numerator (src/ensembles.cpp:108-118)
+ *   sum_out    3*N_accum doubles, xyz interleaved: sum over the handle's frames of W_f x_f
+ *   out_xforms F x 16 doubles or NULL */
+int loosb200_align_accumulate(loosb200_frames* align, loosb200_frames* accum_set, const double* target,
+                              double* sum_out, double* out_xforms);
+
 /* ---- timing hooks (bench.py) ----
  * Device time in milliseconds of the kernels of the most recent compute call on
  * this handle, measured with CUDA events on the stream they were launched on:

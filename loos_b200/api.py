@@ -197,3 +197,18 @@ def rmsd2ref_iterative(fs_align, fs_rmsd=None, tol=1e-6, maxiter=1000):
     check(lib().loosb200_rmsd2ref_iterative(fs_align._h, None if fs_rmsd is None else fs_rmsd._h, tol, maxiter,
                                             _dptr(out), _dptr(xf), _dptr(avg), C.byref(it), C.byref(rms)))
     return {"rmsd": out, "xforms": xf, "avg": avg, "iters": it.value, "rms": rms.value}
+
+
+def align_accumulate(fs_align, target, fs_accum=None, want_xforms=False):
+    """One pass of iterativeAlignment's loop body over this frame set: every frame superposed onto
+    `target` (N_align x 3), transformed coordinates of `fs_accum` (default: the align set) summed.
+    Returns the (N_accum, 3) sum [and the (F, 4, 4) transforms].  Building block of the sharded
+    iterative alignment (loos_b200/multigpu.py)."""
+    tgt = np.ascontiguousarray(target, dtype=np.float64).reshape(-1)
+    if tgt.size != 3 * fs_align.N:
+        raise LoosB200Error(capi.ERR_SIZE_MISMATCH, "target has %d coordinates, the frames have %d atoms" % (tgt.size, fs_align.N))
+    na = (fs_accum or fs_align).N
+    out = np.zeros((na, 3))
+    xf = np.zeros((fs_align.F, 4, 4)) if want_xforms else None
+    check(lib().loosb200_align_accumulate(fs_align._h, None if fs_accum is None else fs_accum._h, _dptr(tgt), _dptr(out), _dptr(xf)))
+    return (out, xf) if want_xforms else out

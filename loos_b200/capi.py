@@ -56,6 +56,7 @@ SIGNATURES = {
     "loosb200_rmsds_self_part_device": (_i, [_vp, _i, _i, _vp, _sz, _sp, _i]),
     "loosb200_rmsd2ref": (_i, [_vp, _vp, _dp, _dp, _dp, _dp]),
     "loosb200_rmsd2ref_iterative": (_i, [_vp, _vp, C.c_double, _i, _dp, _dp, _dp, C.POINTER(_i), _dp]),
+    "loosb200_align_accumulate": (_i, [_vp, _vp, _dp, _dp, _dp]),
     "loosb200_last_timing": (_i, [_vp, _dp, _dp]),
 }
 

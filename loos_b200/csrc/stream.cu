@@ -565,6 +565,61 @@ extern "C" int loosb200_rmsd2ref(loosb200_frames* align, loosb200_frames* rmsd_s
   return LOOSB200_OK;
 }
 
+extern "C" int loosb200_align_accumulate(loosb200_frames* align, loosb200_frames* accum_set, const double* target,
+                                         double* sum_out, double* out_xforms) {
+  int rc = check_pair(align, accum_set);
+  if (rc) return rc;
+  if (!target || !sum_out) return LOOSB200_ERR_INVALID;
+  loosb200_frames* as = accum_set ? accum_set : align;
+  LB_CUDA(cudaSetDevice(align->device));
+  cudaStream_t st = align->stream;
+  const size_t F = align->F, NpS = as->Npad;
+  const int smem = smem_for_accum(NpS);
+  if (smem > 200 * 1024) return LOOSB200_ERR_UNSUPPORTED;
+  LB_CUDA(cudaFuncSetAttribute(k_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+
+  std::vector<double> soaA;
+  double c[3], cs[3];
+  to_soa(target, align->N, align->Npad, true, soaA, c, cs);
+  double *dA = nullptr, *dCov = nullptr, *dXf = nullptr, *dSum = nullptr;
+  auto cleanup = [&]() { dev_release(dA); dev_release(dCov); dev_release(dXf); dev_release(dSum); };
+  const bool ok = dev_alloc_t(&dA, sizeof(double) * soaA.size()) == cudaSuccess &&
+                  dev_alloc_t(&dCov, sizeof(double) * 9 * F) == cudaSuccess &&
+                  dev_alloc_t(&dXf, sizeof(double) * 16 * F) == cudaSuccess &&
+                  dev_alloc_t(&dSum, sizeof(double) * 3 * NpS) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); cleanup(); return LOOSB200_ERR_NOMEM; }
+  cudaEventRecord(align->timing.ev[0], st);
+  cudaMemcpyAsync(dA, soaA.data(), sizeof(double) * soaA.size(), cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(dSum, 0, sizeof(double) * 3 * NpS, st);
+  cudaEventRecord(align->timing.ev[1], st);
+  CovArgs ca;
+  ca.raw = align->raw; ca.Npad = align->Npad; ca.ref = dA; ca.F = (uint32_t)F; ca.cov = dCov;
+  k_cov<<<grid_warp((uint32_t)F, k_cov), SW_THREADS, 0, st>>>(ca);
+  SolveArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.cov = dCov; sa.cen = align->centroid; sa.gd = align->gd;
+  for (int k = 0; k < 3; ++k) { sa.ref_c[k] = c[k]; sa.ref_sum[k] = cs[k]; }
+  for (double v : soaA) sa.ref_g += v * v;
+  sa.F = (uint32_t)F; sa.Na = (uint32_t)align->N; sa.xf = dXf;
+  k_solve<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(sa);
+  AccumArgs aa;
+  aa.raw = as->raw; aa.Npad = NpS; aa.N = (uint32_t)as->N; aa.xf = dXf; aa.F = (uint32_t)F; aa.avg = dSum;
+  k_accum<<<grid_accum((uint32_t)F, smem), ST, smem, st>>>(aa);
+  cudaEventRecord(align->timing.ev[2], st);
+  std::vector<double> sum_h(3 * NpS);
+  cudaMemcpyAsync(sum_h.data(), dSum, sizeof(double) * 3 * NpS, cudaMemcpyDeviceToHost, st);
+  if (out_xforms) cudaMemcpyAsync(out_xforms, dXf, sizeof(double) * 16 * F, cudaMemcpyDeviceToHost, st);
+  cudaEventRecord(align->timing.ev[3], st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cleanup();
+  if (e != cudaSuccess) return cuda_fail(e, "align_accumulate", __FILE__, __LINE__);
+  for (size_t i = 0; i < as->N; ++i)
+    for (int ax = 0; ax < 3; ++ax) sum_out[3 * i + ax] = sum_h[ax * NpS + i];
+  align->timing.launches = 3; align->timing.valid = true; align->timing.kev_used = 0;
+  return LOOSB200_OK;
+}
+
 extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_frames* rmsd_set,
                                            double tol, int maxiter, double* out_rmsd,
                                            double* out_xforms, double* out_avg, int* iters,

@@ -64,3 +64,49 @@ def gather_matrix(rows, block, F, rank, world, group=None):
     dist.send(t_rows, dst=0, group=group)
     dist.send(t_blk.contiguous(), dst=0, group=group)
     return None
+
+
+# ---------------------------------------------------------------------------------------------
+# Iterative alignment over a trajectory whose frames are sharded across ranks
+# (rmsd2ref's default mode, iterativeAlignment src/alignment.cpp:355-404 + averageStructure
+# src/ensembles.cpp:91-121).  This is the one place of the whole RMSD path with a real exchange
+# step: the running average is a sum over ALL frames, so every iteration all-reduces 3*N doubles.
+
+def _all_reduce_sum(x, group=None):
+    """Sum a small float64 numpy array over the ranks (NCCL needs it on the device, gloo on the host)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return x
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+def rmsd2ref_iterative_sharded(fs_align, fs_rmsd, first_frame, n_frames_total, tol=1e-6, maxiter=1000, group=None,
+                               accumulate=None, rmsd_to=None):
+    """Each rank holds a contiguous or strided shard of the frames as FrameSets (align selection,
+    rmsd selection or None for "same").  `first_frame` is the align selection of GLOBAL frame 0
+    ((N_align, 3), identical on every rank: the reference primes the loop with it).
+
+    Returns dict(rmsd, xforms, avg, iters, rms) with `rmsd`/`xforms` for the LOCAL frames and the
+    rest identical on every rank.  `accumulate` / `rmsd_to` default to the GPU entry points
+    (api.align_accumulate, api.rmsd2ref); the CPU tests inject restatements to cover the loop and
+    the collective without a GPU."""
+    accumulate = accumulate or api.align_accumulate
+    rmsd_to = rmsd_to or (lambda fa, tgt, fr, ref: api.rmsd2ref(fa, tgt, fr, ref, want_xforms=True))
+    first = np.asarray(first_frame, dtype=np.float64).reshape(-1, 3)
+    target = first - first.mean(axis=0)          # target.centerAtOrigin(), alignment.cpp:372-373
+    it, rms, used = 0, 0.0, target
+    while True:
+        used = target                             # the transforms of the last pass refer to this target
+        avg = _all_reduce_sum(accumulate(fs_align, target), group) / float(n_frames_total)
+        rms = float(np.sqrt(((avg - target) ** 2).sum(axis=1).mean()))   # avg.rmsd(target), AG_numerical.cpp:301-318
+        target = avg
+        it += 1
+        if not (rms > tol and it <= maxiter):     # alignment.cpp:399
+            break
+    avg_r = _all_reduce_sum(accumulate(fs_align, used, fs_rmsd), group) / float(n_frames_total)
+    rmsd, xf = rmsd_to(fs_align, used, fs_rmsd, avg_r)
+    return {"rmsd": rmsd, "xforms": xf, "avg": avg_r, "iters": it, "rms": rms}

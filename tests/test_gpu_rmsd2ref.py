@@ -104,3 +104,30 @@ def test_eigenvalue_shortcut_equals_explicit_residuals(lb, monkeypatch):
         d_expl, xf_expl = lb.rmsd2ref(fs, tgt, want_xforms=True)
     assert np.abs(d_short - d_expl).max() < RMSD_TOL
     assert np.array_equal(xf_short, xf_expl)
+
+
+def test_align_accumulate_and_sharded_driver(lb):
+    """loosb200_align_accumulate (one pass of the iterative-alignment loop over a shard) and the
+    sharded driver: (1) the sum over two shards equals the sum over the whole set and a float64
+    restatement; (2) with a single shard the driver reproduces loosb200_rmsd2ref_iterative
+    (same iteration count, average and per-frame rmsd)."""
+    from loos_b200 import api, multigpu
+    from loos_b200.synth import synth_frames
+    X = synth_frames(301, 260, seed=31)
+    sel = np.arange(0, 260, 2, dtype=np.uint32)
+    tgt = X[7][sel].astype(np.float64)
+    with lb.FrameSet(X, sel=sel) as fa, lb.FrameSet(X) as fr, \
+         lb.FrameSet(X[:150], sel=sel) as fa0, lb.FrameSet(X[:150]) as fr0, \
+         lb.FrameSet(X[150:], sel=sel) as fa1, lb.FrameSet(X[150:]) as fr1:
+        S, xf = api.align_accumulate(fa, tgt, fr, want_xforms=True)
+        S0 = api.align_accumulate(fa0, tgt, fr0)
+        S1 = api.align_accumulate(fa1, tgt, fr1)
+        want = np.einsum("fij,fnj->ni", xf[:, :3, :3], X.astype(np.float64)) + xf[:, :3, 3].sum(axis=0)
+        assert np.abs(S - want).max() < 1e-7 * np.abs(want).max()
+        assert np.abs(S0 + S1 - S).max() < 1e-8 * np.abs(S).max()
+        built_in = lb.rmsd2ref_iterative(fa, fr, tol=1e-6, maxiter=1000)
+        sharded = multigpu.rmsd2ref_iterative_sharded(fa, fr, X[0][sel], 301, tol=1e-6, maxiter=1000)
+    assert sharded["iters"] == built_in["iters"]
+    assert np.abs(sharded["avg"] - built_in["avg"]).max() < 1e-8
+    assert np.abs(sharded["rmsd"] - built_in["rmsd"]).max() < RMSD_TOL
+    assert np.abs(sharded["xforms"] - built_in["xforms"]).max() < 1e-8

@@ -65,3 +65,69 @@ def test_split_is_a_partition_for_many_world_sizes():
             seen = np.concatenate([part_rows(F, r, world) for r in range(world)])
             real = np.sort(seen[seen != 0xFFFFFFFF])
             assert np.array_equal(real, np.arange(F)), (F, world)
+
+
+def _iter_worker(rank, world, port, F, Na, q):
+    """Sharded iterative alignment: frames dealt round-robin to two ranks; the per-shard compute
+    (superpose + sum, per-frame rmsd) is the CPU oracle's kabsch here, the loop, the all-reduce of
+    the running average and the convergence rule are loos_b200.multigpu's."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from loos_b200 import multigpu
+    from loos_b200.synth import synth_frames
+    from oracle.oracle import Checker
+    chk = Checker("port")
+    X = synth_frames(F, Na + 7, seed=21).astype(np.float64)
+    A, R = X[:, :Na], X                                   # align selection = first Na atoms, rmsd selection = all
+    mine = np.arange(rank, F, world)
+
+    def xform(frame, target):                            # 4x4 W mapping frame onto target (alignment::kabsch)
+        return np.asarray(chk.kabsch(frame.reshape(-1), target.reshape(-1))).reshape(4, 4)
+
+    def accumulate(fa, target, fr=None):
+        src = A if fr is None else R
+        out = np.zeros((src.shape[1], 3))
+        for f in mine:
+            W = xform(A[f], target)
+            out += src[f] @ W[:3, :3].T + W[:3, 3]
+        return out
+
+    def rmsd_to(fa, target, fr, ref):
+        d, xf = np.zeros(len(mine)), np.zeros((len(mine), 4, 4))
+        for k, f in enumerate(mine):
+            W = xform(A[f], target)
+            y = R[f] @ W[:3, :3].T + W[:3, 3]
+            d[k] = np.sqrt(((y - ref) ** 2).sum(axis=1).mean())
+            xf[k] = W
+        return d, xf
+
+    res = multigpu.rmsd2ref_iterative_sharded("align shard", "rmsd shard", A[0], F, tol=1e-6, maxiter=1000,
+                                              accumulate=accumulate, rmsd_to=rmsd_to)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (mine, res["rmsd"], res["avg"], res["iters"]))
+    if rank == 0:
+        want_d, _, want_avg, want_it, _ = chk.rmsd2ref_iterative(A, R, 1e-6, 1000)
+        d = np.zeros(F)
+        for idx, dd, _, _ in gathered:
+            d[idx] = dd
+        q.put((int(res["iters"]) == int(want_it), all(g[3] == res["iters"] for g in gathered),
+               float(np.abs(d - want_d).max()) < 1e-9, float(np.abs(res["avg"] - want_avg).max()) < 1e-9,
+               all(np.array_equal(g[2], res["avg"]) for g in gathered)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_iterative_alignment():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_iter_worker, args=(r, 2, 29777, 41, 30, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(res), res
