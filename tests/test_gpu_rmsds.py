@@ -308,3 +308,43 @@ def test_large_configs_sampled_parity_and_properties(lb, checker, F, N, name):
         lb.rmsds(fa, out=A, engine="tensor")
         lb.rmsds(fb, out=B, engine="tensor")
     assert float((A - B).abs().max()) < 5e-5
+
+
+def test_atom_limit_of_the_tensor_engine(lb, checker):
+    """N = 43 000 is the largest selection whose class sums provably fit int32 (3 digit products of
+    at most 2^14 per atom).  Worst case for the accumulators: every centred coordinate at +-max, so all
+    three digits of every operand are extreme.  The tensor engine must still be exact (compared with
+    the fp64 engine and the oracle), N = 43 001 must be refused by it and taken by the fp64 engine
+    under engine="auto"."""
+    from loos_b200 import capi
+    rng = np.random.default_rng(43)
+    F, N = 44, 43000
+    signs = rng.choice([-1.0, 1.0], size=(F, N, 3))
+    signs[:, N // 2:, :] = -signs[:, :N // 2, :]            # centroid exactly 0: max |x - c| = L everywhere
+    X = (signs * 99.99).astype(np.float32)
+    X[3] = X[2]                                              # an identical pair
+    X[5] = -X[4]                                             # and an inverted one
+    with lb.FrameSet(X) as fs:
+        Mt, st = lb.rmsds(fs, engine="tensor")
+        Mf, sf = lb.rmsds(fs, engine="fp64")
+    # identical frames: exactly 0 while the integer sums stay below 2^53 (any realistic input); here
+    # they reach 2^63 and the fp64 combine rounds at 1e-16 relative: a few 1e-5 A at most
+    # (the fp64 engine, like the reference, carries the cancellation noise of Ga + Gb - 2 lambda:
+    # sqrt(1e-16 * 1.3e9 A^2 * few / N) ~ 2e-4 A for this pair)
+    assert Mt[3, 2] < 5e-5 and Mf[3, 2] < 5e-4
+    D = np.abs(Mt - Mf)
+    D[3, 2] = D[2, 3] = 0.0
+    assert D.max() <= 2 * np.spacing(np.float32(Mf.max()))    # RMSDs of ~200 A: two float32 ulps = 3e-5
+    Xd = X.astype(np.float64)
+    cen = [checker.center_at_origin(x)[0] for x in Xd[:6]]
+    for i, j in [(1, 0), (5, 4), (5, 0)]:
+        assert abs(float(Mt[i, j]) - checker.centered_rmsd(cen[i], cen[j])) < 1e-4
+    assert checker.centered_rmsd(cen[3], cen[2]) < 5e-4      # the reference's own noise floor here
+    X1 = np.concatenate([X[:9], X[:9, :1]], axis=1)         # 43 001 atoms
+    with lb.FrameSet(X1) as fs:
+        with pytest.raises(lb.LoosB200Error) as e:
+            lb.rmsds(fs, engine="tensor")
+        assert e.value.code == capi.ERR_UNSUPPORTED
+        Ma, _ = lb.rmsds(fs, engine="auto")
+        Mf1, _ = lb.rmsds(fs, engine="fp64")
+    assert np.array_equal(Ma, Mf1)
