@@ -1027,6 +1027,43 @@ bool Options::parse(int argc, char* argv[]) {
     ++pos_count;
     if (positional_[pos_i].second >= 0 && (int)pos_count >= positional_[pos_i].second) { ++pos_i; pos_count = 0; }
   }
+  // --config file (src/OptionsFramework.cpp:746,765-771): boost's parse_config_file -- one
+  // "name = value" per line, '#' starts a comment, "[section]" prefixes the names that follow with
+  // "section."; what the command line already set wins (first store wins in a variables_map), a
+  // name may repeat for options that take several values (the trajectory list).
+  if (const Opt* cfg = find("config")) {
+    if (cfg->set) {
+      std::ifstream ifs(cfg->values.back().c_str());
+      if (!ifs) { std::cerr << "Error- Cannot open options config file\n"; return false; }
+      std::vector<std::string> from_cmdline;
+      for (const auto& o : opts_) if (o.set) from_cmdline.push_back(o.name);
+      std::string line, section;
+      while (std::getline(ifs, line)) {
+        const size_t hash = line.find('#');
+        if (hash != std::string::npos) line.erase(hash);
+        auto trim = [](std::string& t) {
+          const size_t a = t.find_first_not_of(" \t\r\n");
+          const size_t b = t.find_last_not_of(" \t\r\n");
+          t = a == std::string::npos ? "" : t.substr(a, b - a + 1);
+        };
+        trim(line);
+        if (line.empty()) continue;
+        if (line.front() == '[' && line.back() == ']') { section = line.substr(1, line.size() - 2); if (!section.empty()) section += "."; continue; }
+        const size_t eq = line.find('=');
+        if (eq == std::string::npos) { std::cerr << "Error- the options configuration file contains an invalid line '" << line << "'\n"; return false; }
+        std::string name = line.substr(0, eq), val = line.substr(eq + 1);
+        trim(name); trim(val);
+        name = section + name;
+        Opt* o = find(name);
+        if (!o) {  // positionals are ordinary named options in the reference's options_description
+          for (const auto& pz : positional_) if (pz.first == name) { add(name, 0, "", "", false); o = find(name); }
+        }
+        if (!o) { std::cerr << "Error- unrecognised option '" << name << "'\n"; return false; }
+        if (std::find(from_cmdline.begin(), from_cmdline.end(), name) != from_cmdline.end()) continue;
+        if (!store(o, val)) return false;
+      }
+    }
+  }
   return true;
 }
 

@@ -25,6 +25,7 @@ inline void addBasicOptions(Options& o) {  // BasicOptions, src/OptionsFramework
   o.add("help", 'h', "", "Produce this message", true);
   o.add("fullhelp", 0, "", "More detailed help", true);
   o.add("verbosity", 'v', "0", "Verbosity of output (if available)");
+  o.add("config", 0, "", "Options config file");
   o.add("gpu", 0, "0", "CUDA device to use (extension; the reference has no such option)");
   o.add("engine", 0, "auto", "auto|tensor|fp64 contraction engine (extension)");
 }

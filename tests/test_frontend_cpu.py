@@ -342,3 +342,27 @@ def test_matrix_write_read_round_trip(fe):
     assert b"Invalid conversion on matrix read at (1,1) of 'x'" in fe.lbfe_last_error()
     assert fe.lbfe_read_matrix(b"1 2 3\n", 6, back.ctypes.data_as(C.POINTER(C.c_float)), back.size, C.byref(mm), C.byref(nn)) == -1
     assert b"Could not find magic marker" in fe.lbfe_last_error()
+
+
+def test_config_file_option(system, tmp_path):
+    """--config file (src/OptionsFramework.cpp:746,765-771, boost parse_config_file): name = value
+    lines, comments, positionals by name, command line wins.  Observed through the errors the tool
+    raises before it needs a GPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the runs would go through")
+    exe = os.path.join(ROOT, "loos_b200", "bin", "rmsds")
+    cfg = tmp_path / "opts.cfg"
+    cfg.write_text("# options for rmsds\nmodel1 = %s\ntraj1=%s   # the trajectory\n\nsel1 = name == 'NOPE'\nprecision = 5\n" % (system["pdb"], system["dcd"]))
+    r = subprocess.run([exe, "--config", str(cfg)], capture_output=True, text=True)
+    assert r.returncode == 255 and "name == 'NOPE'" in r.stderr and "matched no atoms" in r.stderr
+    r = subprocess.run([exe, "--config", str(cfg), "--sel1", "name == 'CA'"], capture_output=True, text=True)
+    assert r.returncode == 255 and "no usable sm_100" in r.stderr            # got past the selection: command line won
+    cfg.write_text("model1 = %s\nbogus = 1\n" % system["pdb"])
+    r = subprocess.run([exe, "--config", str(cfg)], capture_output=True, text=True)
+    assert r.returncode == 255 and "unrecognised option 'bogus'" in r.stderr
+    cfg.write_text("model1 %s\n" % system["pdb"])
+    r = subprocess.run([exe, "--config", str(cfg)], capture_output=True, text=True)
+    assert r.returncode == 255 and "invalid line" in r.stderr
+    r = subprocess.run([exe, "--config", str(tmp_path / "missing.cfg"), system["pdb"], system["dcd"]], capture_output=True, text=True)
+    assert r.returncode == 255 and "Cannot open options config file" in r.stderr
