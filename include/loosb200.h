@@ -132,6 +132,18 @@ int loosb200_rmsds_cross(loosb200_frames* a, loosb200_frames* b, float* out, siz
 int loosb200_rmsds_cross_device(loosb200_frames* a, loosb200_frames* b, float* out_dev, size_t ld,
                                 loosb200_stats* stats, int engine);
 
+/* ---- result as text, formatted on the GPU  (src/MatrixImpl.hpp:210-222, Tools/rmsds.cpp:566-567) ----
+ * `cout << setprecision(p) << M`: "# m n (0)\n", then one line per row, every value as "%.{p}g"
+ * followed by a space.  The float32 matrix stays in HBM; rows are formatted there (exact integer
+ * arithmetic, the same bytes as printf) and only the text crosses PCIe, in row order, through
+ * `sink(user, data, nbytes)` (return non-zero to abort).  At 100 000 frames that is 45 GB of text,
+ * which costs a minute of host time even on all cores.  precision 0..9. */
+typedef int (*loosb200_sink)(void* user, const char* data, size_t nbytes);
+int loosb200_rmsds_self_text(loosb200_frames* h, unsigned precision, loosb200_sink sink, void* user,
+                             loosb200_stats* stats, int engine);
+int loosb200_rmsds_cross_text(loosb200_frames* a, loosb200_frames* b, unsigned precision,
+                              loosb200_sink sink, void* user, loosb200_stats* stats, int engine);
+
 /* ---- multi-GPU work splitting ----
  * The upper-triangular tile space is cut statically into `nparts` interleaved
  * sets of 40-frame tile rows; part `part` computes its rows against all columns

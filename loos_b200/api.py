@@ -212,3 +212,23 @@ def align_accumulate(fs_align, target, fs_accum=None, want_xforms=False):
     xf = np.zeros((fs_align.F, 4, 4)) if want_xforms else None
     check(lib().loosb200_align_accumulate(fs_align._h, None if fs_accum is None else fs_accum._h, _dptr(tgt), _dptr(out), _dptr(xf)))
     return (out, xf) if want_xforms else out
+
+
+def rmsds_text(fs, fs_b=None, precision=2, engine="auto", write=None):
+    """The result matrix as the reference prints it (`cout << setprecision(p) << M`), formatted on
+    the GPU and streamed in row order.  `write(bytes)` receives the pieces (default: they are
+    collected and returned).  Returns (text or None, stats)."""
+    pieces = []
+    emit = write or pieces.append
+
+    def _sink(_user, data, n):
+        emit(C.string_at(data, n))
+        return 0
+
+    cb = capi.SINK(_sink)
+    st = Stats()
+    if fs_b is None:
+        check(lib().loosb200_rmsds_self_text(fs._h, int(precision), cb, None, C.byref(st), capi.ENGINES[engine]))
+    else:
+        check(lib().loosb200_rmsds_cross_text(fs._h, fs_b._h, int(precision), cb, None, C.byref(st), capi.ENGINES[engine]))
+    return (None if write else b"".join(pieces)), _stats_tuple(st)

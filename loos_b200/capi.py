@@ -32,6 +32,8 @@ _sz, _i = C.c_size_t, C.c_int
 _sp = C.POINTER(Stats)
 
 # every symbol include/loosb200.h declares: name -> (restype, argtypes)
+SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)   # loosb200_sink
+
 SIGNATURES = {
     "loosb200_version": (C.c_char_p, []),
     "loosb200_strerror": (C.c_char_p, [_i]),
@@ -57,6 +59,8 @@ SIGNATURES = {
     "loosb200_rmsd2ref": (_i, [_vp, _vp, _dp, _dp, _dp, _dp]),
     "loosb200_rmsd2ref_iterative": (_i, [_vp, _vp, C.c_double, _i, _dp, _dp, _dp, C.POINTER(_i), _dp]),
     "loosb200_align_accumulate": (_i, [_vp, _vp, _dp, _dp, _dp]),
+    "loosb200_rmsds_self_text": (_i, [_vp, C.c_uint, SINK, _vp, _sp, _i]),
+    "loosb200_rmsds_cross_text": (_i, [_vp, _vp, C.c_uint, SINK, _vp, _sp, _i]),
     "loosb200_last_timing": (_i, [_vp, _dp, _dp]),
 }
 

@@ -428,6 +428,33 @@ extern "C" int loosb200_rmsds_cross_device(loosb200_frames* a, loosb200_frames* 
   return run_pairs(a, b, false, false, false, all_rows(a->F), out_dev, out_dev ? OutKind::Device : OutKind::None, ld, stats, engine);
 }
 
+// matrix in HBM -> text through the sink (text.cu)
+static int pairs_text(loosb200_frames* a, loosb200_frames* b, bool self, unsigned precision, loosb200_sink sink,
+                      void* user, loosb200_stats* stats, int engine) {
+  if (!sink) return LOOSB200_ERR_INVALID;
+  LB_CUDA(cudaSetDevice(a->device));
+  const size_t m = a->F, n = b->F;
+  float* d_M = nullptr;
+  if (dev_alloc_t(&d_M, sizeof(float) * std::max<size_t>(1, m * n)) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
+  int rc = run_pairs(a, b, self, self, false, all_rows(a->F), d_M, OutKind::Device, m, stats, engine);
+  if (rc == LOOSB200_OK) rc = stream_matrix_text(d_M, m, n, m, self, precision, sink, user, a->stream);
+  dev_release(d_M);
+  return rc;
+}
+
+extern "C" int loosb200_rmsds_self_text(loosb200_frames* h, unsigned precision, loosb200_sink sink, void* user,
+                                        loosb200_stats* stats, int engine) {
+  if (!h) return LOOSB200_ERR_INVALID;
+  return pairs_text(h, h, true, precision, sink, user, stats, engine);
+}
+
+extern "C" int loosb200_rmsds_cross_text(loosb200_frames* a, loosb200_frames* b, unsigned precision,
+                                         loosb200_sink sink, void* user, loosb200_stats* stats, int engine) {
+  int rc = check_cross(a, b, nullptr, 0);
+  if (rc) return rc;
+  return pairs_text(a, b, false, precision, sink, user, stats, engine);
+}
+
 extern "C" int loosb200_part_rows(size_t F, int part, int nparts, uint32_t* rows_or_null, size_t* nrows) {
   if (F == 0 || nparts < 1 || part < 0 || part >= nparts) return LOOSB200_ERR_INVALID;
   std::vector<uint32_t> rt = part_row_tiles(F, part, nparts);

@@ -45,6 +45,9 @@ cudaError_t host_alloc(void** p, size_t bytes);  // pinned host blocks, same cac
 void host_release(void* p);
 template <class T> inline cudaError_t dev_alloc_t(T** p, size_t bytes) { return dev_alloc(reinterpret_cast<void**>(p), bytes); }
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+// text.cu: "# m n (0)" + the rows of a device matrix (column-major) as "%.{p}g " text through `sink`
+int stream_matrix_text(const float* d_M, size_t m, size_t n, size_t ld, bool symmetric, unsigned precision,
+                       loosb200_sink sink, void* user, cudaStream_t st);
 
 #define LB_CUDA(call)                                                       \
   do {                                                                      \

@@ -56,17 +56,10 @@ int main(int argc, char* argv[]) {
     if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
     std::vector<float> M;
     const std::string binary = o.str("binary");
-    const bool want_m = !noop || !binary.empty();
-    if (want_m) M.assign(F * F, 0.0f);
-    loosb200_stats st;
-    check(loosb200_rmsds_self(A.h, want_m ? M.data() : nullptr, F, &st, engine), "multi-rmsds");
-    if (!binary.empty()) writeNpy(binary, M.data(), F, F, F);
-    if (verbosity || noop || stats) {
-      char line[128];
-      snprintf(line, sizeof(line), "Max rmsd = %.4f, avg rmsd = %.4f\n", st.max, st.count ? st.sum / (double)st.count : 0.0);
-      std::cerr << line;
-    }
-    if (!noop) {
+    const unsigned precision = (unsigned)o.uns("precision");
+    const bool gpu_text = !noop && gpuText(!binary.empty(), precision);  // text formatted on the GPU
+    const bool want_m = (!noop || !binary.empty()) && !gpu_text;
+    auto preamble = [&]() {
       std::cout << "# " << header << std::endl;
       // trajectoryTable(), src/OptionsFramework.cpp:479-502
       if (!range.empty()) std::cout << "# Note- composite frame range used was '" << range << "'\n";
@@ -78,7 +71,26 @@ int main(int argc, char* argv[]) {
         else { std::cout << "# " << j << "\t" << start_cnt << "\t" << (start_cnt + n - 1) << "\t" << mt.trajs[i]->filename() << "\n"; ++j; }
         start_cnt += n;
       }
-      writeMatrix(std::cout, M.data(), F, F, F, (unsigned)o.uns("precision"));
+      std::cout.flush();
+    };
+    if (want_m) M.assign(F * F, 0.0f);
+    loosb200_stats st;
+    if (gpu_text) {
+      preamble();
+      check(loosb200_rmsds_self_text(A.h, precision, stdoutSink, nullptr, &st, engine), "multi-rmsds");
+      fflush(stdout);
+    } else {
+      check(loosb200_rmsds_self(A.h, want_m ? M.data() : nullptr, F, &st, engine), "multi-rmsds");
+    }
+    if (!binary.empty()) writeNpy(binary, M.data(), F, F, F);
+    if (verbosity || noop || stats) {
+      char line[128];
+      snprintf(line, sizeof(line), "Max rmsd = %.4f, avg rmsd = %.4f\n", st.max, st.count ? st.sum / (double)st.count : 0.0);
+      std::cerr << line;
+    }
+    if (!noop && !gpu_text) {
+      preamble();
+      writeMatrix(std::cout, M.data(), F, F, F, precision);
     }
   } catch (const std::exception& e) {
     std::cerr << e.what() << std::endl;

@@ -92,11 +92,21 @@ int main(int argc, char* argv[]) {
     if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
     const bool want_fraction = cutoff > 0;
     const std::string binary = o.str("binary");
-    const bool need_matrix = !noop || want_fraction || !binary.empty();
+    const unsigned precision = (unsigned)o.uns("precision");
+    const bool gpu_text = !noop && gpuText(want_fraction || !binary.empty(), precision);  // text formatted on the GPU
+    const bool need_matrix = (!noop || want_fraction || !binary.empty()) && !gpu_text;
     std::vector<float> M;
     if (need_matrix) M.assign(F[0] * F[1], 0.0f);
     loosb200_stats st;
-    check(loosb200_rmsds_cross(fs[0].h, fs[1].h, need_matrix ? M.data() : nullptr, F[0], &st, engine), "rms-overlap");
+    if (gpu_text) {
+      std::cout << "# " << header << std::endl;
+      std::cout << trajectoryTable(mt[0], range) << trajectoryTable(mt[1], range);
+      std::cout.flush();
+      check(loosb200_rmsds_cross_text(fs[0].h, fs[1].h, precision, stdoutSink, nullptr, &st, engine), "rms-overlap");
+      fflush(stdout);
+    } else {
+      check(loosb200_rmsds_cross(fs[0].h, fs[1].h, need_matrix ? M.data() : nullptr, F[0], &st, engine), "rms-overlap");
+    }
     if (!binary.empty()) writeNpy(binary, M.data(), F[0], F[1], F[0]);
     if (verbosity || noop || stats || want_fraction) {
       char line[512];
@@ -124,10 +134,10 @@ int main(int argc, char* argv[]) {
         std::cerr << line;
       }
     }
-    if (!noop) {
+    if (!noop && !gpu_text) {
       std::cout << "# " << header << std::endl;
       std::cout << trajectoryTable(mt[0], range) << trajectoryTable(mt[1], range);
-      writeMatrix(std::cout, M.data(), F[0], F[1], F[0], (unsigned)o.uns("precision"));
+      writeMatrix(std::cout, M.data(), F[0], F[1], F[0], precision);
     }
   } catch (const std::exception& e) {
     std::cerr << e.what() << std::endl;

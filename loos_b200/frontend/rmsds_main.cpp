@@ -32,7 +32,10 @@ int main(int argc, char* argv[]) {
     const long verbosity = std::stol(o.str("verbosity"));
     const bool noop = o.flag("noout"), stats = o.flag("stats");
     const std::string binary = o.str("binary");
-    const bool want_m = !noop || !binary.empty();
+    const unsigned precision = (unsigned)o.uns("precision");
+    const bool gpu_text = !noop && gpuText(!binary.empty(), precision);  // text formatted on the GPU
+    const bool want_m = (!noop || !binary.empty()) && !gpu_text;
+    if (gpu_text) { std::cout << "# " << header << std::endl; std::cout.flush(); }
     const int device = (int)o.uns("gpu"), engine = engineOf(o);
 
     Model model = readPDB(o.str("model1"));
@@ -53,7 +56,8 @@ int main(int argc, char* argv[]) {
     if (!o.has("model2")) {
       if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
       if (want_m) M.assign(rows * cols, 0.0f);
-      check(loosb200_rmsds_self(A.h, want_m ? M.data() : nullptr, rows, &st, engine), "rmsds");
+      if (gpu_text) check(loosb200_rmsds_self_text(A.h, precision, stdoutSink, nullptr, &st, engine), "rmsds");
+      else check(loosb200_rmsds_self(A.h, want_m ? M.data() : nullptr, rows, &st, engine), "rmsds");
     } else {
       Model model2 = readPDB(o.str("model2"));
       const std::shared_ptr<Trajectory> traj2p = openTrajectory(o.str("traj2"), (uint32_t)model2.size());
@@ -68,7 +72,8 @@ int main(int argc, char* argv[]) {
       cols = indices2.size();
       if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
       if (want_m) M.assign(rows * cols, 0.0f);
-      check(loosb200_rmsds_cross(A.h, B.h, want_m ? M.data() : nullptr, rows, &st, engine), "rmsds");
+      if (gpu_text) check(loosb200_rmsds_cross_text(A.h, B.h, precision, stdoutSink, nullptr, &st, engine), "rmsds");
+      else check(loosb200_rmsds_cross(A.h, B.h, want_m ? M.data() : nullptr, rows, &st, engine), "rmsds");
     }
     if (verbosity || noop || stats) {  // showStatsHalf / showStatsWhole, :425-456
       char line[128];
@@ -76,9 +81,10 @@ int main(int argc, char* argv[]) {
       std::cerr << line;
     }
     if (!binary.empty()) writeNpy(binary, M.data(), rows, cols, rows);
-    if (!noop) {
+    if (gpu_text) fflush(stdout);
+    if (!noop && !gpu_text) {
       std::cout << "# " << header << std::endl;
-      writeMatrix(std::cout, M.data(), rows, cols, rows, (unsigned)o.uns("precision"));
+      writeMatrix(std::cout, M.data(), rows, cols, rows, precision);
     }
   } catch (const std::exception& e) {
     std::cerr << e.what() << std::endl;

@@ -2,6 +2,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <iostream>
 #include <memory>
 #include <string>
@@ -36,6 +37,16 @@ inline int engineOf(const Options& o) {
   if (e == "fp64") return LOOSB200_ENGINE_FP64;
   if (e == "auto") return LOOSB200_ENGINE_AUTO;
   throw Error("the argument ('" + e + "') for option '--engine' is invalid");
+}
+
+// loosb200_sink writing to stdout: the matrix text arrives already formatted from the GPU
+inline int stdoutSink(void*, const char* data, size_t n) { return fwrite(data, 1, n, stdout) == n ? 0 : 1; }
+// The GPU formats the text unless the float matrix itself is needed on the host (--binary, or
+// rms-overlap's fractional statistics), the precision exceeds what it handles exactly, or
+// LOOSB200_HOST_TEXT=1 asks for the host writer.
+inline bool gpuText(bool need_host_matrix, unsigned long precision) {
+  const char* env = getenv("LOOSB200_HOST_TEXT");
+  return !need_host_matrix && precision <= 9 && !(env && atoi(env) != 0);
 }
 
 struct Frames {  // RAII around loosb200_frames

@@ -348,3 +348,27 @@ def test_atom_limit_of_the_tensor_engine(lb, checker):
         Ma, _ = lb.rmsds(fs, engine="auto")
         Mf1, _ = lb.rmsds(fs, engine="fp64")
     assert np.array_equal(Ma, Mf1)
+
+
+@pytest.mark.parametrize("precision", [0, 2, 6, 9])
+def test_matrix_text_formatted_on_the_gpu(lb, precision):
+    """loosb200_rmsds_self_text / _cross_text: the text leaves the GPU already formatted.  Same bytes
+    as the reference's `cout << setprecision(p) << M` (checked through the oracle's matrix_text of
+    the float32 matrix the library returns), for the symmetric and the rectangular matrix, with
+    rows longer than one chunk, zeros on the diagonal and values needing every notation."""
+    from loos_b200.api import rmsds_text
+    from loos_b200.synth import synth_frames
+    from oracle.oracle import matrix_text
+    X = synth_frames(1100, 40, seed=5)              # 1100 values per row: two chunks
+    X[7] = X[6]                                     # an exact 0 off the diagonal
+    X[9] = X[8] * (1 + 1e-6)                        # a tiny RMSD (scientific notation at low precision)
+    X[11] = X[10] * 40.0                            # a large one
+    Y = synth_frames(37, 40, seed=6)
+    with lb.FrameSet(X) as fs, lb.FrameSet(Y) as fy:
+        M, st = lb.rmsds(fs, engine="tensor")
+        text, st2 = rmsds_text(fs, precision=precision, engine="tensor")
+        Cm, _ = lb.rmsds_cross(fs, fy, engine="tensor")
+        ctext, _ = rmsds_text(fs, fy, precision=precision, engine="tensor")
+    assert st2["max"] == st["max"] and st2["count"] == st["count"]
+    assert text.decode() == matrix_text(M, precision)
+    assert ctext.decode() == matrix_text(Cm, precision)
