@@ -35,7 +35,6 @@ int main(int argc, char* argv[]) {
     const unsigned precision = (unsigned)o.uns("precision");
     const bool gpu_text = !noop && gpuText(!binary.empty(), precision);  // text formatted on the GPU
     const bool want_m = (!noop || !binary.empty()) && !gpu_text;
-    if (gpu_text) { std::cout << "# " << header << std::endl; std::cout.flush(); }
     const int device = (int)o.uns("gpu"), engine = engineOf(o);
 
     Model model = readPDB(o.str("model1"));
@@ -56,7 +55,10 @@ int main(int argc, char* argv[]) {
     if (!o.has("model2")) {
       if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
       if (want_m) M.assign(rows * cols, 0.0f);
-      if (gpu_text) check(loosb200_rmsds_self_text(A.h, precision, stdoutSink, nullptr, &st, engine), "rmsds");
+      if (gpu_text) {
+        std::cout << "# " << header << std::endl;
+        check(loosb200_rmsds_self_text(A.h, precision, stdoutSink, nullptr, &st, engine), "rmsds");
+      }
       else check(loosb200_rmsds_self(A.h, want_m ? M.data() : nullptr, rows, &st, engine), "rmsds");
     } else {
       Model model2 = readPDB(o.str("model2"));
@@ -72,7 +74,10 @@ int main(int argc, char* argv[]) {
       cols = indices2.size();
       if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
       if (want_m) M.assign(rows * cols, 0.0f);
-      if (gpu_text) check(loosb200_rmsds_cross_text(A.h, B.h, precision, stdoutSink, nullptr, &st, engine), "rmsds");
+      if (gpu_text) {
+        std::cout << "# " << header << std::endl;
+        check(loosb200_rmsds_cross_text(A.h, B.h, precision, stdoutSink, nullptr, &st, engine), "rmsds");
+      }
       else check(loosb200_rmsds_cross(A.h, B.h, want_m ? M.data() : nullptr, rows, &st, engine), "rmsds");
     }
     if (verbosity || noop || stats) {  // showStatsHalf / showStatsWhole, :425-456
