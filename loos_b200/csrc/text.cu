@@ -241,63 +241,95 @@ int stream_matrix_text(const float* d_M, size_t m, size_t n, size_t ld, bool sym
     k_transpose<<<grid, block, 0, st>>>(d_M, ld, m, n, d_T);
     rows_src = d_T; pitch = n;
   }
+  // Batches of rows (<= 256 MB of text), two buffers deep: while batch b is being formatted, the text
+  // of batch b-1 is on its way to the host on a second stream and the sink consumes batch b-2.
   const size_t worst_row = n * (size_t)(precision + 7) + 1;
-  size_t batch = std::max<size_t>(1, std::min<size_t>(m, ((size_t)256 << 20) / worst_row));
-  char* d_text = nullptr;
-  char* h_text = nullptr;
+  const size_t batch = std::max<size_t>(1, std::min<size_t>(m, ((size_t)256 << 20) / worst_row));
+  const size_t cap = batch * worst_row + 64;
+  char* d_text[2] = {nullptr, nullptr};
+  char* h_text[2] = {nullptr, nullptr};
   unsigned long long *d_len = nullptr, *d_off = nullptr;
   int* d_slow = nullptr;
-  const size_t cap = batch * worst_row + 64;
-  bool ok = dev_alloc_t(&d_text, cap) == cudaSuccess && dev_alloc_t(&d_len, sizeof(unsigned long long) * batch) == cudaSuccess &&
+  cudaStream_t cst = nullptr;
+  cudaEvent_t formatted[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+  bool ok = dev_alloc_t(&d_len, sizeof(unsigned long long) * batch) == cudaSuccess &&
             dev_alloc_t(&d_off, sizeof(unsigned long long) * batch) == cudaSuccess &&
             dev_alloc_t(&d_slow, sizeof(int) * batch) == cudaSuccess &&
-            host_alloc(reinterpret_cast<void**>(&h_text), cap) == cudaSuccess;
+            cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking) == cudaSuccess;
+  for (int k = 0; k < 2 && ok; ++k)
+    ok = dev_alloc_t(&d_text[k], cap) == cudaSuccess && host_alloc(reinterpret_cast<void**>(&h_text[k]), cap) == cudaSuccess &&
+         cudaEventCreateWithFlags(&formatted[k], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming) == cudaSuccess;
   auto cleanup = [&]() {
-    dev_release(d_text); dev_release(d_len); dev_release(d_off); dev_release(d_slow); dev_release(d_T); host_release(h_text);
+    for (int k = 0; k < 2; ++k) {
+      dev_release(d_text[k]); host_release(h_text[k]);
+      if (formatted[k]) cudaEventDestroy(formatted[k]);
+      if (copied[k]) cudaEventDestroy(copied[k]);
+    }
+    dev_release(d_len); dev_release(d_off); dev_release(d_slow); dev_release(d_T);
+    if (cst) cudaStreamDestroy(cst);
   };
   if (!ok) { cudaGetLastError(); cleanup(); return LOOSB200_ERR_NOMEM; }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  std::vector<unsigned long long> len(batch), off(batch);
-  std::vector<int> slow(batch);
+  struct Batch { size_t r0; uint32_t nr; unsigned long long total; std::vector<unsigned long long> len, off; std::vector<int> slow; };
+  Batch bt[2];
   std::vector<float> rowbuf;
   int rc = LOOSB200_OK;
-  for (size_t r0 = 0; r0 < m && rc == LOOSB200_OK; r0 += batch) {
-    const uint32_t nr = (uint32_t)std::min(batch, m - r0);
-    const unsigned grid = (unsigned)std::min<size_t>(nr, (size_t)sms * 8);
-    cudaMemsetAsync(d_slow, 0, sizeof(int) * nr, st);
-    k_text_rows<false><<<grid, TX_THREADS, 0, st>>>(rows_src, pitch, n, r0, nr, precision, d_len, nullptr, nullptr, d_slow);
-    cudaMemcpyAsync(len.data(), d_len, sizeof(unsigned long long) * nr, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(slow.data(), d_slow, sizeof(int) * nr, cudaMemcpyDeviceToHost, st);
+
+  auto issue = [&](size_t r0, int k) -> int {  // format rows [r0, r0 + nr) into d_text[k], start its copy to h_text[k]
+    Batch& B = bt[k];
+    B.r0 = r0; B.nr = (uint32_t)std::min(batch, m - r0);
+    B.len.resize(B.nr); B.off.resize(B.nr); B.slow.resize(B.nr);
+    const unsigned grid = (unsigned)std::min<size_t>(B.nr, (size_t)sms * 8);
+    cudaMemsetAsync(d_slow, 0, sizeof(int) * B.nr, st);
+    k_text_rows<false><<<grid, TX_THREADS, 0, st>>>(rows_src, pitch, n, r0, B.nr, precision, d_len, nullptr, nullptr, d_slow);
+    cudaMemcpyAsync(B.len.data(), d_len, sizeof(unsigned long long) * B.nr, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(B.slow.data(), d_slow, sizeof(int) * B.nr, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { rc = cuda_fail(e, "matrix text (lengths)", __FILE__, __LINE__); break; }
-    unsigned long long total = 0;
-    for (uint32_t r = 0; r < nr; ++r) { off[r] = total; total += len[r]; }
-    cudaMemcpyAsync(d_off, off.data(), sizeof(unsigned long long) * nr, cudaMemcpyHostToDevice, st);
-    k_text_rows<true><<<grid, TX_THREADS, 0, st>>>(rows_src, pitch, n, r0, nr, precision, nullptr, d_off, d_text, nullptr);
-    cudaMemcpyAsync(h_text, d_text, total, cudaMemcpyDeviceToHost, st);
-    e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) { rc = cuda_fail(e, "matrix text", __FILE__, __LINE__); break; }
+    if (e != cudaSuccess) return cuda_fail(e, "matrix text (lengths)", __FILE__, __LINE__);
+    B.total = 0;
+    for (uint32_t r = 0; r < B.nr; ++r) { B.off[r] = B.total; B.total += B.len[r]; }
+    cudaMemcpyAsync(d_off, B.off.data(), sizeof(unsigned long long) * B.nr, cudaMemcpyHostToDevice, st);
+    k_text_rows<true><<<grid, TX_THREADS, 0, st>>>(rows_src, pitch, n, r0, B.nr, precision, nullptr, d_off, d_text[k], nullptr);
+    cudaEventRecord(formatted[k], st);
+    cudaStreamWaitEvent(cst, formatted[k], 0);
+    cudaMemcpyAsync(h_text[k], d_text[k], B.total, cudaMemcpyDeviceToHost, cst);
+    cudaEventRecord(copied[k], cst);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? LOOSB200_OK : cuda_fail(e, "matrix text", __FILE__, __LINE__);
+  };
+  auto retire = [&](int k) -> int {  // hand the text of the batch in buffer k to the sink
+    Batch& B = bt[k];
+    const cudaError_t e = cudaEventSynchronize(copied[k]);
+    if (e != cudaSuccess) return cuda_fail(e, "matrix text (copy)", __FILE__, __LINE__);
     bool any_slow = false;
-    for (uint32_t r = 0; r < nr; ++r) any_slow = any_slow || slow[r];
-    if (!any_slow) {
-      if (sink(user, h_text, (size_t)total)) rc = LOOSB200_ERR_INVALID;
-      continue;
-    }
+    for (uint32_t r = 0; r < B.nr; ++r) any_slow = any_slow || B.slow[r];
+    if (!any_slow) return sink(user, h_text[k], (size_t)B.total) ? LOOSB200_ERR_INVALID : LOOSB200_OK;
     // rows holding values outside the exact device range (|v| < 1e-5, >= 1e9, inf, nan): libc formats them
-    for (uint32_t r = 0; r < nr && rc == LOOSB200_OK; ++r) {
-      if (!slow[r]) { if (sink(user, h_text + off[r], (size_t)len[r])) rc = LOOSB200_ERR_INVALID; continue; }
+    for (uint32_t r = 0; r < B.nr; ++r) {
+      if (!B.slow[r]) { if (sink(user, h_text[k] + B.off[r], (size_t)B.len[r])) return LOOSB200_ERR_INVALID; continue; }
       rowbuf.resize(n);
-      cudaMemcpy(rowbuf.data(), rows_src + (r0 + r) * pitch, sizeof(float) * n, cudaMemcpyDeviceToHost);
+      if (cudaMemcpy(rowbuf.data(), rows_src + (B.r0 + r) * pitch, sizeof(float) * n, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return cuda_fail(cudaGetLastError(), "matrix text (row)", __FILE__, __LINE__);
       std::string line;
       char buf[48];
       for (size_t i = 0; i < n; ++i) { const int l = snprintf(buf, sizeof(buf), "%.*g ", (int)precision, (double)rowbuf[i]); line.append(buf, (size_t)l); }
       line += '\n';
-      if (sink(user, line.data(), line.size())) rc = LOOSB200_ERR_INVALID;
+      if (sink(user, line.data(), line.size())) return LOOSB200_ERR_INVALID;
     }
+    return LOOSB200_OK;
+  };
+
+  size_t nb = 0;
+  for (size_t r0 = 0; r0 < m && rc == LOOSB200_OK; r0 += batch, ++nb) {
+    rc = issue(r0, (int)(nb & 1));
+    if (rc == LOOSB200_OK && nb >= 1) rc = retire((int)((nb - 1) & 1));
   }
+  if (rc == LOOSB200_OK && nb >= 1) rc = retire((int)((nb - 1) & 1));
+  cudaStreamSynchronize(cst);
+  cudaStreamSynchronize(st);
   cleanup();
   return rc;
 }
