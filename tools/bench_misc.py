@@ -54,9 +54,35 @@ def rmsd2ref(F, N, steps=3):
     fs.close()
 
 
+def rmsd2ref_e2e(F, N, steps=2):
+    """C2 end to end: pinned host frames -> stage -> rmsd2ref -> host results (H2D of 12*N*F bytes dominates)."""
+    X = synth_frames_torch(F, N, seed=20261021, device="cuda", chunk=4096)
+    tgt = X[0].double().cpu().numpy()
+    Xh = torch.empty((F, N, 3), dtype=torch.float32, pin_memory=True)
+    Xh.copy_(X)
+    del X
+    torch.cuda.empty_cache()
+    xh = Xh.numpy()
+    ts = []
+    for _ in range(steps + 1):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        fs = lb.FrameSet(xh)
+        t1 = time.perf_counter()
+        d = lb.rmsd2ref(fs, tgt)
+        t2 = time.perf_counter()
+        fs.close()
+        ts.append((time.perf_counter() - t0, t1 - t0, t2 - t1))
+    tot, stage, comp = min(ts[1:])
+    print(json.dumps({"measure": "rmsd2ref_e2e", "frames": F, "atoms": N, "total_ms": 1e3 * tot, "stage_ms": 1e3 * stage,
+                      "rmsd2ref_ms": 1e3 * comp, "frames_per_s": F / tot, "h2d_GBps": F * N * 12 / stage / 1e9,
+                      "rmsd_mean": float(d.mean())}))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "pcie"):
         pcie()
+    if what in ("rmsd2ref_e2e",):
+        rmsd2ref_e2e(int(os.environ.get("C2_FRAMES", 1000000)), 2000)
     if what in ("all", "rmsd2ref"):
         rmsd2ref(int(os.environ.get("C2_FRAMES", 1000000)), 2000)
