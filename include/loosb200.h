@@ -137,7 +137,9 @@ int loosb200_rmsds_cross_device(loosb200_frames* a, loosb200_frames* b, float* o
  * followed by a space.  The float32 matrix stays in HBM; rows are formatted there (exact integer
  * arithmetic, the same bytes as printf) and only the text crosses PCIe, in row order, through
  * `sink(user, data, nbytes)` (return non-zero to abort).  At 100 000 frames that is 45 GB of text,
- * which costs a minute of host time even on all cores.  precision 0..9. */
+ * which costs a minute of host time even on all cores.  precision 0..9.  If the F x F float
+ * matrix does not fit in device memory, bands of rows are computed as rectangles and streamed one
+ * after the other (same bytes, same stats). */
 typedef int (*loosb200_sink)(void* user, const char* data, size_t nbytes);
 int loosb200_rmsds_self_text(loosb200_frames* h, unsigned precision, loosb200_sink sink, void* user,
                              loosb200_stats* stats, int engine);

@@ -325,7 +325,10 @@ static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool sym
         cnt += (i1 * (i1 - 1) - i0 * (i0 ? i0 - 1 : 0)) / 2;
       }
     } else {
-      cnt = (uint64_t)FA * FB;
+      for (uint32_t t : rows) {
+        const uint64_t i0 = (uint64_t)t * TILE_FRAMES, i1 = std::min<uint64_t>(FA, i0 + TILE_FRAMES);
+        if (i1 > i0) cnt += (i1 - i0) * (uint64_t)FB;
+      }
     }
     stats->count = cnt;
   }
@@ -434,11 +437,42 @@ static int pairs_text(loosb200_frames* a, loosb200_frames* b, bool self, unsigne
   if (!sink) return LOOSB200_ERR_INVALID;
   LB_CUDA(cudaSetDevice(a->device));
   const size_t m = a->F, n = b->F;
-  float* d_M = nullptr;
-  if (dev_alloc_t(&d_M, sizeof(float) * std::max<size_t>(1, m * n)) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
-  int rc = run_pairs(a, b, self, self, false, all_rows(a->F), d_M, OutKind::Device, m, stats, engine);
-  if (rc == LOOSB200_OK) rc = stream_matrix_text(d_M, m, n, m, self, precision, sink, user, a->stream);
-  dev_release(d_M);
+  // The whole float matrix in HBM when it fits (one pass over the triangle, rows read back by symmetry);
+  // otherwise bands of rows computed as rectangles against every column -- memory is then bounded by
+  // the band, at twice the arithmetic of the triangle plus one stats-only pass.
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  const size_t full_bytes = sizeof(float) * std::max<size_t>(1, m * n) * (self ? 1 : 2);  // + transposed copy
+  size_t band_rows = 0;
+  if (const char* env = getenv("LOOSB200_TEXT_BAND_ROWS")) band_rows = (size_t)std::max(0, atoi(env));
+  else if (full_bytes + ((size_t)2 << 30) > free_b) band_rows = std::max<size_t>(TILE_FRAMES, ((size_t)8 << 30) / (sizeof(float) * n));
+  if (band_rows == 0) {
+    float* d_M = nullptr;
+    if (dev_alloc_t(&d_M, sizeof(float) * std::max<size_t>(1, m * n)) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
+    int rc = run_pairs(a, b, self, self, false, all_rows(a->F), d_M, OutKind::Device, m, stats, engine);
+    if (rc == LOOSB200_OK) rc = stream_matrix_text(d_M, m, n, m, self, precision, sink, user, a->stream);
+    dev_release(d_M);
+    return rc;
+  }
+  band_rows = (band_rows + TILE_FRAMES - 1) / TILE_FRAMES * TILE_FRAMES;
+  int rc = LOOSB200_OK;
+  if (stats && self) rc = run_pairs(a, b, true, false, false, all_rows(a->F), nullptr, OutKind::None, m, stats, engine);
+  if (stats && !self) { stats->sum = 0.0; stats->max = 0.0; stats->count = 0; }
+  if (rc == LOOSB200_OK) rc = matrix_text_header(m, n, sink, user);
+  float* d_band = nullptr;
+  if (rc == LOOSB200_OK && dev_alloc_t(&d_band, sizeof(float) * band_rows * n) != cudaSuccess) { cudaGetLastError(); rc = LOOSB200_ERR_NOMEM; }
+  for (size_t R0 = 0; R0 < m && rc == LOOSB200_OK; R0 += band_rows) {
+    const size_t R1 = std::min(m, R0 + band_rows);
+    std::vector<uint32_t> tiles;
+    for (size_t t = R0 / TILE_FRAMES; t * TILE_FRAMES < R1; ++t) tiles.push_back((uint32_t)t);
+    loosb200_stats bst;
+    rc = run_pairs(a, b, false, false, true, tiles, d_band, OutKind::Device, n, (stats && !self) ? &bst : nullptr, engine);
+    if (rc != LOOSB200_OK) break;
+    if (stats && !self) { stats->sum += bst.sum; stats->max = std::max(stats->max, bst.max); stats->count += bst.count; }
+    if (self) zero_band_diagonal(d_band, n, R0, (uint32_t)(R1 - R0), a->stream);
+    rc = stream_rows_text(d_band, n, R1 - R0, n, precision, sink, user, a->stream);
+  }
+  dev_release(d_band);
   return rc;
 }
 

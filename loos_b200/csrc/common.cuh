@@ -48,6 +48,12 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // text.cu: "# m n (0)" + the rows of a device matrix (column-major) as "%.{p}g " text through `sink`
 int stream_matrix_text(const float* d_M, size_t m, size_t n, size_t ld, bool symmetric, unsigned precision,
                        loosb200_sink sink, void* user, cudaStream_t st);
+// the pieces, for results that are produced band by band: header line; m rows of n values with row j
+// contiguous at rows_src + j * pitch; exact zeros on the diagonal of rows [R0, R0 + nrows) of a band
+int matrix_text_header(size_t m, size_t n, loosb200_sink sink, void* user);
+int stream_rows_text(const float* rows_src, size_t pitch, size_t m, size_t n, unsigned precision,
+                     loosb200_sink sink, void* user, cudaStream_t st);
+void zero_band_diagonal(float* band, size_t pitch, size_t R0, uint32_t nrows, cudaStream_t st);
 
 #define LB_CUDA(call)                                                       \
   do {                                                                      \

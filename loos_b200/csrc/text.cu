@@ -220,27 +220,46 @@ __global__ void k_transpose(const float* __restrict__ in, size_t ld, size_t rows
   }
 }
 
+// rows [R0, R0 + nrows) of a self matrix computed as a rectangle: M(i, i) = 0 exactly
+// (SingleWorker::calc never writes the diagonal, Tools/rmsds.cpp:359-365)
+__global__ void k_zero_diag(float* band, size_t pitch, size_t R0, uint32_t nrows) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nrows) band[(size_t)r * pitch + R0 + r] = 0.0f;
+}
+
 }  // namespace
+
+void zero_band_diagonal(float* band, size_t pitch, size_t R0, uint32_t nrows, cudaStream_t st) {
+  k_zero_diag<<<(nrows + 255) / 256, 256, 0, st>>>(band, pitch, R0, nrows);
+}
+
+int matrix_text_header(size_t m, size_t n, loosb200_sink sink, void* user) {
+  char head[64];
+  const int hl = snprintf(head, sizeof(head), "# %zu %zu (0)\n", m, n);
+  return sink(user, head, (size_t)hl) ? LOOSB200_ERR_INVALID : LOOSB200_OK;
+}
 
 // Streams "# m n (0)\n" and the m rows of the device matrix (column-major, M(i,j) at d_M[j*ld + i])
 // to `sink`.  `symmetric`: M(i,j) == M(j,i), so row j is read from column j.
 int stream_matrix_text(const float* d_M, size_t m, size_t n, size_t ld, bool symmetric, unsigned precision,
                        loosb200_sink sink, void* user, cudaStream_t st) {
+  int rc = matrix_text_header(m, n, sink, user);
+  if (rc) return rc;
+  if (symmetric) return stream_rows_text(d_M, ld, m, n, precision, sink, user, st);
+  float* d_T = nullptr;
+  if (dev_alloc_t(&d_T, sizeof(float) * m * n) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
+  dim3 grid((unsigned)((m + 31) / 32), (unsigned)((n + 31) / 32)), block(32, 8);
+  k_transpose<<<grid, block, 0, st>>>(d_M, ld, m, n, d_T);
+  rc = stream_rows_text(d_T, n, m, n, precision, sink, user, st);
+  dev_release(d_T);
+  return rc;
+}
+
+// m rows of n values, row j contiguous at rows_src + j * pitch, as text lines through `sink`.
+int stream_rows_text(const float* rows_src, size_t pitch, size_t m, size_t n, unsigned precision,
+                     loosb200_sink sink, void* user, cudaStream_t st) {
   if (precision == 0) precision = 1;  // "%.0g" formats like "%.1g"
   if (precision > 9) return LOOSB200_ERR_UNSUPPORTED;
-  char head[64];
-  const int hl = snprintf(head, sizeof(head), "# %zu %zu (0)\n", m, n);
-  if (sink(user, head, (size_t)hl)) return LOOSB200_ERR_INVALID;
-
-  const float* rows_src = d_M;
-  size_t pitch = ld;
-  float* d_T = nullptr;
-  if (!symmetric) {
-    if (dev_alloc_t(&d_T, sizeof(float) * m * n) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
-    dim3 grid((unsigned)((m + 31) / 32), (unsigned)((n + 31) / 32)), block(32, 8);
-    k_transpose<<<grid, block, 0, st>>>(d_M, ld, m, n, d_T);
-    rows_src = d_T; pitch = n;
-  }
   // Batches of rows (<= 256 MB of text), two buffers deep: while batch b is being formatted, the text
   // of batch b-1 is on its way to the host on a second stream and the sink consumes batch b-2.
   const size_t worst_row = n * (size_t)(precision + 7) + 1;
@@ -266,7 +285,7 @@ int stream_matrix_text(const float* d_M, size_t m, size_t n, size_t ld, bool sym
       if (formatted[k]) cudaEventDestroy(formatted[k]);
       if (copied[k]) cudaEventDestroy(copied[k]);
     }
-    dev_release(d_len); dev_release(d_off); dev_release(d_slow); dev_release(d_T);
+    dev_release(d_len); dev_release(d_off); dev_release(d_slow);
     if (cst) cudaStreamDestroy(cst);
   };
   if (!ok) { cudaGetLastError(); cleanup(); return LOOSB200_ERR_NOMEM; }

@@ -372,3 +372,22 @@ def test_matrix_text_formatted_on_the_gpu(lb, precision):
     assert st2["max"] == st["max"] and st2["count"] == st["count"]
     assert text.decode() == matrix_text(M, precision)
     assert ctext.decode() == matrix_text(Cm, precision)
+
+
+def test_matrix_text_in_row_bands(lb, monkeypatch):
+    """When the F x F float matrix does not fit in HBM the text is produced from bands of rows computed
+    as rectangles (LOOSB200_TEXT_BAND_ROWS forces it here): identical bytes, identical stats, exact
+    zeros on the diagonal, for the self and the cross matrix, with a ragged last band."""
+    from loos_b200.api import rmsds_text
+    from loos_b200.synth import synth_frames
+    X = synth_frames(333, 50, seed=15)
+    Y = synth_frames(61, 50, seed=16)
+    with lb.FrameSet(X) as fs, lb.FrameSet(Y) as fy:
+        whole, st = rmsds_text(fs, precision=7, engine="tensor")
+        cwhole, cst = rmsds_text(fs, fy, precision=7, engine="tensor")
+        monkeypatch.setenv("LOOSB200_TEXT_BAND_ROWS", "120")
+        banded, bst = rmsds_text(fs, precision=7, engine="tensor")
+        cbanded, cbst = rmsds_text(fs, fy, precision=7, engine="tensor")
+    assert banded == whole and cbanded == cwhole
+    assert bst["count"] == st["count"] and bst["max"] == st["max"] and abs(bst["sum"] - st["sum"]) < 1e-6
+    assert cbst["count"] == cst["count"] and cbst["max"] == cst["max"] and abs(cbst["sum"] - cst["sum"]) < 1e-6 * cst["sum"]
