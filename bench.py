@@ -277,6 +277,10 @@ def main():
     N = args.atoms or N
     pairs_total = F * (F - 1) // 2
     peaks, peaks_kind = load_peaks()
+    # the result stays in HBM (F x F float32 on one GPU, packed row blocks otherwise): refuse what cannot fit
+    out_bytes = 4 * F * F if world == 1 else 4 * F * (F // world + 80)
+    if out_bytes + 12 * F * N + 9 * F * (N + 128) > 170e9:
+        raise SystemExit("workload %s needs %.0f GB of HBM per GPU at --gpus %d; use more GPUs" % (args.workload, out_bytes / 1e9, world))
 
     X = synth_frames_torch(F, N, seed=SEED0 + 4, device=dev)   # same frames on every rank
     torch.cuda.synchronize()
