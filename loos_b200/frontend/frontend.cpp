@@ -724,14 +724,206 @@ void AmberNetcdf::readFramePlanes(uint32_t i, float* out) {  // readRawFrame + u
   }
 }
 
+// =================================================================== GROMACS XTC
+
+namespace {
+
+// the xdrfile table of "small" ranges: index smallidx selects how many values a small difference may take
+const int kXtcMagicInts[] = {
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 8, 10, 12, 16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322, 406, 512,
+    645, 812, 1024, 1290, 1625, 2048, 2580, 3250, 4096, 5060, 6501, 8192, 10321, 13003, 16384, 20642, 26007,
+    32768, 41285, 52015, 65536, 82570, 104031, 131072, 165140, 208063, 262144, 330280, 416127, 524287, 660561,
+    832255, 1048576, 1321122, 1664510, 2097152, 2642245, 3329021, 4194304, 5284491, 6658042, 8388607, 10568983,
+    13316085, 16777216};
+const int kXtcFirstIdx = 9;
+const int kXtcMagic = 1995;
+
+struct XdrIn {  // big-endian 4-byte items
+  std::ifstream& f;
+  const std::string& name;
+  bool u32(uint32_t* v) {
+    unsigned char b[4];
+    f.read((char*)b, 4);
+    if (!f) return false;
+    *v = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+    return true;
+  }
+  bool i32(int* v) { uint32_t u; if (!u32(&u)) return false; *v = (int)u; return true; }
+  bool f32(float* v) { uint32_t u; if (!u32(&u)) return false; memcpy(v, &u, 4); return true; }
+};
+
+struct BitIn {  // most-significant-bit-first reader over the compressed block
+  const unsigned char* p;
+  size_t n, pos = 0;  // pos in bits
+  uint32_t take(unsigned nbits) {  // nbits <= 32
+    uint32_t v = 0;
+    for (unsigned k = 0; k < nbits; ++k, ++pos) {
+      const size_t byte = pos >> 3;
+      const unsigned bit = byte < n ? (p[byte] >> (7 - (pos & 7))) & 1u : 0u;
+      v = (v << 1) | bit;
+    }
+    return v;
+  }
+  // three values packed as one number in the mixed radix (sizes[1], sizes[2]), stored least significant
+  // BYTE first, each byte most significant bit first (decodeints, src/xtc.cpp:132-158)
+  void take3(unsigned nbits, const uint32_t sizes[3], int out[3]) {
+    unsigned __int128 v = 0;
+    unsigned shift = 0;
+    while (nbits > 8) { v |= (unsigned __int128)take(8) << shift; shift += 8; nbits -= 8; }
+    if (nbits > 0) v |= (unsigned __int128)take(nbits) << shift;
+    out[2] = (int)(uint32_t)(v % sizes[2]); v /= sizes[2];
+    out[1] = (int)(uint32_t)(v % sizes[1]); v /= sizes[1];
+    out[0] = (int)(uint32_t)v;
+  }
+};
+
+unsigned bitLength(unsigned __int128 v) { unsigned n = 0; while (v) { ++n; v >>= 1; } return n; }
+
+}  // namespace
+
+XTC::XTC(const std::string& path) : path_(path), ifs_(path.c_str(), std::ios::binary) {
+  if (!ifs_) throw Error("Error- cannot open " + path);
+  XdrIn x{ifs_, path_};
+  ifs_.seekg(0, std::ios::end);
+  const uint64_t file_size = (uint64_t)ifs_.tellg();
+  ifs_.seekg(0);
+  // scanFrames (src/xtc.cpp:421-477): walk the frames, remember where each one starts
+  for (;;) {
+    const uint64_t pos = (uint64_t)ifs_.tellg();
+    int magic;
+    if (!x.i32(&magic)) break;  // clean end of file
+    if (magic != kXtcMagic)
+      throw Error("Error- " + path + ": Invalid XTC magic number (got " + std::to_string(magic) + " but expected " + std::to_string(kXtcMagic) + ")");
+    uint32_t na, step;
+    float time, box[9];
+    bool ok = x.u32(&na) && x.u32(&step) && x.f32(&time);
+    for (int k = 0; k < 9 && ok; ++k) ok = x.f32(&box[k]);
+    if (!ok) throw Error("Error- " + path + ": Problem reading XTC header");
+    if (natoms_ == 0) natoms_ = na;
+    else if (natoms_ != na) throw Error("Error- " + path + ": XTC frames have differing numbers of atoms");
+    uint32_t nbytes;
+    if (natoms_ <= 9) {
+      uint32_t lsize;
+      if (!x.u32(&lsize) || lsize != natoms_) throw Error("Error- " + path + ": XTC small system vector size is not what was expected");
+      nbytes = natoms_ * 12;
+    } else {
+      ifs_.seekg(9 * 4, std::ios::cur);  // natoms, precision, minint[3], maxint[3], smallidx
+      if (!x.u32(&nbytes)) throw Error("Error- " + path + ": Problem scanning XTC trajectory to build frame indices");
+    }
+    ifs_.seekg((std::streamoff)((nbytes + 3) / 4 * 4), std::ios::cur);
+    // a seek past the end succeeds on a file; a frame cut short is an error here, not a frame
+    if (!ifs_ || (uint64_t)ifs_.tellg() > file_size)
+      throw Error("Error- " + path + ": XTC frame " + std::to_string(frame_pos_.size()) + " is truncated");
+    frame_pos_.push_back(pos);
+  }
+  ifs_.clear();
+  if (frame_pos_.empty()) throw Error("Error- " + path + ": Unable to read in the first frame");
+}
+
+void XTC::readFramePlanes(uint32_t fi, float* out) {
+  if (fi >= frame_pos_.size()) throw Error("Error- " + path_ + ": Requested XTC frame is out of range");
+  ifs_.clear();
+  ifs_.seekg((std::streamoff)(frame_pos_[fi] + 13 * 4));  // past magic, natoms, step, time, box
+  XdrIn x{ifs_, path_};
+  uint32_t lsize;
+  if (!x.u32(&lsize) || lsize != natoms_) throw Error("Error- " + path_ + ": Problem reading XTC frame");
+  const size_t n = natoms_;
+  if (lsize <= 9) {  // plain floats, nm
+    for (size_t k = 0; k < n; ++k)
+      for (int ax = 0; ax < 3; ++ax) {
+        float v;
+        if (!x.f32(&v)) throw Error("Error- " + path_ + ": XTC Error: number of uncompressed coords read did not match number expected");
+        out[ax * n + k] = (float)((double)v * 10.0);
+      }
+    return;
+  }
+  float precision;
+  int minint[3], maxint[3], smallidx;
+  bool ok = x.f32(&precision);
+  for (int k = 0; k < 3 && ok; ++k) ok = x.i32(&minint[k]);
+  for (int k = 0; k < 3 && ok; ++k) ok = x.i32(&maxint[k]);
+  uint32_t nbytes = 0;
+  ok = ok && x.i32(&smallidx) && x.u32(&nbytes);
+  if (!ok || smallidx < kXtcFirstIdx || smallidx >= (int)(sizeof(kXtcMagicInts) / sizeof(int)) || nbytes > (1u << 30))
+    throw Error("Error- " + path_ + ": Problem reading XTC frame");
+  bits_.resize(nbytes);
+  ifs_.read((char*)bits_.data(), nbytes);
+  if (!ifs_) throw Error("Error- " + path_ + ": Problem reading XTC frame");
+
+  uint32_t sizeint[3], bitsizeint[3] = {0, 0, 0};
+  for (int k = 0; k < 3; ++k) sizeint[k] = (uint32_t)(maxint[k] - minint[k] + 1);
+  unsigned bitsize;
+  if ((sizeint[0] | sizeint[1] | sizeint[2]) > 0xffffffu) {  // too large to pack as one number: separate fields
+    for (int k = 0; k < 3; ++k) bitsizeint[k] = bitLength(sizeint[k]);
+    bitsize = 0;
+  } else {
+    bitsize = bitLength((unsigned __int128)sizeint[0] * sizeint[1] * sizeint[2]);
+  }
+  int smaller = kXtcMagicInts[std::max(kXtcFirstIdx, smallidx - 1)] / 2;
+  int smallnum = kXtcMagicInts[smallidx] / 2;
+  uint32_t sizesmall[3] = {(uint32_t)kXtcMagicInts[smallidx], (uint32_t)kXtcMagicInts[smallidx], (uint32_t)kXtcMagicInts[smallidx]};
+  const float inv_precision = 1.0f / precision;
+  auto emit = [&](size_t atom, const int c[3]) {
+    if (atom >= n) throw Error("Error- " + path_ + ": corrupt XTC frame (more atoms than announced)");
+    for (int ax = 0; ax < 3; ++ax) out[ax * n + atom] = (float)((double)((float)c[ax] * inv_precision) * 10.0);
+  };
+  BitIn in{bits_.data(), bits_.size()};
+  size_t i = 0;
+  int run = 0;
+  while (i < n) {
+    int cur[3], prev[3];
+    if (bitsize == 0) for (int k = 0; k < 3; ++k) cur[k] = (int)in.take(bitsizeint[k]);
+    else in.take3(bitsize, sizeint, cur);
+    for (int k = 0; k < 3; ++k) { cur[k] += minint[k]; prev[k] = cur[k]; }
+    int is_smaller = 0;
+    if (in.take(1)) {  // the run length (and the change of the small range) is stated anew
+      run = (int)in.take(5);
+      is_smaller = run % 3;
+      run -= is_smaller;
+      --is_smaller;
+    }
+    if (run > 0) {
+      for (int k = 0; k < run; k += 3) {
+        int d[3];
+        in.take3((unsigned)smallidx, sizesmall, d);
+        for (int q = 0; q < 3; ++q) d[q] += prev[q] - smallnum;
+        if (k == 0) {  // the writer stored the second atom of the run first (water: O after H): swap back
+          emit(i, d);
+          emit(i + 1, cur);
+          i += 2;
+        } else {
+          emit(i, d);
+          ++i;
+        }
+        for (int q = 0; q < 3; ++q) prev[q] = d[q];  // differences chain through the small-coded atoms
+      }
+    } else {
+      emit(i, cur);
+      ++i;
+    }
+    smallidx += is_smaller;
+    if (is_smaller < 0) {
+      smallnum = smaller;
+      smaller = smallidx > kXtcFirstIdx ? kXtcMagicInts[smallidx - 1] / 2 : 0;
+    } else if (is_smaller > 0) {
+      smaller = smallnum;
+      smallnum = kXtcMagicInts[smallidx] / 2;
+    }
+    if (smallidx < kXtcFirstIdx || smallidx >= (int)(sizeof(kXtcMagicInts) / sizeof(int)))
+      throw Error("Error- " + path_ + ": corrupt XTC frame");
+    sizesmall[0] = sizesmall[1] = sizesmall[2] = (uint32_t)kXtcMagicInts[smallidx];
+  }
+}
+
 std::shared_ptr<Trajectory> openTrajectory(const std::string& path, uint32_t natoms) {
   const size_t dot = path.rfind('.');
   std::string suffix = dot == std::string::npos ? "" : path.substr(dot + 1);
   std::transform(suffix.begin(), suffix.end(), suffix.begin(), ::tolower);
   if (suffix == "dcd") return std::make_shared<DCD>(path);
+  if (suffix == "xtc") return std::make_shared<XTC>(path);
   if (suffix == "nc" || suffix == "netcdf") return std::make_shared<AmberNetcdf>(path, natoms);
   if ((suffix == "crd" || suffix == "mdcrd") && AmberNetcdf::isNetcdf(path)) return std::make_shared<AmberNetcdf>(path, natoms);
-  throw Error("Error- unknown or unsupported trajectory format for '" + path + "' (supported here: dcd, nc/netcdf)");
+  throw Error("Error- unknown or unsupported trajectory format for '" + path + "' (supported here: dcd, xtc, nc/netcdf)");
 }
 
 uint32_t MultiTraj::nframes(size_t i) const {

@@ -115,6 +115,30 @@ class AmberNetcdf : public Trajectory {
   std::vector<unsigned char> raw_;
 };
 
+// ---- GROMACS XTC trajectories (src/xtc.cpp:165-486; format of the xdrfile library) ----
+// XDR (big-endian) frames: magic 1995, natoms, step, time, box[9], natoms again; up to 9 atoms as plain
+// floats, otherwise precision, integer bounding box, the "small" table index and a bit stream in which
+// every atom is either three integers packed against the bounding box or a short run of small
+// differences to its predecessor (with the first two atoms of a run swapped: water molecules).
+// Coordinates come out as the reference computes them: (float)int * (1 / precision) in float, times
+// 10.0 in double (nm -> Angstrom).  The frame index is built by one scan over the file (scanFrames).
+class XTC : public Trajectory {
+ public:
+  explicit XTC(const std::string& path);
+  uint32_t natoms() const override { return natoms_; }
+  uint32_t nframes() const override { return (uint32_t)frame_pos_.size(); }
+  const std::string& filename() const override { return path_; }
+  void readFramePlanes(uint32_t i, float* out) override;
+
+ private:
+  std::string path_;
+  std::ifstream ifs_;
+  uint32_t natoms_ = 0;
+  std::vector<uint64_t> frame_pos_;
+  std::vector<unsigned char> bits_;
+  std::vector<int> ints_;
+};
+
 // ---- MultiTrajectory indexing (src/MultiTraj.hpp:98-105, src/MultiTraj.cpp:48-58) ----
 struct MultiTraj {
   std::vector<std::shared_ptr<Trajectory>> trajs;

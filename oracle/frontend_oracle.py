@@ -323,3 +323,238 @@ def read_dcd(path):
             out[f, k] = np.frombuffer(b, dtype=np.dtype(np.float32).newbyteorder(e), count=natoms, offset=q + 4)
             q += 8 + 4 * natoms
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# GROMACS XTC (test infrastructure).  The reference reads XTC with src/xtc.cpp (165-486) and writes
+# it with src/xtcwriter.cpp (387-655), both following the xdrfile library.  No XTC file ships with
+# the reference and no other XTC implementation exists in this image, so the native reader
+# (loos_b200/frontend) is checked against files produced by `write_xtc` below, a restatement of the
+# reference's writer, and against `read_xtc`, a restatement of its reader -- parity with files
+# written by GROMACS itself is UNPINNED.
+
+XTC_MAGICINTS = [
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 8, 10, 12, 16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322, 406, 512,
+    645, 812, 1024, 1290, 1625, 2048, 2580, 3250, 4096, 5060, 6501, 8192, 10321, 13003, 16384, 20642, 26007,
+    32768, 41285, 52015, 65536, 82570, 104031, 131072, 165140, 208063, 262144, 330280, 416127, 524287, 660561,
+    832255, 1048576, 1321122, 1664510, 2097152, 2642245, 3329021, 4194304, 5284491, 6658042, 8388607, 10568983,
+    13316085, 16777216]
+XTC_FIRSTIDX = 9
+
+
+class _BitsOut:
+    def __init__(self):
+        self.bits = []
+
+    def put(self, nbits, value):
+        for k in range(nbits - 1, -1, -1):
+            self.bits.append((value >> k) & 1)
+
+    def put3(self, nbits, sizes, nums):
+        """encodeints (src/xtcwriter.cpp:334-381): one number in mixed radix, least significant byte first."""
+        v = (int(nums[0]) * int(sizes[1]) + int(nums[1])) * int(sizes[2]) + int(nums[2])
+        nb = max(1, (v.bit_length() + 7) // 8)
+        by = v.to_bytes(nb, "little")
+        if nbits >= nb * 8:
+            for b in by:
+                self.put(8, b)
+            self.put(nbits - nb * 8, 0)
+        else:
+            for b in by[:-1]:
+                self.put(8, b)
+            self.put(nbits - (nb - 1) * 8, by[-1])
+
+    def tobytes(self):
+        bits = self.bits + [0] * ((-len(self.bits)) % 8)
+        return bytes(int("".join(map(str, bits[k:k + 8])), 2) for k in range(0, len(bits), 8))
+
+
+def _xtc_bitsize(sizeint):
+    if (sizeint[0] | sizeint[1] | sizeint[2]) > 0xffffff:
+        return 0, [int(s).bit_length() for s in sizeint]
+    return (int(sizeint[0]) * int(sizeint[1]) * int(sizeint[2])).bit_length(), [0, 0, 0]
+
+
+def write_xtc(path, frames_angstrom, precision=1000.0, box_nm=(5.0, 6.0, 7.0), dt=1.0):
+    """frames_angstrom: (F, N, 3).  Compression as the reference's writer does it
+    (writeCompressedCoordsFloat, src/xtcwriter.cpp:387-655)."""
+    import struct
+    X = np.asarray(frames_angstrom, dtype=np.float64)
+    F, N, _ = X.shape
+    prec = np.float32(precision)
+    with open(path, "wb") as f:
+        for fi in range(F):
+            nm = (X[fi] / 10.0).astype(np.float32)
+            box = [0.0] * 9
+            box[0], box[4], box[8] = box_nm
+            f.write(struct.pack(">iiif9f", 1995, N, fi, fi * dt, *box))
+            f.write(struct.pack(">i", N))
+            if N <= 9:
+                f.write(nm.astype(">f4").tobytes())
+                continue
+            f.write(struct.pack(">f", float(prec)))
+            lf = nm * prec + np.where(nm >= 0, np.float32(0.5), np.float32(-0.5)).astype(np.float32)   # float32 arithmetic
+            ints = np.trunc(lf.astype(np.float64)).astype(np.int64).reshape(N, 3)          # (int) truncates
+            minint, maxint = ints.min(axis=0), ints.max(axis=0)
+            f.write(struct.pack(">3i", *map(int, minint)))
+            f.write(struct.pack(">3i", *map(int, maxint)))
+            sizeint = [int(maxint[k] - minint[k] + 1) for k in range(3)]
+            bitsize, bitsizeint = _xtc_bitsize(sizeint)
+            d = np.abs(np.diff(ints, axis=0)).sum(axis=1)
+            mindiff = int(d.min()) if N > 1 else 2 ** 31 - 1
+            smallidx = XTC_FIRSTIDX
+            while smallidx < len(XTC_MAGICINTS) and XTC_MAGICINTS[smallidx] < mindiff:
+                smallidx += 1
+            f.write(struct.pack(">i", smallidx))
+            maxidx = min(len(XTC_MAGICINTS), smallidx + 8)
+            minidx = maxidx - 8
+            smaller = XTC_MAGICINTS[max(XTC_FIRSTIDX, smallidx - 1)] // 2
+            smallnum = XTC_MAGICINTS[smallidx] // 2
+            sizesmall = [XTC_MAGICINTS[smallidx]] * 3
+            larger = XTC_MAGICINTS[maxidx] // 2 if maxidx < len(XTC_MAGICINTS) else 2 ** 31 - 1
+            c = [list(map(int, r)) for r in ints]
+            out = _BitsOut()
+            i, prevrun, prev = 0, -1, [0, 0, 0]
+            while i < N:
+                is_small = 0
+                this = c[i]
+                if smallidx < maxidx and i >= 1 and all(abs(this[k] - prev[k]) < larger for k in range(3)):
+                    is_smaller = 1
+                elif smallidx > minidx:
+                    is_smaller = -1
+                else:
+                    is_smaller = 0
+                if i + 1 < N and all(abs(c[i][k] - c[i + 1][k]) < smallnum for k in range(3)):
+                    c[i], c[i + 1] = c[i + 1], c[i]          # water trick: second atom first
+                    this = c[i]
+                    is_small = 1
+                tmp = [this[k] - int(minint[k]) for k in range(3)]
+                if bitsize == 0:
+                    for k in range(3):
+                        out.put(bitsizeint[k], tmp[k])
+                else:
+                    out.put3(bitsize, sizeint, tmp)
+                prev = list(this)
+                i += 1
+                run, smalls = 0, []
+                if is_small == 0 and is_smaller == -1:
+                    is_smaller = 0
+                while is_small and run < 8 * 3:
+                    this = c[i]
+                    if is_smaller == -1 and sum((this[k] - prev[k]) ** 2 for k in range(3)) >= smaller * smaller:
+                        is_smaller = 0
+                    smalls.append([this[k] - prev[k] + smallnum for k in range(3)])
+                    run += 3
+                    prev = list(this)
+                    i += 1
+                    is_small = 1 if (i < N and all(abs(c[i][k] - prev[k]) < smallnum for k in range(3))) else 0
+                if run != prevrun or is_smaller != 0:
+                    prevrun = run
+                    out.put(1, 1)
+                    out.put(5, run + is_smaller + 1)
+                else:
+                    out.put(1, 0)
+                for s3 in smalls:
+                    out.put3(smallidx, sizesmall, s3)
+                if is_smaller != 0:
+                    smallidx += is_smaller
+                    if is_smaller < 0:
+                        smallnum = smaller
+                        smaller = XTC_MAGICINTS[smallidx - 1] // 2
+                    else:
+                        smaller = smallnum
+                        smallnum = XTC_MAGICINTS[smallidx] // 2
+                    sizesmall = [XTC_MAGICINTS[smallidx]] * 3
+            blob = out.tobytes()
+            f.write(struct.pack(">i", len(blob)))
+            f.write(blob + b"\0" * ((-len(blob)) % 4))
+
+
+class _BitsIn:
+    def __init__(self, data):
+        self.data, self.pos = data, 0
+
+    def take(self, nbits):
+        v = 0
+        for _ in range(nbits):
+            byte = self.pos >> 3
+            bit = (self.data[byte] >> (7 - (self.pos & 7))) & 1 if byte < len(self.data) else 0
+            v = (v << 1) | bit
+            self.pos += 1
+        return v
+
+    def take3(self, nbits, sizes):
+        v, shift = 0, 0
+        while nbits > 8:
+            v |= self.take(8) << shift
+            shift += 8
+            nbits -= 8
+        if nbits > 0:
+            v |= self.take(nbits) << shift
+        n2 = v % sizes[2]; v //= sizes[2]
+        n1 = v % sizes[1]; v //= sizes[1]
+        return [v, n1, n2]
+
+
+def read_xtc(path):
+    """All frames as float32 (F, N, 3) in Angstrom, the reference's arithmetic
+    (readCompressedCoords, src/xtc.cpp:165-332): (float)int * (1/precision) in float, times 10.0 in double."""
+    import struct
+    data = open(path, "rb").read()
+    pos, frames = 0, []
+    while pos < len(data):
+        magic, N, step = struct.unpack_from(">iii", data, pos)
+        assert magic == 1995
+        pos += 13 * 4
+        (lsize,) = struct.unpack_from(">i", data, pos); pos += 4
+        assert lsize == N
+        if N <= 9:
+            nm = np.frombuffer(data, dtype=">f4", count=3 * N, offset=pos).astype(np.float32).reshape(N, 3)
+            pos += 12 * N
+            frames.append((nm.astype(np.float64) * 10.0).astype(np.float32))
+            continue
+        (precision,) = struct.unpack_from(">f", data, pos); pos += 4
+        minint = struct.unpack_from(">3i", data, pos); pos += 12
+        maxint = struct.unpack_from(">3i", data, pos); pos += 12
+        (smallidx, nbytes) = struct.unpack_from(">ii", data, pos); pos += 8
+        bits = _BitsIn(data[pos:pos + nbytes]); pos += (nbytes + 3) // 4 * 4
+        sizeint = [maxint[k] - minint[k] + 1 for k in range(3)]
+        bitsize, bitsizeint = _xtc_bitsize(sizeint)
+        smaller = XTC_MAGICINTS[max(XTC_FIRSTIDX, smallidx - 1)] // 2
+        smallnum = XTC_MAGICINTS[smallidx] // 2
+        sizesmall = [XTC_MAGICINTS[smallidx]] * 3
+        inv = np.float32(1.0) / np.float32(precision)
+        out, run = [], 0
+        while len(out) < N:
+            cur = [bits.take(bitsizeint[k]) for k in range(3)] if bitsize == 0 else bits.take3(bitsize, sizeint)
+            cur = [cur[k] + minint[k] for k in range(3)]
+            prev = list(cur)
+            is_smaller = 0
+            if bits.take(1):
+                run = bits.take(5)
+                is_smaller = run % 3
+                run -= is_smaller
+                is_smaller -= 1
+            if run > 0:
+                for k in range(0, run, 3):
+                    d = bits.take3(smallidx, sizesmall)
+                    d = [d[q] + prev[q] - smallnum for q in range(3)]
+                    if k == 0:
+                        out.append(d); out.append(cur)
+                    else:
+                        out.append(d)
+                    prev = d
+            else:
+                out.append(cur)
+            smallidx += is_smaller
+            if is_smaller < 0:
+                smallnum = smaller
+                smaller = XTC_MAGICINTS[smallidx - 1] // 2 if smallidx > XTC_FIRSTIDX else 0
+            elif is_smaller > 0:
+                smaller = smallnum
+                smallnum = XTC_MAGICINTS[smallidx] // 2
+            sizesmall = [XTC_MAGICINTS[smallidx]] * 3
+        ints = np.array(out[:N], dtype=np.int64)
+        fl = (ints.astype(np.float32) * inv).astype(np.float32)
+        frames.append((fl.astype(np.float64) * 10.0).astype(np.float32))
+    return np.stack(frames)

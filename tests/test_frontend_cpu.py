@@ -308,7 +308,7 @@ def test_amber_netcdf_validation(fe, tmp_path):
     assert "different number of atoms than expected" in err(p, natoms=6)
     p = str(tmp_path / "e.nc"); open(p, "wb").write(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
     assert "NetCDF-4" in err(p)
-    p = str(tmp_path / "f.xtc"); open(p, "wb").write(b"\0" * 64)
+    p = str(tmp_path / "f.trr"); open(p, "wb").write(b"\0" * 64)
     assert "unsupported trajectory format" in err(p)
     # the suffix rules of createTrajectory: .crd is NetCDF when it carries the magic
     p = str(tmp_path / "g.crd"); _write_amber_nc(p, xyz)
@@ -366,3 +366,66 @@ def test_config_file_option(system, tmp_path):
     assert r.returncode == 255 and "invalid line" in r.stderr
     r = subprocess.run([exe, "--config", str(tmp_path / "missing.cfg"), system["pdb"], system["dcd"]], capture_output=True, text=True)
     assert r.returncode == 255 and "Cannot open options config file" in r.stderr
+
+
+# ------------------------------------------------------------------ GROMACS XTC reader
+def _xtc_read_native(fe, path, N, F):
+    na, nf = C.c_uint32(), C.c_uint32()
+    assert fe.lbfe_traj_info(path.encode(), N, C.byref(na), C.byref(nf)) == 0, fe.lbfe_last_error()
+    assert (na.value, nf.value) == (N, F)
+    out = np.zeros((F, 3, N), np.float32)
+    for k in range(F):
+        assert fe.lbfe_traj_read(path.encode(), N, k, out[k].ctypes.data_as(C.POINTER(C.c_float))) == 0, fe.lbfe_last_error()
+    return out.transpose(0, 2, 1)
+
+
+@pytest.mark.parametrize("case", ["protein", "water", "wide", "tiny", "huge_box"])
+def test_xtc_reader(fe, tmp_path, case):
+    """XTC frames decoded by the native reader equal, bit for bit, the restatement of the reference's
+    reader (readCompressedCoords, src/xtc.cpp:165-332) on files made by the restatement of the
+    reference's writer (src/xtcwriter.cpp:387-655); and both are within half a quantum of the input.
+    Parity with GROMACS-written files is unpinned (no such file exists in the reference or this image)."""
+    from oracle import frontend_oracle as fo
+    from loos_b200.synth import synth_system
+    rng = np.random.default_rng(5)
+    precision = 1000.0
+    if case == "protein":
+        _, xyz = synth_system(40, 5, seed=3, flavour="rich")
+    elif case == "water":       # triplets of close atoms: exercises the swap and the run-length coding
+        O = rng.uniform(0, 40, (4, 300, 1, 3))
+        xyz = (O + rng.normal(0, 0.4, (4, 300, 3, 3))).reshape(4, 900, 3).astype(np.float32)
+    elif case == "wide":        # spread-out atoms: no runs, smallidx walks down and up
+        xyz = rng.uniform(-300, 300, (3, 200, 3)).astype(np.float32)
+        xyz[:, 50:120] = (xyz[:, 50:51] + rng.normal(0, 0.05, (3, 70, 3))).astype(np.float32)
+    elif case == "tiny":        # <= 9 atoms are stored as plain floats
+        xyz = rng.uniform(-20, 20, (5, 7, 3)).astype(np.float32)
+    else:                       # extent above 2^24 quanta: per-axis bit fields instead of the mixed radix
+        xyz = rng.uniform(-1.2e5, 1.2e5, (2, 64, 3)).astype(np.float32)
+        xyz[:, 10] = xyz[:, 9] + 1.0      # one close pair: with every atom far apart the reference's writer
+                                          # indexes past its table (src/xtcwriter.cpp:513-525), not a case to restate
+    F, N, _ = xyz.shape
+    path = str(tmp_path / "t.xtc")
+    fo.write_xtc(path, xyz, precision=precision)
+    want = fo.read_xtc(path)
+    got = _xtc_read_native(fe, path, N, F)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    if case == "tiny":
+        assert np.abs(got - xyz).max() <= 4e-6 * np.abs(xyz).max()
+    else:
+        assert np.abs(got.astype(np.float64) - xyz).max() <= 5.0 / precision * 1.001 + np.abs(xyz).max() * 2e-7
+
+
+def test_xtc_validation(fe, tmp_path):
+    from oracle import frontend_oracle as fo
+    xyz = np.random.default_rng(1).uniform(0, 30, (3, 20, 3)).astype(np.float32)
+    p = str(tmp_path / "a.xtc"); fo.write_xtc(p, xyz)
+    na, nf = C.c_uint32(), C.c_uint32()
+    # like DCD, the file states its own atom count; the tools compare it with the model
+    assert fe.lbfe_traj_info(p.encode(), 21, C.byref(na), C.byref(nf)) == 0 and (na.value, nf.value) == (20, 3)
+    raw = open(p, "rb").read()
+    q = str(tmp_path / "b.xtc"); open(q, "wb").write(b"\0\0\0\1" + raw[4:])
+    assert fe.lbfe_traj_info(q.encode(), 20, C.byref(na), C.byref(nf)) == -1
+    assert "magic" in fe.lbfe_last_error().decode().lower()
+    r = str(tmp_path / "c.xtc"); open(r, "wb").write(raw[:len(raw) - 10])      # last frame cut short
+    assert fe.lbfe_traj_info(r.encode(), 20, C.byref(na), C.byref(nf)) == -1
+    assert "truncated" in fe.lbfe_last_error().decode()

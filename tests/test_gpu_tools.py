@@ -210,6 +210,21 @@ def test_amber_netcdf_trajectories_give_the_same_matrices(files, tmp_path):
     assert body(a) == body(b)
 
 
+def test_xtc_trajectory_gives_the_same_matrix_as_its_decoded_frames(files, tmp_path):
+    """An XTC file (written by the restatement of the reference's writer) and a DCD holding the
+    frames the reference's reader arithmetic decodes from it: rmsds and rmsd2ref print the same numbers."""
+    d, xyz = files["d"], files["xyz"]
+    fo.write_xtc(str(tmp_path / "all.xtc"), xyz)
+    write_dcd(str(tmp_path / "decoded.dcd"), fo.read_xtc(str(tmp_path / "all.xtc")))
+    body = lambda out: "\n".join(l for l in out.splitlines() if not (l.startswith("# ") and "[loos-b200" in l))
+    a, _ = run("rmsds", "-p", "6", d / "model.pdb", tmp_path / "decoded.dcd")
+    b, _ = run("rmsds", "-p", "6", d / "model.pdb", tmp_path / "all.xtc")
+    assert body(a) == body(b)
+    a, _ = run("rmsd2ref", "--target", d / "target.pdb", d / "model.pdb", tmp_path / "decoded.dcd")
+    b, _ = run("rmsd2ref", "--target", d / "target.pdb", d / "model.pdb", tmp_path / "all.xtc")
+    assert body(a) == body(b)
+
+
 def test_binary_side_channel(files, tmp_path):
     """--binary writes the float32 matrix as .npy (fortran order): identical to the values behind the
     text at -p 9, also with --noout 1, for the self and the cross matrix."""
