@@ -189,6 +189,20 @@ int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_frames* rmsd_se
                                 int maxiter, double* out_rmsd, double* out_xforms,
                                 double* out_avg, int* iters, double* final_rms);
 
+/* ---- all-to-all RMSD with different alignment and RMSD selections
+ *      (Packages/Clustering/rmsds-align.py:236-256) ----
+ * out(i,j) = rmsd of rmsd2's frame j against rmsd1's frame i moved by the superposition of
+ * align1's frame i onto align2's frame j (AtomicGroup::alignOnto / applyTransform / rmsd:
+ * src/AG_linalg.cpp:188-197, src/AG_numerical.cpp:363-370,301-318).  Not symmetric in general.
+ *   align1, rmsd1  align- and rmsd-selection coordinates of the SAME F1 frames (trajectory 1);
+ *                  rmsd1 == NULL: the align selection serves as both
+ *   align2, rmsd2  the same for trajectory 2 (F2 frames); pass the handles of trajectory 1
+ *                  again for the one-trajectory case
+ *   out            host, F1 x F2 doubles column-major: out[j*ld + i], ld >= F1
+ * Selections of the two trajectories must agree in size (LOOSB200_ERR_SIZE_MISMATCH). */
+int loosb200_rmsds_align(loosb200_frames* align1, loosb200_frames* rmsd1, loosb200_frames* align2,
+                         loosb200_frames* rmsd2, double* out, size_t ld);
+
 /* One pass of iterativeAlignment's loop body over THIS handle's frames (src/alignment.cpp:379-390:
  * alignOnto(target) for every frame, transformed coordinates summed), for callers that shard a
  * trajectory over several GPUs / processes: sum the per-shard results (the one collective of the

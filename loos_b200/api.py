@@ -214,6 +214,19 @@ def align_accumulate(fs_align, target, fs_accum=None, want_xforms=False):
     return (out, xf) if want_xforms else out
 
 
+def rmsds_align(align1, rmsd1=None, align2=None, rmsd2=None):
+    """Pairwise RMSD over one selection after aligning on another
+    (Packages/Clustering/rmsds-align.py:236-256): M[i, j] = rmsd of rmsd2[j] against rmsd1[i] moved by
+    the superposition of align1[i] onto align2[j].  Second trajectory defaults to the first.
+    Returns an (F1, F2) float64 array."""
+    if align2 is None:
+        align2, rmsd2 = align1, rmsd1
+    out = np.zeros((align1.F, align2.F), dtype=np.float64, order="F")
+    check(lib().loosb200_rmsds_align(align1._h, None if rmsd1 is None else rmsd1._h, align2._h,
+                                     None if rmsd2 is None else rmsd2._h, _dptr(out), max(1, align1.F)))
+    return out
+
+
 def rmsds_text(fs, fs_b=None, precision=2, engine="auto", write=None):
     """The result matrix as the reference prints it (`cout << setprecision(p) << M`), formatted on
     the GPU and streamed in row order.  `write(bytes)` receives the pieces (default: they are

@@ -1,0 +1,256 @@
+// All-to-all RMSD with DIFFERENT alignment and RMSD selections
+// (Packages/Clustering/rmsds-align.py:236-256).
+//
+// For frame i of trajectory 1 and frame j of trajectory 2 the reference script does
+//   W = ref_align.alignOnto(align_selection_2)      (AtomicGroup::superposition, src/AG_linalg.cpp:188-197)
+//   ref_target.applyTransform(W)                    (src/AG_numerical.cpp:363-370)
+//   rmsd_selection_2.rmsd(ref_target)               (src/AG_numerical.cpp:301-318)
+// where ref_align / ref_target are copies of frame i's align / rmsd selections that keep the
+// transforms of the earlier j (a composition of optimal superpositions is the optimal
+// superposition).  With ca_i, cb_j the centroids of the two ALIGN selections, x' = x - ca_i and
+// y' = y - cb_j the rmsd-selection atoms about them, and Z_ij the rotation that superposes the
+// align selection of i onto that of j,
+//   d_ij^2 = ( sum |x'|^2 + sum |y'|^2 - 2 sum_ab Z_ab C_ba ) / N_r ,   C_ab = sum_k x'_a y'_b .
+// So a pair needs two 3x3 contractions -- R over the align selection (it gives Z through the
+// quartic / adjugate solve of qcp.cuh) and C over the rmsd selection -- and nothing per atom
+// after that.  This first version runs both on the fp64 CUDA cores, a 40 x 40 tile of pairs per
+// CTA and a 2 x 2 block of pairs per thread, as pairs_fp64.cu does for the one-selection case.
+// Roofline: fp64 pipe, 18 (N_a + N_r) flop per pair.  The result is not symmetric and is kept
+// in double: the script prints Python doubles.
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "qcp.cuh"
+
+namespace loosb200 {
+
+namespace {
+
+constexpr int TF = TILE_FRAMES;  // 40
+constexpr int KC = 16;           // atoms per smem chunk
+constexpr int NT = 416;          // 13 warps; threads 0..399 own a 2x2 block of pairs
+
+// g[f] = sum over the set's atoms of |x - cen[f]|^2 with cen taken from ANOTHER set (the align
+// selection of the same frame).  One warp per frame.
+__global__ void __launch_bounds__(128)
+k_g_about(const float* __restrict__ raw, size_t Npad, uint32_t N, uint32_t F,
+          const double* __restrict__ cen, double* __restrict__ g) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t f = blockIdx.x * 4 + (threadIdx.x >> 5); f < F; f += gridDim.x * 4) {
+    double s = 0.0;
+    for (int ax = 0; ax < 3; ++ax) {
+      const double c = cen[(size_t)f * 3 + ax];
+      const float* p = raw + ((size_t)f * 3 + ax) * Npad;
+      for (uint32_t k = lane; k < N; k += 32) {
+        const double v = (double)p[k] - c;
+        s = fma(v, v, s);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) g[f] = s;
+  }
+}
+
+struct AlignArgs {
+  const float *alnA, *alnB, *rmsA, *rmsB;  // raw planes of the four staged sets
+  size_t padAlnA, padAlnB, padRmsA, padRmsB;
+  const double *cenA, *cenB;               // centroids of the ALIGN sets
+  const double *gdA, *gdB;                 // sum of squares of the centred align sets
+  const double *gxA, *gxB;                 // rmsd-set sum of squares about the align centroid
+  uint32_t FA, FB, Na, Nr;
+  uint32_t row0;                           // first frame of this band of rows
+  uint32_t band_rows;                      // frames in the band (= leading dimension of out)
+  double* out;                             // band, column-major: out[j * band_rows + (i - row0)]
+};
+
+__global__ void __launch_bounds__(NT)
+k_pairs_align(const AlignArgs a) {
+  __shared__ double As[3][KC][TF];
+  __shared__ double Bs[3][KC][TF];
+  __shared__ double cA[TF][3], cB[TF][3];
+
+  const uint32_t I0 = a.row0 + blockIdx.y * TF, J0 = blockIdx.x * TF;
+  const int tid = threadIdx.x;
+  const bool worker = tid < TF * TF / 4;
+  const int ty = tid / 20, tx = tid % 20;
+
+  for (int t = tid; t < TF * 3; t += NT) {
+    const uint32_t fa = I0 + t / 3, fb = J0 + t / 3;
+    cA[t / 3][t % 3] = fa < a.FA ? a.cenA[(size_t)fa * 3 + t % 3] : 0.0;
+    cB[t / 3][t % 3] = fb < a.FB ? a.cenB[(size_t)fb * 3 + t % 3] : 0.0;
+  }
+  __syncthreads();
+
+  double acc[2][2][9];
+  double Z[2][2][9];
+
+  // phase 0: R over the align selection -> Z;  phase 1: C over the rmsd selection
+  for (int phase = 0; phase < 2; ++phase) {
+    const float* rawA = phase ? a.rmsA : a.alnA;
+    const float* rawB = phase ? a.rmsB : a.alnB;
+    const size_t padA = phase ? a.padRmsA : a.padAlnA, padB = phase ? a.padRmsB : a.padAlnB;
+    const uint32_t N = phase ? a.Nr : a.Na;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[p][q][k] = 0.0;
+
+    for (uint32_t k0 = 0; k0 < N; k0 += KC) {
+      for (int idx = tid; idx < TF * 3 * KC; idx += NT) {
+        const int f = idx / (3 * KC), rem = idx % (3 * KC), ax = rem / KC, k = rem % KC;
+        const uint32_t fa = I0 + f, fb = J0 + f, at = k0 + k;
+        double va = 0.0, vb = 0.0;
+        if (at < N) {
+          if (fa < a.FA) va = (double)rawA[((size_t)fa * 3 + ax) * padA + at] - cA[f][ax];
+          if (fb < a.FB) vb = (double)rawB[((size_t)fb * 3 + ax) * padB + at] - cB[f][ax];
+        }
+        As[ax][k][f] = va;
+        Bs[ax][k][f] = vb;
+      }
+      __syncthreads();
+      if (worker) {
+#pragma unroll 4
+        for (int k = 0; k < KC; ++k) {
+          double a0[3], a1[3], b0[3], b1[3];
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) {
+            a0[ax] = As[ax][k][ty]; a1[ax] = As[ax][k][ty + 20];
+            b0[ax] = Bs[ax][k][tx]; b1[ax] = Bs[ax][k][tx + 20];
+          }
+#pragma unroll
+          for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              acc[0][0][3 * p + q] = fma(a0[p], b0[q], acc[0][0][3 * p + q]);
+              acc[0][1][3 * p + q] = fma(a0[p], b1[q], acc[0][1][3 * p + q]);
+              acc[1][0][3 * p + q] = fma(a1[p], b0[q], acc[1][0][3 * p + q]);
+              acc[1][1][3 * p + q] = fma(a1[p], b1[q], acc[1][1][3 * p + q]);
+            }
+        }
+      }
+      __syncthreads();
+    }
+
+    if (!worker) continue;
+    if (phase == 0) {
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t i = I0 + ty + 20 * p, j = J0 + tx + 20 * q;
+          if (i >= a.FA || j >= a.FB) continue;
+          // Z maps the align selection of i onto that of j; the Jacobi solve takes the
+          // (near-)degenerate cases -- collinear / planar selections, fewer than 3 atoms
+          if (!qcp_rotation_fast(acc[p][q], a.gdA[i], a.gdB[j], Z[p][q])) qcp_rotation(acc[p][q], Z[p][q], nullptr);
+        }
+    } else {
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t i = I0 + ty + 20 * p, j = J0 + tx + 20 * q;
+          if (i >= a.FA || j >= a.FB || i >= a.row0 + a.band_rows) continue;
+          const double* C = acc[p][q];
+          const double* z = Z[p][q];
+          double tr = 0.0;  // sum_k (Z x'_k) . y'_k = sum_ab Z_ab C_ba
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) tr = fma(z[3 * r + c], C[3 * c + r], tr);
+          const double ss = a.gxA[i] + a.gxB[j] - 2.0 * tr;
+          a.out[(size_t)j * a.band_rows + (i - a.row0)] = sqrt(fmax(ss, 0.0) / (double)a.Nr);
+        }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace loosb200
+
+using namespace loosb200;
+
+extern "C" int loosb200_rmsds_align(loosb200_frames* align1, loosb200_frames* rmsd1, loosb200_frames* align2,
+                                    loosb200_frames* rmsd2, double* out, size_t ld) {
+  if (!align1 || !align2 || !out) return LOOSB200_ERR_INVALID;
+  if (!rmsd1) rmsd1 = align1;
+  if (!rmsd2) rmsd2 = align2;
+  const loosb200_frames* all[4] = {align1, rmsd1, align2, rmsd2};
+  for (const loosb200_frames* h : all)
+    if (h->stager || !h->raw) { set_last_error("rmsds_align: a frame set is not staged"); return LOOSB200_ERR_INVALID; }
+  if (rmsd1->F != align1->F || rmsd2->F != align2->F) { set_last_error("rmsds_align: align and rmsd sets of one trajectory differ in frame count"); return LOOSB200_ERR_SIZE_MISMATCH; }
+  // AtomicGroup::superposition / ::rmsd throw on unequal sizes (src/AG_linalg.cpp:189-192, src/AG_numerical.cpp:303-304)
+  if (align1->N != align2->N || rmsd1->N != rmsd2->N) { set_last_error("rmsds_align: selections of the two trajectories differ in size"); return LOOSB200_ERR_SIZE_MISMATCH; }
+  for (const loosb200_frames* h : all)
+    if (h->device != align1->device) { set_last_error("rmsds_align: frame sets live on different devices"); return LOOSB200_ERR_INVALID; }
+  const size_t FA = align1->F, FB = align2->F;
+  if (FA == 0 || FB == 0) return LOOSB200_OK;
+  if (ld < FA) return LOOSB200_ERR_INVALID;
+  if (FA > 0xffffff00ull || FB > 0xffffff00ull || (FB + TF - 1) / TF > 0x7fffffffull) return LOOSB200_ERR_UNSUPPORTED;
+  LB_CUDA(cudaSetDevice(align1->device));
+  cudaStream_t st = align1->stream;
+
+  // bands of whole row tiles, at most ~1 GiB of doubles each (and 65535 tiles: gridDim.y)
+  size_t band_tiles = std::max<size_t>(1, (size_t(1) << 30) / (sizeof(double) * TF * FB));
+  band_tiles = std::min<size_t>(band_tiles, 65535);
+  if (const char* env = getenv("LOOSB200_ALIGN_BAND_TILES")) band_tiles = std::max<long>(1, atol(env));  // tests: force several bands
+  const size_t row_tiles = (FA + TF - 1) / TF;
+  band_tiles = std::min(band_tiles, row_tiles);
+  const size_t band_rows_max = std::min(FA, band_tiles * TF);
+
+  double *gxA = nullptr, *gxB = nullptr, *d_band = nullptr;
+  bool ok = dev_alloc_t(&gxA, sizeof(double) * FA) == cudaSuccess &&
+            dev_alloc_t(&gxB, sizeof(double) * FB) == cudaSuccess &&
+            dev_alloc_t(&d_band, sizeof(double) * band_rows_max * FB) == cudaSuccess;
+  auto cleanup = [&]() { dev_release(gxA); dev_release(gxB); dev_release(d_band); };
+  if (!ok) { cudaGetLastError(); cleanup(); return LOOSB200_ERR_NOMEM; }
+
+  // the frame sets were staged on their own streams: wait for all of them
+  for (const loosb200_frames* h : all)
+    if (h->stream != st) {
+      cudaError_t e = cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "rmsds_align: staging", __FILE__, __LINE__); }
+    }
+
+  cudaEventRecord(align1->timing.ev[0], st);
+  int launches = 0;
+  k_g_about<<<(unsigned)std::min<size_t>((FA + 3) / 4, 148 * 16), 128, 0, st>>>(rmsd1->raw, rmsd1->Npad, (uint32_t)rmsd1->N, (uint32_t)FA, align1->centroid, gxA);
+  k_g_about<<<(unsigned)std::min<size_t>((FB + 3) / 4, 148 * 16), 128, 0, st>>>(rmsd2->raw, rmsd2->Npad, (uint32_t)rmsd2->N, (uint32_t)FB, align2->centroid, gxB);
+  launches += 2;
+  cudaEventRecord(align1->timing.ev[1], st);
+
+  AlignArgs a;
+  a.alnA = align1->raw; a.alnB = align2->raw; a.rmsA = rmsd1->raw; a.rmsB = rmsd2->raw;
+  a.padAlnA = align1->Npad; a.padAlnB = align2->Npad; a.padRmsA = rmsd1->Npad; a.padRmsB = rmsd2->Npad;
+  a.cenA = align1->centroid; a.cenB = align2->centroid;
+  a.gdA = align1->gd; a.gdB = align2->gd;
+  a.gxA = gxA; a.gxB = gxB;
+  a.FA = (uint32_t)FA; a.FB = (uint32_t)FB; a.Na = (uint32_t)align1->N; a.Nr = (uint32_t)rmsd1->N;
+  a.out = d_band;
+  cudaError_t e = cudaSuccess;
+  for (size_t t0 = 0; t0 < row_tiles && e == cudaSuccess; t0 += band_tiles) {
+    const size_t nt = std::min(band_tiles, row_tiles - t0);
+    a.row0 = (uint32_t)(t0 * TF);
+    a.band_rows = (uint32_t)std::min<size_t>(nt * TF, FA - a.row0);
+    const dim3 grid((unsigned)((FB + TF - 1) / TF), (unsigned)nt);
+    k_pairs_align<<<grid, NT, 0, st>>>(a);
+    ++launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) break;
+    // band (column-major, ld = band_rows) -> rows [row0, row0 + band_rows) of the caller's matrix
+    e = cudaMemcpy2DAsync(out + a.row0, ld * sizeof(double), d_band, (size_t)a.band_rows * sizeof(double),
+                          (size_t)a.band_rows * sizeof(double), FB, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && t0 + band_tiles < row_tiles) e = cudaStreamSynchronize(st);  // the band buffer is reused
+  }
+  cudaEventRecord(align1->timing.ev[2], st);
+  cudaEventRecord(align1->timing.ev[3], st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cleanup();
+  if (e != cudaSuccess) return cuda_fail(e, "rmsds_align kernels", __FILE__, __LINE__);
+  align1->timing.launches = launches; align1->timing.valid = true; align1->timing.kev_used = 0;
+  return LOOSB200_OK;
+}

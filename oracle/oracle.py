@@ -131,6 +131,42 @@ class Checker:
         return out, xf.reshape(F, 4, 4), avg.reshape(-1, 3), it, rms.value
 
 
+def _apply44(W, X):
+    """XForm applied to coordinates: AtomicGroup::applyTransform (src/AG_numerical.cpp:363-370)."""
+    return X @ W[:3, :3].T + W[:3, 3]
+
+
+def rmsds_align(checker, A1, R1, A2, R2):
+    """The loop of Packages/Clustering/rmsds-align.py:236-256 on in-memory frames.
+    A1: (F1, Na, 3) align selection of trajectory 1, R1: (F1, Nr, 3) its rmsd selection, A2 / R2 the
+    same for trajectory 2.  As in the script, the copies of frame i (ref_align, ref_target) KEEP
+    the transforms of the earlier j: alignOnto (src/AG_linalg.cpp:188-197 superposition +
+    applyTransform) moves ref_align every time.  checker.kabsch is alignment::kabsch
+    (src/alignment.cpp:217-233; the reference's own code when checker.kind == "reference").
+    Returns the (F1, F2) float64 matrix the script prints (before round())."""
+    A1 = np.asarray(A1, dtype=np.float64); R1 = np.asarray(R1, dtype=np.float64)
+    A2 = np.asarray(A2, dtype=np.float64); R2 = np.asarray(R2, dtype=np.float64)
+    if A1.shape[1] != A2.shape[1]:
+        raise ValueError("Cannot superimpose groups with differing numbers of atoms")    # src/AG_linalg.cpp:189-192
+    if R1.shape[1] != R2.shape[1]:
+        raise ValueError("Cannot compute RMSD between groups with different sizes")      # src/AG_numerical.cpp:303-304
+    M = np.zeros((len(A1), len(A2)))
+    for i in range(len(A1)):
+        ref_align, ref_target = A1[i].copy(), R1[i].copy()
+        for j in range(len(A2)):
+            W = checker.kabsch(ref_align, A2[j])
+            ref_align = _apply44(W, ref_align)
+            ref_target = _apply44(W, ref_target)
+            d = R2[j] - ref_target
+            M[i, j] = np.sqrt((d * d).sum() / R2.shape[1])                                # src/AG_numerical.cpp:301-318
+    return M
+
+
+def py_round_text(M, precision=2):
+    """rmsds-align.py:254-256: print(round(v, precision), "", end='') per value, print("") per row."""
+    return "".join("".join("%s " % repr(round(float(v), precision)) for v in row) + "\n" for row in M)
+
+
 def have_reference():
     return os.path.exists(os.path.join(_HERE, "_ref", "libloosref.so"))
 

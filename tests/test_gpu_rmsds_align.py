@@ -1,0 +1,99 @@
+"""GPU parity tests for the all-to-all RMSD with different alignment and RMSD selections
+(loosb200_rmsds_align; Packages/Clustering/rmsds-align.py:236-256).  The checker is the oracle's
+restatement of the script's loop on the reference's own alignment::kabsch."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4      # north_star's bound on the RMSD
+TIGHT = 1e-8    # what fp64 contractions + the fp64 rotation actually give on generic structures
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import loos_b200
+    from loos_b200 import capi
+    assert capi.device_count() >= 1
+    return loos_b200
+
+
+def _sets(F, natoms, seed):
+    from loos_b200.synth import synth_frames
+    return synth_frames(F, natoms, seed=seed)
+
+
+@pytest.mark.parametrize("F1,F2,Na,Nr", [(45, 53, 60, 90), (1, 1, 3, 1), (40, 80, 17, 200), (83, 7, 500, 33)])
+def test_two_trajectories_vs_oracle(lb, checker, F1, F2, Na, Nr):
+    from oracle import oracle
+    X = _sets(F1, Na + Nr, seed=77 + F1 + Na)
+    Y = _sets(F2, Na + Nr, seed=78 + F2 + Nr)
+    sa = np.arange(0, Na, dtype=np.uint32)
+    sr = np.arange(Na, Na + Nr, dtype=np.uint32)
+    want = oracle.rmsds_align(checker, X[:, sa], X[:, sr], Y[:, sa], Y[:, sr])
+    with lb.FrameSet(X, sel=sa) as a1, lb.FrameSet(X, sel=sr) as r1, lb.FrameSet(Y, sel=sa) as a2, lb.FrameSet(Y, sel=sr) as r2:
+        got = lb.rmsds_align(a1, r1, a2, r2)
+    assert got.shape == (F1, F2) and got.dtype == np.float64
+    err = np.abs(got - want).max()
+    assert err <= TOL
+    if Na >= 4:
+        assert err < TIGHT, err
+
+
+def test_one_trajectory_overlapping_selections_and_bands(lb, checker, monkeypatch):
+    """The one-trajectory call (second pair of handles = the first), selections that overlap, and the
+    result produced in several row bands: identical numbers."""
+    from oracle import oracle
+    F, N = 130, 120
+    X = _sets(F, N, seed=4)
+    sa = np.arange(0, 80, 2, dtype=np.uint32)          # 40 atoms
+    sr = np.arange(30, 120, dtype=np.uint32)           # 90 atoms, overlaps the align selection
+    want = oracle.rmsds_align(checker, X[:, sa], X[:, sr], X[:, sa], X[:, sr])
+    with lb.FrameSet(X, sel=sa) as a1, lb.FrameSet(X, sel=sr) as r1:
+        whole = lb.rmsds_align(a1, r1)
+        monkeypatch.setenv("LOOSB200_ALIGN_BAND_TILES", "1")
+        banded = lb.rmsds_align(a1, r1)
+    assert np.array_equal(whole, banded)
+    assert np.abs(np.diag(whole)).max() < 1e-5          # a frame against itself: 0 up to the cancellation floor
+    off = ~np.eye(F, dtype=bool)
+    assert np.abs(whole - want)[off].max() < TIGHT
+    assert np.abs(whole - whole.T).max() > 1e-3         # genuinely not symmetric
+
+
+def test_same_selection_reduces_to_rmsds(lb):
+    """With the rmsd selection equal to the align selection the matrix is the minimal RMSD that
+    rmsds computes (float32 there)."""
+    F, N = 90, 150
+    X = _sets(F, N, seed=9)
+    Y = _sets(70, N, seed=10)
+    with lb.FrameSet(X) as a, lb.FrameSet(Y) as b:
+        M = lb.rmsds_align(a, None, b, None)
+        ref, _ = lb.rmsds_cross(a, b, engine="fp64")
+    assert np.abs(M - ref).max() < 2e-6
+
+
+def test_degenerate_align_selection(lb, checker):
+    """Two align atoms (rotation about their axis is free in the reference too): the result is still the
+    RMSD under A valid optimal superposition -- checked on the part that is determined, the align atoms
+    themselves -- and stays finite everywhere."""
+    X = _sets(12, 40, seed=21)
+    sa = np.array([3, 17], dtype=np.uint32)
+    with lb.FrameSet(X, sel=sa) as a1:
+        M = lb.rmsds_align(a1, None)
+    from oracle import oracle
+    want = oracle.rmsds_align(checker, X[:, sa], X[:, sa], X[:, sa], X[:, sa])
+    assert np.isfinite(M).all()
+    assert np.abs(M - want).max() < 1e-5
+
+
+def test_errors(lb):
+    X = _sets(10, 30, seed=1)
+    with lb.FrameSet(X, sel=np.arange(10, dtype=np.uint32)) as a10, lb.FrameSet(X, sel=np.arange(12, dtype=np.uint32)) as a12, \
+            lb.FrameSet(X[:8], sel=np.arange(10, dtype=np.uint32)) as short:
+        with pytest.raises(lb.LoosB200Error):
+            lb.rmsds_align(a10, None, a12, None)        # align selections differ in size
+        with pytest.raises(lb.LoosB200Error):
+            lb.rmsds_align(a10, a10, a10, a12)          # rmsd selections differ in size
+        with pytest.raises(lb.LoosB200Error):
+            lb.rmsds_align(a10, short, a10, a10)        # align / rmsd sets of one trajectory differ in frames
