@@ -915,6 +915,123 @@ void XTC::readFramePlanes(uint32_t fi, float* out) {
   }
 }
 
+// ---- Python float text ----------------------------------------------------------------------
+namespace {
+
+// repr() of a double: shortest digit string that converts back to the same double
+void pyRepr(double x, std::string& out) {
+  if (std::isnan(x)) { out += "nan"; return; }
+  if (std::isinf(x)) { out += x < 0 ? "-inf" : "inf"; return; }
+  if (x == 0.0) { out += std::signbit(x) ? "-0.0" : "0.0"; return; }
+  char buf[40];
+  int prec = 1;
+  for (; prec <= 17; ++prec) {
+    snprintf(buf, sizeof(buf), "%.*e", prec - 1, x);
+    if (strtod(buf, nullptr) == x) break;
+  }
+  // buf = [-]d[.ddd]e[+-]XX
+  const char* p = buf;
+  if (*p == '-') { out += '-'; ++p; }
+  std::string digits;
+  for (; *p && *p != 'e'; ++p)
+    if (*p != '.') digits += *p;
+  const int exp10 = atoi(p + 1);
+  while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+  const int decpt = exp10 + 1;  // value = 0.DIGITS x 10^decpt
+  if (decpt <= -4 || decpt > 16) {  // format_float_short, 'r': exponent form
+    out += digits[0];
+    if (digits.size() > 1) { out += '.'; out.append(digits, 1, std::string::npos); }
+    char e[8];
+    snprintf(e, sizeof(e), "e%+03d", decpt - 1);
+    out += e;
+  } else if (decpt <= 0) {
+    out += "0.";
+    out.append((size_t)(-decpt), '0');
+    out += digits;
+  } else if ((size_t)decpt >= digits.size()) {
+    out += digits;
+    out.append((size_t)decpt - digits.size(), '0');
+    out += ".0";
+  } else {
+    out.append(digits, 0, (size_t)decpt);
+    out += '.';
+    out.append(digits, (size_t)decpt, std::string::npos);
+  }
+}
+
+}  // namespace
+
+void pyRoundRepr(double v, int ndigits, std::string& out) {
+  if (!std::isfinite(v) || v == 0.0) { pyRepr(v, out); return; }
+  char buf[64];
+  // common case: 0..15 decimals of a value of ordinary size.  glibc's %.{n}f is the correctly rounded
+  // decimal (ties decided on the exact binary value, as _Py_dg_dtoa mode 3 does); with at most 15
+  // significant digits it IS the shortest string of the double it converts to.
+  if (ndigits >= 0 && ndigits <= 15 && std::fabs(v) < 1e15) {
+    const int n = snprintf(buf, sizeof(buf), "%.*f", ndigits, v);
+    int sig = 0;
+    bool lead = true, allzero = true;
+    for (int k = 0; k < n; ++k) {
+      const char c = buf[k];
+      if (c < '0' || c > '9') continue;
+      if (c != '0') { lead = false; allzero = false; }
+      if (!lead) ++sig;
+    }
+    if (allzero) { out += buf[0] == '-' ? "-0.0" : "0.0"; return; }
+    const double r = strtod(buf, nullptr);
+    if (sig <= 15 && std::fabs(r) >= 1e-4) {
+      int end = n;
+      if (ndigits > 0) {
+        while (buf[end - 1] == '0') --end;
+        if (buf[end - 1] == '.') ++end;  // keep one zero: "2.0"
+        out.append(buf, (size_t)end);
+      } else {
+        out.append(buf, (size_t)n);
+        out += ".0";
+      }
+      return;
+    }
+    pyRepr(r, out);
+    return;
+  }
+  // general case (float.__round__, Objects/floatobject.c double_round): exact decimal expansion,
+  // round half even at the requested position, convert back, repr
+  if (ndigits > 323) { pyRepr(v, out); return; }
+  if (ndigits < -308) { pyRepr(v < 0 ? -0.0 : 0.0, out); return; }
+  std::vector<char> big(1500);
+  const int n = snprintf(big.data(), big.size(), "%.1100f", std::fabs(v));  // exact: a double has <= 1074 fractional bits
+  std::string s(big.data(), (size_t)n);
+  const size_t dot = s.find('.');
+  std::string ip = s.substr(0, dot), fp = s.substr(dot + 1);
+  std::string all = ip + fp;                     // digits, point after ip.size()
+  long keep = (long)ip.size() + ndigits;         // digits kept
+  std::string res;
+  if (keep < 0) res = "0";
+  else {
+    bool up = false;
+    if ((size_t)keep < all.size()) {
+      const char d = all[(size_t)keep];
+      bool rest = false;
+      for (size_t k = (size_t)keep + 1; k < all.size() && !rest; ++k) rest = all[k] != '0';
+      if (d > '5' || (d == '5' && rest)) up = true;
+      else if (d == '5') up = keep > 0 && ((all[(size_t)keep - 1] - '0') & 1);
+    }
+    res = all.substr(0, (size_t)keep);
+    if (up) {
+      long k = (long)res.size() - 1;
+      for (; k >= 0; --k) {
+        if (res[(size_t)k] == '9') res[(size_t)k] = '0';
+        else { ++res[(size_t)k]; break; }
+      }
+      if (k < 0) { res.insert(res.begin(), '1'); ++keep; ip.insert(ip.begin(), '0'); }
+    }
+    if (res.empty()) res = "0";
+  }
+  // res holds the kept digits; its decimal point sits ndigits from the right (ndigits may be negative)
+  std::string text = (v < 0 ? "-" : "") + res + "e" + std::to_string(-ndigits);
+  pyRepr(strtod(text.c_str(), nullptr), out);
+}
+
 std::shared_ptr<Trajectory> openTrajectory(const std::string& path, uint32_t natoms) {
   const size_t dot = path.rfind('.');
   std::string suffix = dot == std::string::npos ? "" : path.substr(dot + 1);

@@ -170,6 +170,12 @@ int formatFloatG(float v, unsigned precision, char* out);
 // ---- options (src/OptionsFramework.cpp:742-795: boost::program_options semantics used by
 // the tools: long names without prefix guessing, short aliases, every option takes a
 // value -- booleans too --, positionals in declaration order) ----
+// The text Python prints for `round(v, ndigits)` of a float (float.__round__ = correctly rounded
+// decimal at that position, converted back to double; repr = shortest digits that round-trip,
+// exponent form when the decimal exponent is < -4 or >= 16).  Packages/Clustering/rmsds-align.py:254
+// writes its matrix that way.  Appends to `out`.
+void pyRoundRepr(double v, int ndigits, std::string& out);
+
 class Options {
  public:
   void add(const std::string& longname, char shortname, const std::string& defval, const std::string& help,

@@ -68,6 +68,15 @@ int lbfe_dcd_read(const char* path, uint32_t frame, float* planes) {
 }
 
 // any supported trajectory through openTrajectory (suffix dispatch)
+// Python's repr(round(v, ndigits)) (the text of rmsds-align.py's matrix); returns the length or -1
+int lbfe_py_round_repr(double v, int ndigits, char* out, int cap) {
+  std::string s;
+  pyRoundRepr(v, ndigits, s);
+  if ((int)s.size() + 1 > cap) return -1;
+  memcpy(out, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
+
 int lbfe_traj_info(const char* path, uint32_t natoms_expected, uint32_t* natoms, uint32_t* nframes) {
   try { auto t = openTrajectory(path, natoms_expected); *natoms = t->natoms(); *nframes = t->nframes(); return 0; }
   catch (const std::exception& e) { return fail(e); }

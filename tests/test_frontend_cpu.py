@@ -58,6 +58,7 @@ SELECTIONS = [
     "id > 100 && id <= 120", "(resid) == 10001", "(name == 'CA')", "((name == 'CA') && (index > 5))",
     "name -> '(\\d+)' == 12", "name -> '(\\d+)' < 13", "name -> 'H(\\d)' >= 1", "chainid == 'W' && name == 'OH2'",
     "resname =~ 'tip'", "name == \"CB\"", "backbone && !hydrogen", "name == 'CA' # trailing comment", "resid+ == 10003",
+    'name =~ "^(C|O|N|CA)$"', 'resid <= 10020 && name== "CA"', 'resid > 10025 && name =~ "^(C|CA|CB|O|N)$"',    # rmsds-align.py's defaults / examples
 ]
 
 
@@ -429,3 +430,56 @@ def test_xtc_validation(fe, tmp_path):
     r = str(tmp_path / "c.xtc"); open(r, "wb").write(raw[:len(raw) - 10])      # last frame cut short
     assert fe.lbfe_traj_info(r.encode(), 20, C.byref(na), C.byref(nf)) == -1
     assert "truncated" in fe.lbfe_last_error().decode()
+
+
+# ------------------------------------------------------------------ Python float text (rmsds-align)
+def test_py_round_repr_matches_python(fe):
+    """pyRoundRepr(v, n) == repr(round(v, n)): the text Packages/Clustering/rmsds-align.py:254 prints.
+    Pinned against this interpreter's own float.__round__ / repr."""
+    fe.lbfe_py_round_repr.argtypes = [C.c_double, C.c_int, C.c_char_p, C.c_int]
+    buf = C.create_string_buffer(400)
+
+    def native(v, n):
+        k = fe.lbfe_py_round_repr(v, n, buf, 400)
+        assert k >= 0
+        return buf.value.decode()
+
+    rng = np.random.default_rng(17)
+    vals = list(rng.gamma(2.0, 2.0, 4000)) + list(rng.uniform(0, 1e-3, 500)) + list(rng.uniform(0, 5e4, 500))
+    vals += [0.0, -0.0, 0.5, 1.5, 2.5, 0.125, 0.375, 2.675, 1.005, 1e-5, 1.23456e-7, 9.995, 99.995, 0.99999999, 1e15, 1e16, 1.5e16,
+             123456789012345.678, 2.0 ** -20, 2.0 ** 60, 1e22, 1e23, float("inf"), float("nan"), -3.14159, -0.004, 5e-324, 1.7976931348623157e308]
+    vals += [k / 1000.0 for k in range(0, 4000, 5)] + [k + 0.5 for k in range(20)]
+    for n in (0, 1, 2, 3, 4, 6, 9, 12, 15, 16, 17, 20, -1, -2, -5, 400, -400):
+        for v in vals:
+            v = float(v)
+            assert native(v, n) == repr(round(v, n)), (v, n)
+
+
+def test_rmsds_align_command_line(system, tmp_path):
+    """What rmsds-align decides before any GPU work, as Packages/Clustering/rmsds-align.py:118-206 does:
+    required positionals (argparse: status 2), the range forms, "Error in range" on stdout with status 0,
+    frames beyond the trajectory, and -- without a GPU -- a loud failure with an empty stdout."""
+    import shutil
+    exe = os.path.join(ROOT, "loos_b200", "bin", "rmsds-align")
+    run = lambda *a: subprocess.run([exe] + [str(x) for x in a], capture_output=True, text=True)
+    r = run(system["pdb"])
+    assert r.returncode == 2 and "the following arguments are required" in r.stderr and r.stdout == ""
+    r = run("--range1", "0", system["pdb"], system["dcd"])
+    assert r.returncode == 0 and r.stdout == "Error in range\n"
+    r = run("--range1", "0:1:2:3", system["pdb"], system["dcd"])
+    assert r.returncode == 0 and r.stdout == "Error in range\n"
+    r = run("--range1", "0:1:5", "--range2", "0:1", system["pdb"], system["dcd"])      # range_2[2] in the script
+    assert r.returncode == 1 and "IndexError" in r.stderr
+    r = run("--range1", "0:0:5", system["pdb"], system["dcd"])
+    assert r.returncode == 1 and "range() arg 3 must not be zero" in r.stderr
+    r = run("--range1", "0:1:100000", system["pdb"], system["dcd"])
+    assert r.returncode == 1 and "out of range" in r.stderr and r.stdout == ""
+    # the open-ended form stops at len(file name): a long name asks for frames the trajectory does not have
+    long_name = tmp_path / ("x" * 150 + ".dcd")
+    shutil.copy(system["dcd"], long_name)
+    r = run(system["pdb"], long_name)
+    assert r.returncode == 1 and "length of the trajectory's file name" in r.stderr and "out of range" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = run("--range1", "0:1:4", system["pdb"], system["dcd"])
+        assert r.returncode == 1 and "no usable sm_100" in r.stderr and r.stdout == ""

@@ -243,3 +243,54 @@ def test_binary_side_channel(files, tmp_path):
     assert np.array_equal(C2, parse_matrix(out)[1].astype(np.float32))
     run("multi-rmsds", "-N", "1", "--binary", npy, d / "model.pdb", d / "a.dcd", d / "b.dcd")
     assert np.load(npy).shape == (115, 115)
+
+
+def test_rmsds_align_tool(files, checker, tmp_path):
+    """rmsds-align: header, one line per frame of trajectory 1, values as Python prints round(v, p);
+    against the oracle's restatement of the script's loop fed through the restated readers/selection.
+    One trajectory with different align / rmsd selections, then two trajectories with ranges."""
+    import shutil
+    from oracle import oracle
+    d, atoms, xyz = files["d"], files["atoms"], files["xyz"]
+    exe = os.path.join(BIN, "rmsds-align")
+
+    def go(*args):
+        r = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        return r
+
+    align, rmsd = 'resid <= 20 && name == "CA"', 'resid > 25 && name =~ "^(C|CA|CB|O|N)$"'
+    ia, ir = fo.select(atoms, align), fo.select(atoms, rmsd)
+    assert len(ia) == 20 and len(ir) > 100
+    X = xyz.astype(np.float64)
+    # explicit stop: frames 5, 8, ..., 38
+    fr = list(range(5, 40, 3))
+    r = go("--align", align, "--rmsd", rmsd, "--range1", "5:3:40", "--precision", "4", d / "model.pdb", d / "all.dcd")
+    want = oracle.rmsds_align(checker, X[fr][:, ia], X[fr][:, ir], X[fr][:, ia], X[fr][:, ir])
+    lines = r.stdout.splitlines()
+    assert lines[0].startswith("# ") and lines[0].endswith("all.dcd") and "--precision 4" in lines[0]
+    assert r.stdout[len(lines[0]) + 1:] == oracle.py_round_text(want, 4)
+    # the default range stops at len(name), the length of the path as given
+    short = tmp_path / "t.dcd"
+    shutil.copy(d / "all.dcd", short)
+    n = len(str(short))
+    r = go(d / "model.pdb", short)
+    assert "length of the trajectory's file name" in r.stderr
+    body = r.stdout.splitlines()[1:]
+    assert len(body) == n and all(len(l.split()) == n for l in body)
+    ia, ir = fo.select(atoms, 'name == "CA"'), fo.select(atoms, 'name =~ "^(C|O|N|CA)$"')
+    want = oracle.rmsds_align(checker, X[:n][:, ia], X[:n][:, ir], X[:n][:, ia], X[:n][:, ir])
+    assert "\n".join(body) + "\n" == oracle.py_round_text(want, 2)
+    # two trajectories, different selections of equal size on each side
+    a1, a2 = 'resid <= 20 && name == "CA"', 'resid >= 25 && resid <= 44 && name == "CA"'
+    r1, r2 = 'resid > 25 && resid < 50 && name == "CB"', 'resid < 25 && name == "CB"'
+    r = go("--align", a1, "--align2", a2, "--rmsd", r1, "--rmsd2", r2, "--model2", d / "model.pdb", "--traj2", d / "b.dcd",
+           "--range1", "0:7:70", "--range2", "1:2:30", "--precision", "3", d / "model.pdb", d / "a.dcd")
+    f1, f2 = list(range(0, 70, 7)), [70 + k for k in range(1, 30, 2)]          # b.dcd holds frames 70..114
+    s = lambda q: fo.select(atoms, q)
+    want = oracle.rmsds_align(checker, X[f1][:, s(a1)], X[f1][:, s(r1)], X[f2][:, s(a2)], X[f2][:, s(r2)])
+    assert r.stdout.split("\n", 1)[1] == oracle.py_round_text(want, 3)
+    # selections of different sizes: the reference's exception text, status 1, nothing on stdout
+    r = subprocess.run([exe, "--align2", 'resid <= 10 && name == "CA"', "--range1", "0:1:5", str(d / "model.pdb"), str(d / "all.dcd")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "differing numbers of atoms" in r.stderr and r.stdout == ""
