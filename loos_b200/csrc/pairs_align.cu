@@ -240,12 +240,12 @@ extern "C" int loosb200_rmsds_align(loosb200_frames* align1, loosb200_frames* rm
     ++launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) break;
+    cudaEventRecord(align1->timing.ev[2], st);  // re-recorded per band: the kernels (and, with several bands, the copies between them)
     // band (column-major, ld = band_rows) -> rows [row0, row0 + band_rows) of the caller's matrix
     e = cudaMemcpy2DAsync(out + a.row0, ld * sizeof(double), d_band, (size_t)a.band_rows * sizeof(double),
                           (size_t)a.band_rows * sizeof(double), FB, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && t0 + band_tiles < row_tiles) e = cudaStreamSynchronize(st);  // the band buffer is reused
   }
-  cudaEventRecord(align1->timing.ev[2], st);
   cudaEventRecord(align1->timing.ev[3], st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaGetLastError();

@@ -78,11 +78,31 @@ def rmsd2ref_e2e(F, N, steps=2):
                       "rmsd_mean": float(d.mean())}))
 
 
+def rmsds_align(F, Na, Nr, steps=3):
+    """rmsds-align: F x F pairs, align on Na atoms, rmsd over Nr others; fp64 pipe, 18 (Na + Nr) flop per pair."""
+    X = synth_frames_torch(F, Na + Nr, seed=20261022, device="cuda", chunk=4096).cpu().numpy()
+    sa, sr = np.arange(Na, dtype=np.uint32), np.arange(Na, Na + Nr, dtype=np.uint32)
+    with lb.FrameSet(X, sel=sa) as a, lb.FrameSet(X, sel=sr) as r:
+        lb.rmsds_align(a, r)
+        ms, wall = [], []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            M = lb.rmsds_align(a, r)
+            wall.append(1e3 * (time.perf_counter() - t0))
+            ms.append(a.last_timing()[0])
+    ms, wall = float(np.median(ms)), float(np.median(wall))
+    pairs = float(F) * F
+    print(json.dumps({"measure": "rmsds_align", "frames": F, "align_atoms": Na, "rmsd_atoms": Nr, "kernel_ms": ms, "call_ms": wall,
+                      "pairs_per_s": pairs / ms * 1e3, "fp64_TFLOPs": 18.0 * (Na + Nr) * pairs / ms / 1e9, "mean": float(M.mean())}))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "pcie"):
         pcie()
     if what in ("rmsd2ref_e2e",):
         rmsd2ref_e2e(int(os.environ.get("C2_FRAMES", 1000000)), 2000)
+    if what in ("rmsds_align",):
+        rmsds_align(int(os.environ.get("ALIGN_FRAMES", 4000)), 500, 500)
     if what in ("all", "rmsd2ref"):
         rmsd2ref(int(os.environ.get("C2_FRAMES", 1000000)), 2000)
