@@ -29,6 +29,8 @@ namespace {
 
 constexpr int TF = TILE_FRAMES;  // 40
 constexpr int KC = 16;           // atoms per smem chunk
+constexpr int TFP = 42;          // row pitch of the smem tiles in doubles: 16-byte aligned pairs, and the k-fastest fill
+                                 // hits 8 distinct bank pairs instead of 2 (pitch 40: 16-way conflicts on every store)
 constexpr int NT = 416;          // 13 warps; threads 0..399 own a 2x2 block of pairs
 
 // g[f] = sum over the set's atoms of |x - cen[f]|^2 with cen taken from ANOTHER set (the align
@@ -65,10 +67,12 @@ struct AlignArgs {
   double* out;                             // band, column-major: out[j * band_rows + (i - row0)]
 };
 
+// 13 warps put 4 on one SM sub-partition (16,384 registers): 128 registers per thread is the most that
+// launches (144 and 152 fail with cudaErrorLaunchOutOfResources), which is what __launch_bounds__ settles on
 __global__ void __launch_bounds__(NT)
 k_pairs_align(const AlignArgs a) {
-  __shared__ double As[3][KC][TF];
-  __shared__ double Bs[3][KC][TF];
+  __shared__ __align__(16) double As[3][KC][TFP];
+  __shared__ __align__(16) double Bs[3][KC][TFP];
   __shared__ double cA[TF][3], cB[TF][3];
 
   const uint32_t I0 = a.row0 + blockIdx.y * TF, J0 = blockIdx.x * TF;
@@ -84,7 +88,7 @@ k_pairs_align(const AlignArgs a) {
   __syncthreads();
 
   double acc[2][2][9];
-  double Z[2][2][9];
+  double quat[2][2][4];  // the rotations of phase 0, kept as unit quaternions while phase 1 accumulates
 
   // phase 0: R over the align selection -> Z;  phase 1: C over the rmsd selection
   for (int phase = 0; phase < 2; ++phase) {
@@ -99,27 +103,45 @@ k_pairs_align(const AlignArgs a) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) acc[p][q][k] = 0.0;
 
-    for (uint32_t k0 = 0; k0 < N; k0 += KC) {
-      for (int idx = tid; idx < TF * 3 * KC; idx += NT) {
+    // the chunk after the one being multiplied is already on its way from global memory (registers):
+    // with one CTA per SM nothing else would hide that latency
+    constexpr int PF = (TF * 3 * KC + NT - 1) / NT;  // elements of each operand per thread and chunk
+    float pa[PF], pb[PF];
+    auto prefetch = [&](uint32_t k0) {
+#pragma unroll
+      for (int r = 0; r < PF; ++r) {
+        const int idx = tid + r * NT;
         const int f = idx / (3 * KC), rem = idx % (3 * KC), ax = rem / KC, k = rem % KC;
         const uint32_t fa = I0 + f, fb = J0 + f, at = k0 + k;
-        double va = 0.0, vb = 0.0;
-        if (at < N) {
-          if (fa < a.FA) va = (double)rawA[((size_t)fa * 3 + ax) * padA + at] - cA[f][ax];
-          if (fb < a.FB) vb = (double)rawB[((size_t)fb * 3 + ax) * padB + at] - cB[f][ax];
-        }
-        As[ax][k][f] = va;
-        Bs[ax][k][f] = vb;
+        const bool in = idx < TF * 3 * KC && at < N;
+        pa[r] = in && fa < a.FA ? rawA[((size_t)fa * 3 + ax) * padA + at] : 0.f;
+        pb[r] = in && fb < a.FB ? rawB[((size_t)fb * 3 + ax) * padB + at] : 0.f;
       }
+    };
+    prefetch(0);
+    for (uint32_t k0 = 0; k0 < N; k0 += KC) {
+#pragma unroll
+      for (int r = 0; r < PF; ++r) {
+        const int idx = tid + r * NT;
+        if (idx < TF * 3 * KC) {
+          const int f = idx / (3 * KC), rem = idx % (3 * KC), ax = rem / KC, k = rem % KC;
+          const bool in = k0 + k < N;  // padded atoms and frames beyond the sets contribute exact zeros
+          As[ax][k][f] = in && I0 + f < a.FA ? (double)pa[r] - cA[f][ax] : 0.0;
+          Bs[ax][k][f] = in && J0 + f < a.FB ? (double)pb[r] - cB[f][ax] : 0.0;
+        }
+      }
+      if (k0 + KC < N) prefetch(k0 + KC);
       __syncthreads();
       if (worker) {
 #pragma unroll 4
         for (int k = 0; k < KC; ++k) {
           double a0[3], a1[3], b0[3], b1[3];
 #pragma unroll
-          for (int ax = 0; ax < 3; ++ax) {
-            a0[ax] = As[ax][k][ty]; a1[ax] = As[ax][k][ty + 20];
-            b0[ax] = Bs[ax][k][tx]; b1[ax] = Bs[ax][k][tx + 20];
+          for (int ax = 0; ax < 3; ++ax) {  // frames 2 ty, 2 ty + 1 and 2 tx, 2 tx + 1: one 16-byte load each
+            const double2 av = *reinterpret_cast<const double2*>(&As[ax][k][2 * ty]);
+            const double2 bv = *reinterpret_cast<const double2*>(&Bs[ax][k][2 * tx]);
+            a0[ax] = av.x; a1[ax] = av.y;
+            b0[ax] = bv.x; b1[ax] = bv.y;
           }
 #pragma unroll
           for (int p = 0; p < 3; ++p)
@@ -141,21 +163,22 @@ k_pairs_align(const AlignArgs a) {
       for (int p = 0; p < 2; ++p)
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const uint32_t i = I0 + ty + 20 * p, j = J0 + tx + 20 * q;
+          const uint32_t i = I0 + 2 * ty + p, j = J0 + 2 * tx + q;
           if (i >= a.FA || j >= a.FB) continue;
           // Z maps the align selection of i onto that of j; the Jacobi solve takes the
           // (near-)degenerate cases -- collinear / planar selections, fewer than 3 atoms
-          if (!qcp_rotation_fast(acc[p][q], a.gdA[i], a.gdB[j], Z[p][q])) qcp_rotation(acc[p][q], Z[p][q], nullptr);
+          if (!qcp_rotation_fast(acc[p][q], a.gdA[i], a.gdB[j], nullptr, nullptr, quat[p][q])) qcp_rotation(acc[p][q], nullptr, nullptr, quat[p][q]);
         }
     } else {
 #pragma unroll
       for (int p = 0; p < 2; ++p)
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const uint32_t i = I0 + ty + 20 * p, j = J0 + tx + 20 * q;
+          const uint32_t i = I0 + 2 * ty + p, j = J0 + 2 * tx + q;
           if (i >= a.FA || j >= a.FB || i >= a.row0 + a.band_rows) continue;
           const double* C = acc[p][q];
-          const double* z = Z[p][q];
+          double z[9];
+          qcp_quat_to_rot(quat[p][q], z);
           double tr = 0.0;  // sum_k (Z x'_k) . y'_k = sum_ab Z_ab C_ba
 #pragma unroll
           for (int r = 0; r < 3; ++r)

@@ -16,6 +16,8 @@ namespace {
 
 constexpr int TF = TILE_FRAMES;  // 40
 constexpr int KC = 16;           // atoms per smem chunk
+constexpr int TFP = 42;          // row pitch of the smem tiles in doubles: 16-byte aligned pairs, and the k-fastest fill
+                                 // hits 8 distinct bank pairs instead of 2 (pitch 40: 16-way conflicts on every store)
 constexpr int NT = 416;          // 13 warps; threads 0..399 own a 2x2 block of pairs
 
 __device__ __forceinline__ uint32_t find_row_tile(const uint32_t* __restrict__ prefix, uint32_t n,
@@ -36,8 +38,8 @@ k_pairs_fp64(const float* __restrict__ rawA, const double* __restrict__ cenA,
              const uint32_t* __restrict__ row_tiles, const uint32_t* __restrict__ prefix,
              uint32_t n_row_tiles, int self, int symmetric, int packed, float* __restrict__ out,
              size_t ld, double* __restrict__ stats) {
-  __shared__ double As[3][KC][TF];
-  __shared__ double Bs[3][KC][TF];
+  __shared__ __align__(16) double As[3][KC][TFP];
+  __shared__ __align__(16) double Bs[3][KC][TFP];
   __shared__ double cA[TF][3], cB[TF][3];
   __shared__ double red_sum[13], red_max[13];
 
@@ -82,9 +84,11 @@ k_pairs_fp64(const float* __restrict__ rawA, const double* __restrict__ cenA,
       for (int k = 0; k < KC; ++k) {
         double a0[3], a1[3], b0[3], b1[3];
 #pragma unroll
-        for (int ax = 0; ax < 3; ++ax) {
-          a0[ax] = As[ax][k][ty]; a1[ax] = As[ax][k][ty + 20];
-          b0[ax] = Bs[ax][k][tx]; b1[ax] = Bs[ax][k][tx + 20];
+        for (int ax = 0; ax < 3; ++ax) {  // frames 2 ty, 2 ty + 1 and 2 tx, 2 tx + 1: one 16-byte load each
+          const double2 av = *reinterpret_cast<const double2*>(&As[ax][k][2 * ty]);
+          const double2 bv = *reinterpret_cast<const double2*>(&Bs[ax][k][2 * tx]);
+          a0[ax] = av.x; a1[ax] = av.y;
+          b0[ax] = bv.x; b1[ax] = bv.y;
         }
 #pragma unroll
         for (int p = 0; p < 3; ++p)
@@ -106,7 +110,7 @@ k_pairs_fp64(const float* __restrict__ rawA, const double* __restrict__ cenA,
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
-        const uint32_t la = ty + 20 * a, lb = tx + 20 * b;
+        const uint32_t la = 2 * ty + a, lb = 2 * tx + b;
         const uint32_t i = I * TF + la, j = J * TF + lb;
         if (i >= FA || j >= FB) continue;
         if (self && j >= i) {

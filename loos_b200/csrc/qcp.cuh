@@ -512,17 +512,24 @@ LB_HD double qcp_rmsd(const double* R, double ga, double gb, double n, double un
 // Rotation (row-major 3x3, maps u onto v: v ~ Z u) from R, via the eigenvector of
 // K for lambda_max.  Always uses the Jacobi solve: it is called once per frame on
 // the streaming path, never per pair.
-LB_HD void qcp_rotation(const double* R, double* Z, double* lambda_out) {
+// Unit quaternion (w, x, y, z) -> rotation matrix, row-major.
+LB_HD void qcp_quat_to_rot(const double* q, double* Z) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  Z[0] = w * w + x * x - y * y - z * z; Z[1] = 2 * (x * y - w * z);           Z[2] = 2 * (x * z + w * y);
+  Z[3] = 2 * (x * y + w * z);           Z[4] = w * w - x * x + y * y - z * z; Z[5] = 2 * (y * z - w * x);
+  Z[6] = 2 * (x * z - w * y);           Z[7] = 2 * (y * z + w * x);           Z[8] = w * w - x * x - y * y + z * z;
+}
+
+LB_HD void qcp_rotation(const double* R, double* Z, double* lambda_out, double* quat_out = 0) {
   double K[10], q[4];
   qcp_build_K(R, K);
   const double lam = qcp_jacobi_max(K, q);
   if (lambda_out) *lambda_out = lam;
   const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
   const double s = n2 > 0 ? 1.0 / sqrt(n2) : 0.0;
-  const double w = q[0] * s, x = q[1] * s, y = q[2] * s, z = q[3] * s;
-  Z[0] = w * w + x * x - y * y - z * z; Z[1] = 2 * (x * y - w * z);           Z[2] = 2 * (x * z + w * y);
-  Z[3] = 2 * (x * y + w * z);           Z[4] = w * w - x * x + y * y - z * z; Z[5] = 2 * (y * z - w * x);
-  Z[6] = 2 * (x * z - w * y);           Z[7] = 2 * (y * z + w * x);           Z[8] = w * w - x * x - y * y + z * z;
+  const double u[4] = {q[0] * s, q[1] * s, q[2] * s, q[3] * s};
+  if (quat_out) { quat_out[0] = u[0]; quat_out[1] = u[1]; quat_out[2] = u[2]; quat_out[3] = u[3]; }
+  if (Z) qcp_quat_to_rot(u, Z);
 }
 
 // Rotation for the streaming path without the Jacobi sweeps: lambda_max from the
@@ -531,7 +538,8 @@ LB_HD void qcp_rotation(const double* R, double* Z, double* lambda_out) {
 // Returns false (caller falls back to qcp_rotation) when the top eigenvalue is not
 // well separated -- collinear / planar / N < 3 inputs -- or the solve did not settle.
 // *resid (optional) receives ga + gb - 2 lambda_max = 2 e0 y, free of cancellation.
-LB_HD bool qcp_rotation_fast(const double* R, double ga, double gb, double* Z, double* resid = 0) {
+// quat_out (optional) receives the unit quaternion; Z may then be null.
+LB_HD bool qcp_rotation_fast(const double* R, double ga, double gb, double* Z, double* resid = 0, double* quat_out = 0) {
   const double e0 = 0.5 * (ga + gb);
   if (!(e0 > 0.0)) return false;
   const QcpPoly p = qcp_poly(R, e0);
@@ -589,10 +597,9 @@ LB_HD bool qcp_rotation_fast(const double* R, double ga, double gb, double* Z, d
   if (!(dm > 1e-7)) return false;
   const double n2 = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
   const double sN = 1.0 / sqrt(n2);
-  const double w = q0 * sN, x = q1 * sN, yv = q2 * sN, z = q3 * sN;
-  Z[0] = w * w + x * x - yv * yv - z * z; Z[1] = 2 * (x * yv - w * z);           Z[2] = 2 * (x * z + w * yv);
-  Z[3] = 2 * (x * yv + w * z);           Z[4] = w * w - x * x + yv * yv - z * z; Z[5] = 2 * (yv * z - w * x);
-  Z[6] = 2 * (x * z - w * yv);           Z[7] = 2 * (yv * z + w * x);           Z[8] = w * w - x * x - yv * yv + z * z;
+  const double u[4] = {q0 * sN, q1 * sN, q2 * sN, q3 * sN};
+  if (quat_out) { quat_out[0] = u[0]; quat_out[1] = u[1]; quat_out[2] = u[2]; quat_out[3] = u[3]; }
+  if (Z) qcp_quat_to_rot(u, Z);
   return true;
 }
 
