@@ -66,18 +66,34 @@ k_pairs_fp64(const float* __restrict__ rawA, const double* __restrict__ cenA,
 #pragma unroll
       for (int k = 0; k < 9; ++k) acc[a][b][k] = 0.0;
 
-  for (uint32_t k0 = 0; k0 < N; k0 += KC) {
-    for (int idx = tid; idx < TF * 3 * KC; idx += NT) {
+  // the chunk after the one being multiplied is already on its way from global memory (registers):
+  // with one CTA per SM nothing else would hide that latency
+  constexpr int PF = (TF * 3 * KC + NT - 1) / NT;  // elements of each operand per thread and chunk
+  float pa[PF], pb[PF];
+  auto prefetch = [&](uint32_t k0) {
+#pragma unroll
+    for (int r = 0; r < PF; ++r) {
+      const int idx = tid + r * NT;
       const int f = idx / (3 * KC), rem = idx % (3 * KC), ax = rem / KC, k = rem % KC;
       const uint32_t fa = I * TF + f, fb = J * TF + f, at = k0 + k;
-      double va = 0.0, vb = 0.0;
-      if (at < N) {
-        if (fa < FA) va = (double)rawA[((size_t)fa * 3 + ax) * NpadA + at] - cA[f][ax];
-        if (fb < FB) vb = (double)rawB[((size_t)fb * 3 + ax) * NpadB + at] - cB[f][ax];
-      }
-      As[ax][k][f] = va;
-      Bs[ax][k][f] = vb;
+      const bool in = idx < TF * 3 * KC && at < N;
+      pa[r] = in && fa < FA ? rawA[((size_t)fa * 3 + ax) * NpadA + at] : 0.f;
+      pb[r] = in && fb < FB ? rawB[((size_t)fb * 3 + ax) * NpadB + at] : 0.f;
     }
+  };
+  prefetch(0);
+  for (uint32_t k0 = 0; k0 < N; k0 += KC) {
+#pragma unroll
+    for (int r = 0; r < PF; ++r) {
+      const int idx = tid + r * NT;
+      if (idx < TF * 3 * KC) {
+        const int f = idx / (3 * KC), rem = idx % (3 * KC), ax = rem / KC, k = rem % KC;
+        const bool in = k0 + k < N;  // padded atoms and frames beyond the sets contribute exact zeros
+        As[ax][k][f] = in && I * TF + f < FA ? (double)pa[r] - cA[f][ax] : 0.0;
+        Bs[ax][k][f] = in && J * TF + f < FB ? (double)pb[r] - cB[f][ax] : 0.0;
+      }
+    }
+    if (k0 + KC < N) prefetch(k0 + KC);
     __syncthreads();
     if (worker) {
 #pragma unroll 4
