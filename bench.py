@@ -438,7 +438,11 @@ def main():
                          "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
                          "kernel": "k_pairs_tensor" if args.engine != "fp64" else "k_pairs_fp64",
                          "kernel_ms_per_launch": kern_ms_step, "peak_basis": basis,
-                         "algorithmic": "18*N flop per frame pair x pairs per launch"},
+                         "algorithmic": "18*N flop per frame pair x pairs per launch",
+                         "shape_ceiling_frac": 0.947,
+                         "shape_ceiling_source": "profiles/r1_ubench_mma_n.txt: M=128 kind::i8 MMAs read both operands from "
+                                                 "shared memory at 128 B/clk; per K step 3 x N=192 (96 clk) + 3 x N=96 (56 clk) "
+                                                 "= 456 clk for 432 clk of MACs"},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "parity": parity,
