@@ -67,30 +67,38 @@ k_pairs_fp64(const float* __restrict__ rawA, const double* __restrict__ cenA,
       for (int k = 0; k < 9; ++k) acc[a][b][k] = 0.0;
 
   // the chunk after the one being multiplied is already on its way from global memory (registers):
-  // with one CTA per SM nothing else would hide that latency
-  constexpr int PF = (TF * 3 * KC + NT - 1) / NT;  // elements of each operand per thread and chunk
-  float pa[PF], pb[PF];
+  // with one CTA per SM nothing else would hide that latency.  A chunk is 120 rows (frame, axis) of
+  // 16 atoms per operand = 2 x 480 float4; item = tid + r * NT names (operand, row, quarter).
+  constexpr int ITEMS = 2 * TF * 3 * (KC / 4);       // 960
+  constexpr int PF = (ITEMS + NT - 1) / NT;          // 3 float4 per thread and chunk
+  float4 pv[PF];
   auto prefetch = [&](uint32_t k0) {
 #pragma unroll
     for (int r = 0; r < PF; ++r) {
-      const int idx = tid + r * NT;
-      const int f = idx / (3 * KC), rem = idx % (3 * KC), ax = rem / KC, k = rem % KC;
-      const uint32_t fa = I * TF + f, fb = J * TF + f, at = k0 + k;
-      const bool in = idx < TF * 3 * KC && at < N;
-      pa[r] = in && fa < FA ? rawA[((size_t)fa * 3 + ax) * NpadA + at] : 0.f;
-      pb[r] = in && fb < FB ? rawB[((size_t)fb * 3 + ax) * NpadB + at] : 0.f;
+      const int item = tid + r * NT;
+      const int op = item / (ITEMS / 2), within = item % (ITEMS / 2), row = within >> 2, qd = within & 3;
+      const uint32_t fr = (op ? J : I) * TF + row / 3, at = k0 + 4 * qd;
+      // Npad is a multiple of 4, so a quarter that starts below N lies inside the row
+      const bool in = item < ITEMS && at < N && fr < (op ? FB : FA);
+      const float* src = (op ? rawB : rawA) + ((size_t)fr * 3 + row % 3) * (op ? NpadB : NpadA) + at;
+      pv[r] = in ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   prefetch(0);
   for (uint32_t k0 = 0; k0 < N; k0 += KC) {
 #pragma unroll
     for (int r = 0; r < PF; ++r) {
-      const int idx = tid + r * NT;
-      if (idx < TF * 3 * KC) {
-        const int f = idx / (3 * KC), rem = idx % (3 * KC), ax = rem / KC, k = rem % KC;
-        const bool in = k0 + k < N;  // padded atoms and frames beyond the sets contribute exact zeros
-        As[ax][k][f] = in && I * TF + f < FA ? (double)pa[r] - cA[f][ax] : 0.0;
-        Bs[ax][k][f] = in && J * TF + f < FB ? (double)pb[r] - cB[f][ax] : 0.0;
+      const int item = tid + r * NT;
+      if (item < ITEMS) {
+        const int op = item / (ITEMS / 2), within = item % (ITEMS / 2), row = within >> 2, qd = within & 3;
+        const int f = row / 3, ax = row % 3;
+        const bool fr_ok = (op ? J : I) * TF + f < (op ? FB : FA);
+        const double c = op ? cB[f][ax] : cA[f][ax];
+        double (*dst)[TFP] = op ? Bs[ax] : As[ax];
+        const float v[4] = {pv[r].x, pv[r].y, pv[r].z, pv[r].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)  // padded atoms and frames beyond the sets contribute exact zeros
+          dst[4 * qd + e][f] = fr_ok && k0 + 4 * qd + e < N ? (double)v[e] - c : 0.0;
       }
     }
     if (k0 + KC < N) prefetch(k0 + KC);
