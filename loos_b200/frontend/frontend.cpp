@@ -9,6 +9,8 @@
 #include <string.h>
 #include <time.h>
 #include <unistd.h>
+#include <fcntl.h>
+#include <sys/stat.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -468,6 +470,33 @@ std::vector<uint32_t> uniquify(const std::vector<uint32_t>& v) {
 
 static uint32_t swab32(uint32_t x) { return __builtin_bswap32(x); }
 
+// ---- positional file reads ---------------------------------------------------------------------
+PosFile::~PosFile() { if (fd_ >= 0) ::close(fd_); }
+void PosFile::open(const std::string& path) {
+  fd_ = ::open(path.c_str(), O_RDONLY);
+  struct stat st;
+  if (fd_ < 0 || fstat(fd_, &st) != 0) throw Error("Cannot open " + path);
+  size_ = (uint64_t)st.st_size;
+}
+void PosFile::readAt(uint64_t off, void* dst, size_t n, const std::string& what) const {
+  char* p = (char*)dst;
+  while (n > 0) {
+    const ssize_t got = ::pread(fd_, p, n, (off_t)off);
+    if (got < 0 && errno == EINTR) continue;
+    if (got <= 0) throw Error(what);
+    p += got; off += (uint64_t)got; n -= (size_t)got;
+  }
+}
+
+namespace {
+// per-thread staging area for the raw bytes of one frame
+std::vector<unsigned char>& frameScratch(size_t n) {
+  static thread_local std::vector<unsigned char> buf;
+  if (buf.size() < n) buf.resize(n);
+  return buf;
+}
+}  // namespace
+
 uint32_t DCD::recordLen() {
   uint32_t n = 0;
   ifs_.read((char*)&n, 4);
@@ -478,6 +507,7 @@ uint32_t DCD::recordLen() {
 
 DCD::DCD(const std::string& path) : path_(path), ifs_(path.c_str(), std::ios::binary) {
   if (!ifs_) throw Error("Cannot open " + path);
+  pf_.open(path);
   uint32_t datum = 0;
   ifs_.read((char*)&datum, 4);
   if (ifs_.eof() || ifs_.fail()) throw Error("Unable to read first datum from DCD file " + path);
@@ -520,21 +550,29 @@ DCD::DCD(const std::string& path) : path_(path), ifs_(path.c_str(), std::ios::bi
 
 void DCD::readFramePlanes(uint32_t i, float* out) {  // src/dcd.cpp:329-371
   if (i >= nframes_) throw Error("Requested DCD frame is out of range");
-  ifs_.clear();
-  ifs_.seekg((std::streamoff)(first_frame_pos_ + (uint64_t)i * frame_size_));
+  std::vector<unsigned char>& raw = frameScratch(frame_size_);
+  pf_.readAt(first_frame_pos_ + (uint64_t)i * frame_size_, raw.data(), frame_size_, "Error reading data record from DCD");
+  const unsigned char* p = raw.data();
+  auto marker = [&]() {  // F77 record length word
+    uint32_t n;
+    memcpy(&n, p, 4);
+    p += 4;
+    return swab_ ? swab32(n) : n;
+  };
   if (hasCrystal()) {
-    if (recordLen() != 48) throw Error("Cannot read crystal parameters");
-    ifs_.seekg(48, std::ios::cur);
-    if (recordLen() != 48) throw Error("Mismatch in record length while reading from DCD");
+    if (marker() != 48) throw Error("Cannot read crystal parameters");
+    p += 48;
+    if (marker() != 48) throw Error("Mismatch in record length while reading from DCD");
   }
   for (int k = 0; k < 3; ++k) {
-    const uint32_t len = recordLen();
+    const uint32_t len = marker();
     if (len != 4 * natoms_) throw Error("Size of coords stored in frame does not match model size");
-    ifs_.read((char*)(out + (size_t)k * natoms_), len);
-    if (ifs_.fail()) throw Error("Error reading data record from DCD");
-    if (recordLen() != len) throw Error("Mismatch in record length while reading from DCD");
+    float* dst = out + (size_t)k * natoms_;
+    memcpy(dst, p, len);
+    p += len;
+    if (marker() != len) throw Error("Mismatch in record length while reading from DCD");
     if (swab_) {
-      uint32_t* w = (uint32_t*)(out + (size_t)k * natoms_);
+      uint32_t* w = (uint32_t*)dst;
       for (uint32_t a = 0; a < natoms_; ++a) w[a] = swab32(w[a]);
     }
   }
@@ -694,16 +732,15 @@ AmberNetcdf::AmberNetcdf(const std::string& path, uint32_t natoms_expected)
   }
   nframes_ = numrecs;  // length of the unlimited dimension "frame"
   if (dims[frame_dim].second != 0) nframes_ = dims[frame_dim].second;  // fixed-size frame dimension
-  raw_.resize(coord_vsize);
+  coord_vsize_ = coord_vsize;
+  pf_.open(path);
 }
 
 void AmberNetcdf::readFramePlanes(uint32_t i, float* out) {  // readRawFrame + updateGroupCoords, :108-150
   if (i >= nframes_) throw Error("Error- " + path_ + ": Cannot read Amber netcdf frame (coords)");
-  ifs_.clear();
-  ifs_.seekg((std::streamoff)(coord_begin_ + (uint64_t)i * rec_size_));
-  ifs_.read((char*)raw_.data(), (std::streamsize)raw_.size());
-  if (!ifs_) throw Error("Error- " + path_ + ": Cannot read Amber netcdf frame (coords)");
-  const unsigned char* p = raw_.data();
+  std::vector<unsigned char>& raw = frameScratch(coord_vsize_);
+  pf_.readAt(coord_begin_ + (uint64_t)i * rec_size_, raw.data(), coord_vsize_, "Error- " + path_ + ": Cannot read Amber netcdf frame (coords)");
+  const unsigned char* p = raw.data();
   const size_t n = natoms_;
   if (!coords_double_) {
     for (size_t k = 0; k < n; ++k)
@@ -755,18 +792,41 @@ struct XdrIn {  // big-endian 4-byte items
 struct BitIn {  // most-significant-bit-first reader over the compressed block
   const unsigned char* p;
   size_t n, pos = 0;  // pos in bits
-  uint32_t take(unsigned nbits) {  // nbits <= 32
-    uint32_t v = 0;
-    for (unsigned k = 0; k < nbits; ++k, ++pos) {
-      const size_t byte = pos >> 3;
-      const unsigned bit = byte < n ? (p[byte] >> (7 - (pos & 7))) & 1u : 0u;
-      v = (v << 1) | bit;
+  // the 64 bits that start at byte `byte`, first byte most significant; zeros past the end
+  uint64_t window(size_t byte) const {
+    if (byte + 8 <= n) {
+      uint64_t v;
+      memcpy(&v, p + byte, 8);
+      return __builtin_bswap64(v);
     }
+    uint64_t v = 0;
+    for (size_t k = 0; k < 8; ++k) v = (v << 8) | (byte + k < n ? p[byte + k] : 0u);
     return v;
   }
+  uint64_t take56(unsigned nbits) {  // 1 <= nbits <= 56: with the bit offset (<= 7) still inside one window
+    const uint64_t w = window(pos >> 3);
+    const uint64_t v = (w << (pos & 7)) >> (64 - nbits);
+    pos += nbits;
+    return v;
+  }
+  uint32_t take(unsigned nbits) { return nbits ? (uint32_t)take56(nbits) : 0u; }  // nbits <= 32
   // three values packed as one number in the mixed radix (sizes[1], sizes[2]), stored least significant
   // BYTE first, each byte most significant bit first (decodeints, src/xtc.cpp:132-158)
   void take3(unsigned nbits, const uint32_t sizes[3], int out[3]) {
+    if (nbits >= 1 && nbits <= 56) {  // the usual case: one window, 64-bit arithmetic
+      const uint64_t x = take56(nbits);  // bytes b0 b1 ... (b0 first) then the `rem` leftover bits, as one big-endian string
+      const unsigned nfull = nbits >> 3, rem = nbits & 7;
+      const uint64_t top = x & ((1ull << rem) - 1);  // the leftover bits are the most significant part
+      const uint64_t be = x >> rem;                  // nfull bytes, b0 most significant
+      uint64_t v = nfull ? __builtin_bswap64(be) >> (64 - 8 * nfull) : 0;  // b0 least significant
+      v |= top << (8 * nfull);
+      const uint64_t q2 = v / sizes[2];
+      out[2] = (int)(uint32_t)(v - q2 * sizes[2]);
+      const uint64_t q1 = q2 / sizes[1];
+      out[1] = (int)(uint32_t)(q2 - q1 * sizes[1]);
+      out[0] = (int)(uint32_t)q1;
+      return;
+    }
     unsigned __int128 v = 0;
     unsigned shift = 0;
     while (nbits > 8) { v |= (unsigned __int128)take(8) << shift; shift += 8; nbits -= 8; }
@@ -818,37 +878,61 @@ XTC::XTC(const std::string& path) : path_(path), ifs_(path.c_str(), std::ios::bi
   }
   ifs_.clear();
   if (frame_pos_.empty()) throw Error("Error- " + path + ": Unable to read in the first frame");
+  // one more entry: where the last frame ends (every frame is fetched whole with one positional read)
+  ifs_.seekg((std::streamoff)frame_pos_.back());
+  {
+    XdrIn y{ifs_, path_};
+    uint32_t nbytes = 0;
+    if (natoms_ <= 9) {
+      nbytes = natoms_ * 12;
+      frame_pos_.push_back(frame_pos_.back() + 14 * 4 + nbytes);
+    } else {
+      ifs_.seekg((13 + 9) * 4, std::ios::cur);
+      if (!y.u32(&nbytes)) throw Error("Error- " + path + ": Problem scanning XTC trajectory to build frame indices");
+      frame_pos_.push_back(frame_pos_.back() + (13 + 9 + 1) * 4 + (nbytes + 3) / 4 * 4);
+    }
+  }
+  ifs_.clear();
+  pf_.open(path);
 }
 
 void XTC::readFramePlanes(uint32_t fi, float* out) {
-  if (fi >= frame_pos_.size()) throw Error("Error- " + path_ + ": Requested XTC frame is out of range");
-  ifs_.clear();
-  ifs_.seekg((std::streamoff)(frame_pos_[fi] + 13 * 4));  // past magic, natoms, step, time, box
-  XdrIn x{ifs_, path_};
+  if (fi + 1 >= frame_pos_.size()) throw Error("Error- " + path_ + ": Requested XTC frame is out of range");
+  const size_t frame_bytes = (size_t)(frame_pos_[fi + 1] - frame_pos_[fi]);
+  std::vector<unsigned char>& raw = frameScratch(frame_bytes + 8);
+  pf_.readAt(frame_pos_[fi], raw.data(), frame_bytes, "Error- " + path_ + ": Problem reading XTC frame");
+  size_t off = 13 * 4;  // past magic, natoms, step, time, box
+  auto word = [&](uint32_t* v) {  // XDR: big-endian 32-bit words
+    if (off + 4 > frame_bytes) return false;
+    const unsigned char* b = raw.data() + off;
+    *v = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+    off += 4;
+    return true;
+  };
+  auto wordf = [&](float* f) { uint32_t u; if (!word(&u)) return false; memcpy(f, &u, 4); return true; };
+  auto wordi = [&](int* i) { uint32_t u; if (!word(&u)) return false; *i = (int)u; return true; };
   uint32_t lsize;
-  if (!x.u32(&lsize) || lsize != natoms_) throw Error("Error- " + path_ + ": Problem reading XTC frame");
+  if (!word(&lsize) || lsize != natoms_) throw Error("Error- " + path_ + ": Problem reading XTC frame");
   const size_t n = natoms_;
   if (lsize <= 9) {  // plain floats, nm
     for (size_t k = 0; k < n; ++k)
       for (int ax = 0; ax < 3; ++ax) {
         float v;
-        if (!x.f32(&v)) throw Error("Error- " + path_ + ": XTC Error: number of uncompressed coords read did not match number expected");
+        if (!wordf(&v)) throw Error("Error- " + path_ + ": XTC Error: number of uncompressed coords read did not match number expected");
         out[ax * n + k] = (float)((double)v * 10.0);
       }
     return;
   }
   float precision;
   int minint[3], maxint[3], smallidx;
-  bool ok = x.f32(&precision);
-  for (int k = 0; k < 3 && ok; ++k) ok = x.i32(&minint[k]);
-  for (int k = 0; k < 3 && ok; ++k) ok = x.i32(&maxint[k]);
+  bool ok = wordf(&precision);
+  for (int k = 0; k < 3 && ok; ++k) ok = wordi(&minint[k]);
+  for (int k = 0; k < 3 && ok; ++k) ok = wordi(&maxint[k]);
   uint32_t nbytes = 0;
-  ok = ok && x.i32(&smallidx) && x.u32(&nbytes);
-  if (!ok || smallidx < kXtcFirstIdx || smallidx >= (int)(sizeof(kXtcMagicInts) / sizeof(int)) || nbytes > (1u << 30))
+  ok = ok && wordi(&smallidx) && word(&nbytes);
+  if (!ok || smallidx < kXtcFirstIdx || smallidx >= (int)(sizeof(kXtcMagicInts) / sizeof(int)) || off + nbytes > frame_bytes)
     throw Error("Error- " + path_ + ": Problem reading XTC frame");
-  bits_.resize(nbytes);
-  ifs_.read((char*)bits_.data(), nbytes);
-  if (!ifs_) throw Error("Error- " + path_ + ": Problem reading XTC frame");
+  const unsigned char* bits = raw.data() + off;
 
   uint32_t sizeint[3], bitsizeint[3] = {0, 0, 0};
   for (int k = 0; k < 3; ++k) sizeint[k] = (uint32_t)(maxint[k] - minint[k] + 1);
@@ -867,7 +951,7 @@ void XTC::readFramePlanes(uint32_t fi, float* out) {
     if (atom >= n) throw Error("Error- " + path_ + ": corrupt XTC frame (more atoms than announced)");
     for (int ax = 0; ax < 3; ++ax) out[ax * n + atom] = (float)((double)((float)c[ax] * inv_precision) * 10.0);
   };
-  BitIn in{bits_.data(), bits_.size()};
+  BitIn in{bits, nbytes};
   size_t i = 0;
   int run = 0;
   while (i < n) {

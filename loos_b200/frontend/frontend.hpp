@@ -58,7 +58,26 @@ class Trajectory {
   virtual uint32_t natoms() const = 0;
   virtual uint32_t nframes() const = 0;
   virtual const std::string& filename() const = 0;
-  virtual void readFramePlanes(uint32_t i, float* out) = 0;  // out holds 3*natoms floats
+  // out holds 3*natoms floats.  Safe to call from several threads at once (frames are fetched with
+  // positional reads into per-thread scratch): the staging loop decodes a batch of frames in parallel.
+  virtual void readFramePlanes(uint32_t i, float* out) = 0;
+};
+
+// A file opened for positional reads (pread): no shared file position, no shared buffer.
+class PosFile {
+ public:
+  PosFile() {}
+  ~PosFile();
+  PosFile(const PosFile&) = delete;
+  PosFile& operator=(const PosFile&) = delete;
+  void open(const std::string& path);  // throws Error
+  uint64_t size() const { return size_; }
+  // exactly n bytes from offset `off`, or throws Error(what)
+  void readAt(uint64_t off, void* dst, size_t n, const std::string& what) const;
+
+ private:
+  int fd_ = -1;
+  uint64_t size_ = 0;
 };
 // createTrajectory (src/sfactories.cpp:133-148): by suffix -- dcd; nc / netcdf (Amber NetCDF);
 // crd / mdcrd when the file is NetCDF (the reference's text Amber format is not read here).
@@ -81,7 +100,8 @@ class DCD : public Trajectory {
  private:
   uint32_t recordLen();
   std::string path_;
-  std::ifstream ifs_;
+  std::ifstream ifs_;  // header only; frames go through pf_
+  PosFile pf_;
   bool swab_ = false;
   int icntrl_[20];
   float delta_ = 0;
@@ -108,11 +128,11 @@ class AmberNetcdf : public Trajectory {
 
  private:
   std::string path_;
-  std::ifstream ifs_;
+  std::ifstream ifs_;  // header only; frames go through pf_
+  PosFile pf_;
   uint32_t natoms_ = 0, nframes_ = 0;
   bool periodic_ = false, coords_double_ = false;
-  uint64_t coord_begin_ = 0, rec_size_ = 0;
-  std::vector<unsigned char> raw_;
+  uint64_t coord_begin_ = 0, rec_size_ = 0, coord_vsize_ = 0;
 };
 
 // ---- GROMACS XTC trajectories (src/xtc.cpp:165-486; format of the xdrfile library) ----
@@ -126,17 +146,16 @@ class XTC : public Trajectory {
  public:
   explicit XTC(const std::string& path);
   uint32_t natoms() const override { return natoms_; }
-  uint32_t nframes() const override { return (uint32_t)frame_pos_.size(); }
+  uint32_t nframes() const override { return (uint32_t)frame_pos_.size() - 1; }
   const std::string& filename() const override { return path_; }
   void readFramePlanes(uint32_t i, float* out) override;
 
  private:
   std::string path_;
-  std::ifstream ifs_;
+  std::ifstream ifs_;  // frame scan only; frames go through pf_
+  PosFile pf_;
   uint32_t natoms_ = 0;
-  std::vector<uint64_t> frame_pos_;
-  std::vector<unsigned char> bits_;
-  std::vector<int> ints_;
+  std::vector<uint64_t> frame_pos_;  // start of every frame, plus the end of the last one
 };
 
 // ---- MultiTrajectory indexing (src/MultiTraj.hpp:98-105, src/MultiTraj.cpp:48-58) ----

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <sstream>
+#include <thread>
 
 #include "frontend.hpp"
 
@@ -85,6 +86,26 @@ int lbfe_traj_info(const char* path, uint32_t natoms_expected, uint32_t* natoms,
 int lbfe_traj_read(const char* path, uint32_t natoms_expected, uint32_t frame, float* planes) {
   try { auto t = openTrajectory(path, natoms_expected); t->readFramePlanes(frame, planes); return 0; }
   catch (const std::exception& e) { return fail(e); }
+}
+
+// Frames frames[0..n) of one open trajectory decoded by `threads` threads at once (frame k by thread
+// k % threads) into out[k][3][natoms]: what the staging loop of the tools does with a batch.
+int lbfe_traj_read_many(const char* path, uint32_t natoms_expected, const uint32_t* frames, int n, int threads, float* out) {
+  try {
+    auto t = openTrajectory(path, natoms_expected);
+    const size_t stride = 3 * (size_t)t->natoms();
+    std::vector<std::thread> pool;
+    std::vector<std::string> errs((size_t)threads);
+    for (int w = 0; w < threads; ++w)
+      pool.emplace_back([&, w]() {
+        try {
+          for (int k = w; k < n; k += threads) t->readFramePlanes(frames[k], out + (size_t)k * stride);
+        } catch (const std::exception& e) { errs[(size_t)w] = e.what(); }
+      });
+    for (std::thread& th : pool) th.join();
+    for (const std::string& e : errs) if (!e.empty()) throw Error(e);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
 }
 
 // MultiTraj: sizes[] = frames in each sub-trajectory; returns composite count and the

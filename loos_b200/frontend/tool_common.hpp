@@ -5,7 +5,9 @@
 #include <cstdlib>
 #include <iostream>
 #include <memory>
+#include <exception>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/loosb200.h"
@@ -59,6 +61,12 @@ struct Frames {  // RAII around loosb200_frames
 // one or more staged sets; while batch k+1 is being decoded, batch k is on its way to
 // the GPU (pinned bounce buffer -> async H2D on a side stream -> gather kernel).
 // `read(j, dst)` must put frame j of the list (3 * natoms floats) at dst.
+// Reader threads for the staging loop (LOOSB200_READER_THREADS, default: the host's threads, at most 8).
+inline unsigned readerThreads() {
+  if (const char* env = getenv("LOOSB200_READER_THREADS")) return (unsigned)std::max(1, atoi(env));
+  return std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+}
+
 template <class ReadFrame>
 inline void stageStreaming(std::vector<Frames*> sets, const std::vector<const std::vector<uint32_t>*>& sels,
                            size_t F, size_t natoms, int device, ReadFrame read, std::vector<float>* keep = nullptr) {
@@ -68,9 +76,26 @@ inline void stageStreaming(std::vector<Frames*> sets, const std::vector<const st
   const size_t batch = std::max<size_t>(1, std::min<size_t>(F, (16u << 20) / (natoms * 12)));
   std::vector<float> buf(batch * 3 * natoms);
   if (keep) keep->resize(F * 3 * natoms);
+  const unsigned nthreads = readerThreads();
   for (size_t j0 = 0; j0 < F; j0 += batch) {
     const size_t nb = std::min(batch, F - j0);
-    for (size_t j = 0; j < nb; ++j) read(j0 + j, buf.data() + j * 3 * natoms);
+    // the frames of a batch are decoded by several threads (Trajectory::readFramePlanes is re-entrant):
+    // XTC decompression and NetCDF byte swapping are CPU work, and even DCD reads gain from parallel preads
+    const unsigned nt = (unsigned)std::min<size_t>(nthreads, nb);
+    if (nt <= 1) {
+      for (size_t j = 0; j < nb; ++j) read(j0 + j, buf.data() + j * 3 * natoms);
+    } else {
+      std::vector<std::thread> pool;
+      std::vector<std::exception_ptr> errs(nt);
+      for (unsigned t = 0; t < nt; ++t)
+        pool.emplace_back([&, t]() {
+          try {
+            for (size_t j = t; j < nb; j += nt) read(j0 + j, buf.data() + j * 3 * natoms);
+          } catch (...) { errs[t] = std::current_exception(); }
+        });
+      for (std::thread& th : pool) th.join();
+      for (const std::exception_ptr& e : errs) if (e) std::rethrow_exception(e);
+    }
     if (keep) std::copy(buf.begin(), buf.begin() + nb * 3 * natoms, keep->begin() + j0 * 3 * natoms);
     for (size_t k = 0; k < sets.size(); ++k) check(loosb200_stage_append(sets[k]->h, buf.data(), nb), "staging frames");
   }

@@ -483,3 +483,37 @@ def test_rmsds_align_command_line(system, tmp_path):
     if not torch.cuda.is_available():
         r = run("--range1", "0:1:4", system["pdb"], system["dcd"])
         assert r.returncode == 1 and "no usable sm_100" in r.stderr and r.stdout == ""
+
+
+@pytest.mark.parametrize("fmt", ["dcd", "dcd_swapped_crystal", "nc", "xtc"])
+def test_trajectory_reads_are_reentrant(fe, tmp_path, fmt):
+    """Trajectory::readFramePlanes from 6 threads at once (positional reads, per-thread scratch) gives the
+    frames a single thread reads, for every format: the tools decode a staging batch in parallel."""
+    from oracle import frontend_oracle as fo
+    from loos_b200.synth import write_dcd
+    rng = np.random.default_rng(8)
+    F, N = 57, 311
+    xyz = (rng.normal(0, 15, (1, N, 3)) + rng.normal(0, 1.0, (F, N, 3))).astype(np.float32)
+    path = str(tmp_path / ("t." + ("dcd" if fmt.startswith("dcd") else fmt)))
+    if fmt == "dcd":
+        write_dcd(path, xyz)
+    elif fmt == "dcd_swapped_crystal":
+        write_dcd(path, xyz, with_crystal=True, big_endian=True)
+    elif fmt == "nc":
+        _write_amber_nc(path, xyz)
+    else:
+        fo.write_xtc(path, xyz)
+    order = rng.permutation(np.arange(F).repeat(3)).astype(np.uint32)       # every frame three times, shuffled
+    many = np.zeros((len(order), 3, N), np.float32)
+    assert fe.lbfe_traj_read_many(path.encode(), N, order.ctypes.data_as(_u32p), len(order), 6,
+                                  many.ctypes.data_as(C.POINTER(C.c_float))) == 0, fe.lbfe_last_error()
+    one = np.zeros((3, N), np.float32)
+    for k in range(F):
+        assert fe.lbfe_traj_read(path.encode(), N, k, one.ctypes.data_as(C.POINTER(C.c_float))) == 0
+        for pos in np.nonzero(order == k)[0]:
+            assert np.array_equal(many[pos], one)
+        if fmt != "xtc":
+            assert np.array_equal(one, xyz[k].T)
+    # a frame beyond the end is an error from any thread
+    bad = np.array([0, 1, F, 2], dtype=np.uint32)
+    assert fe.lbfe_traj_read_many(path.encode(), N, bad.ctypes.data_as(_u32p), 4, 3, many.ctypes.data_as(C.POINTER(C.c_float))) == -1
