@@ -1122,9 +1122,10 @@ std::shared_ptr<Trajectory> openTrajectory(const std::string& path, uint32_t nat
   std::transform(suffix.begin(), suffix.end(), suffix.begin(), ::tolower);
   if (suffix == "dcd") return std::make_shared<DCD>(path);
   if (suffix == "xtc") return std::make_shared<XTC>(path);
+  if (suffix == "h5") return std::make_shared<MDTrajH5>(path, natoms);
   if (suffix == "nc" || suffix == "netcdf") return std::make_shared<AmberNetcdf>(path, natoms);
   if ((suffix == "crd" || suffix == "mdcrd") && AmberNetcdf::isNetcdf(path)) return std::make_shared<AmberNetcdf>(path, natoms);
-  throw Error("Error- unknown or unsupported trajectory format for '" + path + "' (supported here: dcd, xtc, nc/netcdf)");
+  throw Error("Error- unknown or unsupported trajectory format for '" + path + "' (supported here: dcd, xtc, nc/netcdf, h5)");
 }
 
 uint32_t MultiTraj::nframes(size_t i) const {

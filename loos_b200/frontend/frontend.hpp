@@ -158,6 +158,28 @@ class XTC : public Trajectory {
   std::vector<uint64_t> frame_pos_;  // start of every frame, plus the end of the last one
 };
 
+// ---- MDTraj HDF5 trajectories (src/mdtrajtraj.cpp:32-142) ----
+// Root-level dataset "coordinates" (frames x atoms x 3 floats, nm -> x 10.0), optional "cell_lengths".
+// The reference links libhdf5; here the subset of the HDF5 file format that PyTables / MDTraj / h5py
+// write for such files is parsed directly (hdf5_mini.cpp lists it).  Parity unpinned -- see there.
+class MDTrajH5 : public Trajectory {
+ public:
+  MDTrajH5(const std::string& path, uint32_t natoms_expected);
+  ~MDTrajH5() override;
+  uint32_t natoms() const override { return natoms_; }
+  uint32_t nframes() const override { return nframes_; }
+  const std::string& filename() const override { return path_; }
+  bool hasPeriodicBox() const { return periodic_; }
+  void readFramePlanes(uint32_t i, float* out) override;
+
+ private:
+  struct Impl;
+  std::string path_;
+  std::unique_ptr<Impl> impl_;
+  uint32_t natoms_ = 0, nframes_ = 0;
+  bool periodic_ = false;
+};
+
 // ---- MultiTrajectory indexing (src/MultiTraj.hpp:98-105, src/MultiTraj.cpp:48-58) ----
 struct MultiTraj {
   std::vector<std::shared_ptr<Trajectory>> trajs;

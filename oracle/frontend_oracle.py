@@ -558,3 +558,222 @@ def read_xtc(path):
         fl = (ints.astype(np.float32) * inv).astype(np.float32)
         frames.append((fl.astype(np.float64) * 10.0).astype(np.float32))
     return np.stack(frames)
+
+
+# ---------------------------------------------------------------------------------------------
+# MDTraj HDF5 (test infrastructure).  The reference reads such files through libhdf5
+# (src/mdtrajtraj.cpp:32-142); neither libhdf5 nor h5py / PyTables exists in this image, so the test
+# files for the native parser (loos_b200/frontend/hdf5_mini.cpp) are written here, byte by byte, from
+# the published HDF5 file format specification (version 3.0): parity with files MDTraj itself writes is
+# UNPINNED.  Two styles: "v1" = what the HDF5 1.8 defaults (PyTables, MDTraj) produce -- superblock 0,
+# version-1 object headers, the root group as a symbol table (B-tree v1, local heap, SNOD), chunked
+# datasets indexed by a B-tree v1, shuffle + deflate; "v2" = the libver='latest' forms -- superblock 2,
+# version-2 object headers with link messages, contiguous or single-chunk layout version 4.
+
+def write_mdtraj_h5(path, frames_angstrom, style="v1", chunk=(4, 100, 3), compress=True, shuffle=True, fletcher=False,
+                    dtype="<f4", box=True, extra_filter=None, coords_name="coordinates", node_fanout=4, userblock=0):
+    import struct
+    import zlib
+    X = (np.asarray(frames_angstrom, dtype=np.float64) / 10.0).astype(dtype)       # nanometres
+    F, N, _ = X.shape
+    es = X.dtype.itemsize
+    UNDEF = 0xffffffffffffffff
+    buf = bytearray(b"\0" * (2048 if style == "v1" else 1024))                      # superblock area, patched at the end
+
+    def put(data, align=8):
+        while len(buf) % align:
+            buf.append(0)
+        a = len(buf)
+        buf.extend(data)
+        return a
+
+    def datatype_msg(dt):
+        dt = np.dtype(dt)
+        big = dt.byteorder == ">"
+        if dt.itemsize == 4:
+            prop = struct.pack("<HHBBBBI", 0, 32, 23, 8, 0, 23, 127); sign = 31
+        else:
+            prop = struct.pack("<HHBBBBI", 0, 64, 52, 11, 0, 52, 1023); sign = 63
+        return struct.pack("<BBBBI", 0x11, (1 if big else 0) | 0x20, sign, 0, dt.itemsize) + prop
+
+    def dataspace_msg(dims, version, maxdims=None):
+        if version == 1:
+            m = struct.pack("<BBBB4x", 1, len(dims), 1 if maxdims else 0, 0)
+        else:
+            m = struct.pack("<BBBB", 2, len(dims), 1 if maxdims else 0, 1)
+        m += b"".join(struct.pack("<Q", d) for d in dims)
+        if maxdims:
+            m += b"".join(struct.pack("<Q", d) for d in maxdims)
+        return m
+
+    def filter_msg(filters, version):
+        m = struct.pack("<BB6x", 1, len(filters)) if version == 1 else struct.pack("<BB", 2, len(filters))
+        for fid, cd in filters:
+            name = {1: b"deflate\0", 2: b"shuffle\0", 3: b"fletcher32\0"}.get(fid, b"custom\0")
+            if version == 1:
+                name = name + b"\0" * ((-len(name)) % 8)
+                m += struct.pack("<HHHH", fid, len(name), 1, len(cd)) + name + b"".join(struct.pack("<I", c) for c in cd)
+                if len(cd) & 1:
+                    m += b"\0\0\0\0"
+            else:
+                if fid >= 256:
+                    m += struct.pack("<HHHH", fid, len(name), 1, len(cd)) + name
+                else:
+                    m += struct.pack("<HHH", fid, 1, len(cd))
+                m += b"".join(struct.pack("<I", c) for c in cd)
+        return m
+
+    def object_header_v1(msgs, split_after=None):
+        """msgs: [(type, data)].  With split_after = k the messages after the k-th live in a continuation block."""
+        def enc(ms):
+            out = b""
+            for t, d in ms:
+                d = d + b"\0" * ((-len(d)) % 8)
+                out += struct.pack("<HHB3x", t, len(d), 0) + d
+            return out
+        if split_after is None:
+            body = enc(msgs)
+            return put(struct.pack("<BBHII4x", 1, 0, len(msgs), 1, len(body)) + body)
+        tail = enc(msgs[split_after:])
+        caddr = put(tail)
+        head = msgs[:split_after] + [(0x0000, b"\0" * 8), (0x0010, struct.pack("<QQ", caddr, len(tail)))]
+        body = enc(head)
+        return put(struct.pack("<BBHII4x", 1, 0, len(head) + len(msgs) - split_after, 1, len(body)) + body)
+
+    def object_header_v2(msgs, split_after=None):
+        def enc(ms):
+            return b"".join(struct.pack("<BHB", t, len(d), 0) + d for t, d in ms)
+        if split_after is not None:
+            tail = enc(msgs[split_after:])
+            block = b"OCHK" + tail + b"\0\0\0\0"                                    # checksum not verified by the reader
+            caddr = put(block)
+            msgs = msgs[:split_after] + [(0x10, struct.pack("<QQ", caddr, len(block)))]
+        body = enc(msgs) + b"\0\0"                                                  # a gap smaller than a message header
+        return put(b"OHDR" + struct.pack("<BBH", 2, 0x01, len(body)) + body + b"\0\0\0\0")
+
+    def make_dataset(A, chunkshape, filters, layout_version, header_version):
+        """Returns the object header address of a dataset holding array A."""
+        A = np.ascontiguousarray(A)
+        rank = A.ndim
+        msgs_space = dataspace_msg(A.shape, 1 if header_version == 1 else 2,
+                                   maxdims=[UNDEF] + list(A.shape[1:]) if chunkshape else None)
+        msgs = [(0x01, msgs_space), (0x03, datatype_msg(A.dtype))]
+        if chunkshape is None:
+            daddr = put(A.tobytes()) if A.size else UNDEF
+            if layout_version == 3:
+                lay = struct.pack("<BBQQ", 3, 1, daddr, A.nbytes)
+            else:
+                lay = struct.pack("<BBQQ", 4, 1, daddr, A.nbytes)
+            msgs.append((0x08, lay))
+        else:
+            cs = tuple(chunkshape)
+            def filt(raw):
+                mask = 0
+                for k, (fid, cd) in enumerate(filters):
+                    if fid == 2:
+                        a = np.frombuffer(raw, dtype=np.uint8)
+                        n = len(a) // A.itemsize
+                        raw = a[:n * A.itemsize].reshape(n, A.itemsize).T.tobytes() + bytes(a[n * A.itemsize:])
+                    elif fid == 1:
+                        raw = zlib.compress(raw, cd[0] if cd else 6)
+                    elif fid == 3:
+                        raw = raw + b"\x12\x34\x56\x78"
+                return raw, mask
+            entries = []
+            grid = [range(0, max(A.shape[d], 1), cs[d]) for d in range(rank)]
+            import itertools
+            for corner in itertools.product(*grid):
+                block = np.zeros(cs, dtype=A.dtype)                                  # edge chunks are stored whole
+                sl = tuple(slice(c, min(c + s, dim)) for c, s, dim in zip(corner, cs, A.shape))
+                sub = A[sl]
+                block[tuple(slice(0, n) for n in sub.shape)] = sub
+                if A.shape[0] == 0:
+                    continue
+                data, mask = filt(block.tobytes())
+                entries.append((corner, put(data), len(data), mask))
+            if layout_version == 4:                                                   # single chunk (index type 1)
+                assert len(entries) == 1
+                corner, addr, size, mask = entries[0]
+                lay = struct.pack("<BBBBB", 4, 2, 0x02 if filters else 0, rank + 1, 4)
+                lay += b"".join(struct.pack("<I", c) for c in cs) + struct.pack("<I", A.itemsize) + struct.pack("<B", 1)
+                if filters:
+                    lay += struct.pack("<QI", size, mask)
+                lay += struct.pack("<Q", addr)
+                msgs.append((0x08, lay))
+            else:
+                def key(corner, size, mask):
+                    return struct.pack("<II", size, mask) + b"".join(struct.pack("<Q", c) for c in corner) + struct.pack("<Q", 0)
+                level, nodes = 0, [(e[0], e[1], e[2], e[3]) for e in entries]         # (corner, child, size, mask)
+                root = UNDEF
+                while nodes:
+                    parents = []
+                    for g in range(0, len(nodes), node_fanout):
+                        grp = nodes[g:g + node_fanout]
+                        body = b"".join(key(c, s, m) + struct.pack("<Q", child) for c, child, s, m in grp)
+                        last = tuple(c + s for c, s in zip(grp[-1][0], cs))
+                        body += key(last, 0, 0)
+                        node = put(b"TREE" + struct.pack("<BBHQQ", 1, level, len(grp), UNDEF, UNDEF) + body)
+                        parents.append((grp[0][0], node, 0, 0))
+                    if len(parents) == 1:
+                        root = parents[0][1]
+                        break
+                    nodes, level = parents, level + 1
+                lay = struct.pack("<BBBQ", 3, 2, rank + 1, root) + b"".join(struct.pack("<I", c) for c in cs) + struct.pack("<I", A.itemsize)
+                msgs.append((0x08, lay))
+            if filters:
+                msgs.append((0x0b, filter_msg(filters, 1 if header_version == 1 else 2)))
+        if header_version == 1:
+            return object_header_v1(msgs, split_after=2)       # layout (and filters) behind a continuation message
+        return object_header_v2(msgs, split_after=3 if len(msgs) > 3 else None)
+
+    filters = []
+    if shuffle:
+        filters.append((2, [es]))
+    if compress:
+        filters.append((1, [1]))
+    if fletcher:
+        filters.append((3, []))
+    if extra_filter:
+        filters.append((extra_filter, [0, 0]))
+    members = {}
+    hv = 1 if style == "v1" else 2
+    if style == "v1":
+        members[coords_name] = make_dataset(X, chunk, filters, 3, 1)
+    elif chunk is None:
+        members[coords_name] = make_dataset(X, None, [], 4, 2)
+    else:
+        members[coords_name] = make_dataset(X, (max(F, 1), N, 3), filters, 4, 2)   # one chunk holds everything
+    members["time"] = make_dataset(np.arange(F, dtype="<f4"), None, [], 3, hv)
+    if box:
+        members["cell_lengths"] = make_dataset(np.tile(np.array([5, 6, 7], dtype="<f4"), (F, 1)), None, [], 3, hv)
+
+    names = sorted(members)
+    if style == "v1":
+        heap = bytearray(b"\0" * 8)
+        offs = {}
+        for nm in names:
+            offs[nm] = len(heap)
+            heap += nm.encode() + b"\0"
+            heap += b"\0" * ((-len(heap)) % 8)
+        seg = put(bytes(heap))
+        heap_addr = put(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), UNDEF, seg))
+        snods = []
+        for g in range(0, len(names), 2):                                             # two symbols per node: several SNODs
+            grp = names[g:g + 2]
+            ents = b"".join(struct.pack("<QQII16x", offs[nm], members[nm], 0, 0) for nm in grp)
+            snods.append((offs[grp[-1]], put(b"SNOD" + struct.pack("<BBH", 1, 0, len(grp)) + ents)))
+        body = struct.pack("<Q", 0) + b"".join(struct.pack("<Q", a) + struct.pack("<Q", k) for k, a in snods)
+        btree = put(b"TREE" + struct.pack("<BBHQQ", 0, 0, len(snods), UNDEF, UNDEF) + body)
+        root = object_header_v1([(0x11, struct.pack("<QQ", btree, heap_addr))])
+        sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, 4, 16, 0)
+        sb += struct.pack("<QQQQ", userblock, UNDEF, len(buf), UNDEF)
+        sb += struct.pack("<QQII", 0, root, 1, 0) + struct.pack("<QQ", btree, heap_addr)
+    else:
+        links = [(0x02, struct.pack("<BBQQ", 0, 0, UNDEF, UNDEF))]                    # link info: no fractal heap
+        for nm in names:
+            links.append((0x06, struct.pack("<BBB", 1, 0x00, len(nm)) + nm.encode() + struct.pack("<Q", members[nm])))
+        root = object_header_v2(links)
+        sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBB", 2, 8, 8, 0) + struct.pack("<QQQQ", userblock, UNDEF, len(buf), root) + b"\0\0\0\0"
+    buf[0:len(sb)] = sb
+    with open(path, "wb") as f:
+        f.write(b"\0" * userblock + bytes(buf))

@@ -485,7 +485,7 @@ def test_rmsds_align_command_line(system, tmp_path):
         assert r.returncode == 1 and "no usable sm_100" in r.stderr and r.stdout == ""
 
 
-@pytest.mark.parametrize("fmt", ["dcd", "dcd_swapped_crystal", "nc", "xtc"])
+@pytest.mark.parametrize("fmt", ["dcd", "dcd_swapped_crystal", "nc", "xtc", "h5"])
 def test_trajectory_reads_are_reentrant(fe, tmp_path, fmt):
     """Trajectory::readFramePlanes from 6 threads at once (positional reads, per-thread scratch) gives the
     frames a single thread reads, for every format: the tools decode a staging batch in parallel."""
@@ -501,6 +501,8 @@ def test_trajectory_reads_are_reentrant(fe, tmp_path, fmt):
         write_dcd(path, xyz, with_crystal=True, big_endian=True)
     elif fmt == "nc":
         _write_amber_nc(path, xyz)
+    elif fmt == "h5":
+        fo.write_mdtraj_h5(path, xyz, chunk=(5, 100, 3))
     else:
         fo.write_xtc(path, xyz)
     order = rng.permutation(np.arange(F).repeat(3)).astype(np.uint32)       # every frame three times, shuffled
@@ -512,8 +514,73 @@ def test_trajectory_reads_are_reentrant(fe, tmp_path, fmt):
         assert fe.lbfe_traj_read(path.encode(), N, k, one.ctypes.data_as(C.POINTER(C.c_float))) == 0
         for pos in np.nonzero(order == k)[0]:
             assert np.array_equal(many[pos], one)
-        if fmt != "xtc":
+        if fmt not in ("xtc", "h5"):
             assert np.array_equal(one, xyz[k].T)
     # a frame beyond the end is an error from any thread
     bad = np.array([0, 1, F, 2], dtype=np.uint32)
     assert fe.lbfe_traj_read_many(path.encode(), N, bad.ctypes.data_as(_u32p), 4, 3, many.ctypes.data_as(C.POINTER(C.c_float))) == -1
+
+
+# ------------------------------------------------------------------ MDTraj HDF5 reader (src/mdtrajtraj.cpp)
+H5_CASES = {
+    "pytables_like": dict(style="v1"),                                        # chunked, shuffle + deflate, B-tree v1, symbol-table group
+    "chunks_split_atoms_and_axes": dict(style="v1", chunk=(3, 50, 2), fletcher=True),
+    "uncompressed_chunks": dict(style="v1", compress=False, shuffle=False, chunk=(7, 400, 3)),
+    "deep_chunk_btree": dict(style="v1", chunk=(1, 16, 3), node_fanout=3),
+    "big_endian_double": dict(style="v1", dtype=">f8"),
+    "user_block": dict(style="v1", userblock=1024),
+    "latest_contiguous": dict(style="v2", chunk=None),
+    "latest_single_chunk": dict(style="v2"),
+    "no_box": dict(style="v1", box=False),
+}
+
+
+@pytest.mark.parametrize("case", sorted(H5_CASES))
+def test_mdtraj_h5_reader(fe, tmp_path, case):
+    """Frames of an MDTraj-style HDF5 file as the reference produces them: 10.0 * (the stored nm value) per
+    coordinate (src/mdtrajtraj.cpp:118-123), here rounded to the float32 planes every format is staged as.
+    The files come from the tests' own restatement of the HDF5 format (oracle/frontend_oracle.py): parity with
+    files written by MDTraj itself is unpinned -- no HDF5 library exists in this image."""
+    from oracle import frontend_oracle as fo
+    rng = np.random.default_rng(31)
+    F, N = 13, 257
+    xyz = rng.normal(0, 25, (F, N, 3)).astype(np.float32)
+    kw = H5_CASES[case]
+    path = str(tmp_path / "t.h5")
+    fo.write_mdtraj_h5(path, xyz, **kw)
+    stored = (xyz.astype(np.float64) / 10.0).astype(kw.get("dtype", "<f4"))      # what the file holds, nm
+    want = (10.0 * stored.astype(np.float64)).astype(np.float32)
+    na, nf = C.c_uint32(), C.c_uint32()
+    assert fe.lbfe_traj_info(path.encode(), N, C.byref(na), C.byref(nf)) == 0, fe.lbfe_last_error()
+    assert (na.value, nf.value) == (N, F)
+    buf = np.zeros((3, N), np.float32)
+    for k in list(range(F)) + [4, 0]:
+        assert fe.lbfe_traj_read(path.encode(), N, k, buf.ctypes.data_as(C.POINTER(C.c_float))) == 0, fe.lbfe_last_error()
+        assert np.array_equal(buf, want[k].T), (case, k)
+    assert fe.lbfe_traj_read(path.encode(), N, F, buf.ctypes.data_as(C.POINTER(C.c_float))) == -1
+
+
+def test_mdtraj_h5_validation(fe, tmp_path):
+    """The checks of MDTrajTraj::init (src/mdtrajtraj.cpp:52-72) and what this reader refuses to guess at."""
+    from oracle import frontend_oracle as fo
+    xyz = np.random.default_rng(2).normal(0, 10, (4, 20, 3)).astype(np.float32)
+    na, nf = C.c_uint32(), C.c_uint32()
+
+    def err(path, natoms=20):
+        assert fe.lbfe_traj_info(path.encode(), natoms, C.byref(na), C.byref(nf)) == -1
+        return fe.lbfe_last_error().decode()
+
+    p = str(tmp_path / "a.h5"); fo.write_mdtraj_h5(p, xyz, coords_name="positions")
+    assert "No coordinates dataset found in HDF5" in err(p)
+    p = str(tmp_path / "b.h5"); fo.write_mdtraj_h5(p, xyz)
+    assert "Number of atoms in HDF5 does not match the AtomicGroup" in err(p, natoms=21)
+    p = str(tmp_path / "c.h5"); fo.write_mdtraj_h5(p, xyz, extra_filter=32001)
+    assert "filter 32001 (blosc)" in err(p)
+    p = str(tmp_path / "d.h5"); open(p, "wb").write(b"CDF\x01" + b"\0" * 600)
+    assert "not an HDF5 file" in err(p)
+    p = str(tmp_path / "e.h5"); fo.write_mdtraj_h5(p, xyz)
+    raw = open(p, "rb").read()
+    open(p, "wb").write(raw[:len(raw) // 2])                                    # cut in half: addresses point past the end
+    assert "truncated or corrupt HDF5 file" in err(p)
+    p = str(tmp_path / "f.h5"); fo.write_mdtraj_h5(p, xyz[:0])                  # no frames yet: opens, zero frames
+    assert fe.lbfe_traj_info(p.encode(), 20, C.byref(na), C.byref(nf)) == 0 and nf.value == 0

@@ -225,6 +225,23 @@ def test_xtc_trajectory_gives_the_same_matrix_as_its_decoded_frames(files, tmp_p
     assert body(a) == body(b)
 
 
+def test_mdtraj_h5_trajectory_gives_the_same_matrix_as_its_decoded_frames(files, tmp_path):
+    """An MDTraj-style HDF5 file (chunked, shuffle + deflate; written by the tests' restatement of the format) and
+    a DCD holding 10.0 * its stored nm values: rmsds and multi-rmsds (mixed formats) print the same numbers."""
+    d, xyz = files["d"], files["xyz"]
+    fo.write_mdtraj_h5(str(tmp_path / "all.h5"), xyz, chunk=(8, 500, 3))
+    decoded = (10.0 * (xyz.astype(np.float64) / 10.0).astype(np.float32).astype(np.float64)).astype(np.float32)
+    write_dcd(str(tmp_path / "decoded.dcd"), decoded)
+    body = lambda out: "\n".join(l for l in out.splitlines() if not (l.startswith("# ") and "[loos-b200" in l))
+    a, _ = run("rmsds", "-p", "6", d / "model.pdb", tmp_path / "decoded.dcd")
+    b, _ = run("rmsds", "-p", "6", d / "model.pdb", tmp_path / "all.h5")
+    assert body(a) == body(b)
+    strip = lambda out: "\n".join(l for l in body(out).splitlines() if not l.startswith("# "))
+    a, _ = run("multi-rmsds", "-p", "5", d / "model.pdb", tmp_path / "decoded.dcd", d / "b.dcd")
+    b, _ = run("multi-rmsds", "-p", "5", d / "model.pdb", tmp_path / "all.h5", d / "b.dcd")
+    assert strip(a) == strip(b)
+
+
 def test_binary_side_channel(files, tmp_path):
     """--binary writes the float32 matrix as .npy (fortran order): identical to the values behind the
     text at -p 9, also with --noout 1, for the self and the cross matrix."""
