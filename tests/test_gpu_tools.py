@@ -18,6 +18,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "loos_b200", "bin")
 
 
+@pytest.fixture(scope="module", autouse=True)
+def tools_built():
+    """The tools are build products (git-ignored): build them if this checkout has none yet."""
+    names = ["rmsds", "multi-rmsds", "rmsd2ref", "rms-overlap", "rmsds-align"]
+    if not all(os.path.exists(os.path.join(BIN, n)) for n in names):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "loos_b200", "frontend")], check=True, stdout=subprocess.DEVNULL)
+
+
 @pytest.fixture(scope="module")
 def files(tmp_path_factory):
     d = tmp_path_factory.mktemp("tools")
