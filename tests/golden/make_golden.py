@@ -61,8 +61,27 @@ def main():
     np.savez_compressed(os.path.join(HERE, "rmsd2ref_small.npz"), Z=Z.astype(np.float32), sel_a=sel_a,
                         sel_r=sel_r, rmsd=d, xforms=xf, it_rmsd=it[0], it_xforms=it[1], it_avg=it[2],
                         it_iters=np.array(it[3]), it_rms=np.array(it[4]))
+    align_golden(R)
     print("golden fixtures written to", HERE)
 
 
+def align_golden(R):
+    """(4) rmsds-align: the script's loop (Packages/Clustering/rmsds-align.py:236-256) on the reference's kabsch,
+    two trajectories, align selection != rmsd selection, plus the text the script prints at precision 3."""
+    from oracle.oracle import py_round_text, rmsds_align
+    F1, F2, N = 14, 9, 70
+    X = synth_frames(F1, N, seed=SEED0 + 106)
+    Y = synth_frames(F2, N, seed=SEED0 + 107)
+    sel_a = np.arange(0, 40, 2)
+    sel_r = np.arange(25, N)
+    M = rmsds_align(R, X[:, sel_a], X[:, sel_r], Y[:, sel_a], Y[:, sel_r])
+    M1 = rmsds_align(R, X[:, sel_a], X[:, sel_r], X[:, sel_a], X[:, sel_r])
+    np.savez_compressed(os.path.join(HERE, "rmsds_align_small.npz"), X=X, Y=Y, sel_a=sel_a, sel_r=sel_r, M=M, M_self=M1,
+                        text_p3=np.array(py_round_text(M, 3)))
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-align" in sys.argv:
+        align_golden(Checker("reference"))
+    else:
+        main()

@@ -99,3 +99,17 @@ def test_errors(lb):
             lb.rmsds_align(a10, a10, a10, a12)          # rmsd selections differ in size
         with pytest.raises(lb.LoosB200Error):
             lb.rmsds_align(a10, short, a10, a10)        # align / rmsd sets of one trajectory differ in frames
+
+
+def test_golden(lb):
+    """Against the committed fixture made with the reference's own kabsch (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rmsds_align_small.npz"))
+    X, Y = g["X"], g["Y"]
+    sa, sr = g["sel_a"].astype(np.uint32), g["sel_r"].astype(np.uint32)
+    with lb.FrameSet(X, sel=sa) as a1, lb.FrameSet(X, sel=sr) as r1, lb.FrameSet(Y, sel=sa) as a2, lb.FrameSet(Y, sel=sr) as r2:
+        M = lb.rmsds_align(a1, r1, a2, r2)
+        M1 = lb.rmsds_align(a1, r1)
+    assert np.abs(M - g["M"]).max() < TIGHT
+    off = ~np.eye(len(X), dtype=bool)
+    assert np.abs(M1 - g["M_self"])[off].max() < TIGHT
+    assert np.abs(np.diag(M1)).max() < 1e-5

@@ -84,3 +84,15 @@ def test_matrix_text_format():
     g = np.load(os.path.join(G, "rmsds_small.npz"))
     assert str(g["text_p2"]) == matrix_text(g["M"], 2)
     assert str(g["text_p8"]).splitlines()[0] == "# 53 53 (0)"
+
+
+def test_rmsds_align_restatement_matches_golden(port):
+    """oracle.rmsds_align on the C restatement's kabsch against the fixture made with the reference's kabsch
+    (tests/golden/make_golden.py::align_golden), and the Python float text of the script."""
+    from oracle.oracle import py_round_text, rmsds_align
+    g = np.load(os.path.join(G, "rmsds_align_small.npz"))
+    X, Y, sa, sr = g["X"], g["Y"], g["sel_a"], g["sel_r"]
+    M = rmsds_align(port, X[:, sa], X[:, sr], Y[:, sa], Y[:, sr])
+    assert np.abs(M - g["M"]).max() < 1e-9
+    assert py_round_text(g["M"], 3) == str(g["text_p3"])
+    assert py_round_text(M, 3) == str(g["text_p3"])
