@@ -1,7 +1,13 @@
 """TEST INFRASTRUCTURE ONLY: Python restatement of the reference's integer/text
 front-end semantics (selection language, PDB fields, hybrid-36, frame ranges,
 MultiTrajectory indexing, DCD layout), used to check loos_b200/frontend bit-exactly.
-Each function cites the reference code it follows (paths under /root/reference)."""
+Each function cites the reference code it follows (paths under /root/reference).
+
+Parity status.  PDB / selection / ranges / DCD: restated from the reference's sources, which cannot be
+built here (Boost, bison/flex); the native front-end and this file are two independent readings that the
+tests hold to bit-equality.  XTC (write_xtc / read_xtc, restating src/xtcwriter.cpp and src/xtc.cpp) and
+MDTraj HDF5 (write_mdtraj_h5, written from the HDF5 file format specification): PARITY UNPINNED -- no file
+written by GROMACS or MDTraj, and no other implementation of either format, exists in this image."""
 import re
 import struct
 
