@@ -935,7 +935,10 @@ void XTC::readFramePlanes(uint32_t fi, float* out) {
   const unsigned char* bits = raw.data() + off;
 
   uint32_t sizeint[3], bitsizeint[3] = {0, 0, 0};
-  for (int k = 0; k < 3; ++k) sizeint[k] = (uint32_t)(maxint[k] - minint[k] + 1);
+  for (int k = 0; k < 3; ++k) {  // unsigned arithmetic: a corrupt header must not overflow (or divide by zero below)
+    sizeint[k] = (uint32_t)maxint[k] - (uint32_t)minint[k] + 1u;
+    if (sizeint[k] == 0 || maxint[k] < minint[k]) throw Error("Error- " + path_ + ": corrupt XTC frame (bounding box)");
+  }
   unsigned bitsize;
   if ((sizeint[0] | sizeint[1] | sizeint[2]) > 0xffffffu) {  // too large to pack as one number: separate fields
     for (int k = 0; k < 3; ++k) bitsizeint[k] = bitLength(sizeint[k]);
@@ -958,7 +961,7 @@ void XTC::readFramePlanes(uint32_t fi, float* out) {
     int cur[3], prev[3];
     if (bitsize == 0) for (int k = 0; k < 3; ++k) cur[k] = (int)in.take(bitsizeint[k]);
     else in.take3(bitsize, sizeint, cur);
-    for (int k = 0; k < 3; ++k) { cur[k] += minint[k]; prev[k] = cur[k]; }
+    for (int k = 0; k < 3; ++k) { cur[k] = (int)((uint32_t)cur[k] + (uint32_t)minint[k]); prev[k] = cur[k]; }
     int is_smaller = 0;
     if (in.take(1)) {  // the run length (and the change of the small range) is stated anew
       run = (int)in.take(5);
@@ -970,7 +973,7 @@ void XTC::readFramePlanes(uint32_t fi, float* out) {
       for (int k = 0; k < run; k += 3) {
         int d[3];
         in.take3((unsigned)smallidx, sizesmall, d);
-        for (int q = 0; q < 3; ++q) d[q] += prev[q] - smallnum;
+        for (int q = 0; q < 3; ++q) d[q] = (int)((uint32_t)d[q] + (uint32_t)prev[q] - (uint32_t)smallnum);
         if (k == 0) {  // the writer stored the second atom of the run first (water: O after H): swap back
           emit(i, d);
           emit(i + 1, cur);

@@ -60,9 +60,10 @@ struct MDTrajH5::Impl {
   [[noreturn]] void bad(const std::string& what) const { throw Error("Error- " + path + ": " + what); }
 
   std::vector<unsigned char> get(uint64_t off, size_t n) const {
-    if (off == kUndef || off + base + n > pf.size()) bad("truncated or corrupt HDF5 file");
+    const uint64_t start = off + base;  // sizes and addresses come from the file: check before allocating
+    if (off == kUndef || start < off || n > pf.size() || start > pf.size() - n) bad("truncated or corrupt HDF5 file");
     std::vector<unsigned char> b(n);
-    pf.readAt(off + base, b.data(), n, "Error- " + path + ": cannot read HDF5 file");
+    pf.readAt(start, b.data(), n, "Error- " + path + ": cannot read HDF5 file");
     return b;
   }
   static uint64_t le(const unsigned char* p, unsigned n) {
@@ -312,7 +313,12 @@ struct MDTrajH5::Impl {
     });
     if (ds.layout == 2) {
       if (layout_ndims != (unsigned)ds.rank + 1) bad(std::string("dataset ") + name + ": chunk rank does not match the dataspace");
-      for (int k = 0; k < ds.rank; ++k) if (ds.chunk[k] == 0) bad("corrupt HDF5 layout message");
+      uint64_t chunk_bytes = ds.elem_size;
+      for (int k = 0; k < ds.rank; ++k) {
+        if (ds.chunk[k] == 0) bad("corrupt HDF5 layout message");
+        chunk_bytes *= ds.chunk[k];
+        if (chunk_bytes > (1ull << 30)) bad(std::string("dataset ") + name + ": implausible chunk size (more than 1 GiB)");
+      }
       if (single_chunk) {
         uint64_t raw = ds.elem_size;
         for (int k = 0; k < ds.rank; ++k) raw *= ds.chunk[k];
@@ -439,6 +445,7 @@ MDTrajH5::MDTrajH5(const std::string& path, uint32_t natoms_expected) : path_(pa
   const H5Dataset& c = f.coords;
   if (c.rank != 3 || c.dims[2] != 3) f.bad("the coordinates dataset of an MDTraj HDF5 file must be frames x atoms x 3");
   if (c.type_class != 1 || (c.elem_size != 4 && c.elem_size != 8)) f.bad("the coordinates dataset is not IEEE float32 / float64");
+  if (c.layout < 0 || c.layout > 2) f.bad("the coordinates dataset has no data layout this reader knows");
   if (periodic_ && box.rank >= 1 && box.dims[0] != c.dims[0]) f.bad("Number of frames in box and coords datasets in HDF5 do not match");
   if (c.dims[0] > 0xffffffffull || c.dims[1] > 0xffffffffull) f.bad("HDF5 coordinates dataset is too large");
   nframes_ = (uint32_t)c.dims[0];

@@ -584,3 +584,15 @@ def test_mdtraj_h5_validation(fe, tmp_path):
     assert "truncated or corrupt HDF5 file" in err(p)
     p = str(tmp_path / "f.h5"); fo.write_mdtraj_h5(p, xyz[:0])                  # no frames yet: opens, zero frames
     assert fe.lbfe_traj_info(p.encode(), 20, C.byref(na), C.byref(nf)) == 0 and nf.value == 0
+
+
+@pytest.mark.parametrize("fmt", ["dcd", "nc", "xtc", "h5", "h5v2"])
+def test_corrupt_files_never_crash(fe, tmp_path, fmt):
+    """120 corrupted copies of a valid file per format (tests/host/fuzz_readers.py): every one is either
+    refused with an error or read; the process survives.  (Run with thousands of mutants under
+    AddressSanitizer / UBSan while the readers were written; this is the cheap regression guard.)"""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host", "fuzz_readers.py"), fmt, "0", "120", str(tmp_path)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    assert "survived 120 mutants" in r.stdout
