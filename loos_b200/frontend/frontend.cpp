@@ -1328,9 +1328,13 @@ std::vector<float> readMatrix(std::istream& is, size_t* m_out, size_t* n_out) {
     if (sscanf(line.c_str(), "# %d %d", &m, &n) == 2) break;
   if (m == 0 && n == 0) throw Error("Could not find magic marker in matrix file");
   if (m <= 0 || n <= 0) throw Error("Error while reading magic marker");
-  std::vector<float> M((size_t)m * (size_t)n);
   // the rest of the stream in one piece: strtof per token (operator>> per value is ~10x slower)
   std::string body((std::istreambuf_iterator<char>(is)), std::istreambuf_iterator<char>());
+  // every value takes at least one character and a separator: a marker that promises more than the
+  // stream can hold is refused before anything of that size is allocated
+  if ((uint64_t)m * (uint64_t)n > body.size() / 2 + 1)
+    throw Error("Read error: the matrix file ends before the " + std::to_string(m) + " x " + std::to_string(n) + " values its marker announces");
+  std::vector<float> M((size_t)m * (size_t)n);
   const char* p = body.c_str();
   for (int j = 0; j < m; ++j)
     for (int i = 0; i < n; ++i) {
