@@ -1050,6 +1050,46 @@ void pyRepr(double x, std::string& out) {
 
 void pyRoundRepr(double v, int ndigits, std::string& out) {
   if (!std::isfinite(v) || v == 0.0) { pyRepr(v, out); return; }
+  // Fast exact path for the values a distance matrix holds: 1e-4 <= |v| < 1e15 and 0..15 decimals.
+  // v = m 2^-s exactly (m < 2^53, 1 <= s <= 66 in this range), so R = round-half-even(m 10^nd / 2^s) is
+  // integer arithmetic on 128 bits -- the correctly rounded decimal float.__round__ produces.  With at most
+  // 15 significant digits that decimal is also the shortest text of the double it converts to (repr).
+  const double av = std::fabs(v);
+  if (ndigits >= 0 && ndigits <= 15 && av >= 1e-4 && av < 1e15) {
+    static const uint64_t kPow10[16] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull,
+                                        1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull,
+                                        100000000000000ull, 1000000000000000ull};
+    uint64_t bits;
+    memcpy(&bits, &av, 8);
+    const int be = (int)(bits >> 52);  // normal here: av >= 1e-4
+    const uint64_t m = (bits & ((1ull << 52) - 1)) | (1ull << 52);
+    const int sh = 1075 - be;          // v = m * 2^-sh
+    if (sh >= 1 && sh <= 70) {
+      const unsigned __int128 P = (unsigned __int128)m * kPow10[ndigits];
+      unsigned __int128 R = P >> sh;
+      const unsigned __int128 rem = P & (((unsigned __int128)1 << sh) - 1), half = (unsigned __int128)1 << (sh - 1);
+      if (rem > half || (rem == half && (R & 1))) ++R;
+      if (R < (unsigned __int128)kPow10[15]) {
+        const uint64_t r = (uint64_t)R;
+        if (v < 0) out += '-';
+        if (r == 0) { out += "0.0"; return; }
+        const uint64_t ip = r / kPow10[ndigits];
+        uint64_t fp = r % kPow10[ndigits];
+        char tmp[24];
+        int n = 0;
+        uint64_t t = ip;
+        do { tmp[n++] = (char)('0' + t % 10); t /= 10; } while (t);
+        while (n) out += tmp[--n];
+        out += '.';
+        if (fp == 0) { out += '0'; return; }
+        int nd = ndigits;
+        while (fp % 10 == 0) { fp /= 10; --nd; }  // trailing zeros are not printed
+        for (int k = nd - 1; k >= 0; --k) { tmp[k] = (char)('0' + fp % 10); fp /= 10; }
+        out.append(tmp, (size_t)nd);
+        return;
+      }
+    }
+  }
   char buf[64];
   // common case: 0..15 decimals of a value of ordinary size.  glibc's %.{n}f is the correctly rounded
   // decimal (ties decided on the exact binary value, as _Py_dg_dtoa mode 3 does); with at most 15
@@ -1117,6 +1157,33 @@ void pyRoundRepr(double v, int ndigits, std::string& out) {
   // res holds the kept digits; its decimal point sits ndigits from the right (ndigits may be negative)
   std::string text = (v < 0 ? "-" : "") + res + "e" + std::to_string(-ndigits);
   pyRepr(strtod(text.c_str(), nullptr), out);
+}
+
+void writePyRoundMatrix(const double* M, size_t rows, size_t cols, size_t ld, int precision, unsigned threads,
+                        const std::function<void(const char*, size_t)>& write) {
+  if (rows == 0) return;
+  const size_t block = std::max<size_t>(1, (1u << 20) / std::max<size_t>(1, cols));
+  const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, (rows + block - 1) / block));
+  std::vector<std::string> text(nt);
+  for (size_t r0 = 0; r0 < rows; r0 += block * nt) {
+    auto work = [&](unsigned t) {
+      std::string& out = text[t];
+      out.clear();
+      const size_t lo = std::min(rows, r0 + t * block), hi = std::min(rows, lo + block);
+      for (size_t i = lo; i < hi; ++i) {
+        for (size_t j = 0; j < cols; ++j) { pyRoundRepr(M[j * ld + i], precision, out); out += ' '; }
+        out += '\n';
+      }
+    };
+    if (nt == 1) work(0);
+    else {
+      std::vector<std::thread> pool;
+      for (unsigned t = 0; t < nt; ++t) pool.emplace_back(work, t);
+      for (std::thread& th : pool) th.join();
+    }
+    for (unsigned t = 0; t < nt; ++t)
+      if (!text[t].empty()) write(text[t].data(), text[t].size());
+  }
 }
 
 std::shared_ptr<Trajectory> openTrajectory(const std::string& path, uint32_t natoms) {

@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include <fstream>
+#include <functional>
 #include <iosfwd>
 #include <map>
 #include <memory>
@@ -216,6 +217,11 @@ int formatFloatG(float v, unsigned precision, char* out);
 // exponent form when the decimal exponent is < -4 or >= 16).  Packages/Clustering/rmsds-align.py:254
 // writes its matrix that way.  Appends to `out`.
 void pyRoundRepr(double v, int ndigits, std::string& out);
+// The body of rmsds-align.py's output (:254-256): row i = `round(M(i,j), precision)` + " " for every j, then a
+// newline; M column-major with leading dimension ld.  Rows are formatted in blocks on `threads` threads and
+// handed to `write` in order.
+void writePyRoundMatrix(const double* M, size_t rows, size_t cols, size_t ld, int precision, unsigned threads,
+                        const std::function<void(const char*, size_t)>& write);
 
 class Options {
  public:

@@ -78,6 +78,18 @@ int lbfe_py_round_repr(double v, int ndigits, char* out, int cap) {
   return (int)s.size();
 }
 
+// rmsds-align's matrix text for a column-major double matrix; returns the length or -1 when `cap` is too small
+long lbfe_py_round_matrix(const double* M, long rows, long cols, long ld, int precision, int threads, char* out, long cap) {
+  try {
+    std::string all;
+    writePyRoundMatrix(M, (size_t)rows, (size_t)cols, (size_t)ld, precision, (unsigned)threads,
+                       [&](const char* d, size_t n) { all.append(d, n); });
+    if ((long)all.size() > cap) return -1;
+    memcpy(out, all.data(), all.size());
+    return (long)all.size();
+  } catch (const std::exception& e) { return fail(e); }
+}
+
 int lbfe_traj_info(const char* path, uint32_t natoms_expected, uint32_t* natoms, uint32_t* nframes) {
   try { auto t = openTrajectory(path, natoms_expected); *natoms = t->natoms(); *nframes = t->nframes(); return 0; }
   catch (const std::exception& e) { return fail(e); }

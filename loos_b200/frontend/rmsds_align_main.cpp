@@ -156,13 +156,8 @@ int main(int argc, char* argv[]) {
     check(loosb200_rmsds_align(fa1.h, fr1.h, fa2.h, fr2.h, M.data(), F1), "rmsds-align");
 
     std::cout << "# " << header << std::endl;
-    std::string line;
-    for (size_t i = 0; i < F1; ++i) {
-      line.clear();
-      for (size_t j = 0; j < F2; ++j) { pyRoundRepr(M[j * F1 + i], precision, line); line += ' '; }
-      line += '\n';
-      fwrite(line.data(), 1, line.size(), stdout);
-    }
+    writePyRoundMatrix(M.data(), F1, F2, F1, precision, readerThreads(),
+                       [](const char* data, size_t n) { if (fwrite(data, 1, n, stdout) != n) throw Error("Error- cannot write to stdout"); });
     fflush(stdout);
   } catch (const std::exception& e) {
     std::cerr << e.what() << std::endl;

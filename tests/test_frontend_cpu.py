@@ -449,6 +449,7 @@ def test_py_round_repr_matches_python(fe):
     vals += [0.0, -0.0, 0.5, 1.5, 2.5, 0.125, 0.375, 2.675, 1.005, 1e-5, 1.23456e-7, 9.995, 99.995, 0.99999999, 1e15, 1e16, 1.5e16,
              123456789012345.678, 2.0 ** -20, 2.0 ** 60, 1e22, 1e23, float("inf"), float("nan"), -3.14159, -0.004, 5e-324, 1.7976931348623157e308]
     vals += [k / 1000.0 for k in range(0, 4000, 5)] + [k + 0.5 for k in range(20)]
+    vals += list(10.0 ** rng.uniform(-6, 16.5, 3000)) + [k / 16.0 + 1 / 32 for k in range(400)]      # around the exact fast path's limits; binary ties
     for n in (0, 1, 2, 3, 4, 6, 9, 12, 15, 16, 17, 20, -1, -2, -5, 400, -400):
         for v in vals:
             v = float(v)
@@ -596,3 +597,22 @@ def test_corrupt_files_never_crash(fe, tmp_path, fmt):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
     assert "survived 120 mutants" in r.stdout
+
+
+@pytest.mark.parametrize("rows,cols,threads", [(1, 1, 1), (7, 5, 3), (300, 4001, 4), (2500, 9, 8), (1100, 1000, 5)])
+def test_py_round_matrix_text(fe, rows, cols, threads):
+    """The body of rmsds-align's output (blocks of rows formatted on several threads, written in order) equals
+    what the script's print loop produces (oracle.py_round_text = Python's own round/repr), for shapes that
+    give one block, many blocks and a ragged last wave."""
+    from oracle.oracle import py_round_text
+    rng = np.random.default_rng(rows * 31 + cols)
+    M = np.asfortranarray(rng.gamma(2.0, 2.0, (rows + 3, cols)))      # ld > rows
+    M[0, 0] = 0.0
+    fe.lbfe_py_round_matrix.restype = C.c_long
+    fe.lbfe_py_round_matrix.argtypes = [C.POINTER(C.c_double), C.c_long, C.c_long, C.c_long, C.c_int, C.c_int, C.c_char_p, C.c_long]
+    cap = rows * cols * 12 + rows + 64
+    buf = C.create_string_buffer(cap)
+    for precision in (2, 5):
+        n = fe.lbfe_py_round_matrix(M.ctypes.data_as(C.POINTER(C.c_double)), rows, cols, rows + 3, precision, threads, buf, cap)
+        assert n > 0
+        assert buf.raw[:n].decode() == py_round_text(M[:rows], precision)
