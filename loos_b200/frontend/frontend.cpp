@@ -13,6 +13,7 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -34,12 +35,41 @@ static std::string fieldStr(const std::string& s, unsigned pos, unsigned n) {
   return v;
 }
 
+// A field that is just [blanks][sign]digits[.digits][blanks] -- every number a PDB writer prints -- goes
+// straight to strtof, which is what the stream extraction below ends up calling for it (libstdc++ num_get
+// collects the characters and converts them with strtof): same value, a tenth of the time.
+static bool plainDecimal(const char* p, unsigned n, float* out) {
+  char buf[24];
+  if (n >= sizeof(buf)) return false;
+  unsigned i = 0, digits = 0, dots = 0;
+  while (i < n && p[i] == ' ') ++i;
+  const unsigned start = i;
+  if (i < n && (p[i] == '-' || p[i] == '+')) ++i;
+  for (; i < n; ++i) {
+    if (p[i] >= '0' && p[i] <= '9') ++digits;
+    else if (p[i] == '.' && !dots) ++dots;
+    else break;
+  }
+  const unsigned end = i;
+  for (; i < n; ++i)
+    if (p[i] != ' ') return false;
+  if (!digits) return false;
+  memcpy(buf, p + start, end - start);
+  buf[end - start] = 0;
+  *out = strtof(buf, nullptr);
+  return true;
+}
+
 // parseStringAs<T> (src/utils.hpp:324-360): stream extraction from the (clipped) field.
 template <typename T>
 static T fieldNum(const std::string& s, unsigned pos, unsigned nelem) {
   if (pos >= s.size()) throw Error("Missing Field at position " + std::to_string(pos) + "\n> " + s);
   unsigned n = nelem;
   if ((size_t)pos + n > s.size()) n = (unsigned)(s.size() - pos + 1);
+  if (std::is_same<T, float>::value) {
+    float f;
+    if (plainDecimal(s.data() + pos, (unsigned)std::min<size_t>(n, s.size() - pos), &f)) return (T)f;
+  }
   std::istringstream iss(s.substr(pos, n));
   T val(0);
   if (!(iss >> val)) throw Error("PARSE ERROR\n" + s);
@@ -103,7 +133,7 @@ static void parseAtomRecord(const std::string& s, Model& m) {  // src/pdb.cpp:66
       }
     }
   }
-  m.push_back(a);
+  m.push_back(std::move(a));
 }
 
 Model readPDB(std::istream& is) {
@@ -118,9 +148,24 @@ Model readPDB(std::istream& is) {
 }
 
 Model readPDB(const std::string& path) {
-  std::ifstream ifs(path.c_str());
-  if (!ifs) throw Error("Cannot open " + path);
-  return readPDB(ifs);
+  // the whole file in one read, then lines out of memory (an ifstream costs more per line than the parsing)
+  PosFile pf;
+  pf.open(path);
+  std::string text((size_t)pf.size(), '\0');
+  if (pf.size()) pf.readAt(0, &text[0], text.size(), "Cannot read " + path);
+  Model m;
+  m.reserve(text.size() / 64 + 16);  // ATOM lines are 67-81 bytes
+  std::string line;
+  size_t p = 0;
+  while (p < text.size()) {
+    size_t e = text.find('\n', p);
+    if (e == std::string::npos) e = text.size();
+    line.assign(text, p, e - p);
+    p = e + 1;
+    if (line.compare(0, 4, "ATOM") == 0 || line.compare(0, 6, "HETATM") == 0) parseAtomRecord(line, m);
+    else if (line.compare(0, 3, "END") == 0) break;
+  }
+  return m;
 }
 
 // ================================================================= selection
