@@ -110,3 +110,54 @@ def rmsd2ref_iterative_sharded(fs_align, fs_rmsd, first_frame, n_frames_total, t
     avg_r = _all_reduce_sum(accumulate(fs_align, used, fs_rmsd), group) / float(n_frames_total)
     rmsd, xf = rmsd_to(fs_align, used, fs_rmsd, avg_r)
     return {"rmsd": rmsd, "xforms": xf, "avg": avg_r, "iters": it, "rms": rms}
+
+
+# ---------------------------------------------------------------------------------------------
+# rmsds-align over several GPUs: rows (frames of trajectory 1) are independent and cost the same,
+# so every rank takes a contiguous stripe of them against all of trajectory 2.  No collective while
+# computing; the stripes are gathered on rank 0 at the end.
+
+def stripe(n, rank, world):
+    """[lo, hi) of rank's share of n rows: contiguous, sizes differ by at most one."""
+    base, extra = divmod(int(n), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def rmsds_align_sharded(X1, sel_align1, sel_rmsd1, X2, sel_align2, sel_rmsd2, rank, world, group=None, compute=None):
+    """X1: (F1, natoms1, 3) frames of trajectory 1, X2: (F2, natoms2, 3) of trajectory 2 (every rank
+    holds both; only its stripe of X1 is staged).  Returns the (F1, F2) float64 matrix on rank 0, None
+    elsewhere.  `compute(A1, R1, A2, R2)` (arrays of selected coordinates) defaults to staging on this
+    rank's GPU and api.rmsds_align; the CPU tests inject the oracle's loop."""
+    lo, hi = stripe(len(X1), rank, world)
+
+    def on_gpu(A1, R1, A2, R2):
+        with api.FrameSet(A1) as a1, api.FrameSet(R1) as r1, api.FrameSet(A2) as a2, api.FrameSet(R2) as r2:
+            return api.rmsds_align(a1, r1, a2, r2)
+
+    compute = compute or on_gpu
+    X1 = np.asarray(X1)
+    X2 = np.asarray(X2)
+    block = np.zeros((0, len(X2)))
+    if hi > lo:
+        block = np.ascontiguousarray(compute(X1[lo:hi][:, sel_align1], X1[lo:hi][:, sel_rmsd1], X2[:, sel_align2], X2[:, sel_rmsd2]),
+                                     dtype=np.float64)
+    if world == 1:
+        return block
+    import torch
+    import torch.distributed as dist
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    if rank != 0:
+        if hi > lo:
+            dist.send(torch.as_tensor(block, device=dev), dst=0, group=group)
+        return None
+    M = np.zeros((len(X1), len(X2)))
+    M[lo:hi] = block
+    for src in range(1, world):
+        slo, shi = stripe(len(X1), src, world)
+        if shi > slo:
+            t = torch.empty((shi - slo, len(X2)), dtype=torch.float64, device=dev)
+            dist.recv(t, src=src, group=group)
+            M[slo:shi] = t.cpu().numpy()
+    return M

@@ -131,3 +131,55 @@ def test_two_rank_sharded_iterative_alignment():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(res), res
+
+
+def _align_worker(rank, world, port, F1, F2, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from loos_b200 import multigpu
+    from loos_b200.synth import synth_frames
+    from oracle import oracle
+    ck = oracle.Checker("port")
+    X = synth_frames(F1, 40, seed=21)
+    Y = synth_frames(F2, 40, seed=22)
+    sa, sr = np.arange(0, 24, 2), np.arange(10, 40)
+    M = multigpu.rmsds_align_sharded(X, sa, sr, Y, sa, sr, rank, world,
+                                     compute=lambda a1, r1, a2, r2: oracle.rmsds_align(ck, a1, r1, a2, r2))
+    if rank == 0:
+        whole = oracle.rmsds_align(ck, X[:, sa], X[:, sr], Y[:, sa], Y[:, sr])
+        q.put((M.shape == (F1, F2), float(np.abs(M - whole).max())))
+    else:
+        assert M is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("F1,F2", [(9, 7), (1, 5)])
+def test_two_rank_rmsds_align_stripes(F1, F2):
+    """rmsds-align rows striped over two ranks (the second rank's stripe is empty when F1 = 1), gathered on
+    rank 0: equals the unsharded matrix.  The per-rank compute is stood in by the oracle's loop."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + F1
+    procs = [ctx.Process(target=_align_worker, args=(r, 2, port, F1, F2, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok_shape, err = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok_shape and err < 1e-9
+
+
+def test_stripes_partition_the_rows():
+    from loos_b200.multigpu import stripe
+    for n in (0, 1, 7, 8, 100001):
+        for world in (1, 2, 3, 8):
+            parts = [stripe(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[k][1] == parts[k + 1][0] for k in range(world - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
