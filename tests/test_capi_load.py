@@ -73,3 +73,29 @@ def test_product_does_not_touch_oracle():
                     if re.search(r"\boracle[./]|import oracle|from oracle|liboracle|libloosref", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_null_arguments_are_errors_not_crashes():
+    """Every entry point called with null pointers / zero sizes returns (an error code where it has one)."""
+    import ctypes as C
+    import re
+
+    from loos_b200 import capi
+    L = capi.lib()
+    names = re.findall(r'"(loosb200_\w+)":', open(capi.__file__).read())
+    assert len(names) >= 28
+    for n in names:
+        f = getattr(L, n)
+        args = []
+        for a in f.argtypes or []:
+            if a is C.c_double:
+                args.append(0.0)
+            elif a is capi.SINK:
+                args.append(capi.SINK(0))
+            elif isinstance(a, type) and issubclass(a, C._SimpleCData) and a not in (C.c_void_p, C.c_char_p):
+                args.append(0)
+            else:
+                args.append(None)
+        r = f(*args)
+        if n.startswith(("loosb200_stage", "loosb200_rmsd", "loosb200_align", "loosb200_frames_info", "loosb200_get", "loosb200_part", "loosb200_last_timing")):
+            assert isinstance(r, int) and r < 0, (n, r)
