@@ -587,7 +587,7 @@ def test_mdtraj_h5_validation(fe, tmp_path):
     assert fe.lbfe_traj_info(p.encode(), 20, C.byref(na), C.byref(nf)) == 0 and nf.value == 0
 
 
-@pytest.mark.parametrize("fmt", ["dcd", "nc", "xtc", "h5", "h5v2"])
+@pytest.mark.parametrize("fmt", ["dcd", "nc", "xtc", "h5", "h5v2", "text"])
 def test_corrupt_files_never_crash(fe, tmp_path, fmt):
     """120 corrupted copies of a valid file per format (tests/host/fuzz_readers.py): every one is either
     refused with an error or read; the process survives.  (Run with thousands of mutants under
