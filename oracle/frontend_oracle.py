@@ -5,9 +5,11 @@ Each function cites the reference code it follows (paths under /root/reference).
 
 Parity status.  PDB / selection / ranges / DCD: restated from the reference's sources, which cannot be
 built here (Boost, bison/flex); the native front-end and this file are two independent readings that the
-tests hold to bit-equality.  XTC (write_xtc / read_xtc, restating src/xtcwriter.cpp and src/xtc.cpp) and
-MDTraj HDF5 (write_mdtraj_h5, written from the HDF5 file format specification): PARITY UNPINNED -- no file
-written by GROMACS or MDTraj, and no other implementation of either format, exists in this image."""
+tests hold to bit-equality.  XTC (write_xtc / read_xtc, restating src/xtcwriter.cpp and src/xtc.cpp): PINNED --
+byte-identical files and bit-identical coordinates against the reference's own writer and reader compiled in
+place (oracle/xtc_ref_wrapper.cpp, tests/golden/xtc_ref.npz).  MDTraj HDF5 (write_mdtraj_h5, written from the
+HDF5 file format specification): PARITY UNPINNED -- no file written by MDTraj and no other implementation of
+the format exists in this image."""
 import re
 import struct
 
@@ -333,11 +335,10 @@ def read_dcd(path):
 
 # ---------------------------------------------------------------------------------------------
 # GROMACS XTC (test infrastructure).  The reference reads XTC with src/xtc.cpp (165-486) and writes
-# it with src/xtcwriter.cpp (387-655), both following the xdrfile library.  No XTC file ships with
-# the reference and no other XTC implementation exists in this image, so the native reader
-# (loos_b200/frontend) is checked against files produced by `write_xtc` below, a restatement of the
-# reference's writer, and against `read_xtc`, a restatement of its reader -- parity with files
-# written by GROMACS itself is UNPINNED.
+# it with src/xtcwriter.cpp (387-655), both following the xdrfile library.  `write_xtc` / `read_xtc`
+# below restate them; both are PINNED to the reference's own code compiled in place
+# (oracle/xtc_ref_wrapper.cpp -> oracle/_ref/libloosxtc.so, fixtures in tests/golden/xtc_ref.npz):
+# byte-identical files, bit-identical coordinates.  Only a file written by GROMACS itself is untested.
 
 XTC_MAGICINTS = [
     0, 0, 0, 0, 0, 0, 0, 0, 0, 8, 10, 12, 16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322, 406, 512,

@@ -171,6 +171,44 @@ def have_reference():
     return os.path.exists(os.path.join(_HERE, "_ref", "libloosref.so"))
 
 
+class RefXTC:
+    """The reference's OWN XTC writer and reader (src/xtcwriter.cpp, src/xtc.cpp, src/xdr.hpp compiled where they
+    lie: oracle/xtc_ref_wrapper.cpp, oracle/_ref/libloosxtc.so).  Exists only where /root/reference did at build
+    time (`available()`); the fixtures it generated travel in tests/golden/xtc_ref.npz."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(_HERE, "_ref", "libloosxtc.so"))
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(_HERE, "_ref", "libloosxtc.so"))
+        self.lib.ref_xtc_write.restype = C.c_long
+        self.lib.ref_xtc_write.argtypes = [_dp, C.c_int, C.c_int, C.c_float, _dp, C.c_double, C.c_char_p, C.c_long]
+        self.lib.ref_xtc_read.argtypes = [C.c_char_p, C.c_long, _dp, C.c_int, C.POINTER(C.c_int)]
+
+    def write(self, frames_angstrom, precision=1000.0, box_angstrom=(50.0, 60.0, 70.0), dt=1.0):
+        """XTCWriter::writeFrame over the frames (GCoords are double) -> the bytes of the file."""
+        X = np.ascontiguousarray(frames_angstrom, dtype=np.float64)
+        F, N, _ = X.shape
+        box = np.array(box_angstrom, dtype=np.float64)
+        cap = 256 + F * (N * 16 + 256)
+        buf = C.create_string_buffer(cap)
+        n = self.lib.ref_xtc_write(X.ctypes.data_as(_dp), F, N, precision, box.ctypes.data_as(_dp), dt, buf, cap)
+        if n < 0:
+            raise RuntimeError("reference XTC writer failed (%d)" % n)
+        return buf.raw[:n]
+
+    def read(self, data, max_frames, natoms):
+        """XTC::parseFrame over the bytes -> (frames, natoms, 3) float64, the GCoords the reference hands on."""
+        out = np.zeros((max_frames, natoms, 3))
+        na = C.c_int()
+        nf = self.lib.ref_xtc_read(data, len(data), out.ctypes.data_as(_dp), max_frames, C.byref(na))
+        if nf < 0:
+            raise RuntimeError("reference XTC reader failed (%d)" % nf)
+        assert na.value == natoms
+        return out[:nf]
+
+
 # ---------------------------------------------------------------------------
 # Text format of the result matrix: src/MatrixImpl.hpp:210-222 under
 # `cout << setprecision(p)` (Tools/rmsds.cpp:566-567).  C++ default floatfield

@@ -80,8 +80,44 @@ def align_golden(R):
                         text_p3=np.array(py_round_text(M, 3)))
 
 
+def xtc_cases():
+    """The five XTC test shapes (also used by tests/test_frontend_cpu.py): protein, water triplets, a wide box in which
+    the small-range index walks both ways, <= 9 atoms (stored as plain floats), extent above 2^24 quanta."""
+    from loos_b200.synth import synth_system
+    rng = np.random.default_rng(5)
+    out = {}
+    out["protein"] = synth_system(40, 5, seed=3, flavour="rich")[1]
+    O = rng.uniform(0, 40, (4, 300, 1, 3))
+    out["water"] = (O + rng.normal(0, 0.4, (4, 300, 3, 3))).reshape(4, 900, 3).astype(np.float32)
+    w = rng.uniform(-300, 300, (3, 200, 3)).astype(np.float32)
+    w[:, 50:120] = (w[:, 50:51] + rng.normal(0, 0.05, (3, 70, 3))).astype(np.float32)
+    out["wide"] = w
+    out["tiny"] = rng.uniform(-20, 20, (5, 7, 3)).astype(np.float32)
+    h = rng.uniform(-1.2e5, 1.2e5, (2, 64, 3)).astype(np.float32)
+    h[:, 10] = h[:, 9] + 1.0
+    out["huge_box"] = h
+    return out
+
+
+def xtc_golden():
+    """(5) XTC: files written by the reference's own XTCWriter and the coordinates its own XTC reader decodes
+    from them (oracle/_ref/libloosxtc.so)."""
+    from oracle.oracle import RefXTC
+    R = RefXTC()
+    out = {}
+    for name, xyz in xtc_cases().items():
+        data = R.write(xyz)
+        out[name + "_xyz"] = xyz
+        out[name + "_file"] = np.frombuffer(data, dtype=np.uint8)
+        out[name + "_decoded"] = R.read(data, len(xyz), xyz.shape[1])
+    np.savez_compressed(os.path.join(HERE, "xtc_ref.npz"), **out)
+
+
 if __name__ == "__main__":
     if "--only-align" in sys.argv:
         align_golden(Checker("reference"))
+    elif "--only-xtc" in sys.argv:
+        xtc_golden()
     else:
         main()
+        xtc_golden()

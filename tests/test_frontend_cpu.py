@@ -385,7 +385,8 @@ def test_xtc_reader(fe, tmp_path, case):
     """XTC frames decoded by the native reader equal, bit for bit, the restatement of the reference's
     reader (readCompressedCoords, src/xtc.cpp:165-332) on files made by the restatement of the
     reference's writer (src/xtcwriter.cpp:387-655); and both are within half a quantum of the input.
-    Parity with GROMACS-written files is unpinned (no such file exists in the reference or this image)."""
+    Both restatements are pinned to the reference's own compiled code further down
+    (test_xtc_against_the_references_own_writer_and_reader)."""
     from oracle import frontend_oracle as fo
     from loos_b200.synth import synth_system
     rng = np.random.default_rng(5)
@@ -616,3 +617,53 @@ def test_py_round_matrix_text(fe, rows, cols, threads):
         n = fe.lbfe_py_round_matrix(M.ctypes.data_as(C.POINTER(C.c_double)), rows, cols, rows + 3, precision, threads, buf, cap)
         assert n > 0
         assert buf.raw[:n].decode() == py_round_text(M[:rows], precision)
+
+
+# ------------------------------------------------------------------ XTC pinned to the reference's own code
+XTC_GOLDEN = os.path.join(ROOT, "tests", "golden", "xtc_ref.npz")
+
+
+@pytest.mark.parametrize("case", ["protein", "water", "wide", "tiny", "huge_box"])
+def test_xtc_against_the_references_own_writer_and_reader(fe, tmp_path, case):
+    """tests/golden/xtc_ref.npz holds files written by the reference's own XTCWriter (src/xtcwriter.cpp) and the
+    GCoords its own reader (src/xtc.cpp) decodes from them, both compiled from the sources where they lie
+    (oracle/_ref/libloosxtc.so, tests/golden/make_golden.py::xtc_golden).  The native reader reproduces those
+    coordinates bit for bit (narrowed to the float32 every format is staged as), and the tests' restatement of the
+    writer reproduces the reference's files byte for byte -- so the other XTC tests stand on pinned ground."""
+    from oracle import frontend_oracle as fo
+    g = np.load(XTC_GOLDEN)
+    xyz, data, decoded = g[case + "_xyz"], g[case + "_file"].tobytes(), g[case + "_decoded"]
+    F, N, _ = xyz.shape
+    path = str(tmp_path / "ref.xtc")
+    open(path, "wb").write(data)
+    got = _xtc_read_native(fe, path, N, F)
+    assert np.array_equal(got.view(np.uint32), decoded.astype(np.float32).view(np.uint32))
+    assert np.array_equal(fo.read_xtc(path).view(np.uint32), got.view(np.uint32))
+    mine = str(tmp_path / "mine.xtc")
+    fo.write_xtc(mine, xyz)
+    assert open(mine, "rb").read() == data
+
+
+def test_xtc_reference_library_live():
+    """Where the reference library itself is present (the build container): regenerate the fixture's content and
+    compare, plus a case that is not in the fixture."""
+    from oracle.oracle import RefXTC
+    if not RefXTC.available():
+        pytest.skip("oracle/_ref/libloosxtc.so not built (no /root/reference here)")
+    from oracle import frontend_oracle as fo
+    R = RefXTC()
+    g = np.load(XTC_GOLDEN)
+    for case in ("protein", "water", "tiny"):
+        xyz = g[case + "_xyz"]
+        data = R.write(xyz)
+        assert data == g[case + "_file"].tobytes()
+        assert np.array_equal(R.read(data, len(xyz), xyz.shape[1]), g[case + "_decoded"])
+    rng = np.random.default_rng(99)
+    xyz = (rng.normal(0, 18, (1, 517, 3)) + rng.normal(0, 0.8, (6, 517, 3))).astype(np.float32)
+    data = R.write(xyz, precision=100.0)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "a.xtc")
+        fo.write_xtc(p, xyz, precision=100.0)
+        assert open(p, "rb").read() == data
+        assert np.array_equal(fo.read_xtc(p), R.read(data, 6, 517).astype(np.float32))
