@@ -3,9 +3,10 @@ front-end semantics (selection language, PDB fields, hybrid-36, frame ranges,
 MultiTrajectory indexing, DCD layout), used to check loos_b200/frontend bit-exactly.
 Each function cites the reference code it follows (paths under /root/reference).
 
-Parity status.  PDB / selection / ranges / DCD: restated from the reference's sources, which cannot be
+Parity status.  PDB / selection / ranges: restated from the reference's sources, which cannot be
 built here (Boost, bison/flex); the native front-end and this file are two independent readings that the
-tests hold to bit-equality.  XTC (write_xtc / read_xtc, restating src/xtcwriter.cpp and src/xtc.cpp): PINNED --
+tests hold to bit-equality.  DCD (read_dcd, and write_dcd in loos_b200/synth.py): PINNED to the reference's own
+reader and writer compiled in place (oracle/dcd_ref_wrapper.cpp, tests/golden/dcd_ref.npz).  XTC (write_xtc / read_xtc, restating src/xtcwriter.cpp and src/xtc.cpp): PINNED --
 byte-identical files and bit-identical coordinates against the reference's own writer and reader compiled in
 place (oracle/xtc_ref_wrapper.cpp, tests/golden/xtc_ref.npz).  MDTraj HDF5 (write_mdtraj_h5, written from the
 HDF5 file format specification): PARITY UNPINNED -- no file written by MDTraj and no other implementation of

@@ -209,6 +209,44 @@ class RefXTC:
         return out[:nf]
 
 
+class RefDCD:
+    """The reference's OWN DCD reader and writer (src/dcd.cpp, src/dcdwriter.cpp compiled where they lie:
+    oracle/dcd_ref_wrapper.cpp, oracle/_ref/libloosdcd.so).  Exists only where /root/reference did at build time
+    (`available()`); the fixtures it generated travel in tests/golden/dcd_ref.npz."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(_HERE, "_ref", "libloosdcd.so"))
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(_HERE, "_ref", "libloosdcd.so"))
+        self.lib.ref_dcd_write.restype = C.c_long
+        self.lib.ref_dcd_write.argtypes = [_dp, C.c_int, C.c_int, _dp, C.c_char_p, C.c_long]
+        self.lib.ref_dcd_read.argtypes = [C.c_char_p, C.c_long, _fp, C.c_long, C.POINTER(C.c_int)]
+
+    def write(self, frames, box=None):
+        """DCDWriter::writeFrame over the frames -> the bytes of the file (box: 3 edge lengths or None)."""
+        X = np.ascontiguousarray(frames, dtype=np.float64)
+        F, N, _ = X.shape
+        b = None if box is None else np.array(box, dtype=np.float64)
+        cap = 4096 + F * (N * 12 + 256)
+        buf = C.create_string_buffer(cap)
+        n = self.lib.ref_dcd_write(X.ctypes.data_as(_dp), F, N, None if b is None else b.ctypes.data_as(_dp), buf, cap)
+        if n < 0:
+            raise RuntimeError("reference DCD writer failed (%d)" % n)
+        return buf.raw[:n]
+
+    def read(self, data, max_frames, natoms):
+        """DCD::readHeader + seekFrame/parseFrame per frame -> dict(natoms, nframes, crystal, swabbed, xyz (F, natoms, 3) float32)."""
+        out = np.zeros((max_frames, 3, natoms), np.float32)
+        info = (C.c_int * 4)()
+        nf = self.lib.ref_dcd_read(data, len(data), out.ctypes.data_as(_fp), out.size, info)
+        if nf < 0:
+            raise RuntimeError("reference DCD reader failed (%d)" % nf)
+        return {"natoms": info[0], "nframes": info[1], "crystal": bool(info[2]), "swabbed": bool(info[3]),
+                "xyz": out[:nf].transpose(0, 2, 1).copy()}
+
+
 # ---------------------------------------------------------------------------
 # Text format of the result matrix: src/MatrixImpl.hpp:210-222 under
 # `cout << setprecision(p)` (Tools/rmsds.cpp:566-567).  C++ default floatfield

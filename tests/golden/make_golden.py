@@ -113,11 +113,46 @@ def xtc_golden():
     np.savez_compressed(os.path.join(HERE, "xtc_ref.npz"), **out)
 
 
+def dcd_golden():
+    """(6) DCD: files written by the reference's own DCDWriter (with and without a periodic box) and what its own DCD
+    reader makes of them and of the test-suite's own DCD variants (byte-swapped, crystal records, frame count from the
+    file size) -- oracle/_ref/libloosdcd.so."""
+    import tempfile
+
+    from loos_b200.synth import write_dcd
+    from oracle.oracle import RefDCD
+    R = RefDCD()
+    rng = np.random.default_rng(3)
+    F, N = 11, 97
+    xyz = rng.normal(0, 30, (F, N, 3)).astype(np.float32)
+    out = {"xyz": xyz}
+    for name, box in (("ref_written", None), ("ref_written_box", (61.0, 62.0, 63.0))):
+        data = R.write(xyz, box)
+        got = R.read(data, F, N)
+        out[name + "_file"] = np.frombuffer(data, dtype=np.uint8)
+        out[name + "_decoded"] = got["xyz"]
+        out[name + "_info"] = np.array([got["natoms"], got["nframes"], got["crystal"], got["swabbed"]])
+    with tempfile.TemporaryDirectory() as d:
+        for name, kw in (("plain", {}), ("crystal", dict(with_crystal=True)), ("big_endian", dict(big_endian=True)),
+                         ("be_crystal", dict(big_endian=True, with_crystal=True)), ("nframes_from_size", dict(header_nframes=0))):
+            p = os.path.join(d, "t.dcd")
+            write_dcd(p, xyz, **kw)
+            data = open(p, "rb").read()
+            got = R.read(data, F, N)
+            out[name + "_file"] = np.frombuffer(data, dtype=np.uint8)
+            out[name + "_decoded"] = got["xyz"]
+            out[name + "_info"] = np.array([got["natoms"], got["nframes"], got["crystal"], got["swabbed"]])
+    np.savez_compressed(os.path.join(HERE, "dcd_ref.npz"), **out)
+
+
 if __name__ == "__main__":
-    if "--only-align" in sys.argv:
+    if "--only-dcd" in sys.argv:
+        dcd_golden()
+    elif "--only-align" in sys.argv:
         align_golden(Checker("reference"))
     elif "--only-xtc" in sys.argv:
         xtc_golden()
     else:
         main()
         xtc_golden()
+        dcd_golden()
