@@ -1448,10 +1448,12 @@ std::vector<float> readMatrix(std::istream& is, size_t* m_out, size_t* n_out) {
     throw Error("Read error: the matrix file ends before the " + std::to_string(m) + " x " + std::to_string(n) + " values its marker announces");
   std::vector<float> M((size_t)m * (size_t)n);
   const char* p = body.c_str();
+  const char *last = p, *last_end = p;  // the previous token (empty before the first)
   for (int j = 0; j < m; ++j)
     for (int i = 0; i < n; ++i) {
       while (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r') ++p;
-      if (!*p) throw Error("Read error at (" + std::to_string(j) + "," + std::to_string(i) + ") with input ''");
+      // the reference's `is >> inbuf` fails at the end of the stream without touching inbuf: its message shows the LAST token read
+      if (!*p) throw Error("Read error at (" + std::to_string(j) + "," + std::to_string(i) + ") with input '" + std::string(last, last_end) + "'");
       char* end = nullptr;
       const float v = strtof(p, &end);
       if (end == p) {
@@ -1460,6 +1462,9 @@ std::vector<float> readMatrix(std::istream& is, size_t* m_out, size_t* n_out) {
         throw Error("Invalid conversion on matrix read at (" + std::to_string(j) + "," + std::to_string(i) + ") of '" + std::string(p, q) + "'");
       }
       M[(size_t)i * (size_t)m + (size_t)j] = v;
+      last = p;
+      last_end = end;
+      while (*last_end && *last_end != ' ' && *last_end != '\n' && *last_end != '\t' && *last_end != '\r') ++last_end;  // a token is whitespace-delimited
       p = end;
     }
   *m_out = (size_t)m; *n_out = (size_t)n;

@@ -209,6 +209,44 @@ class RefXTC:
         return out[:nf]
 
 
+class RefMatrix:
+    """The reference's OWN matrix text writer and reader (operator<< of src/MatrixImpl.hpp:208-222 under setprecision,
+    readAsciiMatrix of src/MatrixRead.hpp:102-143; header-only, included where they lie: oracle/matrix_ref_wrapper.cpp,
+    oracle/_ref/libloosmatrix.so).  Exists only where /root/reference did at build time; fixtures from it travel in
+    tests/golden/matrix_ref.npz."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(_HERE, "_ref", "libloosmatrix.so"))
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(_HERE, "_ref", "libloosmatrix.so"))
+        self.lib.ref_matrix_text.restype = C.c_long
+        self.lib.ref_matrix_text.argtypes = [_fp, C.c_int, C.c_int, C.c_long, C.c_int, C.c_char_p, C.c_long]
+        self.lib.ref_matrix_read.argtypes = [C.c_char_p, C.c_long, _fp, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_int]
+
+    def text(self, M, precision):
+        M = np.asfortranarray(M, dtype=np.float32)
+        m, n = M.shape
+        cap = 64 + m * n * (precision + 16) + m
+        buf = C.create_string_buffer(cap)
+        k = self.lib.ref_matrix_text(M.ctypes.data_as(_fp), m, n, m, precision, buf, cap)
+        if k < 0:
+            raise RuntimeError("reference matrix writer failed (%d)" % k)
+        return buf.raw[:k].decode()
+
+    def read(self, text):
+        """-> (M, None) or (None, the reference's error message)."""
+        data = text.encode() if isinstance(text, str) else text
+        out = np.zeros(max(16, len(data)), np.float32)
+        m, n = C.c_int(), C.c_int()
+        err = C.create_string_buffer(400)
+        rc = self.lib.ref_matrix_read(data, len(data), out.ctypes.data_as(_fp), out.size, C.byref(m), C.byref(n), err, 400)
+        if rc != 0:
+            return None, err.value.decode()
+        return out[:m.value * n.value].reshape(n.value, m.value).T.copy(), None
+
+
 class RefDCD:
     """The reference's OWN DCD reader and writer (src/dcd.cpp, src/dcdwriter.cpp compiled where they lie:
     oracle/dcd_ref_wrapper.cpp, oracle/_ref/libloosdcd.so).  Exists only where /root/reference did at build time

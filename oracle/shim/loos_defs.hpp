@@ -43,7 +43,9 @@ struct NumericalError : public std::runtime_error {
 }  // namespace loos
 
 // boost::format is only used for a warning message on the hot path
-// (alignment.cpp:56-58); swallow it.
+// (alignment.cpp:56-58); swallow it.  (The matrix wrapper needs the header line it formats and brings
+// shim/boost/format.hpp instead: LOOS_SHIM_REAL_FORMAT.)
+#if !defined(LOOS_SHIM_REAL_FORMAT)
 namespace boost {
 struct fmtstub {
   template <class T> fmtstub& operator%(const T&) { return *this; }
@@ -51,5 +53,6 @@ struct fmtstub {
 inline fmtstub format(const char*) { return fmtstub(); }
 inline std::ostream& operator<<(std::ostream& o, const fmtstub&) { return o; }
 }  // namespace boost
+#endif
 
 #endif

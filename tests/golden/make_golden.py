@@ -145,8 +145,31 @@ def dcd_golden():
     np.savez_compressed(os.path.join(HERE, "dcd_ref.npz"), **out)
 
 
+def matrix_golden():
+    """(7) matrix text: what the reference's own operator<< prints for a float matrix at several precisions, and what its
+    own readAsciiMatrix makes of good and bad input (oracle/_ref/libloosmatrix.so)."""
+    from oracle.oracle import RefMatrix
+    R = RefMatrix()
+    rng = np.random.default_rng(4)
+    M = np.asfortranarray(rng.gamma(2.0, 2.5, (37, 23)).astype(np.float32))
+    for k, v in enumerate([0, 1e-7, 123456.789, 9.9999, 0.00012345, 1e10, 99.5, 0.5, 2.5, 0.25, 1e-5, 3.4e38, 1.17549435e-38, 16777216.0]):
+        M[k, k] = v
+    out = {"M": M}
+    for p in (0, 1, 2, 3, 6, 8, 9, 12):
+        out["text_p%d" % p] = np.array(R.text(M, p))
+    bad = ["no marker here\n1 2 3\n", "# 2 2 (0)\n1 2 \n3 x \n", "# 2 2 (0)\n1 2 \n3 \n", "# 0 5 (0)\n", "# 2 2 (0)\n1 2 3 4 5 6\n",
+           "junk\n# header line\n# 2 3 (0)\n1e-3 2.5 -7 \n4 5 6 \n"]
+    out["bad_inputs"] = np.array(bad)
+    res = [R.read(b) for b in bad]
+    out["bad_errors"] = np.array([e or "" for _, e in res])
+    out["bad_values"] = np.array([np.array2string(m.ravel(order="F"), separator=",") if m is not None else "" for m, _ in res])
+    np.savez_compressed(os.path.join(HERE, "matrix_ref.npz"), **out)
+
+
 if __name__ == "__main__":
-    if "--only-dcd" in sys.argv:
+    if "--only-matrix" in sys.argv:
+        matrix_golden()
+    elif "--only-dcd" in sys.argv:
         dcd_golden()
     elif "--only-align" in sys.argv:
         align_golden(Checker("reference"))
@@ -156,3 +179,4 @@ if __name__ == "__main__":
         main()
         xtc_golden()
         dcd_golden()
+        matrix_golden()

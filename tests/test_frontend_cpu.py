@@ -709,3 +709,49 @@ def test_dcd_reference_library_live(tmp_path):
     got = R.read(open(p, "rb").read(), 5, 1003)
     assert got["swabbed"] and got["crystal"] and got["nframes"] == 5 and np.array_equal(got["xyz"], xyz)
     assert np.array_equal(fo.read_dcd(p).transpose(0, 2, 1), xyz)     # the Python restatement (planes per frame) agrees too
+
+
+# ------------------------------------------------------------------ matrix text pinned to the reference's own code
+def test_matrix_text_and_reader_against_the_references_own_code(fe):
+    """tests/golden/matrix_ref.npz: what the reference's own `os << setprecision(p) << M` (src/MatrixImpl.hpp:208-222)
+    prints for a float matrix with awkward values at p = 0 ... 12, and what its own readAsciiMatrix
+    (src/MatrixRead.hpp:102-143) returns or throws for good and bad input -- both compiled from the headers where they
+    lie (oracle/_ref/libloosmatrix.so).  The oracle's matrix_text, the native writer and the native reader agree with
+    them character for character, message for message."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "matrix_ref.npz"))
+    M = np.asfortranarray(g["M"])
+    m, n = M.shape
+    cap = 1 << 20
+    out = C.create_string_buffer(cap)
+    for p in (0, 1, 2, 3, 6, 8, 9, 12):
+        want = str(g["text_p%d" % p])
+        assert matrix_text(M, p) == want
+        k = fe.lbfe_matrix_text(M.ctypes.data_as(C.POINTER(C.c_float)), m, n, m, p, out, cap)
+        assert out.raw[:k].decode() == want
+    fe.lbfe_read_matrix.restype = C.c_int
+    buf = np.zeros(64, np.float32)
+    mm, nn = C.c_long(), C.c_long()
+    for text, err, vals in zip(g["bad_inputs"], g["bad_errors"], g["bad_values"]):
+        data = str(text).encode()
+        rc = fe.lbfe_read_matrix(data, len(data), buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size, C.byref(mm), C.byref(nn))
+        if str(err):
+            assert rc == -1 and fe.lbfe_last_error().decode() == str(err), (text, fe.lbfe_last_error())
+        else:
+            assert rc == 0
+            got = np.array2string(buf[:mm.value * nn.value], separator=",")
+            assert got == str(vals)
+
+
+def test_matrix_reference_library_live():
+    from oracle.oracle import RefMatrix
+    if not RefMatrix.available():
+        pytest.skip("oracle/_ref/libloosmatrix.so not built (no /root/reference here)")
+    R = RefMatrix()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "matrix_ref.npz"))
+    assert R.text(g["M"], 2) == str(g["text_p2"])
+    rng = np.random.default_rng(77)
+    M = (10.0 ** rng.uniform(-6, 7, (40, 40))).astype(np.float32)
+    for p in (2, 5, 9):
+        assert R.text(M, p) == matrix_text(M, p)
+    back, err = R.read(matrix_text(M, 9))
+    assert err is None and np.array_equal(back, M)
