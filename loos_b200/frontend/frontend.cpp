@@ -63,7 +63,7 @@ static bool plainDecimal(const char* p, unsigned n, float* out) {
 // parseStringAs<T> (src/utils.hpp:324-360): stream extraction from the (clipped) field.
 template <typename T>
 static T fieldNum(const std::string& s, unsigned pos, unsigned nelem) {
-  if (pos >= s.size()) throw Error("Missing Field at position " + std::to_string(pos) + "\n> " + s);
+  if (pos >= s.size()) throw Error("Missing Field at position " + std::to_string(pos) + "\n> " + s + "\n");
   unsigned n = nelem;
   if ((size_t)pos + n > s.size()) n = (unsigned)(s.size() - pos + 1);
   if (std::is_same<T, float>::value) {
@@ -72,7 +72,8 @@ static T fieldNum(const std::string& s, unsigned pos, unsigned nelem) {
   }
   std::istringstream iss(s.substr(pos, n));
   T val(0);
-  if (!(iss >> val)) throw Error("PARSE ERROR\n" + s);
+  if (!(iss >> val))  // the reference underlines the field (src/utils.hpp:343-355)
+    throw Error("PARSE ERROR\n" + s + "\n" + std::string(pos, ' ') + std::string(n > 1 ? n : 1, '^') + "\n");
   return val;
 }
 
@@ -114,12 +115,11 @@ static void parseAtomRecord(const std::string& s, Model& m) {  // src/pdb.cpp:66
   a.resname = fieldStr(s, 17, 4);
   a.chain = fieldStr(s, 21, 1);
   a.resid = parseHybrid36(s, 22, 4);
-  std::string t = s.size() > 26 ? s.substr(26, 1) : std::string(" ");
-  if (t[0] != ' ' && isdigit((unsigned char)t[0])) {  // frame-shifted resid (non-strict policy)
+  a.icode = fieldStr(s, 26, 1);
+  if (!a.icode.empty() && isdigit((unsigned char)a.icode[0])) {  // frame-shifted resid (non-strict policy)
     a.resid = fieldNum<int>(s, 22, 5);
-    t = " ";
+    a.icode = " ";  // the reference stores the blank it substitutes (src/pdb.cpp:106-112)
   }
-  a.icode = t == " " ? "" : t;
   a.x = fieldNum<float>(s, 30, 8);
   a.y = fieldNum<float>(s, 38, 8);
   a.z = fieldNum<float>(s, 46, 8);

@@ -27,9 +27,10 @@ struct Error : std::runtime_error {
 struct Atom {
   uint32_t index = 0;  // position among the atom records of the file (pdb.cpp:73)
   long id = 0, resid = 0;
-  std::string record, name, altloc, resname, chain, icode, segid, element;
+  std::string record, name, altloc, resname, chain, icode, element;
+  std::string segid = "    ";  // Atom::init (src/Atom.cpp:189-207): what a line too short for the field keeps
   double x = 0, y = 0, z = 0;
-  double occupancy = 1.0, bfactor = 0.0;
+  double occupancy = 1.0, bfactor = 0.0;  // defaults of Atom::init as well
 };
 typedef std::vector<Atom> Model;
 

@@ -39,6 +39,22 @@ long lbfe_pdb_atoms(const char* pdb_path, long* ids, long* resids, double* xyz, 
   } catch (const std::exception& e) { return fail(e); }
 }
 
+// One ATOM / HETATM line through the PDB parser; same interface as the reference-side checker's ref_pdb_atom:
+// ints: id, resid; strs (16 bytes apart): record, name, altloc, resname, chain, icode, segid, element; reals: x y z occ b
+int lbfe_pdb_atom_line(const char* line, int* ints2, char* strs8x16, double* reals5) {
+  try {
+    std::istringstream is(std::string(line) + "\n");
+    const Model m = readPDB(is);
+    if (m.size() != 1) throw Error("not an ATOM/HETATM record");
+    const Atom& a = m[0];
+    ints2[0] = a.id; ints2[1] = a.resid;
+    const std::string* f[8] = {&a.record, &a.name, &a.altloc, &a.resname, &a.chain, &a.icode, &a.segid, &a.element};
+    for (int k = 0; k < 8; ++k) { memset(strs8x16 + 16 * k, 0, 16); strncpy(strs8x16 + 16 * k, f[k]->c_str(), 15); }
+    reals5[0] = a.x; reals5[1] = a.y; reals5[2] = a.z; reals5[3] = a.occupancy; reals5[4] = a.bfactor;
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+
 int lbfe_hybrid36(const char* field, int n) { try { return parseHybrid36(std::string(field), 0, (unsigned)n); } catch (const std::exception& e) { fail(e); return -999999; } }
 
 long lbfe_parse_range(const char* spec, uint32_t maxsize, uint32_t* out, long cap) {
@@ -56,6 +72,13 @@ long lbfe_assign_frames(uint32_t nframes, const char* spec, uint32_t skip, uint3
     for (long i = 0; i < (long)r.size() && i < cap; ++i) out[i] = r[i];
     return (long)r.size();
   } catch (const std::exception& e) { return fail(e); }
+}
+
+// uniquifyVector (src/utils.hpp:426-436): sorted, duplicates removed
+long lbfe_uniquify(const uint32_t* v, long n, uint32_t* out) {
+  const std::vector<uint32_t> u = uniquify(std::vector<uint32_t>(v, v + n));
+  for (size_t i = 0; i < u.size(); ++i) out[i] = u[i];
+  return (long)u.size();
 }
 
 int lbfe_dcd_info(const char* path, uint32_t* natoms, uint32_t* nframes, int* crystal) {

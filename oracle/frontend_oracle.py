@@ -3,9 +3,10 @@ front-end semantics (selection language, PDB fields, hybrid-36, frame ranges,
 MultiTrajectory indexing, DCD layout), used to check loos_b200/frontend bit-exactly.
 Each function cites the reference code it follows (paths under /root/reference).
 
-Parity status.  PDB / selection / ranges: restated from the reference's sources, which cannot be
-built here (Boost, bison/flex); the native front-end and this file are two independent readings that the
-tests hold to bit-equality.  DCD (read_dcd, and write_dcd in loos_b200/synth.py): PINNED to the reference's own
+Parity status.  Selection language / frame ranges: restated from the reference's sources, which cannot be
+built here (bison/flex, Boost.Spirit); the native front-end and this file are two independent readings that the
+tests hold to bit-equality.  PDB records, hybrid-36, MultiTrajectory indexing: PINNED to the reference's own
+functions compiled in place (oracle/pdb_ref_wrapper.cpp, tests/golden/pdb_ref.json).  DCD (read_dcd, and write_dcd in loos_b200/synth.py): PINNED to the reference's own
 reader and writer compiled in place (oracle/dcd_ref_wrapper.cpp, tests/golden/dcd_ref.npz).  XTC (write_xtc / read_xtc, restating src/xtcwriter.cpp and src/xtc.cpp): PINNED --
 byte-identical files and bit-identical coordinates against the reference's own writer and reader compiled in
 place (oracle/xtc_ref_wrapper.cpp, tests/golden/xtc_ref.npz).  MDTraj HDF5 (write_mdtraj_h5, written from the
@@ -57,7 +58,7 @@ def read_pdb(path):
         if line.startswith("ATOM") or line.startswith("HETATM"):
             a = dict(index=len(atoms), id=hybrid36(line[6:11]) if len(line) >= 11 else 0, name=_fs(line, 12, 4),
                      resname=_fs(line, 17, 4), chain=_fs(line, 21, 1),
-                     resid=hybrid36(line[22:26]) if len(line) >= 26 else 0, segid=_fs(line, 72, 4) if len(line) > 72 else "")
+                     resid=hybrid36(line[22:26]) if len(line) >= 26 else 0, segid=_fs(line, 72, 4) if len(line) > 72 else "    ")      # Atom::init default (src/Atom.cpp:202) survives a short line
             if len(line) > 26 and line[26].isdigit():
                 a["resid"] = int(line[22:27])
             a["xyz"] = tuple(float(np.float32(float(line[p:p + 8]))) for p in (30, 38, 46))

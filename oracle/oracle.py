@@ -247,6 +247,50 @@ class RefMatrix:
         return out[:m.value * n.value].reshape(n.value, m.value).T.copy(), None
 
 
+class RefPDB:
+    """The reference's OWN PDB atom-record parser (src/pdb.cpp:65-156 with parseStringAs / parseStringAsHybrid36 of
+    src/utils.{hpp,cpp}), uniquifyVector and MultiTrajectory indexing (src/MultiTraj.hpp:97-105, MultiTraj.cpp:48-58),
+    compiled where they lie: oracle/pdb_ref_wrapper.cpp, oracle/_ref/libloospdb.so.  Fixtures: tests/golden/pdb_ref.npz."""
+    FIELDS = ("record", "name", "altloc", "resname", "chain", "icode", "segid", "element")
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(_HERE, "_ref", "libloospdb.so"))
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(_HERE, "_ref", "libloospdb.so"))
+        self.lib.ref_multitraj.restype = C.c_long
+        self.lib.ref_uniquify.restype = C.c_long
+
+    def atom(self, line):
+        """-> dict of the fields parseAtomRecord stores, or the ParseError text."""
+        i, s, r, err = (C.c_int * 2)(), C.create_string_buffer(128), (C.c_double * 5)(), C.create_string_buffer(800)
+        if self.lib.ref_pdb_atom(line.encode(), i, s, r, err, 800) != 0:
+            return err.value.decode()
+        d = {"id": i[0], "resid": i[1], "x": r[0], "y": r[1], "z": r[2], "occupancy": r[3], "bfactor": r[4]}
+        for k, name in enumerate(self.FIELDS):
+            d[name] = s.raw[16 * k:16 * k + 16].split(b"\0")[0].decode()
+        return d
+
+    def hybrid36(self, field):
+        return self.lib.ref_hybrid36(field.encode(), len(field))
+
+    def multitraj(self, sizes, skip, stride):
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint32)
+        cap = int(sizes.sum()) + 1
+        lt, lf = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+        P = C.POINTER(C.c_uint32)
+        n = self.lib.ref_multitraj(sizes.ctypes.data_as(P), len(sizes), skip, stride, lt.ctypes.data_as(P), lf.ctypes.data_as(P), cap)
+        return [(int(a), int(b)) for a, b in zip(lt[:n], lf[:n])]
+
+    def uniquify(self, v):
+        v = np.ascontiguousarray(v, dtype=np.uint32)
+        out = np.zeros(max(1, len(v)), np.uint32)
+        P = C.POINTER(C.c_uint32)
+        n = self.lib.ref_uniquify(v.ctypes.data_as(P), len(v), out.ctypes.data_as(P))
+        return out[:n].tolist()
+
+
 class RefDCD:
     """The reference's OWN DCD reader and writer (src/dcd.cpp, src/dcdwriter.cpp compiled where they lie:
     oracle/dcd_ref_wrapper.cpp, oracle/_ref/libloosdcd.so).  Exists only where /root/reference did at build time

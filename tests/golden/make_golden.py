@@ -166,8 +166,54 @@ def matrix_golden():
     np.savez_compressed(os.path.join(HERE, "matrix_ref.npz"), **out)
 
 
+PDB_LINES = [
+    "ATOM      1  N   ALA A   1      11.104   6.134  -6.504  1.00  0.00      PROT N",
+    "ATOM  A0000  CA  ALA A9999      -1.500 123.456-100.250  0.50 12.34      PROT C",
+    "HETATM99999  OH2 TIP3W a000       0.000   0.000   0.000  1.00  0.00      SOLV O",
+    "ATOM     12 HA12 LYS B -12A      1.000   2.000   3.000",
+    "ATOM     13  CB  LYS B  13       1.000   2.000   3.000  0.75",
+    "ATOM     14  CG  LYS B  14       1.000   2.000   3.000  0.75 20.00",
+    "ATOM     15  CD  LYS B10015       1.000   2.000   3.000  1.00  0.00      SEG1 C",
+    "ATOM     15  CD  LYS B 10015      1.000   2.000   3.000  1.00  0.00      SEG1",
+    "ATOM  1e+04  CE  LYS B  16       1.5e1   2.000   3.000  1.00  0.00      SEG2 C1",
+    "ATOM     17  NZ  LYS B  17       abc     2.000   3.000",
+    "ATOM     18  C   LYS B  18 ",
+    "ATOM  zzzzz  O   LYSXB ZZZZ      9.999  -0.001   0.000  1.00  0.00      Q",
+    "HETATM  100 CAL  CAL     7       0.100   0.200   0.300  1.00  0.00          CA",
+    "ATOM    200  P     A C  22  .    1.      2.     3.      .5    .25       RNA  P ",
+    "ATOM    201  C1' DA  D  23      -0.5     +2.25   3e0     1     2",
+]
+HYBRID36_FIELDS = ["    1", "99999", "A0000", "ZZZZZ", "a0000", "zzzzz", "  -12", " 1234", "A000", "zzzz", "9999", "-999", "   0", "a00",
+                   "Zz", "9", " ", "12 4", "1e3", "-A00", "    ", "00012", "AAAAA"]
+
+
+def pdb_golden():
+    """(8) PDB atom records, hybrid-36 fields, MultiTrajectory indexing and uniquifyVector through the reference's own
+    functions (oracle/_ref/libloospdb.so)."""
+    import json
+
+    from oracle.oracle import RefPDB
+    R = RefPDB()
+    rng = np.random.default_rng(0)
+    mt = []
+    for _ in range(120):
+        sizes = rng.integers(0, 40, int(rng.integers(1, 6))).tolist()
+        skip, stride = int(rng.integers(0, 12)), int(rng.integers(1, 7))
+        mt.append({"sizes": sizes, "skip": skip, "stride": stride, "locations": R.multitraj(sizes, skip, stride)})
+    uq = []
+    for _ in range(30):
+        v = rng.integers(0, 25, int(rng.integers(0, 40))).tolist()
+        uq.append({"in": v, "out": R.uniquify(v)})
+    out = {"atoms": [{"line": ln, "parsed": R.atom(ln)} for ln in PDB_LINES],
+           "hybrid36": [{"field": f, "value": R.hybrid36(f)} for f in HYBRID36_FIELDS], "multitraj": mt, "uniquify": uq}
+    with open(os.path.join(HERE, "pdb_ref.json"), "w") as fh:
+        json.dump(out, fh, indent=0)
+
+
 if __name__ == "__main__":
-    if "--only-matrix" in sys.argv:
+    if "--only-pdb" in sys.argv:
+        pdb_golden()
+    elif "--only-matrix" in sys.argv:
         matrix_golden()
     elif "--only-dcd" in sys.argv:
         dcd_golden()
@@ -180,3 +226,4 @@ if __name__ == "__main__":
         xtc_golden()
         dcd_golden()
         matrix_golden()
+        pdb_golden()

@@ -755,3 +755,68 @@ def test_matrix_reference_library_live():
         assert R.text(M, p) == matrix_text(M, p)
     back, err = R.read(matrix_text(M, 9))
     assert err is None and np.array_equal(back, M)
+
+
+# ------------------------------------------------------------------ PDB records, hybrid-36, MultiTrajectory pinned to the reference's own code
+def test_pdb_records_hybrid36_multitraj_against_the_references_own_code(fe, tmp_path):
+    """tests/golden/pdb_ref.json: what the reference's own PDB::parseAtomRecord (src/pdb.cpp:65-156, with parseStringAs
+    and parseStringAsHybrid36 of src/utils.{hpp,cpp}) stores or throws for 15 ATOM/HETATM lines -- hybrid-36 ids, a
+    negative resid with an insertion code, frame-shifted resids, truncated lines (Atom::init defaults survive: occupancy
+    1, segid four blanks), exponent notation, unparsable fields --, parseStringAsHybrid36 on 23 fields,
+    MultiTrajectory::nframes(i) / frameIndexToLocation (src/MultiTraj.{hpp,cpp}) for 120 random (sizes, skip, stride)
+    and uniquifyVector, all compiled from the sources where they lie (oracle/_ref/libloospdb.so).  The native
+    front-end and the Python restatement reproduce every field, value and message."""
+    import json
+    from oracle import frontend_oracle as fo
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "pdb_ref.json")))
+    names = ("record", "name", "altloc", "resname", "chain", "icode", "segid", "element")
+    for k, rec in enumerate(g["atoms"]):
+        line, want = rec["line"], rec["parsed"]
+        ints, strs, reals = (C.c_int * 2)(), C.create_string_buffer(128), (C.c_double * 5)()
+        rc = fe.lbfe_pdb_atom_line(line.encode(), ints, strs, reals)
+        if isinstance(want, str):                                   # the reference threw: same message
+            assert rc == -1 and fe.lbfe_last_error().decode() == want, (line, fe.lbfe_last_error())
+            continue
+        assert rc == 0, (line, fe.lbfe_last_error())
+        got = {"id": ints[0], "resid": ints[1], "x": reals[0], "y": reals[1], "z": reals[2], "occupancy": reals[3], "bfactor": reals[4]}
+        for j, nm in enumerate(names):
+            got[nm] = strs.raw[16 * j:16 * j + 16].split(b"\0")[0].decode()
+        assert got == want, (line, got, want)
+        p = tmp_path / ("l%d.pdb" % k)                              # and the Python restatement of the reader
+        p.write_text(line + "\n")
+        try:
+            a = fo.read_pdb(str(p))[0]
+        except ValueError:                                          # it float()s whole fields: not for the mis-columned lines
+            continue
+        assert (a["id"], a["resid"], a["name"], a["resname"], a["segid"]) == (want["id"], want["resid"], want["name"], want["resname"], want["segid"])
+    for rec in g["hybrid36"]:
+        f = rec["field"]
+        assert fe.lbfe_hybrid36(f.encode(), len(f)) == rec["value"], f
+    P = C.POINTER(C.c_uint32)
+    for rec in g["multitraj"]:
+        sizes = np.array(rec["sizes"], dtype=np.uint32)
+        want = [tuple(x) for x in rec["locations"]]
+        lt, lf = np.zeros(len(want) + 1, np.uint32), np.zeros(len(want) + 1, np.uint32)
+        n = fe.lbfe_multitraj(sizes.ctypes.data_as(P), len(sizes), rec["skip"], rec["stride"], lt.ctypes.data_as(P), lf.ctypes.data_as(P), len(lt))
+        assert n == len(want) and list(zip(lt[:n].tolist(), lf[:n].tolist())) == want
+        assert fo.multitraj_locations(rec["sizes"], rec["skip"], rec["stride"]) == want
+    fe.lbfe_uniquify.restype = C.c_long
+    for rec in g["uniquify"]:
+        v = np.array(rec["in"], dtype=np.uint32)
+        out = np.zeros(len(v) + 1, np.uint32)
+        n = fe.lbfe_uniquify(v.ctypes.data_as(P), len(v), out.ctypes.data_as(P))
+        assert out[:n].tolist() == rec["out"]
+
+
+def test_pdb_reference_library_live():
+    from oracle.oracle import RefPDB
+    if not RefPDB.available():
+        pytest.skip("oracle/_ref/libloospdb.so not built (no /root/reference here)")
+    import json
+    R = RefPDB()
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "pdb_ref.json")))
+    for rec in g["atoms"]:
+        assert R.atom(rec["line"]) == rec["parsed"]
+    for rec in g["hybrid36"]:
+        assert R.hybrid36(rec["field"]) == rec["value"]
+    assert [list(x) for x in R.multitraj([5, 0, 9], 2, 3)] == [[0, 2], [2, 2], [2, 5], [2, 8]]
