@@ -283,6 +283,15 @@ class RefPDB:
         n = self.lib.ref_multitraj(sizes.ctypes.data_as(P), len(sizes), skip, stride, lt.ctypes.data_as(P), lf.ctypes.data_as(P), cap)
         return [(int(a), int(b)) for a, b in zip(lt[:n], lf[:n])]
 
+    def backbone(self, resname, name):
+        """BackboneSelector (src/Selectors.cpp:37-132) on an atom with this residue and atom name."""
+        return bool(self.lib.ref_backbone(resname.encode(), name.encode()))
+
+    def hydrogen(self, name, mass=None):
+        """HydrogenSelector (src/Selectors.cpp:156-164); mass=None: the mass property is not set (PDB input)."""
+        self.lib.ref_hydrogen.argtypes = [C.c_char_p, C.c_int, C.c_double]
+        return bool(self.lib.ref_hydrogen(name.encode(), 0 if mass is None else 1, 0.0 if mass is None else float(mass)))
+
     def uniquify(self, v):
         v = np.ascontiguousarray(v, dtype=np.uint32)
         out = np.zeros(max(1, len(v)), np.uint32)

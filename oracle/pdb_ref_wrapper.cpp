@@ -6,6 +6,7 @@
 //   * src/utils.cpp:253-317       parseStringAsHybrid36 (with its tables)
 //   * src/utils.hpp:426-436       uniquifyVector
 //   * src/MultiTraj.hpp:97-105    MultiTrajectory::nframes(i);  src/MultiTraj.cpp:48-58 frameIndexToLocation
+//   * src/Selectors.cpp:37-132,156-164  BackboneSelector (its two name tables) and HydrogenSelector
 // oracle/Makefile extracts the line ranges into a throw-away directory; nothing of them stays in the repo.
 // Below: shells for Atom / PDB / MultiTrajectory with just the members those functions touch (the real classes,
 // src/Atom.hpp, src/pdb.hpp, src/MultiTraj.hpp, stand on AtomicGroup / Trajectory / Boost), and a C interface.
@@ -52,6 +53,14 @@ class Atom {  // the setters parseAtomRecord calls (src/Atom.hpp)
   void bfactor(greal r) { b = r; }
   void segid(const std::string& s) { segid_ = s; }
   void PDBelement(const std::string& s) { element = s; }
+  // what the selectors read (src/Atom.hpp)
+  enum bits { nullbit = 0, massbit = 1 };
+  std::string name() const { return name_; }
+  std::string resname() const { return resname_; }
+  bool checkProperty(bits) const { return has_mass; }
+  double mass() const { return mass_; }
+  bool has_mass = false;
+  double mass_ = 1.0;
   // defaults: Atom::init, src/Atom.cpp:189-207
   uint index_ = 0;
   int id_ = 1, resid_ = 1;
@@ -73,6 +82,19 @@ class PDB {
 };
 
 #include "_ref/pdb_atom_record.inc"      // PDB::parseAtomRecord
+
+struct AtomSelector {};
+class BackboneSelector : public AtomSelector {  // src/Selectors.hpp:53-62
+  static const uint nresnames = 48;
+  static std::string residue_names[nresnames];
+  static const uint natomnames = 33;
+  static std::string atom_names[natomnames];
+ public:
+  bool operator()(const pAtom&) const;
+};
+struct HydrogenSelector : public AtomSelector { bool operator()(const pAtom&) const; };
+#include "_ref/selectors_backbone.inc"   // the tables and BackboneSelector::operator()
+#include "_ref/selectors_hydrogen.inc"   // HydrogenSelector::operator()
 
 struct FakeTraj { uint n; uint nframes() const { return n; } };
 class MultiTrajectory {
@@ -121,6 +143,17 @@ long ref_multitraj(const unsigned* sizes, int ntraj, unsigned skip, unsigned str
     loc_traj[k] = loc.first; loc_frame[k] = loc.second;
   }
   return total;
+}
+
+int ref_backbone(const char* resname, const char* name) {
+  loos::pAtom a(new loos::Atom);
+  a->resname(resname); a->name(name);
+  return loos::BackboneSelector()(a) ? 1 : 0;
+}
+int ref_hydrogen(const char* name, int has_mass, double mass) {
+  loos::pAtom a(new loos::Atom);
+  a->name(name); a->has_mass = has_mass != 0; a->mass_ = mass;
+  return loos::HydrogenSelector()(a) ? 1 : 0;
 }
 
 // uniquifyVector<uint>: returns the number of unique values written to out

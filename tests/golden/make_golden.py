@@ -204,7 +204,20 @@ def pdb_golden():
     for _ in range(30):
         v = rng.integers(0, 25, int(rng.integers(0, 40))).tolist()
         uq.append({"in": v, "out": R.uniquify(v)})
-    out = {"atoms": [{"line": ln, "parsed": R.atom(ln)} for ln in PDB_LINES],
+    # every (residue name, atom name) pair of a candidate set that contains the selector's own tables and near misses
+    resnames = ["A", "A3", "A5", "ALA", "ARG", "ASN", "ASP", "C", "C3", "C5", "CYS", "CYX", "DA", "DC", "DG", "DT", "G", "G3", "G5", "GLN", "GLU",
+                "GLY", "HID", "HIE", "HIP", "HIS", "HSD", "HSE", "HSP", "ILE", "LEU", "LYS", "MET", "PHE", "PRO", "SER", "THR", "TRP", "TYR", "U", "U3",
+                "U5", "VAL", "RA", "RC", "RG", "RU", "DA3", "DA5", "DC3", "DC5", "DG3", "DG5", "DT3", "DT5", "T", "TIP3", "HOH", "POPC", "ala", "Ala",
+                "ACE", "NME", "CYM", "ASH", "GLH", "LYN", "MSE", "SOL", "NA", "CL", "ATP", "HEM", "DU", "N", "UNK", "AL", "ALAX", "PTR", "T3", "T5", "SEP",
+                "TPO", "HYP", "GLX"]
+    names = ["C", "C1'", "C2'", "C3'", "C4'", "C5'", "CA", "H", "H1'", "H12'", "H15'", "H2'", "H2''", "H22'", "H25'", "H3'", "H4'", "H5'", "H5''",
+             "HO2'", "HO3'", "HO5'", "N", "O", "O2'", "O3'", "O4'", "O5'", "OP1", "OP2", "OP3", "OXT", "P", "CB", "HA", "HN", "O1P", "O2P", "C1*", "H5'1",
+             "OT1", "OT2", "N1", "N9", "C2", "ca", "Ca", "HB1", "1HB", "OH2", "H1", "H2", "HT1", "CG", "SG", "FE", "HG", "He", "c", "O5*"]
+    sel = {"resnames": resnames, "names": names,
+           "backbone": [[int(R.backbone(r, n)) for n in names] for r in resnames],
+           "hydrogen": [int(R.hydrogen(n)) for n in names],
+           "hydrogen_mass": [[m, int(R.hydrogen("H1", m)), int(R.hydrogen("C1", m))] for m in (0.5, 1.008, 1.09, 1.1, 2.014, 4.0, 12.0)]}
+    out = {"selectors": sel, "atoms": [{"line": ln, "parsed": R.atom(ln)} for ln in PDB_LINES],
            "hybrid36": [{"field": f, "value": R.hybrid36(f)} for f in HYBRID36_FIELDS], "multitraj": mt, "uniquify": uq}
     with open(os.path.join(HERE, "pdb_ref.json"), "w") as fh:
         json.dump(out, fh, indent=0)

@@ -820,3 +820,35 @@ def test_pdb_reference_library_live():
     for rec in g["hybrid36"]:
         assert R.hybrid36(rec["field"]) == rec["value"]
     assert [list(x) for x in R.multitraj([5, 0, 9], 2, 3)] == [[0, 2], [2, 2], [2, 5], [2, 8]]
+
+
+def test_backbone_and_hydrogen_selectors_against_the_references_own_code(fe, tmp_path):
+    """tests/golden/pdb_ref.json["selectors"]: the decisions of the reference's own BackboneSelector (its two sorted
+    tables, src/Selectors.cpp:37-132) and HydrogenSelector (:156-164), compiled in place, for every pair of 85 residue
+    names x 60 atom names (the tables themselves plus near misses: other case, CHARMM/AMBER variants, waters, ions).
+    The native `backbone` and `hydrogen` keywords select exactly the same atoms of a PDB holding all the pairs."""
+    import json
+    from oracle import frontend_oracle as fo
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "pdb_ref.json")))["selectors"]
+    resnames, names = g["resnames"], g["names"]
+    lines, want_bb, want_h = [], [], []
+    k = 0
+    for i, r in enumerate(resnames):
+        for j, nm in enumerate(names):
+            k += 1
+            # name in columns 13-16 as given (left-justified), residue name in 18-21; parseStringAs strips blanks
+            lines.append("ATOM  %5d %-4s %-4s%1s%4d    %8.3f%8.3f%8.3f  1.00  0.00      SEG " % (k % 100000, nm, r, "A", (k // 60) % 10000, 1.0, 2.0, 3.0))
+            want_bb.append(g["backbone"][i][j])
+            want_h.append(g["hydrogen"][j])
+    path = str(tmp_path / "pairs.pdb")
+    open(path, "w").write("\n".join(lines) + "\nEND\n")
+    out = np.zeros(len(lines), np.uint32)
+    for sel, want in (("backbone", want_bb), ("hydrogen", want_h)):
+        n = fe.lbfe_select(path.encode(), sel.encode(), out.ctypes.data_as(_u32p), len(out))
+        assert n >= 0, fe.lbfe_last_error()
+        got = np.zeros(len(lines), int)
+        got[out[:n]] = 1
+        assert got.tolist() == want, sel
+        atoms = fo.read_pdb(path)
+        assert list(fo.select(atoms, sel)) == [i for i, w in enumerate(want) if w]      # and the Python restatement
+    assert sum(want_bb) == 48 * 33
