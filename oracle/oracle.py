@@ -167,6 +167,19 @@ def py_round_text(M, precision=2):
     return "".join("".join("%s " % repr(round(float(v), precision)) for v in row) + "\n" for row in M)
 
 
+def reference_iterative_vecmatrix(checker, frames, tol=1e-6, maxiter=1000):
+    """The reference's OWN iterativeAlignment(vecMatrix&, threshold, maxiter) (src/alignment.cpp:288-318, compiled in
+    place; reference checker only).  frames: (F, N, 3).  Returns (xforms (F, 4, 4), rms, iterations)."""
+    assert checker.kind == "reference"
+    X = np.ascontiguousarray(frames, dtype=np.float64).reshape(len(frames), -1)
+    xf = np.zeros((len(X), 16))
+    rms = C.c_double()
+    f = checker.lib.ref_iterative_vecmatrix
+    f.argtypes = [_dp, C.c_int, C.c_int, C.c_double, C.c_int, _dp, _dp]
+    it = f(X.ctypes.data_as(_dp), len(X), X.shape[1], tol, maxiter, xf.ctypes.data_as(_dp), C.byref(rms))
+    return xf.reshape(-1, 4, 4), rms.value, it
+
+
 def have_reference():
     return os.path.exists(os.path.join(_HERE, "_ref", "libloosref.so"))
 

@@ -36,6 +36,13 @@ typedef boost::tuple<vecDouble, vecDouble, vecDouble> SVDTupleVec;  // alignment
 }  // namespace loos
 
 #include "_ref/alignment_core.inc"  // verbatim reference lines, built by Makefile
+// src/alignment.cpp:288-318: the reference's own iterativeAlignment over a vecMatrix (frames as plain vectors).
+// rmsd2ref calls the trajectory-based overload (:355-404, restated below as ref_rmsd2ref_iterative because it needs
+// AtomicGroup / Trajectory); this overload is the same algorithm on the same arithmetic and is the cross-check for
+// that restatement (tests/test_oracle.py).
+namespace loos {
+#include "_ref/alignment_iterative.inc"
+}
 
 using loos::GCoord;
 using loos::GMatrix;
@@ -258,6 +265,21 @@ int ref_rmsd2ref_iterative(const double* fa, const double* fr, int F, int na3, i
   if (avg_out)
     for (int i = 0; i < nr; ++i) { avg_out[3*i] = tavg[i].x(); avg_out[3*i+1] = tavg[i].y(); avg_out[3*i+2] = tavg[i].z(); }
   return iter;
+}
+
+
+// The reference's own iterativeAlignment(vecMatrix&, threshold, maxiter) (src/alignment.cpp:288-318): frames F x n3
+// doubles (transformed in place there: a copy here), xf16 = F row-major 4x4 accumulated transforms.  Returns iterations.
+int ref_iterative_vecmatrix(const double* frames, int F, int n3, double tol, int maxiter, double* xf16, double* final_rms) {
+  loos::alignment::vecMatrix ens = to_rows(frames, F, n3);
+  boost::tuple<std::vector<XForm>, loos::greal, int> res = loos::iterativeAlignment(ens, tol, maxiter);
+  const std::vector<XForm>& xf = boost::get<0>(res);
+  for (int f = 0; f < F; ++f) {
+    GMatrix W = xf[f].current();
+    for (int k = 0; k < 16; ++k) xf16[(size_t)f * 16 + k] = W[k];
+  }
+  if (final_rms) *final_rms = boost::get<1>(res);
+  return boost::get<2>(res);
 }
 
 }  // extern "C"

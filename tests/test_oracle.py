@@ -96,3 +96,18 @@ def test_rmsds_align_restatement_matches_golden(port):
     assert np.abs(M - g["M"]).max() < 1e-9
     assert py_round_text(g["M"], 3) == str(g["text_p3"])
     assert py_round_text(M, 3) == str(g["text_p3"])
+
+
+def test_restated_iterative_loop_matches_the_references_own_iterative_alignment(reference):
+    """rmsd2ref's default mode calls the trajectory-based iterativeAlignment (src/alignment.cpp:355-404), which needs
+    AtomicGroup / Trajectory and is therefore RESTATED in oracle/ref_wrapper.cpp on top of the reference's compiled
+    kabsch.  The reference's vector-based overload (:288-318) is the same algorithm and IS compiled in place: both must
+    give the same iteration count, final rms and transforms."""
+    from oracle.oracle import reference_iterative_vecmatrix
+    for F, N, seed in [(40, 90, 1), (25, 30, 2), (60, 200, 3), (12, 4, 4)]:
+        Z = synth_frames(F, N, seed=seed).astype(np.float64)
+        _, xf, _, it, rms = reference.rmsd2ref_iterative(Z, Z, 1e-6, 1000)
+        xf2, rms2, it2 = reference_iterative_vecmatrix(reference, Z, 1e-6, 1000)
+        assert it == it2
+        assert abs(rms - rms2) < 1e-12
+        assert np.abs(xf - xf2).max() < 1e-10
