@@ -313,6 +313,79 @@ class RefPDB:
         return out[:n].tolist()
 
 
+# ---------------------------------------------------------------------------
+# The statistics lines of the tools, restated (the GPU tool tests compare the tools' stderr / stdout with these).
+def stats_line_half(M):
+    """showStatsHalf (Tools/rmsds.cpp:425-439): max and mean over the strict lower triangle, from the float32 entries."""
+    M = np.asarray(M, dtype=np.float32)
+    low = M[np.tril_indices(len(M), -1)].astype(np.float64)
+    return "Max rmsd = %.4f, avg rmsd = %.4f\n" % (low.max() if low.size else 0.0, low.sum() / (len(M) * (len(M) - 1) // 2))
+
+
+def stats_line_whole(M):
+    """showStatsWhole (Tools/rmsds.cpp:442-456) / rms-overlap's showStats (Tools/rms-overlap.cpp:458-473)."""
+    r = np.asarray(M, dtype=np.float32).astype(np.float64)
+    return "Max rmsd = %.4f, avg rmsd = %.4f\n" % (r.max(), r.sum() / r.size)
+
+
+def fractional_stats_line(M, cutoff):
+    """showFractionalStats (Tools/rms-overlap.cpp:475-521), bug for bug: the `if (R(i,j) > max)` has no braces, so only
+    the row index is conditional -- the column index and the "max" value are those of the LAST off-diagonal element
+    visited; avg and variance skip i == j but divide by the full size."""
+    M32 = np.asarray(M, dtype=np.float32)
+    r = M32.astype(np.float64)
+    m, n = r.shape
+    off = ~np.eye(m, n, dtype=bool)
+    avg = r[off].sum() / r.size
+    var = (r[off] ** 2).sum() / r.size - avg * avg
+    mval, mi, mj = 0.0, 0, 0
+    for i in range(m):
+        for j in range(n):
+            if i != j:
+                if r[i, j] > mval:
+                    mi = i
+                mj = j
+                mval = r[i, j]
+    return "Max rmsd = %.4f between frames %d, %d, avg rmsd = %.4f, variance = %.4f, frames below %.4f = %d, total = %d\n" % (
+        mval, mi, mj, avg, var, float(np.float32(cutoff)), int((M32[off] < np.float32(cutoff)).sum()), r.size)
+
+
+class RefStats:
+    """The reference's OWN showStatsHalf / showStatsWhole (Tools/rmsds.cpp:425-456) and showStats / showFractionalStats
+    (Tools/rms-overlap.cpp:458-521), compiled where they lie (oracle/stats_ref_wrapper.cpp, oracle/_ref/libloosstats.so)."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(_HERE, "_ref", "libloosstats.so"))
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(_HERE, "_ref", "libloosstats.so"))
+        for name in ("ref_stats_half", "ref_stats_whole", "ref_overlap_stats", "ref_overlap_fractional"):
+            getattr(self.lib, name).restype = C.c_long
+
+    def _call(self, name, M, *extra):
+        M = np.asfortranarray(M, dtype=np.float32)
+        m, n = M.shape
+        buf = C.create_string_buffer(1024)
+        args = [M.ctypes.data_as(_fp)] + ([C.c_int(m)] if name == "ref_stats_half" else [C.c_int(m), C.c_int(n)]) + [C.c_long(m)] + list(extra) + [buf, C.c_long(1024)]
+        k = getattr(self.lib, name)(*args)
+        if k < 0:
+            raise RuntimeError("%s failed (%d)" % (name, k))
+        return buf.raw[:k].decode()
+
+    def half(self, M):
+        return self._call("ref_stats_half", M)
+
+    def whole(self, M):
+        return self._call("ref_stats_whole", M)
+
+    def overlap(self, M):
+        return self._call("ref_overlap_stats", M)
+
+    def fractional(self, M, cutoff, is_noop=True):
+        return self._call("ref_overlap_fractional", M, C.c_float(cutoff), C.c_int(1 if is_noop else 0))
+
+
 class RefDCD:
     """The reference's OWN DCD reader and writer (src/dcd.cpp, src/dcdwriter.cpp compiled where they lie:
     oracle/dcd_ref_wrapper.cpp, oracle/_ref/libloosdcd.so).  Exists only where /root/reference did at build time

@@ -223,8 +223,32 @@ def pdb_golden():
         json.dump(out, fh, indent=0)
 
 
+def stats_golden():
+    """(9) the statistics lines of the tools from the reference's own functions (oracle/_ref/libloosstats.so)."""
+    import json
+
+    from oracle.oracle import RefStats
+    R = RefStats()
+    rng = np.random.default_rng(0)
+    cases = []
+    for m, n in [(58, 18), (7, 7), (1, 5), (30, 41), (2, 2), (18, 58)]:
+        M = rng.gamma(2.0, 2.5, (m, n)).astype(np.float32)
+        rec = {"M": M.tolist(), "whole": R.whole(M), "overlap": R.overlap(M),
+               "fractional": {str(c): R.fractional(M, c) for c in (6.5, 0.1, 3.0)}}
+        if m == n:
+            S = np.tril(M, -1)
+            S = S + S.T
+            rec["S"] = S.tolist()
+            rec["half"] = R.half(S)
+        cases.append(rec)
+    with open(os.path.join(HERE, "stats_ref.json"), "w") as fh:
+        json.dump(cases, fh)
+
+
 if __name__ == "__main__":
-    if "--only-pdb" in sys.argv:
+    if "--only-stats" in sys.argv:
+        stats_golden()
+    elif "--only-pdb" in sys.argv:
         pdb_golden()
     elif "--only-matrix" in sys.argv:
         matrix_golden()
@@ -240,3 +264,4 @@ if __name__ == "__main__":
         dcd_golden()
         matrix_golden()
         pdb_golden()
+        stats_golden()

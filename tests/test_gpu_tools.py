@@ -167,24 +167,11 @@ def test_rms_overlap(files, checker):
     assert head[1] == "# traj\tstart\tend\tfilename" and head[2].endswith("a.dcd") and head[3].endswith("b.dcd")
     assert head[4] == "# traj\tstart\tend\tfilename" and head[5] == "# 0\t0\t17\t%s" % (d / "c.dcd")
     assert M.shape == ref.shape == (58, 18) and np.abs(M - ref).max() < 2e-5
-    assert err.strip() == "Max rmsd = %.4f, avg rmsd = %.4f" % (ref.astype(np.float64).max(), ref.astype(np.float64).mean())
+    from oracle.oracle import fractional_stats_line, stats_line_whole     # pinned to the reference's own functions (CPU suite)
+    assert err.strip() == stats_line_whole(ref).strip()
     out, err = run("rms-overlap", "-s", "backbone && !hydrogen", "-i", "2", "-c", "6.5", "-N", "1",
                    "-A", "%s %s" % (d / "a.dcd", d / "b.dcd"), "-B", str(d / "c.dcd"), d / "model.pdb")
-    r64 = ref.astype(np.float64)
-    off = ~np.eye(58, 18, dtype=bool)
-    avg = r64[off].sum() / r64.size
-    var = (r64[off] ** 2).sum() / r64.size - avg * avg
-    # bug-compatible "max": the last off-diagonal element visited, row index of the last increase
-    mval, mi = 0.0, 0
-    for i in range(58):
-        for j in range(18):
-            if i != j:
-                if r64[i, j] > mval:
-                    mi = i
-                mval = r64[i, j]
-    want = "Max rmsd = %.4f between frames %d, %d, avg rmsd = %.4f, variance = %.4f, frames below %.4f = %d, total = %d" % (
-        mval, mi, 17, avg, var, 6.5, int((ref[off] < np.float32(6.5)).sum()), ref.size)
-    assert out.strip() == want and err == ""
+    assert out.strip() == fractional_stats_line(ref, 6.5).strip() and err == ""
 
 
 def test_amber_netcdf_trajectories_give_the_same_matrices(files, tmp_path):

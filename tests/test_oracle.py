@@ -111,3 +111,27 @@ def test_restated_iterative_loop_matches_the_references_own_iterative_alignment(
         assert it == it2
         assert abs(rms - rms2) < 1e-12
         assert np.abs(xf - xf2).max() < 1e-10
+
+
+def test_stats_lines_against_the_references_own_functions():
+    """tests/golden/stats_ref.json: what the reference's own showStatsHalf / showStatsWhole (Tools/rmsds.cpp:425-456) and
+    showStats / showFractionalStats (Tools/rms-overlap.cpp:458-521, brace-less `if` included) print for six matrices,
+    compiled from the tool sources where they lie (oracle/_ref/libloosstats.so).  The oracle's restatements, which the GPU
+    tool tests hold the tools' stderr / stdout to, reproduce every line."""
+    import json
+
+    from oracle.oracle import RefStats, fractional_stats_line, stats_line_half, stats_line_whole
+    cases = json.load(open(os.path.join(G, "stats_ref.json")))
+    live = RefStats() if RefStats.available() else None
+    for rec in cases:
+        M = np.array(rec["M"], dtype=np.float32)
+        assert stats_line_whole(M) == rec["whole"] == rec["overlap"]
+        for c, line in rec["fractional"].items():
+            assert fractional_stats_line(M, float(c)) == line
+            if live:
+                assert live.fractional(M, float(c)) == line
+        if "half" in rec:
+            S = np.array(rec["S"], dtype=np.float32)
+            assert stats_line_half(S) == rec["half"]
+            if live:
+                assert live.half(S) == rec["half"]
