@@ -3,9 +3,10 @@ front-end semantics (selection language, PDB fields, hybrid-36, frame ranges,
 MultiTrajectory indexing, DCD layout), used to check loos_b200/frontend bit-exactly.
 Each function cites the reference code it follows (paths under /root/reference).
 
-Parity status.  Selection language / frame ranges: restated from the reference's sources, which cannot be
-built here (bison/flex, Boost.Spirit); the native front-end and this file are two independent readings that the
-tests hold to bit-equality.  PDB records, hybrid-36, MultiTrajectory indexing: PINNED to the reference's own
+Parity status.  Selection language: PINNED to the reference's own scanner / grammar / kernel compiled in place
+(oracle/selection_ref_wrapper.cpp, tests/golden/selection_ref.json, 843 strings).  Frame ranges: restated from
+src/index_range_parser.cpp (Boost.Spirit: not compilable here); the native front-end and this file are two
+independent readings that the tests hold to bit-equality.  PDB records, hybrid-36, MultiTrajectory indexing: PINNED to the reference's own
 functions compiled in place (oracle/pdb_ref_wrapper.cpp, tests/golden/pdb_ref.json).  DCD (read_dcd, and write_dcd in loos_b200/synth.py): PINNED to the reference's own
 reader and writer compiled in place (oracle/dcd_ref_wrapper.cpp, tests/golden/dcd_ref.npz).  XTC (write_xtc / read_xtc, restating src/xtcwriter.cpp and src/xtc.cpp): PINNED --
 byte-identical files and bit-identical coordinates against the reference's own writer and reader compiled in

@@ -386,6 +386,39 @@ class RefStats:
         return self._call("ref_overlap_fractional", M, C.c_float(cutoff), C.c_int(1 if is_noop else 0))
 
 
+class RefSelect:
+    """The reference's OWN selection language: its pre-generated flex scanner and bison grammar, the kernel, Atom and the
+    backbone / hydrogen predicates compiled unmodified from /root/reference/src (oracle/selection_ref_wrapper.cpp,
+    oracle/shim_sel/, oracle/_ref/libloosselect.so).  Fixture: tests/golden/selection_ref.json."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(_HERE, "_ref", "libloosselect.so"))
+
+    def __init__(self, atoms):
+        """atoms: list of dicts with id, resid, name, resname, segid, chain (as oracle/frontend_oracle.py::read_pdb returns)."""
+        self.lib = C.CDLL(os.path.join(_HERE, "_ref", "libloosselect.so"))
+        self.n = len(atoms)
+        self.ids = np.array([a["id"] for a in atoms], np.int32)
+        self.resids = np.array([a["resid"] for a in atoms], np.int32)
+        self.strs = np.zeros((self.n, 4, 8), np.uint8)
+        for i, a in enumerate(atoms):
+            for j, key in enumerate(("name", "resname", "segid", "chain")):
+                b = a[key].encode()[:7]
+                self.strs[i, j, :len(b)] = list(b)
+
+    def select(self, selection):
+        """-> (list of selected indices, None) or (None, the exception text)."""
+        mask = np.zeros(self.n, np.uint8)
+        err = C.create_string_buffer(800)
+        ip = C.POINTER(C.c_int)
+        rc = self.lib.ref_select(selection.encode(), self.n, self.ids.ctypes.data_as(ip), self.resids.ctypes.data_as(ip),
+                                 self.strs.ctypes.data_as(C.c_char_p), mask.ctypes.data_as(C.POINTER(C.c_ubyte)), err, 800)
+        if rc != 0:
+            return None, err.value.decode()
+        return np.nonzero(mask)[0].tolist(), None
+
+
 class RefDCD:
     """The reference's OWN DCD reader and writer (src/dcd.cpp, src/dcdwriter.cpp compiled where they lie:
     oracle/dcd_ref_wrapper.cpp, oracle/_ref/libloosdcd.so).  Exists only where /root/reference did at build time

@@ -245,8 +245,74 @@ def stats_golden():
         json.dump(cases, fh)
 
 
+def selection_list():
+    """~830 selection strings: every pairing / triple of a set of atomic predicates under && || ! not and parentheses
+    (precedence and associativity), comparisons between keywords, literals on either side, string ordering, regular
+    expressions, the -> operator, comments, odd spacing, wrong case, and a collection of malformed inputs."""
+    import itertools
+    atomsx = ["name == 'CA'", "resid < 10010", "index >= 100", "hydrogen", "backbone", "segid == 'SOLV'", "name =~ '^H'", "id <= 50", "all",
+              "resname == 'ALA'", "chainid == 'A'"]
+    sels = []
+    for a, b in itertools.product(atomsx[:7], atomsx[:7]):
+        sels += ["%s && %s" % (a, b), "%s || %s" % (a, b), "!%s && %s" % (a, b), "!(%s || %s)" % (a, b), "not %s || not %s" % (a, b)]
+    for a, b, c in itertools.product(atomsx[:5], atomsx[3:8], atomsx[6:]):
+        sels += ["%s && %s || %s" % (a, b, c), "%s || %s && %s" % (a, b, c), "(%s || %s) && %s" % (a, b, c), "%s && (%s || !%s)" % (a, b, c)]
+    sels += ["resid == 10001", "10001 == resid", "resid != 10001", "resid > id", "id < index", "index == index", "name == name", "name != resname",
+             "name == resname", "'CA' == name", "name < 'CB'", "name >= 'N'", "resname <= 'B'", "name > \"C\"", "resid+1 == 10002", "resid == +10001",
+             "  name  ==  'CA'  ", "name=='CA'", "name=~'C'&&resid<10005", "name =~ 'c.'", "name =~ '^[CN]A?$'", "resname =~ 'A.A'", "segid =~ '^S'",
+             "chainid =~ 'a'", "name =~ ''", "name == ''", "segid == ''", "name =~ '\\d'", "name =~ \"'\"", "!!hydrogen", "! ! hydrogen", "not not hydrogen",
+             "!not hydrogen", "((((all))))", "(hydrogen)", "hydrogen && all", "all || hydrogen", "ALL", "Hydrogen", "NAME == 'CA'", "name == 'ca'",
+             "name -> '(\\d+)' == 12", "name -> '(\\d+)' > 1", "name -> '(\\d+)' >= 2", "name -> '(\\d+)' < 2", "name -> '(\\d+)' <= 2",
+             "name -> '(\\d+)' != 2", "resname -> '(\\d)' == 3", "segid -> '(\\d+)' > 0", "resid -> '1' == 1", "name -> 'x'",
+             "id == 1 || id == 2 || id == 3", "id == 1 && id == 2", "index < 5 # comment || all", "index < 5 || # comment", "resid == 10001 resid == 10002",
+             "resid 10001", "name 'CA'", "== 'CA'", "name == 'CA' &&", "&& name == 'CA'", "()", "( )", "name == (('CA'))", "(resid) < (10005)", "index < 1e3",
+             "index < 10.5", "index < -1", "index > 99999999999", "name == 'CA", "name == CA", "name == \"CA'", "resid == 0x10", "resid==10001||resid==10002",
+             "hydrogenx", "backbone2", "allx", "name=='CA'#c", "resid <= 10002 and name == 'CA'", "resid <= 10002 or name == 'CA'",
+             "name != 'CA' && name ne 'CB'", "segname != 'SOLV'", "index <= 10 || index >= 425", "!(index > 10) && !(index < 5)",
+             "name == 5", "name ==", "name === 'CA'", "resid == 'A'", "foo == 1", "(name == 'CA'", "name =~ 3", "'CA' =~ 'C'", "index",
+             "backbone && !hydrogen", "!(hydrogen || segid =~ 'SOLV|BULK')", "name =~ \"^(C|O|N|CA)$\"", "resname =~ 'tip'", "chainid == 'W' && name == 'OH2'"]
+    return sels
+
+
+def selection_golden():
+    """(10) the selection language through the reference's own scanner, grammar and kernel (oracle/_ref/libloosselect.so):
+    for every string of selection_list(), the set of selected atoms of a 432-atom model (as a bit string) or the fact that
+    the reference refuses it."""
+    import json
+    import tempfile
+
+    from loos_b200.synth import synth_system, write_pdb
+    from oracle import frontend_oracle as fo
+    from oracle.oracle import RefSelect
+    atoms, xyz = synth_system(40, 3, seed=7, flavour="rich")
+    for a in atoms:
+        a["resid"] = a["resid"] + 9990 if a["segid"] == "PROT" else a["resid"]
+    atoms[3]["name"] = "H12'"
+    atoms[7]["resname"] = "DA"
+    atoms[7]["name"] = "C1'"
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "m.pdb")
+        write_pdb(p, atoms, xyz[0])
+        text = open(p).read()
+        A = fo.read_pdb(p)
+    R = RefSelect(A)
+    out = {"pdb": text, "natoms": len(A), "cases": []}
+    for sel in selection_list():
+        got, err = R.select(sel)
+        if got is None:
+            out["cases"].append({"selection": sel, "error": err})
+        else:
+            bits = np.zeros(len(A), int)
+            bits[got] = 1
+            out["cases"].append({"selection": sel, "mask": "".join(map(str, bits))})
+    with open(os.path.join(HERE, "selection_ref.json"), "w") as fh:
+        json.dump(out, fh, indent=0)
+
+
 if __name__ == "__main__":
-    if "--only-stats" in sys.argv:
+    if "--only-selection" in sys.argv:
+        selection_golden()
+    elif "--only-stats" in sys.argv:
         stats_golden()
     elif "--only-pdb" in sys.argv:
         pdb_golden()
@@ -265,3 +331,4 @@ if __name__ == "__main__":
         matrix_golden()
         pdb_golden()
         stats_golden()
+        selection_golden()

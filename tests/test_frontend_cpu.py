@@ -852,3 +852,56 @@ def test_backbone_and_hydrogen_selectors_against_the_references_own_code(fe, tmp
         atoms = fo.read_pdb(path)
         assert list(fo.select(atoms, sel)) == [i for i, w in enumerate(want) if w]      # and the Python restatement
     assert sum(want_bb) == 48 * 33
+
+
+# ------------------------------------------------------------------ the selection language pinned to the reference's own code
+def test_selection_language_against_the_references_own_scanner_grammar_and_kernel(fe, tmp_path):
+    """tests/golden/selection_ref.json: 843 selection strings -- every pairing and triple of a set of predicates under
+    && || ! not and parentheses (precedence, associativity), keyword/keyword and literal/keyword comparisons, string
+    ordering, regular expressions, the -> operator, comments, odd spacing, wrong case, malformed input -- run through the
+    reference's OWN selection language (its pre-generated flex scanner and bison grammar, Kernel*.cpp, Atom.cpp and the
+    backbone / hydrogen predicates, compiled unmodified from the sources where they lie: oracle/_ref/libloosselect.so) on
+    a 432-atom model.  The native parser selects exactly the same atoms for every accepted string and refuses exactly
+    the strings the reference refuses; so does the Python restatement the other tests use."""
+    import json
+    from oracle import frontend_oracle as fo
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "selection_ref.json")))
+    path = str(tmp_path / "model.pdb")
+    open(path, "w").write(g["pdb"])
+    n = g["natoms"]
+    atoms = fo.read_pdb(path)
+    assert len(atoms) == n
+    out = np.zeros(n, np.uint32)
+    refused = 0
+    for case in g["cases"]:
+        sel = case["selection"]
+        k = fe.lbfe_select(path.encode(), sel.encode(), out.ctypes.data_as(_u32p), n)
+        if "error" in case:
+            refused += 1
+            assert k == -1, (sel, "the reference refuses this:", case["error"])
+            with pytest.raises(Exception):
+                fo.select(atoms, sel)
+            continue
+        assert k >= 0, (sel, fe.lbfe_last_error())
+        want = [i for i, c in enumerate(case["mask"]) if c == "1"]
+        assert out[:k].tolist() == want, sel
+        assert list(fo.select(atoms, sel)) == want, sel
+    assert refused >= 30 and len(g["cases"]) >= 800
+
+
+def test_selection_reference_library_live(tmp_path):
+    from oracle.oracle import RefSelect
+    if not RefSelect.available():
+        pytest.skip("oracle/_ref/libloosselect.so not built (no /root/reference here)")
+    import json
+    from oracle import frontend_oracle as fo
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "selection_ref.json")))
+    path = str(tmp_path / "model.pdb")
+    open(path, "w").write(g["pdb"])
+    R = RefSelect(fo.read_pdb(path))
+    for case in g["cases"][::7]:
+        got, err = R.select(case["selection"])
+        if "error" in case:
+            assert got is None
+        else:
+            assert got == [i for i, c in enumerate(case["mask"]) if c == "1"]
