@@ -161,6 +161,43 @@ int loosb200_rmsds_self_part(loosb200_frames* h, int part, int nparts, float* ou
 int loosb200_rmsds_self_part_device(loosb200_frames* h, int part, int nparts, float* out_dev,
                                     size_t ld, loosb200_stats* stats, int engine);
 
+/* ---- several GPUs of one box, ONE process, ONE result matrix ----
+ * The reference fills one RealMatrix from `np` worker threads inside one process
+ * (Master / Threader, Tools/rmsds.cpp:219-285,387-419,515-535; Tools/multi-rmsds.cpp:395-417).
+ * Here the workers are GPUs: stage the frames once, replicate the staged set to the other
+ * devices (device-to-device over NVLink, no second pass over PCIe), and hand the replicas to the
+ * *_multi calls.  The lower triangle is cut statically into `n` contiguous equal-work ranges of
+ * 40-frame row tiles; nothing is exchanged while computing.  replicas[0] is "rank 0".
+ *   _multi          out = HOST matrix as in loosb200_rmsds_self: every device copies its own row
+ *                   strips and their mirror images straight into it over its own PCIe link, band by
+ *                   band behind its kernel (pinned memory from loosb200_host_alloc() recommended:
+ *                   it is pinned for all devices).
+ *   _multi_device   out_dev = F x F matrix in the HBM of replicas[0]'s device: gather of the row
+ *                   blocks to rank 0 over NVLink.  Default: the other devices' kernels store their
+ *                   tiles there directly (peer stores, the transfer rides under the contraction);
+ *                   LOOSB200_GATHER=copy: local strips pushed by the copy engines band by band.
+ *   _multi_text     the text of loosb200_rmsds_self_text: row bands dealt round-robin to the
+ *                   devices, each formats its bands and ships the text over its own link; the
+ *                   sink receives them in row order.
+ * Results are bit-identical to the one-device calls.  out == NULL: stats only. */
+int loosb200_replicate(const loosb200_frames* src, int device, loosb200_frames** out);
+int loosb200_rmsds_self_multi(loosb200_frames* const* replicas, int n, float* out, size_t ld,
+                              loosb200_stats* stats, int engine);
+int loosb200_rmsds_self_multi_device(loosb200_frames* const* replicas, int n, float* out_dev, size_t ld,
+                                     loosb200_stats* stats, int engine);
+/* a[d] and b[d] on the same device; rows of `a` are split over the devices */
+int loosb200_rmsds_cross_multi(loosb200_frames* const* a, loosb200_frames* const* b, int n, float* out,
+                               size_t ld, loosb200_stats* stats, int engine);
+int loosb200_rmsds_self_multi_text(loosb200_frames* const* replicas, int n, unsigned precision,
+                                   loosb200_sink sink, void* user, loosb200_stats* stats, int engine);
+int loosb200_rmsds_cross_multi_text(loosb200_frames* const* a, loosb200_frames* const* b, int n,
+                                    unsigned precision, loosb200_sink sink, void* user,
+                                    loosb200_stats* stats, int engine);
+/* Page-locked host memory, pinned for every device of the process (result matrices of the host-output
+ * calls: pageable memory works but the copies then run at a fraction of the PCIe rate). */
+void* loosb200_host_alloc(size_t bytes);
+void loosb200_host_free(void* p);
+
 /* ---- single-reference streaming RMSD  (Tools/rmsd2ref.cpp:205-216,238-245) ----
  * For every frame f of `align`: W_f = superposition of the frame's align
  * selection onto ref_align (AtomicGroup::superposition == alignment::kabsch,

@@ -57,6 +57,18 @@ class FrameSet:
         self.F = F
         self.N = nsel if sel_arr is not None else natoms
 
+    @classmethod
+    def _wrap(cls, handle, F, N, device):
+        self = cls.__new__(cls)
+        self._h, self.F, self.N, self.device = handle, F, N, device
+        return self
+
+    def replicate(self, device):
+        """A copy of this staged set on another GPU (device-to-device, loosb200_replicate)."""
+        h = C.c_void_p()
+        check(lib().loosb200_replicate(self._h, int(device), C.byref(h)))
+        return FrameSet._wrap(h, self.F, self.N, int(device))
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             lib().loosb200_free(self._h)
@@ -244,4 +256,94 @@ def rmsds_text(fs, fs_b=None, precision=2, engine="auto", write=None):
         check(lib().loosb200_rmsds_self_text(fs._h, int(precision), cb, None, C.byref(st), capi.ENGINES[engine]))
     else:
         check(lib().loosb200_rmsds_cross_text(fs._h, fs_b._h, int(precision), cb, None, C.byref(st), capi.ENGINES[engine]))
+    return (None if write else b"".join(pieces)), _stats_tuple(st)
+
+
+class PinnedMatrix:
+    """Page-locked host memory that is pinned for every GPU of the process (loosb200_host_alloc),
+    seen as a numpy array (`.array`).  Keep the object alive while the array is in use."""
+
+    def __init__(self, shape, dtype=np.float32, order="F"):
+        count = int(np.prod(shape))
+        nbytes = max(1, count * np.dtype(dtype).itemsize)
+        self._p = lib().loosb200_host_alloc(nbytes)
+        if not self._p:
+            raise MemoryError("loosb200_host_alloc(%d)" % nbytes)
+        buf = (C.c_char * nbytes).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape, order=order)
+
+    def free(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            lib().loosb200_host_free(self._p)
+            self._p = None
+
+    __del__ = free
+
+
+def _handles(sets):
+    arr = (C.c_void_p * len(sets))(*[fs._h for fs in sets])
+    return arr
+
+
+def rmsds_multi(replicas, out=None, noout=False, engine="auto", want_stats=True):
+    """rmsds() on several GPUs of one process: `replicas` are FrameSets of the same frames on
+    different devices (fs.replicate(d)); replicas[0] is rank 0.  out: None (a Fortran-ordered numpy
+    matrix is returned), a preallocated host matrix, or a torch CUDA tensor on replicas[0]'s device
+    (gather of the row blocks into rank 0's HBM over NVLink)."""
+    L = lib()
+    st = Stats()
+    sp = C.byref(st) if want_stats else None
+    eng = capi.ENGINES[engine]
+    hs = _handles(replicas)
+    F = replicas[0].F
+    if noout:
+        check(L.loosb200_rmsds_self_multi(hs, len(replicas), None, 0, sp, eng))
+        return None, _stats_tuple(st)
+    if out is not None and hasattr(out, "is_cuda") and out.is_cuda:
+        assert out.shape == (F, F) and out.is_contiguous() and (out.device.index or 0) == replicas[0].device
+        check(L.loosb200_rmsds_self_multi_device(hs, len(replicas), _dev_ptr(out), F, sp, eng))
+        return out, _stats_tuple(st)
+    if out is None:
+        out = np.empty((F, F), dtype=np.float32, order="F")
+    assert out.dtype == np.float32 and out.shape == (F, F) and out.flags.f_contiguous
+    check(L.loosb200_rmsds_self_multi(hs, len(replicas), out.ctypes.data_as(C.c_void_p), F, sp, eng))
+    return out, _stats_tuple(st)
+
+
+def rmsds_cross_multi(a_replicas, b_replicas, out=None, noout=False, engine="auto", want_stats=True):
+    """rmsds_cross() with the rows of `a` split over several GPUs."""
+    L = lib()
+    st = Stats()
+    sp = C.byref(st) if want_stats else None
+    eng = capi.ENGINES[engine]
+    ha, hb = _handles(a_replicas), _handles(b_replicas)
+    FA, FB = a_replicas[0].F, b_replicas[0].F
+    if noout:
+        check(L.loosb200_rmsds_cross_multi(ha, hb, len(a_replicas), None, 0, sp, eng))
+        return None, _stats_tuple(st)
+    if out is None:
+        out = np.empty((FA, FB), dtype=np.float32, order="F")
+    assert out.dtype == np.float32 and out.shape == (FA, FB) and out.flags.f_contiguous
+    check(L.loosb200_rmsds_cross_multi(ha, hb, len(a_replicas), out.ctypes.data_as(C.c_void_p), FA, sp, eng))
+    return out, _stats_tuple(st)
+
+
+def rmsds_text_multi(replicas, b_replicas=None, precision=2, engine="auto", write=None):
+    """rmsds_text() with the row bands dealt to several GPUs; same bytes."""
+    pieces = []
+    emit = write or pieces.append
+
+    def _sink(_user, data, n):
+        emit(C.string_at(data, n))
+        return 0
+
+    cb = capi.SINK(_sink)
+    st = Stats()
+    if b_replicas is None:
+        check(lib().loosb200_rmsds_self_multi_text(_handles(replicas), len(replicas), int(precision), cb, None,
+                                                   C.byref(st), capi.ENGINES[engine]))
+    else:
+        check(lib().loosb200_rmsds_cross_multi_text(_handles(replicas), _handles(b_replicas), len(replicas),
+                                                    int(precision), cb, None, C.byref(st), capi.ENGINES[engine]))
     return (None if write else b"".join(pieces)), _stats_tuple(st)

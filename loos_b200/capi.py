@@ -63,6 +63,14 @@ SIGNATURES = {
     "loosb200_rmsds_self_text": (_i, [_vp, C.c_uint, SINK, _vp, _sp, _i]),
     "loosb200_rmsds_cross_text": (_i, [_vp, _vp, C.c_uint, SINK, _vp, _sp, _i]),
     "loosb200_last_timing": (_i, [_vp, _dp, _dp]),
+    "loosb200_replicate": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "loosb200_rmsds_self_multi": (_i, [C.POINTER(_vp), _i, _vp, _sz, _sp, _i]),
+    "loosb200_rmsds_self_multi_device": (_i, [C.POINTER(_vp), _i, _vp, _sz, _sp, _i]),
+    "loosb200_rmsds_cross_multi": (_i, [C.POINTER(_vp), C.POINTER(_vp), _i, _vp, _sz, _sp, _i]),
+    "loosb200_rmsds_self_multi_text": (_i, [C.POINTER(_vp), _i, C.c_uint, SINK, _vp, _sp, _i]),
+    "loosb200_rmsds_cross_multi_text": (_i, [C.POINTER(_vp), C.POINTER(_vp), _i, C.c_uint, SINK, _vp, _sp, _i]),
+    "loosb200_host_alloc": (_vp, [_sz]),
+    "loosb200_host_free": (None, [_vp]),
 }
 
 _lib = None

@@ -5,7 +5,9 @@
 
 #include <algorithm>
 #include <map>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -187,38 +189,78 @@ static int pick_engine(int engine, const loosb200_frames* a) {
   return LOOSB200_ERR_INVALID;
 }
 
-enum class OutKind { None, Host, Device };
+// Equal-work cut of the row tiles [0, T) into `nparts` CONTIGUOUS ranges: row tile t of the self
+// matrix costs (t + 1) tiles, of a rectangle a constant.  Contiguous ranges (instead of the
+// interleaved deal above) make every part's share a few wide rectangles of the matrix, which is
+// what the copy engines want when the parts are gathered into one matrix over PCIe or NVLink.
+std::vector<uint32_t> contiguous_cuts(size_t F, int nparts, bool self) {
+  const uint32_t T = (uint32_t)((F + TILE_FRAMES - 1) / TILE_FRAMES);
+  std::vector<uint32_t> cuts(nparts + 1, T);
+  cuts[0] = 0;
+  const double total = self ? 0.5 * (double)T * (T + 1) : (double)T;
+  uint32_t t = 0;
+  for (int p = 1; p < nparts; ++p) {
+    const double want = total * p / nparts;
+    while (t < T && (self ? 0.5 * (double)t * (t + 1) : (double)t) < want) ++t;
+    cuts[p] = t;
+  }
+  return cuts;
+}
 
 // The one driver behind every all-to-all entry point.
-static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric, bool packed,
-                     const std::vector<uint32_t>& rows, float* out, OutKind okind, size_t ld,
-                     loosb200_stats* stats, int engine) {
+//   okind None    stats only, the matrix never leaves the SMs
+//         Device  `out` is the matrix (or the packed rows) in memory the kernel can store to: the
+//                 handle's own HBM, or a peer's (NVLink stores) -- written directly, one launch
+//         Copy    `out` is the matrix somewhere the copy engines reach (pinned or pageable host memory,
+//                 another GPU's HBM): the job runs as up to 16 bands, heaviest rows first, every band
+//                 into its own compact strips, which are copied out behind the next band's kernel
+int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric, bool packed,
+              const std::vector<uint32_t>& rows, float* out, OutKind okind, size_t ld,
+              loosb200_stats* stats, int engine) {
   LB_CUDA(cudaSetDevice(a->device));
+  const bool engine_auto = engine == LOOSB200_ENGINE_AUTO;
   engine = pick_engine(engine, a);
   if (engine < 0) return engine;
   if (engine == LOOSB200_ENGINE_TENSOR) {
     int rc;
     if (self) {
-      if ((rc = ensure_quantised(a, INT_MIN))) return rc;
+      rc = ensure_quantised(a, INT_MIN);
     } else {
       // both sets must share one fixed-point unit: quantise each, then re-quantise
       // the finer one on the coarser grid
-      if ((rc = ensure_quantised(a, INT_MIN))) return rc;
-      if ((rc = ensure_quantised(b, INT_MIN))) return rc;
-      const int e = std::max(a->unit_log2, b->unit_log2);
-      if ((rc = ensure_quantised(a, e))) return rc;
-      if ((rc = ensure_quantised(b, e))) return rc;
+      if (!(rc = ensure_quantised(a, INT_MIN)) && !(rc = ensure_quantised(b, INT_MIN))) {
+        const int e = std::max(a->unit_log2, b->unit_log2);
+        if (!(rc = ensure_quantised(a, e))) rc = ensure_quantised(b, e);
+      }
     }
+    // NaN / Inf coordinates have no fixed-point image; the fp64 engine propagates them like the reference
+    if (rc == LOOSB200_ERR_NUMERICAL && engine_auto) engine = LOOSB200_ENGINE_FP64;
+    else if (rc) return rc;
   }
   cudaStream_t st = a->stream;
   const size_t FA = a->F, FB = b->F;
   const uint32_t col_tiles = (uint32_t)((FB + TILE_FRAMES - 1) / TILE_FRAMES);
+  const bool copy = okind == OutKind::Copy;
+  const bool strips = copy && !packed;  // compact per-band strips (rows must be contiguous row tiles)
+  if (strips)
+    for (size_t r = 1; r < rows.size(); ++r)
+      if (rows[r] != rows[r - 1] + 1) return LOOSB200_ERR_INVALID;
   const size_t out_rows = packed ? rows.size() * TILE_FRAMES : 0;  // packed: rows x ld (row-major)
-  const size_t out_cols = packed ? 0 : FB;                          // else: FB columns of ld
-  const size_t dev_ld = (okind == OutKind::Host) ? (packed ? FB : FA) : ld;
 
-  const int maxbands = (okind == OutKind::Host) ? 16 : 1;
+  const int maxbands = copy ? 16 : 1;
   Bands B = make_bands(rows, self, col_tiles, maxbands);
+  // band k covers matrix rows [bA[k], bB[k]); strip mode: its row strip S_k and column strip T_k
+  std::vector<size_t> bA(B.bands.size()), bB(B.bands.size()), offS(B.bands.size()), offT(B.bands.size());
+  size_t strip_floats = 0;
+  for (size_t k = 0; k < B.bands.size(); ++k) {
+    const Bands::Band& bd = B.bands[k];
+    bA[k] = (size_t)B.rows[bd.r0] * TILE_FRAMES;
+    bB[k] = std::min(FA, ((size_t)B.rows[bd.r1 - 1] + 1) * TILE_FRAMES);
+    if (bB[k] < bA[k]) bB[k] = bA[k];
+    const size_t h = bB[k] - bA[k];
+    offS[k] = strip_floats; strip_floats += h * (self ? bB[k] : FB);
+    offT[k] = strip_floats; strip_floats += (self && symmetric) ? h * bA[k] : 0;
+  }
 
   uint32_t *d_rows = nullptr, *d_prefix = nullptr;
   float* d_out = nullptr;
@@ -229,15 +271,15 @@ static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool sym
   auto cleanup = [&]() {
     dev_release(d_rows); dev_release(d_prefix); dev_release(d_stats);
     for (void* p : scratch) dev_release(p);
-    if (okind == OutKind::Host) dev_release(d_out);
+    if (copy) dev_release(d_out);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     for (auto e : evs) if (e) cudaEventDestroy(e);
   };
   bool ok = dev_alloc_t(&d_rows, sizeof(uint32_t) * std::max<size_t>(1, B.rows.size())) == cudaSuccess &&
             dev_alloc_t(&d_prefix, sizeof(uint32_t) * std::max<size_t>(1, B.prefix.size())) == cudaSuccess &&
             dev_alloc_t(&d_stats, 2 * sizeof(double)) == cudaSuccess;
-  if (ok && okind == OutKind::Host) {
-    const size_t n = packed ? out_rows * dev_ld : out_cols * dev_ld;
+  if (ok && copy) {
+    const size_t n = packed ? out_rows * FB : strip_floats;
     ok = dev_alloc_t(&d_out, sizeof(float) * std::max<size_t>(1, n)) == cudaSuccess &&
          cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (auto& e : evs) if (ok) ok = cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
@@ -256,14 +298,23 @@ static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool sym
     const Bands::Band& bd = B.bands[k];
     PairJob job;
     job.a = a; job.b = b; job.self = self; job.symmetric = symmetric;
-    job.ld = dev_ld;
     job.rows_host = B.rows.data() + bd.r0;
     job.row_tiles_dev = d_rows + bd.r0;
     job.tile_prefix_dev = d_prefix + bd.p0;
     job.n_row_tiles = bd.r1 - bd.r0;
     job.n_tiles = bd.ntiles;
     job.packed_rows = packed;
-    job.out = d_out ? (packed ? d_out + (size_t)bd.r0 * TILE_FRAMES * dev_ld : d_out) : nullptr;
+    if (!d_out) {
+      job.out = nullptr; job.ld = ld;
+    } else if (strips) {
+      job.out = d_out + offS[k]; job.ld = bB[k] - bA[k]; job.row_off = bA[k];
+      job.out_t = d_out + offT[k]; job.ld_t = bA[k];
+    } else if (packed) {
+      job.ld = copy ? FB : ld;
+      job.out = d_out + (size_t)bd.r0 * TILE_FRAMES * job.ld;
+    } else {
+      job.out = d_out; job.ld = ld;
+    }
     job.stats_dev = stats ? d_stats : nullptr;
     job.scratch = &scratch;
     while (a->timing.kev.size() < 2 * (k + 1)) { cudaEvent_t e = nullptr; cudaEventCreate(&e); a->timing.kev.push_back(e); }
@@ -277,35 +328,30 @@ static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool sym
       rc = launch_pairs_fp64(job, st);
       launches += 1;
     }
-    if (rc == LOOSB200_OK && okind == OutKind::Host) {
+    if (rc == LOOSB200_OK && copy) {
       cudaEventRecord(evs[k], st);
       cudaStreamWaitEvent(copy_stream, evs[k], 0);
       if (packed) {
         // rows of the band are contiguous in the packed buffer; only columns j < i exist
         const size_t r_lo = (size_t)bd.r0 * TILE_FRAMES, nr = (size_t)(bd.r1 - bd.r0) * TILE_FRAMES;
         const size_t width = std::min(FB, ((size_t)B.rows[bd.r1 - 1] + 1) * TILE_FRAMES);
-        cudaMemcpy2DAsync(out + r_lo * ld, ld * sizeof(float), d_out + r_lo * dev_ld, dev_ld * sizeof(float),
-                          width * sizeof(float), nr, cudaMemcpyDeviceToHost, copy_stream);
-      } else if (self) {
-        // Everything that involves the band's rows [R0, R1) is final once the band is done:
-        // the row strip rows [R0,R1) x cols [0,R1) and its mirror cols [R0,R1) x rows [0,R0).
-        // Both are copied now, so the D2H volume of a band is proportional to its work
-        // and only the last band's copy is exposed.
-        const size_t R0 = (size_t)B.rows[bd.r0] * TILE_FRAMES;
-        const size_t R1 = std::min(FA, ((size_t)B.rows[bd.r1 - 1] + 1) * TILE_FRAMES);
-        cudaMemcpy2DAsync(out + R0, ld * sizeof(float), d_out + R0, dev_ld * sizeof(float),
-                          (R1 - R0) * sizeof(float), R1, cudaMemcpyDeviceToHost, copy_stream);
-        if (R0 > 0)
-          cudaMemcpy2DAsync(out + R0 * ld, ld * sizeof(float), d_out + R0 * dev_ld, dev_ld * sizeof(float),
-                            R0 * sizeof(float), R1 - R0, cudaMemcpyDeviceToHost, copy_stream);
+        cudaMemcpy2DAsync(out + r_lo * ld, ld * sizeof(float), d_out + r_lo * FB, FB * sizeof(float),
+                          width * sizeof(float), nr, cudaMemcpyDefault, copy_stream);
+      } else if (bB[k] > bA[k]) {
+        // Everything that involves the band's rows [A, B) is final once the band is done: the row
+        // strip rows [A,B) x cols [0,B) (all columns in rectangle mode) and, for the symmetric matrix,
+        // its mirror cols [A,B) x rows [0,A).  Both go out now, so the copy volume of a band is
+        // proportional to its work and only the last (lightest) band's copy is exposed.
+        const size_t A = bA[k], Bk = bB[k], h = Bk - A;
+        cudaMemcpy2DAsync(out + A, ld * sizeof(float), d_out + offS[k], h * sizeof(float),
+                          h * sizeof(float), self ? Bk : FB, cudaMemcpyDefault, copy_stream);
+        if (self && symmetric && A > 0)
+          cudaMemcpy2DAsync(out + A * ld, ld * sizeof(float), d_out + offT[k], A * sizeof(float),
+                            A * sizeof(float), h, cudaMemcpyDefault, copy_stream);
       }
     }
   }
   cudaEventRecord(a->timing.ev[2], st);
-  if (rc == LOOSB200_OK && okind == OutKind::Host && !packed && !self) {
-    cudaMemcpy2DAsync(out, ld * sizeof(float), d_out, dev_ld * sizeof(float), FA * sizeof(float), FB,
-                      cudaMemcpyDeviceToHost, st);
-  }
   double hs[2] = {0.0, 0.0};
   if (stats) cudaMemcpyAsync(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st);
   cudaEventRecord(a->timing.ev[3], st);
@@ -334,6 +380,12 @@ static int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool sym
   }
   a->timing.launches = launches; a->timing.valid = true;
   return LOOSB200_OK;
+}
+
+std::vector<uint32_t> row_tile_range(uint32_t t0, uint32_t t1) {
+  std::vector<uint32_t> r;
+  for (uint32_t t = t0; t < t1; ++t) r.push_back(t);
+  return r;
 }
 
 }  // namespace loosb200
@@ -402,7 +454,7 @@ static std::vector<uint32_t> all_rows(size_t F) { return part_row_tiles(F, 0, 1)
 extern "C" int loosb200_rmsds_self(loosb200_frames* h, float* out, size_t ld, loosb200_stats* stats, int engine) {
   int rc = check_self(h, out, ld);
   if (rc) return rc;
-  return run_pairs(h, h, true, true, false, all_rows(h->F), out, out ? OutKind::Host : OutKind::None, ld, stats, engine);
+  return run_pairs(h, h, true, true, false, all_rows(h->F), out, out ? OutKind::Copy : OutKind::None, ld, stats, engine);
 }
 
 extern "C" int loosb200_rmsds_self_device(loosb200_frames* h, float* out_dev, size_t ld, loosb200_stats* stats, int engine) {
@@ -422,7 +474,7 @@ static int check_cross(loosb200_frames* a, loosb200_frames* b, float* out, size_
 extern "C" int loosb200_rmsds_cross(loosb200_frames* a, loosb200_frames* b, float* out, size_t ld, loosb200_stats* stats, int engine) {
   int rc = check_cross(a, b, out, ld);
   if (rc) return rc;
-  return run_pairs(a, b, false, false, false, all_rows(a->F), out, out ? OutKind::Host : OutKind::None, ld, stats, engine);
+  return run_pairs(a, b, false, false, false, all_rows(a->F), out, out ? OutKind::Copy : OutKind::None, ld, stats, engine);
 }
 
 extern "C" int loosb200_rmsds_cross_device(loosb200_frames* a, loosb200_frames* b, float* out_dev, size_t ld, loosb200_stats* stats, int engine) {
@@ -476,6 +528,144 @@ static int pairs_text(loosb200_frames* a, loosb200_frames* b, bool self, unsigne
   return rc;
 }
 
+// ---- the same text from several GPUs ------------------------------------------------------------
+// Bands of rows (about one 256 MB batch of text each) are dealt round-robin to the devices; every
+// device computes its band as a rectangle against all columns, formats it and copies the text to
+// the host over its own PCIe link, and the bands are handed to the sink in row order through a
+// turnstile.  Each device is at most one band ahead of the sink, so n bands are in flight.
+namespace {
+struct Turnstile {
+  std::mutex mu;
+  std::condition_variable cv;
+  size_t next = 0;
+  bool failed = false;
+  loosb200_sink sink = nullptr;
+  void* user = nullptr;
+};
+struct TurnUser { Turnstile* t; size_t band; };
+int turnstile_sink(void* u, const char* data, size_t n) {
+  TurnUser* tu = static_cast<TurnUser*>(u);
+  Turnstile* t = tu->t;
+  {
+    std::unique_lock<std::mutex> lk(t->mu);
+    t->cv.wait(lk, [&] { return t->next == tu->band || t->failed; });
+    if (t->failed) return 1;
+  }
+  // only the band whose turn it is gets here, and the calls of one band are sequential
+  const int r = t->sink(t->user, data, n);
+  if (r) { std::lock_guard<std::mutex> lk(t->mu); t->failed = true; t->cv.notify_all(); }
+  return r;
+}
+}  // namespace
+
+static int pairs_text_multi(loosb200_frames* const* a, loosb200_frames* const* b, int ndev, bool self,
+                            unsigned precision, loosb200_sink sink, void* user, loosb200_stats* stats, int engine) {
+  if (!sink) return LOOSB200_ERR_INVALID;
+  if (precision > 9) return LOOSB200_ERR_UNSUPPORTED;
+  const size_t m = a[0]->F, n = b[0]->F;
+  const unsigned prec = precision == 0 ? 1 : precision;
+  const size_t worst_row = n * (size_t)(prec + 7) + 1;
+  size_t band_rows = std::max<size_t>(1, ((size_t)256 << 20) / worst_row);
+  if (const char* env = getenv("LOOSB200_TEXT_BAND_ROWS")) { const int v = atoi(env); if (v > 0) band_rows = (size_t)v; }
+  band_rows = std::max<size_t>(TILE_FRAMES, band_rows / TILE_FRAMES * TILE_FRAMES);
+  const size_t nbands = (m + band_rows - 1) / band_rows;
+  int rc = LOOSB200_OK;
+  // statistics: the triangle (self) split over the devices, no output; rectangles report their own
+  if (stats && self) {
+    std::vector<loosb200_stats> ps(ndev);
+    const std::vector<uint32_t> cuts = contiguous_cuts(m, ndev, true);
+    std::vector<int> rcs(ndev, LOOSB200_OK);
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev; ++d)
+      th.emplace_back([&, d]() {
+        ps[d].sum = 0.0; ps[d].max = 0.0; ps[d].count = 0;
+        const std::vector<uint32_t> rows = row_tile_range(cuts[d], cuts[d + 1]);
+        if (!rows.empty()) rcs[d] = run_pairs(a[d], a[d], true, false, false, rows, nullptr, OutKind::None, m, &ps[d], engine);
+      });
+    for (auto& t : th) t.join();
+    stats->sum = 0.0; stats->max = 0.0; stats->count = 0;
+    for (int d = 0; d < ndev; ++d) {
+      if (rcs[d]) return rcs[d];
+      stats->sum += ps[d].sum; stats->max = std::max(stats->max, ps[d].max); stats->count += ps[d].count;
+    }
+  }
+  if ((rc = matrix_text_header(m, n, sink, user))) return rc;
+  Turnstile ts;
+  ts.sink = sink; ts.user = user;
+  std::vector<int> rcs(ndev, LOOSB200_OK);
+  std::vector<loosb200_stats> ps(ndev);
+  std::vector<std::thread> th;
+  for (int d = 0; d < ndev; ++d)
+    th.emplace_back([&, d]() {
+      ps[d].sum = 0.0; ps[d].max = 0.0; ps[d].count = 0;
+      int r = LOOSB200_OK;
+      float* d_band = nullptr;
+      if (cudaSetDevice(a[d]->device) != cudaSuccess || dev_alloc_t(&d_band, sizeof(float) * band_rows * n) != cudaSuccess) {
+        cudaGetLastError();
+        r = LOOSB200_ERR_NOMEM;
+      }
+      for (size_t k = (size_t)d; k < nbands; k += (size_t)ndev) {
+        const size_t R0 = k * band_rows, R1 = std::min(m, R0 + band_rows);
+        if (r == LOOSB200_OK) {
+          const std::vector<uint32_t> tiles = row_tile_range((uint32_t)(R0 / TILE_FRAMES), (uint32_t)((R1 + TILE_FRAMES - 1) / TILE_FRAMES));
+          loosb200_stats bst;
+          r = run_pairs(a[d], b[d], false, false, true, tiles, d_band, OutKind::Device, n, (stats && !self) ? &bst : nullptr, engine);
+          if (r == LOOSB200_OK && stats && !self) { ps[d].sum += bst.sum; ps[d].max = std::max(ps[d].max, bst.max); ps[d].count += bst.count; }
+        }
+        if (r == LOOSB200_OK) {
+          if (self) zero_band_diagonal(d_band, n, R0, (uint32_t)(R1 - R0), a[d]->stream);
+          TurnUser tu{&ts, k};
+          r = stream_rows_text(d_band, n, R1 - R0, n, precision, turnstile_sink, &tu, a[d]->stream);
+        }
+        std::lock_guard<std::mutex> lk(ts.mu);
+        if (r != LOOSB200_OK) ts.failed = true;
+        else ts.next = k + 1;
+        ts.cv.notify_all();
+        if (r != LOOSB200_OK) break;
+      }
+      dev_release(d_band);
+      rcs[d] = r;
+    });
+  for (auto& t : th) t.join();
+  for (int d = 0; d < ndev; ++d) if (rcs[d]) return rcs[d];
+  if (stats && !self) {
+    stats->sum = 0.0; stats->max = 0.0; stats->count = 0;
+    for (int d = 0; d < ndev; ++d) { stats->sum += ps[d].sum; stats->max = std::max(stats->max, ps[d].max); stats->count += ps[d].count; }
+  }
+  return LOOSB200_OK;
+}
+
+static int check_text_replicas(loosb200_frames* const* r, int n) {
+  if (!r || n < 1) return LOOSB200_ERR_INVALID;
+  for (int d = 0; d < n; ++d) {
+    if (!r[d] || r[d]->stager) return LOOSB200_ERR_INVALID;
+    if (r[d]->F != r[0]->F || r[d]->N != r[0]->N) return LOOSB200_ERR_SIZE_MISMATCH;
+  }
+  return LOOSB200_OK;
+}
+
+extern "C" int loosb200_rmsds_self_multi_text(loosb200_frames* const* replicas, int n, unsigned precision,
+                                              loosb200_sink sink, void* user, loosb200_stats* stats, int engine) {
+  int rc = check_text_replicas(replicas, n);
+  if (rc) return rc;
+  if (n == 1) return pairs_text(replicas[0], replicas[0], true, precision, sink, user, stats, engine);
+  return pairs_text_multi(replicas, replicas, n, true, precision, sink, user, stats, engine);
+}
+
+extern "C" int loosb200_rmsds_cross_multi_text(loosb200_frames* const* a, loosb200_frames* const* b, int n,
+                                               unsigned precision, loosb200_sink sink, void* user,
+                                               loosb200_stats* stats, int engine) {
+  int rc = check_text_replicas(a, n);
+  if (!rc) rc = check_text_replicas(b, n);
+  if (rc) return rc;
+  for (int d = 0; d < n; ++d) {
+    if (a[d]->device != b[d]->device) return LOOSB200_ERR_INVALID;
+    if (a[d]->N != b[d]->N) return LOOSB200_ERR_SIZE_MISMATCH;
+  }
+  if (n == 1) return pairs_text(a[0], b[0], false, precision, sink, user, stats, engine);
+  return pairs_text_multi(a, b, n, false, precision, sink, user, stats, engine);
+}
+
 extern "C" int loosb200_rmsds_self_text(loosb200_frames* h, unsigned precision, loosb200_sink sink, void* user,
                                         loosb200_stats* stats, int engine) {
   if (!h) return LOOSB200_ERR_INVALID;
@@ -513,7 +703,7 @@ static int check_part(loosb200_frames* h, int part, int nparts, float* out, size
 extern "C" int loosb200_rmsds_self_part(loosb200_frames* h, int part, int nparts, float* out, size_t ld, loosb200_stats* stats, int engine) {
   int rc = check_part(h, part, nparts, out, ld);
   if (rc) return rc;
-  return run_pairs(h, h, true, false, true, part_row_tiles(h->F, part, nparts), out, out ? OutKind::Host : OutKind::None, ld, stats, engine);
+  return run_pairs(h, h, true, false, true, part_row_tiles(h->F, part, nparts), out, out ? OutKind::Copy : OutKind::None, ld, stats, engine);
 }
 
 extern "C" int loosb200_rmsds_self_part_device(loosb200_frames* h, int part, int nparts, float* out_dev, size_t ld, loosb200_stats* stats, int engine) {

@@ -32,6 +32,8 @@ constexpr int K_CHUNK = 128;   // atoms (bytes of int8) per pipeline stage = one
 constexpr int NUM_SLICES = 3;  // signed 8-bit digits of the 24-bit fixed-point coordinate
 // int32 accumulators hold up to 3 slice products of magnitude <= 2^14 per atom.
 constexpr size_t TENSOR_MAX_ATOMS = 43000;
+// largest magnitude three balanced base-256 digits in [-128, 127] can hold on the positive side
+constexpr long long Q_MAX = 127LL * 65793LL;  // 8355711
 
 void set_last_error(const std::string& s);
 
@@ -110,8 +112,15 @@ struct PairJob {
   const loosb200_frames* b;   // == a for self mode
   bool self;                  // lower triangle only (j < i), else full rectangle
   bool symmetric;             // self mode: also store M(j,i); rows unpacked
-  float* out;                 // device, may be null (stats only)
+  float* out;                 // device (or peer-mapped), may be null (stats only)
   size_t ld;
+  // Strip delivery (self + symmetric, contiguous rows [row_off, B) of the matrix): `out` is the compact
+  // row strip S, column-major with ld = B - row_off: M(i,j) at out[j*ld + (i - row_off)], and the mirror
+  // entry M(j,i) goes into S as well when j >= row_off (the band's diagonal block), else into the
+  // column strip out_t[(i - row_off)*ld_t + j].  row_off = 0 / out_t = null is the plain F x F matrix.
+  size_t row_off = 0;
+  float* out_t = nullptr;
+  size_t ld_t = 0;
   // row blocks (of TILE_FRAMES frames of `a`) this launch covers, ascending
   const uint32_t* rows_host;       // [n_row_tiles] same list on the host
   const uint32_t* row_tiles_dev;   // [n_row_tiles]
@@ -126,6 +135,14 @@ struct PairJob {
 };
 
 int ensure_quantised(loosb200_frames* h, int force_unit_log2 /* INT_MIN: auto */);
+int alloc_frames(loosb200_frames** out, size_t F, size_t N, int device);  // stage.cu: empty frame set
+// capi.cu: the driver behind every all-to-all entry point (see there), and the work split of multi.cu
+enum class OutKind { None, Copy, Device };
+int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric, bool packed,
+              const std::vector<uint32_t>& rows, float* out, OutKind okind, size_t ld,
+              loosb200_stats* stats, int engine);
+std::vector<uint32_t> contiguous_cuts(size_t F, int nparts, bool self);
+std::vector<uint32_t> row_tile_range(uint32_t t0, uint32_t t1);
 int launch_pairs_fp64(const PairJob& job, cudaStream_t st);
 int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches);
 bool tensor_path_available();

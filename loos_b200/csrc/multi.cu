@@ -1,0 +1,175 @@
+// Several GPUs in one process: the reference fills ONE matrix from np worker threads
+// (Master / Threader, Tools/rmsds.cpp:219-285,387-419; multi-rmsds.cpp:395-417); here the workers are
+// the GPUs of one box.  Frame pairs are independent, so there is no exchange step while computing:
+// every device holds a replica of the staged frames (loosb200_replicate: one H2D upload, then
+// NVLink copies), computes a CONTIGUOUS equal-work range of row tiles of the lower triangle, and
+// delivers its part of the matrix itself:
+//   host output     every device copies its row strips and their mirror images straight into the
+//                   caller's matrix over ITS OWN PCIe link, band by band behind its kernel;
+//   device output   the matrix is gathered in the HBM of replicas[0]'s device over NVLink: either the
+//                   other devices' kernels store their tiles there directly (peer stores, the
+//                   transfer rides under the contraction tile by tile), or they fill local strips
+//                   that the copy engines push band by band (LOOSB200_GATHER=copy).
+#include <limits.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <new>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace loosb200 {
+
+// peer access src -> dst (kernels and copy engines of `dev` may touch memory of `peer`)
+static bool enable_peer(int dev, int peer) {
+  if (dev == peer) return true;
+  int can = 0;
+  if (cudaDeviceCanAccessPeer(&can, dev, peer) != cudaSuccess || !can) { cudaGetLastError(); return false; }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  cudaSetDevice(dev);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  cudaSetDevice(cur);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return true; }
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return true;
+}
+
+static int check_replicas(loosb200_frames* const* r, int n) {
+  if (!r || n < 1) return LOOSB200_ERR_INVALID;
+  for (int d = 0; d < n; ++d) {
+    if (!r[d] || r[d]->stager) return LOOSB200_ERR_INVALID;
+    if (r[d]->F != r[0]->F || r[d]->N != r[0]->N) return LOOSB200_ERR_SIZE_MISMATCH;
+    // (two replicas on one device are allowed: wasteful, but it lets a one-GPU box run this path)
+  }
+  return LOOSB200_OK;
+}
+
+// Run fn(d) for d = 0..n-1 on n host threads (each binds its device inside run_pairs); first error wins.
+template <class Fn>
+static int on_all_devices(int n, Fn fn) {
+  std::vector<int> rc(n, LOOSB200_OK);
+  std::vector<std::string> msg(n);
+  std::vector<std::thread> th;
+  for (int d = 1; d < n; ++d)
+    th.emplace_back([&, d]() { rc[d] = fn(d); if (rc[d]) msg[d] = loosb200_last_error(); });
+  rc[0] = fn(0);
+  for (auto& t : th) t.join();
+  for (int d = 0; d < n; ++d)
+    if (rc[d]) { if (d) set_last_error(msg[d]); return rc[d]; }
+  return LOOSB200_OK;
+}
+
+static void merge_stats(loosb200_stats* total, const std::vector<loosb200_stats>& parts) {
+  if (!total) return;
+  total->sum = 0.0; total->max = 0.0; total->count = 0;
+  for (const loosb200_stats& s : parts) {
+    total->sum += s.sum;
+    total->max = std::max(total->max, s.max);
+    total->count += s.count;
+  }
+}
+
+// All parts of one all-to-all job.  kind Copy: out is the caller's matrix (host memory, or the HBM of
+// any device): every device delivers its strips there.  kind Device: out lives in the HBM of
+// a[0]'s device; that device writes its share directly, the others by peer stores or strip copies.
+static int pairs_multi(loosb200_frames* const* a, loosb200_frames* const* b, int n, bool self, float* out,
+                       OutKind kind, size_t ld, loosb200_stats* stats, int engine) {
+  const size_t F = a[0]->F;
+  const std::vector<uint32_t> cuts = contiguous_cuts(F, n, self);
+  bool peer_stores = false;
+  if (kind == OutKind::Device) {
+    const char* g = getenv("LOOSB200_GATHER");
+    peer_stores = !(g && strcmp(g, "copy") == 0);
+    for (int d = 1; d < n; ++d)
+      if (!enable_peer(a[d]->device, a[0]->device)) return LOOSB200_ERR_UNSUPPORTED;
+  }
+  std::vector<loosb200_stats> ps(n);
+  int rc = on_all_devices(n, [&](int d) -> int {
+    const std::vector<uint32_t> rows = row_tile_range(cuts[d], cuts[d + 1]);
+    loosb200_stats* st = stats ? &ps[d] : nullptr;
+    if (st) { st->sum = 0.0; st->max = 0.0; st->count = 0; }
+    if (rows.empty()) return LOOSB200_OK;
+    OutKind k = kind;
+    if (kind == OutKind::Device && d > 0 && !peer_stores) k = OutKind::Copy;
+    return run_pairs(a[d], b ? b[d] : a[d], self, self, false, rows, out, k, ld, st, engine);
+  });
+  if (rc == LOOSB200_OK) merge_stats(stats, ps);
+  return rc;
+}
+
+}  // namespace loosb200
+
+using namespace loosb200;
+
+extern "C" int loosb200_replicate(const loosb200_frames* src, int device, loosb200_frames** out) {
+  if (!src || !out || src->stager) return LOOSB200_ERR_INVALID;
+  if (device < 0 || device >= loosb200_device_count()) return LOOSB200_ERR_NO_DEVICE;
+  // an empty staged set on `device`, then plane-for-plane copies (peer-to-peer over NVLink when the
+  // devices allow it, through the host otherwise); the digit planes are re-derived there on first use
+  // from the same fp32 planes and centroids, hence bit-identical
+  loosb200_frames* h = nullptr;
+  int rc = alloc_frames(&h, src->F, src->N, device);
+  if (rc) return rc;
+  enable_peer(device, src->device);
+  enable_peer(src->device, device);
+  LB_CUDA(cudaSetDevice(device));
+  cudaStream_t st = h->stream;
+  cudaError_t e = cudaMemcpyPeerAsync(h->raw, device, src->raw, src->device, sizeof(float) * src->F * 3 * src->Npad, st);
+  if (e == cudaSuccess) e = cudaMemcpyPeerAsync(h->centroid, device, src->centroid, src->device, sizeof(double) * 3 * src->F, st);
+  if (e == cudaSuccess) e = cudaMemcpyPeerAsync(h->gd, device, src->gd, src->device, sizeof(double) * src->F, st);
+  if (e == cudaSuccess) e = cudaMemcpyPeerAsync(h->maxabs, device, src->maxabs, src->device, sizeof(float) * src->F, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { loosb200_free(h); return cuda_fail(e, "replicate", __FILE__, __LINE__); }
+  h->timing.valid = false;
+  *out = h;
+  return LOOSB200_OK;
+}
+
+extern "C" int loosb200_rmsds_self_multi(loosb200_frames* const* replicas, int n, float* out, size_t ld,
+                                         loosb200_stats* stats, int engine) {
+  int rc = check_replicas(replicas, n);
+  if (rc) return rc;
+  if (out && ld < replicas[0]->F) return LOOSB200_ERR_INVALID;
+  return pairs_multi(replicas, nullptr, n, true, out, out ? OutKind::Copy : OutKind::None, ld, stats, engine);
+}
+
+extern "C" int loosb200_rmsds_self_multi_device(loosb200_frames* const* replicas, int n, float* out_dev, size_t ld,
+                                                loosb200_stats* stats, int engine) {
+  int rc = check_replicas(replicas, n);
+  if (rc) return rc;
+  if (out_dev && ld < replicas[0]->F) return LOOSB200_ERR_INVALID;
+  return pairs_multi(replicas, nullptr, n, true, out_dev, out_dev ? OutKind::Device : OutKind::None, ld, stats, engine);
+}
+
+extern "C" int loosb200_rmsds_cross_multi(loosb200_frames* const* a, loosb200_frames* const* b, int n, float* out,
+                                          size_t ld, loosb200_stats* stats, int engine) {
+  int rc = check_replicas(a, n);
+  if (!rc) rc = check_replicas(b, n);
+  if (rc) return rc;
+  for (int d = 0; d < n; ++d) {
+    if (a[d]->device != b[d]->device) return LOOSB200_ERR_INVALID;
+    if (a[d]->N != b[d]->N) return LOOSB200_ERR_SIZE_MISMATCH;
+  }
+  if (out && ld < a[0]->F) return LOOSB200_ERR_INVALID;
+  return pairs_multi(a, b, n, false, out, out ? OutKind::Copy : OutKind::None, ld, stats, engine);
+}
+
+extern "C" void* loosb200_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 1;
+  // portable: pinned for every device of the process, so each GPU can copy its strips into it
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+extern "C" void loosb200_host_free(void* p) {
+  if (p) { cudaFreeHost(p); cudaGetLastError(); }
+}

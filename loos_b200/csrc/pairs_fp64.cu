@@ -37,7 +37,8 @@ k_pairs_fp64(const float* __restrict__ rawA, const double* __restrict__ cenA,
              const double* __restrict__ gdB, uint32_t FB, size_t NpadB, uint32_t N,
              const uint32_t* __restrict__ row_tiles, const uint32_t* __restrict__ prefix,
              uint32_t n_row_tiles, int self, int symmetric, int packed, float* __restrict__ out,
-             size_t ld, double* __restrict__ stats) {
+             size_t ld, float* __restrict__ out_t, size_t ld_t, uint32_t row_off,
+             double* __restrict__ stats) {
   __shared__ __align__(16) double As[3][KC][TFP];
   __shared__ __align__(16) double Bs[3][KC][TFP];
   __shared__ double cA[TF][3], cB[TF][3];
@@ -141,7 +142,7 @@ k_pairs_fp64(const float* __restrict__ rawA, const double* __restrict__ cenA,
           // the diagonal is never computed and stays 0 (Tools/rmsds.cpp:359-365)
           if (j == i && out) {
             if (packed) out[((size_t)rt * TF + la) * ld + j] = 0.f;
-            else out[(size_t)j * ld + i] = 0.f;
+            else out[(size_t)j * ld + (i - row_off)] = 0.f;
           }
           continue;
         }
@@ -153,8 +154,11 @@ k_pairs_fp64(const float* __restrict__ rawA, const double* __restrict__ cenA,
           if (packed) {
             out[((size_t)rt * TF + la) * ld + j] = v;
           } else {
-            out[(size_t)j * ld + i] = v;
-            if (symmetric) out[(size_t)i * ld + j] = v;
+            out[(size_t)j * ld + (i - row_off)] = v;
+            if (symmetric) {  // strip delivery: see PairJob
+              if (j >= row_off) out[(size_t)i * ld + (j - row_off)] = v;
+              else out_t[(size_t)(i - row_off) * ld_t + j] = v;
+            }
           }
         }
       }
@@ -189,7 +193,7 @@ int launch_pairs_fp64(const PairJob& job, cudaStream_t st) {
       a->raw, a->centroid, a->gd, (uint32_t)a->F, a->Npad, b->raw, b->centroid, b->gd,
       (uint32_t)b->F, b->Npad, (uint32_t)a->N, job.row_tiles_dev, job.tile_prefix_dev,
       job.n_row_tiles, job.self ? 1 : 0, job.symmetric ? 1 : 0, job.packed_rows ? 1 : 0, job.out,
-      job.ld, job.stats_dev);
+      job.ld, job.out_t, job.ld_t, (uint32_t)job.row_off, job.stats_dev);
   if (job.ev_k1) cudaEventRecord(job.ev_k1, st);
   LB_CUDA(cudaGetLastError());
   return LOOSB200_OK;

@@ -245,6 +245,7 @@ struct TensorArgs {
   int self, symmetric, packed;
   double unit;                 // Angstrom per fixed-point unit
   float* out; size_t ld;
+  float* out_t; size_t ld_t; uint32_t row_off;  // strip delivery, see PairJob
   double* stats;
   int release_at;  // when the epilogue hands TMEM back (see kernel)
   long long* prof;  // optional [grid][14 warps][8] cycle counters (LOOSB200_PROF=1)
@@ -661,13 +662,18 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int idx = et; idx < TILE_FRAMES * COL_TILE_FRAMES; idx += NUM_EPI_THREADS) {
             const int bl = idx / TILE_FRAMES, al_ = idx - bl * TILE_FRAMES;
             const float val = ctl->T[buf][bl][al_];
-            if (val >= 0.0f) a.out[(j0 + bl) * a.ld + i0 + al_] = val;  // M(i,j), column-major
+            if (val >= 0.0f) a.out[(j0 + bl) * a.ld + (i0 - a.row_off) + al_] = val;  // M(i,j), column-major
           }
           if (a.symmetric) {
             for (int idx = et; idx < TILE_FRAMES * COL_TILE_FRAMES; idx += NUM_EPI_THREADS) {
               const int al_ = idx / COL_TILE_FRAMES, bl = idx - al_ * COL_TILE_FRAMES;
               const float val = ctl->T[buf][bl][al_];
-              if (val >= 0.0f) a.out[(i0 + al_) * a.ld + j0 + bl] = val;  // M(j,i)
+              if (val >= 0.0f) {  // M(j,i): inside the band's own rows it lives in the row strip too
+                const size_t j = j0 + bl;
+                float* dst = j >= a.row_off ? a.out + (i0 + al_) * a.ld + (j - a.row_off)
+                                            : a.out_t + (i0 - a.row_off + al_) * a.ld_t + j;
+                *dst = val;
+              }
             }
           }
         }
@@ -770,6 +776,7 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   ta.self = job.self; ta.symmetric = job.symmetric; ta.packed = job.packed_rows;
   ta.unit = exp2((double)A->unit_log2);
   ta.out = job.out; ta.ld = job.ld; ta.stats = job.stats_dev;
+  ta.out_t = job.out_t; ta.ld_t = job.ld_t; ta.row_off = (uint32_t)job.row_off;
   ta.prof = nullptr;
   // The accumulators are handed back right after the drain (0): rounds 2 and 3 of the coefficient
   // phase then run next to the MMAs (fp64 crawls there, but the tensor pipe is not left idle).

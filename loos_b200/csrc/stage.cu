@@ -96,12 +96,17 @@ k_stage(const float* __restrict__ src, size_t natoms, const uint32_t* __restrict
     for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) mm = fmaxf(mm, redf[w]);
     centroid[f * 3 + 0] = cx; centroid[f * 3 + 1] = cy; centroid[f * 3 + 2] = cz;
     gd[f] = g[0];
-    maxabs[f] = mm;
+    // a NaN / Inf coordinate makes the centred sum of squares non-finite (fmaxf alone would drop
+    // the NaN): mark the frame so that k_unit refuses the fixed-point path for this set
+    maxabs[f] = (g[0] <= 1.7e308) ? mm : __int_as_float(0x7f800000);
   }
 }
 
-// unit = 2^e with max|x-c| / unit <= 2^23 - 2^8 (headroom for rounding and for the
-// balanced-digit carry).  force != INT_MIN overrides (cross mode: common unit).
+// unit = 2^e with max|x-c| / unit <= 127 * 65793 - 2: three balanced digits in [-128, 127] hold
+// -128 * 65793 .. 127 * 65793 = 8355711 (NOT 2^23 - 1: the carry of the lower digits pushes a value
+// above that into a top digit of +128); 2 units of headroom cover the rounding to the grid and
+// the fp32 rounding of maxabs.  force != INT_MIN overrides (cross mode: common unit).
+// e_out[1]: 0 fine, 1 forced unit too fine for these coordinates, 2 non-finite / absurd coordinates.
 __global__ void k_unit(const float* __restrict__ maxabs, size_t F, int force, int* __restrict__ e_out) {
   __shared__ float redf[32];
   float m = 0.f;
@@ -112,11 +117,12 @@ __global__ void k_unit(const float* __restrict__ maxabs, size_t F, int force, in
   if (threadIdx.x == 0) {
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, redf[w]);
     int e = -20;  // never finer than 2^-20 A (float32 inputs carry no more)
-    const double lim = 8388608.0 - 256.0;
+    const double lim = (double)Q_MAX - 2.0;
     while (e < 40 && (double)m / exp2((double)e) > lim) ++e;
+    const bool absurd = !((double)m / exp2((double)e) <= lim);  // Inf (NaN frames are marked Inf) or > 2^63 A
     if (force != INT_MIN && force > e) e = force;
     e_out[0] = e;
-    e_out[1] = (force != INT_MIN && force < e) ? 1 : 0;  // forced unit too fine: range error
+    e_out[1] = absurd ? 2 : ((force != INT_MIN && force < e) ? 1 : 0);  // forced unit too fine: range error
   }
 }
 
@@ -141,7 +147,8 @@ k_quantise(const float* __restrict__ raw, const double* __restrict__ centroid, s
       const int x0 = (int)(int8_t)(q & 0xff);
       const long long q1 = (q - x0) >> 8;
       const int x1 = (int)(int8_t)(q1 & 0xff);
-      const long long x2 = (q1 - x1) >> 8;
+      long long x2 = (q1 - x1) >> 8;
+      x2 = x2 > 127 ? 127 : (x2 < -128 ? -128 : x2);  // unreachable below k_unit's limit; never wrap
       d0[i] = (int8_t)x0;
       d0[plane + i] = (int8_t)x1;
       d0[2 * plane + i] = (int8_t)x2;
@@ -194,6 +201,7 @@ int ensure_quantised(loosb200_frames* h, int force_unit_log2) {
   int e[2];
   LB_CUDA(cudaMemcpyAsync(e, h->unit_log2_dev, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
   LB_CUDA(cudaStreamSynchronize(h->stream));
+  if (e[1] == 2) return LOOSB200_ERR_NUMERICAL;  // NaN / Inf coordinates: the fp64 engine propagates them
   if (e[1]) return LOOSB200_ERR_RANGE;
   h->unit_log2 = e[0];
   h->quantised = true;
@@ -223,7 +231,7 @@ int ensure_quantised(loosb200_frames* h, int force_unit_log2) {
 
 // ---- host side of staging -------------------------------------------------
 
-static int alloc_handle(loosb200_frames** out, size_t F, size_t N, int device) {
+int alloc_frames(loosb200_frames** out, size_t F, size_t N, int device) {
   loosb200_frames* h = new (std::nothrow) loosb200_frames();
   if (!h) return LOOSB200_ERR_NOMEM;
   h->device = device; h->F = F; h->N = N;
@@ -283,7 +291,7 @@ extern "C" int loosb200_stage_frames_device(loosb200_frames** out, const float* 
   int rc = check_stage_args(out, dev_xyz, F, natoms, sel, nsel, layout, device);
   if (rc) return rc;
   loosb200_frames* h = nullptr;
-  if ((rc = alloc_handle(&h, F, sel ? nsel : natoms, device))) return rc;
+  if ((rc = alloc_frames(&h, F, sel ? nsel : natoms, device))) return rc;
   uint32_t* sel_dev = nullptr;
   if ((rc = upload_sel(sel, nsel, &sel_dev, h->stream))) { loosb200_free(h); return rc; }
   cudaEventRecord(h->timing.ev[0], h->stream);
@@ -360,7 +368,7 @@ extern "C" int loosb200_stage_begin(loosb200_frames** out, size_t F, size_t nato
   int rc = check_stage_args(out, &dummy, F, natoms, sel, nsel, layout, device);
   if (rc) return rc;
   loosb200_frames* h = nullptr;
-  if ((rc = alloc_handle(&h, F, sel ? nsel : natoms, device))) return rc;
+  if ((rc = alloc_frames(&h, F, sel ? nsel : natoms, device))) return rc;
   Stager* s = new (std::nothrow) Stager();
   if (!s) { loosb200_free(h); return LOOSB200_ERR_NOMEM; }
   h->stager = s;

@@ -29,7 +29,7 @@ int main(int argc, char* argv[]) {
     }
     const long verbosity = std::stol(o.str("verbosity"));
     const bool noop = o.flag("noout"), stats = o.flag("stats");
-    const int device = (int)o.uns("gpu"), engine = engineOf(o);
+    const int device = (int)o.uns("gpu"), engine = engineOf(o), ngpus = gpusOf(o);
     const std::string range = o.str("range");
 
     Model model = readPDB(o.str("model"));
@@ -53,8 +53,10 @@ int main(int argc, char* argv[]) {
       const std::pair<uint32_t, uint32_t> loc = mt.location(indices[j]);
       mt.trajs[loc.first]->readFramePlanes(loc.second, dst);
     });
+    Replicas RA;
+    RA.build(A, device, ngpus);
     if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
-    std::vector<float> M;
+    HostMatrix M;
     const std::string binary = o.str("binary");
     const unsigned precision = (unsigned)o.uns("precision");
     const bool gpu_text = !noop && gpuText(!binary.empty(), precision);  // text formatted on the GPU
@@ -73,14 +75,15 @@ int main(int argc, char* argv[]) {
       }
       std::cout.flush();
     };
-    if (want_m) M.assign(F * F, 0.0f);
+    warnHostMemory(want_m ? F * F * sizeof(float) : 0, verbosity);
+    if (want_m) M.allocate(F * F);
     loosb200_stats st;
     if (gpu_text) {
       preamble();
-      check(loosb200_rmsds_self_text(A.h, precision, stdoutSink, nullptr, &st, engine), "multi-rmsds");
+      check(loosb200_rmsds_self_multi_text(RA.h.data(), ngpus, precision, stdoutSink, nullptr, &st, engine), "multi-rmsds");
       fflush(stdout);
     } else {
-      check(loosb200_rmsds_self(A.h, want_m ? M.data() : nullptr, F, &st, engine), "multi-rmsds");
+      check(loosb200_rmsds_self_multi(RA.h.data(), ngpus, want_m ? M.data() : nullptr, F, &st, engine), "multi-rmsds");
     }
     if (!binary.empty()) writeNpy(binary, M.data(), F, F, F);
     if (verbosity || noop || stats) {

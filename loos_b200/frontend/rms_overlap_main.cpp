@@ -62,7 +62,7 @@ int main(int argc, char* argv[]) {
     const long verbosity = std::stol(o.str("verbosity"));
     const bool noop = o.flag("noout"), stats = o.flag("stats");
     const float cutoff = (float)o.dbl("cutoff");
-    const int device = (int)o.uns("gpu"), engine = engineOf(o);
+    const int device = (int)o.uns("gpu"), engine = engineOf(o), ngpus = gpusOf(o);
     const std::string range = o.str("range");
     Model model = readPDB(o.str("model"));
     MultiTraj mt[2];
@@ -95,19 +95,24 @@ int main(int argc, char* argv[]) {
     const unsigned precision = (unsigned)o.uns("precision");
     const bool gpu_text = !noop && gpuText(want_fraction || !binary.empty(), precision);  // text formatted on the GPU
     const bool need_matrix = (!noop || want_fraction || !binary.empty()) && !gpu_text;
-    std::vector<float> M;
-    if (need_matrix) M.assign(F[0] * F[1], 0.0f);
+    Replicas R0, R1;
+    R0.build(fs[0], device, ngpus);
+    R1.build(fs[1], device, ngpus);
+    HostMatrix Mh;
+    warnHostMemory(need_matrix ? F[0] * F[1] * sizeof(float) : 0, verbosity);
+    if (need_matrix) Mh.allocate(F[0] * F[1]);
+    const float* M = Mh.data();
     loosb200_stats st;
     if (gpu_text) {
       std::cout << "# " << header << std::endl;
       std::cout << trajectoryTable(mt[0], range) << trajectoryTable(mt[1], range);
       std::cout.flush();
-      check(loosb200_rmsds_cross_text(fs[0].h, fs[1].h, precision, stdoutSink, nullptr, &st, engine), "rms-overlap");
+      check(loosb200_rmsds_cross_multi_text(R0.h.data(), R1.h.data(), ngpus, precision, stdoutSink, nullptr, &st, engine), "rms-overlap");
       fflush(stdout);
     } else {
-      check(loosb200_rmsds_cross(fs[0].h, fs[1].h, need_matrix ? M.data() : nullptr, F[0], &st, engine), "rms-overlap");
+      check(loosb200_rmsds_cross_multi(R0.h.data(), R1.h.data(), ngpus, need_matrix ? Mh.data() : nullptr, F[0], &st, engine), "rms-overlap");
     }
-    if (!binary.empty()) writeNpy(binary, M.data(), F[0], F[1], F[0]);
+    if (!binary.empty()) writeNpy(binary, M, F[0], F[1], F[0]);
     if (verbosity || noop || stats || want_fraction) {
       char line[512];
       if (want_fraction) {  // showFractionalStats, bug-for-bug (see the header comment)
@@ -137,7 +142,7 @@ int main(int argc, char* argv[]) {
     if (!noop && !gpu_text) {
       std::cout << "# " << header << std::endl;
       std::cout << trajectoryTable(mt[0], range) << trajectoryTable(mt[1], range);
-      writeMatrix(std::cout, M.data(), F[0], F[1], F[0], precision);
+      writeMatrix(std::cout, M, F[0], F[1], F[0], precision);
     }
   } catch (const std::exception& e) {
     std::cerr << e.what() << std::endl;

@@ -35,7 +35,7 @@ int main(int argc, char* argv[]) {
     const unsigned precision = (unsigned)o.uns("precision");
     const bool gpu_text = !noop && gpuText(!binary.empty(), precision);  // text formatted on the GPU
     const bool want_m = (!noop || !binary.empty()) && !gpu_text;
-    const int device = (int)o.uns("gpu"), engine = engineOf(o);
+    const int device = (int)o.uns("gpu"), engine = engineOf(o), ngpus = gpusOf(o);
 
     Model model = readPDB(o.str("model1"));
     const std::shared_ptr<Trajectory> trajp = openTrajectory(o.str("traj1"), (uint32_t)model.size());
@@ -49,17 +49,21 @@ int main(int argc, char* argv[]) {
     Frames A;
     stageTrajectory(A, traj, indices, model.size(), sel, device);
 
-    std::vector<float> M;
+    Replicas RA;
+    RA.build(A, device, ngpus);
+
+    HostMatrix M;
     size_t rows = indices.size(), cols = indices.size();
     loosb200_stats st;
     if (!o.has("model2")) {
       if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
-      if (want_m) M.assign(rows * cols, 0.0f);
+      warnHostMemory(want_m ? rows * cols * sizeof(float) : 0, verbosity);
+      if (want_m) M.allocate(rows * cols);
       if (gpu_text) {
         std::cout << "# " << header << std::endl;
-        check(loosb200_rmsds_self_text(A.h, precision, stdoutSink, nullptr, &st, engine), "rmsds");
+        check(loosb200_rmsds_self_multi_text(RA.h.data(), ngpus, precision, stdoutSink, nullptr, &st, engine), "rmsds");
       }
-      else check(loosb200_rmsds_self(A.h, want_m ? M.data() : nullptr, rows, &st, engine), "rmsds");
+      else check(loosb200_rmsds_self_multi(RA.h.data(), ngpus, want_m ? M.data() : nullptr, rows, &st, engine), "rmsds");
     } else {
       Model model2 = readPDB(o.str("model2"));
       const std::shared_ptr<Trajectory> traj2p = openTrajectory(o.str("traj2"), (uint32_t)model2.size());
@@ -72,13 +76,16 @@ int main(int argc, char* argv[]) {
       Frames B;
       stageTrajectory(B, traj2, indices2, model2.size(), sel2, device);
       cols = indices2.size();
+      Replicas RB;
+      RB.build(B, device, ngpus);
       if (verbosity > 1) std::cerr << "Calculating RMSD...\n";
-      if (want_m) M.assign(rows * cols, 0.0f);
+      warnHostMemory(want_m ? rows * cols * sizeof(float) : 0, verbosity);
+      if (want_m) M.allocate(rows * cols);
       if (gpu_text) {
         std::cout << "# " << header << std::endl;
-        check(loosb200_rmsds_cross_text(A.h, B.h, precision, stdoutSink, nullptr, &st, engine), "rmsds");
+        check(loosb200_rmsds_cross_multi_text(RA.h.data(), RB.h.data(), ngpus, precision, stdoutSink, nullptr, &st, engine), "rmsds");
       }
-      else check(loosb200_rmsds_cross(A.h, B.h, want_m ? M.data() : nullptr, rows, &st, engine), "rmsds");
+      else check(loosb200_rmsds_cross_multi(RA.h.data(), RB.h.data(), ngpus, want_m ? M.data() : nullptr, rows, &st, engine), "rmsds");
     }
     if (verbosity || noop || stats) {  // showStatsHalf / showStatsWhole, :425-456
       char line[128];

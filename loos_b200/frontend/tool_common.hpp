@@ -10,6 +10,8 @@
 #include <thread>
 #include <vector>
 
+#include <unistd.h>
+
 #include "../../include/loosb200.h"
 #include "frontend.hpp"
 
@@ -30,7 +32,17 @@ inline void addBasicOptions(Options& o) {  // BasicOptions, src/OptionsFramework
   o.add("verbosity", 'v', "0", "Verbosity of output (if available)");
   o.add("config", 0, "", "Options config file");
   o.add("gpu", 0, "0", "CUDA device to use (extension; the reference has no such option)");
+  o.add("gpus", 0, "1", "Number of GPUs the matrix is split over, starting at --gpu (extension)");
   o.add("engine", 0, "auto", "auto|tensor|fp64 contraction engine (extension)");
+}
+
+// --gpus: how many devices work on the matrix (the GPU counterpart of --threads)
+inline int gpusOf(const Options& o) {
+  const unsigned long n = o.uns("gpus");
+  const int have = loosb200_device_count();
+  if (n < 1 || (have > 0 && n > (unsigned long)have))
+    throw Error("the argument ('" + o.str("gpus") + "') for option '--gpus' is invalid: " + std::to_string(have) + " usable device(s)");
+  return (int)n;
 }
 
 inline int engineOf(const Options& o) {
@@ -55,6 +67,67 @@ struct Frames {  // RAII around loosb200_frames
   loosb200_frames* h = nullptr;
   ~Frames() { if (h) loosb200_free(h); }
 };
+
+// A staged set and its copies on the other devices of the job; h[0] is the original (not owned).
+struct Replicas {
+  std::vector<loosb200_frames*> h;
+  Replicas() {}
+  Replicas(const Replicas&) = delete;
+  Replicas& operator=(const Replicas&) = delete;
+  ~Replicas() { for (size_t k = 1; k < h.size(); ++k) if (h[k]) loosb200_free(h[k]); }
+  void build(const Frames& first, int first_device, int ngpus) {
+    h.assign(1, first.h);
+    const int have = std::max(1, loosb200_device_count());
+    for (int k = 1; k < ngpus; ++k) {
+      loosb200_frames* r = nullptr;
+      check(loosb200_replicate(first.h, (first_device + k) % have, &r), "replicating frames");
+      h.push_back(r);
+    }
+  }
+};
+
+// The F x F float matrix on the host, when it is needed there at all (--binary, -p > 9, fractional
+// statistics): page-locked for every device so that the result copies run at the PCIe rate
+// (40 GB at 100,000 frames), pageable only if the host refuses to pin that much.
+struct HostMatrix {
+  float* p = nullptr;
+  bool pinned = false;
+  HostMatrix() {}
+  HostMatrix(const HostMatrix&) = delete;
+  HostMatrix& operator=(const HostMatrix&) = delete;
+  ~HostMatrix() { release(); }
+  void release() {
+    if (p) { if (pinned) loosb200_host_free(p); else free(p); }
+    p = nullptr;
+  }
+  void allocate(size_t count) {
+    release();
+    p = static_cast<float*>(loosb200_host_alloc(std::max<size_t>(1, count) * sizeof(float)));
+    pinned = p != nullptr;
+    if (!p) p = static_cast<float*>(calloc(std::max<size_t>(1, count), sizeof(float)));
+    if (!p) throw Error("Error- cannot allocate the " + std::to_string(count * sizeof(float) >> 20) + " MB result matrix");
+  }
+  float* data() const { return p; }
+};
+
+// The reference warns before it fills two thirds of the machine with the coordinate cache and the
+// matrix (checkMemoryUsage, Tools/rmsds.cpp:58-60,467-485,516-518).  Here the coordinates live in
+// HBM, so the estimate is the host matrix alone (zero when the text is formatted on the GPU).
+inline void warnHostMemory(size_t used_bytes, long verbosity) {
+  const long pagesize = sysconf(_SC_PAGESIZE), pages = sysconf(_SC_PHYS_PAGES);  // loos::availableMemory(), src/utils.cpp:433-439
+  if (pagesize <= 0 || pages <= 0) return;
+  const double mem = (double)pagesize * (double)pages;
+  char line[256];
+  if (verbosity > 2) {
+    snprintf(line, sizeof(line), "Memory: available=%ld GB, estimated used=%.2f MB\n", (long)(mem / (double)(1ul << 30)), (double)used_bytes / (double)(1ul << 20));
+    std::cerr << line;
+  }
+  if ((double)used_bytes / mem >= 0.66) {
+    snprintf(line, sizeof(line), "***WARNING***\nThe estimated memory used is %.1f%% (%zu MB) of your total memory (%ld GB).\n",
+             100.0 * (double)used_bytes / mem, used_bytes >> 20, (long)(mem / (double)(1ul << 30)));
+    std::cerr << line << "If your machine starts swapping, try subsampling the trajectories\n";
+  }
+}
 
 // readCoords (src/ensembles.cpp:253-296) without the host-side coordinate cache: frames
 // are decoded in batches (planes X|Y|Z per frame, the DCD record order) and appended to

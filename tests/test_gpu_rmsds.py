@@ -391,3 +391,66 @@ def test_matrix_text_in_row_bands(lb, monkeypatch):
     assert banded == whole and cbanded == cwhole
     assert bst["count"] == st["count"] and bst["max"] == st["max"] and abs(bst["sum"] - st["sum"]) < 1e-6
     assert cbst["count"] == cst["count"] and cbst["max"] == cst["max"] and abs(cbst["sum"] - cst["sum"]) < 1e-6 * cst["sum"]
+
+
+@pytest.mark.parametrize("top", [127.9, 63.9, 255.7, 127.4999])
+def test_fixed_point_range_top_of_a_power_of_two_band(lb, top):
+    """Centred coordinates in the top 0.4 % of a power-of-two band (127.50-127.996 A at unit 2^-16,
+    63.75-64 A at 2^-17, ...) exceed what three balanced base-256 digits hold (127 * 65793); the unit
+    must step up instead of letting the top digit wrap to -128 (stage.cu, k_unit / k_quantise)."""
+    rng = np.random.default_rng(int(top * 1000))
+    F, N = 24, 96
+    X = rng.normal(scale=12.0, size=(F, N, 3))
+    X -= X.mean(axis=1, keepdims=True)
+    # two atoms on opposite sides keep the centroid at the origin: centred x of atom 0 is exactly `top`
+    X[:, 0, :] = 0.0
+    X[:, 1, :] = 0.0
+    X[:, 0, 0] = top
+    X[:, 1, 0] = -top
+    X = X.astype(np.float32)
+    with lb.FrameSet(X) as fs:
+        e = fs.unit_log2()
+        assert top / 2.0 ** e <= 127 * 65793, (top, e)
+        Mt, _ = lb.rmsds(fs, engine="tensor")
+        Md, _ = lb.rmsds(fs, engine="fp64")
+    assert np.abs(Mt.astype(np.float64) - Md.astype(np.float64)).max() <= 2e-5
+    # rectangle mode against a set with a smaller extent: the common (coarser) unit is forced on it
+    Y = (rng.normal(scale=3.0, size=(F, N, 3))).astype(np.float32)
+    with lb.FrameSet(X) as a, lb.FrameSet(Y) as b:
+        Ct, _ = lb.rmsds_cross(a, b, engine="tensor")
+        Cd, _ = lb.rmsds_cross(a, b, engine="fp64")
+    assert np.abs(Ct.astype(np.float64) - Cd.astype(np.float64)).max() <= 2e-5
+
+
+def test_non_finite_coordinates_are_not_absorbed(lb):
+    """A NaN / Inf coordinate has no fixed-point image: the tensor engine refuses the set
+    (NumericalError in the reference's dgesvj path, src/alignment.cpp:66-67) and AUTO falls back to the
+    fp64 engine, which propagates NaN into every entry that involves the bad frame."""
+    from loos_b200 import capi
+    from loos_b200.synth import synth_frames
+    X = synth_frames(50, 64, seed=8).copy()
+    X[17, 5, 1] = np.nan
+    with lb.FrameSet(X) as fs:
+        with pytest.raises(lb.LoosB200Error) as ei:
+            lb.rmsds(fs, engine="tensor")
+        assert ei.value.code == capi.ERR_NUMERICAL
+        M, _ = lb.rmsds(fs, engine="auto")
+    bad = np.isnan(M)
+    assert bad[17, :17].all() and bad[:17, 17].all() and bad[18:, 17].all()
+    good = np.delete(np.delete(M, 17, axis=0), 17, axis=1)
+    assert np.isfinite(good).all()
+    X[17, 5, 1] = np.inf
+    with lb.FrameSet(X) as fs:
+        with pytest.raises(lb.LoosB200Error):
+            lb.rmsds(fs, engine="tensor")
+
+
+def test_centroids_match_center_at_origin(lb, checker):
+    """a3: the staged centroids against alignment::centerAtOrigin (src/alignment.cpp:90-109) directly."""
+    from loos_b200.synth import synth_frames
+    X = synth_frames(200, 333, seed=12)
+    sel = np.arange(1, 333, 3, dtype=np.uint32)
+    with lb.FrameSet(X, sel=sel) as fs:
+        c = fs.centroids()
+    want = np.array([checker.center_at_origin(X[f][sel].astype(np.float64))[1] for f in range(200)])
+    assert np.abs(c - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
