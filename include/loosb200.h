@@ -260,6 +260,12 @@ int loosb200_align_accumulate(loosb200_frames* align, loosb200_frames* accum_set
  * of operands, reductions, copies).  Returns the number of kernel launches the
  * call made (>= 1), or a negative error code. */
 int loosb200_last_timing(const loosb200_frames* h, double* ms_main, double* ms_other);
+/* Sustained dense int8 tensor-pipe rate of `device` (the roofline denominator of the all-to-all
+ * kernel): every SM pair issues back-to-back tcgen05.mma.cta_group::2.kind::i8,
+ * M = 256, N = 256, K = 32, operands resident in shared memory, for about `seconds` (>= 2: under
+ * the power cap).  tops_out: tera-operations per second (2 per multiply-add); ms_out: duration of
+ * the measured launch, may be NULL. */
+int loosb200_measure_int8_peak(int device, double seconds, double* tops_out, double* ms_out);
 
 #ifdef __cplusplus
 }

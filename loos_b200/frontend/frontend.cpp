@@ -77,32 +77,38 @@ static T fieldNum(const std::string& s, unsigned pos, unsigned nelem) {
   return val;
 }
 
-int parseHybrid36(const std::string& source, unsigned pos, unsigned nelem) {
-  static const int pow10[6] = {1, 10, 100, 1000, 10000, 100000};
-  static const int pow36[6] = {1, 36, 1296, 46656, 1679616, 60466176};
-  unsigned n = !nelem ? (unsigned)(source.size() - pos) : nelem;
-  if ((size_t)pos + n > source.size()) return 0;
-  if (n > 6) throw std::logic_error("Requested size exceeds max");
-  std::string s(source.substr(pos, n));
-  bool negative = false;
-  std::string::iterator si = s.begin();
-  n = (unsigned)s.size();
-  if (si != s.end() && *si == '-') { negative = true; ++si; --n; }
-  for (; si != s.end() && *si == ' '; ++si, --n) {}
-  int offset = 0, ibase = 10;
-  char cbase = 'a';
-  if (si != s.end() && n >= 1 && n <= 5) {
-    if (*si >= 'a') { offset = pow10[n] + 16 * pow36[n - 1]; cbase = 'a'; ibase = 36; }
-    else if (*si >= 'A') { offset = pow10[n] - 10 * pow36[n - 1]; cbase = 'A'; ibase = 36; }
+// Hybrid-36 (the cctbx / iotbx.pdb convention for serial numbers that outgrow a fixed-width field): a
+// field of w characters is an ordinary decimal number while the count fits; the values after 10^w - 1
+// are written in base 36 with upper-case letters -- "A000..." being the first, 10^w -- and after those
+// 26 * 36^(w-1) words the same again in lower case.  What the reference's reader
+// (parseStringAsHybrid36, src/utils.cpp:253-311) does with malformed fields is kept, because the PDB
+// fixtures pin it: a leading '-' then blanks are skipped, the width that selects the alphabet is what
+// remains after them, only fields of 1..5 significant characters can be base 36, a field that runs
+// past the end of the line reads as 0, and a stray letter inside a decimal field counts from 'a' = 10.
+int parseHybrid36(const std::string& line, unsigned pos, unsigned width) {
+  const size_t field = width ? width : line.size() - pos;
+  if ((size_t)pos + field > line.size()) return 0;
+  if (field > 6) throw std::logic_error("Requested size exceeds max");
+  const char* p = line.data() + pos;
+  const char* const end = p + field;
+  const bool minus = p < end && *p == '-';
+  if (minus) ++p;
+  while (p < end && *p == ' ') ++p;
+  const size_t w = (size_t)(end - p);
+  enum Alphabet { DECIMAL, UPPER, LOWER };
+  Alphabet alphabet = DECIMAL;
+  if (w >= 1 && w <= 5) alphabet = *p >= 'a' ? LOWER : (*p >= 'A' ? UPPER : DECIMAL);
+  const int radix = alphabet == DECIMAL ? 10 : 36;
+  const char ten = alphabet == UPPER ? 'A' : 'a';  // the character worth 10
+  int value = 0;
+  for (; p < end; ++p) value = value * radix + (*p >= ten ? *p - ten + 10 : *p - '0');
+  if (alphabet != DECIMAL) {
+    int first_word = 1, decimal_span = 10;  // 36^(w-1) and 10^w
+    for (size_t k = 1; k < w; ++k) { first_word *= 36; decimal_span *= 10; }
+    // upper case starts at 10^w with the word worth 10 * 36^(w-1); lower case 26 * 36^(w-1) later
+    value += decimal_span + (alphabet == UPPER ? -10 : 16) * first_word;
   }
-  int result = 0;
-  while (si != s.end()) {
-    const int c = (*si >= cbase) ? *si - cbase + 10 : *si - '0';
-    result = result * ibase + c;
-    ++si;
-  }
-  result += offset;
-  return negative ? -result : result;
+  return minus ? -value : value;
 }
 
 static void parseAtomRecord(const std::string& s, Model& m) {  // src/pdb.cpp:66-141

@@ -5,9 +5,9 @@
 // stack.hh / location.hh / position.hh, pre-generated from grammar.yy), Kernel.cpp, KernelActions.cpp,
 // KernelValue.cpp, KernelStack.cpp, ParserDriver.hpp, LoosLexer.hpp, Atom.{hpp,cpp}, Coord.hpp, exceptions.hpp --
 // all unmodified, passed to the compiler by oracle/Makefile -- plus Selectors.cpp:37-132,156-164 (backbone /
-// hydrogen) extracted into a throw-away directory.  Stand-ins (oracle/shim_sel): <FlexLexer.h> (flex is not
-// installed; the header only declares the classes scanner.cc implements), boost::regex over std::regex,
-// loos_defs.hpp without Boost, Selectors.hpp without AtomicGroup.
+// hydrogen) extracted into a throw-away directory.  <FlexLexer.h> is the reference's own src/FlexLexer.h (on the
+// include path where it lies).  Stand-ins (oracle/shim_sel): boost::regex over std::regex, loos_defs.hpp without
+// Boost, Selectors.hpp without AtomicGroup.
 // Restated here: selectAtoms (src/utils.cpp:183-201: Parser::parse, error prefix), AtomicGroup::select
 // (src/AtomicGroup.cpp:341-351: atoms in order, those the predicate accepts) and KernelSelector::operator()
 // (src/Selectors.cpp:189-200), because Parser.hpp / AtomicGroup stand on the rest of LOOS.
