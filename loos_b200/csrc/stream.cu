@@ -11,6 +11,7 @@
 // HBM-bound: 12 N_align (+ 12 N_rmsd if a different selection) bytes per frame and pass.
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include <stdlib.h>
@@ -24,27 +25,33 @@ namespace {
 constexpr int ST = 128;  // threads per CTA
 
 // Sum of the transformed frames, sum_f (W_f x_f), for iterativeAlignment's running average
-// (src/alignment.cpp:385-397) and averageStructure (src/ensembles.cpp:91-121).  Each CTA walks
-// frames f = blockIdx.x, blockIdx.x + gridDim.x, ... and keeps its partial sum in shared memory;
-// a thread owns atoms tid, tid + ST, ..., so there is no synchronisation inside the frame loop and
-// no atomic until the final flush.  W_f ([F][16], from k_solve) is read straight from global memory
-// (one broadcast line per frame).
+// (src/alignment.cpp:385-397) and averageStructure (src/ensembles.cpp:91-121).  The grid is
+// (frame walkers) x (atom chunks): a CTA walks frames f = blockIdx.x, blockIdx.x + gridDim.x, ...
+// over ITS chunk of at most ACC_CHUNK atoms and keeps the partial sum of that chunk in shared
+// memory; a thread owns the float4 groups tid, tid + ST, ... of the chunk, so there is no
+// synchronisation inside the frame loop and no atomic until the final flush.  Selections of any
+// size work (rmsd2ref's default --rmsd is every heavy atom): more atoms, more chunks.  W_f
+// ([F][16], from k_solve) is read straight from global memory (one broadcast line per frame).
+constexpr uint32_t ACC_CHUNK = 8192;  // atoms per chunk: 3 x 8192 doubles = 192 KB of shared memory
 struct AccumArgs {
   const float* raw; size_t Npad; uint32_t N;  // frame planes [F][3][Npad]
   const double* xf;                           // [F][16]
   uint32_t F;
+  uint32_t chunk4;                            // float4 groups per atom chunk (blockIdx.y)
   double* avg;                                // [3][Npad] global accumulators (zeroed by the caller)
 };
 
 __global__ void __launch_bounds__(ST) k_accum(const AccumArgs a) {
-  extern __shared__ double acc_s[];  // [3][Npad]
+  extern __shared__ double acc_s[];  // [3][4 * chunk4]
   const int tid = threadIdx.x;
-  for (size_t i = tid; i < 3 * a.Npad; i += ST) acc_s[i] = 0.0;
+  const uint32_t n4 = (uint32_t)(a.Npad / 4);
+  const uint32_t g_lo = blockIdx.y * a.chunk4, g_hi = min(n4, g_lo + a.chunk4);
+  const uint32_t clen = 4 * a.chunk4;  // doubles per plane of the chunk
+  for (uint32_t i = tid; i < 3 * clen; i += ST) acc_s[i] = 0.0;
   __syncthreads();  // the zeroing and the flush stride over all three planes, the frame loop does not
-  const uint32_t n4 = (uint32_t)(a.Npad / 4);  // a thread owns the float4 groups tid, tid + ST, ...
   double2* ax = reinterpret_cast<double2*>(acc_s);
-  double2* ay = reinterpret_cast<double2*>(acc_s + a.Npad);
-  double2* az = reinterpret_cast<double2*>(acc_s + 2 * a.Npad);
+  double2* ay = reinterpret_cast<double2*>(acc_s + clen);
+  double2* az = reinterpret_cast<double2*>(acc_s + 2 * clen);
   for (uint32_t f = blockIdx.x; f < a.F; f += gridDim.x) {
     double W[12];
 #pragma unroll
@@ -52,9 +59,9 @@ __global__ void __launch_bounds__(ST) k_accum(const AccumArgs a) {
     const float4* px = reinterpret_cast<const float4*>(a.raw + (size_t)f * 3 * a.Npad);
     const float4* py = px + n4, *pz = py + n4;
     // two groups per trip, all six loads issued before the first use
-    for (uint32_t g0 = tid; g0 < n4; g0 += 2 * ST) {
+    for (uint32_t g0 = g_lo + tid; g0 < g_hi; g0 += 2 * ST) {
       const uint32_t g1 = g0 + ST;
-      const bool two = g1 < n4;
+      const bool two = g1 < g_hi;
       const float4 X0 = __ldcs(px + g0), Y0 = __ldcs(py + g0), Z0 = __ldcs(pz + g0);
       float4 X1 = X0, Y1 = Y0, Z1 = Z0;
       if (two) { X1 = __ldcs(px + g1); Y1 = __ldcs(py + g1); Z1 = __ldcs(pz + g1); }
@@ -73,19 +80,23 @@ __global__ void __launch_bounds__(ST) k_accum(const AccumArgs a) {
           ty[k] = real ? W[4] * x + W[5] * y + W[6] * z + W[7] : 0.0;
           tz[k] = real ? W[8] * x + W[9] * y + W[10] * z + W[11] : 0.0;
         }
+        const uint32_t l = g - g_lo;  // group inside the chunk
         double2 u;
-        u = ax[2 * g]; u.x += tx[0]; u.y += tx[1]; ax[2 * g] = u;
-        u = ax[2 * g + 1]; u.x += tx[2]; u.y += tx[3]; ax[2 * g + 1] = u;
-        u = ay[2 * g]; u.x += ty[0]; u.y += ty[1]; ay[2 * g] = u;
-        u = ay[2 * g + 1]; u.x += ty[2]; u.y += ty[3]; ay[2 * g + 1] = u;
-        u = az[2 * g]; u.x += tz[0]; u.y += tz[1]; az[2 * g] = u;
-        u = az[2 * g + 1]; u.x += tz[2]; u.y += tz[3]; az[2 * g + 1] = u;
+        u = ax[2 * l]; u.x += tx[0]; u.y += tx[1]; ax[2 * l] = u;
+        u = ax[2 * l + 1]; u.x += tx[2]; u.y += tx[3]; ax[2 * l + 1] = u;
+        u = ay[2 * l]; u.x += ty[0]; u.y += ty[1]; ay[2 * l] = u;
+        u = ay[2 * l + 1]; u.x += ty[2]; u.y += ty[3]; ay[2 * l + 1] = u;
+        u = az[2 * l]; u.x += tz[0]; u.y += tz[1]; az[2 * l] = u;
+        u = az[2 * l + 1]; u.x += tz[2]; u.y += tz[3]; az[2 * l + 1] = u;
       }
     }
   }
   __syncthreads();
-  for (size_t i = tid; i < 3 * a.Npad; i += ST)
-    if (acc_s[i] != 0.0) atomicAdd(&a.avg[i], acc_s[i]);
+  const uint32_t here = 4 * (g_hi > g_lo ? g_hi - g_lo : 0);  // doubles of this chunk that exist
+  for (uint32_t i = tid; i < 3 * clen; i += ST) {
+    const uint32_t plane = i / clen, within = i - plane * clen;
+    if (within < here && acc_s[i] != 0.0) atomicAdd(&a.avg[(size_t)plane * a.Npad + 4 * g_lo + within], acc_s[i]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -446,14 +457,23 @@ void to_soa(const double* xyz, size_t n, size_t Npad, bool centre, std::vector<d
     }
 }
 
-int grid_accum(uint32_t F, int smem) {  // as many CTAs as the shared-memory accumulators allow
+// Launch k_accum over all frames and all atoms of a [F][3][Npad] plane set: atom chunks of at most
+// ACC_CHUNK atoms (equal sizes), and per chunk as many frame walkers as fill the device.
+int launch_accum(AccumArgs aa, cudaStream_t st) {
+  const uint32_t n4 = (uint32_t)(aa.Npad / 4);
+  const uint32_t nchunks = std::max<uint32_t>(1, (n4 * 4 + ACC_CHUNK - 1) / ACC_CHUNK);
+  aa.chunk4 = std::max<uint32_t>(1, (n4 + nchunks - 1) / nchunks);
+  const int smem = (int)(3 * 4 * aa.chunk4 * sizeof(double));
+  LB_CUDA(cudaFuncSetAttribute(k_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accum, ST, (size_t)smem);
   if (per_sm < 1) per_sm = 1;
-  const uint32_t g = (uint32_t)(sms * per_sm);
-  return (int)(F < g ? F : g);
+  uint32_t walkers = std::max<uint32_t>(1, (uint32_t)(sms * per_sm) / nchunks);
+  if (walkers > aa.F) walkers = aa.F;
+  k_accum<<<dim3(walkers, nchunks), ST, smem, st>>>(aa);
+  return LOOSB200_OK;
 }
 
 template <class K>
@@ -468,8 +488,6 @@ int grid_warp(uint32_t F, K kernel) {  // persistent: as many CTAs as fit, each 
   const uint32_t cap = (uint32_t)(sms * per_sm);
   return (int)(need < cap ? need : cap);
 }
-
-int smem_for_accum(size_t Npad) { return (int)(3 * Npad * sizeof(double)); }
 
 }  // namespace
 }  // namespace loosb200
@@ -574,9 +592,6 @@ extern "C" int loosb200_align_accumulate(loosb200_frames* align, loosb200_frames
   LB_CUDA(cudaSetDevice(align->device));
   cudaStream_t st = align->stream;
   const size_t F = align->F, NpS = as->Npad;
-  const int smem = smem_for_accum(NpS);
-  if (smem > 200 * 1024) return LOOSB200_ERR_UNSUPPORTED;
-  LB_CUDA(cudaFuncSetAttribute(k_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 
   std::vector<double> soaA;
   double c[3], cs[3];
@@ -604,7 +619,7 @@ extern "C" int loosb200_align_accumulate(loosb200_frames* align, loosb200_frames
   k_solve<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(sa);
   AccumArgs aa;
   aa.raw = as->raw; aa.Npad = NpS; aa.N = (uint32_t)as->N; aa.xf = dXf; aa.F = (uint32_t)F; aa.avg = dSum;
-  k_accum<<<grid_accum((uint32_t)F, smem), ST, smem, st>>>(aa);
+  launch_accum(aa, st);
   cudaEventRecord(align->timing.ev[2], st);
   std::vector<double> sum_h(3 * NpS);
   cudaMemcpyAsync(sum_h.data(), dSum, sizeof(double) * 3 * NpS, cudaMemcpyDeviceToHost, st);
@@ -631,10 +646,6 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
   LB_CUDA(cudaSetDevice(align->device));
   cudaStream_t st = align->stream;
   const size_t F = align->F, Na = align->N, NpA = align->Npad, Nr = rs->N, NpR = rs->Npad;
-  const int smemA = smem_for_accum(NpA), smemR = smem_for_accum(NpR);
-  if (smemA > 200 * 1024 || smemR > 200 * 1024) return LOOSB200_ERR_UNSUPPORTED;
-  LB_CUDA(cudaFuncSetAttribute(k_accum, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               smemA > smemR ? smemA : smemR));
 
   double *dT = nullptr, *dAvg = nullptr, *dAvgR = nullptr, *dXf = nullptr, *dOut = nullptr, *dScal = nullptr, *dRc = nullptr, *dCov = nullptr;
   float2* dRff = nullptr;
@@ -696,7 +707,7 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
     k_solve<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(sa);
     AccumArgs aa;
     aa.raw = align->raw; aa.Npad = NpA; aa.N = (uint32_t)Na; aa.xf = dXf; aa.F = (uint32_t)F; aa.avg = dAvg;
-    k_accum<<<grid_accum((uint32_t)F, smemA), ST, smemA, st>>>(aa);
+    launch_accum(aa, st);
     k_finish_iter<<<1, 1024, 0, st>>>(dAvg, dT, tgt_cen, tgt_sum, dScal + 7, (uint32_t)Na, NpA, 1.0 / (double)F, rms_dev);
     launches += 4;
     cudaMemcpyAsync(&rms, rms_dev, sizeof(double), cudaMemcpyDeviceToHost, st);
@@ -708,7 +719,7 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
     cudaMemsetAsync(dAvgR, 0, sizeof(double) * 3 * NpR, st);
     AccumArgs ar;
     ar.raw = rs->raw; ar.Npad = NpR; ar.N = (uint32_t)Nr; ar.xf = dXf; ar.F = (uint32_t)F; ar.avg = dAvgR;
-    k_accum<<<grid_accum((uint32_t)F, smemR), ST, smemR, st>>>(ar);
+    launch_accum(ar, st);
     k_scale<<<(unsigned)((3 * NpR + 255) / 256), 256, 0, st>>>(dAvgR, 3 * NpR, 1.0 / (double)F);
     // per-frame rmsd to the average: rmsd2ref.cpp:238-245
     k_ref_split<<<1, 1024, 0, st>>>(dAvgR, (uint32_t)Nr, NpR, dRff, dRc);

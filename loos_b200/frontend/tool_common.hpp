@@ -60,6 +60,11 @@ inline int stdoutSink(void*, const char* data, size_t n) { return fwrite(data, 1
 // LOOSB200_HOST_TEXT=1 asks for the host writer.
 inline bool gpuText(bool need_host_matrix, unsigned long precision) {
   const char* env = getenv("LOOSB200_HOST_TEXT");
+  if (!need_host_matrix && precision > 9) {
+    static bool told = false;  // a float carries 9 significant digits; beyond that the host writer pads like printf
+    if (!told) std::cerr << "Note- precision " << precision << " exceeds the 9 digits the GPU formatter writes exactly; the matrix is copied to the host and formatted there (slower)\n";
+    told = true;
+  }
   return !need_host_matrix && precision <= 9 && !(env && atoi(env) != 0);
 }
 

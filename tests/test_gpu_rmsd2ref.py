@@ -131,3 +131,27 @@ def test_align_accumulate_and_sharded_driver(lb):
     assert np.abs(sharded["avg"] - built_in["avg"]).max() < 1e-8
     assert np.abs(sharded["rmsd"] - built_in["rmsd"]).max() < RMSD_TOL
     assert np.abs(sharded["xforms"] - built_in["xforms"]).max() < 1e-8
+
+
+@pytest.mark.parametrize("Na,Nr", [(400, 30000), (9000, 9000), (20000, 20000)])
+def test_iterative_mode_large_selections(lb, checker, Na, Nr):
+    """rmsd2ref's default --rmsd is every heavy atom ("!(hydrogen || segid =~ 'SOLV|BULK')",
+    Tools/rmsd2ref.cpp:97-105): tens of thousands of atoms on a membrane system.  The running sums of
+    iterativeAlignment / averageStructure (src/alignment.cpp:355-404, src/ensembles.cpp:91-121) are
+    tiled over atom chunks, so no selection size is refused."""
+    from loos_b200.synth import synth_frames
+    F = 24
+    N = max(Na, Nr)
+    X = synth_frames(F, N, seed=Na + Nr)
+    sa = np.arange(0, Na, dtype=np.uint32) if Na == N else np.sort(np.random.default_rng(1).choice(N, Na, replace=False)).astype(np.uint32)
+    sr = np.arange(0, Nr, dtype=np.uint32)
+    ref_rmsd, ref_xf, ref_avg, ref_it, ref_rms = checker.rmsd2ref_iterative(X[:, sa], X[:, sr], 1e-6, 1000)
+    with lb.FrameSet(X, sel=sa) as fa, lb.FrameSet(X, sel=sr) as fr:
+        r = lb.rmsd2ref_iterative(fa, fr, tol=1e-6, maxiter=1000)
+        from loos_b200 import api
+        S = api.align_accumulate(fa, X[3][sa].astype(np.float64), fr)   # the sharded building block, same size
+    assert r["iters"] == ref_it
+    assert np.abs(r["rmsd"] - ref_rmsd).max() < RMSD_TOL
+    assert np.abs(r["avg"] - ref_avg).max() < 1e-6
+    assert np.abs(r["xforms"] - ref_xf).max() < 1e-6
+    assert S.shape == (Nr, 3) and np.isfinite(S).all()
