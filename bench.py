@@ -400,8 +400,7 @@ def all_to_all(ctx, args, name, F, N, steps, warmup, want_e2e, want_cpu):
 
             def step_e2e(dst):
                 t0 = time.perf_counter()
-                fs0 = lb.FrameSet(Xh, device=devices[0])
-                reps = [fs0] + [fs0.replicate(d) for d in devices[1:]]
+                reps = lb.stage_multi(Xh, devices)
                 t1 = time.perf_counter()
                 lb.rmsds_multi(reps, out=dst, engine=args.engine, want_stats=False)
                 t2 = time.perf_counter()
@@ -439,13 +438,13 @@ def all_to_all(ctx, args, name, F, N, steps, warmup, want_e2e, want_cpu):
             e2e = {"value": pairs_total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": F * N * 12, "d2h_bytes_per_step": F * F * 4,
                    "p2p_bytes_per_step": (world - 1) * F * (N + 3) * 12,
-                   "stage_and_replicate_ms": ms_stage, "call_ms": ms_call,
+                   "stage_ms": ms_stage, "call_ms": ms_call,
                    "d2h_gbs_over_call": F * F * 4 / (ms_call * 1e-3) / 1e9,
                    "delivered": "full symmetric F x F float32 matrix in ONE pinned host buffer" + ("" if sym_ok else " (SYMMETRY CHECK FAILED)"),
                    "to_rank0_hbm": hbm,
-                   "note": "host pinned coords -> loosb200_stage_frames on GPU 0 -> loosb200_replicate to the other %d GPUs (NVLink) -> "
-                           "loosb200_rmsds_self_multi: each GPU copies its row strips + mirror strips into the host matrix over its own PCIe link"
-                           % (world - 1)}
+                   "note": "host pinned coords -> loosb200_stage_frames_multi (each of the %d GPUs uploads its slice over its own PCIe link, "
+                           "slices exchanged over NVLink) -> loosb200_rmsds_self_multi: each GPU copies its row strips + mirror strips "
+                           "into the host matrix over its own PCIe link" % world}
             del X_host
             torch.cuda.empty_cache()
             capi.lib().loosb200_trim()
@@ -507,9 +506,10 @@ def stream_c2(ctx, args, F, N, steps, warmup, want_e2e):
     X = synth_frames_torch(F, N, seed=SEED0 + 2, device=ctx.dev, chunk=4096)
     tgt = X[F // 2].double().cpu().numpy()
     fs = lb.FrameSet(X)
+    res = lb.PinnedMatrix((F,), np.float64, order="C")   # the per-frame series lands in pinned host memory
 
     def step():
-        d = lb.rmsd2ref(fs, tgt)
+        d = lb.rmsd2ref(fs, tgt, out=res.array)
         return d, fs.last_timing()
 
     for _ in range(warmup):
@@ -528,6 +528,8 @@ def stream_c2(ctx, args, F, N, steps, warmup, want_e2e):
     err = np.abs(d[idx] - want)
     parity = {"frames": int(idx.size), "max_abs_err": float(err.max()), "mean_abs_err": float(err.mean()), "tolerance": 1e-4, "checker": kind}
     fs.close()
+    del d, outs
+    res.free()
     e2e = None
     if want_e2e:
         Xh_t = torch.empty((F, N, 3), dtype=torch.float32, pin_memory=True)

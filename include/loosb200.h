@@ -181,6 +181,11 @@ int loosb200_rmsds_self_part_device(loosb200_frames* h, int part, int nparts, fl
  *                   sink receives them in row order.
  * Results are bit-identical to the one-device calls.  out == NULL: stats only. */
 int loosb200_replicate(const loosb200_frames* src, int device, loosb200_frames** out);
+/* loosb200_stage_frames + loosb200_replicate in one, with the upload spread over the devices: device k
+ * stages the k-th slice of the frames over its own PCIe link, then every device collects the other
+ * slices device-to-device.  out[0..n-1] receive the replicas (out[k] on devices[k]). */
+int loosb200_stage_frames_multi(loosb200_frames** out, const int* devices, int n, const float* host_xyz,
+                                size_t F, size_t natoms, const uint32_t* sel, size_t nsel, int layout);
 int loosb200_rmsds_self_multi(loosb200_frames* const* replicas, int n, float* out, size_t ld,
                               loosb200_stats* stats, int engine);
 int loosb200_rmsds_self_multi_device(loosb200_frames* const* replicas, int n, float* out_dev, size_t ld,

@@ -7,9 +7,9 @@ C ABI in include/loosb200.h.  All arithmetic runs in hand-written sm_100a CUDA
 kernels (loos_b200/csrc); there is no CPU path in this package.
 """
 from .api import (FrameSet, rmsds, rmsds_cross, rmsd2ref, rmsd2ref_iterative, part_rows,  # noqa: F401
-                  rmsds_align, rmsds_multi, rmsds_cross_multi, rmsds_text, rmsds_text_multi, PinnedMatrix,
+                  rmsds_align, rmsds_multi, rmsds_cross_multi, rmsds_text, rmsds_text_multi, PinnedMatrix, stage_multi,
                   LoosB200Error)
 
 __all__ = ["FrameSet", "rmsds", "rmsds_cross", "rmsd2ref", "rmsd2ref_iterative", "part_rows",
-           "rmsds_align", "rmsds_multi", "rmsds_cross_multi", "rmsds_text", "rmsds_text_multi", "PinnedMatrix",
+           "rmsds_align", "rmsds_multi", "rmsds_cross_multi", "rmsds_text", "rmsds_text_multi", "PinnedMatrix", "stage_multi",
            "LoosB200Error"]

@@ -181,10 +181,12 @@ def _dptr(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def rmsd2ref(fs_align, ref_align, fs_rmsd=None, ref_rmsd=None, want_xforms=False):
+def rmsd2ref(fs_align, ref_align, fs_rmsd=None, ref_rmsd=None, want_xforms=False, out=None):
     """Per-frame RMSD to a reference after superposition (Tools/rmsd2ref.cpp with
     --target).  ref_align: (N_a, 3) target align-selection coords, or None for no
-    alignment; fs_rmsd / ref_rmsd: the rmsd selection (default: the align one)."""
+    alignment; fs_rmsd / ref_rmsd: the rmsd selection (default: the align one).
+    out: optional preallocated float64 array of F values (pinned memory, e.g. PinnedMatrix((F,),
+    np.float64).array, lets the result copy run at the PCIe rate)."""
     F = fs_align.F
     ra = None if ref_align is None else np.ascontiguousarray(ref_align, dtype=np.float64).reshape(-1)
     rr = None if ref_rmsd is None else np.ascontiguousarray(ref_rmsd, dtype=np.float64).reshape(-1)
@@ -193,7 +195,9 @@ def rmsd2ref(fs_align, ref_align, fs_rmsd=None, ref_rmsd=None, want_xforms=False
     nr = (fs_rmsd or fs_align).N
     if rr is not None and rr.size != 3 * nr:
         raise LoosB200Error(capi.ERR_SIZE_MISMATCH, "Cannot compute RMSD between groups with different sizes")
-    out = np.zeros(F)
+    if out is None:
+        out = np.zeros(F)
+    assert out.dtype == np.float64 and out.shape == (F,) and out.flags.c_contiguous
     xf = np.zeros((F, 4, 4)) if want_xforms else None
     check(lib().loosb200_rmsd2ref(fs_align._h, None if fs_rmsd is None else fs_rmsd._h, _dptr(ra), _dptr(rr),
                                   _dptr(out), _dptr(xf)))
@@ -279,6 +283,25 @@ class PinnedMatrix:
             self._p = None
 
     __del__ = free
+
+
+def stage_multi(coords, devices, sel=None, layout="xyz"):
+    """FrameSets of the same host frames on several GPUs (loosb200_stage_frames_multi): every device
+    uploads its slice over its own PCIe link, the slices are exchanged device-to-device."""
+    lay = {"xyz": capi.LAYOUT_XYZ, "planes": capi.LAYOUT_PLANES}[layout]
+    a = _as_f32(coords)
+    assert a.ndim == 3
+    F = a.shape[0]
+    natoms = a.shape[1] if lay == capi.LAYOUT_XYZ else a.shape[2]
+    sel_arr = None if sel is None else np.ascontiguousarray(sel, dtype=np.uint32)
+    sel_p = None if sel_arr is None else sel_arr.ctypes.data_as(C.POINTER(C.c_uint32))
+    nsel = 0 if sel_arr is None else sel_arr.size
+    n = len(devices)
+    hs = (C.c_void_p * n)()
+    devs = (C.c_int * n)(*[int(d) for d in devices])
+    check(lib().loosb200_stage_frames_multi(hs, devs, n, a.ctypes.data_as(C.c_void_p), F, natoms, sel_p, nsel, lay))
+    N = nsel if sel_arr is not None else natoms
+    return [FrameSet._wrap(C.c_void_p(hs[k]), F, N, int(devices[k])) for k in range(n)]
 
 
 def _handles(sets):

@@ -64,6 +64,7 @@ SIGNATURES = {
     "loosb200_rmsds_cross_text": (_i, [_vp, _vp, C.c_uint, SINK, _vp, _sp, _i]),
     "loosb200_last_timing": (_i, [_vp, _dp, _dp]),
     "loosb200_measure_int8_peak": (_i, [_i, C.c_double, _dp, _dp]),
+    "loosb200_stage_frames_multi": (_i, [C.POINTER(_vp), C.POINTER(_i), _i, _vp, _sz, _sz, _up, _sz, _i]),
     "loosb200_replicate": (_i, [_vp, _i, C.POINTER(_vp)]),
     "loosb200_rmsds_self_multi": (_i, [C.POINTER(_vp), _i, _vp, _sz, _sp, _i]),
     "loosb200_rmsds_self_multi_device": (_i, [C.POINTER(_vp), _i, _vp, _sz, _sp, _i]),

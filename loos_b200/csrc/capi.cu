@@ -1,6 +1,7 @@
 // C-ABI glue: argument checking, tile-space partitioning, band pipelining of the
 // result copy, error reporting.  See include/loosb200.h for the contract.
 #include <limits.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -217,6 +218,7 @@ std::vector<uint32_t> contiguous_cuts(size_t F, int nparts, bool self) {
 int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric, bool packed,
               const std::vector<uint32_t>& rows, float* out, OutKind okind, size_t ld,
               loosb200_stats* stats, int engine) {
+  NvtxRange nvtx_call(self ? "loosb200 all-to-all (self)" : "loosb200 all-to-all (cross)");
   LB_CUDA(cudaSetDevice(a->device));
   const bool engine_auto = engine == LOOSB200_ENGINE_AUTO;
   engine = pick_engine(engine, a);
@@ -265,14 +267,17 @@ int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric,
   uint32_t *d_rows = nullptr, *d_prefix = nullptr;
   float* d_out = nullptr;
   double* d_stats = nullptr;
-  cudaStream_t copy_stream = nullptr;
+  // the strips of consecutive bands leave on alternating streams: two copies in flight keep the link
+  // busy across the gaps between 2-D transfers (LOOSB200_COPY_STREAMS=1: one stream)
+  cudaStream_t copy_streams[2] = {nullptr, nullptr};
+  const int ncopy = (getenv("LOOSB200_COPY_STREAMS") && atoi(getenv("LOOSB200_COPY_STREAMS")) == 1) ? 1 : 2;
   std::vector<void*> scratch;  // per-launch device scratch of the engines, released after the final sync
   std::vector<cudaEvent_t> evs(B.bands.size(), nullptr);
   auto cleanup = [&]() {
     dev_release(d_rows); dev_release(d_prefix); dev_release(d_stats);
     for (void* p : scratch) dev_release(p);
     if (copy) dev_release(d_out);
-    if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (cudaStream_t cs : copy_streams) if (cs) cudaStreamDestroy(cs);
     for (auto e : evs) if (e) cudaEventDestroy(e);
   };
   bool ok = dev_alloc_t(&d_rows, sizeof(uint32_t) * std::max<size_t>(1, B.rows.size())) == cudaSuccess &&
@@ -280,8 +285,8 @@ int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric,
             dev_alloc_t(&d_stats, 2 * sizeof(double)) == cudaSuccess;
   if (ok && copy) {
     const size_t n = packed ? out_rows * FB : strip_floats;
-    ok = dev_alloc_t(&d_out, sizeof(float) * std::max<size_t>(1, n)) == cudaSuccess &&
-         cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = dev_alloc_t(&d_out, sizeof(float) * std::max<size_t>(1, n)) == cudaSuccess;
+    for (int c = 0; c < ncopy && ok; ++c) ok = cudaStreamCreateWithFlags(&copy_streams[c], cudaStreamNonBlocking) == cudaSuccess;
     for (auto& e : evs) if (ok) ok = cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
   } else if (okind == OutKind::Device) {
     d_out = out;
@@ -329,6 +334,7 @@ int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric,
       launches += 1;
     }
     if (rc == LOOSB200_OK && copy) {
+      cudaStream_t copy_stream = copy_streams[k % ncopy];
       cudaEventRecord(evs[k], st);
       cudaStreamWaitEvent(copy_stream, evs[k], 0);
       if (packed) {
@@ -355,8 +361,9 @@ int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric,
   double hs[2] = {0.0, 0.0};
   if (stats) cudaMemcpyAsync(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st);
   cudaEventRecord(a->timing.ev[3], st);
+  NvtxRange nvtx_wait("loosb200 contract + copy (wait)");
   cudaError_t e = cudaStreamSynchronize(st);
-  if (e == cudaSuccess && copy_stream) e = cudaStreamSynchronize(copy_stream);
+  for (cudaStream_t cs : copy_streams) if (e == cudaSuccess && cs) e = cudaStreamSynchronize(cs);
   if (e == cudaSuccess) e = cudaGetLastError();
   cleanup();
   if (rc != LOOSB200_OK) return rc;

@@ -9,9 +9,20 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges show up in nsys / ncu timelines, free otherwise
+
 #include "../../include/loosb200.h"
 
 namespace loosb200 {
+
+// NVTX range for the duration of a scope: the stages of a call (stage / quantise / contract / copy)
+// are named in profiler timelines.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // Frames are grouped in blocks of FRAMES_PER_BLOCK; one block of frames occupies
 // ROWS_PER_BLOCK rows of the tensor-core operand planes (row = 3*j + axis for
@@ -23,11 +34,12 @@ constexpr int ROWS_PER_BLOCK = 32;
 constexpr int BLOCKS_PER_TILE = 4;
 constexpr int TILE_FRAMES = FRAMES_PER_BLOCK * BLOCKS_PER_TILE;  // 40
 constexpr int TILE_ROWS = ROWS_PER_BLOCK * BLOCKS_PER_TILE;      // 128
-// Tensor path: an accumulator tile is 40 "a" frames (128 TMEM lanes) x 30 "b"
-// frames (96 TMEM columns per weight class, 5 classes = 480 of 512 columns).
-constexpr int COL_BLOCKS_PER_TILE = 3;
-constexpr int COL_TILE_FRAMES = FRAMES_PER_BLOCK * COL_BLOCKS_PER_TILE;  // 30
-constexpr int COL_TILE_ROWS = ROWS_PER_BLOCK * COL_BLOCKS_PER_TILE;      // 96
+// Tensor path: an accumulator tile is 40 "a" frames (128 TMEM lanes) x 32 "b"
+// frames (96 TMEM columns per weight class, 5 classes = 480 of 512 columns).  The "b" operand
+// is a second copy of the digit planes with DENSE rows (row = 3*frame + axis, no padding): TMEM
+// columns have no warp structure to respect, so all 96 columns of a class carry data.
+constexpr int COL_TILE_FRAMES = 32;
+constexpr int COL_TILE_ROWS = 3 * COL_TILE_FRAMES;  // 96
 constexpr int K_CHUNK = 128;   // atoms (bytes of int8) per pipeline stage = one 128-byte swizzle row
 constexpr int NUM_SLICES = 3;  // signed 8-bit digits of the 24-bit fixed-point coordinate
 // int32 accumulators hold up to 3 slice products of magnitude <= 2^14 per atom.
@@ -90,14 +102,15 @@ struct loosb200_frames {
 
   // tensor-core operands (lazy): q8[(slice*rows_total + row)*Kpad + atom]
   int8_t* q8 = nullptr;
+  int8_t* q8b = nullptr;    // the same digits as the "b" operand: q8b[(slice*rows_total_b + 3*frame + axis)*Kpad + atom]
   double* gq = nullptr;     // [F] sum q^2 of the quantised frame (exact integer, rounded once to double)
   int* unit_log2_dev = nullptr;
   int unit_log2 = 0;
   bool quantised = false;
-  size_t rows_total = 0, Kpad = 0;
+  size_t rows_total = 0, rows_total_b = 0, Kpad = 0;
   CUtensorMap tmapA;  // 3-D map over q8 (atom, row, slice), box 128 x 128 x 3
-  CUtensorMap tmapB96, tmapB48;  // same tensor, boxes 128 x 96 x 1 and 128 x 48 x 1: the halves of a "b" stage a CTA of a pair loads
-  CUtensorMap tmapB;  // same tensor, box 128 x 96 x 3
+  CUtensorMap tmapB;  // 3-D map over q8b, box 128 x 96 x 3
+  CUtensorMap tmapB96, tmapB48;  // q8b, boxes 128 x 96 x 1 and 128 x 48 x 1: the halves of a "b" stage a CTA of a pair loads
   bool tmap_valid = false;
 
   cudaStream_t stream = nullptr;

@@ -112,6 +112,7 @@ using namespace loosb200;
 extern "C" int loosb200_replicate(const loosb200_frames* src, int device, loosb200_frames** out) {
   if (!src || !out || src->stager) return LOOSB200_ERR_INVALID;
   if (device < 0 || device >= loosb200_device_count()) return LOOSB200_ERR_NO_DEVICE;
+  NvtxRange nvtx("loosb200 replicate (device to device)");
   // an empty staged set on `device`, then plane-for-plane copies (peer-to-peer over NVLink when the
   // devices allow it, through the host otherwise); the digit planes are re-derived there on first use
   // from the same fp32 planes and centroids, hence bit-identical
@@ -131,6 +132,58 @@ extern "C" int loosb200_replicate(const loosb200_frames* src, int device, loosb2
   h->timing.valid = false;
   *out = h;
   return LOOSB200_OK;
+}
+
+// Host frames -> a replica on every device, with the upload itself spread over the devices: device d
+// stages frames [F d/n, F (d+1)/n) from the caller's buffer over ITS OWN PCIe link (gather of the
+// selection, centroids, G: the ordinary staging path), then every device collects the other slices
+// device-to-device.  The host buffer crosses PCIe once in total, n links wide.
+extern "C" int loosb200_stage_frames_multi(loosb200_frames** out, const int* devices, int n, const float* host_xyz,
+                                           size_t F, size_t natoms, const uint32_t* sel, size_t nsel, int layout) {
+  if (!out || !devices || n < 1 || !host_xyz) return LOOSB200_ERR_INVALID;
+  for (int d = 0; d < n; ++d) out[d] = nullptr;
+  if (n == 1 || F < (size_t)n * 64) {  // nothing to gain from splitting a small upload
+    int rc = loosb200_stage_frames(&out[0], host_xyz, F, natoms, sel, nsel, layout, devices[0]);
+    for (int d = 1; d < n && rc == LOOSB200_OK; ++d) rc = loosb200_replicate(out[0], devices[d], &out[d]);
+    if (rc) for (int d = 0; d < n; ++d) { loosb200_free(out[d]); out[d] = nullptr; }
+    return rc;
+  }
+  NvtxRange nvtx("loosb200 stage frames on several devices");
+  std::vector<size_t> off(n + 1);
+  for (int d = 0; d <= n; ++d) off[d] = F * (size_t)d / (size_t)n;
+  std::vector<loosb200_frames*> part(n, nullptr);
+  int rc = on_all_devices(n, [&](int d) -> int {
+    return loosb200_stage_frames(&part[d], host_xyz + off[d] * natoms * 3, off[d + 1] - off[d], natoms, sel, nsel, layout, devices[d]);
+  });
+  if (rc == LOOSB200_OK)
+    for (int d = 0; d < n; ++d)
+      for (int s = 0; s < n; ++s) enable_peer(devices[d], devices[s]);
+  for (int d = 0; d < n && rc == LOOSB200_OK; ++d) rc = alloc_frames(&out[d], F, part[0]->N, devices[d]);
+  cudaError_t e = cudaSuccess;
+  if (rc == LOOSB200_OK) {
+    for (int d = 0; d < n && e == cudaSuccess; ++d) {  // every device pulls all slices (its own included) on its stream
+      loosb200_frames* h = out[d];
+      cudaSetDevice(h->device);
+      for (int k = 0; k < n && e == cudaSuccess; ++k) {
+        const int s = (d + k) % n;  // start with the local slice, then walk the peers in a different order per device
+        const loosb200_frames* p = part[s];
+        const size_t f0 = off[s], nf = off[s + 1] - off[s];
+        e = cudaMemcpyPeerAsync(h->raw + f0 * 3 * h->Npad, h->device, p->raw, p->device, sizeof(float) * nf * 3 * h->Npad, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(h->centroid + f0 * 3, h->device, p->centroid, p->device, sizeof(double) * 3 * nf, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(h->gd + f0, h->device, p->gd, p->device, sizeof(double) * nf, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(h->maxabs + f0, h->device, p->maxabs, p->device, sizeof(float) * nf, h->stream);
+      }
+    }
+    for (int d = 0; d < n; ++d) {
+      cudaSetDevice(out[d]->device);
+      const cudaError_t es = cudaStreamSynchronize(out[d]->stream);
+      if (e == cudaSuccess) e = es;
+    }
+  }
+  for (int d = 0; d < n; ++d) loosb200_free(part[d]);
+  if (rc == LOOSB200_OK && e != cudaSuccess) rc = cuda_fail(e, "stage_frames_multi", __FILE__, __LINE__);
+  if (rc) for (int d = 0; d < n; ++d) { loosb200_free(out[d]); out[d] = nullptr; }
+  return rc;
 }
 
 extern "C" int loosb200_rmsds_self_multi(loosb200_frames* const* replicas, int n, float* out, size_t ld,

@@ -11,7 +11,7 @@
 //
 // Tile = 128 TMEM lanes x 96 columns per class:
 //   lane   = 32*blk + 3*jf + axis   -> "a" frame 10*blk + jf of the row tile (40 frames)
-//   column = 96*s + 32*g + 3*jb + axis' -> "b" frame 10*g + jb of the column tile (30 frames)
+//   column = 96*s + 3*jb + axis'    -> "b" frame jb of the column tile (32 frames, dense)
 // 5 x 96 = 480 of the 512 TMEM columns.  The three axes of one "a" frame sit in
 // three adjacent lanes of one warp, so the epilogue assembles each 3x3 with a few
 // warp shuffles and solves one pair per lane (QCP, qcp.cuh) straight out of TMEM:
@@ -22,7 +22,7 @@
 //            3 digits = 48 KB) and one for B (128 B x 96 x 3 = 36 KB), SWIZZLE_128B
 //   warp 1   TMEM allocator + MMA issuer: per 32-atom K step six tcgen05.mma
 //            (three with N = 192 spanning two adjacent classes, three with N = 96)
-//   warps 2-13 epilogue, one (lane quarter, 10-frame column group) each:
+//   warps 2-13 epilogue, one (lane quarter, 11/11/10-frame column group = 33/33/30 columns) each:
 //            tcgen05.ld -> exact integer combine in fp64 -> shuffle -> quartic coefficients
 //            (fp64) -> TMEM handed back to the MMA warp -> fp32 Newton + float-float
 //            correction -> float32 tile in smem -> coalesced (and mirrored) stores.
@@ -63,6 +63,7 @@ template <> struct Shape<2> {
 };
 template <int CL> __host__ __device__ constexpr int stage_bytes() { return A_STAGE_BYTES + Shape<CL>::B_STAGE_BYTES; }
 constexpr int NUM_CLASSES = 5;
+constexpr int GROUP_FRAMES = 11;  // "b" frames per epilogue column group (33 columns); the third group has 10
 constexpr int CLASS_COLS = COL_TILE_ROWS;  // 96
 constexpr int TMEM_COLS = 512;
 constexpr int NTHREADS = 448;  // 2 control warps + 12 epilogue warps; 65536/448 -> 144 regs
@@ -208,6 +209,17 @@ __device__ __forceinline__ void tc_wait_ld16(uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
                  "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+
+__device__ __forceinline__ void tc_ld2(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld18(uint32_t (&r)[18]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17])
                :: "memory");
 }
 
@@ -477,13 +489,14 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else {
     // ================= epilogue (warps 2..13) =================
     const int q = warp & 3;                 // TMEM lane quarter == frame block of the row tile
-    const int g = (warp - 2) >> 2;          // 10-frame column group of the column tile
+    const int g = (warp - 2) >> 2;          // column group of the column tile: frames [11 g, 11 g + 11) (10 in the last)
+    const int nfr = g < 2 ? GROUP_FRAMES : COL_TILE_FRAMES - 2 * GROUP_FRAMES;
     const int et = (warp - 2) * 32 + lane;  // 0..383
     const int jf = lane / 3, al = lane - 3 * jf;
     const bool active = lane < 30;
     const int a_local = q * FRAMES_PER_BLOCK + jf;
     const int tri = lane - al;              // first lane of this frame's lane triple
-    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 32);
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 3 * GROUP_FRAMES);
     uint32_t tphase = 0, buf = 0;
     float sum_h = 0.0f, sum_l = 0.0f, tmax = 0.0f;
     const double inv_n = 1.0 / (double)a.N;
@@ -498,15 +511,16 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t i = I * TILE_FRAMES + a_local;
       const bool i_ok = active && i < a.FA && !masked;  // a shadow tile contributes nothing
       const double ga = i_ok ? __ldg(a.gA + i) : 0.0;
-      // The ten "b" frames of this warp's column group are solved in four rounds: the lanes of a
-      // triple (al = 0, 1, 2) own frames base + al for base = 0, 3, 5, 8 (3, 2, 3, 2 frames).  Rounds
-      // 0 and 1 only need TMEM columns 0..14, so they run while the loads of columns 16..31 are in
-      // flight: the latency-bound coefficient chains and the issue-bound combine fill each other's gaps.
-      constexpr int RBASE[4] = {0, 3, 5, 8}, RCNT[4] = {3, 2, 3, 2};
+      // The eleven (ten) "b" frames of this warp's column group are solved in four rounds: the lanes of
+      // a triple (al = 0, 1, 2) own frames base + al for base = 0, 3, 6, 9 (3, 3, 3, 2 frames; the last
+      // group has no frame 10).  Rounds 0 and 1 only need the group's columns 0..17, so they run while
+      // the loads of columns 18..32 are in flight: the latency-bound coefficient chains and the
+      // issue-bound combine fill each other's gaps.
+      constexpr int RBASE[4] = {0, 3, 6, 9}, RCNT[4] = {3, 3, 3, 2};
       double gbq[4];  // G of the four "b" frames this lane solves against (prefetched)
 #pragma unroll
       for (int round = 0; round < 4; ++round) {
-        const uint32_t j = J * COL_TILE_FRAMES + g * FRAMES_PER_BLOCK + RBASE[round] + (al < RCNT[round] ? al : 0);
+        const uint32_t j = J * COL_TILE_FRAMES + g * GROUP_FRAMES + RBASE[round] + (RBASE[round] + al < nfr ? al : 0);
         gbq[round] = j < a.FB ? __ldg(a.gB + j) : 0.0;
       }
       mbar_wait<32>(&ctl->tmem_full, tphase);
@@ -514,21 +528,21 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_after();
       LB_TICK(0);  // waiting for the accumulators
 
-      double v[32];  // v[3 jb + axis'] = sum_s 2^(8s) D_s, exact (|v| < 2^58 rounds at 2^-53)
+      double v[3 * GROUP_FRAMES];  // v[3 jb + axis'] = sum_s 2^(8s) D_s, exact (|v| < 2^58 rounds at 2^-53)
 #pragma unroll
-      for (int c = 0; c < 32; ++c) v[c] = 0.0;
+      for (int c = 0; c < 3 * GROUP_FRAMES; ++c) v[c] = 0.0;
       QcpPolyF polf[4];
       float e0s[4];
       int state[4];  // 0: no entry, 1: zero, 2: solve
 
       // int32 -> double without the conversion unit: the bits (0x433+8s)<<52 | (D ^ 2^31)
       // are the double 2^(52+8s) + (D + 2^31) 2^(8s); subtracting the bias leaves D 2^(8s).
-      auto combine = [&](const uint32_t (&r)[16], int s, int c0) {
+      auto combine = [&](const uint32_t (&r)[18], int s, int c0, int count) {
         const uint32_t hi = (uint32_t)(0x433 + 8 * s) << 20;
         const double bias = __hiloint2double((int)hi, (int)0x80000000u);
 #pragma unroll
-        for (int c = 0; c < 16; ++c)
-          if (c0 + c < 30) v[c0 + c] += __hiloint2double((int)hi, (int)(r[c] ^ 0x80000000u)) - bias;
+        for (int c = 0; c < 18; ++c)
+          if (c < count) v[c0 + c] += __hiloint2double((int)hi, (int)(r[c] ^ 0x80000000u)) - bias;
       };
       // exchange rows inside each lane triple and build the quartic of this lane's pair (fp64)
       auto do_round = [&](const int round) {
@@ -553,8 +567,8 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           R[6 + be] = __shfl_sync(0xffffffffu, s2[be], src2);
         }
         const int jb = RBASE[round] + al;
-        const uint32_t j = J * COL_TILE_FRAMES + g * FRAMES_PER_BLOCK + jb;
-        const bool owner = active && al < RCNT[round];
+        const uint32_t j = J * COL_TILE_FRAMES + g * GROUP_FRAMES + jb;
+        const bool owner = active && al < RCNT[round] && jb < nfr;
         // 0: no entry (idle lane, out of range, or j > i of the self matrix), 1: exact zero (the
         // diagonal, Tools/rmsds.cpp:359-365, or every atom at the centroid in both frames), 2: solve.
         // Idle lanes run the same arithmetic on whatever their registers hold; their results are
@@ -569,26 +583,33 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         polf[round] = qcp_poly_split(qcp_poly(R, e0));
       };
 
-      // ---- drain, software-pipelined 16-column loads: columns 0..15 of the five classes first ----
+      // ---- drain, software-pipelined: columns 0..17 of the five classes first (x16 + x2), then 18..32 ----
+      // (The x16 load of the second half reads one column past the group; for the last group that is
+      // the next class's first columns -- loaded, never used.)
       // On sm_100 CUDA-core fp64 shares the tensor pipe with tcgen05.mma and gets ~10 % of its
       // throughput while MMAs run (tools/ubench_contend.cu), so the accumulators are handed back
       // only AFTER the fp64-heavy part; the fp32 Newton recurrences, the final correction and the
       // stores then overlap the next tile's MMAs.
-      uint32_t rb[2][16];
-      tc_ld16(tlane, rb[0]);
+      uint32_t rb[2][18];
+      auto load_a = [&](uint32_t col, uint32_t (&r)[18]) {
+        tc_ld16(col, reinterpret_cast<uint32_t(&)[16]>(r));
+        tc_ld2(col + 16, r[16], r[17]);
+      };
+      load_a(tlane, rb[0]);
 #pragma unroll
       for (int s5 = 0; s5 < NUM_CLASSES; ++s5) {
-        tc_wait_ld16(rb[s5 & 1]);
-        tc_ld16(tlane + (uint32_t)(s5 + 1 < NUM_CLASSES ? (s5 + 1) * CLASS_COLS : 16), rb[(s5 + 1) & 1]);
-        combine(rb[s5 & 1], s5, 0);
+        tc_wait_ld18(rb[s5 & 1]);
+        if (s5 + 1 < NUM_CLASSES) load_a(tlane + (uint32_t)((s5 + 1) * CLASS_COLS), rb[(s5 + 1) & 1]);
+        else tc_ld16(tlane + 18u, reinterpret_cast<uint32_t(&)[16]>(rb[(s5 + 1) & 1]));
+        combine(rb[s5 & 1], s5, 0, 18);
       }
-      // columns 16..31: class 0 is in flight in rb[1]
+      // columns 18..32: class 0 is in flight in rb[1]
       do_round(0);
 #pragma unroll
       for (int s5 = 0; s5 < NUM_CLASSES; ++s5) {
-        tc_wait_ld16(rb[(s5 + 1) & 1]);
-        if (s5 + 1 < NUM_CLASSES) tc_ld16(tlane + (uint32_t)((s5 + 1) * CLASS_COLS + 16), rb[s5 & 1]);
-        combine(rb[(s5 + 1) & 1], s5, 16);
+        tc_wait_ld18(rb[(s5 + 1) & 1]);
+        if (s5 + 1 < NUM_CLASSES) tc_ld16(tlane + (uint32_t)((s5 + 1) * CLASS_COLS + 18), reinterpret_cast<uint32_t(&)[16]>(rb[s5 & 1]));
+        combine(rb[(s5 + 1) & 1], s5, 18, 15);
         if (s5 == 1) do_round(1);
       }
       tc_fence_before();  // this warp's TMEM reads are complete
@@ -624,8 +645,8 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
       for (int round = 0; round < 4; ++round) {
         const int jb = RBASE[round] + al;
-        const int b_local = g * FRAMES_PER_BLOCK + jb;
-        const bool owner = active && al < RCNT[round];
+        const int b_local = g * GROUP_FRAMES + jb;
+        const bool owner = active && al < RCNT[round] && jb < nfr;
         float val = state[round] == 1 ? 0.0f : -1.0f;  // -1: "no entry"
         if (state[round] == 2) {
           bool ok;

@@ -7,8 +7,10 @@
 //   k_unit      picks the power-of-two fixed-point unit from the global max.
 //   k_quantise  centres in fp64, rounds to the 24-bit fixed-point grid, splits
 //               into three signed 8-bit digits and writes them as K-major operand
-//               planes for tcgen05 (row = 32*(f/10) + 3*(f%10) + axis), together
-//               with the exact integer sum of squares G.
+//               planes for tcgen05, once with the "a" row layout (row = 32*(f/10) +
+//               3*(f%10) + axis: a frame's axes in one warp's TMEM lanes) and once dense
+//               (row = 3*f + axis: the "b" operand), together with the exact integer
+//               sum of squares G.
 //
 // All three are HBM-bound byte movers: one CTA per frame, coalesced reads of the
 // source frame, coalesced writes of the planes.
@@ -128,18 +130,20 @@ __global__ void k_unit(const float* __restrict__ maxabs, size_t F, int force, in
 
 __global__ void __launch_bounds__(256)
 k_quantise(const float* __restrict__ raw, const double* __restrict__ centroid, size_t N,
-           size_t Npad, size_t rows_total, size_t Kpad, const int* __restrict__ unit_log2,
-           int8_t* __restrict__ q8, double* __restrict__ gq) {
+           size_t Npad, size_t rows_total, size_t rows_total_b, size_t Kpad,
+           const int* __restrict__ unit_log2, int8_t* __restrict__ q8, int8_t* __restrict__ q8b,
+           double* __restrict__ gq) {
   __shared__ long long red[32];
   const size_t f = blockIdx.x;
   const double inv_unit = exp2(-(double)unit_log2[0]);
   const size_t row0 = (f / FRAMES_PER_BLOCK) * ROWS_PER_BLOCK + (f % FRAMES_PER_BLOCK) * 3;
-  const size_t plane = rows_total * Kpad;
+  const size_t plane = rows_total * Kpad, plane_b = rows_total_b * Kpad;
   long long g = 0;
   for (int axis = 0; axis < 3; ++axis) {
     const float* p = raw + (f * 3 + axis) * Npad;
     const double c = centroid[f * 3 + axis];
     int8_t* d0 = q8 + (row0 + axis) * Kpad;
+    int8_t* b0 = q8b + (f * 3 + axis) * Kpad;
     for (int i = threadIdx.x; i < (int)N; i += blockDim.x) {
       const long long q = __double2ll_rn(((double)p[i] - c) * inv_unit);
       g += q * q;
@@ -152,6 +156,9 @@ k_quantise(const float* __restrict__ raw, const double* __restrict__ centroid, s
       d0[i] = (int8_t)x0;
       d0[plane + i] = (int8_t)x1;
       d0[2 * plane + i] = (int8_t)x2;
+      b0[i] = (int8_t)x0;
+      b0[plane_b + i] = (int8_t)x1;
+      b0[2 * plane_b + i] = (int8_t)x2;
     }
   }
   // exact integer block sum
@@ -181,22 +188,27 @@ int ensure_quantised(loosb200_frames* h, int force_unit_log2) {
   if (h->quantised && (force_unit_log2 == INT_MIN || force_unit_log2 == h->unit_log2))
     return LOOSB200_OK;
   if (h->N > TENSOR_MAX_ATOMS) return LOOSB200_ERR_UNSUPPORTED;
+  NvtxRange nvtx("loosb200 quantise (fixed-point digit planes)");
   LB_CUDA(cudaSetDevice(h->device));
   const size_t nblocks = (h->F + FRAMES_PER_BLOCK - 1) / FRAMES_PER_BLOCK;
   const size_t ntiles = (nblocks + BLOCKS_PER_TILE - 1) / BLOCKS_PER_TILE;
-  // a 96-row B box may start at the last frame block: pad so that no box runs out of bounds
   h->rows_total = ntiles * TILE_ROWS + TILE_ROWS;
+  // dense "b" rows, a whole number of 96-row column tiles (plus one of slack): no TMA box leaves the tensor
+  h->rows_total_b = ((h->F + COL_TILE_FRAMES - 1) / COL_TILE_FRAMES + 1) * COL_TILE_ROWS;
   h->Kpad = ((h->N + K_CHUNK - 1) / K_CHUNK) * K_CHUNK;
   const size_t bytes = (size_t)NUM_SLICES * h->rows_total * h->Kpad;
+  const size_t bytes_b = (size_t)NUM_SLICES * h->rows_total_b * h->Kpad;
   if (!h->q8) {
     if (dev_alloc_t(&h->q8, bytes) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
+    if (dev_alloc_t(&h->q8b, bytes_b) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
     if (dev_alloc_t(&h->gq, sizeof(double) * h->F) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
     if (dev_alloc_t(&h->unit_log2_dev, 2 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
   }
   LB_CUDA(cudaMemsetAsync(h->q8, 0, bytes, h->stream));
+  LB_CUDA(cudaMemsetAsync(h->q8b, 0, bytes_b, h->stream));
   k_unit<<<1, 1024, 0, h->stream>>>(h->maxabs, h->F, force_unit_log2, h->unit_log2_dev);
   k_quantise<<<(unsigned)h->F, 256, 0, h->stream>>>(h->raw, h->centroid, h->N, h->Npad, h->rows_total,
-                                                    h->Kpad, h->unit_log2_dev, h->q8, h->gq);
+                                                    h->rows_total_b, h->Kpad, h->unit_log2_dev, h->q8, h->q8b, h->gq);
   LB_CUDA(cudaGetLastError());
   int e[2];
   LB_CUDA(cudaMemcpyAsync(e, h->unit_log2_dev, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
@@ -210,14 +222,15 @@ int ensure_quantised(loosb200_frames* h, int force_unit_log2) {
   // 3-D tensor map (atom, row, slice); one TMA box = 128 atoms x 128 rows x 3 slices.
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   if (!enc) { set_last_error("cuTensorMapEncodeTiled not available"); return LOOSB200_ERR_CUDA; }
-  cuuint64_t dims[3] = {(cuuint64_t)h->Kpad, (cuuint64_t)h->rows_total, (cuuint64_t)NUM_SLICES};
-  cuuint64_t strides[2] = {(cuuint64_t)h->Kpad, (cuuint64_t)(h->rows_total * h->Kpad)};
   cuuint32_t estr[3] = {1, 1, 1};
   for (int which = 0; which < 4; ++which) {
+    const size_t nrows = which == 0 ? h->rows_total : h->rows_total_b;
+    cuuint64_t dims[3] = {(cuuint64_t)h->Kpad, (cuuint64_t)nrows, (cuuint64_t)NUM_SLICES};
+    cuuint64_t strides[2] = {(cuuint64_t)h->Kpad, (cuuint64_t)(nrows * h->Kpad)};
     const cuuint32_t rows[4] = {TILE_ROWS, COL_TILE_ROWS, COL_TILE_ROWS, COL_TILE_ROWS / 2};
     cuuint32_t box[3] = {(cuuint32_t)K_CHUNK, rows[which], (cuuint32_t)(which < 2 ? NUM_SLICES : 1)};
     CUtensorMap* dst = which == 0 ? &h->tmapA : which == 1 ? &h->tmapB : which == 2 ? &h->tmapB96 : &h->tmapB48;
-    CUresult r = enc(dst, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->q8, dims, strides, box,
+    CUresult r = enc(dst, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, which == 0 ? h->q8 : h->q8b, dims, strides, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -434,6 +447,7 @@ extern "C" int loosb200_stage_frames(loosb200_frames** out, const float* host_xy
                                      size_t natoms, const uint32_t* sel, size_t nsel, int layout,
                                      int device) {
   if (!host_xyz) return LOOSB200_ERR_INVALID;
+  NvtxRange nvtx("loosb200 stage frames (H2D + gather + centre)");
   loosb200_frames* h = nullptr;
   int rc = loosb200_stage_begin(&h, F, natoms, sel, nsel, layout, device);
   if (rc) return rc;
@@ -448,7 +462,7 @@ extern "C" void loosb200_free(loosb200_frames* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->stager) { delete h->stager; h->stager = nullptr; }
   dev_release(h->raw); dev_release(h->centroid); dev_release(h->gd); dev_release(h->maxabs);
-  dev_release(h->q8); dev_release(h->gq); dev_release(h->unit_log2_dev);
+  dev_release(h->q8); dev_release(h->q8b); dev_release(h->gq); dev_release(h->unit_log2_dev);
   for (int i = 0; i < 4; ++i) if (h->timing.ev[i]) cudaEventDestroy(h->timing.ev[i]);
   for (cudaEvent_t e : h->timing.kev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);

@@ -158,3 +158,36 @@ def test_tools_gpus_option(lb, tmp_path):
         mr = subprocess.run([tool.replace("rmsds", "multi-rmsds"), "--gpus", g, "--stats", "1", pdb, dcd, dcd], capture_output=True, check=True)
         outs[-1] += (mr.stdout.split(b"\n", 1)[1], mr.stderr)
     assert outs[0] == outs[1]
+
+
+def test_stage_multi_equals_stage_and_replicate(lb):
+    """loosb200_stage_frames_multi: every device uploads its own slice of the frames, the slices are
+    exchanged device-to-device -- the replicas must be indistinguishable from a staged + replicated set."""
+    from loos_b200 import capi
+    from loos_b200.synth import synth_frames
+    nd = capi.device_count()
+    F, natoms = 1500, 400
+    X = synth_frames(F, natoms, seed=21)
+    sel = np.arange(3, natoms, 2, dtype=np.uint32)
+    devices = [k % nd for k in range(3)]
+    reps = lb.stage_multi(X, devices, sel=sel)
+    try:
+        with lb.FrameSet(X, sel=sel) as one:
+            M1, s1 = lb.rmsds(one)
+            c1 = one.centroids()
+        for r in reps:
+            assert r.F == F and r.N == len(sel)
+            assert np.array_equal(r.centroids(), c1)
+        Mn, sn = lb.rmsds_multi(reps)
+        assert np.array_equal(M1, Mn) and sn["max"] == s1["max"]
+        Ms, _ = lb.rmsds(reps[-1])        # any replica alone gives the same matrix
+        assert np.array_equal(M1, Ms)
+    finally:
+        _close(reps)
+    tiny = lb.stage_multi(X[:50], devices)  # too few frames to split: staged once, replicated
+    try:
+        Mt, _ = lb.rmsds_multi(tiny)
+        with lb.FrameSet(X[:50]) as one:
+            assert np.array_equal(Mt, lb.rmsds(one)[0])
+    finally:
+        _close(tiny)
