@@ -739,7 +739,13 @@ bool tensor_path_available() { return true; }
 // Tile order: super-blocks of SB_R row tiles x SB_C column tiles so that the ~150
 // tiles in flight share a few MB of operands in L2 (operand sets are larger than L2).
 int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
-  constexpr uint32_t SB_R = 12, SB_C = 16;
+  // A super-block is SB_R row tiles x SB_C column tiles.  The "a" operands of its row group
+  // (SB_R x 393 KB at N = 1000) stay L2-resident while the column super-blocks stream past, so every
+  // row group reads all "b" operands left of the diagonal once from HBM: DRAM reads ~ F^2 N 3 / (2 SB_R 40).
+  // 12 rows cost 105 GB per C4 launch, 48 rows a quarter of that (LOOSB200_SB_R / LOOSB200_SB_C override).
+  uint32_t SB_R = 48, SB_C = 16;
+  if (const char* e = getenv("LOOSB200_SB_R")) SB_R = (uint32_t)std::max(1, atoi(e));
+  if (const char* e = getenv("LOOSB200_SB_C")) SB_C = (uint32_t)std::max(1, atoi(e));
   const char* cl_env = getenv("LOOSB200_CLUSTER");
   // 1 (default): independent CTAs.  2: CTA pairs (tcgen05 cta_group::2) sharing the "b" operand --
   // 21 % fewer operand bytes out of L2, but the leader then waits for the slower of two epilogues

@@ -204,15 +204,24 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_cov(const CovArgs a) {
 struct SolveArgs {
   const double* cov; const double* cen; const double* gd;  // per frame
   double ref_c[3], ref_sum[3], ref_g;
+  // the same seven scalars in device memory ([0..2] centroid, [3..5] sum, [7] sum of squares), when they
+  // are produced on the device (iterative alignment: k_finish_iter writes the next target's): no host round trip
+  const double* ref_scalars_dev;
   uint32_t F, Na;
   int identity;
   double* xf;        // [F][16] or null
   double* rmsd_out;  // [F] or null
 };
 
-__global__ void __launch_bounds__(128) k_solve(const SolveArgs a) {
+__global__ void __launch_bounds__(128) k_solve(const SolveArgs a_in) {
   const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= a.F) return;
+  if (f >= a_in.F) return;
+  SolveArgs a = a_in;
+  if (a.ref_scalars_dev) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { a.ref_c[k] = __ldg(a.ref_scalars_dev + k); a.ref_sum[k] = __ldg(a.ref_scalars_dev + 3 + k); }
+    a.ref_g = __ldg(a.ref_scalars_dev + 7);
+  }
   double W[12];
   if (a.identity) {
 #pragma unroll
@@ -693,16 +702,13 @@ extern "C" int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_fram
     // one iteration = covariance of every frame with the current target (k_cov), one solve per
     // thread (k_solve -> transforms), transformed frames summed into the new average (k_accum)
     cudaMemsetAsync(dAvg, 0, sizeof(double) * 3 * NpA, st);
-    cudaMemcpyAsync(scal, dScal, sizeof(scal), cudaMemcpyDeviceToHost, st);
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
     CovArgs ca;
     ca.raw = align->raw; ca.Npad = NpA; ca.ref = dT; ca.F = (uint32_t)F; ca.cov = dCov;
     k_cov<<<grid_warp((uint32_t)F, k_cov), SW_THREADS, 0, st>>>(ca);
     SolveArgs sa;
     memset(&sa, 0, sizeof(sa));
     sa.cov = dCov; sa.cen = align->centroid; sa.gd = align->gd;
-    for (int k = 0; k < 3; ++k) { sa.ref_c[k] = scal[k]; sa.ref_sum[k] = scal[3 + k]; }
-    sa.ref_g = scal[7];
+    sa.ref_scalars_dev = dScal;  // the target's centroid, sum and G as k_finish_iter left them on the device
     sa.F = (uint32_t)F; sa.Na = (uint32_t)Na; sa.xf = dXf;
     k_solve<<<(unsigned)((F + 127) / 128), 128, 0, st>>>(sa);
     AccumArgs aa;
