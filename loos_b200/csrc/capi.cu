@@ -217,7 +217,7 @@ std::vector<uint32_t> contiguous_cuts(size_t F, int nparts, bool self) {
 //                 into its own compact strips, which are copied out behind the next band's kernel
 int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric, bool packed,
               const std::vector<uint32_t>& rows, float* out, OutKind okind, size_t ld,
-              loosb200_stats* stats, int engine) {
+              loosb200_stats* stats, int engine, bool canon) {
   NvtxRange nvtx_call(self ? "loosb200 all-to-all (self)" : "loosb200 all-to-all (cross)");
   LB_CUDA(cudaSetDevice(a->device));
   const bool engine_auto = engine == LOOSB200_ENGINE_AUTO;
@@ -309,6 +309,7 @@ int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric,
     job.n_row_tiles = bd.r1 - bd.r0;
     job.n_tiles = bd.ntiles;
     job.packed_rows = packed;
+    job.canon = canon;
     if (!d_out) {
       job.out = nullptr; job.ld = ld;
     } else if (strips) {
@@ -525,7 +526,7 @@ static int pairs_text(loosb200_frames* a, loosb200_frames* b, bool self, unsigne
     std::vector<uint32_t> tiles;
     for (size_t t = R0 / TILE_FRAMES; t * TILE_FRAMES < R1; ++t) tiles.push_back((uint32_t)t);
     loosb200_stats bst;
-    rc = run_pairs(a, b, false, false, true, tiles, d_band, OutKind::Device, n, (stats && !self) ? &bst : nullptr, engine);
+    rc = run_pairs(a, b, false, false, true, tiles, d_band, OutKind::Device, n, (stats && !self) ? &bst : nullptr, engine, self);
     if (rc != LOOSB200_OK) break;
     if (stats && !self) { stats->sum += bst.sum; stats->max = std::max(stats->max, bst.max); stats->count += bst.count; }
     if (self) zero_band_diagonal(d_band, n, R0, (uint32_t)(R1 - R0), a->stream);
@@ -616,7 +617,7 @@ static int pairs_text_multi(loosb200_frames* const* a, loosb200_frames* const* b
         if (r == LOOSB200_OK) {
           const std::vector<uint32_t> tiles = row_tile_range((uint32_t)(R0 / TILE_FRAMES), (uint32_t)((R1 + TILE_FRAMES - 1) / TILE_FRAMES));
           loosb200_stats bst;
-          r = run_pairs(a[d], b[d], false, false, true, tiles, d_band, OutKind::Device, n, (stats && !self) ? &bst : nullptr, engine);
+          r = run_pairs(a[d], b[d], false, false, true, tiles, d_band, OutKind::Device, n, (stats && !self) ? &bst : nullptr, engine, self);
           if (r == LOOSB200_OK && stats && !self) { ps[d].sum += bst.sum; ps[d].max = std::max(ps[d].max, bst.max); ps[d].count += bst.count; }
         }
         if (r == LOOSB200_OK) {

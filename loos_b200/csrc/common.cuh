@@ -141,6 +141,9 @@ struct PairJob {
   uint32_t n_row_tiles;
   uint64_t n_tiles;
   bool packed_rows;           // out row index = position in the launch's row list
+  bool canon = false;         // rectangle over ONE frame set (a and b hold the same frames): the entry (i, j > i) is
+                              // evaluated exactly as its mirror image (j, i) would be, so that a matrix assembled
+                              // from such rectangles is bit-for-bit the symmetric one of the triangle walk
   double* stats_dev;          // [2]: sum, max-as-bits ; may be null
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // optional: recorded right around the contraction kernel
   std::vector<void*>* scratch = nullptr;  // device scratch (dev_alloc) the engine leaves for the caller to
@@ -153,7 +156,7 @@ int alloc_frames(loosb200_frames** out, size_t F, size_t N, int device);  // sta
 enum class OutKind { None, Copy, Device };
 int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric, bool packed,
               const std::vector<uint32_t>& rows, float* out, OutKind okind, size_t ld,
-              loosb200_stats* stats, int engine);
+              loosb200_stats* stats, int engine, bool canon = false);
 std::vector<uint32_t> contiguous_cuts(size_t F, int nparts, bool self);
 std::vector<uint32_t> row_tile_range(uint32_t t0, uint32_t t1);
 int launch_pairs_fp64(const PairJob& job, cudaStream_t st);

@@ -36,7 +36,7 @@ k_pairs_fp64(const float* __restrict__ rawA, const double* __restrict__ cenA,
              const float* __restrict__ rawB, const double* __restrict__ cenB,
              const double* __restrict__ gdB, uint32_t FB, size_t NpadB, uint32_t N,
              const uint32_t* __restrict__ row_tiles, const uint32_t* __restrict__ prefix,
-             uint32_t n_row_tiles, int self, int symmetric, int packed, float* __restrict__ out,
+             uint32_t n_row_tiles, int self, int symmetric, int packed, int canon, float* __restrict__ out,
              size_t ld, float* __restrict__ out_t, size_t ld_t, uint32_t row_off,
              double* __restrict__ stats) {
   __shared__ __align__(16) double As[3][KC][TFP];
@@ -146,7 +146,16 @@ k_pairs_fp64(const float* __restrict__ rawA, const double* __restrict__ cenA,
           }
           continue;
         }
-        const double d = qcp_rmsd(acc[a][b], gdA[i], gdB[j], (double)N, 1.0);
+        double d;
+        if (canon && j > i) {
+          // rectangle over one frame set: the entry above the diagonal is evaluated as its mirror image
+          // (transposed covariance, swapped G), so that both are the same float (see PairJob::canon)
+          const double* R = acc[a][b];
+          const double Rt[9] = {R[0], R[3], R[6], R[1], R[4], R[7], R[2], R[5], R[8]};
+          d = qcp_rmsd(Rt, gdB[j], gdA[i], (double)N, 1.0);
+        } else {
+          d = qcp_rmsd(acc[a][b], gdA[i], gdB[j], (double)N, 1.0);
+        }
         const float v = (float)d;  // Tools/rmsds.cpp:363: double -> float on store
         ssum += (double)v;
         smax = fmax(smax, (double)v);
@@ -192,7 +201,8 @@ int launch_pairs_fp64(const PairJob& job, cudaStream_t st) {
   k_pairs_fp64<<<(unsigned)job.n_tiles, NT, 0, st>>>(
       a->raw, a->centroid, a->gd, (uint32_t)a->F, a->Npad, b->raw, b->centroid, b->gd,
       (uint32_t)b->F, b->Npad, (uint32_t)a->N, job.row_tiles_dev, job.tile_prefix_dev,
-      job.n_row_tiles, job.self ? 1 : 0, job.symmetric ? 1 : 0, job.packed_rows ? 1 : 0, job.out,
+      job.n_row_tiles, job.self ? 1 : 0, job.symmetric ? 1 : 0, job.packed_rows ? 1 : 0,
+      (job.canon && !job.self) ? 1 : 0, job.out,
       job.ld, job.out_t, job.ld_t, (uint32_t)job.row_off, job.stats_dev);
   if (job.ev_k1) cudaEventRecord(job.ev_k1, st);
   LB_CUDA(cudaGetLastError());

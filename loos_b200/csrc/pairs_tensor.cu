@@ -17,12 +17,13 @@
 // warp shuffles and solves one pair per lane (QCP, qcp.cuh) straight out of TMEM:
 // covariance tiles never touch HBM.
 //
-// Warp roles (448 threads, 1 CTA per SM, persistent over a tile list):
+// Warp roles (512 threads, 1 CTA per SM, persistent over a tile list):
 //   warp 0   TMA producer: per 128-atom K chunk one 3-D box for A (128 B x 128 rows x
 //            3 digits = 48 KB) and one for B (128 B x 96 x 3 = 36 KB), SWIZZLE_128B
 //   warp 1   TMEM allocator + MMA issuer: per 32-atom K step six tcgen05.mma
 //            (three with N = 192 spanning two adjacent classes, three with N = 96)
-//   warps 2-13 epilogue, one (lane quarter, 11/11/10-frame column group = 33/33/30 columns) each:
+//   warps 2-3 idle (they complete the control warp group, see setmaxnreg below)
+//   warps 4-15 epilogue, one (lane quarter, 11/11/10-frame column group = 33/33/30 columns) each:
 //            tcgen05.ld -> exact integer combine in fp64 -> shuffle -> quartic coefficients
 //            (fp64) -> TMEM handed back to the MMA warp -> fp32 Newton + float-float
 //            correction -> float32 tile in smem -> coalesced (and mirrored) stores.
@@ -66,7 +67,14 @@ constexpr int NUM_CLASSES = 5;
 constexpr int GROUP_FRAMES = 11;  // "b" frames per epilogue column group (33 columns); the third group has 10
 constexpr int CLASS_COLS = COL_TILE_ROWS;  // 96
 constexpr int TMEM_COLS = 512;
-constexpr int NTHREADS = 448;  // 2 control warps + 12 epilogue warps; 65536/448 -> 144 regs
+// Warp group 0 = the two control warps (+ two idle ones), warp groups 1-3 = the twelve epilogue warps.
+// A sub-partition holds 512 registers per lane and always hosts four of these warps, so an even split
+// would leave every warp 128 -- the epilogue then spills.  setmaxnreg moves the control group's
+// share over: 24 + 3 x 160 = 504 registers per lane and sub-partition.
+constexpr int NTHREADS = 512;
+constexpr int FIRST_EPI_WARP = 4;
+constexpr int NWARPS = NTHREADS / 32;
+constexpr int REGS_CONTROL = 32, REGS_EPILOGUE = 160;
 constexpr int NUM_EPI_WARPS = 12;
 constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;  // 384
 constexpr int TPAD = TILE_FRAMES + 1;  // out tile row pitch (floats)
@@ -255,12 +263,13 @@ struct TensorArgs {
   const double* gA; const double* gB;  // exact sum of squares of every quantised frame, as double
   uint32_t FA, FB, N, n_kchunks;
   int self, symmetric, packed;
+  int canon;                   // rectangle over ONE frame set: entries above the diagonal are evaluated as their mirror image
   double unit;                 // Angstrom per fixed-point unit
   float* out; size_t ld;
   float* out_t; size_t ld_t; uint32_t row_off;  // strip delivery, see PairJob
   double* stats;
   int release_at;  // when the epilogue hands TMEM back (see kernel)
-  long long* prof;  // optional [grid][14 warps][8] cycle counters (LOOSB200_PROF=1)
+  long long* prof;  // optional [grid][NWARPS][8] cycle counters (LOOSB200_PROF=1)
 };
 
 
@@ -345,7 +354,9 @@ __device__ __forceinline__ void release_tmem(SmemCtl* ctl, uint32_t crank) {
   else mbar_arrive_remote(map_to_cta(&ctl->tmem_empty, 0));
 }
 
-template <int CL>
+// CANON: see PairJob::canon (its own instantiation: a branch inside the coefficient rounds would keep the
+// compiler from interleaving them).
+template <int CL, bool CANON>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapB96, const __grid_constant__ CUtensorMap mapB48,
@@ -385,6 +396,9 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
+  if (warp < FIRST_EPI_WARP) {
+  // the register budgets hold for the code DOMINATED by the instruction: the two groups only meet again at the end
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
@@ -453,7 +467,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (uint32_t kc = 0; kc < a.n_kchunks; ++kc) {
           mbar_wait<0>(&ctl->full[stage], phase);
           tc_fence_after();
-          LB_TICK(1);  // waiting for operands
+          LB_TICK(kc == 0 ? 3 : (kc == 1 ? 4 : 1));  // waiting for operands (first, second, later chunks of the tile)
           const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sB = sA + A_STAGE_BYTES;
 #pragma unroll
@@ -484,14 +498,16 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tphase ^= 1;
       }
       if (a.prof)
-        for (int k = 0; k < 8; ++k) a.prof[((size_t)blockIdx.x * 14 + warp) * 8 + k] = pacc[k];
+        for (int k = 0; k < 8; ++k) a.prof[((size_t)blockIdx.x * NWARPS + warp) * 8 + k] = pacc[k];
     }
+  }
   } else {
-    // ================= epilogue (warps 2..13) =================
+    // ================= epilogue (warps 4..15) =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE));
     const int q = warp & 3;                 // TMEM lane quarter == frame block of the row tile
-    const int g = (warp - 2) >> 2;          // column group of the column tile: frames [11 g, 11 g + 11) (10 in the last)
+    const int g = (warp - FIRST_EPI_WARP) >> 2;          // column group of the column tile: frames [11 g, 11 g + 11) (10 in the last)
     const int nfr = g < 2 ? GROUP_FRAMES : COL_TILE_FRAMES - 2 * GROUP_FRAMES;
-    const int et = (warp - 2) * 32 + lane;  // 0..383
+    const int et = (warp - FIRST_EPI_WARP) * 32 + lane;  // 0..383
     const int jf = lane / 3, al = lane - 3 * jf;
     const bool active = lane < 30;
     const int a_local = q * FRAMES_PER_BLOCK + jf;
@@ -569,6 +585,31 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int jb = RBASE[round] + al;
         const uint32_t j = J * COL_TILE_FRAMES + g * GROUP_FRAMES + jb;
         const bool owner = active && al < RCNT[round] && jb < nfr;
+        if (CANON) {
+          // A rectangle over one frame set (the matrix text computed in bands of rows, capi.cu): the
+          // reference's matrix is symmetric by construction (Tools/rmsds.cpp:359-365), so the entry
+          // above the diagonal must be the very float its mirror image below it is.  The quartic's
+          // coefficients are not bit-invariant under R -> R^T or under the cyclic relabelling of the
+          // rows, so (i, j > i) is evaluated on exactly the matrix the lane that owns (j, i) in the
+          // triangle walk would hold: R of the swapped pair, rows relabelled by THAT lane's offset
+          // (the position of frame i inside its column group, modulo 3).
+          const uint32_t ib = i % COL_TILE_FRAMES;
+          const uint32_t gm = ib / GROUP_FRAMES < 2 ? ib / GROUP_FRAMES : 2;
+          const int alm = (int)((ib - gm * GROUP_FRAMES) % 3);
+          auto sel3 = [](int k, double x0, double x1, double x2) { return k == 0 ? x0 : (k == 1 ? x1 : x2); };
+          double T[9], Mr[9];
+#pragma unroll
+          for (int x = 0; x < 3; ++x)  // undo this lane's relabelling: T = the covariance of (i, j) in x, y, z order
+#pragma unroll
+            for (int y = 0; y < 3; ++y) T[3 * x + y] = sel3((x - al + 3) % 3, R[y], R[3 + y], R[6 + y]);
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Mr[3 * r + c] = sel3((alm + r) % 3, T[3 * c + 0], T[3 * c + 1], T[3 * c + 2]);
+          const bool flip = j > i;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) R[k] = flip ? Mr[k] : R[k];
+        }
         // 0: no entry (idle lane, out of range, or j > i of the self matrix), 1: exact zero (the
         // diagonal, Tools/rmsds.cpp:359-365, or every atom at the centroid in both frames), 2: solve.
         // Idle lanes run the same arithmetic on whatever their registers hold; their results are
@@ -630,14 +671,21 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       float tt[4], ls[4];
 #pragma unroll
       for (int r4 = 0; r4 < 4; ++r4) { tt[r4] = polf[r4].t0; ls[r4] = 0.0f; }
+      // A step is applied only while it still matters (|step| > 4e-7 |t|): a settled solve stands still
+      // while the warp iterates on for slower ones, so the result of a pair does not depend on which
+      // other pairs share its warp (the same pair is met again in other launch shapes, bands and as
+      // its mirror image).  The step not taken is second order after the correction below.
       for (int it = 0; it < 12; ++it) {
         bool conv = true;
 #pragma unroll
         for (int r4 = 0; r4 < 4; ++r4) {
-          ls[r4] = qcp_newton_step(polf[r4].c0h, polf[r4].c1h, polf[r4].c2h, polf[r4].c3, tt[r4]);
-          conv = conv && (state[r4] != 2 || fabsf(ls[r4]) <= 4e-7f * fabsf(tt[r4]) + 1e-12f);
+          float t_new = tt[r4];
+          ls[r4] = qcp_newton_step(polf[r4].c0h, polf[r4].c1h, polf[r4].c2h, polf[r4].c3, t_new);
+          const bool c = fabsf(ls[r4]) <= 4e-7f * fabsf(tt[r4]) + 1e-12f;
+          if (!c) tt[r4] = t_new;
+          conv = conv && (c || state[r4] != 2);
         }
-        if (it >= 1 && __all_sync(0xffffffffu, conv)) break;
+        if (__all_sync(0xffffffffu, conv)) break;
       }
       LB_TICK(3);  // Newton (fp32)
 
@@ -704,7 +752,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       // later, after every thread has passed the next tile's barrier
     }
     if (a.prof && lane == 0)
-      for (int k = 0; k < 8; ++k) a.prof[((size_t)blockIdx.x * 14 + warp) * 8 + k] = pacc[k];
+      for (int k = 0; k < 8; ++k) a.prof[((size_t)blockIdx.x * NWARPS + warp) * 8 + k] = pacc[k];
     if (a.stats) {
       double ssum = (double)sum_h + (double)sum_l, smax = (double)tmax;
 #pragma unroll
@@ -712,7 +760,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
         smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, o));
       }
-      if (lane == 0) { ctl->red_sum[warp - 2] = ssum; ctl->red_max[warp - 2] = smax; }
+      if (lane == 0) { ctl->red_sum[warp - FIRST_EPI_WARP] = ssum; ctl->red_max[warp - FIRST_EPI_WARP] = smax; }
       asm volatile("bar.sync 1, 384;" ::: "memory");
       if (et == 0) {
         double sm = 0.0, m = 0.0;
@@ -801,6 +849,7 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   ta.FA = (uint32_t)A->F; ta.FB = FB; ta.N = (uint32_t)A->N;
   ta.n_kchunks = (uint32_t)(A->Kpad / K_CHUNK);
   ta.self = job.self; ta.symmetric = job.symmetric; ta.packed = job.packed_rows;
+  ta.canon = (job.canon && !job.self) ? 1 : 0;
   ta.unit = exp2((double)A->unit_log2);
   ta.out = job.out; ta.ld = job.ld; ta.stats = job.stats_dev;
   ta.out_t = job.out_t; ta.ld_t = job.ld_t; ta.row_off = (uint32_t)job.row_off;
@@ -812,43 +861,44 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   ta.release_at = getenv("LOOSB200_RELEASE_AT") ? (atoi(getenv("LOOSB200_RELEASE_AT")) ? 1 : 0) : 0;
   const bool want_prof = getenv("LOOSB200_PROF") != nullptr;
 
-  LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<1>()));
-  LB_CUDA(cudaFuncSetAttribute(k_pairs_tensor<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<2>()));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sms / CLs, slots) * CLs;
   if (want_prof) {
-    LB_CUDA(dev_alloc_t(&ta.prof, sizeof(long long) * grid * 14 * 8));
-    LB_CUDA(cudaMemsetAsync(ta.prof, 0, sizeof(long long) * grid * 14 * 8, st));
+    LB_CUDA(dev_alloc_t(&ta.prof, sizeof(long long) * grid * NWARPS * 8));
+    LB_CUDA(cudaMemsetAsync(ta.prof, 0, sizeof(long long) * grid * NWARPS * 8, st));
   }
   if (job.ev_k0) cudaEventRecord(job.ev_k0, st);
-  if (CLs == 1) {
-    k_pairs_tensor<1><<<grid, NTHREADS, smem_bytes<1>(), st>>>(A->tmapA, B->tmapB, B->tmapB96, B->tmapB48, ta);
-  } else {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem_bytes<2>(); cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    LB_CUDA(cudaLaunchKernelEx(&cfg, k_pairs_tensor<2>, A->tmapA, B->tmapB, B->tmapB96, B->tmapB48, ta));
-  }
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TensorArgs);
+  Kern kern;
+  if (CLs == 2) kern = k_pairs_tensor<2, false>;
+  else if (ta.canon) kern = k_pairs_tensor<1, true>;
+  else kern = k_pairs_tensor<1, false>;
+  const int smem = CLs == 2 ? smem_bytes<2>() : smem_bytes<1>();
+  LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = CLs == 2 ? 1 : 0;
+  LB_CUDA(cudaLaunchKernelEx(&cfg, kern, A->tmapA, B->tmapB, B->tmapB96, B->tmapB48, ta));
   if (job.ev_k1) cudaEventRecord(job.ev_k1, st);
   LB_CUDA(cudaGetLastError());
   if (want_prof) {
-    std::vector<long long> hp((size_t)grid * 14 * 8);
+    std::vector<long long> hp((size_t)grid * NWARPS * 8);
     LB_CUDA(cudaMemcpyAsync(hp.data(), ta.prof, sizeof(long long) * hp.size(), cudaMemcpyDeviceToHost, st));
     LB_CUDA(cudaStreamSynchronize(st));
     dev_release(ta.prof);
     const char* names_e[7] = {"wait_acc", "drain", "exch+poly", "newton", "polish", "barrier", "stores"};
-    const char* names_m[3] = {"wait_tmem", "wait_operands", "issue"};
+    const char* names_m[5] = {"wait_tmem", "wait_operands(chunks 2+)", "issue", "wait_operands(chunk 0)", "wait_operands(chunk 1)"};
     const double ntl = (double)job.n_tiles * TILE_FRAMES / COL_TILE_FRAMES / grid;  // approximate
     fprintf(stderr, "[loosb200 prof] tiles/CTA %.1f  cycles per tile (mean over CTAs):\n  MMA warp:", ntl);
-    for (int k = 0; k < 3; ++k) { double s = 0; for (unsigned c = 0; c < grid; ++c) s += hp[((size_t)c * 14 + 1) * 8 + k]; fprintf(stderr, " %s=%.0f", names_m[k], s / grid / ntl); }
+    for (int k = 0; k < 5; ++k) { double s = 0; for (unsigned c = 0; c < grid; ++c) s += hp[((size_t)c * NWARPS + 1) * 8 + k]; fprintf(stderr, " %s=%.0f", names_m[k], s / grid / ntl); }
     fprintf(stderr, "\n  epilogue warps:");
-    for (int k = 0; k < 7; ++k) { double s = 0; for (unsigned c = 0; c < grid; ++c) for (int w = 2; w < 14; ++w) s += hp[((size_t)c * 14 + w) * 8 + k]; fprintf(stderr, " %s=%.0f", names_e[k], s / grid / 12 / ntl); }
+    for (int k = 0; k < 7; ++k) { double s = 0; for (unsigned c = 0; c < grid; ++c) for (int w = FIRST_EPI_WARP; w < NWARPS; ++w) s += hp[((size_t)c * NWARPS + w) * 8 + k]; fprintf(stderr, " %s=%.0f", names_e[k], s / grid / 12 / ntl); }
     fprintf(stderr, "\n");
   }
   if (launches) *launches = 1;

@@ -373,21 +373,30 @@ def test_matrix_text_formatted_on_the_gpu(lb, precision):
     assert ctext.decode() == matrix_text(Cm, precision)
 
 
-def test_matrix_text_in_row_bands(lb, monkeypatch):
+@pytest.mark.parametrize("engine", ["tensor", "fp64"])
+def test_matrix_text_in_row_bands(lb, monkeypatch, engine):
     """When the F x F float matrix does not fit in HBM the text is produced from bands of rows computed
     as rectangles (LOOSB200_TEXT_BAND_ROWS forces it here): identical bytes, identical stats, exact
     zeros on the diagonal, for the self and the cross matrix, with a ragged last band."""
     from loos_b200.api import rmsds_text
     from loos_b200.synth import synth_frames
     X = synth_frames(333, 50, seed=15)
+    # frames met twice (multi-rmsds given one trajectory twice): their RMSD is rounding noise of the
+    # solve, and an entry above the diagonal must still be the float its mirror image is
+    X[200:260] = X[0:60]
+    X[300:320] = X[100:120] + np.float32(3.0)
     Y = synth_frames(61, 50, seed=16)
     with lb.FrameSet(X) as fs, lb.FrameSet(Y) as fy:
-        whole, st = rmsds_text(fs, precision=7, engine="tensor")
-        cwhole, cst = rmsds_text(fs, fy, precision=7, engine="tensor")
+        whole, st = rmsds_text(fs, precision=7, engine=engine)
+        cwhole, cst = rmsds_text(fs, fy, precision=7, engine=engine)
         monkeypatch.setenv("LOOSB200_TEXT_BAND_ROWS", "120")
-        banded, bst = rmsds_text(fs, precision=7, engine="tensor")
-        cbanded, cbst = rmsds_text(fs, fy, precision=7, engine="tensor")
-    assert banded == whole and cbanded == cwhole
+        banded, bst = rmsds_text(fs, precision=7, engine=engine)
+        cbanded, cbst = rmsds_text(fs, fy, precision=7, engine=engine)
+    if banded != whole:
+        wl, bl = whole.split(b"\n"), banded.split(b"\n")
+        bad = [(r, c, x, y) for r, (u, v) in enumerate(zip(wl, bl)) if u != v for c, (x, y) in enumerate(zip(u.split(), v.split())) if x != y]
+        raise AssertionError("banded text differs from the whole matrix at (line, column, whole, banded): %r" % bad[:8])
+    assert cbanded == cwhole
     assert bst["count"] == st["count"] and bst["max"] == st["max"] and abs(bst["sum"] - st["sum"]) < 1e-6
     assert cbst["count"] == cst["count"] and cbst["max"] == cst["max"] and abs(cbst["sum"] - cst["sum"]) < 1e-6 * cst["sum"]
 

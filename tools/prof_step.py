@@ -1,5 +1,9 @@
+import os
 import sys, time, torch
 sys.path.insert(0, "/root/repo")
+from loos_b200 import capi as _capi
+if os.environ.get('AB_LIB'):
+    _capi.LIB_PATH = os.environ['AB_LIB']   # A/B runs against another build of the library
 import loos_b200 as lb
 from loos_b200.synth import synth_frames_torch
 F, N = 100000, 1000
