@@ -244,6 +244,14 @@ int loosb200_rmsd2ref_iterative(loosb200_frames* align, loosb200_frames* rmsd_se
  * Selections of the two trajectories must agree in size (LOOSB200_ERR_SIZE_MISMATCH). */
 int loosb200_rmsds_align(loosb200_frames* align1, loosb200_frames* rmsd1, loosb200_frames* align2,
                          loosb200_frames* rmsd2, double* out, size_t ld);
+/* The same with a choice of engine.  LOOSB200_ENGINE_FP64 (what loosb200_rmsds_align uses): both 3x3
+ * contractions of a pair in double on the CUDA cores, results within 1e-8 A of the reference's.
+ * LOOSB200_ENGINE_TENSOR: both contractions on the int8 tensor path (exact integer sums of coordinates
+ * on a 24-bit fixed-point grid; the rmsd selection is put on its grid about the ALIGN centroid), the
+ * rotation from the quartic's root as in the fp64 engine; results within ~1e-6 A, an order of magnitude
+ * faster; selections of up to 43,000 atoms.  LOOSB200_ENGINE_AUTO: tensor when it applies. */
+int loosb200_rmsds_align_engine(loosb200_frames* align1, loosb200_frames* rmsd1, loosb200_frames* align2,
+                                loosb200_frames* rmsd2, double* out, size_t ld, int engine);
 
 /* One pass of iterativeAlignment's loop body over THIS handle's frames (src/alignment.cpp:379-390:
  * alignOnto(target) for every frame, transformed coordinates summed), for callers that shard a

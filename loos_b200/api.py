@@ -230,16 +230,18 @@ def align_accumulate(fs_align, target, fs_accum=None, want_xforms=False):
     return (out, xf) if want_xforms else out
 
 
-def rmsds_align(align1, rmsd1=None, align2=None, rmsd2=None):
+def rmsds_align(align1, rmsd1=None, align2=None, rmsd2=None, engine="auto"):
     """Pairwise RMSD over one selection after aligning on another
     (Packages/Clustering/rmsds-align.py:236-256): M[i, j] = rmsd of rmsd2[j] against rmsd1[i] moved by
     the superposition of align1[i] onto align2[j].  Second trajectory defaults to the first.
+    engine: "fp64" (within 1e-8 A of the reference), "tensor" (int8 tensor path, ~1e-6 A), "auto".
     Returns an (F1, F2) float64 array."""
     if align2 is None:
         align2, rmsd2 = align1, rmsd1
     out = np.zeros((align1.F, align2.F), dtype=np.float64, order="F")
-    check(lib().loosb200_rmsds_align(align1._h, None if rmsd1 is None else rmsd1._h, align2._h,
-                                     None if rmsd2 is None else rmsd2._h, _dptr(out), max(1, align1.F)))
+    check(lib().loosb200_rmsds_align_engine(align1._h, None if rmsd1 is None else rmsd1._h, align2._h,
+                                            None if rmsd2 is None else rmsd2._h, _dptr(out), max(1, align1.F),
+                                            capi.ENGINES[engine]))
     return out
 
 

@@ -144,6 +144,15 @@ struct PairJob {
   bool canon = false;         // rectangle over ONE frame set (a and b hold the same frames): the entry (i, j > i) is
                               // evaluated exactly as its mirror image (j, i) would be, so that a matrix assembled
                               // from such rectangles is bit-for-bit the symmetric one of the triangle walk
+  // rmsds-align on the tensor engine: two launches over the same (packed, rectangular) tile space --
+  // Rotation over the align selections fills `quat` ([column j][local row][4] doubles, ldq local rows),
+  // Trace over the rmsd selections (quantised about the ALIGN centroids) turns it into the result band
+  // out_d[j * ldq + local row] (pairs_tensor.cu, KIND_ROT / KIND_TRACE).  `out` and stats are unused.
+  enum Kind { Rmsd = 0, Rotation = 1, Trace = 2 };
+  Kind kind = Rmsd;
+  double* quat = nullptr;
+  double* out_d = nullptr;
+  size_t ldq = 0;
   double* stats_dev;          // [2]: sum, max-as-bits ; may be null
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // optional: recorded right around the contraction kernel
   std::vector<void*>* scratch = nullptr;  // device scratch (dev_alloc) the engine leaves for the caller to

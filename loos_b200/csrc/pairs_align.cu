@@ -13,10 +13,18 @@
 //   d_ij^2 = ( sum |x'|^2 + sum |y'|^2 - 2 sum_ab Z_ab C_ba ) / N_r ,   C_ab = sum_k x'_a y'_b .
 // So a pair needs two 3x3 contractions -- R over the align selection (it gives Z through the
 // quartic / adjugate solve of qcp.cuh) and C over the rmsd selection -- and nothing per atom
-// after that.  This first version runs both on the fp64 CUDA cores, a 40 x 40 tile of pairs per
-// CTA and a 2 x 2 block of pairs per thread, as pairs_fp64.cu does for the one-selection case.
-// Roofline: fp64 pipe, 18 (N_a + N_r) flop per pair.  The result is not symmetric and is kept
-// in double: the script prints Python doubles.
+// after that.  Two engines:
+//   fp64    both contractions on the fp64 CUDA cores, a 40 x 40 tile of pairs per CTA and a 2 x 2 block
+//           of pairs per thread, as pairs_fp64.cu does for the one-selection case (k_pairs_align below;
+//           roofline: fp64 pipe, 18 (N_a + N_r) flop per pair; agrees with the reference to 1e-8 A)
+//   tensor  both contractions on the int8 tensor path of pairs_tensor.cu (exact integer sums of the
+//           24-bit fixed-point coordinates): pass 1 over the align selections leaves the rotation of
+//           every pair as a unit quaternion, pass 2 over the rmsd selections -- quantised about the
+//           ALIGN centroids -- turns it into d_ij (rmsds_align_tensor below; error = the coordinate grid,
+//           ~1e-6 A)
+// The result is not symmetric and is kept in double: the script prints Python doubles.
+#include <limits.h>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -52,6 +60,32 @@ k_g_about(const float* __restrict__ raw, size_t Npad, uint32_t N, uint32_t F,
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) g[f] = s;
+  }
+}
+
+// maxabs[f] = max over the set's atoms and axes of |x - cen[f]| with cen taken from ANOTHER set: what
+// k_unit needs to put the rmsd selection on a fixed-point grid about the align centroid.  A non-finite
+// coordinate marks the frame with +Inf, as k_stage does.  One warp per frame.
+__global__ void __launch_bounds__(128)
+k_maxabs_about(const float* __restrict__ raw, size_t Npad, uint32_t N, uint32_t F,
+               const double* __restrict__ cen, float* __restrict__ maxabs) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t f = blockIdx.x * 4 + (threadIdx.x >> 5); f < F; f += gridDim.x * 4) {
+    float m = 0.f;
+    bool bad = false;
+    for (int ax = 0; ax < 3; ++ax) {
+      const double c = cen[(size_t)f * 3 + ax];
+      const float* p = raw + ((size_t)f * 3 + ax) * Npad;
+      for (uint32_t k = lane; k < N; k += 32) {
+        const float v = fabsf((float)((double)p[k] - c));
+        bad = bad || !(v <= 3.0e38f);
+        m = fmaxf(m, v);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) maxabs[f] = bad ? __int_as_float(0x7f800000) : m * 1.0000002f;  // fp32 rounding of |x - c|
   }
 }
 
@@ -202,11 +236,127 @@ k_pairs_align(const AlignArgs a) {
 }  // namespace
 }  // namespace loosb200
 
+// ---- tensor engine ----------------------------------------------------------------------------------
+namespace loosb200 {
+namespace {
+
+// The rmsd selection of a trajectory seen from its ALIGN centroids: shares the fp32 planes of the staged
+// rmsd set, borrows the centroids of the align set, owns the digit planes derived from the two.
+struct AboutView {
+  loosb200_frames f;
+  bool owns = false;
+  int build(const loosb200_frames* rmsd, const loosb200_frames* align, cudaStream_t st) {
+    f.device = rmsd->device; f.F = rmsd->F; f.N = rmsd->N; f.Npad = rmsd->Npad;
+    f.raw = rmsd->raw; f.centroid = align->centroid; f.gd = nullptr; f.stream = st;
+    if (dev_alloc_t(&f.maxabs, sizeof(float) * f.F) != cudaSuccess) { cudaGetLastError(); return LOOSB200_ERR_NOMEM; }
+    owns = true;
+    k_maxabs_about<<<(unsigned)std::min<size_t>((f.F + 3) / 4, 148 * 16), 128, 0, st>>>(f.raw, f.Npad, (uint32_t)f.N, (uint32_t)f.F,
+                                                                                  f.centroid, f.maxabs);
+    LB_CUDA(cudaGetLastError());
+    return LOOSB200_OK;
+  }
+  ~AboutView() {
+    if (!owns) return;
+    dev_release(f.maxabs); dev_release(f.q8); dev_release(f.q8b); dev_release(f.gq); dev_release(f.unit_log2_dev);
+    f.raw = nullptr; f.centroid = nullptr;
+  }
+};
+
+// both sets on one fixed-point grid (the coarser of the two)
+int common_grid(loosb200_frames* a, loosb200_frames* b) {
+  int rc = ensure_quantised(a, INT_MIN);
+  if (rc || a == b) return rc;
+  if ((rc = ensure_quantised(b, INT_MIN))) return rc;
+  const int e = std::max(a->unit_log2, b->unit_log2);
+  if ((rc = ensure_quantised(a, e))) return rc;
+  return ensure_quantised(b, e);
+}
+
+int rmsds_align_tensor(loosb200_frames* align1, loosb200_frames* rmsd1, loosb200_frames* align2,
+                       loosb200_frames* rmsd2, double* out, size_t ld) {
+  NvtxRange nvtx("loosb200 rmsds-align (tensor engine)");
+  cudaStream_t st = align1->stream;
+  const size_t FA = align1->F, FB = align2->F;
+  cudaEventRecord(align1->timing.ev[0], st);
+  cudaEventRecord(align1->timing.ev[1], st);  // the fixed-point images of the four sets count as this engine's work
+  int rc = common_grid(align1, align2);
+  if (rc) return rc;
+  // pass-2 operands: the align sets themselves when the rmsd selection IS the align selection
+  AboutView v1, v2;
+  loosb200_frames* x1 = align1;
+  loosb200_frames* x2 = align2;
+  if (rmsd1 != align1) { if ((rc = v1.build(rmsd1, align1, st))) return rc; x1 = &v1.f; }
+  if (rmsd2 == rmsd1 && align2 == align1) x2 = x1;
+  else if (rmsd2 != align2) { if ((rc = v2.build(rmsd2, align2, st))) return rc; x2 = &v2.f; }
+  if ((x1 != align1 || x2 != align2) && (rc = common_grid(x1, x2))) return rc;
+
+  const size_t row_tiles = (FA + TF - 1) / TF;
+  // a band holds 32 B of quaternion and 8 B of result per pair: ~2 GiB at most
+  size_t band_tiles = std::max<size_t>(1, (size_t(2) << 30) / ((size_t)40 * TF * std::max<size_t>(FB, 1)));
+  if (const char* env = getenv("LOOSB200_ALIGN_BAND_TILES")) band_tiles = std::max<long>(1, atol(env));
+  band_tiles = std::min(band_tiles, row_tiles);
+  const size_t ldq = band_tiles * TF;
+
+  std::vector<uint32_t> rows(row_tiles);
+  for (size_t t = 0; t < row_tiles; ++t) rows[t] = (uint32_t)t;
+  uint32_t* d_rows = nullptr;
+  double *d_quat = nullptr, *d_band = nullptr;
+  std::vector<void*> scratch;
+  auto cleanup = [&]() {
+    dev_release(d_rows); dev_release(d_quat); dev_release(d_band);
+    for (void* p : scratch) dev_release(p);
+  };
+  if (dev_alloc_t(&d_rows, sizeof(uint32_t) * row_tiles) != cudaSuccess ||
+      dev_alloc_t(&d_quat, sizeof(double) * 4 * ldq * FB) != cudaSuccess ||
+      dev_alloc_t(&d_band, sizeof(double) * ldq * FB) != cudaSuccess) {
+    cudaGetLastError(); cleanup(); return LOOSB200_ERR_NOMEM;
+  }
+  cudaMemcpyAsync(d_rows, rows.data(), sizeof(uint32_t) * row_tiles, cudaMemcpyHostToDevice, st);
+  int launches = 0;
+  const uint32_t col_tiles = (uint32_t)((FB + COL_TILE_FRAMES - 1) / COL_TILE_FRAMES);
+  for (size_t t0 = 0; t0 < row_tiles && rc == LOOSB200_OK; t0 += band_tiles) {
+    const size_t nt = std::min(band_tiles, row_tiles - t0);
+    PairJob job;
+    job.self = false; job.symmetric = false; job.out = nullptr; job.ld = 0;
+    job.rows_host = rows.data() + t0; job.row_tiles_dev = d_rows + t0; job.tile_prefix_dev = nullptr;
+    job.n_row_tiles = (uint32_t)nt; job.n_tiles = (uint64_t)nt * col_tiles;
+    job.packed_rows = true; job.stats_dev = nullptr; job.scratch = &scratch;
+    job.quat = d_quat; job.out_d = d_band; job.ldq = ldq;
+    int l = 0;
+    job.a = align1; job.b = align2; job.kind = PairJob::Rotation;
+    rc = launch_pairs_tensor(job, st, &l);
+    launches += l;
+    if (rc) break;
+    job.a = x1; job.b = x2; job.kind = PairJob::Trace;
+    rc = launch_pairs_tensor(job, st, &l);
+    launches += l;
+    if (rc) break;
+    cudaEventRecord(align1->timing.ev[2], st);  // re-recorded per band, as the fp64 engine does
+    const size_t row0 = t0 * TF, band_rows = std::min<size_t>(nt * TF, FA - row0);
+    cudaError_t e = cudaMemcpy2DAsync(out + row0, ld * sizeof(double), d_band, ldq * sizeof(double),
+                                      band_rows * sizeof(double), FB, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && t0 + band_tiles < row_tiles) e = cudaStreamSynchronize(st);  // the band buffers are reused
+    if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "rmsds_align (tensor): band copy", __FILE__, __LINE__); }
+  }
+  cudaEventRecord(align1->timing.ev[3], st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cleanup();
+  if (rc) return rc;
+  if (e != cudaSuccess) return cuda_fail(e, "rmsds_align (tensor) kernels", __FILE__, __LINE__);
+  align1->timing.launches = launches; align1->timing.valid = true; align1->timing.kev_used = 0;
+  return LOOSB200_OK;
+}
+
+}  // namespace
+}  // namespace loosb200
+
 using namespace loosb200;
 
-extern "C" int loosb200_rmsds_align(loosb200_frames* align1, loosb200_frames* rmsd1, loosb200_frames* align2,
-                                    loosb200_frames* rmsd2, double* out, size_t ld) {
+extern "C" int loosb200_rmsds_align_engine(loosb200_frames* align1, loosb200_frames* rmsd1, loosb200_frames* align2,
+                                           loosb200_frames* rmsd2, double* out, size_t ld, int engine) {
   if (!align1 || !align2 || !out) return LOOSB200_ERR_INVALID;
+  if (engine != LOOSB200_ENGINE_AUTO && engine != LOOSB200_ENGINE_TENSOR && engine != LOOSB200_ENGINE_FP64) return LOOSB200_ERR_INVALID;
   if (!rmsd1) rmsd1 = align1;
   if (!rmsd2) rmsd2 = align2;
   const loosb200_frames* all[4] = {align1, rmsd1, align2, rmsd2};
@@ -223,6 +373,21 @@ extern "C" int loosb200_rmsds_align(loosb200_frames* align1, loosb200_frames* rm
   if (FA > 0xffffff00ull || FB > 0xffffff00ull || (FB + TF - 1) / TF > 0x7fffffffull) return LOOSB200_ERR_UNSUPPORTED;
   LB_CUDA(cudaSetDevice(align1->device));
   cudaStream_t st = align1->stream;
+  // the frame sets were staged on their own streams: wait for all of them
+  for (const loosb200_frames* h : all)
+    if (h->stream != st) {
+      cudaError_t e = cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) return cuda_fail(e, "rmsds_align: staging", __FILE__, __LINE__);
+    }
+  if (engine != LOOSB200_ENGINE_FP64) {
+    const bool can = tensor_path_available() && align1->N <= TENSOR_MAX_ATOMS && rmsd1->N <= TENSOR_MAX_ATOMS;
+    if (!can && engine == LOOSB200_ENGINE_TENSOR) return LOOSB200_ERR_UNSUPPORTED;
+    if (can) {
+      const int rc = rmsds_align_tensor(align1, rmsd1, align2, rmsd2, out, ld);
+      // NaN / Inf coordinates have no fixed-point image; the fp64 engine propagates them like the reference
+      if (!(rc == LOOSB200_ERR_NUMERICAL && engine == LOOSB200_ENGINE_AUTO)) return rc;
+    }
+  }
 
   // bands of whole row tiles, at most ~1 GiB of doubles each (and 65535 tiles: gridDim.y)
   size_t band_tiles = std::max<size_t>(1, (size_t(1) << 30) / (sizeof(double) * TF * FB));
@@ -238,13 +403,6 @@ extern "C" int loosb200_rmsds_align(loosb200_frames* align1, loosb200_frames* rm
             dev_alloc_t(&d_band, sizeof(double) * band_rows_max * FB) == cudaSuccess;
   auto cleanup = [&]() { dev_release(gxA); dev_release(gxB); dev_release(d_band); };
   if (!ok) { cudaGetLastError(); cleanup(); return LOOSB200_ERR_NOMEM; }
-
-  // the frame sets were staged on their own streams: wait for all of them
-  for (const loosb200_frames* h : all)
-    if (h->stream != st) {
-      cudaError_t e = cudaStreamSynchronize(h->stream);
-      if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "rmsds_align: staging", __FILE__, __LINE__); }
-    }
 
   cudaEventRecord(align1->timing.ev[0], st);
   int launches = 0;
@@ -284,4 +442,9 @@ extern "C" int loosb200_rmsds_align(loosb200_frames* align1, loosb200_frames* rm
   if (e != cudaSuccess) return cuda_fail(e, "rmsds_align kernels", __FILE__, __LINE__);
   align1->timing.launches = launches; align1->timing.valid = true; align1->timing.kev_used = 0;
   return LOOSB200_OK;
+}
+
+extern "C" int loosb200_rmsds_align(loosb200_frames* align1, loosb200_frames* rmsd1, loosb200_frames* align2,
+                                    loosb200_frames* rmsd2, double* out, size_t ld) {
+  return loosb200_rmsds_align_engine(align1, rmsd1, align2, rmsd2, out, ld, LOOSB200_ENGINE_FP64);
 }

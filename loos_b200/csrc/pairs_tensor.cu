@@ -268,6 +268,9 @@ struct TensorArgs {
   float* out; size_t ld;
   float* out_t; size_t ld_t; uint32_t row_off;  // strip delivery, see PairJob
   double* stats;
+  // rmsds-align (KIND_ROT / KIND_TRACE, see the kernel): unit quaternions of the align-selection pass,
+  // [column j][local row][4], and the double result band, column-major; both with `ldq` local rows
+  double* quat; double* out_d; size_t ldq;
   int release_at;  // when the epilogue hands TMEM back (see kernel)
   long long* prof;  // optional [grid][NWARPS][8] cycle counters (LOOSB200_PROF=1)
 };
@@ -354,9 +357,19 @@ __device__ __forceinline__ void release_tmem(SmemCtl* ctl, uint32_t crank) {
   else mbar_arrive_remote(map_to_cta(&ctl->tmem_empty, 0));
 }
 
-// CANON: see PairJob::canon (its own instantiation: a branch inside the coefficient rounds would keep the
-// compiler from interleaving them).
-template <int CL, bool CANON>
+// What the epilogue makes of a pair's 3 x 3 sums (one instantiation each: a branch inside the coefficient
+// rounds would keep the compiler from interleaving them):
+//   KIND_RMSD   the minimal RMSD (float32 tile, symmetric fill, stats)
+//   KIND_CANON  the same with mirror-canonical evaluation, see PairJob::canon
+//   KIND_ROT    rmsds-align, pass 1 over the ALIGN selections: the optimal rotation as a unit quaternion
+//               (eigenvector of Horn's K for the quartic's root, qcp_rotation_fast; Jacobi for degenerate
+//               selections), written to a.quat
+//   KIND_TRACE  rmsds-align, pass 2 over the RMSD selections quantised about the align centroids:
+//               d^2 = (Gx + Gy - 2 sum_ab Z_ab C_ba) / N with Z from a.quat, double result in a.out_d
+// Both passes walk the same tile geometry, so a pair meets the same lane -- and with it the same cyclic
+// relabelling of the rows of R and C, which the trace is invariant under when both carry it.
+constexpr int KIND_RMSD = 0, KIND_CANON = 1, KIND_ROT = 2, KIND_TRACE = 3;
+template <int CL, int KIND>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapB96, const __grid_constant__ CUtensorMap mapB48,
@@ -585,7 +598,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int jb = RBASE[round] + al;
         const uint32_t j = J * COL_TILE_FRAMES + g * GROUP_FRAMES + jb;
         const bool owner = active && al < RCNT[round] && jb < nfr;
-        if (CANON) {
+        if (KIND == KIND_CANON) {
           // A rectangle over one frame set (the matrix text computed in bands of rows, capi.cu): the
           // reference's matrix is symmetric by construction (Tools/rmsds.cpp:359-365), so the entry
           // above the diagonal must be the very float its mirror image below it is.  The quartic's
@@ -616,6 +629,32 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // never stored and they are excluded from the convergence vote below.
         const bool in_range = owner && i_ok && j < a.FB;
         const bool upper = a.self && j >= i;
+        if (KIND == KIND_ROT || KIND == KIND_TRACE) {
+          if (in_range) {
+            const size_t cell = (size_t)j * a.ldq + (size_t)rt * TILE_FRAMES + (size_t)a_local;
+            if (KIND == KIND_ROT) {
+              double qv[4];
+              if (!qcp_rotation_fast(R, ga, gbq[round], nullptr, nullptr, qv)) qcp_rotation(R, nullptr, nullptr, qv);
+              double2* dst = reinterpret_cast<double2*>(a.quat + 4 * cell);
+              dst[0] = make_double2(qv[0], qv[1]);
+              dst[1] = make_double2(qv[2], qv[3]);
+            } else {
+              const double2* src = reinterpret_cast<const double2*>(a.quat + 4 * cell);
+              const double2 q01 = src[0], q23 = src[1];
+              const double qv[4] = {q01.x, q01.y, q23.x, q23.y};
+              double z[9];
+              qcp_quat_to_rot(qv, z);
+              double tr = 0.0;  // sum_k (Z x'_k) . y'_k = sum_ab Z_ab C_ba
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) tr = fma(z[3 * r + c], R[3 * c + r], tr);
+              const double ss = (ga + gbq[round]) - 2.0 * tr;
+              a.out_d[cell] = a.unit * sqrt(fmax(ss, 0.0) * inv_n);
+            }
+          }
+          return;
+        }
         double e0 = 0.5 * (ga + gbq[round]);
         const bool pos = e0 > 0.0;
         e0 = pos ? e0 : 1.0;
@@ -658,13 +697,16 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       LB_TICK(1);  // drain (+ rounds 0, 1)
       do_round(2);
       do_round(3);
+      if (KIND == KIND_RMSD || KIND == KIND_CANON) {
       // pin every fp64-derived value on this side of the hand-over: without this the compiler
       // is free to sink the fp64 -> float conversions below it, into the contended region
 #pragma unroll
       for (int r4 = 0; r4 < 4; ++r4)
         asm volatile("" : "+f"(polf[r4].c0h), "+f"(polf[r4].c0l), "+f"(polf[r4].c1h), "+f"(polf[r4].c1l),
                           "+f"(polf[r4].c2h), "+f"(polf[r4].c2l), "+f"(e0s[r4]), "+f"(polf[r4].t0));
+      }
       if (release_at == 1) { __syncwarp(); if (lane == 0) release_tmem<CL>(ctl, crank); }
+      if (KIND == KIND_RMSD || KIND == KIND_CANON) {
       LB_TICK(2);  // exchange + quartic coefficients (fp64)
 
       // ---- four fp32 Newton recurrences in lock-step, warp-uniform exit ----
@@ -747,6 +789,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
         }
       }
+      }
       LB_TICK(6);  // stores
       // no second barrier: the next tile writes T[buf ^ 1]; T[buf] is rewritten two tiles
       // later, after every thread has passed the next tile's barrier
@@ -798,7 +841,7 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   // 1 (default): independent CTAs.  2: CTA pairs (tcgen05 cta_group::2) sharing the "b" operand --
   // 21 % fewer operand bytes out of L2, but the leader then waits for the slower of two epilogues
   // before every tile; measured equal or 1-3 % slower at N = 1000 and N = 3000 (profiles/r1_summary.md).
-  const uint32_t CLs = (cl_env && atoi(cl_env) == 2) ? 2u : 1u;
+  const uint32_t CLs = (cl_env && atoi(cl_env) == 2 && job.kind == PairJob::Rmsd) ? 2u : 1u;
   const loosb200_frames* A = job.a;
   const loosb200_frames* B = job.b;
   if (!A->quantised || !B->quantised || A->unit_log2 != B->unit_log2 || A->Kpad != B->Kpad)
@@ -854,6 +897,9 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   ta.out = job.out; ta.ld = job.ld; ta.stats = job.stats_dev;
   ta.out_t = job.out_t; ta.ld_t = job.ld_t; ta.row_off = (uint32_t)job.row_off;
   ta.prof = nullptr;
+  ta.quat = job.quat; ta.out_d = job.out_d; ta.ldq = job.ldq;
+  if (job.kind != PairJob::Rmsd && (!job.quat || job.self || !job.packed_rows || (job.kind == PairJob::Trace && !job.out_d)))
+    return LOOSB200_ERR_INVALID;
   // The accumulators are handed back right after the drain (0): rounds 2 and 3 of the coefficient
   // phase then run next to the MMAs (fp64 crawls there, but the tensor pipe is not left idle).
   // LOOSB200_RELEASE_AT=1 holds them until the whole fp64 phase is done -- the better choice for
@@ -872,9 +918,11 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   if (job.ev_k0) cudaEventRecord(job.ev_k0, st);
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TensorArgs);
   Kern kern;
-  if (CLs == 2) kern = k_pairs_tensor<2, false>;
-  else if (ta.canon) kern = k_pairs_tensor<1, true>;
-  else kern = k_pairs_tensor<1, false>;
+  if (job.kind == PairJob::Rotation) kern = k_pairs_tensor<1, KIND_ROT>;
+  else if (job.kind == PairJob::Trace) kern = k_pairs_tensor<1, KIND_TRACE>;
+  else if (CLs == 2) kern = k_pairs_tensor<2, KIND_RMSD>;
+  else if (ta.canon) kern = k_pairs_tensor<1, KIND_CANON>;
+  else kern = k_pairs_tensor<1, KIND_RMSD>;
   const int smem = CLs == 2 ? smem_bytes<2>() : smem_bytes<1>();
   LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg;

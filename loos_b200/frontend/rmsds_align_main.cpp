@@ -89,6 +89,8 @@ int main(int argc, char* argv[]) {
   o.add("range1", 0, "0:1", "Range of frames to use from the first trajectory [FORMAT - skip:stride:stop, stop is optional] (default = 0:1:last)");
   o.add("range2", 0, "", "Range of frames to use from the second trajectory [FORMAT - skip:stride:stop, stop is optional] (default = range1)");
   o.add("gpu", 0, "0", "CUDA device to use (extension; the script has no such option)");
+  o.add("engine", 0, "auto", "auto|tensor|fp64: tensor = int8 tensor cores on a 24-bit fixed-point grid (values within ~1e-6 A of the script's), "
+                             "fp64 = double-precision contractions (within 1e-8 A); auto = tensor for selections of up to 43,000 atoms (extension)");
   o.addPositional("model", 1); o.addPositional("traj", 1);
   try {
     if (!o.parse(argc, argv)) return 2;  // argparse exits with status 2 on a usage error
@@ -105,7 +107,7 @@ int main(int argc, char* argv[]) {
     const std::string rmsd2_sel = o.has("rmsd2") ? o.str("rmsd2") : rmsd_sel;
     const std::string range1 = o.str("range1"), range2 = o.has("range2") ? o.str("range2") : range1;
     const int precision = (int)pyInt(o.str("precision"));
-    const int device = (int)o.uns("gpu");
+    const int device = (int)o.uns("gpu"), engine = engineOf(o);
 
     const std::vector<std::string> parts1 = splitColon(range1), parts2 = splitColon(range2);
     std::vector<long> list1, list2;
@@ -153,7 +155,7 @@ int main(int argc, char* argv[]) {
     stageStreaming({&fa2, &fr2}, {&ia2, &ir2}, F2, model2.size(), device, [&](size_t j, float* dst) { traj2->readFramePlanes(frames2[j], dst); });
 
     std::vector<double> M(F1 * F2);
-    check(loosb200_rmsds_align(fa1.h, fr1.h, fa2.h, fr2.h, M.data(), F1), "rmsds-align");
+    check(loosb200_rmsds_align_engine(fa1.h, fr1.h, fa2.h, fr2.h, M.data(), F1, engine), "rmsds-align");
 
     std::cout << "# " << header << std::endl;
     writePyRoundMatrix(M.data(), F1, F2, F1, precision, readerThreads(),

@@ -277,16 +277,21 @@ def test_rmsds_align_tool(files, checker, tmp_path):
     X = xyz.astype(np.float64)
     # explicit stop: frames 5, 8, ..., 38
     fr = list(range(5, 40, 3))
-    r = go("--align", align, "--rmsd", rmsd, "--range1", "5:3:40", "--precision", "4", d / "model.pdb", d / "all.dcd")
+    # (--engine fp64: values within 1e-8 A of the script's, so the rounded text is the script's; the default
+    # tensor engine is within ~1e-6 A and is held to that below)
+    r = go("--engine", "fp64", "--align", align, "--rmsd", rmsd, "--range1", "5:3:40", "--precision", "4", d / "model.pdb", d / "all.dcd")
     want = oracle.rmsds_align(checker, X[fr][:, ia], X[fr][:, ir], X[fr][:, ia], X[fr][:, ir])
     lines = r.stdout.splitlines()
     assert lines[0].startswith("# ") and lines[0].endswith("all.dcd") and "--precision 4" in lines[0]
     assert r.stdout[len(lines[0]) + 1:] == oracle.py_round_text(want, 4)
+    rt = go("--align", align, "--rmsd", rmsd, "--range1", "5:3:40", "--precision", "7", d / "model.pdb", d / "all.dcd")
+    got = np.array([[float(v) for v in l.split()] for l in rt.stdout.splitlines()[1:]])
+    assert got.shape == want.shape and np.abs(got - want).max() < 1e-5
     # the default range stops at len(name), the length of the path as given
     short = tmp_path / "t.dcd"
     shutil.copy(d / "all.dcd", short)
     n = len(str(short))
-    r = go(d / "model.pdb", short)
+    r = go("--engine", "fp64", d / "model.pdb", short)
     assert "length of the trajectory's file name" in r.stderr
     body = r.stdout.splitlines()[1:]
     assert len(body) == n and all(len(l.split()) == n for l in body)
@@ -296,7 +301,7 @@ def test_rmsds_align_tool(files, checker, tmp_path):
     # two trajectories, different selections of equal size on each side
     a1, a2 = 'resid <= 20 && name == "CA"', 'resid >= 25 && resid <= 44 && name == "CA"'
     r1, r2 = 'resid > 25 && resid < 50 && name == "CB"', 'resid < 25 && name == "CB"'
-    r = go("--align", a1, "--align2", a2, "--rmsd", r1, "--rmsd2", r2, "--model2", d / "model.pdb", "--traj2", d / "b.dcd",
+    r = go("--engine", "fp64", "--align", a1, "--align2", a2, "--rmsd", r1, "--rmsd2", r2, "--model2", d / "model.pdb", "--traj2", d / "b.dcd",
            "--range1", "0:7:70", "--range2", "1:2:30", "--precision", "3", d / "model.pdb", d / "a.dcd")
     f1, f2 = list(range(0, 70, 7)), [70 + k for k in range(1, 30, 2)]          # b.dcd holds frames 70..114
     s = lambda q: fo.select(atoms, q)

@@ -79,21 +79,28 @@ def rmsd2ref_e2e(F, N, steps=2):
 
 
 def rmsds_align(F, Na, Nr, steps=3):
-    """rmsds-align: F x F pairs, align on Na atoms, rmsd over Nr others; fp64 pipe, 18 (Na + Nr) flop per pair."""
+    """rmsds-align: F x F pairs, align on Na atoms, rmsd over Nr others; 18 (Na + Nr) flop per pair on the
+    fp64 pipe or the int8 tensor pipe; the two engines are also compared with each other."""
     X = synth_frames_torch(F, Na + Nr, seed=20261022, device="cuda", chunk=4096).cpu().numpy()
     sa, sr = np.arange(Na, dtype=np.uint32), np.arange(Na, Na + Nr, dtype=np.uint32)
+    res = {}
     with lb.FrameSet(X, sel=sa) as a, lb.FrameSet(X, sel=sr) as r:
-        lb.rmsds_align(a, r)
-        ms, wall = [], []
-        for _ in range(steps):
-            t0 = time.perf_counter()
-            M = lb.rmsds_align(a, r)
-            wall.append(1e3 * (time.perf_counter() - t0))
-            ms.append(a.last_timing()[0])
-    ms, wall = float(np.median(ms)), float(np.median(wall))
-    pairs = float(F) * F
-    print(json.dumps({"measure": "rmsds_align", "frames": F, "align_atoms": Na, "rmsd_atoms": Nr, "kernel_ms": ms, "call_ms": wall,
-                      "pairs_per_s": pairs / ms * 1e3, "fp64_TFLOPs": 18.0 * (Na + Nr) * pairs / ms / 1e9, "mean": float(M.mean())}))
+        for eng in ("fp64", "tensor"):
+            lb.rmsds_align(a, r, engine=eng)
+            ms, wall = [], []
+            for _ in range(steps):
+                t0 = time.perf_counter()
+                M = lb.rmsds_align(a, r, engine=eng)
+                wall.append(1e3 * (time.perf_counter() - t0))
+                ms.append(a.last_timing()[0])
+            res[eng] = M
+            ms, wall = float(np.median(ms)), float(np.median(wall))
+            pairs = float(F) * F
+            print(json.dumps({"measure": "rmsds_align", "engine": eng, "frames": F, "align_atoms": Na, "rmsd_atoms": Nr, "kernel_ms": ms,
+                              "call_ms": wall, "pairs_per_s": pairs / ms * 1e3, "algorithmic_TFLOPs": 18.0 * (Na + Nr) * pairs / ms / 1e9,
+                              "mean": float(M.mean())}), flush=True)
+    d = np.abs(res["fp64"] - res["tensor"])
+    print(json.dumps({"measure": "rmsds_align engines", "max_abs_diff": float(d.max()), "mean_abs_diff": float(d.mean())}))
 
 
 if __name__ == "__main__":
