@@ -271,6 +271,7 @@ struct TensorArgs {
   // rmsds-align (KIND_ROT / KIND_TRACE, see the kernel): unit quaternions of the align-selection pass,
   // [column j][local row][4], and the double result band, column-major; both with `ldq` local rows
   double* quat; double* out_d; size_t ldq;
+  int w256;        // 256: the weight of one digit, as a run-time value (see the epilogue's combine)
   int release_at;  // when the epilogue hands TMEM back (see kernel)
   long long* prof;  // optional [grid][NWARPS][8] cycle counters (LOOSB200_PROF=1)
 };
@@ -557,43 +558,57 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_after();
       LB_TICK(0);  // waiting for the accumulators
 
-      double v[3 * GROUP_FRAMES];  // v[3 jb + axis'] = sum_s 2^(8s) D_s, exact (|v| < 2^58 rounds at 2^-53)
+      // v[3 jb + axis'] = sum_s 2^(8s) D_s as a 64-bit integer (|v| < 2^58): one IMAD.WIDE per class and
+      // element.  (The first version summed in fp64 through the exponent-bias trick: four instructions per
+      // class and element -- constant high word, xor, two DADDs -- a third of all the epilogue issued.)
+      long long v[3 * GROUP_FRAMES];
 #pragma unroll
-      for (int c = 0; c < 3 * GROUP_FRAMES; ++c) v[c] = 0.0;
+      for (int c = 0; c < 3 * GROUP_FRAMES; ++c) v[c] = 0;
+      const int w8[4] = {a.w256 >> 8, a.w256, a.w256 << 8, a.w256 << 16};  // 1, 2^8, 2^16, 2^24
       QcpPolyF polf[4];
       float e0s[4];
       int state[4];  // 0: no entry, 1: zero, 2: solve
 
-      // int32 -> double without the conversion unit: the bits (0x433+8s)<<52 | (D ^ 2^31)
-      // are the double 2^(52+8s) + (D + 2^31) 2^(8s); subtracting the bias leaves D 2^(8s).
       auto combine = [&](const uint32_t (&r)[18], int s, int c0, int count) {
-        const uint32_t hi = (uint32_t)(0x433 + 8 * s) << 20;
-        const double bias = __hiloint2double((int)hi, (int)0x80000000u);
 #pragma unroll
         for (int c = 0; c < 18; ++c)
-          if (c < count) v[c0 + c] += __hiloint2double((int)hi, (int)(r[c] ^ 0x80000000u)) - bias;
+          if (c < count) {
+            // (the weights come from a kernel argument: with an immediate power of two ptxas splits the
+            // multiply-add into shifts, high products and carry chains)
+            if (s < 4) asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(v[c0 + c]) : "r"((int)r[c]), "r"(w8[s]));
+            else asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tadd.s32 hi, hi, %1;\n\tmov.b64 %0, {lo, hi};\n\t}"
+                     : "+l"(v[c0 + c]) : "r"((int)r[c]));  // + D_4 2^32: the high word alone
+          }
+      };
+      // 3-way selection by a lane-dependent index on the 32-bit halves (two SEL each; left to the compiler
+      // a double-valued ?: chain became divergent branches)
+      auto pick = [](bool k0, bool k1, long long x0, long long x1, long long x2) {
+        const int lo = k0 ? (int)x0 : (k1 ? (int)x1 : (int)x2);
+        const int hi = k0 ? (int)(x0 >> 32) : (k1 ? (int)(x1 >> 32) : (int)(x2 >> 32));
+        return ((long long)hi << 32) | (unsigned int)lo;
       };
       // exchange rows inside each lane triple and build the quartic of this lane's pair (fp64)
       auto do_round = [&](const int round) {
         const int cb = 3 * RBASE[round];  // first column of the round's frames
-        double own[3], s1[3], s2[3], R[9];
+        long long own[3], s1[3], s2[3];
+        double R[9];
         const int d1 = (al + 2) % 3, d2 = (al + 1) % 3;  // destination axis served at shift 1, 2
 #pragma unroll
         for (int be = 0; be < 3; ++be) {
-          const double x0 = v[cb + be], x1 = v[cb + 3 + be];
-          const double x2 = RCNT[round] == 3 ? v[cb + 6 + be] : x0;  // two-frame rounds: lane al = 2 idles
-          own[be] = al == 0 ? x0 : (al == 1 ? x1 : x2);
-          s1[be] = d1 == 0 ? x0 : (d1 == 1 ? x1 : x2);
-          s2[be] = d2 == 0 ? x0 : (d2 == 1 ? x1 : x2);
+          const long long x0 = v[cb + be], x1 = v[cb + 3 + be];
+          const long long x2 = RCNT[round] == 3 ? v[cb + 6 + be] : x0;  // two-frame rounds: lane al = 2 idles
+          own[be] = pick(al == 0, al == 1, x0, x1, x2);
+          s1[be] = pick(d1 == 0, d1 == 1, x0, x1, x2);
+          s2[be] = pick(d2 == 0, d2 == 1, x0, x1, x2);
         }
         const int src1 = tri + (al + 1) % 3, src2 = tri + (al + 2) % 3;
 #pragma unroll
         for (int be = 0; be < 3; ++be) {
           // rows of R end up as (al, al+1, al+2) mod 3: a cyclic relabelling of the axes of
           // frame a is a proper rotation and leaves lambda_max unchanged
-          R[be] = own[be];
-          R[3 + be] = __shfl_sync(0xffffffffu, s1[be], src1);
-          R[6 + be] = __shfl_sync(0xffffffffu, s2[be], src2);
+          R[be] = (double)own[be];  // one rounding at 2^-53, only for |v| >= 2^53
+          R[3 + be] = (double)__shfl_sync(0xffffffffu, s1[be], src1);
+          R[6 + be] = (double)__shfl_sync(0xffffffffu, s2[be], src2);
         }
         const int jb = RBASE[round] + al;
         const uint32_t j = J * COL_TILE_FRAMES + g * GROUP_FRAMES + jb;
@@ -897,6 +912,7 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   ta.out = job.out; ta.ld = job.ld; ta.stats = job.stats_dev;
   ta.out_t = job.out_t; ta.ld_t = job.ld_t; ta.row_off = (uint32_t)job.row_off;
   ta.prof = nullptr;
+  ta.w256 = 256;
   ta.quat = job.quat; ta.out_d = job.out_d; ta.ldq = job.ldq;
   if (job.kind != PairJob::Rmsd && (!job.quat || job.self || !job.packed_rows || (job.kind == PairJob::Trace && !job.out_d)))
     return LOOSB200_ERR_INVALID;

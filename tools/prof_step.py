@@ -4,6 +4,11 @@ sys.path.insert(0, "/root/repo")
 from loos_b200 import capi as _capi
 if os.environ.get('AB_LIB'):
     _capi.LIB_PATH = os.environ['AB_LIB']   # A/B runs against another build of the library
+    import ctypes as _C
+    _L = _C.CDLL(_capi.LIB_PATH)
+    for _n in list(_capi.SIGNATURES):           # an older build lacks the newer entry points
+        if not hasattr(_L, _n):
+            del _capi.SIGNATURES[_n]
 import loos_b200 as lb
 from loos_b200.synth import synth_frames_torch
 F, N = 100000, 1000
