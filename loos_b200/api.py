@@ -284,7 +284,11 @@ class PinnedMatrix:
             lib().loosb200_host_free(self._p)
             self._p = None
 
-    __del__ = free
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:   # interpreter shutdown: the module globals may be gone, the process is ending anyway
+            pass
 
 
 def stage_multi(coords, devices, sel=None, layout="xyz"):

@@ -194,14 +194,21 @@ static int pick_engine(int engine, const loosb200_frames* a) {
 // matrix costs (t + 1) tiles, of a rectangle a constant.  Contiguous ranges (instead of the
 // interleaved deal above) make every part's share a few wide rectangles of the matrix, which is
 // what the copy engines want when the parts are gathered into one matrix over PCIe or NVLink.
-std::vector<uint32_t> contiguous_cuts(size_t F, int nparts, bool self) {
+// `weights` (optional, one per part) makes the shares proportional to them instead of equal: the
+// host-output path sizes a device's share by what its PCIe link delivers (multi.cu).
+std::vector<uint32_t> contiguous_cuts(size_t F, int nparts, bool self, const double* weights) {
   const uint32_t T = (uint32_t)((F + TILE_FRAMES - 1) / TILE_FRAMES);
   std::vector<uint32_t> cuts(nparts + 1, T);
   cuts[0] = 0;
   const double total = self ? 0.5 * (double)T * (T + 1) : (double)T;
+  double wsum = 0.0;
+  for (int p = 0; p < nparts; ++p) wsum += weights ? std::max(weights[p], 0.0) : 1.0;
+  if (!(wsum > 0.0)) { weights = nullptr; wsum = nparts; }
   uint32_t t = 0;
+  double wacc = 0.0;
   for (int p = 1; p < nparts; ++p) {
-    const double want = total * p / nparts;
+    wacc += weights ? std::max(weights[p - 1], 0.0) : 1.0;
+    const double want = total * wacc / wsum;
     while (t < T && (self ? 0.5 * (double)t * (t + 1) : (double)t) < want) ++t;
     cuts[p] = t;
   }

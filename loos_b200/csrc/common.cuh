@@ -166,7 +166,7 @@ enum class OutKind { None, Copy, Device };
 int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric, bool packed,
               const std::vector<uint32_t>& rows, float* out, OutKind okind, size_t ld,
               loosb200_stats* stats, int engine, bool canon = false);
-std::vector<uint32_t> contiguous_cuts(size_t F, int nparts, bool self);
+std::vector<uint32_t> contiguous_cuts(size_t F, int nparts, bool self, const double* weights = nullptr);
 std::vector<uint32_t> row_tile_range(uint32_t t0, uint32_t t1);
 int launch_pairs_fp64(const PairJob& job, cudaStream_t st);
 int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches);

@@ -11,6 +11,7 @@
 //                   transfer rides under the contraction tile by tile), or they fill local strips
 //                   that the copy engines push band by band (LOOSB200_GATHER=copy).
 #include <limits.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -77,13 +78,87 @@ static void merge_stats(loosb200_stats* total, const std::vector<loosb200_stats>
   }
 }
 
+// Device-to-host rate of every device's PCIe link with ALL of them copying at once, measured once per
+// process and device list (2 x 64 MiB per device into pinned memory, ~20 ms).  On the 8-GPU boxes this was
+// developed on the links are far from equal (10.8 ... 22.6 GB/s per device with eight copying, 122 GB/s
+// in total: profiles/bench/r2_pinned_d2h_8gpu.jsonl), and with equal shares of the matrix the slowest
+// link sets the time of the host-output call.  Returns false when anything fails (equal shares then).
+static bool link_rates(loosb200_frames* const* a, int n, std::vector<double>& gbs) {
+  static std::mutex mu;
+  static std::vector<int> cached_devs;
+  static std::vector<double> cached;
+  std::vector<int> devs(n);
+  for (int d = 0; d < n; ++d) devs[d] = a[d]->device;
+  std::lock_guard<std::mutex> lk(mu);
+  if (devs == cached_devs) { gbs = cached; return true; }
+  NvtxRange nvtx("loosb200 probe of the devices' PCIe links");
+  constexpr size_t BYTES = (size_t)64 << 20;
+  std::vector<void*> dbuf(n, nullptr), hbuf(n, nullptr);
+  std::vector<double> rate(n, 0.0);
+  std::atomic<int> ready(0), failed(0);
+  std::vector<std::thread> th;
+  for (int d = 0; d < n; ++d)
+    th.emplace_back([&, d]() {
+      bool ok = cudaSetDevice(devs[d]) == cudaSuccess && dev_alloc(&dbuf[d], BYTES) == cudaSuccess &&
+                host_alloc(&hbuf[d], BYTES) == cudaSuccess;
+      cudaStream_t st = nullptr;
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      ok = ok && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
+      if (ok) ok = cudaMemcpyAsync(hbuf[d], dbuf[d], BYTES / 8, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                   cudaStreamSynchronize(st) == cudaSuccess;  // warm-up
+      if (!ok) failed.fetch_add(1);
+      ready.fetch_add(1);
+      while (ready.load() < n) std::this_thread::yield();  // all links start together
+      if (ok && failed.load() == 0) {
+        cudaEventRecord(e0, st);
+        for (int r = 0; r < 2; ++r) cudaMemcpyAsync(hbuf[d], dbuf[d], BYTES, cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(e1, st);
+        float ms = 0.f;
+        if (cudaStreamSynchronize(st) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess && ms > 0.f)
+          rate[d] = 2.0 * (double)BYTES / (ms * 1e-3) / 1e9;
+        else failed.fetch_add(1);
+      }
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+      if (st) cudaStreamDestroy(st);
+      if (dbuf[d]) dev_release(dbuf[d]);
+      if (hbuf[d]) host_release(hbuf[d]);
+      cudaGetLastError();
+    });
+  for (auto& t : th) t.join();
+  if (failed.load()) return false;
+  cached_devs = devs; cached = rate; gbs = rate;
+  if (getenv("LOOSB200_VERBOSE")) {
+    fprintf(stderr, "[loosb200] device-to-host GB/s per device, all copying:");
+    for (double r : rate) fprintf(stderr, " %.1f", r);
+    fprintf(stderr, "\n");
+  }
+  return true;
+}
+
 // All parts of one all-to-all job.  kind Copy: out is the caller's matrix (host memory, or the HBM of
 // any device): every device delivers its strips there.  kind Device: out lives in the HBM of
 // a[0]'s device; that device writes its share directly, the others by peer stores or strip copies.
 static int pairs_multi(loosb200_frames* const* a, loosb200_frames* const* b, int n, bool self, float* out,
                        OutKind kind, size_t ld, loosb200_stats* stats, int engine) {
   const size_t F = a[0]->F;
-  const std::vector<uint32_t> cuts = contiguous_cuts(F, n, self);
+  // Shares of the tile rows: equal work, except when every device ships its part to HOST memory over its
+  // own PCIe link -- then a share costs max(compute, copy) per pair, and the copy term differs by device.
+  std::vector<double> weights;
+  if (kind == OutKind::Copy && n > 1 && out && !(getenv("LOOSB200_EQUAL_SHARES") && atoi(getenv("LOOSB200_EQUAL_SHARES")))) {
+    cudaPointerAttributes pa;
+    const bool host = cudaPointerGetAttributes(&pa, out) != cudaSuccess || pa.type == cudaMemoryTypeHost ||
+                      pa.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    std::vector<double> gbs;
+    if (host && link_rates(a, n, gbs)) {
+      const double compute = 8e-11 * (double)std::max<size_t>(a[0]->N, 256) / 1000.0;  // s per pair, tensor engine on one B200
+      const double bytes = self ? 8.0 : 4.0;                                           // entry + mirror image
+      for (int d = 0; d < n; ++d) weights.push_back(1.0 / std::max(compute, bytes / (std::max(gbs[d], 0.1) * 1e9)));
+    }
+  }
+  const std::vector<uint32_t> cuts = contiguous_cuts(F, n, self, weights.empty() ? nullptr : weights.data());
   bool peer_stores = false;
   if (kind == OutKind::Device) {
     const char* g = getenv("LOOSB200_GATHER");

@@ -1,14 +1,12 @@
 #!/bin/bash
-# round 2, 8-GPU call: the one-process multi-GPU path at full width, bench line with C5, the tools with --gpus 8
+# 8-GPU call 2: host delivery with link-weighted shares against equal shares, then the bench line
 N=${1:-8}
 mkdir -p gpurun_out
-nvidia-smi topo -m > gpurun_out/r2_topo_${N}gpu.txt 2>&1; (lscpu | head -25; numactl -H 2>/dev/null; free -g) > gpurun_out/r2_host_${N}gpu.txt 2>&1
-timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/r2_pytest_multi_${N}gpu.log 2>&1; echo "pytest rc=$?"
-tail -3 gpurun_out/r2_pytest_multi_${N}gpu.log
-D2H_GB=2 timeout 300 python tools/prof_d2h_multi.py > gpurun_out/r2_d2h_${N}gpu.txt 2>&1; cat gpurun_out/r2_d2h_${N}gpu.txt
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/r2_pytest_multi_${N}gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r2_pytest_multi_${N}gpu.log
+LOOSB200_VERBOSE=1 timeout 600 python tools/prof_e2e_multi.py $N > gpurun_out/r2_e2e_shares_${N}gpu.txt 2>&1; cat gpurun_out/r2_e2e_shares_${N}gpu.txt
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
   bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/r2_bench_${N}gpu.json 2> gpurun_out/r2_bench_${N}gpu.err; echo "bench rc=$?"
-tail -c 600 gpurun_out/r2_bench_${N}gpu.err
+tail -c 300 gpurun_out/r2_bench_${N}gpu.err
 python - <<PY
 import json
 try:
@@ -17,4 +15,3 @@ try:
     for k,v in (d.get("also") or {}).items(): print(k, "value %.3e ms %.1f frac %.3f parity %s" % (v["value"], v["ms_per_step"], v["roofline"]["frac"], v["parity"]))
 except Exception as ex: print("no json", ex)
 PY
-timeout 600 python tools/prof_multi_tool.py 1000 5000 $N > gpurun_out/r2_multi_tool_${N}gpu.txt 2>&1; cat gpurun_out/r2_multi_tool_${N}gpu.txt
