@@ -101,9 +101,11 @@ int loosb200_stage_frames_device(loosb200_frames** out, const float* dev_xyz, si
                                  size_t natoms, const uint32_t* sel, size_t nsel, int layout,
                                  int device);
 void loosb200_free(loosb200_frames* h);
-/* Freed handles leave their large device buffers in a size-keyed cache so that the next
- * call of the same shape skips cudaMalloc/cudaFree (hundreds of ms at 40 GB).  This
- * returns the cache to the driver. */
+/* Freed handles and finished calls leave their device buffers (the 40 GB bounce matrix of the
+ * host-output path included) in a size-keyed cache so that the next call of the same shape skips
+ * cudaMalloc/cudaFree (hundreds of ms at 40 GB).  This returns the cache to the driver: call it before
+ * another allocator of the same process needs the memory.  LOOSB200_CACHE_GB caps the cache
+ * (default 96, 0 disables it). */
 void loosb200_trim(void);
 int loosb200_frames_info(const loosb200_frames* h, size_t* F, size_t* N, int* device);
 /* Centroids as centerAtOrigin returns them: F x 3 doubles (host). */

@@ -27,7 +27,20 @@ struct DevCache {
 };
 DevCache& cache() { static DevCache c; return c; }
 constexpr size_t CACHE_MAX_PER_KEY = 64;               // blocks kept per (device, size)
-constexpr size_t CACHE_MAX_TOTAL = (size_t)96 << 30;  // never sit on more than this
+// Never sit on more than this (all devices together).  LOOSB200_CACHE_GB overrides the 96 GB default --
+// 0 turns the cache off -- for processes that share their GPUs with another allocator (a framework's
+// caching allocator, NCCL): those cannot see what is parked here, so either cap it or call
+// loosb200_trim() before handing the device over.  Blocks are only ever released after the stream
+// that used them has been synchronised (every call site does so before dev_release), which is what
+// makes a cached block safe to hand to a handle on another stream.
+size_t cache_max_total() {
+  static const size_t v = [] {
+    const char* e = getenv("LOOSB200_CACHE_GB");
+    const double gb = e ? atof(e) : 96.0;
+    return gb <= 0.0 ? (size_t)0 : (size_t)(gb * 1073741824.0);
+  }();
+  return v;
+}
 }  // namespace
 
 cudaError_t dev_alloc(void** p, size_t bytes) {
@@ -68,7 +81,7 @@ void dev_release(void* p) {
     std::lock_guard<std::mutex> g(c.mu);
     auto it = c.live.find(p);
     if (it != c.live.end()) { info = it->second; c.live.erase(it); }
-    if (info.first >= 0 && c.cached_bytes + info.second <= CACHE_MAX_TOTAL &&
+    if (info.first >= 0 && c.cached_bytes + info.second <= cache_max_total() &&
         c.free_blocks[info].size() < CACHE_MAX_PER_KEY) {
       c.free_blocks[info].push_back(p);
       c.cached_bytes += info.second;
