@@ -853,10 +853,15 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   if (const char* e = getenv("LOOSB200_SB_R")) SB_R = (uint32_t)std::max(1, atoi(e));
   if (const char* e = getenv("LOOSB200_SB_C")) SB_C = (uint32_t)std::max(1, atoi(e));
   const char* cl_env = getenv("LOOSB200_CLUSTER");
-  // 1 (default): independent CTAs.  2: CTA pairs (tcgen05 cta_group::2) sharing the "b" operand --
-  // 21 % fewer operand bytes out of L2, but the leader then waits for the slower of two epilogues
-  // before every tile; measured equal or 1-3 % slower at N = 1000 and N = 3000 (profiles/r1_summary.md).
-  const uint32_t CLs = (cl_env && atoi(cl_env) == 2 && job.kind == PairJob::Rmsd) ? 2u : 1u;
+  // 1: independent CTAs.  2: CTA pairs (tcgen05 cta_group::2) sharing the "b" operand -- a quarter less
+  // shared-memory traffic per MAC and 21 % fewer operand bytes out of L2, but an fp64 instruction on
+  // either SM stalls the pair's MMAs, so the accumulators are held through the whole fp64 part and the
+  // leader waits for the slower of two epilogues before every tile.  That fixed cost per tile loses at
+  // N = 1000 (+2.5 %), is even at N = 2000-3000 and wins 1-3 % from N = 5000 up
+  // (profiles/r2_phase_counters.txt), hence the default by selection size.
+  const uint32_t CLs = job.kind != PairJob::Rmsd ? 1u
+                       : cl_env ? (atoi(cl_env) == 2 ? 2u : 1u)
+                       : (job.a->N >= 4096 && !job.canon ? 2u : 1u);
   const loosb200_frames* A = job.a;
   const loosb200_frames* B = job.b;
   if (!A->quantised || !B->quantised || A->unit_log2 != B->unit_log2 || A->Kpad != B->Kpad)
@@ -918,9 +923,10 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
     return LOOSB200_ERR_INVALID;
   // The accumulators are handed back right after the drain (0): rounds 2 and 3 of the coefficient
   // phase then run next to the MMAs (fp64 crawls there, but the tensor pipe is not left idle).
-  // LOOSB200_RELEASE_AT=1 holds them until the whole fp64 phase is done -- the better choice for
-  // N <= 2048 until rounds 0 and 1 were moved under the drain; now 3 % slower at N = 1000 and 3000.
-  ta.release_at = getenv("LOOSB200_RELEASE_AT") ? (atoi(getenv("LOOSB200_RELEASE_AT")) ? 1 : 0) : 0;
+  // LOOSB200_RELEASE_AT=1 holds them until the whole fp64 phase is done: 3 % slower for independent
+  // CTAs, but what the CTA-pair shape needs (fp64 on either SM stalls the pair's MMAs: 462 ms against
+  // 411 ms at C4).
+  ta.release_at = getenv("LOOSB200_RELEASE_AT") ? (atoi(getenv("LOOSB200_RELEASE_AT")) ? 1 : 0) : (CLs == 2 ? 1 : 0);
   const bool want_prof = getenv("LOOSB200_PROF") != nullptr;
 
   int dev = 0, sms = 148;

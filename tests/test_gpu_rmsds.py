@@ -58,7 +58,7 @@ def test_golden_kats(lb, engine):
 
 
 @pytest.mark.parametrize("engine", ["fp64", "tensor"])
-@pytest.mark.parametrize("F,N", [(1, 5), (2, 1), (41, 64), (80, 65), (121, 333), (200, 1000)])
+@pytest.mark.parametrize("F,N", [(1, 5), (2, 1), (41, 64), (80, 65), (121, 333), (200, 1000), (123, 4500)])
 def test_vs_oracle_shapes(lb, checker, engine, F, N):
     from loos_b200.synth import SEED0, synth_frames
     X = synth_frames(F, N, seed=SEED0 + F * 7 + N)
@@ -68,6 +68,28 @@ def test_vs_oracle_shapes(lb, checker, engine, F, N):
     err = np.abs(M.astype(np.float64) - ref.astype(np.float64))
     assert err.max() <= TOL, (err.max(), err.mean())
     assert np.array_equal(M, M.T) and np.all(np.diag(M) == 0)
+
+
+def test_default_launch_shape_by_selection_size(lb, monkeypatch):
+    """From 4096 atoms up the tensor engine launches CTA pairs by default (pairs_tensor.cu): same bits as
+    the independent-CTA shape asked for explicitly, for the matrix, the cross matrix and the banded text."""
+    from loos_b200.api import rmsds_text
+    from loos_b200.synth import synth_frames
+    X = synth_frames(97, 4100, seed=77)
+    Y = synth_frames(45, 4100, seed=78)
+    got = []
+    for shape in (None, "1"):
+        if shape:
+            monkeypatch.setenv("LOOSB200_CLUSTER", shape)
+        with lb.FrameSet(X) as fs, lb.FrameSet(Y) as fy:
+            M, st = lb.rmsds(fs, engine="tensor")
+            C, _ = lb.rmsds_cross(fs, fy, engine="tensor")
+            monkeypatch.setenv("LOOSB200_TEXT_BAND_ROWS", "40")
+            t, _ = rmsds_text(fs, precision=7, engine="tensor")
+            monkeypatch.delenv("LOOSB200_TEXT_BAND_ROWS")
+        got.append((M, C, t, st["max"]))
+    assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
+    assert got[0][2] == got[1][2] and got[0][3] == got[1][3]
 
 
 @pytest.mark.parametrize("engine", ["fp64", "tensor"])

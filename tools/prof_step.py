@@ -11,7 +11,7 @@ if os.environ.get('AB_LIB'):
             del _capi.SIGNATURES[_n]
 import loos_b200 as lb
 from loos_b200.synth import synth_frames_torch
-F, N = 100000, 1000
+F, N = int(os.environ.get('PS_FRAMES', 100000)), int(os.environ.get('PS_ATOMS', 1000))
 X = synth_frames_torch(F, N, device="cuda")
 out = torch.empty((F, F), dtype=torch.float32, device="cuda")
 for it in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
