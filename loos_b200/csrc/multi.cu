@@ -153,7 +153,9 @@ static int pairs_multi(loosb200_frames* const* a, loosb200_frames* const* b, int
     cudaGetLastError();
     std::vector<double> gbs;
     if (host && link_rates(a, n, gbs)) {
-      const double compute = 8e-11 * (double)std::max<size_t>(a[0]->N, 256) / 1000.0;  // s per pair, tensor engine on one B200
+      // s per pair on one B200: tensor engine 1.25e10 pairs/s at N = 1000, fp64 engine 9.5 TFLOP/s of 18 N flop
+      const bool fp64 = engine == LOOSB200_ENGINE_FP64 || a[0]->N > TENSOR_MAX_ATOMS;
+      const double compute = (fp64 ? 1.9e-9 : 8e-11) * (double)std::max<size_t>(a[0]->N, 256) / 1000.0;
       const double bytes = self ? 8.0 : 4.0;                                           // entry + mirror image
       for (int d = 0; d < n; ++d) weights.push_back(1.0 / std::max(compute, bytes / (std::max(gbs[d], 0.1) * 1e9)));
     }
