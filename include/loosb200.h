@@ -268,6 +268,13 @@ int loosb200_rmsds_align_engine(loosb200_frames* align1, loosb200_frames* rmsd1,
 int loosb200_align_accumulate(loosb200_frames* align, loosb200_frames* accum_set, const double* target,
                               double* sum_out, double* out_xforms);
 
+/* How the one-process multi-GPU calls cut the 40-frame row tiles [0, T), T = ceil(F / 40), into `nparts`
+ * contiguous ranges: equal work (row tile t of the triangle costs t + 1 tiles, of a rectangle a constant),
+ * or, with `weights` (one per part, NULL = equal), work proportional to them -- the host-output calls
+ * weight a device by 1 / max(compute, bytes / its PCIe rate) per pair.  cuts_out[nparts + 1]:
+ * part p owns row tiles [cuts[p], cuts[p + 1]).  Host logic only (no device needed). */
+int loosb200_share_cuts(size_t F, int nparts, int self, const double* weights, uint32_t* cuts_out);
+
 /* ---- timing hooks (bench.py) ----
  * Device time in milliseconds of the kernels of the most recent compute call on
  * this handle, measured with CUDA events on the stream they were launched on:

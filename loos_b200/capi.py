@@ -61,6 +61,7 @@ SIGNATURES = {
     "loosb200_align_accumulate": (_i, [_vp, _vp, _dp, _dp, _dp]),
     "loosb200_rmsds_align": (_i, [_vp, _vp, _vp, _vp, _dp, _sz]),
     "loosb200_rmsds_align_engine": (_i, [_vp, _vp, _vp, _vp, _dp, _sz, _i]),
+    "loosb200_share_cuts": (_i, [_sz, _i, _i, _dp, _up]),
     "loosb200_rmsds_self_text": (_i, [_vp, C.c_uint, SINK, _vp, _sp, _i]),
     "loosb200_rmsds_cross_text": (_i, [_vp, _vp, C.c_uint, SINK, _vp, _sp, _i]),
     "loosb200_last_timing": (_i, [_vp, _dp, _dp]),

@@ -303,3 +303,10 @@ extern "C" void* loosb200_host_alloc(size_t bytes) {
 extern "C" void loosb200_host_free(void* p) {
   if (p) { cudaFreeHost(p); cudaGetLastError(); }
 }
+
+extern "C" int loosb200_share_cuts(size_t F, int nparts, int self, const double* weights, uint32_t* cuts_out) {
+  if (F == 0 || nparts < 1 || !cuts_out) return LOOSB200_ERR_INVALID;
+  const std::vector<uint32_t> c = contiguous_cuts(F, nparts, self != 0, weights);
+  for (int p = 0; p <= nparts; ++p) cuts_out[p] = c[p];
+  return LOOSB200_OK;
+}

@@ -183,3 +183,39 @@ def test_stripes_partition_the_rows():
             assert all(parts[k][1] == parts[k + 1][0] for k in range(world - 1))
             sizes = [hi - lo for lo, hi in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _cuts(F, nparts, self_, weights=None):
+    import ctypes as C
+    from loos_b200 import capi
+    out = (C.c_uint32 * (nparts + 1))()
+    w = None if weights is None else (C.c_double * nparts)(*weights)
+    capi.check(capi.lib().loosb200_share_cuts(F, nparts, 1 if self_ else 0, w, out))
+    return list(out)
+
+
+def test_contiguous_shares_of_the_one_process_multi_gpu_calls():
+    """loosb200_share_cuts (host logic of multi.cu): contiguous ranges of 40-frame row tiles that cover
+    [0, T) exactly once; equal work without weights (row tile t of the triangle costs t + 1 tiles),
+    work proportional to the weights with them -- the host-output path weights a device by what its
+    PCIe link delivers (10.8 ... 22.6 GB/s on the 8-GPU boxes of this pool)."""
+    for F in (1, 40, 41, 1000, 100000):
+        T = (F + 39) // 40
+        for n in (1, 2, 3, 8):
+            for self_ in (True, False):
+                c = _cuts(F, n, self_)
+                assert c[0] == 0 and c[-1] == T and all(a <= b for a, b in zip(c, c[1:])), (F, n, c)
+    work = lambda c, self_: [(b * (b + 1) - a * (a + 1)) / 2 if self_ else b - a for a, b in zip(c, c[1:])]
+    c = _cuts(100000, 8, True)
+    w = work(c, True)
+    assert max(w) / min(w) < 1.02                                    # 2500 row tiles: equal to a row tile
+    rates = [10.8, 10.8, 11.0, 11.0, 18.3, 18.2, 19.2, 22.6]
+    c = _cuts(100000, 8, True, rates)
+    w = work(c, True)
+    tot = sum(w)
+    for share, r in zip(w, rates):
+        assert abs(share / tot - r / sum(rates)) < 0.005, (c, w)
+    c = _cuts(100000, 4, False, [1, 1, 2, 4])
+    assert [b - a for a, b in zip(c, c[1:])] == pytest.approx([312.5, 312.5, 625, 1250], abs=1.01)
+    assert _cuts(1000, 3, True, [0.0, 0.0, 0.0]) == _cuts(1000, 3, True)   # useless weights: equal shares
+    assert _cuts(1000, 3, True, [0.0, 1.0, 0.0])[1:3] == [0, 25]           # a part may be empty
