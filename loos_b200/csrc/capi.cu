@@ -166,18 +166,20 @@ struct Bands {
 // Cut `rows` (ascending) into <= maxbands contiguous bands of about equal tile
 // count, ordered from the last rows to the first so that, in symmetric mode, the
 // columns of a band are complete as soon as the band has been computed.
-static Bands make_bands(const std::vector<uint32_t>& rows, bool self, uint32_t col_tiles, int maxbands) {
+// equal_rows: bands of equal HEIGHT instead (column-block delivery, see run_pairs).
+static Bands make_bands(const std::vector<uint32_t>& rows, bool self, uint32_t col_tiles, int maxbands, bool equal_rows = false) {
   Bands B;
   B.rows = rows;
   uint64_t total = 0;
   for (uint32_t t : rows) total += self ? (uint64_t)t + 1 : col_tiles;
   int nb = (int)std::min<uint64_t>((uint64_t)std::max(1, maxbands), std::max<uint64_t>(1, rows.size()));
   const uint64_t per = (total + nb - 1) / nb;
+  const uint32_t rows_per = (uint32_t)((rows.size() + nb - 1) / nb);
   uint32_t r1 = (uint32_t)rows.size();
   while (r1 > 0) {
     uint64_t acc = 0;
     uint32_t r0 = r1;
-    while (r0 > 0 && (acc < per || B.bands.size() + 1 == (size_t)nb)) {
+    while (r0 > 0 && (equal_rows ? r1 - r0 < rows_per : (acc < per || B.bands.size() + 1 == (size_t)nb))) {
       --r0;
       acc += self ? (uint64_t)rows[r0] + 1 : col_tiles;
     }
@@ -269,8 +271,19 @@ int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric,
       if (rows[r] != rows[r - 1] + 1) return LOOSB200_ERR_INVALID;
   const size_t out_rows = packed ? rows.size() * TILE_FRAMES : 0;  // packed: rows x ld (row-major)
 
-  const int maxbands = copy ? 16 : 1;
-  Bands B = make_bands(rows, self, col_tiles, maxbands);
+  // Column-block delivery: the WHOLE symmetric matrix from one device.  Bands run from the last rows up, so
+  // once the band of rows [A, B) is done the COLUMNS [A, B) of the symmetric matrix are final (rows below B
+  // came from the earlier bands' direct stores, rows above A from this band's mirror stores): the kernels
+  // write into a full F x F bounce matrix and every band ships its columns as ONE contiguous block of
+  // (B - A) x F floats -- the link then runs at its plain-copy rate, which the 2-D strip copies (runs of
+  // B - A floats) do not reach (C4, same box: call 785 -> 714 ms = 56 GB/s, profiles/bench/r2_e2e_column_blocks.txt).  Bands of equal height, so that the copies,
+  // not the shrinking kernels, pace the pipeline; only the first band's kernel is exposed.
+  const bool colmode = strips && self && symmetric && out && !rows.empty() && rows[0] == 0 &&
+                       rows.size() == (FA + TILE_FRAMES - 1) / TILE_FRAMES &&
+                       !(getenv("LOOSB200_STRIPS") && atoi(getenv("LOOSB200_STRIPS")));
+  int maxbands = copy ? (colmode ? 64 : 16) : 1;
+  if (copy) if (const char* e = getenv("LOOSB200_BANDS")) maxbands = std::min(256, std::max(1, atoi(e)));
+  Bands B = make_bands(rows, self, col_tiles, maxbands, colmode);
   // band k covers matrix rows [bA[k], bB[k]); strip mode: its row strip S_k and column strip T_k
   std::vector<size_t> bA(B.bands.size()), bB(B.bands.size()), offS(B.bands.size()), offT(B.bands.size());
   size_t strip_floats = 0;
@@ -304,7 +317,7 @@ int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric,
             dev_alloc_t(&d_prefix, sizeof(uint32_t) * std::max<size_t>(1, B.prefix.size())) == cudaSuccess &&
             dev_alloc_t(&d_stats, 2 * sizeof(double)) == cudaSuccess;
   if (ok && copy) {
-    const size_t n = packed ? out_rows * FB : strip_floats;
+    const size_t n = packed ? out_rows * FB : (colmode ? FA * FA : strip_floats);
     ok = dev_alloc_t(&d_out, sizeof(float) * std::max<size_t>(1, n)) == cudaSuccess;
     for (int c = 0; c < ncopy && ok; ++c) ok = cudaStreamCreateWithFlags(&copy_streams[c], cudaStreamNonBlocking) == cudaSuccess;
     for (auto& e : evs) if (ok) ok = cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
@@ -332,6 +345,8 @@ int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric,
     job.canon = canon;
     if (!d_out) {
       job.out = nullptr; job.ld = ld;
+    } else if (colmode) {
+      job.out = d_out; job.ld = FA;  // the plain F x F matrix, direct and mirror stores
     } else if (strips) {
       job.out = d_out + offS[k]; job.ld = bB[k] - bA[k]; job.row_off = bA[k];
       job.out_t = d_out + offT[k]; job.ld_t = bA[k];
@@ -364,6 +379,10 @@ int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric,
         const size_t width = std::min(FB, ((size_t)B.rows[bd.r1 - 1] + 1) * TILE_FRAMES);
         cudaMemcpy2DAsync(out + r_lo * ld, ld * sizeof(float), d_out + r_lo * FB, FB * sizeof(float),
                           width * sizeof(float), nr, cudaMemcpyDefault, copy_stream);
+      } else if (colmode) {
+        if (bB[k] > bA[k])
+          cudaMemcpy2DAsync(out + bA[k] * ld, ld * sizeof(float), d_out + bA[k] * FA, FA * sizeof(float),
+                            FA * sizeof(float), bB[k] - bA[k], cudaMemcpyDefault, copy_stream);
       } else if (bB[k] > bA[k]) {
         // Everything that involves the band's rows [A, B) is final once the band is done: the row
         // strip rows [A,B) x cols [0,B) (all columns in rectangle mode) and, for the symmetric matrix,
