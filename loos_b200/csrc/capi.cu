@@ -375,8 +375,12 @@ int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric,
       cudaStreamWaitEvent(copy_stream, evs[k], 0);
       if (packed) {
         // rows of the band are contiguous in the packed buffer; only columns j < i exist
-        const size_t r_lo = (size_t)bd.r0 * TILE_FRAMES, nr = (size_t)(bd.r1 - bd.r0) * TILE_FRAMES;
-        const size_t width = std::min(FB, ((size_t)B.rows[bd.r1 - 1] + 1) * TILE_FRAMES);
+        const size_t r_lo = (size_t)bd.r0 * TILE_FRAMES;
+        size_t nr = (size_t)(bd.r1 - bd.r0) * TILE_FRAMES;
+        // canon: the packed rows of a rectangle over one set ARE the columns of its symmetric matrix; the
+        // caller's matrix has exactly FA of them (the packed buffers of the part calls are padded to tiles)
+        if (canon) nr = std::min(nr, FA - std::min(FA, (size_t)B.rows[bd.r0] * TILE_FRAMES));
+        const size_t width = self ? std::min(FB, ((size_t)B.rows[bd.r1 - 1] + 1) * TILE_FRAMES) : FB;
         cudaMemcpy2DAsync(out + r_lo * ld, ld * sizeof(float), d_out + r_lo * FB, FB * sizeof(float),
                           width * sizeof(float), nr, cudaMemcpyDefault, copy_stream);
       } else if (colmode) {
@@ -420,7 +424,9 @@ int run_pairs(loosb200_frames* a, loosb200_frames* b, bool self, bool symmetric,
     } else {
       for (uint32_t t : rows) {
         const uint64_t i0 = (uint64_t)t * TILE_FRAMES, i1 = std::min<uint64_t>(FA, i0 + TILE_FRAMES);
-        if (i1 > i0) cnt += (i1 - i0) * (uint64_t)FB;
+        if (i1 <= i0) continue;
+        if (canon) cnt += (i1 * (i1 - 1) - i0 * (i0 ? i0 - 1 : 0)) / 2;  // only j < i counts, see PairJob::canon
+        else cnt += (i1 - i0) * (uint64_t)FB;
       }
     }
     stats->count = cnt;

@@ -145,6 +145,11 @@ static int pairs_multi(loosb200_frames* const* a, loosb200_frames* const* b, int
   const size_t F = a[0]->F;
   // Shares of the tile rows: equal work, except when every device ships its part to HOST memory over its
   // own PCIe link -- then a share costs max(compute, copy) per pair, and the copy term differs by device.
+  // (Tried and dropped: every device computing the mirror-canonical RECTANGLE of its rows against all
+  // columns and shipping finished, contiguous column blocks of the symmetric matrix -- twice the
+  // arithmetic, no short runs in the copies.  What limits eight devices copying at once is the host
+  // side of the links, not the run length: 405 ms against 383 ms for the strips on 8 GPUs, 637 against
+  // 624 ms on 2, profiles/bench/r2_e2e_modes_{2,8}gpu.txt.)
   std::vector<double> weights;
   if (kind == OutKind::Copy && n > 1 && out && !(getenv("LOOSB200_EQUAL_SHARES") && atoi(getenv("LOOSB200_EQUAL_SHARES")))) {
     cudaPointerAttributes pa;
@@ -156,7 +161,7 @@ static int pairs_multi(loosb200_frames* const* a, loosb200_frames* const* b, int
       // s per pair on one B200: tensor engine 1.25e10 pairs/s at N = 1000, fp64 engine 9.5 TFLOP/s of 18 N flop
       const bool fp64 = engine == LOOSB200_ENGINE_FP64 || a[0]->N > TENSOR_MAX_ATOMS;
       const double compute = (fp64 ? 1.9e-9 : 8e-11) * (double)std::max<size_t>(a[0]->N, 256) / 1000.0;
-      const double bytes = self ? 8.0 : 4.0;                                           // entry + mirror image
+      const double bytes = self ? 8.0 : 4.0;  // entry + mirror image
       for (int d = 0; d < n; ++d) weights.push_back(1.0 / std::max(compute, bytes / (std::max(gbs[d], 0.1) * 1e9)));
     }
   }

@@ -147,7 +147,9 @@ k_pairs_fp64(const float* __restrict__ rawA, const double* __restrict__ cenA,
           continue;
         }
         double d;
-        if (canon && j > i) {
+        if (canon && j == i) {
+          d = 0.0;  // the diagonal of a rectangle over one set: exact zero, as in the triangle walk
+        } else if (canon && j > i) {
           // rectangle over one frame set: the entry above the diagonal is evaluated as its mirror image
           // (transposed covariance, swapped G), so that both are the same float (see PairJob::canon)
           const double* R = acc[a][b];
@@ -157,8 +159,10 @@ k_pairs_fp64(const float* __restrict__ rawA, const double* __restrict__ cenA,
           d = qcp_rmsd(acc[a][b], gdA[i], gdB[j], (double)N, 1.0);
         }
         const float v = (float)d;  // Tools/rmsds.cpp:363: double -> float on store
-        ssum += (double)v;
-        smax = fmax(smax, (double)v);
+        if (!canon || j < i) {  // canon: only the triangle counts (several devices' row ranges add up)
+          ssum += (double)v;
+          smax = fmax(smax, (double)v);
+        }
         if (out) {
           if (packed) {
             out[((size_t)rt * TF + la) * ld + j] = v;

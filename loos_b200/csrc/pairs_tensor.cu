@@ -568,6 +568,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       QcpPolyF polf[4];
       float e0s[4];
       int state[4];  // 0: no entry, 1: zero, 2: solve
+      bool in_stats[4] = {true, true, true, true};
 
       auto combine = [&](const uint32_t (&r)[18], int s, int c0, int count) {
 #pragma unroll
@@ -674,6 +675,13 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const bool pos = e0 > 0.0;
         e0 = pos ? e0 : 1.0;
         state[round] = !in_range ? 0 : (upper ? (j == i ? 1 : 0) : (pos ? 2 : 1));
+        if (KIND == KIND_CANON) {
+          // the rectangle covers the diagonal and both triangles of ONE set: exact zeros on the diagonal
+          // (Tools/rmsds.cpp:359-365 never computes it), and only j < i counts in the statistics, so that
+          // the row ranges of several devices add up to showStatsHalf's sum over the triangle
+          if (in_range && j == i) state[round] = 1;
+          in_stats[round] = j < i;
+        }
         e0s[round] = (float)(2.0 * e0 * inv_n);  // msd = y * this
         polf[round] = qcp_poly_split(qcp_poly(R, e0));
       };
@@ -765,10 +773,12 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           val = (float)a.unit * sqrtf(y * e0s[round]);
           // running sum of the float32 results as a float-float pair (error-free two-sum): the
           // reference accumulates in double (Tools/rmsds.cpp:425-439); no fp64 in this loop
-          const float s2 = sum_h + val, bb2 = s2 - sum_h;
-          sum_l += (sum_h - (s2 - bb2)) + (val - bb2);
-          sum_h = s2;
-          tmax = fmaxf(tmax, val);
+          if (KIND != KIND_CANON || in_stats[round]) {
+            const float s2 = sum_h + val, bb2 = s2 - sum_h;
+            sum_l += (sum_h - (s2 - bb2)) + (val - bb2);
+            sum_h = s2;
+            tmax = fmaxf(tmax, val);
+          }
         }
         if (owner) ctl->T[buf][b_local][a_local] = val;
       }

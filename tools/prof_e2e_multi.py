@@ -1,5 +1,6 @@
 """One process, G GPUs, C4 host-in / host-out (loosb200_stage_frames_multi + loosb200_rmsds_self_multi):
-shares of the matrix sized by each device's measured PCIe rate (default) against equal shares."""
+the two delivery modes of multi.cu (canonical rectangles shipped as column blocks / triangle shares shipped as
+strips), shares sized by each device's measured PCIe rate or equal."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, "/root/repo")
@@ -14,8 +15,9 @@ Xh = torch.empty((F, N, 3), dtype=torch.float32, pin_memory=True); Xh.copy_(X); 
 del X; torch.cuda.empty_cache()
 out = lb.PinnedMatrix((F, F))
 ref = None
-for mode in ("weighted", "equal", "weighted"):
-    os.environ["LOOSB200_EQUAL_SHARES"] = "1" if mode == "equal" else "0"
+for mode in ("strips", "strips, equal shares", "strips"):
+    os.environ["LOOSB200_MULTI_MODE"] = mode.split(",")[0]
+    os.environ["LOOSB200_EQUAL_SHARES"] = "1" if "equal" in mode else "0"
     ts = []
     for it in range(3):
         t0 = time.perf_counter()
@@ -30,5 +32,5 @@ for mode in ("weighted", "equal", "weighted"):
     samp = out.array[ii, jj].copy()
     same = True if ref is None else bool(np.array_equal(samp, ref))
     ref = samp if ref is None else ref
-    print("%d GPUs, %s shares: stage %.1f ms, call %.1f ms = %.1f GB/s of matrix to the host; sampled entries identical: %s" % (
+    print("%d GPUs, %s: stage %.1f ms, call %.1f ms = %.1f GB/s of matrix to the host; sampled entries identical: %s" % (
         G, mode, 1e3 * st, 1e3 * call, F * F * 4 / call / 1e9, same), flush=True)

@@ -4,8 +4,8 @@ N=${1:-8}
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/r2_pytest_multi_${N}gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r2_pytest_multi_${N}gpu.log
 LOOSB200_VERBOSE=1 timeout 600 python tools/prof_e2e_multi.py $N > gpurun_out/r2_e2e_shares_${N}gpu.txt 2>&1; cat gpurun_out/r2_e2e_shares_${N}gpu.txt
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-  bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/r2_bench_${N}gpu.json 2> gpurun_out/r2_bench_${N}gpu.err; echo "bench rc=$?"
+#timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+#  bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/r2_bench_${N}gpu.json 2> gpurun_out/r2_bench_${N}gpu.err; echo "bench rc=$?"
 tail -c 300 gpurun_out/r2_bench_${N}gpu.err
 python - <<PY
 import json
