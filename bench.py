@@ -443,9 +443,11 @@ def all_to_all(ctx, args, name, F, N, steps, warmup, want_e2e, want_cpu):
                    "d2h_gbs_over_call": F * F * 4 / (ms_call * 1e-3) / 1e9,
                    "delivered": "full symmetric F x F float32 matrix in ONE pinned host buffer" + ("" if sym_ok else " (SYMMETRY CHECK FAILED)"),
                    "to_rank0_hbm": hbm,
-                   "note": "host pinned coords -> loosb200_stage_frames_multi (each of the %d GPUs uploads its slice over its own PCIe link, "
-                           "slices exchanged over NVLink) -> loosb200_rmsds_self_multi: each GPU copies its row strips + mirror strips "
-                           "into the host matrix over its own PCIe link" % world}
+                   "note": ("host pinned coords -> loosb200_stage_frames_multi (each of the %d GPUs uploads its slice over its own PCIe link, "
+                            "slices exchanged over NVLink) -> loosb200_rmsds_self_multi: each GPU copies its row strips + mirror strips "
+                            "into the host matrix over its own PCIe link, shares sized by the links' measured rates" % world) if world > 1 else
+                           "host pinned coords -> loosb200_stage_frames_multi -> loosb200_rmsds_self_multi on one device: kernels fill an "
+                           "F x F bounce matrix in HBM, 64 bands ship their finished columns as contiguous blocks behind the kernels"}
             del X_host
             torch.cuda.empty_cache()
             capi.lib().loosb200_trim()
