@@ -257,6 +257,8 @@ struct AboutView {
   }
   ~AboutView() {
     if (!owns) return;
+    cudaStreamSynchronize(f.stream);  // an early error return must not hand buffers of running kernels back to the cache
+    cudaGetLastError();
     dev_release(f.maxabs); dev_release(f.q8); dev_release(f.q8b); dev_release(f.gq); dev_release(f.unit_log2_dev);
     f.raw = nullptr; f.centroid = nullptr;
   }

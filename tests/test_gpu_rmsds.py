@@ -275,7 +275,7 @@ def test_cta_pair_launch_shape_is_bit_identical(lb, F, N, monkeypatch):
     assert (np.diag(got["2"][0]) == 0).all() and np.array_equal(got["2"][0], got["2"][0].T)
 
 
-@pytest.mark.parametrize("F,N,name", [(20000, 3000, "config3"), (100000, 1000, "config4")])
+@pytest.mark.parametrize("F,N,name", [(20000, 3000, "config3"), (100000, 1000, "config4"), (24000, 5000, "config5 at 24,000 of its 200,000 frames")])
 def test_large_configs_sampled_parity_and_properties(lb, checker, F, N, name):
     """BASELINE's large shapes in full (C3: 20 000 x 3 000; C4: 100 000 x 1 000, a 40 GB matrix): frames
     are synthesised on the device, the matrix stays in HBM.  Checked: sampled pairs against the
