@@ -543,9 +543,9 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const double ga = i_ok ? __ldg(a.gA + i) : 0.0;
       // The eleven (ten) "b" frames of this warp's column group are solved in four rounds: the lanes of
       // a triple (al = 0, 1, 2) own frames base + al for base = 0, 3, 6, 9 (3, 3, 3, 2 frames; the last
-      // group has no frame 10).  Rounds 0 and 1 only need the group's columns 0..17, so they run while
-      // the loads of columns 18..32 are in flight: the latency-bound coefficient chains and the
-      // issue-bound combine fill each other's gaps.
+      // group has no frame 10).  Round 0 only needs the group's first columns, so it runs while the
+      // loads of columns 18..32 are in flight: its latency-bound coefficient chain and the issue-bound
+      // class sums fill each other's gaps.
       constexpr int RBASE[4] = {0, 3, 6, 9}, RCNT[4] = {3, 3, 3, 2};
       double gbq[4];  // G of the four "b" frames this lane solves against (prefetched)
 #pragma unroll
@@ -713,11 +713,14 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_wait_ld18(rb[(s5 + 1) & 1]);
         if (s5 + 1 < NUM_CLASSES) tc_ld16(tlane + (uint32_t)((s5 + 1) * CLASS_COLS + 18), reinterpret_cast<uint32_t(&)[16]>(rb[s5 & 1]));
         combine(rb[(s5 + 1) & 1], s5, 18, 15);
-        if (s5 == 1) do_round(1);
       }
       tc_fence_before();  // this warp's TMEM reads are complete
       if (release_at == 0) { __syncwarp(); if (lane == 0) release_tmem<CL>(ctl, crank); }
-      LB_TICK(1);  // drain (+ rounds 0, 1)
+      LB_TICK(1);  // drain (+ round 0)
+      // Rounds 1-3 run next to the next tile's MMAs.  (Round 1 used to sit inside the second half of the
+      // drain; since the class sums became integer work the epilogue has slack and the hand-over is the
+      // critical path: wait for TMEM 5.0 K -> 3.9 K cycles per tile, issue 16.9 K -> 17.4 K, C4 -1 %.)
+      do_round(1);
       do_round(2);
       do_round(3);
       if (KIND == KIND_RMSD || KIND == KIND_CANON) {
