@@ -26,4 +26,28 @@ with lb.FrameSet(X) as fs:
 with lb.FrameSet(X, sel=sel) as fa, lb.FrameSet(X) as fr:
     r = lb.rmsd2ref_iterative(fa, fr, tol=1e-6, maxiter=50)
     print("iterative", r["iters"], r["rmsd"][:3])
+# round 2: rmsds-align on both engines (KIND_ROT / KIND_TRACE, views about the align centroid, several bands),
+# mirror-canonical rectangles (banded text), strips instead of column blocks, the pair shape picked by size
+from loos_b200.api import rmsds_text
+sa, sr = np.arange(0, 120, dtype=np.uint32), np.arange(100, 333, dtype=np.uint32)
+os.environ["LOOSB200_ALIGN_BAND_TILES"] = "2"
+os.environ.pop("LOOSB200_CLUSTER", None)
+with lb.FrameSet(X, sel=sa) as a1, lb.FrameSet(X, sel=sr) as r1, lb.FrameSet(Y, sel=sa) as a2, lb.FrameSet(Y, sel=sr) as r2:
+    Mt = lb.rmsds_align(a1, r1, a2, r2, engine="tensor")
+    Md = lb.rmsds_align(a1, r1, a2, r2, engine="fp64")
+    M1 = lb.rmsds_align(a1, r1, engine="tensor")
+    print("rmsds_align engines", np.abs(Mt - Md).max(), M1.shape)
+with lb.FrameSet(X) as fs:
+    whole, _ = rmsds_text(fs, precision=6, engine="tensor")
+    os.environ["LOOSB200_TEXT_BAND_ROWS"] = "80"
+    banded, _ = rmsds_text(fs, precision=6, engine="tensor")
+    os.environ.pop("LOOSB200_TEXT_BAND_ROWS")
+    os.environ["LOOSB200_STRIPS"] = "1"
+    Ms, _ = lb.rmsds(fs, engine="tensor")
+    os.environ.pop("LOOSB200_STRIPS")
+    print("banded text identical", banded == whole, "strips == column blocks", np.array_equal(Ms, M))
+Z = synth_frames(90, 4200, seed=6)
+with lb.FrameSet(Z) as fs:
+    Mz, _ = lb.rmsds(fs, engine="tensor")
+    print("pair shape by size", Mz.shape, float(Mz.max()))
 print("sanitize smoke done")
