@@ -52,7 +52,8 @@ extern "C" {
 #define LOOSB200_LAYOUT_PLANES 1
 
 /* ---- which all-to-all kernel to use ---- */
-#define LOOSB200_ENGINE_AUTO   0  /* tensor-core path when the shape allows, else fp64 */
+#define LOOSB200_ENGINE_AUTO   0  /* tensor-core path when the shape allows (selections of up to 100,000 atoms,
+                                     finite coordinates), else fp64 */
 #define LOOSB200_ENGINE_TENSOR 1  /* tcgen05 int8 sliced (exact int32) contraction + fused QCP */
 #define LOOSB200_ENGINE_FP64   2  /* CUDA-core fp64 contraction + the same fused QCP */
 

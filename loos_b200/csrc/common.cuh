@@ -42,8 +42,12 @@ constexpr int COL_TILE_FRAMES = 32;
 constexpr int COL_TILE_ROWS = 3 * COL_TILE_FRAMES;  // 96
 constexpr int K_CHUNK = 128;   // atoms (bytes of int8) per pipeline stage = one 128-byte swizzle row
 constexpr int NUM_SLICES = 3;  // signed 8-bit digits of the 24-bit fixed-point coordinate
-// int32 accumulators hold up to 3 slice products of magnitude <= 2^14 per atom.
-constexpr size_t TENSOR_MAX_ATOMS = 43000;
+// int32 accumulators hold up to 3 slice products of magnitude <= 2^14 per atom: 43,000 atoms per accumulation
+// segment.  Larger selections are contracted in several segments whose class sums the epilogue adds up in
+// 64-bit integers (pairs_tensor.cu, SEG); the exact sum of squares of a frame (int64, k_quantise) bounds them
+// at 100,000 atoms: 8355711^2 x 100,000 = 6.98e18 < 2^63.
+constexpr size_t TENSOR_SEG_ATOMS = 43000;
+constexpr size_t TENSOR_MAX_ATOMS = 100000;
 // largest magnitude three balanced base-256 digits in [-128, 127] can hold on the positive side
 constexpr long long Q_MAX = 127LL * 65793LL;  // 8355711
 

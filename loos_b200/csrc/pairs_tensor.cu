@@ -262,6 +262,7 @@ struct TensorArgs {
   const uint32_t* row_tiles;   // row tile index -> I
   const double* gA; const double* gB;  // exact sum of squares of every quantised frame, as double
   uint32_t FA, FB, N, n_kchunks;
+  uint32_t seg_chunks;         // K chunks per accumulation segment (SEG kernels; n_kchunks otherwise)
   int self, symmetric, packed;
   int canon;                   // rectangle over ONE frame set: entries above the diagonal are evaluated as their mirror image
   double unit;                 // Angstrom per fixed-point unit
@@ -370,7 +371,12 @@ __device__ __forceinline__ void release_tmem(SmemCtl* ctl, uint32_t crank) {
 // Both passes walk the same tile geometry, so a pair meets the same lane -- and with it the same cyclic
 // relabelling of the rows of R and C, which the trace is invariant under when both carry it.
 constexpr int KIND_RMSD = 0, KIND_CANON = 1, KIND_ROT = 2, KIND_TRACE = 3;
-template <int CL, int KIND>
+// SEG: selections above 43,000 atoms.  An int32 accumulator holds three digit products of up to 2^14 per atom,
+// i.e. 43,000 atoms; beyond that the K loop is cut into segments of a.seg_chunks chunks: at the end of a
+// segment the epilogue drains the five classes into its 64-bit sums and hands TMEM back, the MMA thread
+// starts the next segment with overwriting MMAs, and only the last drain is followed by the solve.  Its own
+// instantiation: the common case keeps its instruction schedule.
+template <int CL, int KIND, bool SEG = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapB96, const __grid_constant__ CUtensorMap mapB48,
@@ -475,10 +481,24 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       while (walk.template next<false>(a, ctl, rt, I, J, masked)) {
         if (CL > 1 && crank != 0) continue;  // only the leader of a pair issues; the other keeps the ring moving
         // the epilogue (of both CTAs) has drained the previous tile
-        if (CL == 1) mbar_wait<32>(&ctl->tmem_empty, tphase ^ 1); else mbar_wait_cluster<32>(&ctl->tmem_empty, tphase ^ 1);
-        tc_fence_after();
-        LB_TICK(0);  // waiting for TMEM
+        if (!SEG) {
+          if (CL == 1) mbar_wait<32>(&ctl->tmem_empty, tphase ^ 1); else mbar_wait_cluster<32>(&ctl->tmem_empty, tphase ^ 1);
+          tc_fence_after();
+          LB_TICK(0);  // waiting for TMEM
+        }
+        uint32_t seg_left = 0;  // SEG: chunks left in the current accumulation segment
         for (uint32_t kc = 0; kc < a.n_kchunks; ++kc) {
+          bool seg_first = kc == 0;
+          if (SEG) {
+            seg_first = seg_left == 0;
+            if (seg_first) {  // the epilogue has drained the previous segment (or tile)
+              mbar_wait<32>(&ctl->tmem_empty, tphase ^ 1);
+              tc_fence_after();
+              LB_TICK(0);
+              seg_left = a.seg_chunks;
+            }
+            --seg_left;
+          }
           mbar_wait<0>(&ctl->full[stage], phase);
           tc_fence_after();
           LB_TICK(kc == 0 ? 3 : (kc == 1 ? 4 : 1));  // waiting for operands (first, second, later chunks of the tile)
@@ -486,7 +506,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const uint32_t sB = sA + A_STAGE_BYTES;
 #pragma unroll
           for (int ks = 0; ks < K_CHUNK / 32; ++ks) {
-            const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
+            const uint32_t first = (seg_first && ks == 0) ? 0u : 1u;
             const uint64_t A0 = make_desc(sA + 0 * A_SLICE_BYTES + ks * 32);
             const uint64_t A1 = make_desc(sA + 1 * A_SLICE_BYTES + ks * 32);
             const uint64_t A2 = make_desc(sA + 2 * A_SLICE_BYTES + ks * 32);
@@ -505,11 +525,14 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           // smem slot reusable once these MMAs have read it (in both CTAs of a pair)
           if (CL == 1) tc_commit(&ctl->empty[stage]); else tc_commit_pair(&ctl->empty[stage]);
-          if (kc + 1 == a.n_kchunks) { if (CL == 1) tc_commit(&ctl->tmem_full); else tc_commit_pair(&ctl->tmem_full); }
+          if (kc + 1 == a.n_kchunks || (SEG && seg_left == 0)) {
+            if (CL == 1) tc_commit(&ctl->tmem_full); else tc_commit_pair(&ctl->tmem_full);
+            if (SEG) tphase ^= 1;
+          }
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
           LB_TICK(2);  // issuing
         }
-        tphase ^= 1;
+        if (!SEG) tphase ^= 1;
       }
       if (a.prof)
         for (int k = 0; k < 8; ++k) a.prof[((size_t)blockIdx.x * NWARPS + warp) * 8 + k] = pacc[k];
@@ -553,11 +576,6 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t j = J * COL_TILE_FRAMES + g * GROUP_FRAMES + RBASE[round] + (RBASE[round] + al < nfr ? al : 0);
         gbq[round] = j < a.FB ? __ldg(a.gB + j) : 0.0;
       }
-      mbar_wait<32>(&ctl->tmem_full, tphase);
-      tphase ^= 1;
-      tc_fence_after();
-      LB_TICK(0);  // waiting for the accumulators
-
       // v[3 jb + axis'] = sum_s 2^(8s) D_s as a 64-bit integer (|v| < 2^58): one IMAD.WIDE per class and
       // element.  (The first version summed in fp64 through the exponent-bias trick: four instructions per
       // class and element -- constant high word, xor, two DADDs -- a third of all the epilogue issued.)
@@ -698,6 +716,33 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_ld16(col, reinterpret_cast<uint32_t(&)[16]>(r));
         tc_ld2(col + 16, r[16], r[17]);
       };
+      if (SEG) {
+        // all accumulation segments but the last: drain into the 64-bit sums, hand TMEM back, nothing else
+        const uint32_t nseg = (a.n_kchunks + a.seg_chunks - 1) / a.seg_chunks;
+        for (uint32_t sg = 0; sg + 1 < nseg; ++sg) {
+          mbar_wait<32>(&ctl->tmem_full, tphase);
+          tphase ^= 1;
+          tc_fence_after();
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int s5 = 0; s5 < NUM_CLASSES; ++s5) {
+              uint32_t r[18];
+              r[16] = 0u; r[17] = 0u;
+              if (half == 0) load_a(tlane + (uint32_t)(s5 * CLASS_COLS), r);
+              else tc_ld16(tlane + (uint32_t)(s5 * CLASS_COLS + 18), reinterpret_cast<uint32_t(&)[16]>(r));
+              tc_wait_ld18(r);
+              combine(r, s5, half ? 18 : 0, half ? 15 : 18);
+            }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) release_tmem<CL>(ctl, crank);
+        }
+      }
+      mbar_wait<32>(&ctl->tmem_full, tphase);
+      tphase ^= 1;
+      tc_fence_after();
+      LB_TICK(0);  // waiting for the accumulators
       load_a(tlane, rb[0]);
 #pragma unroll
       for (int s5 = 0; s5 < NUM_CLASSES; ++s5) {
@@ -874,7 +919,7 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   // (profiles/r2_phase_counters.txt), hence the default by selection size.
   const uint32_t CLs = job.kind != PairJob::Rmsd ? 1u
                        : cl_env ? (atoi(cl_env) == 2 ? 2u : 1u)
-                       : (job.a->N >= 4096 && !job.canon ? 2u : 1u);
+                       : (job.a->N >= 4096 && job.a->N <= TENSOR_SEG_ATOMS && !job.canon ? 2u : 1u);
   const loosb200_frames* A = job.a;
   const loosb200_frames* B = job.b;
   if (!A->quantised || !B->quantised || A->unit_log2 != B->unit_log2 || A->Kpad != B->Kpad)
@@ -924,6 +969,8 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   ta.gA = A->gq; ta.gB = B->gq;
   ta.FA = (uint32_t)A->F; ta.FB = FB; ta.N = (uint32_t)A->N;
   ta.n_kchunks = (uint32_t)(A->Kpad / K_CHUNK);
+  const bool seg = A->N > TENSOR_SEG_ATOMS;
+  ta.seg_chunks = seg ? (uint32_t)(TENSOR_SEG_ATOMS / K_CHUNK) : ta.n_kchunks;  // 335 chunks = 42,880 atoms
   ta.self = job.self; ta.symmetric = job.symmetric; ta.packed = job.packed_rows;
   ta.canon = (job.canon && !job.self) ? 1 : 0;
   ta.unit = exp2((double)A->unit_log2);
@@ -953,7 +1000,9 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   if (job.ev_k0) cudaEventRecord(job.ev_k0, st);
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TensorArgs);
   Kern kern;
-  if (job.kind == PairJob::Rotation) kern = k_pairs_tensor<1, KIND_ROT>;
+  if (seg && job.kind != PairJob::Rmsd) return LOOSB200_ERR_UNSUPPORTED;
+  if (seg) kern = ta.canon ? k_pairs_tensor<1, KIND_CANON, true> : k_pairs_tensor<1, KIND_RMSD, true>;
+  else if (job.kind == PairJob::Rotation) kern = k_pairs_tensor<1, KIND_ROT>;
   else if (job.kind == PairJob::Trace) kern = k_pairs_tensor<1, KIND_TRACE>;
   else if (CLs == 2) kern = k_pairs_tensor<2, KIND_RMSD>;
   else if (ta.canon) kern = k_pairs_tensor<1, KIND_CANON>;

@@ -335,8 +335,10 @@ def test_atom_limit_of_the_tensor_engine(lb, checker):
     """N = 43 000 is the largest selection whose class sums provably fit int32 (3 digit products of
     at most 2^14 per atom).  Worst case for the accumulators: every centred coordinate at +-max, so all
     three digits of every operand are extreme.  The tensor engine must still be exact (compared with
-    the fp64 engine and the oracle), N = 43 001 must be refused by it and taken by the fp64 engine
-    under engine="auto"."""
+    the fp64 engine and the oracle).  From 43 001 atoms on the contraction runs in several accumulation
+    segments (pairs_tensor.cu, SEG) -- the same worst case with one atom more must agree just as well --
+    up to 100 000 atoms; 100 001 is refused by the tensor engine and taken by the fp64 engine under
+    engine="auto"."""
     from loos_b200 import capi
     rng = np.random.default_rng(43)
     F, N = 44, 43000
@@ -349,7 +351,7 @@ def test_atom_limit_of_the_tensor_engine(lb, checker):
         Mt, st = lb.rmsds(fs, engine="tensor")
         Mf, sf = lb.rmsds(fs, engine="fp64")
     # identical frames: exactly 0 while the integer sums stay below 2^53 (any realistic input); here
-    # they reach 2^63 and the fp64 combine rounds at 1e-16 relative: a few 1e-5 A at most
+    # they reach 2^63 and the conversion to fp64 rounds at 1e-16 relative: a few 1e-5 A at most
     # (the fp64 engine, like the reference, carries the cancellation noise of Ga + Gb - 2 lambda:
     # sqrt(1e-16 * 1.3e9 A^2 * few / N) ~ 2e-4 A for this pair)
     assert Mt[3, 2] < 5e-5 and Mf[3, 2] < 5e-4
@@ -361,14 +363,61 @@ def test_atom_limit_of_the_tensor_engine(lb, checker):
     for i, j in [(1, 0), (5, 4), (5, 0)]:
         assert abs(float(Mt[i, j]) - checker.centered_rmsd(cen[i], cen[j])) < 1e-4
     assert checker.centered_rmsd(cen[3], cen[2]) < 5e-4      # the reference's own noise floor here
-    X1 = np.concatenate([X[:9], X[:9, :1]], axis=1)         # 43 001 atoms
+    # 43 002 atoms (two more, +L and -L: the centroid stays 0): two segments, 42 880 + 122 atoms
+    extra = np.zeros((9, 2, 3), np.float32)
+    extra[:, 0, :] = 99.99
+    extra[:, 1, :] = -99.99
+    X1 = np.concatenate([X[:9], extra], axis=1)
     with lb.FrameSet(X1) as fs:
+        Ms, _ = lb.rmsds(fs, engine="tensor")
+        Mf1, _ = lb.rmsds(fs, engine="fp64")
+        Ma, _ = lb.rmsds(fs, engine="auto")
+    D1 = np.abs(Ms - Mf1)
+    D1[3, 2] = D1[2, 3] = 0.0
+    assert D1.max() <= 2 * np.spacing(np.float32(Mf1.max())) and Ms[3, 2] < 5e-5
+    assert np.array_equal(Ma, Ms)
+    X2 = np.zeros((6, 100001, 3), np.float32)
+    X2[:] = rng.normal(scale=30.0, size=(6, 100001, 3))
+    with lb.FrameSet(X2) as fs:
         with pytest.raises(lb.LoosB200Error) as e:
             lb.rmsds(fs, engine="tensor")
         assert e.value.code == capi.ERR_UNSUPPORTED
         Ma, _ = lb.rmsds(fs, engine="auto")
-        Mf1, _ = lb.rmsds(fs, engine="fp64")
-    assert np.array_equal(Ma, Mf1)
+        Mf2, _ = lb.rmsds(fs, engine="fp64")
+    assert np.array_equal(Ma, Mf2)
+
+
+@pytest.mark.parametrize("N", [50000, 86000, 100000])
+def test_selections_above_43000_atoms_in_segments(lb, checker, N):
+    """Tensor engine beyond one int32 accumulation segment: 2 or 3 segments (42 880 atoms each), the last one
+    short or full; against the fp64 engine on the whole matrix, the oracle on a few pairs, the banded
+    (mirror-canonical) text against the whole-matrix text, and with frames that exist twice."""
+    from loos_b200.api import rmsds_text
+    from loos_b200.synth import synth_frames
+    F = 83
+    X = synth_frames(F, N, seed=N)
+    X[70:75] = X[10:15]
+    with lb.FrameSet(X) as fs:
+        Mt, st = lb.rmsds(fs, engine="tensor")
+        Mf, sf = lb.rmsds(fs, engine="fp64")
+        whole, _ = rmsds_text(fs, precision=7, engine="tensor")
+    assert np.abs(Mt.astype(np.float64) - Mf.astype(np.float64)).max() < 2e-5
+    assert np.array_equal(Mt, Mt.T) and np.all(np.diag(Mt) == 0)
+    # frames that exist twice: 0 up to the one rounding of the integer sums (> 2^53 at this size) to fp64
+    assert Mt[72, 12] < 5e-5 and Mt[70, 10] < 5e-5
+    assert st["count"] == F * (F - 1) // 2 and abs(st["sum"] - sf["sum"]) < 1e-3
+    Xd = X[:4].astype(np.float64)
+    cen = [checker.center_at_origin(x)[0] for x in Xd]
+    for i, j in [(1, 0), (3, 2), (3, 0)]:
+        assert abs(float(Mt[i, j]) - checker.centered_rmsd(cen[i], cen[j])) < 2e-5
+    import os
+    os.environ["LOOSB200_TEXT_BAND_ROWS"] = "40"
+    try:
+        with lb.FrameSet(X) as fs:
+            banded, _ = rmsds_text(fs, precision=7, engine="tensor")
+    finally:
+        del os.environ["LOOSB200_TEXT_BAND_ROWS"]
+    assert banded == whole
 
 
 @pytest.mark.parametrize("precision", [0, 2, 6, 9])

@@ -1,4 +1,4 @@
-"""The fp64 engine (k_pairs_fp64: selections above the tensor path's 43,000-atom bound, and the on-device
+"""The fp64 engine (k_pairs_fp64: selections above the tensor path's 100,000-atom bound, and the on-device
 cross-check) at F x N: kernel ms, pairs/s, fp64 TFLOP/s."""
 import json
 import os
