@@ -252,7 +252,7 @@ int loosb200_rmsds_align(loosb200_frames* align1, loosb200_frames* rmsd1, loosb2
  * LOOSB200_ENGINE_TENSOR: both contractions on the int8 tensor path (exact integer sums of coordinates
  * on a 24-bit fixed-point grid; the rmsd selection is put on its grid about the ALIGN centroid), the
  * rotation from the quartic's root as in the fp64 engine; results within ~1e-6 A, an order of magnitude
- * faster; selections of up to 43,000 atoms.  LOOSB200_ENGINE_AUTO: tensor when it applies. */
+ * faster; selections of up to 100,000 atoms.  LOOSB200_ENGINE_AUTO: tensor when it applies. */
 int loosb200_rmsds_align_engine(loosb200_frames* align1, loosb200_frames* rmsd1, loosb200_frames* align2,
                                 loosb200_frames* rmsd2, double* out, size_t ld, int engine);
 

@@ -382,7 +382,7 @@ extern "C" int loosb200_rmsds_align_engine(loosb200_frames* align1, loosb200_fra
       if (e != cudaSuccess) return cuda_fail(e, "rmsds_align: staging", __FILE__, __LINE__);
     }
   if (engine != LOOSB200_ENGINE_FP64) {
-    const bool can = tensor_path_available() && align1->N <= TENSOR_SEG_ATOMS && rmsd1->N <= TENSOR_SEG_ATOMS;
+    const bool can = tensor_path_available() && align1->N <= TENSOR_MAX_ATOMS && rmsd1->N <= TENSOR_MAX_ATOMS;
     if (!can && engine == LOOSB200_ENGINE_TENSOR) return LOOSB200_ERR_UNSUPPORTED;
     if (can) {
       const int rc = rmsds_align_tensor(align1, rmsd1, align2, rmsd2, out, ld);

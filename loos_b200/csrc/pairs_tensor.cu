@@ -1000,8 +1000,10 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   if (job.ev_k0) cudaEventRecord(job.ev_k0, st);
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TensorArgs);
   Kern kern;
-  if (seg && job.kind != PairJob::Rmsd) return LOOSB200_ERR_UNSUPPORTED;
-  if (seg) kern = ta.canon ? k_pairs_tensor<1, KIND_CANON, true> : k_pairs_tensor<1, KIND_RMSD, true>;
+  if (seg) kern = job.kind == PairJob::Rotation ? k_pairs_tensor<1, KIND_ROT, true>
+                  : job.kind == PairJob::Trace  ? k_pairs_tensor<1, KIND_TRACE, true>
+                  : ta.canon                    ? k_pairs_tensor<1, KIND_CANON, true>
+                                                : k_pairs_tensor<1, KIND_RMSD, true>;
   else if (job.kind == PairJob::Rotation) kern = k_pairs_tensor<1, KIND_ROT>;
   else if (job.kind == PairJob::Trace) kern = k_pairs_tensor<1, KIND_TRACE>;
   else if (CLs == 2) kern = k_pairs_tensor<2, KIND_RMSD>;

@@ -90,7 +90,7 @@ int main(int argc, char* argv[]) {
   o.add("range2", 0, "", "Range of frames to use from the second trajectory [FORMAT - skip:stride:stop, stop is optional] (default = range1)");
   o.add("gpu", 0, "0", "CUDA device to use (extension; the script has no such option)");
   o.add("engine", 0, "auto", "auto|tensor|fp64: tensor = int8 tensor cores on a 24-bit fixed-point grid (values within ~1e-6 A of the script's), "
-                             "fp64 = double-precision contractions (within 1e-8 A); auto = tensor for selections of up to 43,000 atoms (extension)");
+                             "fp64 = double-precision contractions (within 1e-8 A); auto = tensor for selections of up to 100,000 atoms (extension)");
   o.addPositional("model", 1); o.addPositional("traj", 1);
   try {
     if (!o.parse(argc, argv)) return 2;  // argparse exits with status 2 on a usage error

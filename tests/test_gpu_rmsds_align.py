@@ -28,7 +28,8 @@ def _sets(F, natoms, seed):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("F1,F2,Na,Nr", [(45, 53, 60, 90), (1, 1, 3, 1), (40, 80, 17, 200), (83, 7, 500, 33), (130, 97, 257, 1025)])
+@pytest.mark.parametrize("F1,F2,Na,Nr", [(45, 53, 60, 90), (1, 1, 3, 1), (40, 80, 17, 200), (83, 7, 500, 33), (130, 97, 257, 1025),
+                                         (9, 7, 45000, 50000)])   # both selections beyond one accumulation segment
 def test_two_trajectories_vs_oracle(lb, checker, F1, F2, Na, Nr, engine):
     from oracle import oracle
     X = _sets(F1, Na + Nr, seed=77 + F1 + Na)
