@@ -139,26 +139,41 @@ k_quantise(const float* __restrict__ raw, const double* __restrict__ centroid, s
   const size_t row0 = (f / FRAMES_PER_BLOCK) * ROWS_PER_BLOCK + (f % FRAMES_PER_BLOCK) * 3;
   const size_t plane = rows_total * Kpad, plane_b = rows_total_b * Kpad;
   long long g = 0;
+  // four atoms per thread and trip: one 16-byte load, six 4-byte stores (digit planes are Kpad-pitched,
+  // Kpad a multiple of 128; rows of `raw` are Npad-pitched, Npad a multiple of 4).  Byte-wise stores made
+  // this kernel 1.5 ms at C4 (3 GB of traffic).
+  const int n4 = (int)((N + 3) / 4);
   for (int axis = 0; axis < 3; ++axis) {
-    const float* p = raw + (f * 3 + axis) * Npad;
+    const float4* p = reinterpret_cast<const float4*>(raw + (f * 3 + axis) * Npad);
     const double c = centroid[f * 3 + axis];
-    int8_t* d0 = q8 + (row0 + axis) * Kpad;
-    int8_t* b0 = q8b + (f * 3 + axis) * Kpad;
-    for (int i = threadIdx.x; i < (int)N; i += blockDim.x) {
-      const long long q = __double2ll_rn(((double)p[i] - c) * inv_unit);
-      g += q * q;
-      // balanced base-256 digits: q = x0 + 256 x1 + 65536 x2, each in [-128, 127]
-      const int x0 = (int)(int8_t)(q & 0xff);
-      const long long q1 = (q - x0) >> 8;
-      const int x1 = (int)(int8_t)(q1 & 0xff);
-      long long x2 = (q1 - x1) >> 8;
-      x2 = x2 > 127 ? 127 : (x2 < -128 ? -128 : x2);  // unreachable below k_unit's limit; never wrap
-      d0[i] = (int8_t)x0;
-      d0[plane + i] = (int8_t)x1;
-      d0[2 * plane + i] = (int8_t)x2;
-      b0[i] = (int8_t)x0;
-      b0[plane_b + i] = (int8_t)x1;
-      b0[2 * plane_b + i] = (int8_t)x2;
+    uint32_t* d0 = reinterpret_cast<uint32_t*>(q8 + (row0 + axis) * Kpad);
+    uint32_t* b0 = reinterpret_cast<uint32_t*>(q8b + (f * 3 + axis) * Kpad);
+    for (int i4 = threadIdx.x; i4 < n4; i4 += blockDim.x) {
+      const float4 v4 = p[i4];
+      const float vs[4] = {v4.x, v4.y, v4.z, v4.w};
+      uint32_t w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if ((size_t)(4 * i4 + k) < N) {  // pad atoms keep zero digits and do not count in G
+          const long long q = __double2ll_rn(((double)vs[k] - c) * inv_unit);
+          g += q * q;
+          // balanced base-256 digits: q = x0 + 256 x1 + 65536 x2, each in [-128, 127]
+          const int x0 = (int)(int8_t)(q & 0xff);
+          const long long q1 = (q - x0) >> 8;
+          const int x1 = (int)(int8_t)(q1 & 0xff);
+          long long x2 = (q1 - x1) >> 8;
+          x2 = x2 > 127 ? 127 : (x2 < -128 ? -128 : x2);  // unreachable below k_unit's limit; never wrap
+          w0 |= (uint32_t)(uint8_t)x0 << (8 * k);
+          w1 |= (uint32_t)(uint8_t)x1 << (8 * k);
+          w2 |= (uint32_t)(uint8_t)(int)x2 << (8 * k);
+        }
+      }
+      d0[i4] = w0;
+      d0[plane / 4 + i4] = w1;
+      d0[2 * (plane / 4) + i4] = w2;
+      b0[i4] = w0;
+      b0[plane_b / 4 + i4] = w1;
+      b0[2 * (plane_b / 4) + i4] = w2;
     }
   }
   // exact integer block sum
