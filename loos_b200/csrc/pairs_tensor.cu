@@ -63,6 +63,12 @@ template <> struct Shape<2> {
   static constexpr int B_STAGE_BYTES = B_SLICE_BYTES + B_SLICE_BYTES / 2;  // 18432: one digit + half of digit 0
 };
 template <int CL> __host__ __device__ constexpr int stage_bytes() { return A_STAGE_BYTES + Shape<CL>::B_STAGE_BYTES; }
+// Solve rounds inside the drain, i.e. before TMEM is handed back (fp64 runs at full rate there, but the MMAs
+// wait); the others run next to the next tile's MMAs at a fraction of that rate.  C4, same box, with the
+// warp-uniform MMA issue: 1 round 405 ms, 2 rounds 368 ms, 3 rounds 372 ms, all four (RELEASE_AT=1) 376 ms.
+#ifndef LB_INDRAIN
+#define LB_INDRAIN 2
+#endif
 constexpr int NUM_CLASSES = 5;
 constexpr int GROUP_FRAMES = 11;  // "b" frames per epilogue column group (33 columns); the third group has 10
 constexpr int CLASS_COLS = COL_TILE_ROWS;  // 96
@@ -182,6 +188,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
+}
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -470,7 +482,13 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // The WHOLE warp walks the tiles, waits on the barriers and forms the descriptors, so that all of
+    // that is warp-uniform and lives in uniform registers; one elected lane issues.  (With the loop
+    // inside `if (lane == 0)` every tcgen05.mma cost an ELECT and five R2UR.BROADCAST -- operands of
+    // UTCIMMA are uniform registers -- about 16 instructions or ~83 cycles per MMA on this one thread,
+    // more than the 72 cycles the average MMA of this kernel executes in: the issue thread, not the
+    // tensor pipe, the shared-memory feed or the TMA ring, was what bound the MMA phase.)
+    {
       constexpr uint32_t ID192 = make_idesc(2 * CLASS_COLS, 128 * CL), ID96 = make_idesc(CLASS_COLS, 128 * CL);
       uint32_t stage = 0, phase = 0, tphase = 0;
       long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -478,7 +496,7 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       TileWalk<CL> walk(crank);
       uint32_t rt, I, J;
       bool masked;
-      while (walk.template next<false>(a, ctl, rt, I, J, masked)) {
+      while (walk.template next<true>(a, ctl, rt, I, J, masked)) {
         if (CL > 1 && crank != 0) continue;  // only the leader of a pair issues; the other keeps the ring moving
         // the epilogue (of both CTAs) has drained the previous tile
         if (!SEG) {
@@ -515,26 +533,30 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // other half of N at the same offsets of the partner's shared memory.
             const uint64_t B0 = make_desc(sB + (CL == 1 ? 0 : B_SLICE_BYTES) + ks * 32);
             const uint64_t B1 = make_desc(sB + (CL == 1 ? B_SLICE_BYTES : 0) + ks * 32);
-            // class s lives at columns [96 s, 96 s + 96); first touch of a class overwrites
-            tc_mma_i8<CL>(tmem_base + 3 * CLASS_COLS, A2, B1, ID192, first);  // a2.b1 -> s3, a2.b2 -> s4
-            tc_mma_i8<CL>(tmem_base + 1 * CLASS_COLS, A0, B1, ID192, first);  // a0.b1 -> s1, a0.b2 -> s2
-            tc_mma_i8<CL>(tmem_base + 0 * CLASS_COLS, A0, B0, ID96, first);   // a0.b0 -> s0
-            tc_mma_i8<CL>(tmem_base + 2 * CLASS_COLS, A1, B1, ID192, 1u);     // a1.b1 -> s2, a1.b2 -> s3
-            tc_mma_i8<CL>(tmem_base + 2 * CLASS_COLS, A2, B0, ID96, 1u);      // a2.b0 -> s2
-            tc_mma_i8<CL>(tmem_base + 1 * CLASS_COLS, A1, B0, ID96, 1u);      // a1.b0 -> s1
+            if (elect_one()) {
+              // class s lives at columns [96 s, 96 s + 96); first touch of a class overwrites
+              tc_mma_i8<CL>(tmem_base + 3 * CLASS_COLS, A2, B1, ID192, first);  // a2.b1 -> s3, a2.b2 -> s4
+              tc_mma_i8<CL>(tmem_base + 1 * CLASS_COLS, A0, B1, ID192, first);  // a0.b1 -> s1, a0.b2 -> s2
+              tc_mma_i8<CL>(tmem_base + 0 * CLASS_COLS, A0, B0, ID96, first);   // a0.b0 -> s0
+              tc_mma_i8<CL>(tmem_base + 2 * CLASS_COLS, A1, B1, ID192, 1u);     // a1.b1 -> s2, a1.b2 -> s3
+              tc_mma_i8<CL>(tmem_base + 2 * CLASS_COLS, A2, B0, ID96, 1u);      // a2.b0 -> s2
+              tc_mma_i8<CL>(tmem_base + 1 * CLASS_COLS, A1, B0, ID96, 1u);      // a1.b0 -> s1
+            }
           }
-          // smem slot reusable once these MMAs have read it (in both CTAs of a pair)
-          if (CL == 1) tc_commit(&ctl->empty[stage]); else tc_commit_pair(&ctl->empty[stage]);
-          if (kc + 1 == a.n_kchunks || (SEG && seg_left == 0)) {
-            if (CL == 1) tc_commit(&ctl->tmem_full); else tc_commit_pair(&ctl->tmem_full);
-            if (SEG) tphase ^= 1;
+          const bool seg_last = kc + 1 == a.n_kchunks || (SEG && seg_left == 0);
+          if (elect_one()) {
+            // smem slot reusable once these MMAs have read it (in both CTAs of a pair)
+            if (CL == 1) tc_commit(&ctl->empty[stage]); else tc_commit_pair(&ctl->empty[stage]);
+            if (seg_last) { if (CL == 1) tc_commit(&ctl->tmem_full); else tc_commit_pair(&ctl->tmem_full); }
           }
+          __syncwarp();
+          if (SEG && seg_last) tphase ^= 1;
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
           LB_TICK(2);  // issuing
         }
         if (!SEG) tphase ^= 1;
       }
-      if (a.prof)
+      if (a.prof && lane == 0)
         for (int k = 0; k < 8; ++k) a.prof[((size_t)blockIdx.x * NWARPS + warp) * 8 + k] = pacc[k];
     }
   }
@@ -566,9 +588,9 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const double ga = i_ok ? __ldg(a.gA + i) : 0.0;
       // The eleven (ten) "b" frames of this warp's column group are solved in four rounds: the lanes of
       // a triple (al = 0, 1, 2) own frames base + al for base = 0, 3, 6, 9 (3, 3, 3, 2 frames; the last
-      // group has no frame 10).  Round 0 only needs the group's first columns, so it runs while the
-      // loads of columns 18..32 are in flight: its latency-bound coefficient chain and the issue-bound
-      // class sums fill each other's gaps.
+      // group has no frame 10).  Rounds 0 and 1 only need the group's columns 0..17, so they run while
+      // the loads of columns 18..32 are in flight: the latency-bound coefficient chains and the
+      // issue-bound class sums fill each other's gaps.
       constexpr int RBASE[4] = {0, 3, 6, 9}, RCNT[4] = {3, 3, 3, 2};
       double gbq[4];  // G of the four "b" frames this lane solves against (prefetched)
 #pragma unroll
@@ -758,15 +780,22 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_wait_ld18(rb[(s5 + 1) & 1]);
         if (s5 + 1 < NUM_CLASSES) tc_ld16(tlane + (uint32_t)((s5 + 1) * CLASS_COLS + 18), reinterpret_cast<uint32_t(&)[16]>(rb[s5 & 1]));
         combine(rb[(s5 + 1) & 1], s5, 18, 15);
+#if LB_INDRAIN >= 2
+        if (s5 == 1) do_round(1);
+#endif
       }
+#if LB_INDRAIN >= 3
+      do_round(2);
+#endif
       tc_fence_before();  // this warp's TMEM reads are complete
       if (release_at == 0) { __syncwarp(); if (lane == 0) release_tmem<CL>(ctl, crank); }
-      LB_TICK(1);  // drain (+ round 0)
-      // Rounds 1-3 run next to the next tile's MMAs.  (Round 1 used to sit inside the second half of the
-      // drain; since the class sums became integer work the epilogue has slack and the hand-over is the
-      // critical path: wait for TMEM 5.0 K -> 3.9 K cycles per tile, issue 16.9 K -> 17.4 K, C4 -1 %.)
+      LB_TICK(1);  // drain (+ the rounds inside it)
+#if LB_INDRAIN < 2
       do_round(1);
+#endif
+#if LB_INDRAIN < 3
       do_round(2);
+#endif
       do_round(3);
       if (KIND == KIND_RMSD || KIND == KIND_CANON) {
       // pin every fp64-derived value on this side of the hand-over: without this the compiler
