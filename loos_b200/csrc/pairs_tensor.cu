@@ -940,15 +940,16 @@ int launch_pairs_tensor(const PairJob& job, cudaStream_t st, int* launches) {
   if (const char* e = getenv("LOOSB200_SB_R")) SB_R = (uint32_t)std::max(1, atoi(e));
   if (const char* e = getenv("LOOSB200_SB_C")) SB_C = (uint32_t)std::max(1, atoi(e));
   const char* cl_env = getenv("LOOSB200_CLUSTER");
-  // 1: independent CTAs.  2: CTA pairs (tcgen05 cta_group::2) sharing the "b" operand -- a quarter less
-  // shared-memory traffic per MAC and 21 % fewer operand bytes out of L2, but an fp64 instruction on
-  // either SM stalls the pair's MMAs, so the accumulators are held through the whole fp64 part and the
-  // leader waits for the slower of two epilogues before every tile.  That fixed cost per tile loses at
-  // N = 1000 (+2.5 %), is even at N = 2000-3000 and wins 1-3 % from N = 5000 up
-  // (profiles/r2_phase_counters.txt), hence the default by selection size.
-  const uint32_t CLs = job.kind != PairJob::Rmsd ? 1u
-                       : cl_env ? (atoi(cl_env) == 2 ? 2u : 1u)
-                       : (job.a->N >= 4096 && job.a->N <= TENSOR_SEG_ATOMS && !job.canon ? 2u : 1u);
+  // 2 (default): CTA pairs (tcgen05 cta_group::2) sharing the "b" operand -- a quarter less shared-memory
+  // traffic per MAC, which is what bounds the MMA phase of independent CTAs (572 against 432 cycles per
+  // K step), and 21 % fewer operand bytes out of L2.  An fp64 instruction on either SM stalls the pair's
+  // MMAs, so the accumulators are held through the whole fp64 part (release_at = 1) and the leader waits
+  // for the slower of two epilogues before every tile.  1: independent CTAs.  Same box, after the MMA issue
+  // became warp-uniform: C4 376 -> 362 ms, 20,000 x 3,000 38.6 -> 36.0 ms, 20,000 x 5,000 62 -> 56.8 ms
+  // (profiles/r2_phase_counters.txt; before that change the issue thread hid the difference).
+  // Mirror-canonical rectangles, rmsds-align passes and segmented selections run as independent CTAs.
+  const uint32_t CLs = (job.kind != PairJob::Rmsd || job.canon || job.a->N > TENSOR_SEG_ATOMS) ? 1u
+                       : cl_env ? (atoi(cl_env) == 1 ? 1u : 2u) : 2u;
   const loosb200_frames* A = job.a;
   const loosb200_frames* B = job.b;
   if (!A->quantised || !B->quantised || A->unit_log2 != B->unit_log2 || A->Kpad != B->Kpad)

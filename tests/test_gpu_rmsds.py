@@ -70,13 +70,15 @@ def test_vs_oracle_shapes(lb, checker, engine, F, N):
     assert np.array_equal(M, M.T) and np.all(np.diag(M) == 0)
 
 
-def test_default_launch_shape_by_selection_size(lb, monkeypatch):
-    """From 4096 atoms up the tensor engine launches CTA pairs by default (pairs_tensor.cu): same bits as
-    the independent-CTA shape asked for explicitly, for the matrix, the cross matrix and the banded text."""
+@pytest.mark.parametrize("N", [300, 4100])
+def test_default_launch_shape(lb, monkeypatch, N):
+    """The tensor engine launches CTA pairs by default (pairs_tensor.cu): same bits as the independent-CTA
+    shape asked for explicitly, for the matrix, the cross matrix and the banded text (whose mirror-canonical
+    rectangles always run as independent CTAs)."""
     from loos_b200.api import rmsds_text
     from loos_b200.synth import synth_frames
-    X = synth_frames(97, 4100, seed=77)
-    Y = synth_frames(45, 4100, seed=78)
+    X = synth_frames(97, N, seed=77)
+    Y = synth_frames(45, N, seed=78)
     got = []
     for shape in (None, "1"):
         if shape:
