@@ -240,8 +240,8 @@ def parity_sample(X_dev, M_get, F, N, owned=None, nrand=3000, nnear=1000):
             "tolerance": 1e-4, "checker": kind}
 
 
-NCU_TRAFFIC = {("c4", 1, "tensor"): 27.538194e9 + 40.013212e9}
-NCU_TRAFFIC_SOURCE = ("profiles/r2_k_pairs_tensor_C4_full_metrics.csv, ncu --set full of one launch (result matrix 40.0 GB written once, "
+NCU_TRAFFIC = {("c4", 1, "tensor"): 27.789879e9 + 40.010743e9}
+NCU_TRAFFIC_SOURCE = ("profiles/r2_k_pairs_tensor_C4_final_full_metrics.csv, ncu --set full of one launch (result matrix 40.0 GB written once, "
                       "operands 0.9 GB read 30x: one pass over the columns per 48-row-tile group; 145 GB in round 1)")
 
 
