@@ -334,15 +334,19 @@ struct TileWalk {
     return true;
   }
   // Leader producer thread: hand `slot` (or SLOT_END) to every consumer of the cluster.
+  // Called by ALL lanes of the producer warp (the walk's state stays warp-uniform); lane 0 publishes.
   __device__ __forceinline__ void publish(SmemCtl* ctl, uint32_t slot) {
     mbar_wait_cluster<32>(&ctl->sched_empty[ridx], rphase ^ 1);
-    ctl->sched_slot[ridx] = slot;
-    mbar_arrive(&ctl->sched_full[ridx]);
+    if ((threadIdx.x & 31) == 0) {
+      ctl->sched_slot[ridx] = slot;
+      mbar_arrive(&ctl->sched_full[ridx]);
 #pragma unroll
-    for (uint32_t r = 1; r < (uint32_t)CL; ++r) {
-      st_remote_u32(map_to_cta(&ctl->sched_slot[ridx], r), slot);
-      mbar_arrive_remote(map_to_cta(&ctl->sched_full[ridx], r));
+      for (uint32_t r = 1; r < (uint32_t)CL; ++r) {
+        st_remote_u32(map_to_cta(&ctl->sched_slot[ridx], r), slot);
+        mbar_arrive_remote(map_to_cta(&ctl->sched_full[ridx], r));
+      }
     }
+    __syncwarp();
     if (++ridx == NUM_SCHED) { ridx = 0; rphase ^= 1; }
   }
   // Consumers: next tile, false when the cluster is done.  WARP: called by all lanes of a warp
@@ -433,28 +437,38 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
-      if (CL == 1) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-      } else {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB96) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB48) : "memory");
+    // The whole warp walks the tiles (uniform control flow and coordinates, as in the MMA warp below); lane 0
+    // talks to the global tile counter, one elected lane issues the TMA loads.
+    {
+      if (lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        if (CL == 1) {
+          asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        } else {
+          asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB96) : "memory");
+          asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB48) : "memory");
+        }
       }
       uint32_t stage = 0, phase = 0;
       TileWalk<CL> walk(crank);
       uint32_t rt, I, J;
       bool masked;
       const bool leader = (CL == 1 || crank == 0);
-      uint32_t ahead = leader ? atomicAdd(a.counter, 1u) : 0u;  // the slot after the current one, fetched early
+      // the slot after the current one, fetched early
+      auto take_slot = [&]() {
+        uint32_t v = 0;
+        if (lane == 0) v = atomicAdd(a.counter, 1u);
+        return __shfl_sync(0xffffffffu, v, 0);
+      };
+      uint32_t ahead = leader ? take_slot() : 0u;
       while (true) {
         if (leader) {
           const uint32_t slot = ahead;
           if (slot >= a.n_slots) { walk.publish(ctl, SLOT_END); break; }
-          ahead = atomicAdd(a.counter, 1u);
+          ahead = take_slot();
           if (!walk.decode(a, slot, rt, I, J, masked)) continue;  // above the diagonal
           walk.publish(ctl, slot);
-        } else if (!walk.template next<false>(a, ctl, rt, I, J, masked)) {
+        } else if (!walk.template next<true>(a, ctl, rt, I, J, masked)) {
           break;
         }
         const int rowA = (int)I * TILE_ROWS;
@@ -463,19 +477,22 @@ k_pairs_tensor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait<32>(&ctl->empty[stage], phase ^ 1);
           unsigned char* sA = smem + stage * STAGE_BYTES;
           const int k0 = (int)(kc * K_CHUNK);
-          if (CL == 1) {
-            mbar_expect_tx(&ctl->full[stage], STAGE_BYTES);
-            tma_load_3d(sA, &mapA, &ctl->full[stage], k0, rowA, 0);
-            tma_load_3d(sA + A_STAGE_BYTES, &mapB, &ctl->full[stage], k0, rowB, 0);
-          } else {
-            if (crank == 0) mbar_expect_tx(&ctl->full[stage], 2 * STAGE_BYTES);
-            tma_load_3d_pair(sA, &mapA, &ctl->full[stage], k0, rowA, 0);
-            // this CTA's half of "b": digit 1 + crank in full (the N = 192 operand is [digit 1 | digit 2],
-            // one digit per CTA) and rows [48 crank, +48) of digit 0 (the N = 96 operand)
-            tma_load_3d_pair(sA + A_STAGE_BYTES, &mapB96, &ctl->full[stage], k0, rowB, 1 + (int)crank);
-            tma_load_3d_pair(sA + A_STAGE_BYTES + B_SLICE_BYTES, &mapB48, &ctl->full[stage], k0,
-                             rowB + (int)crank * (COL_TILE_ROWS / 2), 0);
+          if (elect_one()) {
+            if (CL == 1) {
+              mbar_expect_tx(&ctl->full[stage], STAGE_BYTES);
+              tma_load_3d(sA, &mapA, &ctl->full[stage], k0, rowA, 0);
+              tma_load_3d(sA + A_STAGE_BYTES, &mapB, &ctl->full[stage], k0, rowB, 0);
+            } else {
+              if (crank == 0) mbar_expect_tx(&ctl->full[stage], 2 * STAGE_BYTES);
+              tma_load_3d_pair(sA, &mapA, &ctl->full[stage], k0, rowA, 0);
+              // this CTA's half of "b": digit 1 + crank in full (the N = 192 operand is [digit 1 | digit 2],
+              // one digit per CTA) and rows [48 crank, +48) of digit 0 (the N = 96 operand)
+              tma_load_3d_pair(sA + A_STAGE_BYTES, &mapB96, &ctl->full[stage], k0, rowB, 1 + (int)crank);
+              tma_load_3d_pair(sA + A_STAGE_BYTES + B_SLICE_BYTES, &mapB48, &ctl->full[stage], k0,
+                               rowB + (int)crank * (COL_TILE_ROWS / 2), 0);
+            }
           }
+          __syncwarp();
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
       }
