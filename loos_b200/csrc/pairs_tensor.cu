@@ -22,13 +22,16 @@
 //            3 digits = 48 KB) and one for B (128 B x 96 x 3 = 36 KB), SWIZZLE_128B
 //   warp 1   TMEM allocator + MMA issuer: per 32-atom K step six tcgen05.mma
 //            (three with N = 192 spanning two adjacent classes, three with N = 96)
+//            (both control warps run their loops with all lanes, so that addresses, coordinates and
+//            descriptors are warp-uniform and sit in uniform registers; one elected lane issues)
 //   warps 2-3 idle (they complete the control warp group, see setmaxnreg below)
 //   warps 4-15 epilogue, one (lane quarter, 11/11/10-frame column group = 33/33/30 columns) each:
-//            tcgen05.ld -> exact integer combine in fp64 -> shuffle -> quartic coefficients
-//            (fp64) -> TMEM handed back to the MMA warp -> fp32 Newton + float-float
+//            tcgen05.ld -> class sums in 64-bit integers -> row exchange by shuffles -> quartic
+//            coefficients (fp64) -> TMEM handed back to the MMA warp -> fp32 Newton + float-float
 //            correction -> float32 tile in smem -> coalesced (and mirrored) stores.
 //            The fp64 part is serial with the next tile's MMAs on purpose: fp64 CUDA-core
 //            math and the tensor pipe contend on sm_100 (see the epilogue).
+// Default launch shape: CTA pairs (CL = 2 below), two row tiles against one column tile.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
