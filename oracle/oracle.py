@@ -288,6 +288,15 @@ class RefPDB:
     def hybrid36(self, field):
         return self.lib.ref_hybrid36(field.encode(), len(field))
 
+    def range_item(self, *args):
+        """RangeItem(a[, b[, c]]).generate() of src/index_range_parser.cpp:63-102 -> list, or None for 'Invalid range'."""
+        self.lib.ref_range_item.restype = C.c_long
+        a = int(args[0]); b = int(args[1]) if len(args) > 1 else 0; c = int(args[2]) if len(args) > 2 else 0
+        cap = 1 << 16
+        out = np.zeros(cap, np.uint32)
+        n = self.lib.ref_range_item(len(args), C.c_uint(a), C.c_uint(b), C.c_int(c), out.ctypes.data_as(C.POINTER(C.c_uint32)), cap)
+        return None if n < 0 else [int(v) for v in out[:min(n, cap)]]
+
     def multitraj(self, sizes, skip, stride):
         sizes = np.ascontiguousarray(sizes, dtype=np.uint32)
         cap = int(sizes.sum()) + 1

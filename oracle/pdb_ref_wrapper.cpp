@@ -7,6 +7,8 @@
 //   * src/utils.hpp:426-436       uniquifyVector
 //   * src/MultiTraj.hpp:97-105    MultiTrajectory::nframes(i);  src/MultiTraj.cpp:48-58 frameIndexToLocation
 //   * src/Selectors.cpp:37-132,156-164  BackboneSelector (its two name tables) and HydrogenSelector
+//   * src/index_range_parser.cpp:63-102 struct RangeItem: validate() and generate() of one range of the frame-range
+//                                 grammar (the Boost.Spirit grammar that builds RangeItems cannot be compiled here)
 // oracle/Makefile extracts the line ranges into a throw-away directory; nothing of them stays in the repo.
 // Below: shells for Atom / PDB / MultiTrajectory with just the members those functions touch (the real classes,
 // src/Atom.hpp, src/pdb.hpp, src/MultiTraj.hpp, stand on AtomicGroup / Trajectory / Boost), and a C interface.
@@ -109,6 +111,11 @@ class MultiTrajectory {
 
 }  // namespace loos
 
+namespace loos { namespace internal {
+using namespace std;
+#include "_ref/range_item.inc"           // struct RangeItem
+} }
+
 extern "C" {
 
 // One ATOM/HETATM line -> the fields parseAtomRecord stores.  ints: index? no -- id, resid; strs (each up to 8 chars,
@@ -154,6 +161,20 @@ int ref_hydrogen(const char* name, int has_mass, double mass) {
   loos::pAtom a(new loos::Atom);
   a->name(name); a->has_mass = has_mass != 0; a->mass_ = mass;
   return loos::HydrogenSelector()(a) ? 1 : 0;
+}
+
+// RangeItem(a) / RangeItem(a, b) / RangeItem(a, b, c) -> generate(): nargs picks the constructor.  Returns the number of
+// values (written up to cap), or -1 when generate() throws ("Invalid range").
+long ref_range_item(int nargs, unsigned a, unsigned b, int c, unsigned* out, long cap) {
+  try {
+    const loos::internal::RangeItem item = nargs == 1 ? loos::internal::RangeItem(a)
+                                           : nargs == 2 ? loos::internal::RangeItem(a, b) : loos::internal::RangeItem(a, b, c);
+    const std::vector<unsigned> v = item.generate();
+    for (long k = 0; k < (long)v.size() && k < cap; ++k) out[k] = v[(size_t)k];
+    return (long)v.size();
+  } catch (const loos::ParseError&) {
+    return -1;
+  }
 }
 
 // uniquifyVector<uint>: returns the number of unique values written to out

@@ -217,7 +217,12 @@ def pdb_golden():
            "backbone": [[int(R.backbone(r, n)) for n in names] for r in resnames],
            "hydrogen": [int(R.hydrogen(n)) for n in names],
            "hydrogen_mass": [[m, int(R.hydrogen("H1", m)), int(R.hydrogen("C1", m))] for m in (0.5, 1.008, 1.09, 1.1, 2.014, 4.0, 12.0)]}
-    out = {"selectors": sel, "atoms": [{"line": ln, "parsed": R.atom(ln)} for ln in PDB_LINES],
+    # RangeItem(a), (a, b), (a, b, c): what one range of the frame-range grammar generates (src/index_range_parser.cpp:63-102)
+    items = [[5], [0], [0, 9], [3, 49], [7, 7], [10, 0], [49, 49], [0, 20, 2], [0, 49, 3], [10, 0, -1], [10, 2, -3], [49, 10, -2],
+             [20, 49, -5], [15, 15, -1], [0, 0, 1], [0, 10, -1], [10, 0, 1], [4, 4, 0], [3, 9, 0], [0, 49, 7], [49, 0, -7], [5, 0, -5],
+             [6, 0, -4], [1, 0, -1], [0, 1, 1], [2, 8, 2], [8, 2, -2], [0, 3, 5], [3, 0, -5], [40, 49, 1], [49, 40, -1], [49, 10, -1]]
+    ranges = [{"args": a, "values": R.range_item(*a)} for a in items]
+    out = {"selectors": sel, "range_items": ranges, "atoms": [{"line": ln, "parsed": R.atom(ln)} for ln in PDB_LINES],
            "hybrid36": [{"field": f, "value": R.hybrid36(f)} for f in HYBRID36_FIELDS], "multitraj": mt, "uniquify": uq}
     with open(os.path.join(HERE, "pdb_ref.json"), "w") as fh:
         json.dump(out, fh, indent=0)

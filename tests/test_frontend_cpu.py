@@ -3,6 +3,7 @@ restatement of the reference semantics in oracle/frontend_oracle.py: selection
 language, PDB/hybrid-36, frame ranges, MultiTrajectory indexing, DCD decoding and
 the Matrix text format -- all integer/byte/text work, so the bar is bit-exact."""
 import ctypes as C
+import json
 import os
 import subprocess
 
@@ -130,6 +131,43 @@ def test_frame_range_errors(fe, spec):
     assert fe.lbfe_parse_range(spec.encode(), 49, out.ctypes.data_as(_u32p), 64) == -1
     with pytest.raises(ValueError):
         fo.parse_index_range(spec, 49)
+
+
+def test_range_items_against_the_reference(fe):
+    """tests/golden/pdb_ref.json["range_items"]: RangeItem::generate() of the reference itself (src/index_range_parser.cpp:63-102,
+    compiled in place: oracle/pdb_ref_wrapper.cpp) for one-, two- and three-argument items -- validation (a step against the
+    direction is 'Invalid range'), step 0, and the descending loop's unsigned wrap at 0.  The Boost.Spirit grammar that maps text
+    onto these items (:123-130) cannot be compiled here; its five alternatives are spelled out below, so the native parser and the
+    Python restatement are held to the reference's own generation semantics through them."""
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "pdb_ref.json")))["range_items"]
+    maxsize = 49
+    out = np.zeros(1 << 16, dtype=np.uint32)
+    assert len(g) >= 30
+    for item in g:
+        a = item["args"]
+        if len(a) == 1:
+            specs = ["%d" % a[0]]                                    # uint                         -> RangeItem(_1)
+        elif len(a) == 2:
+            specs = ["%d:%d" % (a[0], a[1])]                         # uint ':' endpoint            -> RangeItem(_1, _2)
+        else:
+            specs = ["%d:%d:%d" % (a[0], a[2], a[1])]                # uint ':' int ':' endpoint    -> RangeItem(_1, _3, _2)
+        if len(a) == 2 and a[1] == maxsize:
+            specs.append("%d:" % a[0])                               # the endpoint left out = maxsize
+        if len(a) == 3 and a[1] == maxsize:
+            specs.append("%d:%d:" % (a[0], a[2]))
+        if len(a) == 3 and a[0] == maxsize:
+            specs.append(":%d:%d" % (a[2], a[1]))                    # endpoint ':' int ':' uint    -> RangeItem(_1, _3, _2)
+            if a[2] == -1:
+                specs.append(":%d" % a[1])                           # endpoint ':' uint            -> RangeItem(_1, _2, -1)
+        for spec in specs:
+            n = fe.lbfe_parse_range(spec.encode(), maxsize, out.ctypes.data_as(_u32p), len(out))
+            if item["values"] is None:
+                assert n == -1, (spec, n)
+                with pytest.raises(ValueError):
+                    fo.parse_index_range(spec, maxsize)
+            else:
+                assert n == len(item["values"]) and list(out[:n]) == item["values"], (spec, list(out[:n])[:8], item["values"][:8])
+                assert list(fo.parse_index_range(spec, maxsize)) == item["values"], spec
 
 
 def test_assign_frames_sorted_vs_raw(fe):
